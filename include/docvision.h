@@ -1,0 +1,121 @@
+/*
+ * docvision.h -- C ABI of libdocvision.so, the B200 (sm_100a) engine that replaces the per-page
+ * vision hot path of CycloneBoy/pdf_table behind the reference's predictor API.
+ *
+ * Reference interface this ABI stands in for (paths relative to the reference repo,
+ * src/pdftable/model/ocr_pdf/):
+ *   - BaseInferTask.infer / infer_pytorch / build_*_infer_batch   base_infer_task.py:317-381
+ *     (the "trt" predictor slot, _prepare_trt_mode :143-144, is the slot a maintainer fills, see
+ *     INTEGRATION.md)
+ *   - OcrDetectionTask._run_model / _postprocess                  ocr_detection_task.py:89-141
+ *   - OcrRecognitionTask._run_model / _postprocess                ocr_recognition_task.py:81-136
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative dv_status; nothing throws across the ABI.
+ *     dv_last_error(h) returns a thread-unsafe, handle-owned message (h == NULL: creation errors).
+ *   - All data pointers are DEVICE pointers owned by the caller unless the name ends in `_host`.
+ *   - Work is enqueued asynchronously on the handle's stream (dv_set_stream); call dv_sync or
+ *     synchronise the stream yourself before reading results.
+ *   - A handle is bound to one device, is not thread-safe, and distinct handles are independent.
+ *   - No allocation happens on the hot path once a (batch, H, W) shape has been seen: activation
+ *     workspaces and TMA descriptors are planned on first use of a shape and reused.
+ */
+#ifndef DOCVISION_H_
+#define DOCVISION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dv_engine* dv_handle;
+
+enum dv_status {
+    DV_STATUS_OK = 0,
+    DV_STATUS_BAD_ARGUMENT = -1,
+    DV_STATUS_CUDA_ERROR = -2,
+    DV_STATUS_BAD_WEIGHTS = -3,
+    DV_STATUS_UNSUPPORTED = -4,
+    DV_STATUS_BAD_STATE = -5
+};
+
+/* activation / residual / store modes of dv_conv2d_nhwc_f16 (mirror csrc/igemm.cuh) */
+enum dv_act { DV_ACT_NONE = 0, DV_ACT_RELU = 1, DV_ACT_GELU = 2, DV_ACT_SIGMOID = 3, DV_ACT_HSWISH = 4 };
+
+int dv_version(void);
+const char* dv_last_error(dv_handle h);
+
+/*
+ * Create an engine handle.
+ *   model_kind : "post"          post-processing kernels only (no weights)
+ *                "dbnet_r18"     DBNet ResNet-18 text detector   (reference model/db_net/dbnet.py:715-728)
+ *                "convnext_vit"  ConvNextViT text-line recogniser (reference model/convnext_vit/
+ *                                modeling_convnext_vit.py:20-45)
+ *   weight_blob: HOST pointer to a blob written by pdf_table_b200.weights.pack_* (may be NULL for "post")
+ * Replaces: BaseInferTask._get_inference_model / DeployUtils.model_eval (base_infer_task.py:146-169,
+ * utils/deploy_utils.py:226-240).
+ */
+int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbytes, int device, dv_handle* out);
+int dv_destroy(dv_handle h);
+int dv_set_stream(dv_handle h, void* cuda_stream);
+int dv_sync(dv_handle h);
+/* number of kernels launched through this handle so far (bench.py "gpu_launches") */
+long long dv_launch_count(dv_handle h);
+/* algorithmic FLOPs of one forward at the last planned shape (0 if none) */
+double dv_model_flops(dv_handle h);
+
+/*
+ * DBNet forward: fp32 NCHW pages -> fp32 probability map [N,1,H,W].
+ * Replaces OcrDetectionTask._run_model (ocr_detection_task.py:89-124): predictor(image) -> pred[0].
+ * H and W must be multiples of 32 (DetResizeForTest guarantees it, db_pp/image_operators.py:304-305).
+ */
+int dv_dbnet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* prob_out);
+/*
+ * Same network fed with raw uint8 HWC pages; fuses PPOcrDetectionPreprocessor's channel flip +
+ * NormalizeImage + ToCHWImage (db_pp/processor_ocr_db_pp.py:124, image_operators.py:93-118):
+ *   x[c] = (u8[flip ? 2-c : c] * scale - mean[c]) / std[c]     (fp32, then fp16 NHWC)
+ * mean3/std3 are HOST pointers.
+ */
+int dv_dbnet_forward_u8(dv_handle h, const uint8_t* pages_hwc_u8, int n, int height, int width,
+                        const float* mean3_host, const float* std3_host, float scale, int flip,
+                        float* prob_out);
+
+/*
+ * CTC greedy decode of a [B,T,C] fp32 probability tensor.
+ * Replaces CTCLabelDecode.__call__ + BaseRecLabelDecode.decode(is_remove_duplicate=True)
+ * (ocr_rec_pp/rec_postprocess.py:175-191, 126-161).
+ *   out_ids  [B,T] int32 : kept class ids, left-packed, padded with -1
+ *   out_len  [B]   int32 : number of kept ids
+ *   out_conf [B]   fp32  : np.mean of the kept per-step maxima (0 when nothing is kept)
+ *   raw_ids / raw_max [B,T] : optional (may be NULL) per-step argmax / max before collapsing
+ * The id -> character lookup (self.character[text_id]) stays on the host.
+ */
+int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blank, int32_t* out_ids,
+                  int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max);
+
+/*
+ * Operator-level entry used by the parity tests of the tensor-core convolution kernel:
+ * NHWC fp16 convolution (stride 1 or 2, square kernel, zero padding) with fused bias, optional residual
+ * add and activation.  weight_packed: fp16 [cout][kh*kw*cin_pad] (see weights.pack_conv), bias: fp32
+ * padded to a multiple of 256 (or NULL), residual: NHWC fp16 [n,ho,wo,cout] or NULL.
+ * Replaces torch.nn.functional.conv2d as used by every nn.Conv2d on the path (e.g. dbnet.py:23-31).
+ */
+int dv_conv2d_nhwc_f16(dv_handle h, const void* in_nhwc_f16, int n, int height, int width, int cin,
+                       const void* weight_packed_f16, int cin_pad, const float* bias, int cout, int ksize,
+                       int stride, int pad, const void* residual_nhwc_f16, int act, void* out_nhwc_f16);
+/*
+ * Debug / parity aid: copy a named intermediate activation of the last forward (e.g. "c1", "layer2.0",
+ * "fuse", "b2" for dbnet_r18) as fp32 NCHW.  dims4_host (HOST, may be NULL) receives {N,C,H,W};
+ * out_nchw_f32 (DEVICE) may be NULL to query the shape only.  No reference counterpart.
+ */
+int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int* dims4_host);
+/* layout helpers for the tests */
+int dv_nchw_f32_to_nhwc_f16(dv_handle h, const float* in, int n, int c, int height, int width, void* out);
+int dv_nhwc_f16_to_nchw_f32(dv_handle h, const void* in, int n, int c, int height, int width, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOCVISION_H_ */

@@ -1,0 +1,65 @@
+"""ctypes binding of libdocvision.so (include/docvision.h).  No fallback: if the CUDA library is missing
+or no B200 is visible, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdocvision.so")
+
+_lib = None
+
+
+class DocVisionError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); keep in sync with include/docvision.h (tests/test_abi.py checks the header)
+SIGNATURES = {
+    "dv_version": (C.c_int, []),
+    "dv_last_error": (C.c_char_p, [C.c_void_p]),
+    "dv_create": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "dv_destroy": (C.c_int, [C.c_void_p]),
+    "dv_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dv_sync": (C.c_int, [C.c_void_p]),
+    "dv_launch_count": (C.c_longlong, [C.c_void_p]),
+    "dv_model_flops": (C.c_double, [C.c_void_p]),
+    "dv_dbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dv_dbnet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]),
+    "dv_ctc_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dv_debug_get_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "dv_conv2d_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "dv_nchw_f32_to_nhwc_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dv_nhwc_f16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DocVisionError(
+            f"{LIB_PATH} not found: build it with `python -m pdf_table_b200.build` "
+            "(there is no CPU / PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None) -> str:
+    msg = load().dv_last_error(handle)
+    return msg.decode(errors="replace") if msg else ""
+
+
+def check(rc: int, handle=None, what: str = "") -> None:
+    if rc != 0:
+        raise DocVisionError(f"{what or 'libdocvision'} failed (rc={rc}): {last_error(handle)}")

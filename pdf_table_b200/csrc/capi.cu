@@ -1,0 +1,280 @@
+// C ABI (include/docvision.h) over the engine: handle lifetime, weight blob loading, entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/docvision.h"
+#include "engine.h"
+
+namespace dv {
+
+static thread_local std::string g_err;
+
+void set_global_err(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int set_err(Engine* e, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    g_err = buf;
+    return code;
+}
+
+int Engine::dalloc(void** p, size_t bytes, bool zero) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t st = cudaMalloc(p, bytes);
+    if (st != cudaSuccess) return set_err(this, DV_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(st));
+    owned.push_back(*p);
+    if (zero) {
+        st = cudaMemsetAsync(*p, 0, bytes, stream);
+        if (st != cudaSuccess) return set_err(this, DV_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(st));
+    }
+    return 0;
+}
+
+const BlobTensor* Engine::find(const std::string& name) {
+    auto it = weights.find(name);
+    return it == weights.end() ? nullptr : &it->second;
+}
+
+// ---- blob format (pdf_table_b200/weights.py): header, entry table, 256-byte aligned payload
+struct BlobHeader {
+    char magic[8];  // "DVWBLOB1"
+    uint32_t n_tensors;
+    uint32_t reserved;
+    uint64_t data_offset;
+    uint64_t data_bytes;
+};
+struct BlobEntry {
+    char name[96];
+    uint32_t dtype;
+    uint32_t ndim;
+    uint32_t dims[4];
+    uint64_t offset;  // relative to data_offset
+    uint64_t nbytes;
+};
+
+static int load_blob(Engine* e, const void* blob, size_t nbytes) {
+    if (nbytes < sizeof(BlobHeader)) return set_err(e, DV_ERR_WEIGHTS, "weight blob too small");
+    BlobHeader h;
+    memcpy(&h, blob, sizeof(h));
+    if (memcmp(h.magic, "DVWBLOB1", 8) != 0) return set_err(e, DV_ERR_WEIGHTS, "bad weight blob magic");
+    const size_t table_end = sizeof(BlobHeader) + static_cast<size_t>(h.n_tensors) * sizeof(BlobEntry);
+    if (table_end > nbytes || h.data_offset < table_end || h.data_offset + h.data_bytes > nbytes)
+        return set_err(e, DV_ERR_WEIGHTS, "weight blob truncated");
+    DV_CUDA(e, cudaMalloc(&e->weight_base, h.data_bytes ? h.data_bytes : 16));
+    DV_CUDA(e, cudaMemcpy(e->weight_base, static_cast<const char*>(blob) + h.data_offset, h.data_bytes,
+                          cudaMemcpyHostToDevice));
+    const char* tab = static_cast<const char*>(blob) + sizeof(BlobHeader);
+    for (uint32_t i = 0; i < h.n_tensors; ++i) {
+        BlobEntry en;
+        memcpy(&en, tab + static_cast<size_t>(i) * sizeof(BlobEntry), sizeof(en));
+        en.name[95] = 0;
+        if (en.offset + en.nbytes > h.data_bytes || (en.offset % 256) != 0)
+            return set_err(e, DV_ERR_WEIGHTS, "weight blob entry '%s' out of range", en.name);
+        BlobTensor t;
+        t.dptr = static_cast<char*>(e->weight_base) + en.offset;
+        t.dtype = en.dtype;
+        t.ndim = en.ndim;
+        memcpy(t.dims, en.dims, sizeof(t.dims));
+        t.nbytes = en.nbytes;
+        e->weights[en.name] = t;
+    }
+    return 0;
+}
+
+}  // namespace dv
+
+using namespace dv;
+
+struct dv_engine : public dv::Engine {};
+
+extern "C" {
+
+int dv_version(void) { return 100; }
+
+const char* dv_last_error(dv_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbytes, int device, dv_handle* out) {
+    if (!model_kind || !out) {
+        set_global_err("dv_create: null argument");
+        return DV_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0) {
+        set_global_err("dv_create: no CUDA device (%s) -- this engine has no CPU fallback",
+                       st != cudaSuccess ? cudaGetErrorString(st) : "device count 0");
+        return DV_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_global_err("dv_create: device %d out of range (%d devices)", device, ndev);
+        return DV_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_global_err("dv_create: cannot select device %d", device);
+        return DV_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        set_global_err("dv_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                       prop.minor);
+        return DV_ERR_UNSUPPORTED;
+    }
+    dv_engine* e = new dv_engine();
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    e->kind = model_kind;
+    int rc = 0;
+    if (weight_blob_host && nbytes) rc = load_blob(e, weight_blob_host, nbytes);
+    if (rc == 0) {
+        if (e->kind == "post") {
+        } else if (e->kind == "dbnet_r18") {
+            rc = dbnet_create(e);
+        } else {
+            rc = set_err(e, DV_ERR_UNSUPPORTED, "dv_create: unknown model kind '%s'", model_kind);
+        }
+    }
+    if (rc != 0) {
+        set_global_err("%s", e->err.c_str());
+        dv_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return 0;
+}
+
+int dv_destroy(dv_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->model.reset();
+    for (void* p : h->owned) cudaFree(p);
+    if (h->weight_base) cudaFree(h->weight_base);
+    delete h;
+    return 0;
+}
+
+int dv_set_stream(dv_handle h, void* cuda_stream) {
+    if (!h) return DV_ERR_ARG;
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return 0;
+}
+
+int dv_sync(dv_handle h) {
+    if (!h) return DV_ERR_ARG;
+    DV_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+long long dv_launch_count(dv_handle h) { return h ? h->launches : 0; }
+
+double dv_model_flops(dv_handle h) {
+    if (!h) return 0.0;
+    if (h->kind == "dbnet_r18") return dbnet_flops(h);
+    return 0.0;
+}
+
+int dv_dbnet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* prob_out) {
+    if (!h) return DV_ERR_ARG;
+    if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward: null input");
+    cudaSetDevice(h->device);
+    return dbnet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0.f, 0, n, height, width, prob_out);
+}
+
+int dv_dbnet_forward_u8(dv_handle h, const uint8_t* pages_hwc_u8, int n, int height, int width,
+                        const float* mean3_host, const float* std3_host, float scale, int flip, float* prob_out) {
+    if (!h) return DV_ERR_ARG;
+    if (!pages_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward_u8: null input");
+    cudaSetDevice(h->device);
+    return dbnet_forward(h, nullptr, pages_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, prob_out);
+}
+
+int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int* dims4_host) {
+    if (!h || !name) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
+    return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
+}
+
+int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blank, int32_t* out_ids,
+                  int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return ctc_greedy(h, probs, b, t, c, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
+}
+
+int dv_conv2d_nhwc_f16(dv_handle h, const void* in_nhwc_f16, int n, int height, int width, int cin,
+                       const void* weight_packed_f16, int cin_pad, const float* bias, int cout, int ksize,
+                       int stride, int pad, const void* residual_nhwc_f16, int act, void* out_nhwc_f16) {
+    if (!h) return DV_ERR_ARG;
+    if (!in_nhwc_f16 || !weight_packed_f16 || !out_nhwc_f16) return set_err(h, DV_ERR_ARG, "dv_conv2d: null pointer");
+    cudaSetDevice(h->device);
+    Tensor in;
+    in.p = const_cast<__half*>(reinterpret_cast<const __half*>(in_nhwc_f16));
+    in.N = n;
+    in.H = height;
+    in.W = width;
+    in.C = cin;
+    const int Ho = (height + 2 * pad - ksize) / stride + 1;
+    const int Wo = (width + 2 * pad - ksize) / stride + 1;
+    ConvSpec cs;
+    cs.KH = cs.KW = ksize;
+    cs.stride = stride;
+    cs.pad = pad;
+    cs.Cin = cin;
+    cs.Cout = cout;
+    cs.Cin_pad = cin_pad;
+    cs.BK = (cin_pad % 64 == 0) ? 64 : (cin_pad % 32 == 0) ? 32 : 16;
+    cs.w = reinterpret_cast<const __half*>(weight_packed_f16);
+    cs.bias = bias;
+    EpiSpec es;
+    es.out = out_nhwc_f16;
+    es.out_ld = cout;
+    es.act = act;
+    if (residual_nhwc_f16) {
+        es.res = reinterpret_cast<const __half*>(residual_nhwc_f16);
+        es.res_mode = RES_SAME;
+        es.res_ld = cout;
+    }
+    ConvPlan plan;
+    const size_t owned_before = h->owned.size();
+    int rc = plan_conv(h, in, cs, es, Ho, Wo, &plan, "dv_conv2d");
+    if (rc == 0) rc = launch_conv(h, plan);
+    // one-shot plan: release its delta table once the kernel has run
+    cudaError_t sync_st = cudaStreamSynchronize(h->stream);
+    if (rc == 0 && sync_st != cudaSuccess) rc = set_err(h, DV_ERR_CUDA, "dv_conv2d: %s", cudaGetErrorString(sync_st));
+    while (h->owned.size() > owned_before) {
+        cudaFree(h->owned.back());
+        h->owned.pop_back();
+    }
+    if (rc == 0) {
+        cudaError_t st = cudaGetLastError();
+        if (st != cudaSuccess) rc = set_err(h, DV_ERR_CUDA, "dv_conv2d: %s", cudaGetErrorString(st));
+    }
+    return rc;
+}
+
+int dv_nchw_f32_to_nhwc_f16(dv_handle h, const float* in, int n, int c, int height, int width, void* out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return op_nchw_f32_to_nhwc_f16(h, in, n, c, height, width, reinterpret_cast<__half*>(out));
+}
+int dv_nhwc_f16_to_nchw_f32(dv_handle h, const void* in, int n, int c, int height, int width, float* out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return op_nhwc_f16_to_nchw_f32(h, reinterpret_cast<const __half*>(in), n, c, height, width, out);
+}
+
+}  // extern "C"

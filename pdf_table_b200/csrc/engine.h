@@ -1,0 +1,135 @@
+// Internal (non-ABI) declarations shared by the engine's translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "igemm_params.h"
+
+namespace dv {
+
+// ---- error plumbing: every internal function returns 0 or a negative dv error code and leaves a
+// message in Engine::err (never throws across the C ABI).
+enum : int {
+    DV_OK = 0,
+    DV_ERR_ARG = -1,
+    DV_ERR_CUDA = -2,
+    DV_ERR_WEIGHTS = -3,
+    DV_ERR_UNSUPPORTED = -4,
+    DV_ERR_STATE = -5,
+};
+
+struct Engine;
+int set_err(Engine* e, int code, const char* fmt, ...);
+void set_global_err(const char* fmt, ...);
+
+#define DV_CUDA(e, call)                                                                         \
+    do {                                                                                         \
+        cudaError_t _st = (call);                                                                \
+        if (_st != cudaSuccess)                                                                  \
+            return set_err((e), DV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                           __FILE__, __LINE__);                                                  \
+    } while (0)
+#define DV_TRY(call)              \
+    do {                          \
+        int _rc = (call);         \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+// ---- weight blob (format written by pdf_table_b200/weights.py)
+struct BlobTensor {
+    void* dptr = nullptr;  // device pointer
+    uint32_t dtype = 0;    // 0 f32, 1 f16, 2 i32
+    uint32_t ndim = 0;
+    uint32_t dims[4] = {0, 0, 0, 0};
+    uint64_t nbytes = 0;
+};
+
+// NHWC fp16 activation tensor (dense: C channels per pixel)
+struct Tensor {
+    __half* p = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+    size_t elems() const { return static_cast<size_t>(N) * H * W * C; }
+};
+
+struct ConvSpec {
+    int KH = 1, KW = 1, stride = 1, pad = 0;
+    int Cin = 0, Cout = 0;
+    int BK = 64, Cin_pad = 0;  // packing of the weight matrix: [Cout][KH*KW*Cin_pad]
+    const __half* w = nullptr;
+    const float* bias = nullptr;  // padded to a multiple of 256 floats, or nullptr
+    bool stem = false;            // 7x7 s2 on the padded 4-channel image (A_STEM)
+    bool flat = false;            // force A_FLAT (1x1 stride 1 / linear)
+};
+
+struct EpiSpec {
+    const __half* res = nullptr;
+    int res_mode = RES_NONE, res_ld = 0;
+    int act = ACT_NONE;
+    int out_mode = OUT_NHWC;
+    void* out = nullptr;
+    int out_ld = 0, out_coff = 0, rep = 1, out_f32 = 0;
+};
+
+struct ConvPlan {
+    IGemmParams prm;
+    int grid = 0;
+    size_t smem = 0;
+    double flops = 0;  // algorithmic 2*M*K*N (unpadded)
+    std::string name;
+};
+
+struct Model {
+    virtual ~Model() {}
+};
+
+struct Engine {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string kind;
+    std::string err;
+    std::map<std::string, BlobTensor> weights;
+    void* weight_base = nullptr;
+    std::vector<void*> owned;  // device allocations freed at destroy
+    std::unique_ptr<Model> model;
+    long long launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+
+    int dalloc(void** p, size_t bytes, bool zero = false);
+    const BlobTensor* find(const std::string& name);
+};
+
+// igemm_host.cu
+int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
+              ConvPlan* plan, const char* name);
+int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
+                ConvPlan* plan, const char* name);
+int launch_conv(Engine* e, const ConvPlan& plan);
+
+// ops.cu (simple HBM-bound kernels)
+int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);
+int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
+                  float scale, int flip, __half* out);
+int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out);
+int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, float bias, float* out);
+int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out);
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out);
+
+// dbnet.cu
+int dbnet_create(Engine* e);
+int dbnet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3,
+                  const float* std3, float scale, int flip, int N, int H, int W, float* prob_out);
+double dbnet_flops(Engine* e);
+int dbnet_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4);
+
+// ctc.cu
+int ctc_greedy(Engine* e, const float* probs, int B, int T, int C, int blank, int32_t* out_ids,
+               int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max);
+
+}  // namespace dv

@@ -1,0 +1,298 @@
+// conv_igemm_tcgen05 -- the engine's one tensor-core kernel.
+//
+// Implicit-GEMM convolution / linear layer for NHWC fp16 activations:
+//     D[m, n] = sum_k A[m, k] * W[n, k]        m = output pixel, n = output channel,
+//                                              k = (tap r,s ; input channel c)
+// * A tiles (128 output pixels x BK input channels of one filter tap) are fetched by TMA straight from
+//   the NHWC activation tensor: the 128 pixels are a TH x TW patch of one image, so the tile of tap
+//   (r,s) is the same box shifted by (r-pad, s-pad); out-of-image taps are zero-filled by the TMA
+//   unit, i.e. padding costs nothing and no im2col buffer ever exists in HBM.
+// * W tiles (BLOCK_N x BK, K-major) are fetched by TMA from the packed weight matrix.
+// * tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) accumulates in TMEM (fp32), issued by one thread.
+// * The epilogue (4 warps) reads TMEM with tcgen05.ld and fuses bias(+folded BN), residual add
+//   (same resolution or nearest-2x-upsampled), activation, and the store pattern (plain NHWC slice,
+//   s x s nearest replication into a concat slice, or 2x2 pixel-shuffle for ConvTranspose 2x2 s2).
+// * Persistent CTAs (grid = min(tiles, #SM)), a num_stages-deep smem ring between TMA and MMA, and a
+//   2-deep TMEM accumulator ring between MMA and epilogue so the epilogue of tile i overlaps the
+//   main loop of tile i+1.
+#pragma once
+#include "igemm_params.h"
+#include "ptx.cuh"
+
+namespace dv {
+
+static constexpr int kIGemmThreads = 192;
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(x, 0.f);
+        case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+        case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+        case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        default: return x;
+    }
+}
+
+__global__ void __launch_bounds__(kIGemmThreads, 1)
+conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t row_bytes = 2u * p.BK;
+    const uint32_t a_bytes = 128u * row_bytes;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.BLOCK_N) * row_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const int num_stages = p.num_stages;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < num_stages; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&tfull_bar[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 4);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&p.tmA);
+        ptx::prefetch_tmap(&p.tmB);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&tmem_base_smem), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int tiles_per_img = p.tiles_x * p.tiles_y;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles;
+                const int n_tile = tile - m_tile * p.n_tiles;
+                int img = 0, y0 = 0, x0 = 0;
+                if (p.mode != A_FLAT) {
+                    img = m_tile / tiles_per_img;
+                    const int t = m_tile - img * tiles_per_img;
+                    const int ty = t / p.tiles_x;
+                    y0 = ty * p.TH;
+                    x0 = (t - ty * p.tiles_x) * p.TW;
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+                    ptx::mbar_expect_tx(fb, stage_bytes);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = sa + a_bytes;
+                    const int4 d = __ldg(&p.kb_delta[kb]);
+                    switch (p.mode) {
+                        case A_FLAT: ptx::tma_load_5d(sa, &p.tmA, fb, d.x, m_tile * 128, 0, 0, 0); break;
+                        case A_PATCH: ptx::tma_load_5d(sa, &p.tmA, fb, d.x, x0 + d.y, y0 + d.z, img, 0); break;
+                        case A_PATCH_S2:
+                            ptx::tma_load_5d(sa, &p.tmA, fb, d.x, x0 + d.y, d.z, y0 + d.w, img);
+                            break;
+                        default:  // A_STEM: dims {32, Wo, 7, Ho, N}
+                            ptx::tma_load_5d(sa, &p.tmA, fb, 0, x0, d.z, y0, img);
+                            break;
+                    }
+                    ptx::tma_load_2d(sb, &p.tmB, fb, kb * p.BK, n_tile * p.BLOCK_N);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
+            const int k_steps = p.BK >> 4;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint64_t adesc = ptx::make_kmajor_desc(sa, row_bytes);
+                    const uint64_t bdesc = ptx::make_kmajor_desc(sa + a_bytes, row_bytes);
+                    for (int k = 0; k < k_steps; ++k) {
+                        // advance 16 fp16 = 32 B along K inside the swizzle span: +2 in the (addr>>4) field
+                        ptx::umma_f16_ss(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));  // frees the smem slot when MMAs retire
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int tiles_per_img = p.tiles_x * p.tiles_y;
+        const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.out_coff & 7) == 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles;
+            const int n_tile = tile - m_tile * p.n_tiles;
+            // ---- which output pixel does this thread own?
+            int img, y, x;
+            bool valid;
+            if (p.mode == A_FLAT) {
+                const int m = m_tile * 128 + row;
+                valid = m < p.M;
+                const int hw = p.Ho * p.Wo;
+                img = m / hw;
+                const int r = m - img * hw;
+                y = r / p.Wo;
+                x = r - y * p.Wo;
+            } else {
+                img = m_tile / tiles_per_img;
+                const int t = m_tile - img * tiles_per_img;
+                const int ty = t / p.tiles_x;
+                const int tx = t - ty * p.tiles_x;
+                const int ly = row / p.TW;
+                y = ty * p.TH + ly;
+                x = tx * p.TW + (row - ly * p.TW);
+                valid = (y < p.Ho) && (x < p.Wo);
+            }
+            const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
+            long long res_pix = pix;
+            if (p.res_mode == RES_UP2)
+                res_pix = (static_cast<long long>(img) * (p.Ho >> 1) + (y >> 1)) * (p.Wo >> 1) + (x >> 1);
+
+            ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>(acc) * 256u;
+            for (int c = 0; c < p.BLOCK_N; c += 32) {
+                const int col0 = n_tile * p.BLOCK_N + c;
+                if (col0 >= p.Cout) break;  // warp-uniform
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
+                ptx::tmem_ld_wait();
+                if (!valid) continue;
+                const int ncol = min(32, p.Cout - col0);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+                }
+                if (p.res_mode != RES_NONE) {
+                    const __half* rp = p.res + res_pix * p.res_ld + col0;
+                    if (ncol == 32 && ((p.res_ld & 7) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t2 = __half22float2(h2[e]);
+                                f[j * 8 + e * 2] += t2.x;
+                                f[j * 8 + e * 2 + 1] += t2.y;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncol) f[j] += __half2float(rp[j]);
+                    }
+                }
+                if (p.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+                }
+                // ---- store
+                int reps = 1;
+                long long opix0 = pix;
+                int ocol = col0;
+                int orow_stride = 0;  // pixels per output row (for replication)
+                if (p.out_mode == OUT_REPL) {
+                    reps = p.rep;
+                    orow_stride = p.Wo * p.rep;
+                    opix0 = (static_cast<long long>(img) * p.Ho * p.rep + static_cast<long long>(y) * p.rep) *
+                                orow_stride + static_cast<long long>(x) * p.rep;
+                } else if (p.out_mode == OUT_SHUF2) {
+                    const int cq = p.Cout >> 2;
+                    const int quad = col0 / cq;
+                    ocol = col0 - quad * cq;
+                    opix0 = (static_cast<long long>(img) * p.Ho * 2 + 2 * y + (quad >> 1)) * (p.Wo * 2) +
+                            2 * x + (quad & 1);
+                }
+                for (int dy = 0; dy < reps; ++dy) {
+                    for (int dx = 0; dx < reps; ++dx) {
+                        const long long opix = opix0 + static_cast<long long>(dy) * orow_stride + dx;
+                        const long long off = opix * p.out_ld + p.out_coff + ocol;
+                        if (p.out_f32) {
+                            float* op = reinterpret_cast<float*>(p.out) + off;
+                            if (ncol == 32 && ((p.out_ld & 3) == 0) && ((p.out_coff & 3) == 0)) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    reinterpret_cast<float4*>(op)[j] =
+                                        make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < ncol) op[j] = f[j];
+                            }
+                        } else {
+                            __half* op = reinterpret_cast<__half*>(p.out) + off;
+                            if (ncol == 32 && vec_ok) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    uint4 u;
+                                    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        h2[e] = __floats2half2_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                                    reinterpret_cast<uint4*>(op)[j] = u;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < ncol) op[j] = __float2half_rn(f[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[acc]));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace dv

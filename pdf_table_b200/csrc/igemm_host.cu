@@ -1,0 +1,266 @@
+// Host side of conv_igemm_tcgen05: TMA tensor-map construction, tile planning, launch.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "engine.h"
+#include "igemm.cuh"
+
+namespace dv {
+
+// cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so the library
+// does not link against libcuda (which is absent on the CPU-only build box).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+static int encode_map(Engine* e, CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int row_bytes,
+                      const char* what) {
+    auto fn = get_encode_fn();
+    if (!fn) return set_err(e, DV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = row_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                    gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        return set_err(e, DV_ERR_CUDA,
+                       "cuTensorMapEncodeTiled(%s) failed rc=%d dims={%llu,%llu,%llu,%llu,%llu} "
+                       "strides={%llu,%llu,%llu,%llu} box={%u,%u,%u,%u,%u} rank=%d base=%p",
+                       what, (int)r, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+                       (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+                       (unsigned long long)(rank > 4 ? gdim[4] : 0), (unsigned long long)gstr[0],
+                       (unsigned long long)(rank > 2 ? gstr[1] : 0), (unsigned long long)(rank > 3 ? gstr[2] : 0),
+                       (unsigned long long)(rank > 4 ? gstr[3] : 0), bdim[0], rank > 1 ? bdim[1] : 0,
+                       rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0, rank, base);
+    }
+    return 0;
+}
+
+static void choose_patch(int Ho, int Wo, int* TH, int* TW) {
+    long long best = -1;
+    int bth = 8, btw = 16;
+    for (int th = 1; th <= 128; th *= 2) {
+        const int tw = 128 / th;
+        const long long tiles = static_cast<long long>((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+        // prefer fewer tiles; tie-break towards squarer patches (less halo re-read through L2)
+        const long long cost = tiles * 1000 + (th > tw ? th / tw : tw / th);
+        if (best < 0 || cost < best) {
+            best = cost;
+            bth = th;
+            btw = tw;
+        }
+    }
+    *TH = bth;
+    *TW = btw;
+}
+
+static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiSpec& es, int num_kb,
+                       const std::vector<int4>& deltas, const char* name) {
+    IGemmParams& p = plan->prm;
+    p.num_kb = num_kb;
+    p.BK = cs.BK;
+    p.Cout = cs.Cout;
+    int block_n;
+    if (cs.Cout <= 256) {
+        block_n = (cs.Cout + 31) / 32 * 32;
+    } else {
+        block_n = (cs.Cout % 256 == 0 || cs.Cout > 1024) ? 256 : 128;
+    }
+    p.BLOCK_N = block_n;
+    p.n_tiles = (cs.Cout + block_n - 1) / block_n;
+    const int row_bytes = 2 * cs.BK;
+    const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
+    int stages = static_cast<int>((220 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
+    p.num_stages = stages;
+    plan->smem = stages * stage_bytes + 1024;
+    p.bias = cs.bias;
+    p.res = es.res;
+    p.res_mode = es.res_mode;
+    p.res_ld = es.res_ld;
+    p.act = es.act;
+    p.out_mode = es.out_mode;
+    p.out = es.out;
+    p.out_ld = es.out_ld;
+    p.out_coff = es.out_coff;
+    p.rep = es.rep;
+    p.out_f32 = es.out_f32;
+    if (es.out_mode == OUT_SHUF2 && (((cs.Cout >> 2) % 32) != 0 || (cs.Cout & 3)))
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: OUT_SHUF2 needs Cout/4 %% 32 == 0", name);
+    // weight map: [Cout][Ktot] K-major
+    const uint64_t ktot = static_cast<uint64_t>(num_kb) * cs.BK;
+    {
+        uint64_t dims[2] = {ktot, static_cast<uint64_t>(cs.Cout)};
+        uint64_t str[1] = {ktot * 2};
+        uint32_t box[2] = {static_cast<uint32_t>(cs.BK), static_cast<uint32_t>(block_n)};
+        DV_TRY(encode_map(e, &p.tmB, cs.w, 2, dims, str, box, row_bytes, name));
+    }
+    void* dtab = nullptr;
+    DV_TRY(e->dalloc(&dtab, deltas.size() * sizeof(int4)));
+    DV_CUDA(e, cudaMemcpyAsync(dtab, deltas.data(), deltas.size() * sizeof(int4), cudaMemcpyHostToDevice,
+                               e->stream));
+    DV_CUDA(e, cudaStreamSynchronize(e->stream));
+    p.kb_delta = reinterpret_cast<const int4*>(dtab);
+    const int total = p.m_tiles * p.n_tiles;
+    plan->grid = total < e->num_sms ? total : e->num_sms;
+    plan->name = name;
+    return 0;
+}
+
+int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
+                ConvPlan* plan, const char* name) {
+    memset(&plan->prm, 0, sizeof(plan->prm));
+    IGemmParams& p = plan->prm;
+    if (K % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: K %% 8 != 0", name);
+    p.mode = A_FLAT;
+    p.M = M;
+    p.Nimg = 1;
+    p.Ho = 1;
+    p.Wo = M;
+    p.TH = 1;
+    p.TW = 128;
+    p.tiles_x = p.tiles_y = 1;
+    p.m_tiles = (M + 127) / 128;
+    const int num_kb = (K + cs.BK - 1) / cs.BK;
+    if (cs.Cin_pad != num_kb * cs.BK)
+        return set_err(e, DV_ERR_WEIGHTS, "%s: weight packing Cin_pad=%d != %d", name, cs.Cin_pad, num_kb * cs.BK);
+    {
+        uint64_t dims[5] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 1, 1, 1};
+        const uint64_t rs = static_cast<uint64_t>(K) * 2;
+        uint64_t str[4] = {rs, rs * M, rs * M, rs * M};
+        uint32_t box[5] = {static_cast<uint32_t>(cs.BK), 128, 1, 1, 1};
+        DV_TRY(encode_map(e, &p.tmA, A, 5, dims, str, box, 2 * cs.BK, name));
+    }
+    std::vector<int4> deltas(num_kb);
+    for (int kb = 0; kb < num_kb; ++kb) deltas[kb] = make_int4(kb * cs.BK, 0, 0, 0);
+    plan->flops = 2.0 * M * K * cs.Cout;
+    return finish_plan(e, plan, cs, es, num_kb, deltas, name);
+}
+
+int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
+              ConvPlan* plan, const char* name) {
+    if (cs.flat || (cs.KH == 1 && cs.KW == 1 && cs.stride == 1 && cs.pad == 0 && !cs.stem)) {
+        int rc = plan_linear(e, in.p, in.N * in.H * in.W, in.C, cs, es, plan, name);
+        if (rc == 0) {
+            plan->prm.Nimg = in.N;
+            plan->prm.Ho = in.H;
+            plan->prm.Wo = in.W;
+        }
+        return rc;
+    }
+    memset(&plan->prm, 0, sizeof(plan->prm));
+    IGemmParams& p = plan->prm;
+    p.Nimg = in.N;
+    p.Ho = Ho;
+    p.Wo = Wo;
+    choose_patch(Ho, Wo, &p.TH, &p.TW);
+    p.tiles_y = (Ho + p.TH - 1) / p.TH;
+    p.tiles_x = (Wo + p.TW - 1) / p.TW;
+    p.m_tiles = in.N * p.tiles_x * p.tiles_y;
+    const int row_bytes = 2 * cs.BK;
+    std::vector<int4> deltas;
+    int num_kb = 0;
+    if (cs.stem) {
+        // `in` is the padded image [N, Hp, Wp, 4]; windows of 8 pixels x 4 ch = 32 fp16 per tap row.
+        if (cs.BK != 32 || in.C != 4 || cs.KH != 7)
+            return set_err(e, DV_ERR_UNSUPPORTED, "%s: stem expects BK=32, C=4, 7x7", name);
+        p.mode = A_STEM;
+        const uint64_t pitch = static_cast<uint64_t>(in.W) * 4 * 2;
+        if (in.W < 2 * Wo + 6 || in.H < 2 * Ho + 5 || (pitch % 16))
+            return set_err(e, DV_ERR_ARG, "%s: padded stem input too small", name);
+        uint64_t dims[5] = {32, static_cast<uint64_t>(Wo), 7, static_cast<uint64_t>(Ho),
+                            static_cast<uint64_t>(in.N)};
+        uint64_t str[4] = {16, pitch, 2 * pitch, pitch * in.H};
+        uint32_t box[5] = {32, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), 1};
+        DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
+        num_kb = 7;
+        for (int r = 0; r < 7; ++r) deltas.push_back(make_int4(0, 0, r, 0));
+        plan->flops = 2.0 * in.N * Ho * Wo * 147.0 * cs.Cout;
+    } else {
+        if (in.C != cs.Cin) return set_err(e, DV_ERR_ARG, "%s: Cin mismatch %d vs %d", name, in.C, cs.Cin);
+        if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: Cin %% 8 != 0", name);
+        const int cin_blocks = cs.Cin_pad / cs.BK;
+        if (cin_blocks * cs.BK != cs.Cin_pad || cs.Cin_pad < cs.Cin)
+            return set_err(e, DV_ERR_WEIGHTS, "%s: bad Cin_pad", name);
+        const uint64_t cb = static_cast<uint64_t>(in.C) * 2;
+        if (cs.stride == 1) {
+            p.mode = A_PATCH;
+            uint64_t dims[5] = {static_cast<uint64_t>(in.C), static_cast<uint64_t>(in.W),
+                                static_cast<uint64_t>(in.H), static_cast<uint64_t>(in.N), 1};
+            uint64_t str[4] = {cb, cb * in.W, cb * in.W * in.H, cb * in.W * in.H * in.N};
+            uint32_t box[5] = {static_cast<uint32_t>(cs.BK), static_cast<uint32_t>(p.TW),
+                               static_cast<uint32_t>(p.TH), 1, 1};
+            DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
+            for (int r = 0; r < cs.KH; ++r)
+                for (int s = 0; s < cs.KW; ++s)
+                    for (int c = 0; c < cin_blocks; ++c)
+                        deltas.push_back(make_int4(c * cs.BK, s - cs.pad, r - cs.pad, 0));
+        } else if (cs.stride == 2) {
+            if ((in.H & 1) || (in.W & 1) || (cs.Cin % cs.BK))
+                return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride-2 needs even H,W and BK | Cin", name);
+            p.mode = A_PATCH_S2;
+            uint64_t dims[5] = {static_cast<uint64_t>(2 * in.C), static_cast<uint64_t>(in.W / 2), 2,
+                                static_cast<uint64_t>(in.H / 2), static_cast<uint64_t>(in.N)};
+            uint64_t str[4] = {2 * cb, cb * in.W, 2 * cb * in.W, cb * in.W * in.H};
+            uint32_t box[5] = {static_cast<uint32_t>(cs.BK), static_cast<uint32_t>(p.TW), 1,
+                               static_cast<uint32_t>(p.TH), 1};
+            DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
+            for (int r = 0; r < cs.KH; ++r)
+                for (int s = 0; s < cs.KW; ++s)
+                    for (int c = 0; c < cin_blocks; ++c) {
+                        const int xi = s - cs.pad, yi = r - cs.pad;
+                        const int px = xi & 1, py = yi & 1;
+                        deltas.push_back(make_int4(px * in.C + c * cs.BK, (xi - px) / 2, py, (yi - py) / 2));
+                    }
+        } else {
+            return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride %d", name, cs.stride);
+        }
+        num_kb = static_cast<int>(deltas.size());
+        plan->flops = 2.0 * in.N * Ho * Wo * (double)cs.KH * cs.KW * cs.Cin * cs.Cout;
+    }
+    return finish_plan(e, plan, cs, es, num_kb, deltas, name);
+}
+
+int launch_conv(Engine* e, const ConvPlan& plan) {
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] {
+        attr_rc = cudaFuncSetAttribute(conv_igemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_rc != cudaSuccess)
+        return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
+    conv_igemm_tcgen05<<<plan.grid, kIGemmThreads, plan.smem, e->stream>>>(plan.prm);
+    e->launches++;
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess)
+        return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
+    return 0;
+}
+
+}  // namespace dv

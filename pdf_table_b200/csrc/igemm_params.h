@@ -1,0 +1,40 @@
+// Parameter block and mode enums of conv_igemm_tcgen05 (kernel in igemm.cuh, planner in igemm_host.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace dv {
+
+enum AMode : int {
+    A_FLAT = 0,      // A is a plain [M, K] matrix (1x1 stride-1 conv, linear layers)
+    A_PATCH = 1,     // stride-1 KHxKW conv, tensor map dims {C, W, H, N, 1}
+    A_PATCH_S2 = 2,  // stride-2 conv, parity-split view dims {2C, W/2, 2, H/2, N}
+    A_STEM = 3       // 7x7 s2 conv on a 4-channel padded image, overlapping-window view
+};
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_HSWISH = 4 };
+enum ResMode : int { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };
+enum OutMode : int { OUT_NHWC = 0, OUT_REPL = 1, OUT_SHUF2 = 2 };
+
+struct IGemmParams {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    const int4* kb_delta;  // [num_kb] per-k-block coordinate deltas (see producer)
+    int mode;
+    int num_kb;
+    int BK;         // 64 / 32 / 16 fp16 per k-block (row_bytes = 2*BK = swizzle span)
+    int num_stages;
+    int M;          // A_FLAT: number of rows
+    int Nimg, Ho, Wo;
+    int TH, TW, tiles_x, tiles_y;
+    int m_tiles, n_tiles, BLOCK_N, Cout;
+    // epilogue
+    const float* bias;  // padded to n_tiles*BLOCK_N, or nullptr
+    const __half* res;
+    int res_mode, res_ld;
+    int act;
+    int out_mode, out_ld, out_coff, rep, out_f32;
+    void* out;
+};
+
+}  // namespace dv

@@ -1,0 +1,217 @@
+// HBM-bound helper kernels around the tensor-core convolution: layout / dtype conversion,
+// page normalisation (a1), 3x3 s2 max-pool, and the final ConvTranspose(64->1)+sigmoid of the DB head.
+#include "engine.h"
+
+namespace dv {
+
+static inline int grid_for(long long n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+// fp32 NCHW [N,3,H,W] -> zero-bordered fp16 [N,H+6,W+8,4] (interior at +3,+3; channel 3 = 0)
+__global__ void k_nchw_f32_to_stem(const float* __restrict__ in, int N, int H, int W, __half* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * H * W;
+    if (idx >= total) return;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    const long long plane = static_cast<long long>(H) * W;
+    const float* ip = in + static_cast<long long>(n) * 3 * plane + static_cast<long long>(y) * W + x;
+    const __half2 a = __floats2half2_rn(ip[0], ip[plane]);
+    const __half2 b = __floats2half2_rn(ip[2 * plane], 0.f);
+    const int Hp = H + 6, Wp = W + 8;
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4) = u;
+}
+
+int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out) {
+    const long long total = static_cast<long long>(N) * H * W;
+    k_nchw_f32_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, H, W, out);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// uint8 HWC page -> normalised fp16 stem layout. Mirrors NormalizeImage
+// (reference db_pp/image_operators.py:93-102): (x * scale - mean[c]) / std[c] in fp32, applied to the
+// channel-flipped image (processor_ocr_db_pp.py:124) when flip != 0.
+__global__ void k_u8_to_stem(const uint8_t* __restrict__ in, int N, int H, int W, float3 mean, float3 stdv,
+                             float scale, int flip, __half* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * H * W;
+    if (idx >= total) return;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    const uint8_t* ip = in + idx * 3;
+    float c0 = static_cast<float>(ip[0]), c1 = static_cast<float>(ip[1]), c2 = static_cast<float>(ip[2]);
+    if (flip) {
+        const float t = c0;
+        c0 = c2;
+        c2 = t;
+    }
+    // no FMA contraction: numpy evaluates mul, sub, div as separate fp32 roundings
+    const float v0 = __fdiv_rn(__fsub_rn(__fmul_rn(c0, scale), mean.x), stdv.x);
+    const float v1 = __fdiv_rn(__fsub_rn(__fmul_rn(c1, scale), mean.y), stdv.y);
+    const float v2 = __fdiv_rn(__fsub_rn(__fmul_rn(c2, scale), mean.z), stdv.z);
+    const __half2 a = __floats2half2_rn(v0, v1);
+    const __half2 b = __floats2half2_rn(v2, 0.f);
+    const int Hp = H + 6, Wp = W + 8;
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4) = u;
+}
+
+int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
+                  float scale, int flip, __half* out) {
+    const long long total = static_cast<long long>(N) * H * W;
+    k_u8_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(
+        in, N, H, W, make_float3(mean3[0], mean3[1], mean3[2]), make_float3(std3[0], std3[1], std3[2]), scale,
+        flip, out);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// 3x3 stride-2 pad-1 max-pool on NHWC fp16, 8 channels (16 B) per thread.
+__global__ void k_maxpool3x3s2(const __half* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo,
+                               __half* __restrict__ out) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    __half2 m[4];
+    const __half2 ninf = __float2half2_rn(-65504.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = ninf;
+    for (int r = 0; r < 3; ++r) {
+        const int iy = 2 * oy - 1 + r;
+        if (iy < 0 || iy >= H) continue;
+        for (int s = 0; s < 3; ++s) {
+            const int ix = 2 * ox - 1 + s;
+            if (ix < 0 || ix >= W) continue;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+                in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c8 * 8));
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h[i]);
+        }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = m[i];
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + c8 * 8) = o;
+}
+
+int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out) {
+    if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "maxpool: C %% 8 != 0");
+    const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    k_maxpool3x3s2<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, out.H, out.W, out.p);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ConvTranspose2d(64 -> 1, k=2, s=2) + bias + sigmoid: each input pixel produces a 2x2 block of the
+// fp32 probability map (reference db_net/dbnet.py:539). One thread per input pixel; weights w[c][dy*2+dx].
+__global__ void k_deconv2x2_c1_sigmoid(const __half* __restrict__ in, long long npix, int H, int W,
+                                       const __half* __restrict__ w, float bias, float* __restrict__ out) {
+    __shared__ float sw[64 * 4];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sw[i] = __half2float(w[i]);
+    __syncthreads();
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= npix) return;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const long long n = idx / (static_cast<long long>(W) * H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const uint4* ip = reinterpret_cast<const uint4*>(in + idx * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 u = __ldg(ip + j);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 f = __half22float2(h[e2]);
+            const int c = j * 8 + e2 * 2;
+            a0 = fmaf(f.x, sw[c * 4 + 0], a0);
+            a1 = fmaf(f.x, sw[c * 4 + 1], a1);
+            a2 = fmaf(f.x, sw[c * 4 + 2], a2);
+            a3 = fmaf(f.x, sw[c * 4 + 3], a3);
+            a0 = fmaf(f.y, sw[c * 4 + 4], a0);
+            a1 = fmaf(f.y, sw[c * 4 + 5], a1);
+            a2 = fmaf(f.y, sw[c * 4 + 6], a2);
+            a3 = fmaf(f.y, sw[c * 4 + 7], a3);
+        }
+    }
+    const int W2 = 2 * W;
+    float* op = out + (n * 2 * H + 2 * y) * W2 + 2 * x;
+    const float s0 = 1.f / (1.f + expf(-(a0 + bias)));
+    const float s1 = 1.f / (1.f + expf(-(a1 + bias)));
+    const float s2 = 1.f / (1.f + expf(-(a2 + bias)));
+    const float s3 = 1.f / (1.f + expf(-(a3 + bias)));
+    *reinterpret_cast<float2*>(op) = make_float2(s0, s1);
+    *reinterpret_cast<float2*>(op + W2) = make_float2(s2, s3);
+}
+
+int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, float bias, float* out) {
+    if (in.C != 64) return set_err(e, DV_ERR_UNSUPPORTED, "deconv2x2_c1: C != 64");
+    const long long npix = static_cast<long long>(in.N) * in.H * in.W;
+    k_deconv2x2_c1_sigmoid<<<grid_for(npix, 128), 128, 0, e->stream>>>(in.p, npix, in.H, in.W, w, bias, out);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---- generic layout conversion for the operator-level ABI (dv_conv2d_nhwc_f16 tests)
+__global__ void k_nchw_f32_to_nhwc_f16(const float* __restrict__ in, int N, int C, int H, int W,
+                                       __half* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * C * H * W;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    long long t = idx / C;
+    const int x = static_cast<int>(t % W);
+    t /= W;
+    const int y = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    out[idx] = __float2half_rn(in[((static_cast<long long>(n) * C + c) * H + y) * W + x]);
+}
+__global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int C, int H, int W,
+                                       float* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * C * H * W;
+    if (idx >= total) return;
+    const int x = static_cast<int>(idx % W);
+    long long t = idx / W;
+    const int y = static_cast<int>(t % H);
+    t /= H;
+    const int c = static_cast<int>(t % C);
+    const int n = static_cast<int>(t / C);
+    out[idx] = __half2float(in[((static_cast<long long>(n) * H + y) * W + x) * C + c]);
+}
+int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out) {
+    const long long total = static_cast<long long>(N) * C * H * W;
+    k_nchw_f32_to_nhwc_f16<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out) {
+    const long long total = static_cast<long long>(N) * C * H * W;
+    k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out);
+    e->launches++;
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dv

@@ -1,0 +1,151 @@
+"""Python handle over the C ABI.  torch is used only for device memory and streams (plumbing); every
+computation below is a kernel in libdocvision.so.  There is no fallback: without the library or without
+a B200 these calls raise DocVisionError."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DocVisionError, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise DocVisionError(f"{name} must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class Engine:
+    """One handle per (model kind, device).  Not thread-safe; distinct handles are independent."""
+
+    def __init__(self, kind: str = "post", blob: Optional[bytes] = None, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.kind = kind
+        self.device = device
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob) if blob else None
+        rc = self._lib.dv_create(kind.encode(), buf, len(blob) if blob else 0, device, C.byref(self._h))
+        check(rc, None, f"dv_create({kind})")
+        self.use_current_stream()
+
+    # ------------------------------------------------------------------ lifetime / streams
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.dv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_current_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.dv_set_stream(self._h, C.c_void_p(s)), self._h, "dv_set_stream")
+
+    def sync(self):
+        check(self._lib.dv_sync(self._h), self._h, "dv_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.dv_launch_count(self._h))
+
+    @property
+    def model_flops(self) -> float:
+        return float(self._lib.dv_model_flops(self._h))
+
+    # ------------------------------------------------------------------ networks
+    def dbnet_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 NCHW [N,3,H,W] (cuda) -> probability map fp32 [N,1,H,W]."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("dbnet expects 3 channels")
+        if out is None:
+            out = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+        check(self._lib.dv_dbnet_forward(self._h, _ptr(x), n, h, w, _ptr(out)), self._h, "dv_dbnet_forward")
+        return out
+
+    def dbnet_forward_u8(self, pages: torch.Tensor, mean, std, scale: float = 1.0 / 255.0, flip: bool = True,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 HWC pages [N,H,W,3] (cuda) -> probability map; fuses the reference's normalisation."""
+        pages = _require_cuda(pages, torch.uint8, "pages")
+        n, h, w, c = pages.shape
+        if c != 3:
+            raise ValueError("pages must be [N,H,W,3]")
+        if out is None:
+            out = torch.empty((n, 1, h, w), dtype=torch.float32, device=pages.device)
+        m3 = (C.c_float * 3)(*[float(v) for v in mean])
+        s3 = (C.c_float * 3)(*[float(v) for v in std])
+        check(self._lib.dv_dbnet_forward_u8(self._h, _ptr(pages), n, h, w, m3, s3, float(scale), int(flip), _ptr(out)),
+              self._h, "dv_dbnet_forward_u8")
+        return out
+
+    def debug_tensor(self, name: str) -> torch.Tensor:
+        """Named intermediate activation of the last forward as fp32 NCHW (parity debugging)."""
+        dims = (C.c_int * 4)()
+        check(self._lib.dv_debug_get_tensor(self._h, name.encode(), None, dims), self._h, "dv_debug_get_tensor")
+        out = torch.empty(tuple(dims), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(self._lib.dv_debug_get_tensor(self._h, name.encode(), _ptr(out), dims), self._h, "dv_debug_get_tensor")
+        return out
+
+    # ------------------------------------------------------------------ post-processing kernels
+    def ctc_greedy(self, probs: torch.Tensor, blank: int = 0, return_raw: bool = False):
+        """[B,T,C] fp32 (cuda) -> (ids [B,T] int32 left-packed / -1 padded, len [B] int32, conf [B] fp32)."""
+        probs = _require_cuda(probs, torch.float32, "probs")
+        b, t, c = probs.shape
+        dev = probs.device
+        ids = torch.empty((b, t), dtype=torch.int32, device=dev)
+        ln = torch.empty((b,), dtype=torch.int32, device=dev)
+        conf = torch.empty((b,), dtype=torch.float32, device=dev)
+        raw_ids = torch.empty((b, t), dtype=torch.int32, device=dev) if return_raw else None
+        raw_max = torch.empty((b, t), dtype=torch.float32, device=dev) if return_raw else None
+        check(self._lib.dv_ctc_greedy(self._h, _ptr(probs), b, t, c, blank, _ptr(ids), _ptr(ln), _ptr(conf),
+                                      _ptr(raw_ids), _ptr(raw_max)), self._h, "dv_ctc_greedy")
+        if return_raw:
+            return ids, ln, conf, raw_ids, raw_max
+        return ids, ln, conf
+
+    # ------------------------------------------------------------------ operator level (kernel parity tests)
+    def nchw_to_nhwc_f16(self, x: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        out = torch.empty((n, h, w, c), dtype=torch.float16, device=x.device)
+        check(self._lib.dv_nchw_f32_to_nhwc_f16(self._h, _ptr(x), n, c, h, w, _ptr(out)), self._h)
+        return out
+
+    def nhwc_f16_to_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda(x, torch.float16, "x")
+        n, h, w, c = x.shape
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        check(self._lib.dv_nhwc_f16_to_nchw_f32(self._h, _ptr(x), n, c, h, w, _ptr(out)), self._h)
+        return out
+
+    def conv2d_nhwc(self, x_nhwc: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], cout: int,
+                    ksize: int, stride: int, pad: int, residual: Optional[torch.Tensor] = None, act: int = 0):
+        x_nhwc = _require_cuda(x_nhwc, torch.float16, "x")
+        w_packed = _require_cuda(w_packed, torch.float16, "w")
+        n, h, w, cin = x_nhwc.shape
+        cin_pad = w_packed.shape[1] // (ksize * ksize)
+        ho = (h + 2 * pad - ksize) // stride + 1
+        wo = (w + 2 * pad - ksize) // stride + 1
+        out = torch.empty((n, ho, wo, cout), dtype=torch.float16, device=x_nhwc.device)
+        if bias is not None:
+            bias = _require_cuda(bias, torch.float32, "bias")
+        if residual is not None:
+            residual = _require_cuda(residual, torch.float16, "residual")
+        check(self._lib.dv_conv2d_nhwc_f16(self._h, _ptr(x_nhwc), n, h, w, cin, _ptr(w_packed), cin_pad, _ptr(bias),
+                                           cout, ksize, stride, pad, _ptr(residual), act, _ptr(out)), self._h,
+              "dv_conv2d_nhwc_f16")
+        return out

@@ -1,0 +1,157 @@
+"""Weight packer: reference state_dict -> flat blob consumed by libdocvision.so (dv_create).
+
+This is the engine's only "checkpoint" format: BatchNorm folded into the
+convolution, weights converted to fp16 and laid out K-major as [Cout][tap][Cin_pad] so one TMA box is
+one (tap, channel-block) K-slice of the implicit GEMM; biases stay fp32 and are padded to 256.
+
+Blob layout (little endian; mirrored in csrc/capi.cu):
+    header  : magic "DVWBLOB1", u32 n_tensors, u32 reserved, u64 data_offset, u64 data_bytes
+    entries : n_tensors x { char name[96]; u32 dtype; u32 ndim; u32 dims[4]; u64 offset; u64 nbytes }
+    payload : tensors, each 256-byte aligned
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, Mapping, Optional, Tuple
+
+import numpy as np
+
+DT_F32, DT_F16, DT_I32 = 0, 1, 2
+_DT = {np.dtype(np.float32): DT_F32, np.dtype(np.float16): DT_F16, np.dtype(np.int32): DT_I32}
+
+
+def _np(t) -> np.ndarray:
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def cin_pad_of(cin: int) -> int:
+    """Channel padding of the packed K axis; the engine derives BK (64/32/16) from it."""
+    return (cin + 15) // 16 * 16
+
+
+def pad_bias(b: np.ndarray) -> np.ndarray:
+    n = (b.shape[0] + 255) // 256 * 256
+    out = np.zeros(n, np.float32)
+    out[: b.shape[0]] = b
+    return out
+
+
+def bn_affine(bn: Optional[Mapping[str, np.ndarray]], cout: int) -> Tuple[np.ndarray, np.ndarray]:
+    """y = x * scale + shift for an eval-mode BatchNorm (fp32, as torch computes it)."""
+    if bn is None:
+        return np.ones(cout, np.float32), np.zeros(cout, np.float32)
+    g, b, m, v = (_np(bn[k]).astype(np.float32) for k in ("weight", "bias", "running_mean", "running_var"))
+    eps = np.float32(bn.get("eps", 1e-5))
+    scale = g / np.sqrt(v + eps)
+    return scale.astype(np.float32), (b - m * scale).astype(np.float32)
+
+
+def pack_conv(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """[Cout,Cin,KH,KW] fp32 (+bias, +BN) -> (fp16 [Cout, KH*KW*Cin_pad], fp32 bias padded to 256)."""
+    w = _np(weight).astype(np.float32)
+    cout, cin, kh, kw = w.shape
+    scale, shift = bn_affine(bn, cout)
+    b = np.zeros(cout, np.float32) if bias is None else _np(bias).astype(np.float32)
+    w = w * scale[:, None, None, None]
+    b = b * scale + shift
+    cp = cin_pad_of(cin)
+    packed = np.zeros((cout, kh * kw, cp), np.float16)
+    packed[:, :, :cin] = w.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin).astype(np.float16)
+    return packed.reshape(cout, kh * kw * cp), pad_bias(b)
+
+
+def pack_linear(weight, bias=None) -> Tuple[np.ndarray, np.ndarray]:
+    """nn.Linear weight [out, in] -> same packing as a 1x1 conv."""
+    w = _np(weight).astype(np.float32)
+    return pack_conv(w[:, :, None, None], bias)
+
+
+def pack_stem7x7(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """7x7 stride-2 stem on a 3-channel image: K index = r*32 + s*4 + c (s padded 7->8, c padded 3->4),
+    matching the overlapping-window TMA view of the padded 4-channel input (csrc/igemm_host.cu, A_STEM)."""
+    w = _np(weight).astype(np.float32)
+    cout, cin, kh, kw = w.shape
+    assert (cin, kh, kw) == (3, 7, 7), w.shape
+    scale, shift = bn_affine(bn, cout)
+    w = w * scale[:, None, None, None]
+    packed = np.zeros((cout, 7, 8, 4), np.float16)
+    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1).astype(np.float16)
+    return packed.reshape(cout, 7 * 32), pad_bias(shift)
+
+
+def pack_deconv2x2(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """ConvTranspose2d(k=2,s=2) weight [Cin,Cout,2,2] -> GEMM weight [(dy*2+dx)*Cout + co][Cin_pad]
+    whose output is pixel-shuffled by the epilogue (OUT_SHUF2)."""
+    w = _np(weight).astype(np.float32)
+    cin, cout, kh, kw = w.shape
+    assert (kh, kw) == (2, 2)
+    scale, shift = bn_affine(bn, cout)
+    b = np.zeros(cout, np.float32) if bias is None else _np(bias).astype(np.float32)
+    b = b * scale + shift
+    cp = cin_pad_of(cin)
+    packed = np.zeros((4, cout, cp), np.float16)
+    # w[ci, co, dy, dx] -> [q=dy*2+dx, co, ci]
+    packed[:, :, :cin] = (w * scale[None, :, None, None]).transpose(2, 3, 1, 0).reshape(4, cout, cin).astype(np.float16)
+    return packed.reshape(4 * cout, cp), pad_bias(np.tile(b, 4))
+
+
+def write_blob(tensors: Mapping[str, np.ndarray]) -> bytes:
+    names = list(tensors.keys())
+    entries = []
+    payload = bytearray()
+    for name in names:
+        a = np.ascontiguousarray(tensors[name])
+        if a.dtype not in _DT:
+            raise TypeError(f"{name}: unsupported dtype {a.dtype}")
+        if a.ndim > 4 or a.ndim == 0:
+            raise ValueError(f"{name}: rank {a.ndim}")
+        while len(payload) % 256:
+            payload.append(0)
+        off = len(payload)
+        payload += a.tobytes()
+        dims = list(a.shape) + [0] * (4 - a.ndim)
+        nm = name.encode()
+        if len(nm) > 95:
+            raise ValueError(f"tensor name too long: {name}")
+        entries.append(struct.pack("<96sII4IQQ", nm, _DT[a.dtype], a.ndim, *dims, off, a.nbytes))
+    header_size = 8 + 4 + 4 + 8 + 8
+    table = b"".join(entries)
+    data_offset = (header_size + len(table) + 255) // 256 * 256
+    head = struct.pack("<8sIIQQ", b"DVWBLOB1", len(names), 0, data_offset, len(payload))
+    pad = b"\0" * (data_offset - header_size - len(table))
+    return head + table + pad + bytes(payload)
+
+
+# --------------------------------------------------------------------------- DBNet-R18
+def _bn(sd, prefix):
+    return {k: _np(sd[f"{prefix}.{k}"]) for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference DBModel (db_net/dbnet.py:715-728; keys backbone.* / decoder.*)."""
+    t: Dict[str, np.ndarray] = {}
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    put("stem", pack_stem7x7(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1")))
+    for L in range(1, 5):
+        for B in range(2):
+            p = f"backbone.layer{L}.{B}"
+            put(f"layer{L}.{B}.conv1", pack_conv(sd[f"{p}.conv1.weight"], None, _bn(sd, f"{p}.bn1")))
+            put(f"layer{L}.{B}.conv2", pack_conv(sd[f"{p}.conv2.weight"], None, _bn(sd, f"{p}.bn2")))
+            if f"{p}.downsample.0.weight" in sd:
+                put(f"layer{L}.{B}.down", pack_conv(sd[f"{p}.downsample.0.weight"], None, _bn(sd, f"{p}.downsample.1")))
+    for n in ("in5", "in4", "in3", "in2"):
+        put(n, pack_conv(sd[f"decoder.{n}.weight"], sd.get(f"decoder.{n}.bias")))
+    for n in ("out5", "out4", "out3"):
+        put(n, pack_conv(sd[f"decoder.{n}.0.weight"], sd.get(f"decoder.{n}.0.bias")))
+    put("out2", pack_conv(sd["decoder.out2.weight"], sd.get("decoder.out2.bias")))
+    put("bin.conv", pack_conv(sd["decoder.binarize.0.weight"], sd.get("decoder.binarize.0.bias"), _bn(sd, "decoder.binarize.1")))
+    put("bin.deconv1", pack_deconv2x2(sd["decoder.binarize.3.weight"], sd["decoder.binarize.3.bias"], _bn(sd, "decoder.binarize.4")))
+    w2 = _np(sd["decoder.binarize.6.weight"]).astype(np.float32)  # [64,1,2,2]
+    t["bin.deconv2.w"] = w2.reshape(64, 4).astype(np.float16)
+    t["bin.deconv2.b"] = _np(sd["decoder.binarize.6.bias"]).astype(np.float32).reshape(1)
+    return write_blob(t)

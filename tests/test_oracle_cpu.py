@@ -1,0 +1,63 @@
+"""Oracle restatements vs the golden fixtures produced by the reference's own modules
+(oracle/gen_golden.py, run in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc_ref, dbnet_ref, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_ctc_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "ctc_decode.npz"))
+    character = list(g["character"])
+    for case in ("known", "rand_T40", "rand_T7", "rand_T160", "rand_T300", "edge"):
+        res = ctc_ref.ctc_decode_text(g[f"{case}.preds"], character)
+        assert [r[0] for r in res] == list(g[f"{case}.text"]), case
+        np.testing.assert_array_equal(np.array([r[1] for r in res]), g[f"{case}.conf"], err_msg=case)
+    # SURVEY.md 8c known-answer vector
+    assert ctc_ref.ctc_decode_text(g["known.preds"], character)[0][0] == "012 "
+
+
+def test_dbnet_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "dbnet_r18_seed0.npz"))
+    sd = synth.dbnet_r18_state_dict(0)
+    prob = dbnet_ref.dbnet_r18_forward(sd, torch.from_numpy(g["x"])).numpy()
+    np.testing.assert_allclose(prob, g["prob"], atol=1e-6, rtol=0)
+
+
+def test_synth_weights_deterministic():
+    a, b = synth.dbnet_r18_state_dict(0), synth.dbnet_r18_state_dict(0)
+    assert list(a) == list(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    n_params = sum(v.size for k, v in a.items() if "running" not in k)
+    assert 11_000_000 < n_params < 13_000_000  # DBNet-R18 without the training-only thresh branch
+
+
+def test_weight_packer_layouts():
+    from pdf_table_b200 import weights
+
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((5, 24, 3, 3)).astype(np.float32)
+    packed, bias = weights.pack_conv(w)
+    assert packed.shape == (5, 9 * 32) and bias.shape == (256,)
+    p = packed.reshape(5, 9, 32)
+    np.testing.assert_array_equal(p[:, :, 24:], 0)
+    np.testing.assert_array_equal(p[2, 4, :24], w[2, :, 1, 1].astype(np.float16))
+    sw = rng.standard_normal((64, 3, 7, 7)).astype(np.float32)
+    sp, _ = weights.pack_stem7x7(sw)
+    sp = sp.reshape(64, 7, 8, 4)
+    np.testing.assert_array_equal(sp[:, :, 7, :], 0)
+    np.testing.assert_array_equal(sp[:, :, :, 3], 0)
+    np.testing.assert_array_equal(sp[3, 2, 5, 1], sw[3, 1, 2, 5].astype(np.float16))
+    dw = rng.standard_normal((16, 8, 2, 2)).astype(np.float32)
+    dp, db = weights.pack_deconv2x2(dw, np.arange(8, dtype=np.float32))
+    assert dp.shape == (32, 16)
+    np.testing.assert_array_equal(dp[(1 * 2 + 0) * 8 + 3, :], dw[:, 3, 1, 0].astype(np.float16))
+    np.testing.assert_array_equal(db[:32], np.tile(np.arange(8, dtype=np.float32), 4))
+    blob = weights.pack_dbnet_r18(synth.dbnet_r18_state_dict(0))
+    assert blob[:8] == b"DVWBLOB1" and len(blob) > 20_000_000
