@@ -22,17 +22,22 @@
 namespace dv {
 
 static constexpr int kIGemmThreads = 192;
+static constexpr int kMaxKB = 160;  // k-blocks per tile whose coordinate deltas are staged in smem
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-    switch (act) {
-        case ACT_RELU: return fmaxf(x, 0.f);
-        case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-        case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-        case ACT_HSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
-        default: return x;
-    }
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+    if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    if constexpr (ACT == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    if constexpr (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+    if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return x;
 }
 
+// Shape contract enforced by the planner (igemm_host.cu): out_ld, out_coff, res_ld and Cout are multiples
+// of 8 (fp16 out) / 4 (fp32 out), so the epilogue only ever issues 16-byte vector accesses, predicated
+// per vector on the channel bound.  Keeping the epilogue this small matters: it is executed by only four
+// warps and an earlier, fully generic version was instruction-fetch bound (profiles/r1_notes.md).
+template <int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(kIGemmThreads, 1)
 conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -41,6 +46,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ int4 s_delta[kMaxKB];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -51,7 +57,9 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int num_stages = p.num_stages;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    const int num_kb = p.num_kb;
 
+    for (int i = threadIdx.x; i < num_kb; i += kIGemmThreads) s_delta[i] = __ldg(&p.kb_delta[i]);
     if (threadIdx.x == 0) {
         for (int i = 0; i < num_stages; ++i) {
             ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
@@ -80,25 +88,27 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             int stage = 0;
             uint32_t phase = 0;
             const int tiles_per_img = p.tiles_x * p.tiles_y;
+            const int mode = p.mode;
+            const int BK = p.BK, BLOCK_N = p.BLOCK_N, n_tiles = p.n_tiles;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles;
-                const int n_tile = tile - m_tile * p.n_tiles;
+                const int m_tile = tile / n_tiles;
+                const int n_tile = tile - m_tile * n_tiles;
                 int img = 0, y0 = 0, x0 = 0;
-                if (p.mode != A_FLAT) {
+                if (mode != A_FLAT) {
                     img = m_tile / tiles_per_img;
                     const int t = m_tile - img * tiles_per_img;
                     const int ty = t / p.tiles_x;
                     y0 = ty * p.TH;
                     x0 = (t - ty * p.tiles_x) * p.TW;
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int4 d = s_delta[kb];
                     ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
                     const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
                     ptx::mbar_expect_tx(fb, stage_bytes);
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint32_t sb = sa + a_bytes;
-                    const int4 d = __ldg(&p.kb_delta[kb]);
-                    switch (p.mode) {
+                    switch (mode) {
                         case A_FLAT: ptx::tma_load_5d(sa, &p.tmA, fb, d.x, m_tile * 128, 0, 0, 0); break;
                         case A_PATCH: ptx::tma_load_5d(sa, &p.tmA, fb, d.x, x0 + d.y, y0 + d.z, img, 0); break;
                         case A_PATCH_S2:
@@ -108,7 +118,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                             ptx::tma_load_5d(sa, &p.tmA, fb, 0, x0, d.z, y0, img);
                             break;
                     }
-                    ptx::tma_load_2d(sb, &p.tmB, fb, kb * p.BK, n_tile * p.BLOCK_N);
+                    ptx::tma_load_2d(sb, &p.tmB, fb, kb * BK, n_tile * BLOCK_N);
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -126,7 +136,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
@@ -152,61 +162,73 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         int acc = 0;
         uint32_t acc_phase = 0;
         const int tiles_per_img = p.tiles_x * p.tiles_y;
-        const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.out_coff & 7) == 0);
+        const int mode = p.mode, n_tiles = p.n_tiles, BLOCK_N = p.BLOCK_N, Cout = p.Cout;
+        const int Ho = p.Ho, Wo = p.Wo, TW = p.TW, TH = p.TH, tiles_x = p.tiles_x;
+        const int out_mode = p.out_mode, out_ld = p.out_ld, out_coff = p.out_coff, rep = p.rep;
+        const int res_mode = p.res_mode, res_ld = p.res_ld;
+        const float* __restrict__ bias = p.bias;
+        const __half* __restrict__ res = p.res;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles;
-            const int n_tile = tile - m_tile * p.n_tiles;
+            const int m_tile = tile / n_tiles;
+            const int n_tile = tile - m_tile * n_tiles;
             // ---- which output pixel does this thread own?
             int img, y, x;
             bool valid;
-            if (p.mode == A_FLAT) {
+            if (mode == A_FLAT) {
                 const int m = m_tile * 128 + row;
                 valid = m < p.M;
-                const int hw = p.Ho * p.Wo;
+                const int hw = Ho * Wo;
                 img = m / hw;
                 const int r = m - img * hw;
-                y = r / p.Wo;
-                x = r - y * p.Wo;
+                y = r / Wo;
+                x = r - y * Wo;
             } else {
                 img = m_tile / tiles_per_img;
                 const int t = m_tile - img * tiles_per_img;
-                const int ty = t / p.tiles_x;
-                const int tx = t - ty * p.tiles_x;
-                const int ly = row / p.TW;
-                y = ty * p.TH + ly;
-                x = tx * p.TW + (row - ly * p.TW);
-                valid = (y < p.Ho) && (x < p.Wo);
+                const int ty = t / tiles_x;
+                const int tx = t - ty * tiles_x;
+                const int ly = row / TW;
+                y = ty * TH + ly;
+                x = tx * TW + (row - ly * TW);
+                valid = (y < Ho) && (x < Wo);
             }
-            const long long pix = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
+            const long long pix = (static_cast<long long>(img) * Ho + y) * Wo + x;
             long long res_pix = pix;
-            if (p.res_mode == RES_UP2)
-                res_pix = (static_cast<long long>(img) * (p.Ho >> 1) + (y >> 1)) * (p.Wo >> 1) + (x >> 1);
+            if (res_mode == RES_UP2)
+                res_pix = (static_cast<long long>(img) * (Ho >> 1) + (y >> 1)) * (Wo >> 1) + (x >> 1);
 
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                    static_cast<uint32_t>(acc) * 256u;
-            for (int c = 0; c < p.BLOCK_N; c += 32) {
-                const int col0 = n_tile * p.BLOCK_N + c;
-                if (col0 >= p.Cout) break;  // warp-uniform
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                const int col0 = n_tile * BLOCK_N + c;
+                if (col0 >= Cout) break;  // warp-uniform
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
                 ptx::tmem_ld_wait();
                 if (!valid) continue;
-                const int ncol = min(32, p.Cout - col0);
+                const int ncol = min(32, Cout - col0);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.bias != nullptr) {
+                if (bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + col0);  // padded to 256
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        f[4 * j] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
                 }
-                if (p.res_mode != RES_NONE) {
-                    const __half* rp = p.res + res_pix * p.res_ld + col0;
-                    if (ncol == 32 && ((p.res_ld & 7) == 0)) {
+                if (res_mode != RES_NONE) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + res_pix * res_ld + col0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+                    for (int j = 0; j < 4; ++j) {
+                        if (j * 8 < ncol) {
+                            const uint4 u = __ldg(rp + j);
                             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -215,68 +237,56 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                                 f[j * 8 + e * 2 + 1] += t2.y;
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncol) f[j] += __half2float(rp[j]);
                     }
                 }
-                if (p.act != ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-                }
+                for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
                 // ---- store
                 int reps = 1;
                 long long opix0 = pix;
                 int ocol = col0;
                 int orow_stride = 0;  // pixels per output row (for replication)
-                if (p.out_mode == OUT_REPL) {
-                    reps = p.rep;
-                    orow_stride = p.Wo * p.rep;
-                    opix0 = (static_cast<long long>(img) * p.Ho * p.rep + static_cast<long long>(y) * p.rep) *
-                                orow_stride + static_cast<long long>(x) * p.rep;
-                } else if (p.out_mode == OUT_SHUF2) {
-                    const int cq = p.Cout >> 2;
+                if (out_mode == OUT_REPL) {
+                    reps = rep;
+                    orow_stride = Wo * rep;
+                    opix0 = (static_cast<long long>(img) * Ho * rep + static_cast<long long>(y) * rep) * orow_stride +
+                            static_cast<long long>(x) * rep;
+                } else if (out_mode == OUT_SHUF2) {
+                    const int cq = Cout >> 2;
                     const int quad = col0 / cq;
                     ocol = col0 - quad * cq;
-                    opix0 = (static_cast<long long>(img) * p.Ho * 2 + 2 * y + (quad >> 1)) * (p.Wo * 2) +
-                            2 * x + (quad & 1);
+                    opix0 = (static_cast<long long>(img) * Ho * 2 + 2 * y + (quad >> 1)) * (Wo * 2) + 2 * x + (quad & 1);
                 }
-                for (int dy = 0; dy < reps; ++dy) {
-                    for (int dx = 0; dx < reps; ++dx) {
-                        const long long opix = opix0 + static_cast<long long>(dy) * orow_stride + dx;
-                        const long long off = opix * p.out_ld + p.out_coff + ocol;
-                        if (p.out_f32) {
-                            float* op = reinterpret_cast<float*>(p.out) + off;
-                            if (ncol == 32 && ((p.out_ld & 3) == 0) && ((p.out_coff & 3) == 0)) {
+                if constexpr (OUT_F32) {
+                    float4 o[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    reinterpret_cast<float4*>(op)[j] =
-                                        make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                            } else {
+                    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    for (int dy = 0; dy < reps; ++dy)
+                        for (int dx = 0; dx < reps; ++dx) {
+                            const long long opix = opix0 + static_cast<long long>(dy) * orow_stride + dx;
+                            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * out_ld +
+                                                                   out_coff + ocol);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (j < ncol) op[j] = f[j];
-                            }
-                        } else {
-                            __half* op = reinterpret_cast<__half*>(p.out) + off;
-                            if (ncol == 32 && vec_ok) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    uint4 u;
-                                    __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        h2[e] = __floats2half2_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-                                    reinterpret_cast<uint4*>(op)[j] = u;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (j < ncol) op[j] = __float2half_rn(f[j]);
-                            }
+                            for (int j = 0; j < 8; ++j)
+                                if (j * 4 < ncol) op[j] = o[j];
                         }
+                } else {
+                    uint4 o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __half2* h2 = reinterpret_cast<__half2*>(&o[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
                     }
+                    for (int dy = 0; dy < reps; ++dy)
+                        for (int dx = 0; dx < reps; ++dx) {
+                            const long long opix = opix0 + static_cast<long long>(dy) * orow_stride + dx;
+                            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix * out_ld +
+                                                                 out_coff + ocol);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j * 8 < ncol) op[j] = o[j];
+                        }
                 }
             }
             ptx::tc_fence_before();

@@ -95,7 +95,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.n_tiles = (cs.Cout + block_n - 1) / block_n;
     const int row_bytes = 2 * cs.BK;
     const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
-    int stages = static_cast<int>((220 * 1024) / stage_bytes);
+    int stages = static_cast<int>((216 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
     p.num_stages = stages;
@@ -111,6 +111,15 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.out_coff = es.out_coff;
     p.rep = es.rep;
     p.out_f32 = es.out_f32;
+    if (num_kb > kMaxKB) return set_err(e, DV_ERR_UNSUPPORTED, "%s: %d k-blocks > %d", name, num_kb, kMaxKB);
+    {
+        const int al = es.out_f32 ? 4 : 8;
+        if ((cs.Cout % al) || (es.out_ld % al) || (es.out_coff % al) || (es.res_mode != RES_NONE && (es.res_ld % 8)))
+            return set_err(e, DV_ERR_UNSUPPORTED,
+                           "%s: Cout/out_ld/out_coff must be multiples of %d and res_ld of 8 (pad channels)", name, al);
+        if ((reinterpret_cast<uintptr_t>(es.out) & 15) || (reinterpret_cast<uintptr_t>(es.res) & 15))
+            return set_err(e, DV_ERR_ARG, "%s: out/res pointers must be 16-byte aligned", name);
+    }
     if (es.out_mode == OUT_SHUF2 && (((cs.Cout >> 2) % 32) != 0 || (cs.Cout & 3)))
         return set_err(e, DV_ERR_UNSUPPORTED, "%s: OUT_SHUF2 needs Cout/4 %% 32 == 0", name);
     // weight map: [Cout][Ktot] K-major
@@ -247,15 +256,43 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
     return finish_plan(e, plan, cs, es, num_kb, deltas, name);
 }
 
+typedef void (*IGemmKernel)(const IGemmParams);
+
+template <int ACT, bool F32>
+static IGemmKernel kernel_entry() {
+    return conv_igemm_tcgen05<ACT, F32>;
+}
+
+static IGemmKernel pick_kernel(int act, int out_f32) {
+    switch (act * 2 + (out_f32 ? 1 : 0)) {
+        case ACT_NONE * 2: return kernel_entry<ACT_NONE, false>();
+        case ACT_NONE * 2 + 1: return kernel_entry<ACT_NONE, true>();
+        case ACT_RELU * 2: return kernel_entry<ACT_RELU, false>();
+        case ACT_RELU * 2 + 1: return kernel_entry<ACT_RELU, true>();
+        case ACT_GELU * 2: return kernel_entry<ACT_GELU, false>();
+        case ACT_GELU * 2 + 1: return kernel_entry<ACT_GELU, true>();
+        case ACT_SIGMOID * 2: return kernel_entry<ACT_SIGMOID, false>();
+        case ACT_SIGMOID * 2 + 1: return kernel_entry<ACT_SIGMOID, true>();
+        case ACT_HSWISH * 2: return kernel_entry<ACT_HSWISH, false>();
+        case ACT_HSWISH * 2 + 1: return kernel_entry<ACT_HSWISH, true>();
+        default: return nullptr;
+    }
+}
+
 int launch_conv(Engine* e, const ConvPlan& plan) {
     static std::once_flag once;
     static cudaError_t attr_rc = cudaSuccess;
     std::call_once(once, [] {
-        attr_rc = cudaFuncSetAttribute(conv_igemm_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        for (int act = 0; act <= ACT_HSWISH && attr_rc == cudaSuccess; ++act)
+            for (int f = 0; f < 2 && attr_rc == cudaSuccess; ++f)
+                attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_kernel(act, f)),
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     });
     if (attr_rc != cudaSuccess)
         return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
-    conv_igemm_tcgen05<<<plan.grid, kIGemmThreads, plan.smem, e->stream>>>(plan.prm);
+    IGemmKernel k = pick_kernel(plan.prm.act, plan.prm.out_f32);
+    if (!k) return set_err(e, DV_ERR_ARG, "launch %s: bad activation %d", plan.name.c_str(), plan.prm.act);
+    k<<<plan.grid, kIGemmThreads, plan.smem, e->stream>>>(plan.prm);
     e->launches++;
     cudaError_t st = cudaGetLastError();
     if (st != cudaSuccess)

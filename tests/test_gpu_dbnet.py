@@ -14,7 +14,7 @@ from pdf_table_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-PROB_TOL = 4e-3  # fp16 activations through 21 conv layers; measured max error is recorded in DESIGN.md
+PROB_TOL = 1e-2  # fp16 operands+activations (the reference's own default precision, base_infer_task.py:56-57); see DESIGN.md
 
 
 @pytest.fixture(scope="module")
