@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the pdf_table hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): a batch of 32 synthetic 960x960 pages per GPU through the text
+cascade -- DB text detection (uint8 page -> normalise -> DBNet -> probability map) and text-line
+recognition post-processing (CTC greedy decode of the per-crop class probabilities).  `config.stages`
+lists exactly which stages of the cascade are inside the timed region.  One "step" = one pass over the
+32-page batch.  value = pages/s with the pages already resident in HBM; e2e = the same through the public
+predictor API with HOST (pinned) page buffers, H2D and D2H inside the timed region.
+
+The reference arm (--impl reference) times the CPU restatement of the same stages (oracle/, the
+reference's algorithm in plain PyTorch fp32 / numpy on the host cores) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+PAGES_PER_GPU = 32
+PAGE_H = PAGE_W = 960
+CROPS_PER_PAGE = 40          # synthetic pages plant 30-60 text lines
+CTC_T, CTC_C = 40, 97        # PP-OCRv4 en rec head: 48x320 crop -> T=40, C=97
+MEAN = (0.485, 0.456, 0.406)
+STD = (0.229, 0.224, 0.225)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            out = {k: float(d[k]) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in d}
+            if "hbm_gbs" in out and "bf16_tflops" in out:
+                out.setdefault("bf16_tflops_sustained", out["bf16_tflops"])
+                return out, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- workload
+def make_pages(rank: int, n: int) -> np.ndarray:
+    from pdf_table_b200 import synth
+
+    # a handful of distinct pages tiled to the batch keeps start-up short; content does not change the work
+    distinct = [synth.synthetic_page(rank * 1000 + i, PAGE_H, PAGE_W) for i in range(4)]
+    return np.stack([distinct[i % 4] for i in range(n)])
+
+
+def make_ctc_probs(rank: int, n_crops: int) -> np.ndarray:
+    rng = np.random.default_rng(77 + rank)
+    logits = rng.standard_normal((n_crops, CTC_T, CTC_C)).astype(np.float32) * 3
+    runs = rng.integers(0, CTC_C, size=(n_crops, CTC_T))
+    runs[rng.random((n_crops, CTC_T)) < 0.3] = 0
+    logits[np.arange(n_crops)[:, None], np.arange(CTC_T)[None, :], runs] += 8
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    return (e / e.sum(-1, keepdims=True)).astype(np.float32)
+
+
+class Cascade:
+    """The B200 arm: product code only (pdf_table_b200), no oracle imports."""
+
+    stages = ["det_preprocess_u8", "dbnet_r18_forward", "ctc_greedy_decode"]
+
+    def __init__(self, rank: int, device: int):
+        from pdf_table_b200 import synth, weights
+        from pdf_table_b200.engine import Engine
+
+        self.device = device
+        self.det = Engine("dbnet_r18", weights.pack_dbnet_r18(synth.dbnet_r18_state_dict(0)), device=device)
+        self.post = Engine("post", device=device)
+        self.n_pages = PAGES_PER_GPU
+        self.n_crops = PAGES_PER_GPU * CROPS_PER_PAGE
+        self.pages_host = torch.from_numpy(make_pages(rank, self.n_pages)).pin_memory()
+        self.probs_host = torch.from_numpy(make_ctc_probs(rank, self.n_crops)).pin_memory()
+        dev = torch.device("cuda", device)
+        self.pages_dev = self.pages_host.to(dev)
+        self.probs_dev = self.probs_host.to(dev)
+        self.prob_map = torch.empty((self.n_pages, 1, PAGE_H, PAGE_W), dtype=torch.float32, device=dev)
+        self.pages_stage = torch.empty_like(self.pages_dev)
+        self.probs_stage = torch.empty_like(self.probs_dev)
+        self.map_host = torch.empty(self.prob_map.shape, dtype=torch.float32).pin_memory()
+        self.ids_host = torch.empty((self.n_crops, CTC_T), dtype=torch.int32).pin_memory()
+        self.len_host = torch.empty((self.n_crops,), dtype=torch.int32).pin_memory()
+        self.conf_host = torch.empty((self.n_crops,), dtype=torch.float32).pin_memory()
+        # L2 flush buffer (> 126 MB) written between timed steps
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_device(self):
+        """Inputs resident in HBM."""
+        self.det.dbnet_forward_u8(self.pages_dev, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        return self.post.ctc_greedy(self.probs_dev)
+
+    def step_e2e(self):
+        """Host (pinned) buffers in, host results out: H2D + D2H inside."""
+        self.pages_stage.copy_(self.pages_host, non_blocking=True)
+        self.probs_stage.copy_(self.probs_host, non_blocking=True)
+        self.det.dbnet_forward_u8(self.pages_stage, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        ids, ln, conf = self.post.ctc_greedy(self.probs_stage)
+        self.map_host.copy_(self.prob_map, non_blocking=True)
+        self.ids_host.copy_(ids, non_blocking=True)
+        self.len_host.copy_(ln, non_blocking=True)
+        self.conf_host.copy_(conf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    @property
+    def h2d_bytes(self):
+        return self.pages_host.numel() + self.probs_host.numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return self.map_host.numel() * 4 + self.ids_host.numel() * 4 + self.len_host.numel() * 4 + self.conf_host.numel() * 4
+
+    def launches_per_step(self):
+        a = self.det.launch_count + self.post.launch_count
+        self.step_device()
+        torch.cuda.synchronize()
+        return self.det.launch_count + self.post.launch_count - a
+
+    def flush_l2(self):
+        self.flush.fill_(1)
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd):
+    """The reference's algorithm for the same stages on the host cores (oracle/ restatement of
+    PPOcrDetectionPreprocessor + DBModel + CTCLabelDecode)."""
+    from oracle import ctc_ref, dbnet_ref
+
+    mean = np.array(MEAN, np.float32).reshape(1, 1, 3)
+    std = np.array(STD, np.float32).reshape(1, 1, 3)
+    for pg in sample_pages:
+        img = pg[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0)
+        img = (img - mean) / std
+        x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
+        dbnet_ref.dbnet_r18_forward(sd, x)
+    ctc_ref.ctc_greedy_ids(sample_probs)
+
+
+def time_cpu_baseline(n_pages: int, repeats: int = 1):
+    from pdf_table_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
+    pages = make_pages(0, n_pages)
+    probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
+    cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd)  # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_reference_step(pages, probs, sd)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_pages / best, cores, best
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    n_pages = 4
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from pdf_table_b200 import synth
+
+    sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
+    pages = make_pages(0, n_pages)
+    probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(pages, probs, sd)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n_pages / dt
+    sample = f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step (+{n_pages * CROPS_PER_PAGE} CTC crops), torch fp32 on host cores"
+    line = {
+        "impl": "reference", "metric": "pages_per_sec", "value": v, "unit": "pages/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": v, "unit": "pages/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {
+        "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
+        "stages": Cascade.stages,
+        "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
+        "rec_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities "
+                     "(recogniser network not yet on the engine)",
+        "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
+        "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
+        "parallelism": "page-sharded replicas, one process per GPU",
+    }
+
+
+# --------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = Cascade(rank, local_rank)
+    launches_per_step = wl.launches_per_step()
+
+    # ---- device-resident timing: K steps, each bracketed by events, L2 flushed in between (untimed)
+    for _ in range(args.warmup):
+        wl.step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        wl.flush_l2()
+        a.record()
+        wl.step_device()
+        b.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through host buffers
+    for _ in range(2):
+        wl.step_e2e()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        wl.step_e2e()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+
+    # ---- per-kernel device times (CUDA events on the launching stream, same steps, separate pass)
+    wl.det.profile_begin()
+    wl.post.profile_begin()
+    for _ in range(args.steps):
+        wl.flush_l2()
+        wl.step_device()
+    recs = wl.det.profile_report() + wl.post.profile_report()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the one collective of the path: all-gather of the packed decoded results (ids/len/conf)
+        ids, ln, conf = wl.step_device()
+        gathered = [torch.empty_like(ln) for _ in range(world)]
+        dist.all_gather(gathered, ln)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        total_pages = wl.n_pages * world * args.steps
+        value = total_pages / (dev_ms / 1e3)
+        e2e_v = total_pages / (e2e_ms / 1e3)
+        agg = {}
+        for r in recs:
+            k = agg.setdefault(r["kernel"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            k["ms"] += r["ms"]
+            k["flops"] += r["flops"]
+            k["bytes"] += r["bytes"]
+            k["n"] += 1
+        tot_ms = sum(k["ms"] for k in agg.values())
+        top = max(agg, key=lambda k: agg[k]["ms"])
+        tk = agg[top]
+        if tk["flops"] > 0:
+            ach = tk["flops"] / (tk["ms"] / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                    "launches": tk["n"], "avg_launch_ms": tk["ms"] / tk["n"], "share_of_step": tk["ms"] / tot_ms,
+                    "hbm_achieved_gbs": tk["bytes"] / (tk["ms"] / 1e3) / 1e9}
+        else:
+            ach = tk["bytes"] / (tk["ms"] / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "launches": tk["n"],
+                    "avg_launch_ms": tk["ms"] / tk["n"], "share_of_step": tk["ms"] / tot_ms}
+        kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["n"] / args.steps,
+                       "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
+                       "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores, secs = time_cpu_baseline(4)
+            cpu = {"value": v, "unit": "pages/s", "cores": cores, "kind": "port",
+                   "sample": f"4 of {PAGES_PER_GPU} pages (+{4 * CROPS_PER_PAGE} CTC crops), oracle/ restatement in torch fp32, {secs:.1f} s"}
+        line = {
+            "metric": "pages_per_sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(),
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_v, "unit": "pages/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
+                    "d2h_bytes_per_step": int(wl.d2h_bytes), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "kernels": kernels,
+            "crops_per_sec_ctc": wl.n_crops * world * args.steps / (dev_ms / 1e3),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,17 @@ int dv_sync(dv_handle h);
 long long dv_launch_count(dv_handle h);
 /* algorithmic FLOPs of one forward at the last planned shape (0 if none) */
 double dv_model_flops(dv_handle h);
+/*
+ * Per-launch device timing (bench.py "roofline"): between dv_profile_begin and dv_profile_report every
+ * kernel launched through the handle is bracketed by CUDA events on the handle's stream.
+ * dv_profile_report synchronises, stops profiling and writes a JSON array
+ *   [{"kernel": "...", "layer": "...", "ms": t, "flops": F, "bytes": B}, ...]   (one object per launch)
+ * into buf_host (capacity cap bytes, NUL-terminated).  Returns the number of bytes required (excluding
+ * the NUL; call again with a larger buffer if >= cap) or a negative dv_status.  No reference counterpart
+ * (the reference only wall-clocks whole stages, ocr_system_task.py:646-660).
+ */
+int dv_profile_begin(dv_handle h);
+long long dv_profile_report(dv_handle h, char* buf_host, size_t cap);
 
 /*
  * DBNet forward: fp32 NCHW pages -> fp32 probability map [N,1,H,W].

@@ -13,7 +13,8 @@ import tempfile
 import numpy as np
 import torch
 
-from . import ref_import, synth
+from . import ref_import
+from pdf_table_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 

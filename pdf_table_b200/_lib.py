@@ -25,6 +25,8 @@ SIGNATURES = {
     "dv_sync": (C.c_int, [C.c_void_p]),
     "dv_launch_count": (C.c_longlong, [C.c_void_p]),
     "dv_model_flops": (C.c_double, [C.c_void_p]),
+    "dv_profile_begin": (C.c_int, [C.c_void_p]),
+    "dv_profile_report": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "dv_dbnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dv_dbnet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]),

@@ -180,6 +180,45 @@ int dv_sync(dv_handle h) {
 
 long long dv_launch_count(dv_handle h) { return h ? h->launches : 0; }
 
+int dv_profile_begin(dv_handle h) {
+    if (!h) return DV_ERR_ARG;
+    for (auto& r : h->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+    h->profiling = true;
+    return 0;
+}
+
+long long dv_profile_report(dv_handle h, char* buf_host, size_t cap) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    h->profiling = false;
+    DV_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::string js = "[";
+    char line[512];
+    bool first = true;
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = -1.f;
+        snprintf(line, sizeof(line), "%s{\"kernel\": \"%s\", \"layer\": \"%s\", \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+                 first ? "" : ", ", r.kernel, r.layer.c_str(), ms, r.flops, r.bytes);
+        js += line;
+        first = false;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+    js += "]";
+    if (buf_host && cap > 0) {
+        const size_t n = js.size() < cap - 1 ? js.size() : cap - 1;
+        memcpy(buf_host, js.data(), n);
+        buf_host[n] = 0;
+    }
+    return static_cast<long long>(js.size());
+}
+
 double dv_model_flops(dv_handle h) {
     if (!h) return 0.0;
     if (h->kind == "dbnet_r18") return dbnet_flops(h);

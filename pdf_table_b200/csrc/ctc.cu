@@ -127,8 +127,10 @@ int ctc_greedy(Engine* e, const float* probs, int B, int T, int C, int blank, in
     if (!probs || !out_ids || !out_len || !out_conf || B < 0 || T <= 0 || C <= 0)
         return set_err(e, DV_ERR_ARG, "ctc_greedy: bad arguments");
     if (T > kMaxT) return set_err(e, DV_ERR_UNSUPPORTED, "ctc_greedy: T=%d > %d", T, kMaxT);
+    // algorithmic bytes: the [B,T,C] fp32 slab read once + ids/len/conf written once
+    e->launch_begin("k_ctc_greedy", "ctc", 0.0, 4.0 * B * T * C + 4.0 * B * T + 8.0 * B);
     k_ctc_greedy<<<B, 256, 0, e->stream>>>(probs, T, C, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }

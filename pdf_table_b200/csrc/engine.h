@@ -82,7 +82,16 @@ struct ConvPlan {
     int grid = 0;
     size_t smem = 0;
     double flops = 0;  // algorithmic 2*M*K*N (unpadded)
+    double bytes = 0;  // algorithmic HBM bytes: input once + output once + weights once (+ residual)
     std::string name;
+};
+
+// One profiled launch (dv_profile_begin / dv_profile_report): CUDA events on the launching stream.
+struct ProfRec {
+    const char* kernel;
+    std::string layer;
+    double flops, bytes;
+    cudaEvent_t a, b;
 };
 
 struct Model {
@@ -100,6 +109,22 @@ struct Engine {
     std::vector<void*> owned;  // device allocations freed at destroy
     std::unique_ptr<Model> model;
     long long launches = 0;  // kernels launched through this handle (bench "gpu_launches")
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+
+    // Bracket every kernel launch: counts it and, when profiling, records CUDA events around it.
+    void launch_begin(const char* kernel, const std::string& layer, double flops, double bytes) {
+        ++launches;
+        if (!profiling) return;
+        ProfRec r{kernel, layer, flops, bytes, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        prof.push_back(r);
+    }
+    void launch_end() {
+        if (profiling && !prof.empty()) cudaEventRecord(prof.back().b, stream);
+    }
 
     int dalloc(void** p, size_t bytes, bool zero = false);
     const BlobTensor* find(const std::string& name);

@@ -136,6 +136,15 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
                                e->stream));
     DV_CUDA(e, cudaStreamSynchronize(e->stream));
     p.kb_delta = reinterpret_cast<const int4*>(dtab);
+    {
+        // algorithmic HBM bytes: A once, W once, D once (fp16/fp32), residual once
+        const double m_rows = p.mode == A_FLAT ? (double)p.M : (double)p.Nimg * p.Ho * p.Wo;
+        double out_elems = m_rows * cs.Cout;
+        if (es.out_mode == OUT_REPL) out_elems *= (double)es.rep * es.rep;
+        plan->bytes += (double)ktot * cs.Cout * 2 + out_elems * (es.out_f32 ? 4 : 2);
+        if (es.res_mode == RES_SAME) plan->bytes += m_rows * cs.Cout * 2;
+        if (es.res_mode == RES_UP2) plan->bytes += m_rows * cs.Cout * 2 / 4;
+    }
     const int total = p.m_tiles * p.n_tiles;
     plan->grid = total < e->num_sms ? total : e->num_sms;
     plan->name = name;
@@ -145,6 +154,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
                 ConvPlan* plan, const char* name) {
     memset(&plan->prm, 0, sizeof(plan->prm));
+    plan->bytes = 0;
     IGemmParams& p = plan->prm;
     if (K % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: K %% 8 != 0", name);
     p.mode = A_FLAT;
@@ -169,6 +179,7 @@ int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, co
     std::vector<int4> deltas(num_kb);
     for (int kb = 0; kb < num_kb; ++kb) deltas[kb] = make_int4(kb * cs.BK, 0, 0, 0);
     plan->flops = 2.0 * M * K * cs.Cout;
+    plan->bytes = 2.0 * M * K;
     return finish_plan(e, plan, cs, es, num_kb, deltas, name);
 }
 
@@ -184,6 +195,7 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         return rc;
     }
     memset(&plan->prm, 0, sizeof(plan->prm));
+    plan->bytes = 0;
     IGemmParams& p = plan->prm;
     p.Nimg = in.N;
     p.Ho = Ho;
@@ -211,6 +223,7 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         num_kb = 7;
         for (int r = 0; r < 7; ++r) deltas.push_back(make_int4(0, 0, r, 0));
         plan->flops = 2.0 * in.N * Ho * Wo * 147.0 * cs.Cout;
+        plan->bytes = 2.0 * in.N * in.H * in.W * 4;
     } else {
         if (in.C != cs.Cin) return set_err(e, DV_ERR_ARG, "%s: Cin mismatch %d vs %d", name, in.C, cs.Cin);
         if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: Cin %% 8 != 0", name);
@@ -252,6 +265,7 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         }
         num_kb = static_cast<int>(deltas.size());
         plan->flops = 2.0 * in.N * Ho * Wo * (double)cs.KH * cs.KW * cs.Cin * cs.Cout;
+        plan->bytes = 2.0 * in.N * in.H * in.W * in.C;
     }
     return finish_plan(e, plan, cs, es, num_kb, deltas, name);
 }
@@ -292,8 +306,9 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
         return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
     IGemmKernel k = pick_kernel(plan.prm.act, plan.prm.out_f32);
     if (!k) return set_err(e, DV_ERR_ARG, "launch %s: bad activation %d", plan.name.c_str(), plan.prm.act);
+    e->launch_begin("conv_igemm_tcgen05", plan.name, plan.flops, plan.bytes);
     k<<<plan.grid, kIGemmThreads, plan.smem, e->stream>>>(plan.prm);
-    e->launches++;
+    e->launch_end();
     cudaError_t st = cudaGetLastError();
     if (st != cudaSuccess)
         return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));

@@ -27,8 +27,9 @@ __global__ void k_nchw_f32_to_stem(const float* __restrict__ in, int N, int H, i
 
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out) {
     const long long total = static_cast<long long>(N) * H * W;
+    e->launch_begin("k_nchw_f32_to_stem", "pre", 0.0, total * (12.0 + 8.0));
     k_nchw_f32_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, H, W, out);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
@@ -67,10 +68,11 @@ __global__ void k_u8_to_stem(const uint8_t* __restrict__ in, int N, int H, int W
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out) {
     const long long total = static_cast<long long>(N) * H * W;
+    e->launch_begin("k_u8_to_stem", "pre", 0.0, total * (3.0 + 8.0));
     k_u8_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(
         in, N, H, W, make_float3(mean3[0], mean3[1], mean3[2]), make_float3(std3[0], std3[1], std3[2]), scale,
         flip, out);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
@@ -115,8 +117,9 @@ __global__ void k_maxpool3x3s2(const __half* __restrict__ in, int N, int H, int 
 int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out) {
     if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "maxpool: C %% 8 != 0");
     const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    e->launch_begin("k_maxpool3x3s2", "maxpool", 0.0, 2.0 * (double)in.elems() + 2.0 * (double)out.N * out.H * out.W * in.C);
     k_maxpool3x3s2<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, out.H, out.W, out.p);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
@@ -166,8 +169,9 @@ __global__ void k_deconv2x2_c1_sigmoid(const __half* __restrict__ in, long long 
 int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, float bias, float* out) {
     if (in.C != 64) return set_err(e, DV_ERR_UNSUPPORTED, "deconv2x2_c1: C != 64");
     const long long npix = static_cast<long long>(in.N) * in.H * in.W;
+    e->launch_begin("k_deconv2x2_c1_sigmoid", "bin.deconv2", 2.0 * npix * 64 * 4, npix * (128.0 + 16.0));
     k_deconv2x2_c1_sigmoid<<<grid_for(npix, 128), 128, 0, e->stream>>>(in.p, npix, in.H, in.W, w, bias, out);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
@@ -201,15 +205,17 @@ __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int
 }
 int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out) {
     const long long total = static_cast<long long>(N) * C * H * W;
+    e->launch_begin("k_nchw_f32_to_nhwc_f16", "layout", 0.0, total * 6.0);
     k_nchw_f32_to_nhwc_f16<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
 int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out) {
     const long long total = static_cast<long long>(N) * C * H * W;
+    e->launch_begin("k_nhwc_f16_to_nchw_f32", "layout", 0.0, total * 6.0);
     k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out);
-    e->launches++;
+    e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }

@@ -65,6 +65,24 @@ class Engine:
     def model_flops(self) -> float:
         return float(self._lib.dv_model_flops(self._h))
 
+    def profile_begin(self):
+        """Start bracketing every launch with CUDA events (see dv_profile_begin)."""
+        check(self._lib.dv_profile_begin(self._h), self._h, "dv_profile_begin")
+
+    def profile_report(self):
+        """Stop profiling; list of {kernel, layer, ms, flops, bytes} per launch."""
+        import json
+
+        cap = 1 << 20
+        while True:
+            buf = C.create_string_buffer(cap)
+            n = int(self._lib.dv_profile_report(self._h, buf, cap))
+            if n < 0:
+                check(n, self._h, "dv_profile_report")
+            if n < cap:
+                return json.loads(buf.value.decode())
+            raise DocVisionError("profile report truncated; profile fewer launches per report")
+
     # ------------------------------------------------------------------ networks
     def dbnet_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 NCHW [N,3,H,W] (cuda) -> probability map fp32 [N,1,H,W]."""

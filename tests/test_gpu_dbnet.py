@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import dbnet_ref, synth
+from oracle import dbnet_ref
+from pdf_table_b200 import synth
 from pdf_table_b200 import weights
 from pdf_table_b200.engine import Engine
 

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ctc_ref, dbnet_ref, synth
+from oracle import ctc_ref, dbnet_ref
+from pdf_table_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

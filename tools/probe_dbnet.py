@@ -2,7 +2,7 @@
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
-from oracle import synth
+from pdf_table_b200 import synth
 from pdf_table_b200 import weights
 from pdf_table_b200.engine import Engine
 
