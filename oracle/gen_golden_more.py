@@ -1,0 +1,70 @@
+"""More reference-generated fixtures (build container only; see gen_golden.py)."""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from . import ref_import
+from pdf_table_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _ref_rec_processors():
+    """The reference's OCRRecognitionPreprocessor / PostProcessor with a stand-in config object (the real
+    configuration_ocr_recognition.py cannot be imported under transformers>=5)."""
+    ref_import.setup()
+    name = "pdftable.model.ocr_recognition.configuration_ocr_recognition"
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.OCRRecognitionConfig = type("OCRRecognitionConfig", (), {})
+        sys.modules[name] = m
+    from pdftable.model.ocr_recognition.processor_ocr_recognition import (OCRRecognitionPostProcessor,
+                                                                          OCRRecognitionPreprocessor)
+    return OCRRecognitionPreprocessor, OCRRecognitionPostProcessor
+
+
+def gen_convnextvit():
+    """Reference ConvNextViT (convnext_vit/modeling_convnext_vit.py:20) + its pre/post-processors on three
+    synthetic text-line crops (32x320, 32x200 and a 48x700 crop that exercises resize + all three chunks)."""
+    import cv2
+
+    Pre, Post = _ref_rec_processors()
+    cfg = types.SimpleNamespace(do_chunking=True, img_height=32, img_width=804)
+    pre = Pre(cfg)
+    crops = [synth.synthetic_text_crop(0, 32, 320), synth.synthetic_text_crop(1, 32, 200),
+             cv2.resize(np.tile(synth.synthetic_text_crop(2, 32, 320), (1, 2, 1)), (700, 48))]
+    chunks = pre(crops)["image"]
+    model = ref_import.convnext_vit()
+    sd = synth.convnext_vit_state_dict(0)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    with torch.no_grad():
+        feats = model.cnn_model(chunks[:, 0:1] * 0.2989 + chunks[:, 1:2] * 0.5870 + chunks[:, 2:3] * 0.1140).last_hidden_state
+        logits = model(chunks).logits
+    # post-processor semantics: emulate its loop without a vocab file (label_mapping is an id -> char dict)
+    post = Post.__new__(Post)
+    post.label_mapping = {i: chr(0x4E00 + i) for i in range(1, 7644)}
+    preds = post(logits)["preds"]
+    ids = [[ord(ch) - 0x4E00 for ch in s] for s in preds]
+    out = {
+        "n_crops": np.int32(len(crops)),
+        "chunks_sum": chunks.double().sum(dim=(1, 2, 3)).numpy(),
+        "chunk0": chunks[0].numpy(),
+        "feats0": feats[0].numpy().astype(np.float32),                   # chunk 0 of [9,512,1,75]
+        "feats_abs_sum": feats.abs().double().sum(dim=(1, 2, 3)).numpy(),
+        "logits_sub": logits[:, :, ::32].numpy().astype(np.float32),     # every 32nd class
+        "logits_max": logits.max(-1).values.numpy().astype(np.float32),
+        "argmax": logits.argmax(-1).numpy().astype(np.int32),
+    }
+    for i, (c, row) in enumerate(zip(crops, ids)):
+        out[f"crop{i}"] = c
+        out[f"ids{i}"] = np.array(row, np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "convnextvit_seed0.npz"), **out)
+    print("convnextvit_seed0", logits.shape, [len(r) for r in ids], float(logits.abs().max()))
+
+
+GENERATORS = {"convnextvit": gen_convnextvit}

@@ -103,3 +103,77 @@ def synthetic_text_crop(index: int, h: int = 32, w: int = 320) -> np.ndarray:
     cv2.putText(img, s, (4, int(h * 0.75)), cv2.FONT_HERSHEY_SIMPLEX, h / 40.0, (col, col, col), 1, cv2.LINE_AA)
     noise = rng.normal(0, 2, img.shape)
     return np.clip(img.astype(np.float32) + noise, 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------- ConvNextViT
+CONVNEXT_DEPTHS = (3, 3, 8, 3)
+CONVNEXT_DIMS = (96, 192, 256, 512)
+VIT_LAYERS, VIT_DIM, VIT_HEADS, VIT_MLP, VIT_TOKENS, VIT_LABELS = 12, 192, 3, 768, 75, 7644
+
+
+def _lin(rng, cout, cin, gain=1.0):
+    return (rng.standard_normal((cout, cin)) * np.sqrt(gain / cin)).astype(np.float32)
+
+
+def _ln(rng, sd, prefix, c):
+    sd[prefix + ".weight"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    sd[prefix + ".bias"] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+
+
+def _b(rng, c, s=0.1):
+    return (rng.standard_normal(c) * s).astype(np.float32)
+
+
+def convnext_vit_state_dict(seed: int = 0, num_labels: int = VIT_LABELS) -> "OrderedDict[str, np.ndarray]":
+    """Keys / shapes of the reference ConvNextViT (model/convnext_vit/modeling_convnext_vit.py:20-45:
+    ConvNeXt depths [3,3,8,3] dims [96,192,256,512] on 1 channel, (2,1) down-sampling; ViT 12 x 192 x 3 heads
+    over 75 tokens; classifier 192 -> 7644).  layer_scale is drawn O(0.1..0.5) (its 1e-6 init would hide
+    every block); unused parameters (cls_token, cnn_model.layernorm, position 0) are still drawn so the
+    dict loads strictly into the reference module."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    p = "cnn_model.embeddings"
+    sd[p + ".patch_embeddings.weight"] = _conv(rng, 96, 1, 4, 4, gain=1.0)
+    sd[p + ".patch_embeddings.bias"] = _b(rng, 96)
+    _ln(rng, sd, p + ".layernorm", 96)
+    prev = CONVNEXT_DIMS[0]
+    for s, (depth, dim) in enumerate(zip(CONVNEXT_DEPTHS, CONVNEXT_DIMS)):
+        sp = f"cnn_model.encoder.stages.{s}"
+        if s > 0:
+            _ln(rng, sd, sp + ".downsampling_layer.0", prev)
+            sd[sp + ".downsampling_layer.1.weight"] = _conv(rng, dim, prev, 2, 1, gain=1.0)
+            sd[sp + ".downsampling_layer.1.bias"] = _b(rng, dim)
+        for j in range(depth):
+            lp = f"{sp}.layers.{j}"
+            sd[lp + ".layer_scale_parameter"] = rng.uniform(0.1, 0.5, dim).astype(np.float32)
+            sd[lp + ".dwconv.weight"] = _conv(rng, dim, 1, 7, 7, gain=1.0)
+            sd[lp + ".dwconv.bias"] = _b(rng, dim)
+            _ln(rng, sd, lp + ".layernorm", dim)
+            sd[lp + ".pwconv1.weight"] = _lin(rng, 4 * dim, dim, gain=2.0)
+            sd[lp + ".pwconv1.bias"] = _b(rng, 4 * dim)
+            sd[lp + ".pwconv2.weight"] = _lin(rng, dim, 4 * dim)
+            sd[lp + ".pwconv2.bias"] = _b(rng, dim)
+        prev = dim
+    _ln(rng, sd, "cnn_model.layernorm", 512)
+    v = "vitstr.vit"
+    sd[v + ".embeddings.cls_token"] = _b(rng, VIT_DIM, 0.02).reshape(1, 1, VIT_DIM)
+    sd[v + ".embeddings.position_embeddings"] = _b(rng, (VIT_TOKENS + 1) * VIT_DIM, 0.2).reshape(1, VIT_TOKENS + 1, VIT_DIM)
+    sd[v + ".embeddings.patch_embeddings.projection.weight"] = _conv(rng, VIT_DIM, 512, 1, 1, gain=1.0)
+    sd[v + ".embeddings.patch_embeddings.projection.bias"] = _b(rng, VIT_DIM)
+    for L in range(VIT_LAYERS):
+        lp = f"{v}.encoder.layer.{L}"
+        for n in ("query", "key", "value"):
+            sd[f"{lp}.attention.attention.{n}.weight"] = _lin(rng, VIT_DIM, VIT_DIM)
+            sd[f"{lp}.attention.attention.{n}.bias"] = _b(rng, VIT_DIM)
+        sd[lp + ".attention.output.dense.weight"] = _lin(rng, VIT_DIM, VIT_DIM, gain=0.5)
+        sd[lp + ".attention.output.dense.bias"] = _b(rng, VIT_DIM)
+        sd[lp + ".intermediate.dense.weight"] = _lin(rng, VIT_MLP, VIT_DIM, gain=2.0)
+        sd[lp + ".intermediate.dense.bias"] = _b(rng, VIT_MLP)
+        sd[lp + ".output.dense.weight"] = _lin(rng, VIT_DIM, VIT_MLP, gain=0.5)
+        sd[lp + ".output.dense.bias"] = _b(rng, VIT_DIM)
+        _ln(rng, sd, lp + ".layernorm_before", VIT_DIM)
+        _ln(rng, sd, lp + ".layernorm_after", VIT_DIM)
+    _ln(rng, sd, v + ".layernorm", VIT_DIM)
+    sd["vitstr.classifier.weight"] = _lin(rng, num_labels, VIT_DIM, gain=4.0)
+    sd["vitstr.classifier.bias"] = _b(rng, num_labels)
+    return sd

@@ -62,3 +62,24 @@ def test_weight_packer_layouts():
     np.testing.assert_array_equal(db[:32], np.tile(np.arange(8, dtype=np.float32), 4))
     blob = weights.pack_dbnet_r18(synth.dbnet_r18_state_dict(0))
     assert blob[:8] == b"DVWBLOB1" and len(blob) > 20_000_000
+
+
+def test_convnextvit_oracle_matches_reference_golden():
+    from oracle import convnextvit_ref
+
+    g = np.load(os.path.join(GOLDEN, "convnextvit_seed0.npz"))
+    n = int(g["n_crops"])
+    crops = [g[f"crop{i}"] for i in range(n)]
+    chunks = convnextvit_ref.preprocess(crops)
+    np.testing.assert_array_equal(chunks[0].numpy(), g["chunk0"])
+    np.testing.assert_allclose(chunks.double().sum(dim=(1, 2, 3)).numpy(), g["chunks_sum"], rtol=0, atol=1e-9)
+    sd = synth.convnext_vit_state_dict(0)
+    feats = convnextvit_ref.convnext_features(sd, chunks)
+    np.testing.assert_allclose(feats[0].numpy(), g["feats0"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(feats.abs().double().sum(dim=(1, 2, 3)).numpy(), g["feats_abs_sum"], rtol=1e-5)
+    logits = convnextvit_ref.convnextvit_forward(sd, chunks)
+    np.testing.assert_allclose(logits[:, :, ::32].numpy(), g["logits_sub"], atol=5e-5, rtol=0)
+    np.testing.assert_array_equal(logits.argmax(-1).numpy(), g["argmax"])
+    ids = convnextvit_ref.greedy_ids(logits)
+    for i in range(n):
+        np.testing.assert_array_equal(ids[i], g[f"ids{i}"])
