@@ -107,6 +107,31 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
                   int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max);
 
 /*
+ * ConvNextViT text-line recogniser forward.
+ * Replaces OcrRecognitionTask._run_model for model="ConvNextViT" (ocr_recognition_task.py:81-116) =
+ * OCRRecognition.forward (ocr_recognition/modeling_ocr_recognition.py:137-149) -> ConvNextViT.forward
+ * (convnext_vit/modeling_convnext_vit.py:37-45), fused with the arg-max of OCRRecognitionPostProcessor
+ * (ocr_recognition/processor_ocr_recognition.py:147-151; softmax is monotone, so arg-max of the logits).
+ *   chunks_nchw_f32 : [3*n_crops, 3, 32, 300] fp32 in [0,1], the output of OCRRecognitionPreprocessor (:73-115)
+ *   logits_out      : [n_crops, 201, L] fp32 or NULL (parity dump; L = dv_convnextvit_labels)
+ *   ids_out         : [n_crops, 201] int32 per-token arg-max (torch.argmax: first maximum)
+ *   max_out         : [n_crops, 201] fp32 maximum logit or NULL
+ */
+int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
+                           int32_t* ids_out, float* max_out);
+int dv_convnextvit_labels(dv_handle h);
+/* crops per internal pass (default 96): sizes the activation workspace so the widest tensor stays near L2 */
+int dv_convnextvit_set_pass_crops(dv_handle h, int crops);
+/*
+ * Collapse per-step arg-max ids: keep[t] = ids[t] != blank && (t == 0 || ids[t] != ids[t-1]).
+ * Replaces the loop of OCRRecognitionPostProcessor.__call__ (processor_ocr_recognition.py:152-162) and, given
+ * scores, the confidence of BaseRecLabelDecode.decode (ocr_rec_pp/rec_postprocess.py:126-161).
+ * Outputs as dv_ctc_greedy; scores may be NULL (out_conf = 0).
+ */
+int dv_ctc_collapse(dv_handle h, const int32_t* ids, const float* scores, int b, int t, int blank,
+                    int32_t* out_ids, int32_t* out_len, float* out_conf);
+
+/*
  * Operator-level entry used by the parity tests of the tensor-core convolution kernel:
  * NHWC fp16 convolution (stride 1 or 2, square kernel, zero padding) with fused bias, optional residual
  * add and activation.  weight_packed: fp16 [cout][kh*kw*cin_pad] (see weights.pack_conv), bias: fp32

@@ -25,6 +25,12 @@ def _t(sd, k):
     return v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))
 
 
+def to_torch(sd: Mapping, device="cpu", dtype=torch.float32):
+    """state_dict as torch tensors on `device` in `dtype` (dtype=torch.float16 on CUDA reproduces the reference's
+    own default inference precision, DeployUtils.model_eval utils/deploy_utils.py:226-240)."""
+    return {k: _t(sd, k).to(device=device, dtype=dtype) for k in sd}
+
+
 def _ln_cf(x, sd, p, eps):
     """LayerNorm over channels of an NCHW tensor (ConvNextLayerNorm channels_first)."""
     x = x.permute(0, 2, 3, 1)
@@ -35,7 +41,7 @@ def _ln_cf(x, sd, p, eps):
 @torch.no_grad()
 def convnext_features(sd: Mapping, chunks: torch.Tensor) -> torch.Tensor:
     """chunks fp32 [B,3,32,300] in [0,1] -> last_hidden_state [B,512,1,75]."""
-    x = chunks.float()
+    x = chunks.to(_t(sd, "cnn_model.embeddings.patch_embeddings.weight").dtype)
     x = x[:, 0:1] * 0.2989 + x[:, 1:2] * 0.5870 + x[:, 2:3] * 0.1140
     p = "cnn_model.embeddings"
     x = F.conv2d(x, _t(sd, p + ".patch_embeddings.weight"), _t(sd, p + ".patch_embeddings.bias"), stride=4)

@@ -142,6 +142,8 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
         if (e->kind == "post") {
         } else if (e->kind == "dbnet_r18") {
             rc = dbnet_create(e);
+        } else if (e->kind == "convnext_vit") {
+            rc = cnv_create(e);
         } else {
             rc = set_err(e, DV_ERR_UNSUPPORTED, "dv_create: unknown model kind '%s'", model_kind);
         }
@@ -222,6 +224,7 @@ long long dv_profile_report(dv_handle h, char* buf_host, size_t cap) {
 double dv_model_flops(dv_handle h) {
     if (!h) return 0.0;
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
+    if (h->kind == "convnext_vit") return cnv_flops(h);
     return 0.0;
 }
 
@@ -252,6 +255,27 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
     if (!h) return DV_ERR_ARG;
     cudaSetDevice(h->device);
     return ctc_greedy(h, probs, b, t, c, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
+}
+
+int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
+                           int32_t* ids_out, float* max_out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return cnv_forward(h, chunks_nchw_f32, n_crops, logits_out, ids_out, max_out);
+}
+
+int dv_convnextvit_labels(dv_handle h) { return h ? cnv_labels(h) : 0; }
+
+int dv_convnextvit_set_pass_crops(dv_handle h, int crops) {
+    if (!h) return DV_ERR_ARG;
+    return cnv_set_pass_crops(h, crops);
+}
+
+int dv_ctc_collapse(dv_handle h, const int32_t* ids, const float* scores, int b, int t, int blank,
+                    int32_t* out_ids, int32_t* out_len, float* out_conf) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return ctc_collapse(h, ids, scores, b, t, blank, out_ids, out_len, out_conf);
 }
 
 int dv_conv2d_nhwc_f16(dv_handle h, const void* in_nhwc_f16, int n, int height, int width, int cin,

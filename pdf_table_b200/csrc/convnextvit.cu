@@ -1,0 +1,372 @@
+// ConvNextViT text-line recogniser (BASELINE config 4) as a static plan of launches.
+// Architecture restated from the reference: ConvNextViT.forward convnext_vit/modeling_convnext_vit.py:37-45,
+// ConvNextEncoder modeling_convnext.py:28-80 (depths [3,3,8,3], dims [96,192,256,512], (2,1) down-sampling),
+// ViTForSTR.forward_features / forward modeling_vit.py:32-180 (1x1 patch projection, + position_embeddings[:,1:],
+// 12 pre-LN layers, final LN, 3x75 -> 201 stitch, 192 -> 7644 classifier).
+//
+// Data layout: tokens x channels, row-major.  The residual stream is fp32; every GEMM operand is fp16 and every
+// pointwise / attention GEMM runs on conv_igemm_tcgen05 in A_FLAT mode (fp32 TMEM accumulation).  layer_scale
+// is folded into pwconv2, 1/sqrt(64) into the query projection (weights.py).  The classifier's logits are never
+// written to HBM unless the caller asks for them: its epilogue keeps a running arg-max per row.
+//
+// Crops are processed in passes of `pass_crops` (default 96 = 288 chunks) so the widest intermediate (the 4C
+// hidden tensor, 288 x 600 x 384 fp16 = 133 MB at stage 0, less later) stays close to the 126 MB L2 between
+// the GEMM that writes it and the GEMM that reads it.
+#include <stdlib.h>
+
+#include "engine.h"
+
+namespace dv {
+
+int op_cnv_patchify_ln(Engine* e, const float* chunks, int B, const float* w, const float* bias, const float* lnw,
+                       const float* lnb, float* out);
+int op_dwconv7_ln(Engine* e, const float* x, int B, int H, int C, const float* w, const float* b, const float* lnw,
+                  const float* lnb, __half* out, const char* layer);
+int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* lnw, const float* lnb, float eps,
+               int normalise, int map, int H, __half* out, const char* layer);
+int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer);
+
+namespace {
+
+constexpr int kDepths[4] = {3, 3, 8, 3};
+constexpr int kDims[4] = {96, 192, 256, 512};
+constexpr int kVitLayers = 12, kVitDim = 192, kVitMlp = 768, kTok = 75, kStitched = 201;
+
+struct Step {
+    enum Kind { PATCHIFY, DWLN, LN, GEMM, ATTN } kind;
+    ConvPlan plan;            // GEMM
+    const float *w = nullptr, *b = nullptr, *lnw = nullptr, *lnb = nullptr;
+    const float* fin = nullptr;  // fp32 input
+    __half* hout = nullptr;
+    float* fout = nullptr;
+    const __half* hin = nullptr;
+    long long rows = 0;
+    int C = 0, H = 0, map = 0, normalise = 1;
+    float eps = 1e-6f;
+    std::string name;
+};
+
+struct Pass {
+    Engine* e = nullptr;
+    int crops = 0, B = 0;
+    std::vector<void*> mem;
+    std::vector<Step> steps;
+    int cls_step = -1;
+    double flops = 0;
+    float* stage_in = nullptr;  // not owned: set per call
+    ~Pass() {
+        for (void* p : mem) cudaFree(p);
+    }
+    int alloc(void** p, size_t bytes) {
+        cudaError_t st = cudaMalloc(p, bytes ? bytes : 16);
+        if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(st));
+        mem.push_back(*p);
+        return 0;
+    }
+};
+
+struct CnvModel : Model {
+    int labels = 0;
+    int pass_crops = 96;
+    std::map<int, std::unique_ptr<Pass>> passes;
+    double last_flops = 0;
+};
+
+const float* f32(Engine* e, const std::string& name, size_t min_elems, int* rc) {
+    const BlobTensor* t = e->find(name);
+    if (!t || t->dtype != 0 || t->nbytes < min_elems * 4) {
+        *rc = set_err(e, DV_ERR_WEIGHTS, "missing / short fp32 tensor '%s'", name.c_str());
+        return nullptr;
+    }
+    return reinterpret_cast<const float*>(t->dptr);
+}
+
+int get_linear(Engine* e, const std::string& name, int K, int N, ConvSpec* cs) {
+    const BlobTensor* w = e->find(name + ".w");
+    const BlobTensor* b = e->find(name + ".b");
+    if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2)
+        return set_err(e, DV_ERR_WEIGHTS, "missing weights for '%s'", name.c_str());
+    if (static_cast<int>(w->dims[0]) != N || static_cast<int>(w->dims[1]) != K)
+        return set_err(e, DV_ERR_WEIGHTS, "'%s': weight [%u,%u] != [%d,%d]", name.c_str(), w->dims[0], w->dims[1], N, K);
+    if (b->dims[0] < static_cast<uint32_t>((N + 255) / 256 * 256))
+        return set_err(e, DV_ERR_WEIGHTS, "'%s': bias not padded to 256", name.c_str());
+    cs->KH = cs->KW = 1;
+    cs->Cin = K;
+    cs->Cin_pad = K;
+    cs->Cout = N;
+    cs->BK = (K % 64 == 0) ? 64 : (K % 32 == 0) ? 32 : 16;
+    cs->w = reinterpret_cast<const __half*>(w->dptr);
+    cs->bias = reinterpret_cast<const float*>(b->dptr);
+    cs->flat = true;
+    return 0;
+}
+
+int add_gemm(Engine* e, Pass* ps, const std::string& name, const __half* A, long long M, int K, int N, const EpiSpec& es) {
+    ConvSpec cs;
+    DV_TRY(get_linear(e, name, K, N, &cs));
+    Step st;
+    st.kind = Step::GEMM;
+    st.name = name;
+    DV_TRY(plan_linear(e, A, static_cast<int>(M), K, cs, es, &st.plan, st.name.c_str()));
+    // plan_linear allocated its delta table through the engine; move ownership to the pass
+    ps->mem.push_back(e->owned.back());
+    e->owned.pop_back();
+    ps->flops += st.plan.flops;
+    ps->steps.push_back(st);
+    return 0;
+}
+
+EpiSpec epi_f16(__half* out, int ld, int act) {
+    EpiSpec es;
+    es.out = out;
+    es.out_ld = ld;
+    es.act = act;
+    return es;
+}
+// fp32 stream update: out = res + gemm (res may alias out)
+EpiSpec epi_stream(float* out, int ld, const float* res, int res_mod = 0) {
+    EpiSpec es;
+    es.out = out;
+    es.out_ld = ld;
+    es.out_f32 = 1;
+    if (res) {
+        es.res = res;
+        es.res_mode = RES_SAME;
+        es.res_ld = ld;
+        es.res_f32 = 1;
+        es.res_mod = res_mod;
+    }
+    return es;
+}
+
+int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
+    ps->e = e;
+    ps->crops = crops;
+    const int B = ps->B = crops * 3;
+    const long long unit = 57600LL * B;  // tokens x channels of the widest stream tensor (600 x 96 per chunk)
+    float *xa, *xb, *xv;
+    __half *h, *h2, *g;
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&xa), unit * 4));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&xb), unit * 4));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&xv), static_cast<size_t>(B) * kTok * kVitDim * 4));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h), unit * 2));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h2), static_cast<size_t>(B) * kTok * kVitDim * 2));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&g), unit * 4 * 2));
+    int rc = 0;
+    {
+        Step st;
+        st.kind = Step::PATCHIFY;
+        st.name = "patchify";
+        st.w = f32(e, "patch.w", 16 * 96, &rc);
+        st.b = f32(e, "patch.b", 96, &rc);
+        st.lnw = f32(e, "patch.ln.w", 96, &rc);
+        st.lnb = f32(e, "patch.ln.b", 96, &rc);
+        st.fout = xa;
+        if (rc) return rc;
+        ps->steps.push_back(st);
+        ps->flops += 2.0 * 16 * 96 * 600 * B;
+    }
+    float* x = xa;
+    float* xo = xb;
+    int H = 8, blk = 0;
+    for (int s = 0; s < 4; ++s) {
+        const int C = kDims[s];
+        if (s > 0) {
+            const int Cp = kDims[s - 1];
+            const std::string ds = "ds" + std::to_string(s);
+            Step st;
+            st.kind = Step::LN;
+            st.name = ds + ".ln";
+            st.fin = x;
+            st.rows = static_cast<long long>(B) * H * kTok;
+            st.C = Cp;
+            st.H = H;
+            st.map = 1;
+            st.lnw = f32(e, ds + ".ln.w", Cp, &rc);
+            st.lnb = f32(e, ds + ".ln.b", Cp, &rc);
+            st.hout = h;
+            if (rc) return rc;
+            ps->steps.push_back(st);
+            H /= 2;
+            DV_TRY(add_gemm(e, ps, ds + ".conv", h, static_cast<long long>(B) * H * kTok, 2 * Cp, C, epi_stream(xo, C, nullptr)));
+            std::swap(x, xo);
+        }
+        const long long rows = static_cast<long long>(B) * H * kTok;
+        for (int j = 0; j < kDepths[s]; ++j, ++blk) {
+            const std::string bp = "blk" + std::to_string(blk);
+            Step st;
+            st.kind = Step::DWLN;
+            st.name = bp + ".dw";
+            st.fin = x;
+            st.C = C;
+            st.H = H;
+            st.w = f32(e, bp + ".dw.w", 49 * C, &rc);
+            st.b = f32(e, bp + ".dw.b", C, &rc);
+            st.lnw = f32(e, bp + ".ln.w", C, &rc);
+            st.lnb = f32(e, bp + ".ln.b", C, &rc);
+            st.hout = h;
+            if (rc) return rc;
+            ps->steps.push_back(st);
+            ps->flops += 2.0 * 49 * rows * C;
+            DV_TRY(add_gemm(e, ps, bp + ".pw1", h, rows, C, 4 * C, epi_f16(g, 4 * C, ACT_GELU)));
+            DV_TRY(add_gemm(e, ps, bp + ".pw2", g, rows, 4 * C, C, epi_stream(x, C, x)));
+        }
+    }
+    // ---- ViT: features [B,1,75,512] -> cast -> 1x1 projection + position embeddings
+    const long long T = static_cast<long long>(B) * kTok;
+    {
+        Step st;
+        st.kind = Step::LN;
+        st.name = "vit.cast";
+        st.fin = x;
+        st.rows = T;
+        st.C = 512;
+        st.normalise = 0;
+        st.hout = h;
+        ps->steps.push_back(st);
+        const float* pos = f32(e, "vit.pos", kTok * kVitDim, &rc);
+        if (rc) return rc;
+        DV_TRY(add_gemm(e, ps, "vit.proj", h, T, 512, kVitDim, epi_stream(xv, kVitDim, pos, kTok)));
+    }
+    for (int L = 0; L < kVitLayers; ++L) {
+        const std::string lp = "vit" + std::to_string(L);
+        Step ln1;
+        ln1.kind = Step::LN;
+        ln1.name = lp + ".ln1";
+        ln1.fin = xv;
+        ln1.rows = T;
+        ln1.C = kVitDim;
+        ln1.eps = 1e-12f;
+        ln1.lnw = f32(e, lp + ".ln1.w", kVitDim, &rc);
+        ln1.lnb = f32(e, lp + ".ln1.b", kVitDim, &rc);
+        ln1.hout = h;
+        if (rc) return rc;
+        ps->steps.push_back(ln1);
+        DV_TRY(add_gemm(e, ps, lp + ".qkv", h, T, kVitDim, 3 * kVitDim, epi_f16(g, 3 * kVitDim, ACT_NONE)));
+        Step at;
+        at.kind = Step::ATTN;
+        at.name = lp + ".attn";
+        at.hin = g;
+        at.hout = h2;
+        ps->steps.push_back(at);
+        ps->flops += 4.0 * kTok * kTok * kVitDim * B;
+        DV_TRY(add_gemm(e, ps, lp + ".proj", h2, T, kVitDim, kVitDim, epi_stream(xv, kVitDim, xv)));
+        Step ln2 = ln1;
+        ln2.name = lp + ".ln2";
+        ln2.lnw = f32(e, lp + ".ln2.w", kVitDim, &rc);
+        ln2.lnb = f32(e, lp + ".ln2.b", kVitDim, &rc);
+        if (rc) return rc;
+        ps->steps.push_back(ln2);
+        DV_TRY(add_gemm(e, ps, lp + ".fc1", h, T, kVitDim, kVitMlp, epi_f16(g, kVitMlp, ACT_GELU)));
+        DV_TRY(add_gemm(e, ps, lp + ".fc2", g, T, kVitMlp, kVitDim, epi_stream(xv, kVitDim, xv)));
+    }
+    {
+        Step st;
+        st.kind = Step::LN;
+        st.name = "vit.ln+stitch";
+        st.fin = xv;
+        st.rows = T;
+        st.C = kVitDim;
+        st.eps = 1e-12f;
+        st.map = 2;
+        st.lnw = f32(e, "vit.ln.w", kVitDim, &rc);
+        st.lnb = f32(e, "vit.ln.b", kVitDim, &rc);
+        st.hout = h;
+        if (rc) return rc;
+        ps->steps.push_back(st);
+        EpiSpec es;
+        es.out = nullptr;  // patched per call (logits dump) together with arg_out / max_out
+        es.out_ld = m->labels;
+        es.out_f32 = 1;
+        es.arg_out = reinterpret_cast<int32_t*>(g);  // placeholder, patched per call
+        DV_TRY(add_gemm(e, ps, "cls", h, static_cast<long long>(crops) * kStitched, kVitDim, m->labels, es));
+        ps->cls_step = static_cast<int>(ps->steps.size()) - 1;
+    }
+    return 0;
+}
+
+int run_pass(Engine* e, Pass* ps, const float* chunks, float* logits, int32_t* ids, float* maxv) {
+    for (size_t i = 0; i < ps->steps.size(); ++i) {
+        Step& st = ps->steps[i];
+        switch (st.kind) {
+            case Step::PATCHIFY: DV_TRY(op_cnv_patchify_ln(e, chunks, ps->B, st.w, st.b, st.lnw, st.lnb, st.fout)); break;
+            case Step::DWLN:
+                DV_TRY(op_dwconv7_ln(e, st.fin, ps->B, st.H, st.C, st.w, st.b, st.lnw, st.lnb, st.hout, st.name.c_str()));
+                break;
+            case Step::LN:
+                DV_TRY(op_ln_rows(e, st.fin, st.rows, st.C, st.lnw, st.lnb, st.eps, st.normalise, st.map, st.H, st.hout,
+                                  st.name.c_str()));
+                break;
+            case Step::ATTN: DV_TRY(op_attn75(e, st.hin, ps->B, st.hout, st.name.c_str())); break;
+            case Step::GEMM:
+                if (static_cast<int>(i) == ps->cls_step) {
+                    st.plan.prm.out = logits;
+                    st.plan.prm.arg_out = ids;
+                    st.plan.prm.max_out = maxv;
+                }
+                DV_TRY(launch_conv(e, st.plan));
+                break;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+int cnv_create(Engine* e) {
+    auto* m = new CnvModel();
+    e->model.reset(m);
+    const BlobTensor* w = e->find("cls.w");
+    if (!w || w->ndim != 2) return set_err(e, DV_ERR_WEIGHTS, "convnext_vit: missing classifier weights");
+    m->labels = static_cast<int>(w->dims[0]);
+    if (m->labels % 4) return set_err(e, DV_ERR_UNSUPPORTED, "convnext_vit: num_labels %% 4 != 0");
+    if (const char* s = getenv("DV_REC_PASS_CROPS")) {
+        const int v = atoi(s);
+        if (v > 0) m->pass_crops = v;
+    }
+    return 0;
+}
+
+int cnv_set_pass_crops(Engine* e, int crops) {
+    CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
+    if (!m) return set_err(e, DV_ERR_STATE, "not a convnext_vit handle");
+    if (crops <= 0) return set_err(e, DV_ERR_ARG, "pass_crops must be positive");
+    m->pass_crops = crops;
+    return 0;
+}
+
+int cnv_labels(Engine* e) {
+    CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
+    return m ? m->labels : 0;
+}
+
+double cnv_flops(Engine* e) {
+    CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
+    return m ? m->last_flops : 0.0;
+}
+
+int cnv_forward(Engine* e, const float* chunks, int n_crops, float* logits, int32_t* ids, float* maxv) {
+    CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
+    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a convnext_vit model");
+    if (n_crops < 0 || (n_crops > 0 && (!chunks || !ids))) return set_err(e, DV_ERR_ARG, "convnextvit_forward: bad arguments");
+    m->last_flops = 0;
+    for (int done = 0; done < n_crops;) {
+        const int cur = (n_crops - done) < m->pass_crops ? (n_crops - done) : m->pass_crops;
+        auto it = m->passes.find(cur);
+        if (it == m->passes.end()) {
+            if (m->passes.size() >= 4) m->passes.clear();  // bound the plan cache (each pass owns its buffers)
+            std::unique_ptr<Pass> ps(new Pass());
+            DV_TRY(build_pass(e, m, ps.get(), cur));
+            it = m->passes.emplace(cur, std::move(ps)).first;
+        }
+        Pass* ps = it->second.get();
+        DV_TRY(run_pass(e, ps, chunks + static_cast<long long>(done) * 3 * 3 * 32 * 300,
+                        logits ? logits + static_cast<long long>(done) * kStitched * m->labels : nullptr,
+                        ids + static_cast<long long>(done) * kStitched, maxv ? maxv + static_cast<long long>(done) * kStitched : nullptr));
+        m->last_flops += ps->flops;
+        done += cur;
+    }
+    return 0;
+}
+
+}  // namespace dv

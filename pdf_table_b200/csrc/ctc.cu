@@ -51,6 +51,35 @@ __device__ float np_pairwise_sum(const float* a, int n) {
     }
 }
 
+// Second phase, one warp: keep[t] = id[t] != blank && (t == 0 || id[t] != id[t-1]); left-pack with ballots.
+__device__ void collapse_write(const int* s_id, const float* s_p, float* s_kept, int T, int blank, int b, int lane,
+                               int32_t* __restrict__ out_ids, int32_t* __restrict__ out_len,
+                               float* __restrict__ out_conf) {
+    int count = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        int id = 0;
+        if (t < T) {
+            id = s_id[t];
+            keep = (id != blank) && (t == 0 || id != s_id[t - 1]);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = count + __popc(mask & ((1u << lane) - 1u));
+            out_ids[static_cast<long long>(b) * T + pos] = id;
+            s_kept[pos] = s_p[t];
+        }
+        count += __popc(mask);
+    }
+    for (int t = count + lane; t < T; t += 32) out_ids[static_cast<long long>(b) * T + t] = -1;
+    __syncwarp();
+    if (lane == 0) {
+        out_len[b] = count;
+        out_conf[b] = count > 0 ? __fdiv_rn(np_pairwise_sum(s_kept, count), static_cast<float>(count)) : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_ctc_greedy(const float* __restrict__ probs, int T, int C, int blank, int32_t* __restrict__ out_ids,
              int32_t* __restrict__ out_len, float* __restrict__ out_conf, int32_t* __restrict__ raw_ids,
@@ -94,29 +123,28 @@ k_ctc_greedy(const float* __restrict__ probs, int T, int C, int blank, int32_t* 
     }
     __syncthreads();
     if (warp != 0) return;
-    int count = 0;
-    for (int t0 = 0; t0 < T; t0 += 32) {
-        const int t = t0 + lane;
-        bool keep = false;
-        int id = 0;
-        if (t < T) {
-            id = s_id[t];
-            keep = (id != blank) && (t == 0 || id != s_id[t - 1]);
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int pos = count + __popc(mask & ((1u << lane) - 1u));
-            out_ids[static_cast<long long>(b) * T + pos] = id;
-            s_kept[pos] = s_p[t];
-        }
-        count += __popc(mask);
+    collapse_write(s_id, s_p, s_kept, T, blank, b, lane, out_ids, out_len, out_conf);
+}
+
+
+// Collapse of precomputed per-step arg-max ids (the classifier's fused arg-max epilogue already reduced
+// over the class axis).  Follows OCRRecognitionPostProcessor.__call__ (ocr_recognition/
+// processor_ocr_recognition.py:152-162: `if p != last_p and p != 0`, last_p starting at 0), which is the CTC
+// rule with blank = 0.  scores may be NULL (then out_conf = 0 for every row: the reference returns no
+// confidence on this path).
+__global__ void __launch_bounds__(32)
+k_collapse_ids(const int32_t* __restrict__ ids, const float* __restrict__ scores, int T, int blank,
+               int32_t* __restrict__ out_ids, int32_t* __restrict__ out_len, float* __restrict__ out_conf) {
+    __shared__ int s_id[kMaxT];
+    __shared__ float s_p[kMaxT];
+    __shared__ float s_kept[kMaxT];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    for (int t = lane; t < T; t += 32) {
+        s_id[t] = ids[static_cast<long long>(b) * T + t];
+        s_p[t] = scores ? scores[static_cast<long long>(b) * T + t] : 0.f;
     }
-    for (int t = count + lane; t < T; t += 32) out_ids[static_cast<long long>(b) * T + t] = -1;
     __syncwarp();
-    if (lane == 0) {
-        out_len[b] = count;
-        out_conf[b] = count > 0 ? __fdiv_rn(np_pairwise_sum(s_kept, count), static_cast<float>(count)) : 0.f;
-    }
+    collapse_write(s_id, s_p, s_kept, T, blank, b, lane, out_ids, out_len, out_conf);
 }
 
 }  // namespace
@@ -130,6 +158,18 @@ int ctc_greedy(Engine* e, const float* probs, int B, int T, int C, int blank, in
     // algorithmic bytes: the [B,T,C] fp32 slab read once + ids/len/conf written once
     e->launch_begin("k_ctc_greedy", "ctc", 0.0, 4.0 * B * T * C + 4.0 * B * T + 8.0 * B);
     k_ctc_greedy<<<B, 256, 0, e->stream>>>(probs, T, C, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,
+                 int32_t* out_len, float* out_conf) {
+    if (B == 0) return 0;
+    if (!ids || !out_ids || !out_len || !out_conf || B < 0 || T <= 0) return set_err(e, DV_ERR_ARG, "ctc_collapse: bad arguments");
+    if (T > kMaxT) return set_err(e, DV_ERR_UNSUPPORTED, "ctc_collapse: T=%d > %d", T, kMaxT);
+    e->launch_begin("k_collapse_ids", "collapse", 0.0, (scores ? 8.0 : 4.0) * B * T + 4.0 * B * T + 8.0 * B);
+    k_collapse_ids<<<B, 32, 0, e->stream>>>(ids, scores, T, blank, out_ids, out_len, out_conf);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

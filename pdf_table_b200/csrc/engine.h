@@ -69,8 +69,11 @@ struct ConvSpec {
 };
 
 struct EpiSpec {
-    const __half* res = nullptr;
+    const void* res = nullptr;  // fp16, or fp32 when res_f32
     int res_mode = RES_NONE, res_ld = 0;
+    int res_f32 = 0, res_mod = 0;
+    int32_t* arg_out = nullptr;  // classifier arg-max epilogue (see igemm.cuh ARGMAX)
+    float* max_out = nullptr;
     int act = ACT_NONE;
     int out_mode = OUT_NHWC;
     void* out = nullptr;
@@ -83,6 +86,7 @@ struct ConvPlan {
     size_t smem = 0;
     double flops = 0;  // algorithmic 2*M*K*N (unpadded)
     double bytes = 0;  // algorithmic HBM bytes: input once + output once + weights once (+ residual)
+    int res_f32 = 0;
     std::string name;
 };
 
@@ -153,7 +157,16 @@ int dbnet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const f
 double dbnet_flops(Engine* e);
 int dbnet_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4);
 
+// convnextvit.cu
+int cnv_create(Engine* e);
+int cnv_forward(Engine* e, const float* chunks, int n_crops, float* logits, int32_t* ids, float* maxv);
+int cnv_set_pass_crops(Engine* e, int crops);
+int cnv_labels(Engine* e);
+double cnv_flops(Engine* e);
+
 // ctc.cu
+int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,
+                 int32_t* out_len, float* out_conf);
 int ctc_greedy(Engine* e, const float* probs, int B, int T, int C, int blank, int32_t* out_ids,
                int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max);
 

@@ -37,7 +37,30 @@ __device__ __forceinline__ float apply_act(float x) {
 // of 8 (fp16 out) / 4 (fp32 out), so the epilogue only ever issues 16-byte vector accesses, predicated
 // per vector on the channel bound.  Keeping the epilogue this small matters: it is executed by only four
 // warps and an earlier, fully generic version was instruction-fetch bound (profiles/r1_notes.md).
-template <int ACT, bool OUT_F32>
+// Tile scheduler shared by the three roles.  Default: tiles are dealt round-robin (tile = m_tile * n_tiles +
+// n_tile).  n_inner (classifier arg-max epilogue): a CTA owns whole m-tiles and walks all their n-tiles, so
+// one epilogue thread sees every column of its row.
+struct TileIter {
+    int j = 0;
+    __device__ __forceinline__ bool next(const IGemmParams& p, int& m_tile, int& n_tile) {
+        if (p.n_inner) {
+            const int q = j / p.n_tiles;
+            m_tile = blockIdx.x + q * gridDim.x;
+            n_tile = j - q * p.n_tiles;
+        } else {
+            const int tile = blockIdx.x + j * gridDim.x;
+            m_tile = tile / p.n_tiles;
+            n_tile = tile - m_tile * p.n_tiles;
+        }
+        ++j;
+        return m_tile < p.m_tiles;
+    }
+};
+
+// ACT: activation; OUT_F32: fp32 (else fp16) output; RES_F32: the residual operand is fp32 (the fp32
+// residual stream of the ConvNeXt / ViT blocks, updated in place); ARGMAX: classifier epilogue that keeps a
+// running (max, arg-max) per row over all n-tiles and writes ids instead of (optionally besides) logits.
+template <int ACT, bool OUT_F32, bool RES_F32, bool ARGMAX>
 __global__ void __launch_bounds__(kIGemmThreads, 1)
 conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -56,7 +79,6 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const uint32_t b_bytes = static_cast<uint32_t>(p.BLOCK_N) * row_bytes;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int num_stages = p.num_stages;
-    const int total_tiles = p.m_tiles * p.n_tiles;
     const int num_kb = p.num_kb;
 
     for (int i = threadIdx.x; i < num_kb; i += kIGemmThreads) s_delta[i] = __ldg(&p.kb_delta[i]);
@@ -89,10 +111,10 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             uint32_t phase = 0;
             const int tiles_per_img = p.tiles_x * p.tiles_y;
             const int mode = p.mode;
-            const int BK = p.BK, BLOCK_N = p.BLOCK_N, n_tiles = p.n_tiles;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / n_tiles;
-                const int n_tile = tile - m_tile * n_tiles;
+            const int BK = p.BK, BLOCK_N = p.BLOCK_N;
+            TileIter it;
+            int m_tile, n_tile;
+            while (it.next(p, m_tile, n_tile)) {
                 int img = 0, y0 = 0, x0 = 0;
                 if (mode != A_FLAT) {
                     img = m_tile / tiles_per_img;
@@ -132,7 +154,9 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             uint32_t acc_phase = 0;
             const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
             const int k_steps = p.BK >> 4;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            TileIter it;
+            int m_tile, n_tile;
+            while (it.next(p, m_tile, n_tile)) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
@@ -162,15 +186,17 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         int acc = 0;
         uint32_t acc_phase = 0;
         const int tiles_per_img = p.tiles_x * p.tiles_y;
-        const int mode = p.mode, n_tiles = p.n_tiles, BLOCK_N = p.BLOCK_N, Cout = p.Cout;
+        const int mode = p.mode, BLOCK_N = p.BLOCK_N, Cout = p.Cout;
         const int Ho = p.Ho, Wo = p.Wo, TW = p.TW, TH = p.TH, tiles_x = p.tiles_x;
         const int out_mode = p.out_mode, out_ld = p.out_ld, out_coff = p.out_coff, rep = p.rep;
         const int res_mode = p.res_mode, res_ld = p.res_ld;
         const float* __restrict__ bias = p.bias;
-        const __half* __restrict__ res = p.res;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / n_tiles;
-            const int n_tile = tile - m_tile * n_tiles;
+        const __half* __restrict__ res = reinterpret_cast<const __half*>(p.res);
+        TileIter it;
+        int m_tile, n_tile;
+        float best_v = -INFINITY;
+        int best_i = 0;
+        while (it.next(p, m_tile, n_tile)) {
             // ---- which output pixel does this thread own?
             int img, y, x;
             bool valid;
@@ -196,6 +222,13 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             long long res_pix = pix;
             if (res_mode == RES_UP2)
                 res_pix = (static_cast<long long>(img) * (Ho >> 1) + (y >> 1)) * (Wo >> 1) + (x >> 1);
+            if (p.res_mod > 0) res_pix = pix % p.res_mod;  // broadcast rows (position embeddings)
+            if constexpr (ARGMAX) {
+                if (n_tile == 0) {
+                    best_v = -INFINITY;
+                    best_i = 0;
+                }
+            }
 
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
             ptx::tc_fence_after();
@@ -223,7 +256,22 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         f[4 * j + 3] += b.w;
                     }
                 }
-                if (res_mode != RES_NONE) {
+                if constexpr (RES_F32) {
+                    if (res_mode != RES_NONE) {
+                        const float4* rp =
+                            reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + res_pix * res_ld + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j * 4 < ncol) {
+                                const float4 u = rp[j];
+                                f[4 * j] += u.x;
+                                f[4 * j + 1] += u.y;
+                                f[4 * j + 2] += u.z;
+                                f[4 * j + 3] += u.w;
+                            }
+                        }
+                    }
+                } else if (res_mode != RES_NONE) {
                     const uint4* rp = reinterpret_cast<const uint4*>(res + res_pix * res_ld + col0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -241,6 +289,17 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
+                if constexpr (ARGMAX) {
+                    // torch.argmax semantics: first maximum wins (columns are visited in ascending order)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < ncol && f[j] > best_v) {
+                            best_v = f[j];
+                            best_i = col0 + j;
+                        }
+                    }
+                    if (p.out == nullptr) continue;
+                }
                 // ---- store
                 int reps = 1;
                 long long opix0 = pix;
@@ -287,6 +346,12 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                             for (int j = 0; j < 4; ++j)
                                 if (j * 8 < ncol) op[j] = o[j];
                         }
+                }
+            }
+            if constexpr (ARGMAX) {
+                if (n_tile == p.n_tiles - 1 && valid) {
+                    p.arg_out[pix] = best_i;
+                    if (p.max_out != nullptr) p.max_out[pix] = best_v;
                 }
             }
             ptx::tc_fence_before();

@@ -104,6 +104,14 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.res = es.res;
     p.res_mode = es.res_mode;
     p.res_ld = es.res_ld;
+    p.res_mod = es.res_mod;
+    p.arg_out = es.arg_out;
+    p.max_out = es.max_out;
+    p.n_inner = es.arg_out != nullptr ? 1 : 0;
+    plan->res_f32 = es.res_f32;
+    if (es.arg_out != nullptr && !es.out_f32) return set_err(e, DV_ERR_ARG, "%s: arg-max epilogue needs out_f32", name);
+    if (es.res_f32 && es.res_mode != RES_NONE && (es.res_ld % 4))
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: fp32 residual needs res_ld %% 4 == 0", name);
     p.act = es.act;
     p.out_mode = es.out_mode;
     p.out = es.out;
@@ -117,6 +125,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
         if ((cs.Cout % al) || (es.out_ld % al) || (es.out_coff % al) || (es.res_mode != RES_NONE && (es.res_ld % 8)))
             return set_err(e, DV_ERR_UNSUPPORTED,
                            "%s: Cout/out_ld/out_coff must be multiples of %d and res_ld of 8 (pad channels)", name, al);
+        if (es.out == nullptr && es.arg_out == nullptr) return set_err(e, DV_ERR_ARG, "%s: no output", name);
         if ((reinterpret_cast<uintptr_t>(es.out) & 15) || (reinterpret_cast<uintptr_t>(es.res) & 15))
             return set_err(e, DV_ERR_ARG, "%s: out/res pointers must be 16-byte aligned", name);
     }
@@ -142,10 +151,11 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
         double out_elems = m_rows * cs.Cout;
         if (es.out_mode == OUT_REPL) out_elems *= (double)es.rep * es.rep;
         plan->bytes += (double)ktot * cs.Cout * 2 + out_elems * (es.out_f32 ? 4 : 2);
-        if (es.res_mode == RES_SAME) plan->bytes += m_rows * cs.Cout * 2;
+        if (es.arg_out != nullptr) plan->bytes += m_rows * 8 - (es.out == nullptr ? out_elems * 4 : 0);
+        if (es.res_mode == RES_SAME) plan->bytes += (es.res_mod > 0 ? (double)es.res_mod : m_rows) * cs.Cout * (es.res_f32 ? 4 : 2);
         if (es.res_mode == RES_UP2) plan->bytes += m_rows * cs.Cout * 2 / 4;
     }
-    const int total = p.m_tiles * p.n_tiles;
+    const int total = p.n_inner ? p.m_tiles : p.m_tiles * p.n_tiles;
     plan->grid = total < e->num_sms ? total : e->num_sms;
     plan->name = name;
     return 0;
@@ -272,23 +282,22 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
 
 typedef void (*IGemmKernel)(const IGemmParams);
 
-template <int ACT, bool F32>
-static IGemmKernel kernel_entry() {
-    return conv_igemm_tcgen05<ACT, F32>;
-}
-
-static IGemmKernel pick_kernel(int act, int out_f32) {
+// Instantiated epilogue variants: every activation x {fp16, fp32} output with an fp16 (or no) residual,
+// plus the two fp32-stream specials (fp32 residual updated in place; classifier arg-max).
+static IGemmKernel pick_kernel(int act, int out_f32, int res_f32, int argmax) {
+    if (argmax) return (act == ACT_NONE && !res_f32) ? conv_igemm_tcgen05<ACT_NONE, true, false, true> : nullptr;
+    if (res_f32) return (act == ACT_NONE && out_f32) ? conv_igemm_tcgen05<ACT_NONE, true, true, false> : nullptr;
     switch (act * 2 + (out_f32 ? 1 : 0)) {
-        case ACT_NONE * 2: return kernel_entry<ACT_NONE, false>();
-        case ACT_NONE * 2 + 1: return kernel_entry<ACT_NONE, true>();
-        case ACT_RELU * 2: return kernel_entry<ACT_RELU, false>();
-        case ACT_RELU * 2 + 1: return kernel_entry<ACT_RELU, true>();
-        case ACT_GELU * 2: return kernel_entry<ACT_GELU, false>();
-        case ACT_GELU * 2 + 1: return kernel_entry<ACT_GELU, true>();
-        case ACT_SIGMOID * 2: return kernel_entry<ACT_SIGMOID, false>();
-        case ACT_SIGMOID * 2 + 1: return kernel_entry<ACT_SIGMOID, true>();
-        case ACT_HSWISH * 2: return kernel_entry<ACT_HSWISH, false>();
-        case ACT_HSWISH * 2 + 1: return kernel_entry<ACT_HSWISH, true>();
+        case ACT_NONE * 2: return conv_igemm_tcgen05<ACT_NONE, false, false, false>;
+        case ACT_NONE * 2 + 1: return conv_igemm_tcgen05<ACT_NONE, true, false, false>;
+        case ACT_RELU * 2: return conv_igemm_tcgen05<ACT_RELU, false, false, false>;
+        case ACT_RELU * 2 + 1: return conv_igemm_tcgen05<ACT_RELU, true, false, false>;
+        case ACT_GELU * 2: return conv_igemm_tcgen05<ACT_GELU, false, false, false>;
+        case ACT_GELU * 2 + 1: return conv_igemm_tcgen05<ACT_GELU, true, false, false>;
+        case ACT_SIGMOID * 2: return conv_igemm_tcgen05<ACT_SIGMOID, false, false, false>;
+        case ACT_SIGMOID * 2 + 1: return conv_igemm_tcgen05<ACT_SIGMOID, true, false, false>;
+        case ACT_HSWISH * 2: return conv_igemm_tcgen05<ACT_HSWISH, false, false, false>;
+        case ACT_HSWISH * 2 + 1: return conv_igemm_tcgen05<ACT_HSWISH, true, false, false>;
         default: return nullptr;
     }
 }
@@ -297,15 +306,22 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
     static std::once_flag once;
     static cudaError_t attr_rc = cudaSuccess;
     std::call_once(once, [] {
-        for (int act = 0; act <= ACT_HSWISH && attr_rc == cudaSuccess; ++act)
-            for (int f = 0; f < 2 && attr_rc == cudaSuccess; ++f)
-                attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_kernel(act, f)),
+        auto set = [&](IGemmKernel k) {
+            if (attr_rc == cudaSuccess)
+                attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        };
+        for (int act = 0; act <= ACT_HSWISH; ++act)
+            for (int f = 0; f < 2; ++f) set(pick_kernel(act, f, 0, 0));
+        set(pick_kernel(ACT_NONE, 1, 1, 0));
+        set(pick_kernel(ACT_NONE, 1, 0, 1));
     });
     if (attr_rc != cudaSuccess)
         return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
-    IGemmKernel k = pick_kernel(plan.prm.act, plan.prm.out_f32);
-    if (!k) return set_err(e, DV_ERR_ARG, "launch %s: bad activation %d", plan.name.c_str(), plan.prm.act);
+    IGemmKernel k = pick_kernel(plan.prm.act, plan.prm.out_f32, plan.res_f32, plan.prm.arg_out != nullptr);
+    if (!k)
+        return set_err(e, DV_ERR_ARG, "launch %s: unsupported epilogue (act %d, out_f32 %d, res_f32 %d, argmax %d)",
+                       plan.name.c_str(), plan.prm.act, plan.prm.out_f32, plan.res_f32, plan.prm.arg_out != nullptr);
     e->launch_begin("conv_igemm_tcgen05", plan.name, plan.flops, plan.bytes);
     k<<<plan.grid, kIGemmThreads, plan.smem, e->stream>>>(plan.prm);
     e->launch_end();

@@ -30,8 +30,12 @@ struct IGemmParams {
     int m_tiles, n_tiles, BLOCK_N, Cout;
     // epilogue
     const float* bias;  // padded to n_tiles*BLOCK_N, or nullptr
-    const __half* res;
+    const void* res;  // fp16 (or fp32 when the kernel is instantiated with RES_F32)
     int res_mode, res_ld;
+    int res_mod;      // > 0: residual row = output row % res_mod (broadcast table, e.g. position embeddings)
+    int n_inner;      // tile order: a CTA walks all n-tiles of its m-tiles (required by the arg-max epilogue)
+    int32_t* arg_out;  // ARGMAX epilogue: per-row arg-max over all Cout columns
+    float* max_out;    // ARGMAX epilogue: per-row maximum (may be null)
     int act;
     int out_mode, out_ld, out_coff, rep, out_f32;
     void* out;

@@ -1,0 +1,385 @@
+// Non-GEMM kernels of the ConvNextViT text-line recogniser:
+//   k_cnv_patchify_ln  RGB->gray + 4x4 s4 patchify conv (1->96) + LayerNorm      (HF ConvNextEmbeddings)
+//   k_dwconv7_ln       depthwise 7x7 + bias + LayerNorm(eps 1e-6), fp32 stream -> fp16 GEMM operand
+//   k_ln_rows          row LayerNorm / cast with the (2,1) down-sampling re-layout and the 3x75->201 stitch
+//   k_attn75           softmax(QK^T)V for the 75-token ViT (3 heads x 64), one CTA per chunk
+// Reference: convnext_vit/modeling_convnext_vit.py:37-45, modeling_convnext.py:28-80, modeling_vit.py:32-180 and the
+// HF blocks they instantiate (ConvNextLayer: dwconv -> LN -> pwconv1 -> GELU -> pwconv2 -> layer_scale -> +res).
+// The residual stream stays fp32 in HBM (it is only C floats per token; the 4C-wide hidden tensors are fp16).
+#include "engine.h"
+
+namespace dv {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chunks fp32 NCHW [B,3,32,300] in [0,1]  ->  x fp32 [B,8,75,96]
+// gray = R*0.2989 + G*0.5870 + B*0.1140 (modeling_convnext_vit.py:40), conv 4x4 stride 4, LN eps 1e-6.
+__global__ void __launch_bounds__(256)
+k_cnv_patchify_ln(const float* __restrict__ in, int B, const float* __restrict__ w /*[16][96]*/,
+                  const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                  float* __restrict__ out) {
+    __shared__ float sw[16 * 96];
+    for (int i = threadIdx.x; i < 16 * 96; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long pix = static_cast<long long>(blockIdx.x) * 8 + warp;
+    if (pix >= static_cast<long long>(B) * 600) return;
+    const int b = static_cast<int>(pix / 600);
+    const int r = static_cast<int>(pix - static_cast<long long>(b) * 600);
+    const int py = r / 75, px = r - py * 75;
+    float g = 0.f;
+    if (lane < 16) {
+        const int iy = py * 4 + (lane >> 2), ix = px * 4 + (lane & 3);
+        const float* ip = in + (static_cast<long long>(b) * 3 * 32 + iy) * 300 + ix;
+        // same evaluation order as the reference expression: (R*a + G*b) + B*c, no FMA contraction
+        g = __fadd_rn(__fadd_rn(__fmul_rn(ip[0], 0.2989f), __fmul_rn(ip[32 * 300], 0.5870f)),
+                      __fmul_rn(ip[2 * 32 * 300], 0.1140f));
+    }
+    float acc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[j] = bias[lane + 32 * j];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float gk = __shfl_sync(0xffffffffu, g, k);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] = fmaf(gk, sw[k * 96 + lane + 32 * j], acc[j]);
+    }
+    const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.f / 96.f);
+    float d0 = acc[0] - mean, d1 = acc[1] - mean, d2 = acc[2] - mean;
+    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.f / 96.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    float* op = out + pix * 96;
+    op[lane] = d0 * rstd * lnw[lane] + lnb[lane];
+    op[lane + 32] = d1 * rstd * lnw[lane + 32] + lnb[lane + 32];
+    op[lane + 64] = d2 * rstd * lnw[lane + 64] + lnb[lane + 64];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 7x7 (pad 3) + bias + LayerNorm over C.  x fp32 [B,H,75,C] -> h fp16 [B,H,75,C].
+// One CTA = one chunk b, one strip of kStrip output columns, all H rows.  The (H x (kStrip+6) x C) input
+// tile is staged once in shared memory; thread (y, c) produces the kStrip outputs of its row with a
+// register-blocked sliding window (each staged value feeds up to 7 outputs), then the tile memory is
+// re-used to exchange the conv outputs for the per-pixel LayerNorm done by whole warps.
+constexpr int kStrip = 15;  // 75 = 5 strips
+constexpr int kTileW = kStrip + 6;
+
+template <int C, int H>
+__global__ void __launch_bounds__(C* H)
+k_dwconv7_ln(const float* __restrict__ x, const float* __restrict__ w /*[49][C]*/, const float* __restrict__ bias,
+             const float* __restrict__ lnw, const float* __restrict__ lnb, __half* __restrict__ out) {
+    extern __shared__ float tile[];  // [H][kTileW][C]
+    const int b = blockIdx.x / 5;
+    const int x0 = (blockIdx.x - b * 5) * kStrip;
+    const int tid = threadIdx.x;
+    const float* xb = x + static_cast<long long>(b) * H * 75 * C;
+    // ---- stage (zero-filled outside the image); C % 4 == 0 -> float4
+    constexpr int C4 = C / 4;
+    for (int i = tid; i < H * kTileW * C4; i += C * H) {
+        const int c4 = i % C4;
+        const int col = (i / C4) % kTileW;
+        const int row = i / (C4 * kTileW);
+        const int gx = x0 - 3 + col;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < 75) v = *reinterpret_cast<const float4*>(xb + (static_cast<long long>(row) * 75 + gx) * C + c4 * 4);
+        *reinterpret_cast<float4*>(tile + (static_cast<long long>(row) * kTileW + col) * C + c4 * 4) = v;
+    }
+    __syncthreads();
+    const int c = tid % C;
+    const int y = tid / C;
+    float acc[kStrip];
+    const float bv = bias[c];
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) acc[i] = bv;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int iy = y + r - 3;
+        if (iy < 0 || iy >= H) continue;  // zero padding rows
+        float wr[7];
+#pragma unroll
+        for (int s = 0; s < 7; ++s) wr[s] = __ldg(w + (r * 7 + s) * C + c);
+        const float* trow = tile + static_cast<long long>(iy) * kTileW * C + c;
+#pragma unroll
+        for (int col = 0; col < kTileW; ++col) {
+            const float v = trow[col * C];
+#pragma unroll
+            for (int s = 0; s < 7; ++s) {
+                const int o = col - s;  // output column fed by tile column `col` through tap s
+                if (o >= 0 && o < kStrip) acc[o] = fmaf(v, wr[s], acc[o]);
+            }
+        }
+    }
+    __syncthreads();  // everyone is done reading the tile -> reuse it as [H][kStrip][C] conv outputs
+#pragma unroll
+    for (int i = 0; i < kStrip; ++i) tile[(static_cast<long long>(y) * kStrip + i) * C + c] = acc[i];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = C * H / 32;
+    constexpr int CPL = C / 32;
+    for (int p = warp; p < H * kStrip; p += NW) {
+        const float* tp = tile + static_cast<long long>(p) * C;
+        float v[CPL];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            v[j] = tp[lane + 32 * j];
+            s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            v[j] -= mean;
+            q += v[j] * v[j];
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-6f);
+        const int py = p / kStrip, pxs = p - py * kStrip;
+        __half* op = out + ((static_cast<long long>(b) * H + py) * 75 + x0 + pxs) * C;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int cc = lane + 32 * j;
+            op[cc] = __float2half_rn(v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm (or plain cast) fp32 [rows, C] -> fp16 with an output row mapping:
+//   LN_IDENT  out row = in row
+//   LN_DOWN   in [B,H,75,C] -> out [B,H/2,75,2C]: the (2,1)/(2,1) down-sampling conv becomes a flat GEMM with
+//             K = 2C (kernel row p = y&1 selects the half)           (modeling_convnext.py:44-53)
+//   LN_STITCH in [3n,75,C] -> out [n,201,C]: chunk0[0:69] | chunk1[6:69] | chunk2[6:75]  (modeling_vit.py:135-139)
+enum { LN_IDENT = 0, LN_DOWN = 1, LN_STITCH = 2 };
+
+template <int C>
+__global__ void __launch_bounds__(256)
+k_ln_rows(const float* __restrict__ in, long long rows, const float* __restrict__ lnw, const float* __restrict__ lnb,
+          float eps, int normalise, int map, int H, __half* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+    if (row >= rows) return;
+    long long orow = row;
+    int ocoff = 0, old = C;
+    if (map == LN_DOWN) {
+        const int xq = static_cast<int>(row % 75);
+        const long long by = row / 75;  // b*H + y
+        const int y = static_cast<int>(by % H);
+        const long long bb = by / H;
+        orow = (bb * (H / 2) + (y >> 1)) * 75 + xq;
+        ocoff = (y & 1) * C;
+        old = 2 * C;
+    } else if (map == LN_STITCH) {
+        const int t = static_cast<int>(row % 75);
+        const long long chunk = row / 75;
+        const int k = static_cast<int>(chunk % 3);
+        const long long n = chunk / 3;
+        int pos;
+        if (k == 0) {
+            if (t >= 69) return;
+            pos = t;
+        } else if (k == 1) {
+            if (t < 6 || t >= 69) return;
+            pos = 69 + t - 6;
+        } else {
+            if (t < 6) return;
+            pos = 132 + t - 6;
+        }
+        orow = n * 201 + pos;
+    }
+    constexpr int CPL = C / 32;
+    const float* ip = in + row * C;
+    float v[CPL];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        v[j] = ip[lane + 32 * j];
+        s += v[j];
+    }
+    __half* op = out + orow * old + ocoff;
+    if (normalise) {
+        const float mean = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            v[j] -= mean;
+            q += v[j] * v[j];
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const int cc = lane + 32 * j;
+            op[cc] = __float2half_rn(v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) op[lane + 32 * j] = __float2half_rn(v[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT self-attention over the 75 tokens of one chunk: qkv fp16 [B*75, 576] (q|k|v, head-major 3 x 64; the
+// 1/sqrt(64) scale is folded into the packed q weights) -> ctx fp16 [B*75, 192].
+// One CTA per chunk, 3 warp-triples of 96 threads = one (head, query) per thread; K and V of all heads are
+// staged in shared memory as fp32, scores live in a thread-private shared column.
+constexpr int kAttnThreads = 288;
+constexpr int kAttnSmem = (2 * 75 * 192 + 75 * kAttnThreads) * 4;
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
+    extern __shared__ float sm[];
+    float* sK = sm;                 // [75][192]
+    float* sV = sm + 75 * 192;      // [75][192]
+    float* sS = sm + 2 * 75 * 192;  // [75][288]
+    const int b = blockIdx.x;
+    const __half* base = qkv + static_cast<long long>(b) * 75 * 576;
+    for (int i = threadIdx.x; i < 75 * 48; i += kAttnThreads) {  // 48 x 8 halves = K|V of one token
+        const int t = i / 48, c8 = i - t * 48;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + t * 576 + 192 + c8 * 8));
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        float* dst = (c8 < 24 ? sK + t * 192 + c8 * 8 : sV + t * 192 + (c8 - 24) * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            dst[2 * e] = f.x;
+            dst[2 * e + 1] = f.y;
+        }
+    }
+    __syncthreads();
+    const int head = threadIdx.x / 96;
+    const int qi = threadIdx.x - head * 96;
+    if (qi >= 75) return;
+    float q[64];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(base + qi * 576 + head * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 u = __ldg(qp + i);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                q[i * 8 + 2 * e] = f.x;
+                q[i * 8 + 2 * e + 1] = f.y;
+            }
+        }
+    }
+    float* myS = sS + threadIdx.x;
+    float mx = -INFINITY;
+    for (int j = 0; j < 75; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(sK + j * 192 + head * 64);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const float4 k4 = kp[d];
+            a0 = fmaf(q[4 * d], k4.x, a0);
+            a1 = fmaf(q[4 * d + 1], k4.y, a1);
+            a2 = fmaf(q[4 * d + 2], k4.z, a2);
+            a3 = fmaf(q[4 * d + 3], k4.w, a3);
+        }
+        const float s = (a0 + a1) + (a2 + a3);
+        myS[j * kAttnThreads] = s;
+        mx = fmaxf(mx, s);
+    }
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+    float denom = 0.f;
+    for (int j = 0; j < 75; ++j) {
+        const float pj = expf(myS[j * kAttnThreads] - mx);
+        denom += pj;
+        const float4* vp = reinterpret_cast<const float4*>(sV + j * 192 + head * 64);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const float4 v4 = vp[d];
+            o[4 * d] = fmaf(pj, v4.x, o[4 * d]);
+            o[4 * d + 1] = fmaf(pj, v4.y, o[4 * d + 1]);
+            o[4 * d + 2] = fmaf(pj, v4.z, o[4 * d + 2]);
+            o[4 * d + 3] = fmaf(pj, v4.w, o[4 * d + 3]);
+        }
+    }
+    const float inv = 1.f / denom;
+    uint4* op = reinterpret_cast<uint4*>(ctx + (static_cast<long long>(b) * 75 + qi) * 192 + head * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[i * 8 + 2 * e] * inv, o[i * 8 + 2 * e + 1] * inv);
+        op[i] = u;
+    }
+}
+
+template <int C, int H>
+int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, const float* lnw, const float* lnb,
+              __half* out, const char* layer) {
+    const size_t smem = static_cast<size_t>(H) * kTileW * C * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DV_CUDA(e, cudaFuncSetAttribute(k_dwconv7_ln<C, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_done = true;
+    }
+    const double elems = static_cast<double>(B) * H * 75 * C;
+    e->launch_begin("k_dwconv7_ln", layer, 2.0 * 49 * elems, elems * (4 + 2));
+    k_dwconv7_ln<C, H><<<B * 5, C * H, smem, e->stream>>>(x, w, b, lnw, lnb, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int op_cnv_patchify_ln(Engine* e, const float* chunks, int B, const float* w, const float* bias, const float* lnw,
+                       const float* lnb, float* out) {
+    const long long pix = static_cast<long long>(B) * 600;
+    e->launch_begin("k_cnv_patchify_ln", "patchify", 2.0 * 16 * 96 * pix, static_cast<double>(B) * 3 * 32 * 300 * 4 + pix * 96.0 * 4);
+    k_cnv_patchify_ln<<<static_cast<int>((pix + 7) / 8), 256, 0, e->stream>>>(chunks, B, w, bias, lnw, lnb, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int op_dwconv7_ln(Engine* e, const float* x, int B, int H, int C, const float* w, const float* b, const float* lnw,
+                  const float* lnb, __half* out, const char* layer) {
+    if (C == 96 && H == 8) return launch_dw<96, 8>(e, x, B, w, b, lnw, lnb, out, layer);
+    if (C == 192 && H == 4) return launch_dw<192, 4>(e, x, B, w, b, lnw, lnb, out, layer);
+    if (C == 256 && H == 2) return launch_dw<256, 2>(e, x, B, w, b, lnw, lnb, out, layer);
+    if (C == 512 && H == 1) return launch_dw<512, 1>(e, x, B, w, b, lnw, lnb, out, layer);
+    return set_err(e, DV_ERR_UNSUPPORTED, "dwconv7_ln: unsupported (C=%d, H=%d)", C, H);
+}
+
+int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* lnw, const float* lnb, float eps,
+               int normalise, int map, int H, __half* out, const char* layer) {
+    const int grid = static_cast<int>((rows + 7) / 8);
+    e->launch_begin("k_ln_rows", layer, 0.0, static_cast<double>(rows) * C * 6);
+    switch (C) {
+        case 96: k_ln_rows<96><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
+        case 192: k_ln_rows<192><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
+        case 256: k_ln_rows<256><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
+        case 512: k_ln_rows<512><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
+        default: e->launch_end(); return set_err(e, DV_ERR_UNSUPPORTED, "ln_rows: C=%d", C);
+    }
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        DV_CUDA(e, cudaFuncSetAttribute(k_attn75, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        attr_done = true;
+    }
+    e->launch_begin("k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
+    k_attn75<<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dv

@@ -110,6 +110,45 @@ class Engine:
               self._h, "dv_dbnet_forward_u8")
         return out
 
+    def convnextvit_forward(self, chunks: torch.Tensor, return_logits: bool = False, return_max: bool = False):
+        """fp32 [3n,3,32,300] (cuda, in [0,1]) -> per-token arg-max ids int32 [n,201] (+ logits fp32 [n,201,L],
+        + max logit [n,201])."""
+        chunks = _require_cuda(chunks, torch.float32, "chunks")
+        b3, c, hh, ww = chunks.shape
+        if (c, hh, ww) != (3, 32, 300) or b3 % 3:
+            raise ValueError("chunks must be [3n,3,32,300]")
+        n = b3 // 3
+        dev = chunks.device
+        labels = int(self._lib.dv_convnextvit_labels(self._h))
+        ids = torch.empty((n, 201), dtype=torch.int32, device=dev)
+        logits = torch.empty((n, 201, labels), dtype=torch.float32, device=dev) if return_logits else None
+        mx = torch.empty((n, 201), dtype=torch.float32, device=dev) if return_max else None
+        check(self._lib.dv_convnextvit_forward(self._h, _ptr(chunks), n, _ptr(logits), _ptr(ids), _ptr(mx)), self._h,
+              "dv_convnextvit_forward")
+        out = (ids,)
+        if return_logits:
+            out += (logits,)
+        if return_max:
+            out += (mx,)
+        return out if len(out) > 1 else ids
+
+    def set_pass_crops(self, crops: int):
+        check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
+
+    def ctc_collapse(self, ids: torch.Tensor, scores: Optional[torch.Tensor] = None, blank: int = 0):
+        """[B,T] int32 per-step arg-max (+ optional [B,T] fp32 scores) -> (ids left-packed/-1 padded, len, conf)."""
+        ids = _require_cuda(ids, torch.int32, "ids")
+        if scores is not None:
+            scores = _require_cuda(scores, torch.float32, "scores")
+        b, t = ids.shape
+        dev = ids.device
+        out = torch.empty((b, t), dtype=torch.int32, device=dev)
+        ln = torch.empty((b,), dtype=torch.int32, device=dev)
+        conf = torch.empty((b,), dtype=torch.float32, device=dev)
+        check(self._lib.dv_ctc_collapse(self._h, _ptr(ids), _ptr(scores), b, t, blank, _ptr(out), _ptr(ln), _ptr(conf)),
+              self._h, "dv_ctc_collapse")
+        return out, ln, conf
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         """Named intermediate activation of the last forward as fp32 NCHW (parity debugging)."""
         dims = (C.c_int * 4)()

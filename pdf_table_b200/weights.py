@@ -155,3 +155,59 @@ def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"]) -> bytes:
     t["bin.deconv2.w"] = w2.reshape(64, 4).astype(np.float16)
     t["bin.deconv2.b"] = _np(sd["decoder.binarize.6.bias"]).astype(np.float32).reshape(1)
     return write_blob(t)
+
+
+# --------------------------------------------------------------------------- ConvNextViT
+def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference ConvNextViT (convnext_vit/modeling_convnext_vit.py:20-45).
+
+    layer_scale is folded into pwconv2 (gamma * (W x + b)), the attention scale 1/sqrt(64) (an exact power of
+    two) into the query projection, q/k/v are concatenated into one [576,192] GEMM, the (2,1) down-sampling conv
+    becomes a flat [C', 2C] GEMM over the re-laid-out LayerNorm output, and position_embeddings[:, 1:] is kept as
+    an fp32 [75,192] table added by the patch-projection epilogue."""
+    t: Dict[str, np.ndarray] = {}
+    f = lambda k: _np(sd[k]).astype(np.float32)
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    p = "cnn_model.embeddings"
+    t["patch.w"] = np.ascontiguousarray(f(p + ".patch_embeddings.weight").reshape(96, 16).T)  # [16][96], k = dy*4+dx
+    t["patch.b"] = f(p + ".patch_embeddings.bias")
+    t["patch.ln.w"], t["patch.ln.b"] = f(p + ".layernorm.weight"), f(p + ".layernorm.bias")
+    blk = 0
+    depths, dims = (3, 3, 8, 3), (96, 192, 256, 512)
+    for s, (depth, dim) in enumerate(zip(depths, dims)):
+        sp = f"cnn_model.encoder.stages.{s}"
+        if s > 0:
+            t[f"ds{s}.ln.w"], t[f"ds{s}.ln.b"] = f(sp + ".downsampling_layer.0.weight"), f(sp + ".downsampling_layer.0.bias")
+            put(f"ds{s}.conv", pack_conv(f(sp + ".downsampling_layer.1.weight"), f(sp + ".downsampling_layer.1.bias")))
+        for j in range(depth):
+            lp = f"{sp}.layers.{j}"
+            gamma = f(lp + ".layer_scale_parameter")
+            t[f"blk{blk}.dw.w"] = np.ascontiguousarray(f(lp + ".dwconv.weight").reshape(dim, 49).T)  # [49][C]
+            t[f"blk{blk}.dw.b"] = f(lp + ".dwconv.bias")
+            t[f"blk{blk}.ln.w"], t[f"blk{blk}.ln.b"] = f(lp + ".layernorm.weight"), f(lp + ".layernorm.bias")
+            put(f"blk{blk}.pw1", pack_linear(f(lp + ".pwconv1.weight"), f(lp + ".pwconv1.bias")))
+            put(f"blk{blk}.pw2", pack_linear(f(lp + ".pwconv2.weight") * gamma[:, None], f(lp + ".pwconv2.bias") * gamma))
+            blk += 1
+    v = "vitstr.vit"
+    put("vit.proj", pack_conv(f(v + ".embeddings.patch_embeddings.projection.weight"),
+                              f(v + ".embeddings.patch_embeddings.projection.bias")))
+    t["vit.pos"] = np.ascontiguousarray(f(v + ".embeddings.position_embeddings")[0, 1:, :])
+    L = 0
+    while f"{v}.encoder.layer.{L}.attention.attention.query.weight" in sd:
+        lp = f"{v}.encoder.layer.{L}"
+        a = lp + ".attention.attention"
+        wq, bq = f(a + ".query.weight") * np.float32(0.125), f(a + ".query.bias") * np.float32(0.125)
+        put(f"vit{L}.qkv", pack_linear(np.concatenate([wq, f(a + ".key.weight"), f(a + ".value.weight")], 0),
+                                       np.concatenate([bq, f(a + ".key.bias"), f(a + ".value.bias")], 0)))
+        put(f"vit{L}.proj", pack_linear(f(lp + ".attention.output.dense.weight"), f(lp + ".attention.output.dense.bias")))
+        put(f"vit{L}.fc1", pack_linear(f(lp + ".intermediate.dense.weight"), f(lp + ".intermediate.dense.bias")))
+        put(f"vit{L}.fc2", pack_linear(f(lp + ".output.dense.weight"), f(lp + ".output.dense.bias")))
+        t[f"vit{L}.ln1.w"], t[f"vit{L}.ln1.b"] = f(lp + ".layernorm_before.weight"), f(lp + ".layernorm_before.bias")
+        t[f"vit{L}.ln2.w"], t[f"vit{L}.ln2.b"] = f(lp + ".layernorm_after.weight"), f(lp + ".layernorm_after.bias")
+        L += 1
+    t["vit.ln.w"], t["vit.ln.b"] = f(v + ".layernorm.weight"), f(v + ".layernorm.bias")
+    put("cls", pack_linear(f("vitstr.classifier.weight"), f("vitstr.classifier.bias")))
+    return write_blob(t)
