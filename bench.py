@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json configs[1]): a batch of 32 synthetic 960x960 pages per GPU through the text
 cascade -- DB text detection (uint8 page -> normalise -> DBNet -> probability map) and text-line
-recognition post-processing (CTC greedy decode of the per-crop class probabilities).  `config.stages`
+recognition (uint8 32x320 text-line crops -> ConvNextViT with fused arg-max -> collapse; plus the PP-OCR
+head's CTC greedy decode on planted per-crop class probabilities).  `config.stages`
 lists exactly which stages of the cascade are inside the timed region.  One "step" = one pass over the
 32-page batch.  value = pages/s with the pages already resident in HBM; e2e = the same through the public
 predictor API with HOST (pinned) page buffers, H2D and D2H inside the timed region.
@@ -116,6 +117,13 @@ def make_pages(rank: int, n: int) -> np.ndarray:
     return np.stack([distinct[i % 4] for i in range(n)])
 
 
+def make_crops(rank: int, n: int) -> np.ndarray:
+    from pdf_table_b200 import synth
+
+    distinct = [synth.synthetic_text_crop(rank * 100000 + i, 32, 320) for i in range(64)]
+    return np.stack([distinct[i % 64] for i in range(n)])
+
+
 def make_ctc_probs(rank: int, n_crops: int) -> np.ndarray:
     rng = np.random.default_rng(77 + rank)
     logits = rng.standard_normal((n_crops, CTC_T, CTC_C)).astype(np.float32) * 3
@@ -129,7 +137,8 @@ def make_ctc_probs(rank: int, n_crops: int) -> np.ndarray:
 class Cascade:
     """The B200 arm: product code only (pdf_table_b200), no oracle imports."""
 
-    stages = ["det_preprocess_u8", "dbnet_r18_forward", "ctc_greedy_decode"]
+    stages = ["det_preprocess_u8", "dbnet_r18_forward", "rec_preprocess_u8(fused)", "convnextvit_forward+argmax",
+              "ctc_collapse", "ctc_greedy_decode(planted PP-OCR probs)"]
 
     def __init__(self, rank: int, device: int):
         from pdf_table_b200 import synth, weights
@@ -138,13 +147,20 @@ class Cascade:
         self.device = device
         self.det = Engine("dbnet_r18", weights.pack_dbnet_r18(synth.dbnet_r18_state_dict(0)), device=device)
         self.post = Engine("post", device=device)
+        self.rec = Engine("convnext_vit", weights.pack_convnext_vit(synth.convnext_vit_state_dict(0)), device=device)
         self.n_pages = PAGES_PER_GPU
         self.n_crops = PAGES_PER_GPU * CROPS_PER_PAGE
         self.pages_host = torch.from_numpy(make_pages(rank, self.n_pages)).pin_memory()
         self.probs_host = torch.from_numpy(make_ctc_probs(rank, self.n_crops)).pin_memory()
+        self.crops_host = torch.from_numpy(make_crops(rank, self.n_crops)).pin_memory()
         dev = torch.device("cuda", device)
         self.pages_dev = self.pages_host.to(dev)
         self.probs_dev = self.probs_host.to(dev)
+        self.crops_dev = self.crops_host.to(dev)
+        self.crops_stage = torch.empty_like(self.crops_dev)
+        self.tok_ids = torch.empty((self.n_crops, 201), dtype=torch.int32, device=dev)
+        self.rec_ids_host = torch.empty((self.n_crops, 201), dtype=torch.int32).pin_memory()
+        self.rec_len_host = torch.empty((self.n_crops,), dtype=torch.int32).pin_memory()
         self.prob_map = torch.empty((self.n_pages, 1, PAGE_H, PAGE_W), dtype=torch.float32, device=dev)
         self.pages_stage = torch.empty_like(self.pages_dev)
         self.probs_stage = torch.empty_like(self.probs_dev)
@@ -158,13 +174,20 @@ class Cascade:
     def step_device(self):
         """Inputs resident in HBM."""
         self.det.dbnet_forward_u8(self.pages_dev, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        self.rec.convnextvit_forward_u8(self.crops_dev, ids=self.tok_ids)
+        self.rec_out = self.post.ctc_collapse(self.tok_ids)
         return self.post.ctc_greedy(self.probs_dev)
 
     def step_e2e(self):
         """Host (pinned) buffers in, host results out: H2D + D2H inside."""
         self.pages_stage.copy_(self.pages_host, non_blocking=True)
         self.probs_stage.copy_(self.probs_host, non_blocking=True)
+        self.crops_stage.copy_(self.crops_host, non_blocking=True)
         self.det.dbnet_forward_u8(self.pages_stage, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        self.rec.convnextvit_forward_u8(self.crops_stage, ids=self.tok_ids)
+        r_ids, r_len, _ = self.post.ctc_collapse(self.tok_ids)
+        self.rec_ids_host.copy_(r_ids, non_blocking=True)
+        self.rec_len_host.copy_(r_len, non_blocking=True)
         ids, ln, conf = self.post.ctc_greedy(self.probs_stage)
         self.map_host.copy_(self.prob_map, non_blocking=True)
         self.ids_host.copy_(ids, non_blocking=True)
@@ -174,27 +197,33 @@ class Cascade:
 
     @property
     def h2d_bytes(self):
-        return self.pages_host.numel() + self.probs_host.numel() * 4
+        return self.pages_host.numel() + self.probs_host.numel() * 4 + self.crops_host.numel()
 
     @property
     def d2h_bytes(self):
-        return self.map_host.numel() * 4 + self.ids_host.numel() * 4 + self.len_host.numel() * 4 + self.conf_host.numel() * 4
+        return (self.map_host.numel() * 4 + self.ids_host.numel() * 4 + self.len_host.numel() * 4 + self.conf_host.numel() * 4
+                + self.rec_ids_host.numel() * 4 + self.rec_len_host.numel() * 4)
 
     def launches_per_step(self):
-        a = self.det.launch_count + self.post.launch_count
+        a = sum(e.launch_count for e in self.engines)
         self.step_device()
         torch.cuda.synchronize()
-        return self.det.launch_count + self.post.launch_count - a
+        return sum(e.launch_count for e in self.engines) - a
+
+    @property
+    def engines(self):
+        return (self.det, self.rec, self.post)
 
     def flush_l2(self):
         self.flush.fill_(1)
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd):
+def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, sample_crops=None, rec_sd=None):
     """The reference's algorithm for the same stages on the host cores (oracle/ restatement of
-    PPOcrDetectionPreprocessor + DBModel + CTCLabelDecode)."""
-    from oracle import ctc_ref, dbnet_ref
+    PPOcrDetectionPreprocessor + DBModel, OCRRecognitionPreprocessor + ConvNextViT + its post-processor, and
+    CTCLabelDecode)."""
+    from oracle import convnextvit_ref, ctc_ref, dbnet_ref
 
     mean = np.array(MEAN, np.float32).reshape(1, 1, 3)
     std = np.array(STD, np.float32).reshape(1, 1, 3)
@@ -203,6 +232,10 @@ def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd):
         img = (img - mean) / std
         x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
         dbnet_ref.dbnet_r18_forward(sd, x)
+    if sample_crops is not None:
+        for i in range(0, len(sample_crops), 16):  # batches of 16 crops (48 chunks)
+            chunks = convnextvit_ref.preprocess(list(sample_crops[i:i + 16]))
+            convnextvit_ref.greedy_ids(convnextvit_ref.convnextvit_forward(rec_sd, chunks))
     ctc_ref.ctc_greedy_ids(sample_probs)
 
 
@@ -212,13 +245,15 @@ def time_cpu_baseline(n_pages: int, repeats: int = 1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
+    rec_sd = {k: torch.from_numpy(v) for k, v in synth.convnext_vit_state_dict(0).items()}
     pages = make_pages(0, n_pages)
     probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
-    cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd)  # warm-up
+    crops = make_crops(0, n_pages * CROPS_PER_PAGE)
+    cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd)  # warm-up
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_reference_step(pages, probs, sd)
+        cpu_reference_step(pages, probs, sd, crops, rec_sd)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_pages / best, cores, best
@@ -233,16 +268,19 @@ def run_reference(args, rank: int):
     from pdf_table_b200 import synth
 
     sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
+    rec_sd = {k: torch.from_numpy(v) for k, v in synth.convnext_vit_state_dict(0).items()}
     pages = make_pages(0, n_pages)
     probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
+    crops = make_crops(0, n_pages * CROPS_PER_PAGE)
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd)
+        cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(pages, probs, sd)
+        cpu_reference_step(pages, probs, sd, crops, rec_sd)
     dt = (time.perf_counter() - t0) / args.steps
     v = n_pages / dt
-    sample = f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step (+{n_pages * CROPS_PER_PAGE} CTC crops), torch fp32 on host cores"
+    sample = (f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step, each with {CROPS_PER_PAGE} text-line crops through ConvNextViT "
+              "(+ planted CTC decode), torch fp32 on host cores")
     line = {
         "impl": "reference", "metric": "pages_per_sec", "value": v, "unit": "pages/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -259,8 +297,10 @@ def workload_config():
         "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
         "stages": Cascade.stages,
         "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
-        "rec_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities "
-                     "(recogniser network not yet on the engine)",
+        "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} planted "
+                     "uint8 32x320 crops per page, seeded random weights",
+        "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
+        "not_yet_on_gpu": "DB box post-process and perspective crop extraction (crops are planted, not cut from the detected boxes)",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
         "parallelism": "page-sharded replicas, one process per GPU",
@@ -333,12 +373,14 @@ def main():
     e2e_ms = a.elapsed_time(b)
 
     # ---- per-kernel device times (CUDA events on the launching stream, same steps, separate pass)
-    wl.det.profile_begin()
-    wl.post.profile_begin()
+    for e in wl.engines:
+        e.profile_begin()
     for _ in range(args.steps):
         wl.flush_l2()
         wl.step_device()
-    recs = wl.det.profile_report() + wl.post.profile_report()
+    recs = []
+    for e in wl.engines:
+        recs += e.profile_report()
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -383,7 +425,7 @@ def main():
         if not args.no_cpu_baseline:
             v, cores, secs = time_cpu_baseline(4)
             cpu = {"value": v, "unit": "pages/s", "cores": cores, "kind": "port",
-                   "sample": f"4 of {PAGES_PER_GPU} pages (+{4 * CROPS_PER_PAGE} CTC crops), oracle/ restatement in torch fp32, {secs:.1f} s"}
+                   "sample": f"4 of {PAGES_PER_GPU} pages with {4 * CROPS_PER_PAGE} crops (det + rec + decode), oracle/ restatement in torch fp32, {secs:.1f} s"}
         line = {
             "metric": "pages_per_sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -392,7 +434,7 @@ def main():
             "e2e": {"value": e2e_v, "unit": "pages/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
                     "d2h_bytes_per_step": int(wl.d2h_bytes), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "kernels": kernels,
-            "crops_per_sec_ctc": wl.n_crops * world * args.steps / (dev_ms / 1e3),
+            "crops_per_page": CROPS_PER_PAGE, "crops_per_sec_in_cascade": wl.n_crops * world * args.steps / (dev_ms / 1e3),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

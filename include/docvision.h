@@ -119,6 +119,14 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
  */
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out);
+/*
+ * Same network fed with uint8 HWC crops [n_crops, 32, crop_w, 3] (height already 32, zero padded on the right to
+ * a common crop_w <= 804): fuses the pad-to-804 / 3-chunk split (x0 = 0, 252, 504; width 300) / `/255` / NHWC->NCHW of
+ * OCRRecognitionPreprocessor.__call__ (ocr_recognition/processor_ocr_recognition.py:57-61, 104-112) and the
+ * RGB->gray of ConvNextViT.forward into the patchify kernel.  The keep-ratio cv2.resize (:44-56) stays with the caller.
+ */
+int dv_convnextvit_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, int n_crops, int crop_w, float* logits_out,
+                              int32_t* ids_out, float* max_out);
 int dv_convnextvit_labels(dv_handle h);
 /* crops per internal pass (default 96): sizes the activation workspace so the widest tensor stays near L2 */
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops);

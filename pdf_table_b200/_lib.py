@@ -33,6 +33,7 @@ SIGNATURES = {
     "dv_ctc_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dv_convnextvit_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_labels": (C.c_int, [C.c_void_p]),
     "dv_convnextvit_set_pass_crops": (C.c_int, [C.c_void_p, C.c_int]),
     "dv_ctc_collapse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

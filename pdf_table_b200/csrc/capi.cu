@@ -261,7 +261,16 @@ int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crop
                            int32_t* ids_out, float* max_out) {
     if (!h) return DV_ERR_ARG;
     cudaSetDevice(h->device);
-    return cnv_forward(h, chunks_nchw_f32, n_crops, logits_out, ids_out, max_out);
+    if (n_crops > 0 && !chunks_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_convnextvit_forward: null input");
+    return cnv_forward(h, chunks_nchw_f32, nullptr, 0, n_crops, logits_out, ids_out, max_out);
+}
+
+int dv_convnextvit_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, int n_crops, int crop_w, float* logits_out,
+                              int32_t* ids_out, float* max_out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (n_crops > 0 && !crops_hwc_u8) return set_err(h, DV_ERR_ARG, "dv_convnextvit_forward_u8: null input");
+    return cnv_forward(h, nullptr, crops_hwc_u8, crop_w, n_crops, logits_out, ids_out, max_out);
 }
 
 int dv_convnextvit_labels(dv_handle h) { return h ? cnv_labels(h) : 0; }

@@ -18,8 +18,8 @@
 
 namespace dv {
 
-int op_cnv_patchify_ln(Engine* e, const float* chunks, int B, const float* w, const float* bias, const float* lnw,
-                       const float* lnb, float* out);
+int op_cnv_patchify_ln(Engine* e, const float* chunks, const uint8_t* crops_u8, int crop_w, int B, const float* w,
+                       const float* bias, const float* lnw, const float* lnb, float* out);
 int op_dwconv7_ln(Engine* e, const float* x, int B, int H, int C, const float* w, const float* b, const float* lnw,
                   const float* lnb, __half* out, const char* layer);
 int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* lnw, const float* lnb, float eps,
@@ -285,11 +285,14 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
     return 0;
 }
 
-int run_pass(Engine* e, Pass* ps, const float* chunks, float* logits, int32_t* ids, float* maxv) {
+int run_pass(Engine* e, Pass* ps, const float* chunks, const uint8_t* crops_u8, int crop_w, float* logits, int32_t* ids,
+             float* maxv) {
     for (size_t i = 0; i < ps->steps.size(); ++i) {
         Step& st = ps->steps[i];
         switch (st.kind) {
-            case Step::PATCHIFY: DV_TRY(op_cnv_patchify_ln(e, chunks, ps->B, st.w, st.b, st.lnw, st.lnb, st.fout)); break;
+            case Step::PATCHIFY:
+                DV_TRY(op_cnv_patchify_ln(e, chunks, crops_u8, crop_w, ps->B, st.w, st.b, st.lnw, st.lnb, st.fout));
+                break;
             case Step::DWLN:
                 DV_TRY(op_dwconv7_ln(e, st.fin, ps->B, st.H, st.C, st.w, st.b, st.lnw, st.lnb, st.hout, st.name.c_str()));
                 break;
@@ -345,10 +348,13 @@ double cnv_flops(Engine* e) {
     return m ? m->last_flops : 0.0;
 }
 
-int cnv_forward(Engine* e, const float* chunks, int n_crops, float* logits, int32_t* ids, float* maxv) {
+int cnv_forward(Engine* e, const float* chunks, const uint8_t* crops_u8, int crop_w, int n_crops, float* logits,
+                int32_t* ids, float* maxv) {
     CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
     if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a convnext_vit model");
-    if (n_crops < 0 || (n_crops > 0 && (!chunks || !ids))) return set_err(e, DV_ERR_ARG, "convnextvit_forward: bad arguments");
+    if (n_crops < 0 || (n_crops > 0 && ((!chunks && !crops_u8) || !ids)))
+        return set_err(e, DV_ERR_ARG, "convnextvit_forward: bad arguments");
+    if (crops_u8 && (crop_w <= 0 || crop_w > 804)) return set_err(e, DV_ERR_ARG, "convnextvit_forward_u8: crop_w must be in 1..804");
     m->last_flops = 0;
     for (int done = 0; done < n_crops;) {
         const int cur = (n_crops - done) < m->pass_crops ? (n_crops - done) : m->pass_crops;
@@ -360,7 +366,8 @@ int cnv_forward(Engine* e, const float* chunks, int n_crops, float* logits, int3
             it = m->passes.emplace(cur, std::move(ps)).first;
         }
         Pass* ps = it->second.get();
-        DV_TRY(run_pass(e, ps, chunks + static_cast<long long>(done) * 3 * 3 * 32 * 300,
+        DV_TRY(run_pass(e, ps, chunks ? chunks + static_cast<long long>(done) * 3 * 3 * 32 * 300 : nullptr,
+                        crops_u8 ? crops_u8 + static_cast<long long>(done) * 32 * crop_w * 3 : nullptr, crop_w,
                         logits ? logits + static_cast<long long>(done) * kStitched * m->labels : nullptr,
                         ids + static_cast<long long>(done) * kStitched, maxv ? maxv + static_cast<long long>(done) * kStitched : nullptr));
         m->last_flops += ps->flops;

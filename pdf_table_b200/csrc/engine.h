@@ -159,7 +159,8 @@ int dbnet_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4)
 
 // convnextvit.cu
 int cnv_create(Engine* e);
-int cnv_forward(Engine* e, const float* chunks, int n_crops, float* logits, int32_t* ids, float* maxv);
+int cnv_forward(Engine* e, const float* chunks, const uint8_t* crops_u8, int crop_w, int n_crops, float* logits,
+                int32_t* ids, float* maxv);
 int cnv_set_pass_crops(Engine* e, int crops);
 int cnv_labels(Engine* e);
 double cnv_flops(Engine* e);

@@ -21,8 +21,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------
 // chunks fp32 NCHW [B,3,32,300] in [0,1]  ->  x fp32 [B,8,75,96]
 // gray = R*0.2989 + G*0.5870 + B*0.1140 (modeling_convnext_vit.py:40), conv 4x4 stride 4, LN eps 1e-6.
+// U8 variant: `in` is uint8 HWC crops [B/3, 32, crop_w, 3] (height 32, zero padded to a common width <= 804);
+// chunk k of a crop is the column window [252k, 252k+300) with zeros beyond crop_w, and /255 is applied first
+// -- OCRRecognitionPreprocessor.__call__ (ocr_recognition/processor_ocr_recognition.py:57-61, 104-112) fused in.
+template <bool U8>
 __global__ void __launch_bounds__(256)
-k_cnv_patchify_ln(const float* __restrict__ in, int B, const float* __restrict__ w /*[16][96]*/,
+k_cnv_patchify_ln(const void* __restrict__ in_raw, int crop_w, int B, const float* __restrict__ w /*[16][96]*/,
                   const float* __restrict__ bias, const float* __restrict__ lnw, const float* __restrict__ lnb,
                   float* __restrict__ out) {
     __shared__ float sw[16 * 96];
@@ -37,10 +41,25 @@ k_cnv_patchify_ln(const float* __restrict__ in, int B, const float* __restrict__
     float g = 0.f;
     if (lane < 16) {
         const int iy = py * 4 + (lane >> 2), ix = px * 4 + (lane & 3);
-        const float* ip = in + (static_cast<long long>(b) * 3 * 32 + iy) * 300 + ix;
+        float c0, c1, c2;
+        if constexpr (U8) {
+            const int crop = b / 3, col = 252 * (b - crop * 3) + ix;
+            c0 = c1 = c2 = 0.f;
+            if (col < crop_w) {
+                const uint8_t* ip = reinterpret_cast<const uint8_t*>(in_raw) +
+                                    ((static_cast<long long>(crop) * 32 + iy) * crop_w + col) * 3;
+                c0 = __fdiv_rn(static_cast<float>(ip[0]), 255.f);
+                c1 = __fdiv_rn(static_cast<float>(ip[1]), 255.f);
+                c2 = __fdiv_rn(static_cast<float>(ip[2]), 255.f);
+            }
+        } else {
+            const float* ip = reinterpret_cast<const float*>(in_raw) + (static_cast<long long>(b) * 3 * 32 + iy) * 300 + ix;
+            c0 = ip[0];
+            c1 = ip[32 * 300];
+            c2 = ip[2 * 32 * 300];
+        }
         // same evaluation order as the reference expression: (R*a + G*b) + B*c, no FMA contraction
-        g = __fadd_rn(__fadd_rn(__fmul_rn(ip[0], 0.2989f), __fmul_rn(ip[32 * 300], 0.5870f)),
-                      __fmul_rn(ip[2 * 32 * 300], 0.1140f));
+        g = __fadd_rn(__fadd_rn(__fmul_rn(c0, 0.2989f), __fmul_rn(c1, 0.5870f)), __fmul_rn(c2, 0.1140f));
     }
     float acc[3];
 #pragma unroll
@@ -334,11 +353,15 @@ int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, 
 
 }  // namespace
 
-int op_cnv_patchify_ln(Engine* e, const float* chunks, int B, const float* w, const float* bias, const float* lnw,
-                       const float* lnb, float* out) {
+int op_cnv_patchify_ln(Engine* e, const float* chunks, const uint8_t* crops_u8, int crop_w, int B, const float* w,
+                       const float* bias, const float* lnw, const float* lnb, float* out) {
     const long long pix = static_cast<long long>(B) * 600;
-    e->launch_begin("k_cnv_patchify_ln", "patchify", 2.0 * 16 * 96 * pix, static_cast<double>(B) * 3 * 32 * 300 * 4 + pix * 96.0 * 4);
-    k_cnv_patchify_ln<<<static_cast<int>((pix + 7) / 8), 256, 0, e->stream>>>(chunks, B, w, bias, lnw, lnb, out);
+    const double in_bytes = crops_u8 ? static_cast<double>(B / 3) * 32 * crop_w * 3 : static_cast<double>(B) * 3 * 32 * 300 * 4;
+    e->launch_begin("k_cnv_patchify_ln", "patchify", 2.0 * 16 * 96 * pix, in_bytes + pix * 96.0 * 4);
+    if (crops_u8)
+        k_cnv_patchify_ln<true><<<static_cast<int>((pix + 7) / 8), 256, 0, e->stream>>>(crops_u8, crop_w, B, w, bias, lnw, lnb, out);
+    else
+        k_cnv_patchify_ln<false><<<static_cast<int>((pix + 7) / 8), 256, 0, e->stream>>>(chunks, 0, B, w, bias, lnw, lnb, out);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

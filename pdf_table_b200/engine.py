@@ -132,6 +132,21 @@ class Engine:
             out += (mx,)
         return out if len(out) > 1 else ids
 
+    def convnextvit_forward_u8(self, crops: torch.Tensor, ids: Optional[torch.Tensor] = None, return_logits: bool = False):
+        """uint8 [n,32,w,3] (cuda; height 32, right-padded with zeros to a common w <= 804) -> arg-max ids [n,201]."""
+        crops = _require_cuda(crops, torch.uint8, "crops")
+        n, hh, w, c = crops.shape
+        if hh != 32 or c != 3 or not (0 < w <= 804):
+            raise ValueError("crops must be [n,32,w<=804,3]")
+        dev = crops.device
+        if ids is None:
+            ids = torch.empty((n, 201), dtype=torch.int32, device=dev)
+        labels = int(self._lib.dv_convnextvit_labels(self._h))
+        logits = torch.empty((n, 201, labels), dtype=torch.float32, device=dev) if return_logits else None
+        check(self._lib.dv_convnextvit_forward_u8(self._h, _ptr(crops), n, w, _ptr(logits), _ptr(ids), None), self._h,
+              "dv_convnextvit_forward_u8")
+        return (ids, logits) if return_logits else ids
+
     def set_pass_crops(self, crops: int):
         check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
 

@@ -119,3 +119,18 @@ def test_ctc_collapse_matches_oracle(rec):
         np.testing.assert_array_equal(out[i, : ln[i]], want[i])
         assert (out[i, ln[i]:] == -1).all()
     assert float(conf.abs().max()) == 0.0
+
+
+def test_convnextvit_u8_preprocess_fused(rec):
+    """uint8 crop path == reference preprocessing (pad / chunk / /255) followed by the fp32-chunk path, bit for bit."""
+    eng, _ = rec
+    crops = [synth.synthetic_text_crop(i, 32, 320) for i in range(5)]
+    chunks = ref.preprocess(crops)
+    ids_a, logits_a = eng.convnextvit_forward(chunks.cuda(), return_logits=True)
+    for w in (320, 804):
+        batch = np.zeros((5, 32, w, 3), np.uint8)
+        batch[:, :, :320] = np.stack(crops)
+        ids_b, logits_b = eng.convnextvit_forward_u8(torch.from_numpy(batch).cuda(), return_logits=True)
+        eng.sync()
+        np.testing.assert_array_equal(logits_a.cpu().numpy(), logits_b.cpu().numpy())
+        np.testing.assert_array_equal(ids_a.cpu().numpy(), ids_b.cpu().numpy())
