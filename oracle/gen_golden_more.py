@@ -67,4 +67,53 @@ def gen_convnextvit():
     print("convnextvit_seed0", logits.shape, [len(r) for r in ids], float(logits.abs().max()))
 
 
-GENERATORS = {"convnextvit": gen_convnextvit}
+def _ref_db_post():
+    """The reference's DBPostProcess / PPOcrDetectionPostProcessor (db_pp/processor_ocr_db_pp.py:148-386) with the two
+    missing wheels replaced by the restatements in oracle/db_post_ref.py (pyclipper offset, shapely area/length)."""
+    ref_import.setup()
+    from . import db_post_ref
+
+    sys.modules["pyclipper"] = db_post_ref.PyclipperStandIn
+    sg = sys.modules.get("shapely.geometry") or types.ModuleType("shapely.geometry")
+    sg.Polygon = db_post_ref.ShapelyPolygonStandIn
+    sys.modules["shapely.geometry"] = sg
+    name = "pdftable.model.db_pp.configuration_db_pp"
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.DbPPConfig = type("DbPPConfig", (), {})
+        sys.modules[name] = m
+    import pdftable.model.db_pp.processor_ocr_db_pp as mod
+
+    mod.pyclipper = db_post_ref.PyclipperStandIn
+    mod.Polygon = db_post_ref.ShapelyPolygonStandIn
+    return mod
+
+
+DB_POST_CASES = [
+    # name, map index, map h, map w, n_lines, src_h, src_w
+    ("page960", 0, 960, 960, 40, 960, 960),
+    ("page960b", 1, 960, 960, 60, 960, 960),
+    ("scaled", 2, 640, 960, 30, 1000, 1500),
+    ("small", 3, 160, 224, 6, 160, 224),
+    ("tall", 4, 960, 320, 12, 2875, 960),
+]
+
+
+def gen_db_post():
+    """Reference DB post-process on planted probability maps (synth.synthetic_prob_map): det_polygons per case."""
+    mod = _ref_db_post()
+    cfg = types.SimpleNamespace(thresh=0.2, box_thresh=0.6, unclip_ratio=1.5, use_dilation=False, score_mode="fast",
+                                max_candidates=1000)
+    post = mod.PPOcrDetectionPostProcessor(cfg)
+    out = {}
+    for name, idx, h, w, n_lines, src_h, src_w in DB_POST_CASES:
+        prob = synth.synthetic_prob_map(idx, h, w, n_lines)
+        shape_list = np.array([src_h, src_w, h / float(src_h), w / float(src_w)])
+        res = post({"results": torch.from_numpy(prob)[None, None], "org_shape": (src_h, src_w, 3),
+                    "shape_list": shape_list, "inputs": None})
+        out[name] = res["det_polygons"].astype(np.float32)
+        print("db_post", name, out[name].shape)
+    np.savez_compressed(os.path.join(GOLDEN, "db_post.npz"), **out)
+
+
+GENERATORS = {"convnextvit": gen_convnextvit, "db_post": gen_db_post}

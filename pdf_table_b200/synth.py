@@ -177,3 +177,70 @@ def convnext_vit_state_dict(seed: int = 0, num_labels: int = VIT_LABELS) -> "Ord
     sd["vitstr.classifier.weight"] = _lin(rng, num_labels, VIT_DIM, gain=4.0)
     sd["vitstr.classifier.bias"] = _b(rng, num_labels)
     return sd
+
+
+# --------------------------------------------------------------------------- planted DB probability maps
+def synthetic_prob_map(index: int, h: int = 960, w: int = 960, n_lines: int = 40) -> np.ndarray:
+    """A DB-like probability map (fp32 [h,w] in [0,1)) with analytically placed text-line blobs: rotated soft-edged
+    rectangles of varying peak probability (some below box_thresh), a few with holes, a ruled-table frame, and
+    small specks.  numpy only, so the build container and the GPU box produce identical maps."""
+    rng = np.random.default_rng(424242 + index)
+    prob = np.zeros((h, w), np.float32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+
+    def add_rect(cx, cy, bw, bh, ang, peak, soft, hole=None):
+        c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        r = int(np.hypot(bw, bh) / 2 + soft + 2)
+        x0, x1, y0, y1 = max(0, int(cx) - r), min(w, int(cx) + r + 1), max(0, int(cy) - r), min(h, int(cy) + r + 1)
+        if x0 >= x1 or y0 >= y1:
+            return
+        dx, dy = xx[y0:y1, x0:x1] - np.float32(cx), yy[y0:y1, x0:x1] - np.float32(cy)
+        u, v = dx * c + dy * s, -dx * s + dy * c
+        d = np.minimum(np.float32(bw / 2) - np.abs(u), np.float32(bh / 2) - np.abs(v))  # >0 inside
+        val = np.float32(peak) * np.clip(np.float32(0.5) + d / np.float32(soft), 0, 1)
+        if hole is not None:
+            hu, hv, hr = hole
+            val = np.where((u - np.float32(hu)) ** 2 + (v - np.float32(hv)) ** 2 < np.float32(hr * hr), np.float32(0.05), val)
+        prob[y0:y1, x0:x1] = np.maximum(prob[y0:y1, x0:x1], val.astype(np.float32))
+
+    placed = []  # (x0, y0, x1, y1) of accepted blobs incl. margin: blobs never merge
+
+    def try_place(cx, cy, bw, bh, ang, margin=10.0):
+        ex = abs(np.cos(ang)) * bw / 2 + abs(np.sin(ang)) * bh / 2 + margin
+        ey = abs(np.sin(ang)) * bw / 2 + abs(np.cos(ang)) * bh / 2 + margin
+        box = (cx - ex, cy - ey, cx + ex, cy + ey)
+        if box[0] < -5 or box[1] < -5 or box[2] > w + 5 or box[3] > h + 5:
+            return rng.random() < 0.1  # a few blobs may touch the frame
+        for q in placed:
+            if box[0] < q[2] and q[0] < box[2] and box[1] < q[3] and q[1] < box[3]:
+                return False
+        placed.append(box)
+        return True
+
+    # ruled table frame: thin lines forming cells (one big component with many holes)
+    tx, ty, tw, th = rng.uniform(0.1, 0.3) * w, rng.uniform(0.55, 0.7) * h, rng.uniform(0.4, 0.6) * w, rng.uniform(0.15, 0.25) * h
+    rows, cols = int(rng.integers(2, 5)), int(rng.integers(2, 6))
+    for r in range(rows + 1):
+        add_rect(tx + tw / 2, ty + r * th / rows, tw, 3.0, 0.0, 0.9, 1.0)
+    for c in range(cols + 1):
+        add_rect(tx + c * tw / cols, ty + th / 2, 3.0, th, 0.0, 0.9, 1.0)
+    placed.append((tx - 12, ty - 12, tx + tw + 12, ty + th + 12))
+    n_ok = 0
+    for i in range(n_lines * 30):
+        if n_ok >= n_lines:
+            break
+        bw, bh = rng.uniform(40, min(420, w * 0.45)), rng.uniform(8, 30)
+        ang = rng.uniform(-0.2, 0.2) if rng.random() < 0.8 else rng.uniform(-1.5, 1.5)
+        if rng.random() < 0.35:
+            ang = 0.0
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        peak = rng.uniform(0.5, 0.98)
+        hole = (rng.uniform(-bw / 4, bw / 4), 0.0, rng.uniform(1.5, 4.0)) if rng.random() < 0.15 else None
+        soft = rng.uniform(1.0, 3.0)
+        if not try_place(cx, cy, bw, bh, ang):
+            continue
+        add_rect(cx, cy, bw, bh, ang, peak, soft, hole)
+        n_ok += 1
+    for i in range(25):  # specks: tiny components that fail min_size or box_thresh
+        add_rect(rng.uniform(5, w - 5), rng.uniform(5, h - 5), rng.uniform(1, 5), rng.uniform(1, 5), 0.0, rng.uniform(0.3, 0.9), 1.0)
+    return prob

@@ -83,3 +83,37 @@ def test_convnextvit_oracle_matches_reference_golden():
     ids = convnextvit_ref.greedy_ids(logits)
     for i in range(n):
         np.testing.assert_array_equal(ids[i], g[f"ids{i}"])
+
+
+def test_db_post_oracle_matches_reference_golden():
+    """oracle/db_post_ref.py (restatement) == the reference's own DBPostProcess code run in the build container."""
+    from oracle import db_post_ref
+    from oracle.gen_golden_more import DB_POST_CASES
+
+    g = np.load(os.path.join(GOLDEN, "db_post.npz"))
+    for name, idx, h, w, n_lines, src_h, src_w in DB_POST_CASES:
+        prob = synth.synthetic_prob_map(idx, h, w, n_lines)
+        shape_list = np.array([src_h, src_w, h / float(src_h), w / float(src_w)])
+        got = db_post_ref.db_postprocess(prob, shape_list, (src_h, src_w, 3))
+        np.testing.assert_array_equal(got.astype(np.float32), g[name], err_msg=name)
+        assert len(got) > 0
+
+
+def test_clipper_offset_known_answers():
+    """Round-join offset of an axis-aligned rectangle: every point lies within 1 of distance d from the source
+    rectangle, the axis extremes are exactly +-d, and tiny deltas use the reduced arc tolerance."""
+    from oracle.db_post_ref import clipper_offset_round
+
+    rect = [(10, 20), (110, 20), (110, 50), (10, 50)]
+    cround = lambda v: int(v - 0.5) if v < 0 else int(v + 0.5)  # clipper.cpp Round()
+    for d in (0.7, 3.0, 9.5, 40.0):
+        pts = np.array(clipper_offset_round(rect, d))
+        assert pts[:, 0].min() == cround(10 - d) and pts[:, 0].max() == cround(110 + d)
+        assert pts[:, 1].min() == cround(20 - d) and pts[:, 1].max() == cround(50 + d)
+        dx = np.maximum(np.maximum(10 - pts[:, 0], pts[:, 0] - 110), 0)
+        dy = np.maximum(np.maximum(20 - pts[:, 1], pts[:, 1] - 50), 0)
+        assert (np.abs(np.hypot(dx, dy) - d) <= 0.75).all()
+    # orientation: the reversed path gives the same point set
+    a = set(clipper_offset_round(rect, 5.0))
+    b = set(clipper_offset_round(rect[::-1], 5.0))
+    assert a == b
