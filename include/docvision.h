@@ -107,6 +107,25 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
                   int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max);
 
 /*
+ * DB "threshold + box seed": probability maps -> text boxes, entirely on the device.
+ * Replaces OcrDetectionTask._postprocess (ocr_detection_task.py:126-141) = PPOcrDetectionPostProcessor.__call__
+ * (db_pp/processor_ocr_db_pp.py:330-342): DBPostProcess.__call__ / boxes_from_bitmap / get_mini_boxes /
+ * box_score_fast / unclip (:174-311) followed by filter_tag_det_res (:374-386).
+ *   prob          : [n,1,height,width] fp32 (device), the output of dv_dbnet_forward
+ *   src_hw_host   : HOST [n][2] doubles (src_h, src_w) = shape_list[:2] = org_shape[:2] of each page
+ *   thresh        : binarisation threshold (compared in fp32, as numpy does); CLI default 0.2
+ *   box_thresh    : minimum mean probability inside the box (0.6); unclip_ratio (1.5); max_candidates (<= 1000)
+ *   boxes_out     : [n][max_candidates][8] fp32 (device) -- x0,y0,..,x3,y3 clockwise from top-left, source-image pixels,
+ *                   in the reference's contour order, left-packed
+ *   counts_out    : [n] int32 (device) boxes per page
+ *   overflow_host : HOST int32 or NULL; receives the number of contours skipped because they exceed the kernel's
+ *                   vertex capacity (2048 vertices after CHAIN_APPROX_SIMPLE); non-NULL makes the call synchronous
+ */
+int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, const double* src_hw_host, float thresh,
+                double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
+                int32_t* overflow_host);
+
+/*
  * ConvNextViT text-line recogniser forward.
  * Replaces OcrRecognitionTask._run_model for model="ConvNextViT" (ocr_recognition_task.py:81-116) =
  * OCRRecognition.forward (ocr_recognition/modeling_ocr_recognition.py:137-149) -> ConvNextViT.forward

@@ -32,6 +32,8 @@ SIGNATURES = {
                                       C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]),
     "dv_ctc_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dv_db_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_float, C.c_double,
+                              C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "dv_convnextvit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_labels": (C.c_int, [C.c_void_p]),

@@ -162,6 +162,7 @@ int dv_destroy(dv_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->model.reset();
+    h->aux.clear();
     for (void* p : h->owned) cudaFree(p);
     if (h->weight_base) cudaFree(h->weight_base);
     delete h;
@@ -255,6 +256,15 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
     if (!h) return DV_ERR_ARG;
     cudaSetDevice(h->device);
     return ctc_greedy(h, probs, b, t, c, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
+}
+
+int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, const double* src_hw_host, float thresh,
+                double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
+                int32_t* overflow_host) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return db_boxes(h, prob, n, height, width, src_hw_host, thresh, box_thresh, unclip_ratio, max_candidates, boxes_out,
+                    counts_out, overflow_host);
 }
 
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,

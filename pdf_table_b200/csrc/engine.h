@@ -112,6 +112,7 @@ struct Engine {
     void* weight_base = nullptr;
     std::vector<void*> owned;  // device allocations freed at destroy
     std::unique_ptr<Model> model;
+    std::map<std::string, std::unique_ptr<Model>> aux;  // workspaces of the post-processing kernels, by name
     long long launches = 0;  // kernels launched through this handle (bench "gpu_launches")
     bool profiling = false;
     std::vector<ProfRec> prof;
@@ -164,6 +165,10 @@ int cnv_forward(Engine* e, const float* chunks, const uint8_t* crops_u8, int cro
 int cnv_set_pass_crops(Engine* e, int crops);
 int cnv_labels(Engine* e);
 double cnv_flops(Engine* e);
+
+// db_post.cu
+int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* src_hw_host, float thresh, double box_thresh,
+             double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host);
 
 // ctc.cu
 int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,

@@ -173,6 +173,25 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ post-processing kernels
+    def db_boxes(self, prob: torch.Tensor, src_hw, thresh: float = 0.2, box_thresh: float = 0.6, unclip_ratio: float = 1.5,
+                 max_candidates: int = 1000, check_overflow: bool = False):
+        """prob fp32 [N,1,H,W] (cuda); src_hw = [(src_h, src_w)] per page -> (boxes fp32 [N,max_candidates,8], counts
+        int32 [N]) on the device.  Boxes follow the reference's order and corner convention."""
+        prob = _require_cuda(prob, torch.float32, "prob")
+        n, c, h, w = prob.shape
+        if c != 1:
+            raise ValueError("prob must be [N,1,H,W]")
+        src = np.ascontiguousarray(np.asarray(src_hw, np.float64).reshape(n, 2))
+        boxes = torch.empty((n, max_candidates, 8), dtype=torch.float32, device=prob.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=prob.device)
+        ovf = C.c_int32(0)
+        check(self._lib.dv_db_boxes(self._h, _ptr(prob), n, h, w, src.ctypes.data_as(C.POINTER(C.c_double)), float(thresh),
+                                    float(box_thresh), float(unclip_ratio), int(max_candidates), _ptr(boxes), _ptr(counts),
+                                    C.byref(ovf) if check_overflow else None), self._h, "dv_db_boxes")
+        if check_overflow:
+            return boxes, counts, int(ovf.value)
+        return boxes, counts
+
     def ctc_greedy(self, probs: torch.Tensor, blank: int = 0, return_raw: bool = False):
         """[B,T,C] fp32 (cuda) -> (ids [B,T] int32 left-packed / -1 padded, len [B] int32, conf [B] fp32)."""
         probs = _require_cuda(probs, torch.float32, "probs")
