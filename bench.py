@@ -117,6 +117,15 @@ def make_pages(rank: int, n: int) -> np.ndarray:
     return np.stack([distinct[i % 4] for i in range(n)])
 
 
+def make_prob_maps(rank: int, n: int) -> np.ndarray:
+    """Planted DB probability maps (planted network outputs for post-processor throughput): with seeded
+    random weights the detector's own output is texture noise, so the box stage runs on analytic text-line blobs."""
+    from pdf_table_b200 import synth
+
+    distinct = [synth.synthetic_prob_map(rank * 1000 + i, PAGE_H, PAGE_W, CROPS_PER_PAGE) for i in range(4)]
+    return np.stack([distinct[i % 4] for i in range(n)])[:, None]
+
+
 def make_crops(rank: int, n: int) -> np.ndarray:
     from pdf_table_b200 import synth
 
@@ -137,7 +146,8 @@ def make_ctc_probs(rank: int, n_crops: int) -> np.ndarray:
 class Cascade:
     """The B200 arm: product code only (pdf_table_b200), no oracle imports."""
 
-    stages = ["det_preprocess_u8", "dbnet_r18_forward", "rec_preprocess_u8(fused)", "convnextvit_forward+argmax",
+    stages = ["det_preprocess_u8", "dbnet_r18_forward", "db_boxes(planted prob maps)", "rec_preprocess_u8(fused)",
+              "convnextvit_forward+argmax",
               "ctc_collapse", "ctc_greedy_decode(planted PP-OCR probs)"]
 
     def __init__(self, rank: int, device: int):
@@ -153,6 +163,10 @@ class Cascade:
         self.pages_host = torch.from_numpy(make_pages(rank, self.n_pages)).pin_memory()
         self.probs_host = torch.from_numpy(make_ctc_probs(rank, self.n_crops)).pin_memory()
         self.crops_host = torch.from_numpy(make_crops(rank, self.n_crops)).pin_memory()
+        self.planted_maps = torch.from_numpy(make_prob_maps(rank, self.n_pages)).to(torch.device("cuda", device))
+        self.src_hw = [(PAGE_H, PAGE_W)] * self.n_pages
+        self.box_host = torch.empty((self.n_pages, 1000, 8), dtype=torch.float32).pin_memory()
+        self.cnt_host = torch.empty((self.n_pages,), dtype=torch.int32).pin_memory()
         dev = torch.device("cuda", device)
         self.pages_dev = self.pages_host.to(dev)
         self.probs_dev = self.probs_host.to(dev)
@@ -164,7 +178,6 @@ class Cascade:
         self.prob_map = torch.empty((self.n_pages, 1, PAGE_H, PAGE_W), dtype=torch.float32, device=dev)
         self.pages_stage = torch.empty_like(self.pages_dev)
         self.probs_stage = torch.empty_like(self.probs_dev)
-        self.map_host = torch.empty(self.prob_map.shape, dtype=torch.float32).pin_memory()
         self.ids_host = torch.empty((self.n_crops, CTC_T), dtype=torch.int32).pin_memory()
         self.len_host = torch.empty((self.n_crops,), dtype=torch.int32).pin_memory()
         self.conf_host = torch.empty((self.n_crops,), dtype=torch.float32).pin_memory()
@@ -174,6 +187,7 @@ class Cascade:
     def step_device(self):
         """Inputs resident in HBM."""
         self.det.dbnet_forward_u8(self.pages_dev, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        self.boxes = self.post.db_boxes(self.planted_maps, self.src_hw)
         self.rec.convnextvit_forward_u8(self.crops_dev, ids=self.tok_ids)
         self.rec_out = self.post.ctc_collapse(self.tok_ids)
         return self.post.ctc_greedy(self.probs_dev)
@@ -184,12 +198,14 @@ class Cascade:
         self.probs_stage.copy_(self.probs_host, non_blocking=True)
         self.crops_stage.copy_(self.crops_host, non_blocking=True)
         self.det.dbnet_forward_u8(self.pages_stage, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
+        boxes, counts = self.post.db_boxes(self.planted_maps, self.src_hw)
+        self.box_host.copy_(boxes, non_blocking=True)
+        self.cnt_host.copy_(counts, non_blocking=True)
         self.rec.convnextvit_forward_u8(self.crops_stage, ids=self.tok_ids)
         r_ids, r_len, _ = self.post.ctc_collapse(self.tok_ids)
         self.rec_ids_host.copy_(r_ids, non_blocking=True)
         self.rec_len_host.copy_(r_len, non_blocking=True)
         ids, ln, conf = self.post.ctc_greedy(self.probs_stage)
-        self.map_host.copy_(self.prob_map, non_blocking=True)
         self.ids_host.copy_(ids, non_blocking=True)
         self.len_host.copy_(ln, non_blocking=True)
         self.conf_host.copy_(conf, non_blocking=True)
@@ -201,7 +217,7 @@ class Cascade:
 
     @property
     def d2h_bytes(self):
-        return (self.map_host.numel() * 4 + self.ids_host.numel() * 4 + self.len_host.numel() * 4 + self.conf_host.numel() * 4
+        return (self.box_host.numel() * 4 + self.cnt_host.numel() * 4 + self.ids_host.numel() * 4 + self.len_host.numel() * 4 + self.conf_host.numel() * 4
                 + self.rec_ids_host.numel() * 4 + self.rec_len_host.numel() * 4)
 
     def launches_per_step(self):
@@ -219,11 +235,11 @@ class Cascade:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, sample_crops=None, rec_sd=None):
+def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, sample_crops=None, rec_sd=None, sample_maps=None):
     """The reference's algorithm for the same stages on the host cores (oracle/ restatement of
     PPOcrDetectionPreprocessor + DBModel, OCRRecognitionPreprocessor + ConvNextViT + its post-processor, and
     CTCLabelDecode)."""
-    from oracle import convnextvit_ref, ctc_ref, dbnet_ref
+    from oracle import convnextvit_ref, ctc_ref, db_post_ref, dbnet_ref
 
     mean = np.array(MEAN, np.float32).reshape(1, 1, 3)
     std = np.array(STD, np.float32).reshape(1, 1, 3)
@@ -232,6 +248,9 @@ def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, s
         img = (img - mean) / std
         x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
         dbnet_ref.dbnet_r18_forward(sd, x)
+    if sample_maps is not None:
+        for m in sample_maps:
+            db_post_ref.db_postprocess(m[0], np.array([PAGE_H, PAGE_W, 1.0, 1.0]), (PAGE_H, PAGE_W, 3))
     if sample_crops is not None:
         for i in range(0, len(sample_crops), 16):  # batches of 16 crops (48 chunks)
             chunks = convnextvit_ref.preprocess(list(sample_crops[i:i + 16]))
@@ -249,11 +268,12 @@ def time_cpu_baseline(n_pages: int, repeats: int = 1):
     pages = make_pages(0, n_pages)
     probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
     crops = make_crops(0, n_pages * CROPS_PER_PAGE)
-    cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd)  # warm-up
+    maps = make_prob_maps(0, n_pages)
+    cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd, maps[:1])  # warm-up
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_reference_step(pages, probs, sd, crops, rec_sd)
+        cpu_reference_step(pages, probs, sd, crops, rec_sd, maps)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_pages / best, cores, best
@@ -272,11 +292,12 @@ def run_reference(args, rank: int):
     pages = make_pages(0, n_pages)
     probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
     crops = make_crops(0, n_pages * CROPS_PER_PAGE)
+    maps = make_prob_maps(0, n_pages)
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd)
+        cpu_reference_step(pages[:1], probs[:CROPS_PER_PAGE], sd, crops[:16], rec_sd, maps[:1])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(pages, probs, sd, crops, rec_sd)
+        cpu_reference_step(pages, probs, sd, crops, rec_sd, maps)
     dt = (time.perf_counter() - t0) / args.steps
     v = n_pages / dt
     sample = (f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step, each with {CROPS_PER_PAGE} text-line crops through ConvNextViT "
@@ -300,7 +321,9 @@ def workload_config():
         "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} planted "
                      "uint8 32x320 crops per page, seeded random weights",
         "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
-        "not_yet_on_gpu": "DB box post-process and perspective crop extraction (crops are planted, not cut from the detected boxes)",
+        "db_post_stage": "db_boxes on planted probability maps (analytic text-line blobs, ~40 per page): with random weights the "
+                         "detector's own map is texture noise",
+        "not_yet_on_gpu": "perspective crop extraction (crops are planted, not cut from the detected boxes)",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
         "parallelism": "page-sharded replicas, one process per GPU",
@@ -385,10 +408,15 @@ def main():
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the one collective of the path: all-gather of the packed decoded results (ids/len/conf)
-        ids, ln, conf = wl.step_device()
-        gathered = [torch.empty_like(ln) for _ in range(world)]
-        dist.all_gather(gathered, ln)
+        # the one collective of the path: all-gather of the packed decoded results (boxes, counts, token ids, lengths)
+        from pdf_table_b200 import sharding
+
+        wl.step_device()
+        r_ids, r_len, _ = wl.rec_out
+        boxes, counts = wl.boxes
+        gathered = sharding.all_gather_results({"boxes": boxes[:, :64].contiguous(), "box_counts": counts, "ids": r_ids, "id_lens": r_len},
+                                               [wl.n_pages] * world, [wl.n_crops] * world)
+        assert gathered["box_counts"].numel() == wl.n_pages * world
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
     if rank == 0:

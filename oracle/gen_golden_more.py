@@ -116,4 +116,26 @@ def gen_db_post():
     np.savez_compressed(os.path.join(GOLDEN, "db_post.npz"), **out)
 
 
-GENERATORS = {"convnextvit": gen_convnextvit, "db_post": gen_db_post}
+def gen_det_pre():
+    """Reference DetResizeForTest + NormalizeImage + ToCHWImage (db_pp/image_operators.py:78-118, 212-316) on odd page
+    sizes: resized shapes / ratios, and the normalised tensor of one small page."""
+    ref_import.setup()
+    from pdftable.model.db_pp.image_operators import DetResizeForTest, NormalizeImage, ToCHWImage
+
+    op = DetResizeForTest(limit_side_len=960, limit_type="max")
+    shapes = [(960, 960), (1000, 1500), (2875, 960), (700, 500), (33, 47), (20, 30), (1111, 1111), (480, 1919)]
+    rows = []
+    for h, w in shapes:
+        img = (np.arange(h * w * 3, dtype=np.int64) % 251).astype(np.uint8).reshape(h, w, 3)
+        d = op({"image": img})
+        rows.append([h, w, d["image"].shape[0], d["image"].shape[1], d["shape"][2], d["shape"][3]])
+    page = synth.synthetic_page(5, 100, 150)
+    d = op({"image": page[:, :, ::-1]})
+    d = NormalizeImage(scale=1.0 / 255.0, mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], order="hwc")(d)
+    d = ToCHWImage()(d)
+    np.savez_compressed(os.path.join(GOLDEN, "det_pre.npz"), table=np.array(rows, np.float64), page_chw=d["image"].astype(np.float32),
+                        page_shape=np.array(d["shape"], np.float64))
+    print("det_pre", np.array(rows)[:, 2:4].tolist(), d["image"].shape)
+
+
+GENERATORS = {"convnextvit": gen_convnextvit, "db_post": gen_db_post, "det_pre": gen_det_pre}

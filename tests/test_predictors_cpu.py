@@ -1,0 +1,54 @@
+"""Host-side logic of the predictor mirror (no GPU): resize rules vs the reference's golden numbers, error behaviour."""
+import os
+
+import numpy as np
+import pytest
+
+from pdf_table_b200 import predictors, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_det_resize_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "det_pre.npz"))
+    for h, w, rh, rw, ratio_h, ratio_w in g["table"]:
+        h, w = int(h), int(w)
+        img = (np.arange(h * w * 3, dtype=np.int64) % 251).astype(np.uint8).reshape(h, w, 3)
+        out, (a, b) = predictors.det_resize_for_test(img, 960, "max")
+        assert out.shape[:2] == (int(rh), int(rw))
+        assert a == ratio_h and b == ratio_w
+    # pixel values of the resized + normalised page (the GPU kernel's input/normalisation contract)
+    page = synth.synthetic_page(5, 100, 150)
+    res, _ = predictors.det_resize_for_test(page, 960, "max")
+    mean = np.array([0.485, 0.456, 0.406], np.float32).reshape(1, 1, 3)
+    std = np.array([0.229, 0.224, 0.225], np.float32).reshape(1, 1, 3)
+    x = (res[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean) / std
+    np.testing.assert_array_equal(x.transpose(2, 0, 1), g["page_chw"])
+
+
+def test_keepratio_resize_rules():
+    from oracle import convnextvit_ref
+
+    for h, w in [(32, 320), (48, 700), (20, 900), (64, 64), (32, 804), (10, 400)]:
+        crop = (np.arange(h * w * 3) % 255).astype(np.uint8).reshape(h, w, 3)
+        got = predictors.keepratio_resize(crop)
+        want = convnextvit_ref.keepratio_resize(crop)  # reference restatement incl. zero pad to 804
+        assert got.shape[0] == 32 and got.shape[1] <= 804
+        np.testing.assert_array_equal(want[:, : got.shape[1]], got)
+        assert (want[:, got.shape[1]:] == 0).all()
+
+
+def test_error_behaviour_without_gpu():
+    import torch
+
+    with pytest.raises(RuntimeError):
+        predictors.OcrDetectionTask(model="east", state_dict={})
+    with pytest.raises(RuntimeError):
+        predictors.OcrRecognitionTask(model="CRNN", state_dict={})
+    with pytest.raises(TypeError):
+        predictors._read_image(12345)
+    if not torch.cuda.is_available():
+        from pdf_table_b200._lib import DocVisionError
+
+        with pytest.raises(DocVisionError):  # no silent CPU fallback
+            predictors.OcrDetectionTask(model="db_pp", state_dict=synth.dbnet_r18_state_dict(0))

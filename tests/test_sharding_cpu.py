@@ -1,0 +1,56 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard a page/crop list, pack their (fake) decoded results and
+exchange them with the single all-gather of the path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pdf_table_b200 import sharding
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 32, 256, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sharding.shard_sizes(n, world)
+
+
+def _fake_results(p0, p1, c0, c1):
+    """Deterministic per-item results so the gathered tensors can be checked against a single-process run."""
+    pages = torch.arange(p0, p1)
+    boxes = (pages[:, None, None] * 1000 + torch.arange(5)[None, :, None] * 10 + torch.arange(8)[None, None, :]).float() + 0.5
+    counts = (pages % 6).int()
+    crops = torch.arange(c0, c1)
+    ids = (crops[:, None] * 7 + torch.arange(11)[None, :]).int() % 97
+    lens = (crops % 12).int()
+    return {"boxes": boxes, "box_counts": counts, "ids": ids, "id_lens": lens}
+
+
+def _worker(rank, world, port, n_pages, n_crops):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p0, p1 = sharding.shard_range(n_pages, rank, world)
+        c0, c1 = sharding.shard_range(n_crops, rank, world)
+        out = sharding.all_gather_results(_fake_results(p0, p1, c0, c1), sharding.shard_sizes(n_pages, world),
+                                          sharding.shard_sizes(n_crops, world))
+        want = _fake_results(0, n_pages, 0, n_crops)
+        for k in sharding.FIELDS:
+            assert torch.equal(out[k], want[k]), k
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_results_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, 7, 25), nprocs=2, join=True)
