@@ -209,16 +209,17 @@ long long dv_profile_report(dv_handle h, char* buf_host, size_t cap) {
                  first ? "" : ", ", r.kernel, r.layer.c_str(), ms, r.flops, r.bytes);
         js += line;
         first = false;
+    }
+    js += "]";
+    // A buffer that is too small leaves the records in place: the caller retries with the returned size.
+    if (!buf_host || js.size() + 1 > cap) return static_cast<long long>(js.size());
+    memcpy(buf_host, js.data(), js.size());
+    buf_host[js.size()] = 0;
+    for (auto& r : h->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
     h->prof.clear();
-    js += "]";
-    if (buf_host && cap > 0) {
-        const size_t n = js.size() < cap - 1 ? js.size() : cap - 1;
-        memcpy(buf_host, js.data(), n);
-        buf_host[n] = 0;
-    }
     return static_cast<long long>(js.size());
 }
 

@@ -925,7 +925,7 @@ k_db_compact(const float* __restrict__ slot_box, const int* __restrict__ slot_va
     int count = 0;
     for (int s0 = 0; s0 < kMaxSlots; s0 += 32) {
         const int s = s0 + lane;
-        const bool v = s < kMaxSlots && slot_valid[n * kMaxSlots + s] != 0;
+        const bool v = s < max_out && slot_valid[n * kMaxSlots + s] != 0;  // slots >= max_out hold stale flags
         const unsigned m = __ballot_sync(0xffffffffu, v);
         if (v) {
             const int pos = count + __popc(m & ((1u << lane) - 1u));

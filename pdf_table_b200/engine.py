@@ -81,7 +81,7 @@ class Engine:
                 check(n, self._h, "dv_profile_report")
             if n < cap:
                 return json.loads(buf.value.decode())
-            raise DocVisionError("profile report truncated; profile fewer launches per report")
+            cap = n + 1024  # records are kept until a report fits
 
     # ------------------------------------------------------------------ networks
     def dbnet_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

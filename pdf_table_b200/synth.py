@@ -244,3 +244,138 @@ def synthetic_prob_map(index: int, h: int = 960, w: int = 960, n_lines: int = 40
     for i in range(25):  # specks: tiny components that fail min_size or box_thresh
         add_rect(rng.uniform(5, w - 5), rng.uniform(5, h - 5), rng.uniform(1, 5), rng.uniform(1, 5), 0.0, rng.uniform(0.3, 0.9), 1.0)
     return prob
+
+
+# --------------------------------------------------------------------------- Lore (DLA-34 + DCNv2 detector, wtw)
+DLA_LEVELS = (1, 1, 1, 2, 2, 1)
+DLA_CHANNELS = (16, 32, 64, 128, 256, 512)
+LORE_HEADS = (("hm", 2), ("st", 8), ("wh", 8), ("ax", 256), ("cr", 256), ("reg", 2))
+
+
+def _dla_block(rng, sd, p, cin, cout):
+    sd[p + ".conv1.weight"] = _conv(rng, cout, cin, 3, 3)
+    _bn(rng, sd, p + ".bn1", cout)
+    sd[p + ".conv2.weight"] = _conv(rng, cout, cout, 3, 3, gain=1.0)
+    _bn(rng, sd, p + ".bn2", cout)
+
+
+def _dla_tree(rng, sd, p, levels, cin, cout, stride, level_root=False, root_dim=0):
+    """Parameter order of the reference Tree (center_net/modeling_centernet.py:209-287): tree1, tree2, root, project."""
+    if root_dim == 0:
+        root_dim = 2 * cout
+    if level_root:
+        root_dim += cin
+    if levels == 1:
+        _dla_block(rng, sd, p + ".tree1", cin, cout)
+        _dla_block(rng, sd, p + ".tree2", cout, cout)
+        sd[p + ".root.conv.weight"] = _conv(rng, cout, root_dim, 1, 1)
+        _bn(rng, sd, p + ".root.bn", cout)
+    else:
+        _dla_tree(rng, sd, p + ".tree1", levels - 1, cin, cout, stride)
+        _dla_tree(rng, sd, p + ".tree2", levels - 1, cout, cout, 1, root_dim=root_dim + cout)
+    if cin != cout:
+        sd[p + ".project.0.weight"] = _conv(rng, cout, cin, 1, 1, gain=1.0)
+        _bn(rng, sd, p + ".project.1", cout)
+
+
+def _dcn(rng, sd, p, cin, cout, off_std=0.5):
+    """DeformConv (lore_dla_34.py:65-85) = DCN (dcnv2.py:25-86) + BN + ReLU.  The reference zero-initialises
+    conv_offset_mask; here it is drawn so that offsets are O(off_std) pixels and the sampling path is exercised."""
+    _bn(rng, sd, p + ".actf.0", cout)
+    sd[p + ".conv.weight"] = _conv(rng, cout, cin, 3, 3)
+    sd[p + ".conv.bias"] = _b(rng, cout)
+    sd[p + ".conv.conv_offset_mask.weight"] = (_conv(rng, 27, cin, 3, 3, gain=1.0) * off_std).astype(np.float32)
+    sd[p + ".conv.conv_offset_mask.bias"] = _b(rng, 27, 0.2)
+
+
+def _bilinear_up(c, f):
+    """fill_up_weights (lore_dla_34.py:51-62): the fixed bilinear kernel every depthwise ConvTranspose2d starts from."""
+    k = 2 * f
+    ff = int(np.ceil(k / 2))
+    cc = (2 * ff - 1 - ff % 2) / (2.0 * ff)
+    w1 = np.array([1 - abs(i / ff - cc) for i in range(k)], np.float64)
+    w = np.outer(w1, w1).astype(np.float32)
+    return np.broadcast_to(w, (c, 1, k, k)).copy()
+
+
+def _ida(rng, sd, p, o, channels, up_f, perturb_up):
+    for i in range(1, len(channels)):
+        _dcn(rng, sd, f"{p}.proj_{i}", channels[i], o)
+        w = _bilinear_up(o, int(up_f[i]))
+        if perturb_up:  # trained checkpoints may carry non-bilinear kernels: keep the kernel general
+            w = (w * rng.uniform(0.8, 1.2, w.shape)).astype(np.float32)
+        sd[f"{p}.up_{i}.weight"] = w
+        _dcn(rng, sd, f"{p}.node_{i}", o, o)
+
+
+def lore_dla34_state_dict(seed: int = 0, perturb_up: bool = True) -> "OrderedDict[str, np.ndarray]":
+    """Keys / shapes of `get_dla_dcn(34, heads, head_conv=256)` (reference model/lore/lore_dla_34.py:140-206 over
+    `dla34` center_net/modeling_centernet.py:289-402).  `base.fc` (unused in the forward) is omitted."""
+    rng = np.random.Generator(np.random.PCG64(2000 + seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    ch = DLA_CHANNELS
+    sd["base.base_layer.0.weight"] = _conv(rng, ch[0], 3, 7, 7)
+    _bn(rng, sd, "base.base_layer.1", ch[0])
+    sd["base.level0.0.weight"] = _conv(rng, ch[0], ch[0], 3, 3)
+    _bn(rng, sd, "base.level0.1", ch[0])
+    sd["base.level1.0.weight"] = _conv(rng, ch[1], ch[0], 3, 3)
+    _bn(rng, sd, "base.level1.1", ch[1])
+    _dla_tree(rng, sd, "base.level2", DLA_LEVELS[2], ch[1], ch[2], 2, level_root=False)
+    _dla_tree(rng, sd, "base.level3", DLA_LEVELS[3], ch[2], ch[3], 2, level_root=True)
+    _dla_tree(rng, sd, "base.level4", DLA_LEVELS[4], ch[3], ch[4], 2, level_root=True)
+    _dla_tree(rng, sd, "base.level5", DLA_LEVELS[5], ch[4], ch[5], 2, level_root=True)
+    # DLAUp (lore_dla_34.py:113-137) over channels[2:] = [64,128,256,512], scales [1,2,4,8]
+    channels = list(ch[2:])
+    in_channels = list(channels)
+    scales = np.array([1, 2, 4, 8], dtype=int)
+    for i in range(len(channels) - 1):
+        j = -i - 2
+        _ida(rng, sd, f"dla_up.ida_{i}", channels[j], in_channels[j:], scales[j:] // scales[j], perturb_up)
+        scales[j + 1:] = scales[j]
+        in_channels[j + 1:] = [channels[j] for _ in channels[j + 1:]]
+    _ida(rng, sd, "ida_up", ch[2], list(ch[2:5]), [1, 2, 4], perturb_up)
+    for head, classes in LORE_HEADS:
+        sd[f"{head}.0.weight"] = _conv(rng, 256, ch[2], 3, 3)
+        sd[f"{head}.0.bias"] = _b(rng, 256)
+        sd[f"{head}.2.weight"] = _conv(rng, classes, 256, 1, 1, gain=1.0)
+        sd[f"{head}.2.bias"] = _b(rng, classes) if head != "hm" else np.full(classes, -2.19, np.float32)
+    return sd
+
+
+def lore_processor_state_dict(seed: int = 0, layers: int = 4, stacking_layers: int = 4) -> "OrderedDict[str, np.ndarray]":
+    """Keys / shapes of `LoreProcessModel` (reference model/lore/lore_processor.py:399-514), wtw configuration
+    (tsfm_layers = stacking_layers = 4, d = 256, 8 heads, FFN 2048)."""
+    rng = np.random.Generator(np.random.PCG64(3000 + seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    d, dff = 256, 2048
+
+    def lin(p, cout, cin, gain=1.0):
+        sd[p + ".weight"] = _lin(rng, cout, cin, gain)
+        sd[p + ".bias"] = _b(rng, cout)
+
+    def norm(p):
+        sd[p + ".alpha"] = rng.uniform(0.5, 1.5, d).astype(np.float32)
+        sd[p + ".bias"] = _b(rng, d)
+
+    def transformer(p, cin, n_layers):
+        lin(p + ".linear", d, cin)
+        for L in range(n_layers):
+            lp = f"{p}.encoder.layers.{L}"
+            norm(lp + ".norm_1")
+            norm(lp + ".norm_2")
+            for n in ("q_linear", "v_linear", "k_linear"):
+                lin(f"{lp}.attn.{n}", d, d)
+            lin(lp + ".attn.out", d, d, 0.5)
+            lin(lp + ".ff.linear_1", dff, d, 2.0)
+            lin(lp + ".ff.linear_2", d, dff, 0.5)
+        norm(p + ".encoder.norm")
+        lin(p + ".decoder.linear.0", d, d, 2.0)
+        lin(p + ".decoder.linear.2", 4, d, 2.0)
+
+    lin("stacker.logi_encoder.0", d, 4, 2.0)
+    lin("stacker.logi_encoder.2", d, d, 2.0)
+    transformer("stacker.tsfm", 2 * d, stacking_layers)
+    transformer("tsfm_axis", d, layers)
+    sd["x_position_embeddings.weight"] = _b(rng, 256 * d, 1.0).reshape(256, d)
+    sd["y_position_embeddings.weight"] = _b(rng, 256 * d, 1.0).reshape(256, d)
+    return sd
