@@ -379,3 +379,70 @@ def lore_processor_state_dict(seed: int = 0, layers: int = 4, stacking_layers: i
     sd["x_position_embeddings.weight"] = _b(rng, 256 * d, 1.0).reshape(256, d)
     sd["y_position_embeddings.weight"] = _b(rng, 256 * d, 1.0).reshape(256, d)
     return sd
+
+
+# --------------------------------------------------------------------------- planted Lore head maps
+def lore_planted_maps(index: int, h: int = 128, w: int = 128, feat_dim: int = 256, with_feat: bool = True):
+    """Head outputs of a Lore detector for a planted ruled table (numpy only, deterministic): `hm` [2,h,w] AFTER the
+    sigmoid (class 0 = cell centres, class 1 = corner points), `reg` [2,h,w], `wh` [8,h,w], `st` [8,h,w] and, when
+    with_feat, random `ax` / `cr` [feat_dim,h,w].  A jittered rows x cols grid: every cell gets a centre peak whose
+    `wh` points (noisily) at its four corners; every grid intersection gets a corner peak whose `st` spans a small
+    cross reaching into the adjacent cells.  Some peaks are weak (below the 0.2 / 0.3 gates, or weak enough that the
+    x0.4 penalty drops them), some corners are missing, and a low random floor creates thousands of sub-threshold
+    local maxima, so every branch of the reference's decode is exercised."""
+    rng = np.random.default_rng(777000 + index)
+    hm = (rng.random((2, h, w)) * 0.12).astype(np.float32)
+    reg = rng.random((2, h, w)).astype(np.float32)
+    wh = (rng.standard_normal((8, h, w)) * 2).astype(np.float32)
+    st = (rng.standard_normal((8, h, w)) * 2).astype(np.float32)
+    rows, cols = int(rng.integers(3, 9)), int(rng.integers(3, 8))
+    x0, y0 = rng.uniform(4, 0.15 * w), rng.uniform(4, 0.15 * h)
+    x1, y1 = rng.uniform(0.8 * w, w - 5), rng.uniform(0.8 * h, h - 5)
+    gx = np.sort(np.concatenate([[x0, x1], rng.uniform(x0 + 6, x1 - 6, cols - 1)]))
+    gy = np.sort(np.concatenate([[y0, y1], rng.uniform(y0 + 6, y1 - 6, rows - 1)]))
+    skew = rng.uniform(-0.04, 0.04)
+    px = lambda r, c: np.float32(gx[c] + skew * (gy[r] - y0) + rng.normal(0, 0.15))
+    py = lambda r, c: np.float32(gy[r] + skew * (gx[c] - x0) + rng.normal(0, 0.15))
+    P = np.array([[(px(r, c), py(r, c)) for c in range(cols + 1)] for r in range(rows + 1)], np.float32)
+
+    def plant(cls, x, y, score):
+        ix, iy = int(np.floor(x)), int(np.floor(y))
+        if not (1 <= ix < w - 1 and 1 <= iy < h - 1):
+            return None
+        hm[cls, iy - 1:iy + 2, ix - 1:ix + 2] = np.minimum(hm[cls, iy - 1:iy + 2, ix - 1:ix + 2], np.float32(score * 0.5))
+        hm[cls, iy, ix] = np.float32(score)
+        reg_here = reg[:, iy, ix]
+        return ix, iy, np.float32(ix) + reg_here[0], np.float32(iy) + reg_here[1]
+
+    for r in range(rows):
+        for c in range(cols):
+            if rng.random() < 0.05:
+                continue  # undetected cell
+            quad = np.array([P[r, c], P[r, c + 1], P[r + 1, c + 1], P[r + 1, c]], np.float32)
+            cx, cy = quad.mean(0)
+            score = rng.uniform(0.22, 0.98) if rng.random() < 0.85 else rng.uniform(0.1, 0.2)
+            got = plant(0, cx, cy, score)
+            if got is None:
+                continue
+            ix, iy, fx, fy = got
+            noisy = quad + rng.normal(0, 0.6, quad.shape).astype(np.float32)
+            wh[0::2, iy, ix] = fx - noisy[:, 0]
+            wh[1::2, iy, ix] = fy - noisy[:, 1]
+    for r in range(rows + 1):
+        for c in range(cols + 1):
+            if rng.random() < 0.12:
+                continue  # missing corner -> some cells end with count <= 2
+            score = rng.uniform(0.32, 0.97) if rng.random() < 0.9 else rng.uniform(0.15, 0.3)
+            got = plant(1, P[r, c, 0], P[r, c, 1], score)
+            if got is None:
+                continue
+            ix, iy, fx, fy = got
+            arm = rng.uniform(1.5, 4.0)
+            cross = np.array([[-arm, -arm], [arm, -arm], [arm, arm], [-arm, arm]], np.float32) + rng.normal(0, 0.3, (4, 2)).astype(np.float32)
+            st[0::2, iy, ix] = -cross[:, 0]
+            st[1::2, iy, ix] = -cross[:, 1]
+    out = {"hm": hm, "reg": reg, "wh": wh, "st": st}
+    if with_feat:
+        out["ax"] = rng.standard_normal((feat_dim, h, w)).astype(np.float32)
+        out["cr"] = rng.standard_normal((feat_dim, h, w)).astype(np.float32)
+    return out

@@ -1,0 +1,92 @@
+"""Lore oracle restatements vs the golden fixtures produced by the reference's own modules
+(oracle/gen_golden_lore.py, run in the build container)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import lore_decode_ref, lore_net_ref, lore_processor_ref
+from pdf_table_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DECODE_CASES = [("t0", 0, 128, 128), ("t1", 1, 128, 128), ("t2", 2, 96, 160), ("t3", 3, 256, 256)]
+
+
+def test_lore_network_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "lore_dla34_seed0.npz"))
+    sd = synth.lore_dla34_state_dict(0)
+    for tv in (True, False):  # torchvision.ops.deform_conv2d and its plain-torch restatement
+        out = lore_net_ref.lore_dla34_forward(sd, torch.from_numpy(g["x"]), use_torchvision=tv)
+        for k in ("hm", "st", "wh", "ax", "cr", "reg"):
+            np.testing.assert_allclose(out[k].numpy(), g[k], atol=2e-5, rtol=0, err_msg=f"{k} tv={tv}")
+
+
+def test_deform_conv_restatement_matches_torchvision():
+    from torchvision.ops import deform_conv2d
+
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 16, 12, 20, generator=gen)
+    off = torch.randn(2, 18, 12, 20, generator=gen) * 3  # samples far outside the image included
+    mask = torch.rand(2, 9, 12, 20, generator=gen)
+    w, b = torch.randn(8, 16, 3, 3, generator=gen), torch.randn(8, generator=gen)
+    want = deform_conv2d(x, off, w, b, padding=(1, 1), mask=mask)
+    got = lore_net_ref.deform_conv2d_ref(x, off, w, b, mask)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=1e-5, rtol=0)
+
+
+def test_lore_decode_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "lore_decode.npz"))
+    for name, idx, h, w in DECODE_CASES:
+        m = synth.lore_planted_maps(idx, h, w)
+        out = lore_decode_ref.lore_decode(m["hm"], m["reg"], m["wh"], m["st"], m["ax"], m["cr"], g[name + "_meta"])
+        res = g[name + "_results"]
+        n = len(g[name + "_logi_feat"])
+        assert n > 0 and len(out["polygons"]) == n, name
+        np.testing.assert_array_equal(out["polygons"], res[:n, :8], err_msg=name)
+        np.testing.assert_array_equal(out["scores"], res[:n, 8], err_msg=name)
+        np.testing.assert_array_equal(out["dets_feat"], g[name + "_dets_feat"], err_msg=name)
+        np.testing.assert_allclose(out["logi_feat"], g[name + "_logi_feat"], atol=1e-6, rtol=0, err_msg=name)
+        # every row the x0.4 penalty could have produced from a >= 0.2 cell is also in reference order
+        m08 = int((res[:, 8] >= 0.08).sum())
+        np.testing.assert_array_equal(out["all_scores"][:m08], res[:m08, 8], err_msg=name)
+
+
+def test_lore_decode_known_answer():
+    """One cell whose four corners each have a detected corner point inside it: the corners snap to the corner
+    points, the score is kept, and the polygon maps back to source pixels through the inverse affine."""
+    h = w = 80
+    hm = np.zeros((2, h, w), np.float32)
+    reg = np.full((2, h, w), 0.5, np.float32)
+    wh = np.zeros((8, h, w), np.float32)
+    st = np.zeros((8, h, w), np.float32)
+    hm[0, 40, 40] = 0.9
+    corners = [(30, 30), (50, 30), (50, 50), (30, 50)]
+    for k, (x, y) in enumerate(corners):
+        hm[1, y, x] = 0.8 - 0.01 * k
+        wh[2 * k, 40, 40] = 40.5 - (x + 0.5) + (1.0 if x < 40 else -1.0) * -1.5  # predicted corner 1.5 px outside
+        wh[2 * k + 1, 40, 40] = 40.5 - (y + 0.5) + (1.0 if y < 40 else -1.0) * -1.5
+        # the corner's own 4-point box reaches 3 px diagonally into each neighbouring cell
+        for q, (dx, dy) in enumerate([(-3, -3), (3, -3), (3, 3), (-3, 3)]):
+            st[2 * q, y, x], st[2 * q + 1, y, x] = -dx, -dy
+    ax = np.zeros((4, h, w), np.float32)
+    cr = np.zeros((4, h, w), np.float32)
+    meta = np.array([160, 160, 320, 320, 320, 80, 80])
+    out = lore_decode_ref.lore_decode(hm, reg, wh, st, ax, cr, meta)
+    assert len(out["polygons"]) == 1
+    np.testing.assert_array_equal(out["scores"], np.float32([0.9]))
+    np.testing.assert_array_equal(out["dets_feat"][0], [30, 30, 50, 30, 50, 50, 30, 50])
+    np.testing.assert_allclose(out["polygons"][0], np.float32([30.5, 30.5, 50.5, 30.5, 50.5, 50.5, 30.5, 50.5]) * 4, atol=1e-4)
+
+
+def test_lore_processor_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "lore_processor_seed0.npz"))
+    sd = synth.lore_processor_state_dict(0)
+    for n in (1, 7, 64, 200):
+        logic, stacked = lore_processor_ref.lore_processor_forward(sd, torch.from_numpy(g[f"n{n}_feat"]))
+        np.testing.assert_allclose(logic.numpy(), g[f"n{n}_logic"], atol=1e-5, rtol=0)
+        np.testing.assert_allclose(stacked.numpy(), g[f"n{n}_stacked"], atol=1e-5, rtol=0)
+
+
+def test_round_logic_is_half_down():
+    x = np.float32([0.5, 1.5, 2.5000002, 3.49, 0.0, 7.51])
+    np.testing.assert_array_equal(lore_decode_ref.round_logic(x), np.float32([0, 1, 3, 3, 0, 8]))
