@@ -126,6 +126,42 @@ int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, co
                 int32_t* overflow_host);
 
 /*
+ * Lore / CenterNet "heat-map 3x3 max-pool NMS + top-K gather": head maps -> sorted table cells, on the device.
+ * Replaces process_detect_output (lore/lineless_table_process.py:592-655) called from LoreModel.forward
+ * (lore/modeling_lore.py:146-152): corner_decode :97-124, ctdet_4ps_decode incl. the wiz_rev corner snapping
+ * :127-267, ctdet_4ps_post_process :489-507, merge_outputs / filter / normalized_ps :551-589.
+ *   hm, reg, wh, st : fp32 head maps (device).  layout 0: four NCHW tensors [n,2,h,w], [n,2,h,w], [n,8,h,w], [n,8,h,w];
+ *                     layout 1: one NHWC tensor [n,h,w,24] passed as `hm` (channels hm0,hm1,reg0,reg1,wh0-7,st0-7,pad4;
+ *                     reg/wh/st ignored).  `hm` is the map AFTER the sigmoid (the reference's first step, :599).
+ *   inv_affine_host : HOST [n][6] doubles, the row-major 2x3 matrix get_affine_transform(c, s, 0, (out_w, out_h), inv=1)
+ *                     (:403-438) built from the reference's int64 meta (lore/processer_lore.py:112-130)
+ *   K, MK           : top-K cells / corners (reference 3000 / 5000); wiz_rev, vis_thresh: LoreConfig (wtw: 1, 0.2)
+ *   polygons  [n][K][8] fp32 : cell corners in source pixels, rows in the reference's (re-sorted) order = results[1][:, :8]
+ *   scores    [n][K]    fp32 : penalised scores = results[1][:, 8]
+ *   dets_feat [n][K][8] int32: slct_dets_feat (feature-map corner coordinates truncated and clamped to 0..255)
+ *   ax_idx [n][K], cr_idx [n][K][4] int32 : flat h*w indices the logical feature of row j is gathered from
+ *                     (`ax` at the cell centre, `cr` at the four cc_match corners -- dv_lore_gather_logi)
+ *   counts [n] int32 : rows with score >= vis_thresh (= num_valid); rows [n] int32 or NULL: rows written per image.
+ *                     Rows are written for every peak above min(0.2, vis_thresh); the reference's remaining top-K
+ *                     padding (NMS-suppressed zeros at arbitrary positions) is never selected and is not produced.
+ *   overflow_host   : HOST int32 or NULL; non-zero if an image had more than 16384 gated peaks of one class
+ */
+int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* wh, const float* st, int layout, int n,
+                   int height, int width, const double* inv_affine_host, int K, int MK, int wiz_rev, float vis_thresh,
+                   float* polygons, float* scores, int32_t* dets_feat, int32_t* ax_idx, int32_t* cr_idx, int32_t* counts,
+                   int32_t* rows, int32_t* overflow_host);
+
+/*
+ * Logical-location features of the selected cells from DENSE `ax` / `cr` maps ([n,channels,h,w] fp32, NCHW):
+ * logi_feat[i][j] = ax[:, ax_idx[j]] + sum_k cr[:, cr_idx[j][k]] for j < counts[i]   ([n][K][channels] fp32).
+ * Replaces _tranpose_and_gather_feat(ax) + _get_4ps_feat(cc_match, cr).sum(3) + `logi + cr`
+ * (lore/lineless_table_process.py:31-63, 148, 253-254, 644).  The network path computes the same rows without ever
+ * materialising the dense 512-channel maps (dv_lore_forward).
+ */
+int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, int channels, int height, int width, int K,
+                        const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat);
+
+/*
  * ConvNextViT text-line recogniser forward.
  * Replaces OcrRecognitionTask._run_model for model="ConvNextViT" (ocr_recognition_task.py:81-116) =
  * OCRRecognition.forward (ocr_recognition/modeling_ocr_recognition.py:137-149) -> ConvNextViT.forward

@@ -268,6 +268,50 @@ int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, co
                     counts_out, overflow_host);
 }
 
+int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* wh, const float* st, int layout, int n,
+                   int height, int width, const double* inv_affine_host, int K, int MK, int wiz_rev, float vis_thresh,
+                   float* polygons, float* scores, int32_t* dets_feat, int32_t* ax_idx, int32_t* cr_idx, int32_t* counts,
+                   int32_t* rows, int32_t* overflow_host) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    LoreMaps m;
+    const long long hw = static_cast<long long>(height) * width;
+    if (layout == 0) {
+        m.hm = hm;
+        m.reg = reg;
+        m.wh = wh;
+        m.st = st;
+        const int ch[4] = {2, 2, 8, 8};
+        for (int i = 0; i < 4; ++i) {
+            m.img_stride[i] = ch[i] * hw;
+            m.chan_stride[i] = hw;
+            m.pix_stride[i] = 1;
+        }
+    } else if (layout == 1) {
+        if (!hm) return set_err(h, DV_ERR_ARG, "dv_lore_decode: null map");
+        m.hm = hm;
+        m.reg = hm + 2;
+        m.wh = hm + 4;
+        m.st = hm + 12;
+        for (int i = 0; i < 4; ++i) {
+            m.img_stride[i] = 24 * hw;
+            m.chan_stride[i] = 1;
+            m.pix_stride[i] = 24;
+        }
+    } else {
+        return set_err(h, DV_ERR_ARG, "dv_lore_decode: layout must be 0 (NCHW) or 1 (NHWC x24)");
+    }
+    return lore_decode(h, m, n, height, width, inv_affine_host, K, MK, wiz_rev, vis_thresh, polygons, scores, dets_feat, ax_idx,
+                       cr_idx, counts, rows, overflow_host);
+}
+
+int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, int channels, int height, int width, int K,
+                        const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return lore_gather_logi(h, ax, cr, n, channels, height, width, K, counts, ax_idx, cr_idx, logi_feat);
+}
+
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out) {
     if (!h) return DV_ERR_ARG;

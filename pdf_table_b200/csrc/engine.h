@@ -170,6 +170,19 @@ double cnv_flops(Engine* e);
 int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* src_hw_host, float thresh, double box_thresh,
              double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host);
 
+// lore_decode.cu
+// The four small Lore head maps as strided fp32 views: element (n, c, pixel) of map m = ptr[n*img + c*chan + pixel*pix].
+// Order of the stride arrays: hm (AFTER sigmoid), reg, wh, st.
+struct LoreMaps {
+    const float *hm = nullptr, *reg = nullptr, *wh = nullptr, *st = nullptr;
+    long long img_stride[4] = {0, 0, 0, 0}, chan_stride[4] = {0, 0, 0, 0}, pix_stride[4] = {1, 1, 1, 1};
+};
+int lore_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const double* trans_host, int K, int MK, int wiz_rev,
+                float vis_thresh, float* polygons, float* scores, int32_t* dets_feat, int32_t* ax_idx, int32_t* cr_idx,
+                int32_t* counts, int32_t* rows, int32_t* overflow_host);
+int lore_gather_logi(Engine* e, const float* ax, const float* cr, int N, int C, int H, int W, int K, const int32_t* counts,
+                     const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat);
+
 // ctc.cu
 int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,
                  int32_t* out_len, float* out_conf);

@@ -192,6 +192,57 @@ class Engine:
             return boxes, counts, int(ovf.value)
         return boxes, counts
 
+    def lore_decode(self, hm: torch.Tensor, reg: Optional[torch.Tensor], wh: Optional[torch.Tensor], st: Optional[torch.Tensor],
+                    inv_affine, K: int = 3000, MK: int = 5000, wiz_rev: bool = True, vis_thresh: float = 0.2,
+                    check_overflow: bool = False):
+        """Lore head maps -> sorted cells.  Either four NCHW fp32 tensors (hm AFTER sigmoid [N,2,H,W], reg [N,2,H,W],
+        wh [N,8,H,W], st [N,8,H,W]) or one packed NHWC [N,H,W,24] tensor as `hm` with reg = wh = st = None.
+        inv_affine: [N,2,3] float64 (host).  Returns a dict of device tensors: polygons [N,K,8], scores [N,K],
+        dets_feat [N,K,8] int32, ax_idx [N,K] int32, cr_idx [N,K,4] int32, counts [N] int32, rows [N] int32."""
+        hm = _require_cuda(hm, torch.float32, "hm")
+        if reg is None:
+            n, h, w, c = hm.shape
+            if c != 24:
+                raise ValueError("packed Lore maps must be [N,H,W,24]")
+            layout = 1
+        else:
+            reg, wh, st = (_require_cuda(t, torch.float32, nm) for t, nm in ((reg, "reg"), (wh, "wh"), (st, "st")))
+            n, c, h, w = hm.shape
+            if c != 2 or tuple(reg.shape) != (n, 2, h, w) or tuple(wh.shape) != (n, 8, h, w) or tuple(st.shape) != (n, 8, h, w):
+                raise ValueError("Lore maps must be hm [N,2,H,W], reg [N,2,H,W], wh [N,8,H,W], st [N,8,H,W]")
+            layout = 0
+        tr = np.ascontiguousarray(np.asarray(inv_affine, np.float64).reshape(n, 6))
+        dev = hm.device
+        out = {
+            "polygons": torch.empty((n, K, 8), dtype=torch.float32, device=dev),
+            "scores": torch.empty((n, K), dtype=torch.float32, device=dev),
+            "dets_feat": torch.empty((n, K, 8), dtype=torch.int32, device=dev),
+            "ax_idx": torch.empty((n, K), dtype=torch.int32, device=dev),
+            "cr_idx": torch.empty((n, K, 4), dtype=torch.int32, device=dev),
+            "counts": torch.empty((n,), dtype=torch.int32, device=dev),
+            "rows": torch.empty((n,), dtype=torch.int32, device=dev),
+        }
+        ovf = C.c_int32(0)
+        check(self._lib.dv_lore_decode(self._h, _ptr(hm), _ptr(reg), _ptr(wh), _ptr(st), layout, n, h, w,
+                                       tr.ctypes.data_as(C.POINTER(C.c_double)), int(K), int(MK), int(bool(wiz_rev)), float(vis_thresh),
+                                       _ptr(out["polygons"]), _ptr(out["scores"]), _ptr(out["dets_feat"]), _ptr(out["ax_idx"]),
+                                       _ptr(out["cr_idx"]), _ptr(out["counts"]), _ptr(out["rows"]),
+                                       C.byref(ovf) if check_overflow else None), self._h, "dv_lore_decode")
+        if check_overflow:
+            out["overflow"] = int(ovf.value)
+        return out
+
+    def lore_gather_logi(self, ax: torch.Tensor, cr: torch.Tensor, dec: dict) -> torch.Tensor:
+        """Dense ax / cr [N,C,H,W] fp32 + the output of lore_decode -> logi_feat [N,K,C] fp32 (rows < counts[n] written)."""
+        ax = _require_cuda(ax, torch.float32, "ax")
+        cr = _require_cuda(cr, torch.float32, "cr")
+        n, c, h, w = ax.shape
+        k = dec["ax_idx"].shape[1]
+        out = torch.zeros((n, k, c), dtype=torch.float32, device=ax.device)
+        check(self._lib.dv_lore_gather_logi(self._h, _ptr(ax), _ptr(cr), n, c, h, w, k, _ptr(dec["counts"]), _ptr(dec["ax_idx"]),
+                                            _ptr(dec["cr_idx"]), _ptr(out)), self._h, "dv_lore_gather_logi")
+        return out
+
     def ctc_greedy(self, probs: torch.Tensor, blank: int = 0, return_raw: bool = False):
         """[B,T,C] fp32 (cuda) -> (ids [B,T] int32 left-packed / -1 padded, len [B] int32, conf [B] fp32)."""
         probs = _require_cuda(probs, torch.float32, "probs")
