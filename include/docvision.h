@@ -53,6 +53,8 @@ const char* dv_last_error(dv_handle h);
  *                "dbnet_r18"     DBNet ResNet-18 text detector   (reference model/db_net/dbnet.py:715-728)
  *                "convnext_vit"  ConvNextViT text-line recogniser (reference model/convnext_vit/
  *                                modeling_convnext_vit.py:20-45)
+ *                "lore_dla34"    Lore table-structure detector, DLA-34 + DCNv2 (reference model/lore/lore_dla_34.py:193)
+ *                "lore_processor" Lore logical-location transformers (reference model/lore/lore_processor.py:399)
  *   weight_blob: HOST pointer to a blob written by pdf_table_b200.weights.pack_* (may be NULL for "post")
  * Replaces: BaseInferTask._get_inference_model / DeployUtils.model_eval (base_infer_task.py:146-169,
  * utils/deploy_utils.py:226-240).
@@ -160,6 +162,50 @@ int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* 
  */
 int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, int channels, int height, int width, int K,
                         const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat);
+
+/*
+ * Lore table-structure detector (model kind "lore_dla34"): DLA-34 + DCNv2 neck + the four small heads.
+ * Replaces LoreModel.forward's `self.detect_infer_model(pixel_values)` (lore/modeling_lore.py:143) =
+ * DLASeg.forward (lore/lore_dla_34.py:176-190) for get_dla_dcn(34, {'hm':2,'st':8,'wh':8,'ax':256,'cr':256,'reg':2}).
+ *   in_nchw_f32 : [n,3,height,width] fp32, the output of TableLorePreProcessor (lore/processer_lore.py:66-109);
+ *                 height, width multiples of 32 (1024 x 1024 for the wtw configuration)
+ *   _u8 variant : images_hwc_u8 [n,height,width,3] = the warpAffine output; ((x / 255. - mean) / std) is evaluated in
+ *                 float64 as numpy does (:92) and fused into the stem's input kernel; flip swaps channels 0 and 2
+ *   maps_out    : [n,height/4,width/4,24] fp32 NHWC or NULL (kept inside the handle): hm0,hm1 (AFTER sigmoid), reg0,reg1,
+ *                 wh0-7, st0-7, 4 pad -- the `layout 1` input of dv_lore_decode.
+ * The 256-channel `ax` / `cr` heads are NOT evaluated densely (the reference only gathers them at the selected
+ * cells): the 64-channel feature map stays resident in the handle for dv_lore_cell_features.
+ */
+int dv_lore_detect_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out);
+int dv_lore_detect_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                              const float* std3_host, int flip, float* maps_out);
+
+/*
+ * Logical-location features of the selected cells, computed from the feature map of the last dv_lore_detect_forward
+ * on this handle: the `ax` head (3x3 conv + ReLU + 1x1) at each cell centre plus the `cr` head at its four cc_match
+ * corners.  Same values as gathering the reference's dense maps (dv_lore_gather_logi), at 5 x cells rows instead of
+ * height/4 x width/4 pixels.  Replaces the `ax` / `cr` heads of DLASeg.forward together with
+ * _tranpose_and_gather_feat / _get_4ps_feat (lore/lineless_table_process.py:31-63).
+ *   counts [n], ax_idx [n][K], cr_idx [n][K][4] : outputs of dv_lore_decode (device)
+ *   max_rows     : capacity of the packed row list (sum of counts over the batch must fit)
+ *   logi_feat    : [max_rows][256] fp32 (device); image i's cells occupy rows offsets[i] .. offsets[i+1]
+ *   offsets_out  : [n+1] int32 (device) or NULL; offsets_out[n] = total rows (the n_rows_dev of dv_lore_process_forward)
+ *   overflow_host: HOST int32 or NULL; receives the total when it exceeds max_rows (non-NULL makes the call synchronous)
+ */
+int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
+                          float* logi_feat, int32_t* offsets_out, int32_t* overflow_host);
+
+/*
+ * Lore logical-location processor (model kind "lore_processor").
+ * Replaces LoreProcessModel.forward, evaluation branch without 2-D position embeddings (wtw)
+ * (lore/lore_processor.py:465-514) called from LoreModel.forward (lore/modeling_lore.py:158-166).
+ *   feat       : [max_rows][256] fp32 (device) cell features; n_rows_dev: device int32, number of valid rows
+ *   offsets    : [n_images+1] int32 (device): attention runs inside each image's row segment
+ *   logic_out  : [max_rows][4] fp32 or NULL (base regressor); stacked_out: [max_rows][4] fp32 (stacking regressor =
+ *                the `logits` the task rounds with process_logic_output)
+ */
+int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
+                            float* logic_out, float* stacked_out);
 
 /*
  * ConvNextViT text-line recogniser forward.

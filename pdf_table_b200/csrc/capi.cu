@@ -144,6 +144,10 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = dbnet_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
+        } else if (e->kind == "lore_dla34") {
+            rc = lore_create(e);
+        } else if (e->kind == "lore_processor") {
+            rc = lore_proc_create(e);
         } else {
             rc = set_err(e, DV_ERR_UNSUPPORTED, "dv_create: unknown model kind '%s'", model_kind);
         }
@@ -227,6 +231,7 @@ double dv_model_flops(dv_handle h) {
     if (!h) return 0.0;
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
+    if (h->kind == "lore_dla34") return lore_flops(h);
     return 0.0;
 }
 
@@ -249,6 +254,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
     if (!h || !name) return DV_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
+    if (h->kind == "lore_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
     return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
 }
 
@@ -310,6 +316,35 @@ int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, in
     if (!h) return DV_ERR_ARG;
     cudaSetDevice(h->device);
     return lore_gather_logi(h, ax, cr, n, channels, height, width, K, counts, ax_idx, cr_idx, logi_feat);
+}
+
+int dv_lore_detect_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out) {
+    if (!h) return DV_ERR_ARG;
+    if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_lore_detect_forward: null input");
+    cudaSetDevice(h->device);
+    return lore_detect_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0, n, height, width, maps_out);
+}
+
+int dv_lore_detect_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                              const float* std3_host, int flip, float* maps_out) {
+    if (!h) return DV_ERR_ARG;
+    if (!images_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_lore_detect_forward_u8: null input");
+    cudaSetDevice(h->device);
+    return lore_detect_forward(h, nullptr, images_hwc_u8, mean3_host, std3_host, flip, n, height, width, maps_out);
+}
+
+int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
+                          float* logi_feat, int32_t* offsets_out, int32_t* overflow_host) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return lore_cell_features(h, n, K, max_rows, counts, ax_idx, cr_idx, logi_feat, offsets_out, overflow_host);
+}
+
+int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
+                            float* logic_out, float* stacked_out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return lore_process_forward(h, feat, max_rows, n_rows_dev, offsets, n_images, logic_out, stacked_out);
 }
 
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,

@@ -51,11 +51,21 @@ struct BlobTensor {
     uint64_t nbytes = 0;
 };
 
-// NHWC fp16 activation tensor (dense: C channels per pixel)
+// NHWC fp16 activation tensor.  ld = elements between consecutive pixels (0 = dense, C); a channel slice of a
+// wider (concatenation) buffer is a Tensor with p offset to its first channel and ld = the buffer's width.
 struct Tensor {
     __half* p = nullptr;
     int N = 0, H = 0, W = 0, C = 0;
+    int ld = 0;
+    int ldc() const { return ld ? ld : C; }
     size_t elems() const { return static_cast<size_t>(N) * H * W * C; }
+    Tensor slice(int coff, int c) const {
+        Tensor t = *this;
+        t.p = p + coff;
+        t.C = c;
+        t.ld = ldc();
+        return t;
+    }
 };
 
 struct ConvSpec {
@@ -64,8 +74,9 @@ struct ConvSpec {
     int BK = 64, Cin_pad = 0;  // packing of the weight matrix: [Cout][KH*KW*Cin_pad]
     const __half* w = nullptr;
     const float* bias = nullptr;  // padded to a multiple of 256 floats, or nullptr
-    bool stem = false;            // 7x7 s2 on the padded 4-channel image (A_STEM)
+    bool stem = false;            // 7x7 on the padded image (A_STEM): stride 2 on 4 channels, stride 1 on 8 channels
     bool flat = false;            // force A_FLAT (1x1 stride 1 / linear)
+    bool split = false;           // A_FLAT split-fp16: A = [hi | lo] (2K columns), W = [W_hi | W_lo | W_hi] (3K)
 };
 
 struct EpiSpec {
@@ -78,6 +89,8 @@ struct EpiSpec {
     int out_mode = OUT_NHWC;
     void* out = nullptr;
     int out_ld = 0, out_coff = 0, rep = 1, out_f32 = 0;
+    const int* m_dyn = nullptr;  // A_FLAT: device row count (see IGemmParams::m_dyn)
+    int split_off = 0;           // fp16 out: also store the fp16 residual at column + split_off
 };
 
 struct ConvPlan {
@@ -139,7 +152,7 @@ struct Engine {
 int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
               ConvPlan* plan, const char* name);
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
-                ConvPlan* plan, const char* name);
+                ConvPlan* plan, const char* name, int lda = 0);
 int launch_conv(Engine* e, const ConvPlan& plan);
 
 // ops.cu (simple HBM-bound kernels)
@@ -182,6 +195,18 @@ int lore_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const doub
                 int32_t* counts, int32_t* rows, int32_t* overflow_host);
 int lore_gather_logi(Engine* e, const float* ax, const float* cr, int N, int C, int H, int W, int K, const int32_t* counts,
                      const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat);
+
+// lore_net.cu / lore_proc.cu
+int lore_create(Engine* e);
+double lore_flops(Engine* e);
+int lore_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4);
+int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, int flip, int N,
+                        int H, int W, float* maps_out);
+int lore_cell_features(Engine* e, int N, int K, int cap, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
+                       float* logi_feat, int32_t* offsets_out, int32_t* overflow_host);
+int lore_proc_create(Engine* e);
+int lore_process_forward(Engine* e, const float* feat, int cap_rows, const int32_t* rows_dev, const int32_t* offsets, int n_img,
+                         float* logic_out, float* stacked_out);
 
 // ctc.cu
 int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,

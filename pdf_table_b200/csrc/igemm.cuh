@@ -42,6 +42,8 @@ __device__ __forceinline__ float apply_act(float x) {
 // one epilogue thread sees every column of its row.
 struct TileIter {
     int j = 0;
+    int m_tiles;
+    __device__ __forceinline__ explicit TileIter(int mt) : m_tiles(mt) {}
     __device__ __forceinline__ bool next(const IGemmParams& p, int& m_tile, int& n_tile) {
         if (p.n_inner) {
             const int q = j / p.n_tiles;
@@ -53,7 +55,7 @@ struct TileIter {
             n_tile = tile - m_tile * p.n_tiles;
         }
         ++j;
-        return m_tile < p.m_tiles;
+        return m_tile < m_tiles;
     }
 };
 
@@ -80,6 +82,9 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int num_stages = p.num_stages;
     const int num_kb = p.num_kb;
+    // data-dependent row count (A_FLAT): every role derives the same tile range from it
+    const int M_rows = p.m_dyn != nullptr ? min(__ldg(p.m_dyn), p.M) : p.M;
+    const int m_tiles_rt = p.m_dyn != nullptr ? (M_rows + 127) >> 7 : p.m_tiles;
 
     for (int i = threadIdx.x; i < num_kb; i += kIGemmThreads) s_delta[i] = __ldg(&p.kb_delta[i]);
     if (threadIdx.x == 0) {
@@ -112,7 +117,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             const int tiles_per_img = p.tiles_x * p.tiles_y;
             const int mode = p.mode;
             const int BK = p.BK, BLOCK_N = p.BLOCK_N;
-            TileIter it;
+            TileIter it(m_tiles_rt);
             int m_tile, n_tile;
             while (it.next(p, m_tile, n_tile)) {
                 int img = 0, y0 = 0, x0 = 0;
@@ -154,7 +159,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             uint32_t acc_phase = 0;
             const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
             const int k_steps = p.BK >> 4;
-            TileIter it;
+            TileIter it(m_tiles_rt);
             int m_tile, n_tile;
             while (it.next(p, m_tile, n_tile)) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
@@ -192,7 +197,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         const int res_mode = p.res_mode, res_ld = p.res_ld;
         const float* __restrict__ bias = p.bias;
         const __half* __restrict__ res = reinterpret_cast<const __half*>(p.res);
-        TileIter it;
+        TileIter it(m_tiles_rt);
         int m_tile, n_tile;
         float best_v = -INFINITY;
         int best_i = 0;
@@ -202,7 +207,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             bool valid;
             if (mode == A_FLAT) {
                 const int m = m_tile * 128 + row;
-                valid = m < p.M;
+                valid = m < M_rows;
                 const int hw = Ho * Wo;
                 img = m / hw;
                 const int r = m - img * hw;
@@ -346,6 +351,22 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                             for (int j = 0; j < 4; ++j)
                                 if (j * 8 < ncol) op[j] = o[j];
                         }
+                    if (p.split_off > 0) {  // residual halves of the split-fp16 representation
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __half2* h2 = reinterpret_cast<__half2*>(&o[j]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 hi = __half22float2(h2[e]);
+                                h2[e] = __floats2half2_rn(f[j * 8 + e * 2] - hi.x, f[j * 8 + e * 2 + 1] - hi.y);
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix0 * out_ld + out_coff +
+                                                             ocol + p.split_off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 8 < ncol) op[j] = o[j];
+                    }
                 }
             }
             if constexpr (ARGMAX) {

@@ -119,6 +119,11 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.out_coff = es.out_coff;
     p.rep = es.rep;
     p.out_f32 = es.out_f32;
+    p.m_dyn = es.m_dyn;
+    p.split_off = es.split_off;
+    if (es.m_dyn && p.mode != A_FLAT) return set_err(e, DV_ERR_ARG, "%s: m_dyn needs a flat GEMM", name);
+    if (es.split_off && (es.out_f32 || es.out_mode != OUT_NHWC || (es.split_off % 8)))
+        return set_err(e, DV_ERR_ARG, "%s: split store needs fp16 NHWC output and split_off %% 8 == 0", name);
     if (num_kb > kMaxKB) return set_err(e, DV_ERR_UNSUPPORTED, "%s: %d k-blocks > %d", name, num_kb, kMaxKB);
     {
         const int al = es.out_f32 ? 4 : 8;
@@ -162,11 +167,16 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
 }
 
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
-                ConvPlan* plan, const char* name) {
+                ConvPlan* plan, const char* name, int lda) {
     memset(&plan->prm, 0, sizeof(plan->prm));
     plan->bytes = 0;
     IGemmParams& p = plan->prm;
     if (K % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: K %% 8 != 0", name);
+    // split-fp16: A holds [hi | lo] (2K columns); the k-block list walks hi, hi, lo against W = [W_hi | W_lo | W_hi]
+    const int a_cols = cs.split ? 2 * K : K;
+    if (lda == 0) lda = a_cols;
+    if ((lda % 8) || lda < a_cols || (reinterpret_cast<uintptr_t>(A) & 15))
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: A row stride %d / alignment", name, lda);
     p.mode = A_FLAT;
     p.M = M;
     p.Nimg = 1;
@@ -176,27 +186,36 @@ int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, co
     p.TW = 128;
     p.tiles_x = p.tiles_y = 1;
     p.m_tiles = (M + 127) / 128;
-    const int num_kb = (K + cs.BK - 1) / cs.BK;
+    const int kb_per = (K + cs.BK - 1) / cs.BK;
+    if (cs.split && (K % cs.BK)) return set_err(e, DV_ERR_UNSUPPORTED, "%s: split GEMM needs BK | K", name);
+    const int num_kb = cs.split ? 3 * kb_per : kb_per;
     if (cs.Cin_pad != num_kb * cs.BK)
         return set_err(e, DV_ERR_WEIGHTS, "%s: weight packing Cin_pad=%d != %d", name, cs.Cin_pad, num_kb * cs.BK);
     {
-        uint64_t dims[5] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 1, 1, 1};
-        const uint64_t rs = static_cast<uint64_t>(K) * 2;
+        uint64_t dims[5] = {static_cast<uint64_t>(a_cols), static_cast<uint64_t>(M), 1, 1, 1};
+        const uint64_t rs = static_cast<uint64_t>(lda) * 2;
         uint64_t str[4] = {rs, rs * M, rs * M, rs * M};
         uint32_t box[5] = {static_cast<uint32_t>(cs.BK), 128, 1, 1, 1};
         DV_TRY(encode_map(e, &p.tmA, A, 5, dims, str, box, 2 * cs.BK, name));
     }
     std::vector<int4> deltas(num_kb);
-    for (int kb = 0; kb < num_kb; ++kb) deltas[kb] = make_int4(kb * cs.BK, 0, 0, 0);
-    plan->flops = 2.0 * M * K * cs.Cout;
-    plan->bytes = 2.0 * M * K;
+    for (int kb = 0; kb < num_kb; ++kb) {
+        int col = kb * cs.BK;
+        if (cs.split) {
+            const int part = kb / kb_per, k = (kb - part * kb_per) * cs.BK;
+            col = part == 2 ? K + k : k;
+        }
+        deltas[kb] = make_int4(col, 0, 0, 0);
+    }
+    plan->flops = 2.0 * M * K * cs.Cout * (cs.split ? 3 : 1);
+    plan->bytes = 2.0 * M * a_cols;
     return finish_plan(e, plan, cs, es, num_kb, deltas, name);
 }
 
 int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
               ConvPlan* plan, const char* name) {
     if (cs.flat || (cs.KH == 1 && cs.KW == 1 && cs.stride == 1 && cs.pad == 0 && !cs.stem)) {
-        int rc = plan_linear(e, in.p, in.N * in.H * in.W, in.C, cs, es, plan, name);
+        int rc = plan_linear(e, in.p, in.N * in.H * in.W, in.C, cs, es, plan, name, in.ldc());
         if (rc == 0) {
             plan->prm.Nimg = in.N;
             plan->prm.Ho = in.H;
@@ -218,29 +237,33 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
     std::vector<int4> deltas;
     int num_kb = 0;
     if (cs.stem) {
-        // `in` is the padded image [N, Hp, Wp, 4]; windows of 8 pixels x 4 ch = 32 fp16 per tap row.
-        if (cs.BK != 32 || in.C != 4 || cs.KH != 7)
-            return set_err(e, DV_ERR_UNSUPPORTED, "%s: stem expects BK=32, C=4, 7x7", name);
+        // `in` is the zero-bordered image [N, Hp, Wp, cpp]: stride 2 -> cpp = 4 channels per pixel, stride 1 -> 8, so
+        // that one filter-tap row (8 pixels: 7 taps + 1 zero-weight pad) is a 16-byte-strided window of 8*cpp fp16.
+        const int st = cs.stride, cpp = st == 2 ? 4 : 8, win = 8 * cpp;
+        if ((st != 1 && st != 2) || cs.BK != win || in.C != cpp || in.ld != 0 || cs.KH != 7)
+            return set_err(e, DV_ERR_UNSUPPORTED, "%s: stem expects 7x7, stride 1 (C=8, BK=64) or 2 (C=4, BK=32)", name);
         p.mode = A_STEM;
-        const uint64_t pitch = static_cast<uint64_t>(in.W) * 4 * 2;
-        if (in.W < 2 * Wo + 6 || in.H < 2 * Ho + 5 || (pitch % 16))
+        const uint64_t pitch = static_cast<uint64_t>(in.W) * cpp * 2;
+        if (in.W < st * (Wo - 1) + 8 || in.H < st * (Ho - 1) + 7 || (pitch % 16))
             return set_err(e, DV_ERR_ARG, "%s: padded stem input too small", name);
-        uint64_t dims[5] = {32, static_cast<uint64_t>(Wo), 7, static_cast<uint64_t>(Ho),
+        uint64_t dims[5] = {static_cast<uint64_t>(win), static_cast<uint64_t>(Wo), 7, static_cast<uint64_t>(Ho),
                             static_cast<uint64_t>(in.N)};
-        uint64_t str[4] = {16, pitch, 2 * pitch, pitch * in.H};
-        uint32_t box[5] = {32, static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), 1};
+        uint64_t str[4] = {16, pitch, static_cast<uint64_t>(st) * pitch, pitch * in.H};
+        uint32_t box[5] = {static_cast<uint32_t>(win), static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), 1};
         DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
         num_kb = 7;
         for (int r = 0; r < 7; ++r) deltas.push_back(make_int4(0, 0, r, 0));
         plan->flops = 2.0 * in.N * Ho * Wo * 147.0 * cs.Cout;
-        plan->bytes = 2.0 * in.N * in.H * in.W * 4;
+        plan->bytes = 2.0 * in.N * in.H * in.W * cpp;
     } else {
         if (in.C != cs.Cin) return set_err(e, DV_ERR_ARG, "%s: Cin mismatch %d vs %d", name, in.C, cs.Cin);
         if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: Cin %% 8 != 0", name);
         const int cin_blocks = cs.Cin_pad / cs.BK;
         if (cin_blocks * cs.BK != cs.Cin_pad || cs.Cin_pad < cs.Cin)
             return set_err(e, DV_ERR_WEIGHTS, "%s: bad Cin_pad", name);
-        const uint64_t cb = static_cast<uint64_t>(in.C) * 2;
+        const uint64_t cb = static_cast<uint64_t>(in.ldc()) * 2;  // bytes between consecutive pixels
+        if ((in.ldc() % 8) || (reinterpret_cast<uintptr_t>(in.p) & 15))
+            return set_err(e, DV_ERR_UNSUPPORTED, "%s: input slice must be 16-byte aligned (ld %% 8, offset %% 8)", name);
         if (cs.stride == 1) {
             p.mode = A_PATCH;
             uint64_t dims[5] = {static_cast<uint64_t>(in.C), static_cast<uint64_t>(in.W),
@@ -254,8 +277,8 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
                     for (int c = 0; c < cin_blocks; ++c)
                         deltas.push_back(make_int4(c * cs.BK, s - cs.pad, r - cs.pad, 0));
         } else if (cs.stride == 2) {
-            if ((in.H & 1) || (in.W & 1) || (cs.Cin % cs.BK))
-                return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride-2 needs even H,W and BK | Cin", name);
+            if ((in.H & 1) || (in.W & 1) || (cs.Cin % cs.BK) || in.ld != 0)
+                return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride-2 needs even H,W, BK | Cin and a dense input", name);
             p.mode = A_PATCH_S2;
             uint64_t dims[5] = {static_cast<uint64_t>(2 * in.C), static_cast<uint64_t>(in.W / 2), 2,
                                 static_cast<uint64_t>(in.H / 2), static_cast<uint64_t>(in.N)};

@@ -39,6 +39,12 @@ struct IGemmParams {
     int act;
     int out_mode, out_ld, out_coff, rep, out_f32;
     void* out;
+    // A_FLAT only: number of valid rows read from device memory at kernel start (<= M, the planned capacity);
+    // lets data-dependent row counts (selected table cells) run without a host round trip.  nullptr = M.
+    const int* m_dyn;
+    // fp16 output only, > 0: also store lo = fp16(v - fp32(fp16(v))) at column + split_off, so the consumer
+    // GEMM can run the 3-term split-fp16 product (plan_linear_split) at ~fp32 accuracy.
+    int split_off;
 };
 
 }  // namespace dv

@@ -1,0 +1,499 @@
+// Lore table-structure detector: DLA-34 backbone + DCNv2 up-sampling neck + heads, as a static plan of launches.
+// Architecture restated from the reference: DLA / Tree / Root / BasicBlock center_net/modeling_centernet.py:34-402
+// (dla34: levels [1,1,1,2,2,1], channels [16,32,64,128,256,512]), DeformConv / IDAUp / DLAUp / DLASeg
+// lore/lore_dla_34.py:65-190 (first_level 2, last_level 5, head_conv 256), DCN lore/dcnv2.py:25-86.
+// The CPU mirror is oracle/lore_net_ref.py.
+//
+// What is different from a literal translation
+//  * Concatenations never exist as copies: every Root input is one pre-planned NHWC buffer whose channel slices are
+//    written directly by the producing kernels (conv epilogue `out_coff`, max-pool `ldo`) and read through strided
+//    TMA maps.  The level-3/4 `project` branch whose result the reference computes and then discards (Tree.forward
+//    hands it to a sub-Tree that recomputes its own, modeling_centernet.py:266-270) is not evaluated.
+//  * DCN = conv_offset_mask (tcgen05 conv, fp32 epilogue) -> k_dcn_im2col (bilinear gather x sigmoid mask, fp16) ->
+//    one flat tcgen05 GEMM with K = 9*Cin whose epilogue carries bias + folded BatchNorm + ReLU.
+//  * The four small heads (hm, reg, wh, st) run as ONE 3x3 conv 64 -> 1024 and ONE block-diagonal 1x1 -> 24 fp32
+//    channels (+ sigmoid on hm): the packed map dv_lore_decode reads.
+//  * The two wide heads (ax, cr: 256 channels each, 56 of the network's 338 GFLOP per image, 134 MB of fp32 maps)
+//    are never evaluated densely: the reference only ever gathers them at the selected cells' centres / corners, so
+//    lore_cell_features() builds the 3x3 patches at those points and runs the two head GEMMs on (5 x cells) rows.
+#include "engine.h"
+
+namespace dv {
+
+int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
+                    int flip, __half* out);
+int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out);
+int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer);
+int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer);
+int op_sigmoid_cols(Engine* e, float* maps, long long rows, int ld, int ncols);
+int op_cell_offsets(Engine* e, const int32_t* counts, int N, int cap, int32_t* offsets, int32_t* totals, int32_t* overflow);
+int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int32_t* counts, const int32_t* offsets,
+                       const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr);
+int op_logi_combine(Engine* e, const float* ax, const float* cr, int C, int cap, const int32_t* totals, float* out);
+
+namespace {
+
+constexpr int kCh[6] = {16, 32, 64, 128, 256, 512};
+constexpr int kLevels[6] = {1, 1, 1, 2, 2, 1};
+
+struct Step {
+    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID } kind;
+    ConvPlan plan;
+    Tensor a, b, c;
+    const float* wt = nullptr;
+    int f = 0;
+    std::string name;
+};
+
+struct LoreNet : Model {
+    Engine* e = nullptr;
+    int N = 0, H = 0, W = 0;
+    std::vector<void*> mem;
+    std::vector<Step> steps;
+    Tensor stem_in, feat;
+    float* om = nullptr;   // [M_max, 32] fp32 conv_offset_mask scratch
+    __half* col = nullptr;  // [M_max, 9*C] fp16 deformable-sampling scratch
+    size_t col_elems = 0, om_rows = 0;
+    float* maps = nullptr;  // [N, H/4, W/4, 24] fp32 (internal copy when the caller passes no buffer)
+    std::map<std::string, Tensor> named;
+    double flops = 0;
+    // sparse ax / cr heads
+    int cap = 0, K = 0;
+    std::vector<void*> feat_mem;
+    std::vector<ConvPlan> feat_plans;
+    int32_t *offsets = nullptr, *totals = nullptr, *overflow = nullptr;
+    __half *col_ax = nullptr, *col_cr = nullptr, *hid_ax = nullptr, *hid_cr = nullptr;
+    float *out_ax = nullptr, *out_cr = nullptr;
+    ~LoreNet() override {
+        for (void* p : mem) cudaFree(p);
+        for (void* p : feat_mem) cudaFree(p);
+    }
+    int alloc(std::vector<void*>& pool, void** p, size_t bytes, bool zero = false) {
+        cudaError_t st = cudaMalloc(p, bytes ? bytes : 16);
+        if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "lore: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(st));
+        pool.push_back(*p);
+        if (zero) cudaMemsetAsync(*p, 0, bytes, e->stream);
+        return 0;
+    }
+    int tensor(Tensor* t, int n, int h, int w, int c, bool zero = false) {
+        t->N = n;
+        t->H = h;
+        t->W = w;
+        t->C = c;
+        t->ld = 0;
+        void* p = nullptr;
+        DV_TRY(alloc(mem, &p, t->elems() * sizeof(__half), zero));
+        t->p = reinterpret_cast<__half*>(p);
+        return 0;
+    }
+    // plan_* allocate their delta tables through the engine: move them into this model's pool
+    void adopt(std::vector<void*>& pool) {
+        pool.push_back(e->owned.back());
+        e->owned.pop_back();
+    }
+};
+
+int get_conv(Engine* e, const std::string& name, ConvSpec* cs) {
+    const BlobTensor* w = e->find(name + ".w");
+    const BlobTensor* b = e->find(name + ".b");
+    if (!w || !b) return set_err(e, DV_ERR_WEIGHTS, "missing weights for '%s'", name.c_str());
+    if (w->dtype != 1 || b->dtype != 0 || w->ndim != 2) return set_err(e, DV_ERR_WEIGHTS, "bad dtype/rank for '%s'", name.c_str());
+    cs->w = reinterpret_cast<const __half*>(w->dptr);
+    cs->bias = reinterpret_cast<const float*>(b->dptr);
+    const int taps = cs->KH * cs->KW;
+    if (cs->stem) {
+        if (static_cast<int>(w->dims[0]) != cs->Cout || w->dims[1] != 448)
+            return set_err(e, DV_ERR_WEIGHTS, "'%s': stride-1 stem weight must be [%d,448]", name.c_str(), cs->Cout);
+        cs->Cin_pad = 64;
+        cs->BK = 64;
+    } else {
+        if (static_cast<int>(w->dims[0]) != cs->Cout || (w->dims[1] % taps) != 0)
+            return set_err(e, DV_ERR_WEIGHTS, "'%s': weight shape [%u,%u] does not match Cout=%d taps=%d", name.c_str(), w->dims[0],
+                           w->dims[1], cs->Cout, taps);
+        cs->Cin_pad = static_cast<int>(w->dims[1]) / taps;
+        cs->BK = (cs->Cin_pad % 64 == 0) ? 64 : (cs->Cin_pad % 32 == 0) ? 32 : 16;
+    }
+    if (b->dims[0] < static_cast<uint32_t>((cs->Cout + 255) / 256 * 256))
+        return set_err(e, DV_ERR_WEIGHTS, "'%s': bias not padded to 256", name.c_str());
+    return 0;
+}
+
+EpiSpec epi(const Tensor& out, int act, const Tensor* res = nullptr) {
+    EpiSpec es;
+    es.out = out.p;
+    es.out_ld = out.ldc();
+    es.act = act;
+    if (res) {
+        es.res = res->p;
+        es.res_mode = RES_SAME;
+        es.res_ld = res->ldc();
+    }
+    return es;
+}
+
+int add_conv(LoreNet* m, const std::string& name, const Tensor& in, int cout, int k, int stride, const EpiSpec& es, bool stem = false) {
+    ConvSpec cs;
+    cs.KH = cs.KW = k;
+    cs.stride = stride;
+    cs.pad = k / 2;
+    cs.Cin = stem ? 3 : in.C;
+    cs.Cout = cout;
+    cs.stem = stem;
+    DV_TRY(get_conv(m->e, name, &cs));
+    const int Ho = stem ? in.H - 6 : in.H / stride, Wo = stem ? in.W - 8 : in.W / stride;
+    Step st;
+    st.kind = Step::CONV;
+    st.name = name;
+    DV_TRY(plan_conv(m->e, in, cs, es, Ho, Wo, &st.plan, st.name.c_str()));
+    m->adopt(m->mem);
+    m->flops += st.plan.flops;
+    m->steps.push_back(st);
+    return 0;
+}
+
+int add_pool(LoreNet* m, const Tensor& in, const Tensor& out) {
+    Step st;
+    st.kind = Step::MAXPOOL;
+    st.a = in;
+    st.b = out;
+    m->steps.push_back(st);
+    return 0;
+}
+
+// BasicBlock (modeling_centernet.py:34-71): relu(bn2(conv2(relu(bn1(conv1(x))))) + residual) -> dst
+int add_block(LoreNet* m, const std::string& p, const Tensor& x, int cout, int stride, const Tensor& residual, const Tensor& dst) {
+    Tensor t;
+    DV_TRY(m->tensor(&t, x.N, x.H / stride, x.W / stride, cout));
+    DV_TRY(add_conv(m, p + ".conv1", x, cout, 3, stride, epi(t, ACT_RELU)));
+    DV_TRY(add_conv(m, p + ".conv2", t, cout, 3, 1, epi(dst, ACT_RELU, &residual)));
+    return 0;
+}
+
+// A levels == 1 Tree (modeling_centernet.py:186-287).  `root` is the pre-planned Root input [x2 | x1 | children...];
+// `bottom` = max-pooled input (already planned by the caller when stride > 1), `dst` receives the Root output.
+int add_tree1(LoreNet* m, const std::string& p, const Tensor& x, int cin, int cout, int stride, const Tensor& bottom, const Tensor& root,
+              const Tensor& dst) {
+    Tensor residual = bottom;
+    if (cin != cout) {
+        DV_TRY(m->tensor(&residual, bottom.N, bottom.H, bottom.W, cout));
+        DV_TRY(add_conv(m, p + ".project", bottom, cout, 1, 1, epi(residual, ACT_NONE)));
+    }
+    const Tensor x1 = root.slice(cout, cout), x2 = root.slice(0, cout);
+    DV_TRY(add_block(m, p + ".tree1", x, cout, stride, residual, x1));
+    DV_TRY(add_block(m, p + ".tree2", x1, cout, 1, x1, x2));
+    DV_TRY(add_conv(m, p + ".root", root, cout, 1, 1, epi(dst, ACT_RELU)));
+    return 0;
+}
+
+// One DLA level (a Tree with stride 2) -> dense output
+int add_level(LoreNet* m, int lvl, const Tensor& x, Tensor* out) {
+    const std::string p = "level" + std::to_string(lvl);
+    const int cin = kCh[lvl - 1], cout = kCh[lvl], levels = kLevels[lvl];
+    const bool level_root = lvl > 2;
+    const int Ho = x.H / 2, Wo = x.W / 2;
+    DV_TRY(m->tensor(out, x.N, Ho, Wo, cout));
+    if (levels == 1) {
+        Tensor root;
+        DV_TRY(m->tensor(&root, x.N, Ho, Wo, 2 * cout + (level_root ? cin : 0)));
+        Tensor bottom;
+        if (level_root) bottom = root.slice(2 * cout, cin);
+        else DV_TRY(m->tensor(&bottom, x.N, Ho, Wo, cin));
+        DV_TRY(add_pool(m, x, bottom));
+        DV_TRY(add_tree1(m, p, x, cin, cout, 2, bottom, root, *out));
+    } else {
+        // levels == 2: tree1 = Tree(1, cin -> cout, stride 2), tree2 = Tree(1, cout -> cout) whose Root also takes
+        // [bottom, x1]; root2 = [x2b | x1b | bottom | x1]
+        Tensor root2, root1;
+        DV_TRY(m->tensor(&root2, x.N, Ho, Wo, 2 * cout + cin + cout));
+        DV_TRY(m->tensor(&root1, x.N, Ho, Wo, 2 * cout));
+        const Tensor bottom = root2.slice(2 * cout, cin), x1 = root2.slice(2 * cout + cin, cout);
+        DV_TRY(add_pool(m, x, bottom));
+        DV_TRY(add_tree1(m, p + ".tree1", x, cin, cout, 2, bottom, root1, x1));
+        DV_TRY(add_tree1(m, p + ".tree2", x1, cout, cout, 1, x1, root2, *out));
+    }
+    m->named[p] = *out;
+    return 0;
+}
+
+// DeformConv (lore_dla_34.py:65-85): DCN + BN + ReLU -> dst (dense)
+int add_dcn(LoreNet* m, const std::string& p, const Tensor& x, int cout, Tensor* dst) {
+    DV_TRY(m->tensor(dst, x.N, x.H, x.W, cout));
+    const size_t rows = static_cast<size_t>(x.N) * x.H * x.W;
+    if (rows > m->om_rows || rows * 9 * x.C > m->col_elems) return set_err(m->e, DV_ERR_STATE, "lore: DCN scratch too small for %s", p.c_str());
+    {
+        EpiSpec es;
+        es.out = m->om;
+        es.out_ld = 32;
+        es.out_f32 = 1;
+        DV_TRY(add_conv(m, p + ".om", x, 32, 3, 1, es));
+    }
+    {
+        Step st;
+        st.kind = Step::IM2COL;
+        st.a = x;
+        st.name = p + ".sample";
+        m->steps.push_back(st);
+        m->flops += 0;
+    }
+    {
+        ConvSpec cs;
+        cs.KH = cs.KW = 1;
+        cs.Cout = cout;
+        DV_TRY(get_conv(m->e, p + ".dcn", &cs));
+        if (cs.Cin_pad != 9 * x.C) return set_err(m->e, DV_ERR_WEIGHTS, "'%s.dcn': K %d != 9*%d", p.c_str(), cs.Cin_pad, x.C);
+        cs.Cin = 9 * x.C;
+        cs.BK = 64;
+        cs.flat = true;
+        Step st;
+        st.kind = Step::CONV;
+        st.name = p + ".dcn";
+        DV_TRY(plan_linear(m->e, m->col, static_cast<int>(rows), 9 * x.C, cs, epi(*dst, ACT_RELU), &st.plan, st.name.c_str()));
+        m->adopt(m->mem);
+        m->flops += st.plan.flops;
+        m->steps.push_back(st);
+    }
+    return 0;
+}
+
+// IDAUp.forward (lore_dla_34.py:104-110) over layers[startp+1 .. endp)
+int add_ida(LoreNet* m, const std::string& p, std::vector<Tensor>& layers, int startp, int endp, int o, const int* up_f) {
+    for (int i = startp + 1; i < endp; ++i) {
+        const int j = i - startp, f = up_f[j];
+        Tensor proj, sum, node;
+        DV_TRY(add_dcn(m, p + ".proj_" + std::to_string(j), layers[i], o, &proj));
+        const BlobTensor* w = m->e->find(p + ".up_" + std::to_string(j) + ".w");
+        if (!w || w->dtype != 0 || w->nbytes != static_cast<uint64_t>(4 * f * f * o) * 4)
+            return set_err(m->e, DV_ERR_WEIGHTS, "missing / bad '%s.up_%d.w'", p.c_str(), j);
+        DV_TRY(m->tensor(&sum, proj.N, proj.H * f, proj.W * f, o));
+        Step st;
+        st.kind = Step::UPADD;
+        st.a = proj;
+        st.b = layers[i - 1];
+        st.c = sum;
+        st.wt = reinterpret_cast<const float*>(w->dptr);
+        st.f = f;
+        st.name = p + ".up_" + std::to_string(j);
+        m->steps.push_back(st);
+        DV_TRY(add_dcn(m, p + ".node_" + std::to_string(j), sum, o, &node));
+        layers[i] = node;
+    }
+    return 0;
+}
+
+int build(Engine* e, LoreNet* m, int N, int H, int W) {
+    if ((H % 32) || (W % 32)) return set_err(e, DV_ERR_ARG, "lore: H and W must be multiples of 32 (got %dx%d)", H, W);
+    for (void* p : m->mem) cudaFree(p);
+    m->mem.clear();
+    m->steps.clear();
+    m->named.clear();
+    m->flops = 0;
+    m->e = e;
+    m->N = N;
+    m->H = H;
+    m->W = W;
+    DV_TRY(m->tensor(&m->stem_in, N, H + 6, W + 8, 8, /*zero=*/true));
+    // DCN scratch: the largest sampling matrix is 9*64 channels at stride 4 (or 9*128 at stride 8: same size)
+    m->om_rows = static_cast<size_t>(N) * (H / 4) * (W / 4);
+    m->col_elems = m->om_rows * 9 * 64;
+    {
+        void* p = nullptr;
+        DV_TRY(m->alloc(m->mem, &p, m->om_rows * 32 * sizeof(float)));
+        m->om = reinterpret_cast<float*>(p);
+        DV_TRY(m->alloc(m->mem, &p, m->col_elems * sizeof(__half)));
+        m->col = reinterpret_cast<__half*>(p);
+        DV_TRY(m->alloc(m->mem, &p, m->om_rows * 24 * sizeof(float)));
+        m->maps = reinterpret_cast<float*>(p);
+    }
+    Tensor b0, l0, l1;
+    DV_TRY(m->tensor(&b0, N, H, W, 16));
+    DV_TRY(m->tensor(&l0, N, H, W, 16));
+    DV_TRY(m->tensor(&l1, N, H / 2, W / 2, 32));
+    DV_TRY(add_conv(m, "base", m->stem_in, 16, 7, 1, epi(b0, ACT_RELU), /*stem=*/true));
+    DV_TRY(add_conv(m, "level0", b0, 16, 3, 1, epi(l0, ACT_RELU)));
+    DV_TRY(add_conv(m, "level1", l0, 32, 3, 2, epi(l1, ACT_RELU)));
+    m->named["level0"] = l0;
+    m->named["level1"] = l1;
+    std::vector<Tensor> layers(4);
+    Tensor x = l1;
+    for (int lvl = 2; lvl < 6; ++lvl) {
+        DV_TRY(add_level(m, lvl, x, &layers[lvl - 2]));
+        x = layers[lvl - 2];
+    }
+    // DLAUp.forward (lore_dla_34.py:130-137): channels [64,128,256,512], scales [1,2,4,8]
+    std::vector<Tensor> out(1, layers[3]);
+    {
+        const int up2[4] = {1, 2, 2, 2};
+        DV_TRY(add_ida(m, "dla_up.ida_0", layers, 2, 4, 256, up2));
+        out.insert(out.begin(), layers[3]);
+        DV_TRY(add_ida(m, "dla_up.ida_1", layers, 1, 4, 128, up2));
+        out.insert(out.begin(), layers[3]);
+        DV_TRY(add_ida(m, "dla_up.ida_2", layers, 0, 4, 64, up2));
+        out.insert(out.begin(), layers[3]);
+    }
+    // DLASeg.forward (:176-189): y = out[0:3]; ida_up(y, 0, 3) with up factors [1,2,4]
+    std::vector<Tensor> y(out.begin(), out.begin() + 3);
+    {
+        const int upf[3] = {1, 2, 4};
+        DV_TRY(add_ida(m, "ida_up", y, 0, 3, 64, upf));
+    }
+    m->feat = y[2];
+    m->named["feat"] = m->feat;
+    // small heads
+    Tensor hid;
+    DV_TRY(m->tensor(&hid, N, m->feat.H, m->feat.W, 1024));
+    DV_TRY(add_conv(m, "heads.conv", m->feat, 1024, 3, 1, epi(hid, ACT_RELU)));
+    {
+        EpiSpec es;
+        es.out = m->maps;  // re-pointed per call when the caller supplies its own buffer
+        es.out_ld = 24;
+        es.out_f32 = 1;
+        DV_TRY(add_conv(m, "heads.out", hid, 24, 1, 1, es));
+    }
+    {
+        Step st;
+        st.kind = Step::SIGMOID;
+        st.name = "hm.sigmoid";
+        m->steps.push_back(st);
+    }
+    return 0;
+}
+
+int get_flat(Engine* e, const std::string& name, int K, int N, ConvSpec* cs) {
+    cs->KH = cs->KW = 1;
+    cs->Cout = N;
+    DV_TRY(get_conv(e, name, cs));
+    if (cs->Cin_pad != K) return set_err(e, DV_ERR_WEIGHTS, "'%s': K %d != %d", name.c_str(), cs->Cin_pad, K);
+    cs->Cin = K;
+    cs->flat = true;
+    return 0;
+}
+
+int build_feat(Engine* e, LoreNet* m, int K, int cap) {
+    for (void* p : m->feat_mem) cudaFree(p);
+    m->feat_mem.clear();
+    m->feat_plans.clear();
+    m->K = K;
+    m->cap = cap;
+    const int C = 64, D = 256;
+    void* p = nullptr;
+    DV_TRY(m->alloc(m->feat_mem, &p, (m->N + 1 + 2 + 1) * sizeof(int32_t), true));
+    m->offsets = reinterpret_cast<int32_t*>(p);
+    m->totals = m->offsets + m->N + 1;
+    m->overflow = m->totals + 2;
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 9 * C * 2, true));
+    m->col_ax = reinterpret_cast<__half*>(p);
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * 9 * C * 2, true));
+    m->col_cr = reinterpret_cast<__half*>(p);
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 2, true));
+    m->hid_ax = reinterpret_cast<__half*>(p);
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * D * 2, true));
+    m->hid_cr = reinterpret_cast<__half*>(p);
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 4, true));
+    m->out_ax = reinterpret_cast<float*>(p);
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * D * 4, true));
+    m->out_cr = reinterpret_cast<float*>(p);
+    const char* heads[2] = {"ax", "cr"};
+    for (int h = 0; h < 2; ++h) {
+        const int rows = h == 0 ? cap : 4 * cap;
+        const int* m_dyn = m->totals + h;
+        ConvSpec c1, c2;
+        DV_TRY(get_flat(e, std::string(heads[h]) + ".conv", 9 * C, D, &c1));
+        DV_TRY(get_flat(e, std::string(heads[h]) + ".out", D, D, &c2));
+        EpiSpec e1, e2;
+        e1.out = h == 0 ? m->hid_ax : m->hid_cr;
+        e1.out_ld = D;
+        e1.act = ACT_RELU;
+        e1.m_dyn = m_dyn;
+        e2.out = h == 0 ? m->out_ax : m->out_cr;
+        e2.out_ld = D;
+        e2.out_f32 = 1;
+        e2.m_dyn = m_dyn;
+        ConvPlan p1, p2;
+        DV_TRY(plan_linear(e, h == 0 ? m->col_ax : m->col_cr, rows, 9 * C, c1, e1, &p1, (std::string(heads[h]) + ".conv").c_str()));
+        m->adopt(m->feat_mem);
+        DV_TRY(plan_linear(e, h == 0 ? m->hid_ax : m->hid_cr, rows, D, c2, e2, &p2, (std::string(heads[h]) + ".out").c_str()));
+        m->adopt(m->feat_mem);
+        m->feat_plans.push_back(p1);
+        m->feat_plans.push_back(p2);
+    }
+    return 0;
+}
+
+}  // namespace
+
+int lore_create(Engine* e) {
+    LoreNet* m = new LoreNet();
+    m->e = e;
+    e->model.reset(m);
+    return 0;
+}
+
+double lore_flops(Engine* e) {
+    LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
+    return m ? m->flops : 0.0;
+}
+
+int lore_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4) {
+    LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
+    if (!m) return set_err(e, DV_ERR_STATE, "not a lore handle");
+    auto it = m->named.find(name);
+    if (it == m->named.end()) return set_err(e, DV_ERR_ARG, "no tensor named '%s'", name);
+    const Tensor& t = it->second;
+    if (t.ld != 0) return set_err(e, DV_ERR_UNSUPPORTED, "tensor '%s' is a slice", name);
+    if (dims4) {
+        dims4[0] = t.N;
+        dims4[1] = t.C;
+        dims4[2] = t.H;
+        dims4[3] = t.W;
+    }
+    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw);
+    return 0;
+}
+
+int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, int flip, int N,
+                        int H, int W, float* maps_out) {
+    LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
+    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_dla34 model");
+    if (N <= 0 || H <= 0 || W <= 0) return set_err(e, DV_ERR_ARG, "lore_detect_forward: bad arguments");
+    if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
+    if (!in_nchw && !in_u8) return set_err(e, DV_ERR_ARG, "lore_detect_forward: no input");
+    DV_TRY(op_img_to_stem8(e, in_u8, in_nchw, N, H, W, mean3, std3, flip, m->stem_in.p));
+    float* maps = maps_out ? maps_out : m->maps;
+    for (Step& st : m->steps) {
+        switch (st.kind) {
+            case Step::CONV:
+                if (st.name == "heads.out") st.plan.prm.out = maps;
+                DV_TRY(launch_conv(e, st.plan));
+                break;
+            case Step::MAXPOOL: DV_TRY(op_maxpool2x2(e, st.a, st.b)); break;
+            case Step::IM2COL: DV_TRY(op_dcn_im2col(e, st.a, m->om, m->col, st.name.c_str())); break;
+            case Step::UPADD: DV_TRY(op_up_dw_add(e, st.a, st.wt, st.f, st.b, st.c, st.name.c_str())); break;
+            case Step::SIGMOID: DV_TRY(op_sigmoid_cols(e, maps, static_cast<long long>(N) * (H / 4) * (W / 4), 24, 2)); break;
+        }
+    }
+    return 0;
+}
+
+// logi features of the selected cells from the resident 64-channel feature map (the last lore_detect_forward).
+int lore_cell_features(Engine* e, int N, int K, int cap, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
+                       float* logi_feat, int32_t* offsets_out, int32_t* overflow_host) {
+    LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
+    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_dla34 model");
+    if (m->N != N || !m->feat.p) return set_err(e, DV_ERR_STATE, "lore_cell_features: call lore_detect_forward with the same batch first");
+    if (!counts || !ax_idx || !cr_idx || !logi_feat || K <= 0 || cap <= 0) return set_err(e, DV_ERR_ARG, "lore_cell_features: bad arguments");
+    if (m->K != K || m->cap != cap || m->feat_plans.empty()) DV_TRY(build_feat(e, m, K, cap));
+    DV_CUDA(e, cudaMemsetAsync(m->overflow, 0, 4, e->stream));
+    DV_TRY(op_cell_offsets(e, counts, N, cap, m->offsets, m->totals, m->overflow));
+    DV_TRY(op_gather_patch3x3(e, m->feat, K, cap, counts, m->offsets, ax_idx, cr_idx, m->col_ax, m->col_cr));
+    for (const ConvPlan& p : m->feat_plans) DV_TRY(launch_conv(e, p));
+    DV_TRY(op_logi_combine(e, m->out_ax, m->out_cr, 256, cap, m->totals, logi_feat));
+    if (offsets_out)
+        DV_CUDA(e, cudaMemcpyAsync(offsets_out, m->offsets, (N + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    if (overflow_host) {
+        DV_CUDA(e, cudaMemcpyAsync(overflow_host, m->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
+        DV_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+}  // namespace dv

@@ -1,0 +1,351 @@
+// HBM-bound kernels of the Lore / CenterNet table-structure detector around the tensor-core convolution:
+//   k_img_to_stem8        TableLorePreProcessor normalisation (lore/processer_lore.py:66-93) fused with the layout
+//                         change into the zero-bordered 8-channel image the stride-1 7x7 stem reads
+//   k_maxpool2x2          nn.MaxPool2d(2, 2) of Tree.downsample / the level roots (center_net/modeling_centernet.py:253)
+//   k_dcn_im2col          modulated deformable sampling of DCN (lore/dcnv2.py:71-86 -> torchvision deform_conv2d):
+//                         col[m][tap*C + c] = mask * bilinear(x, y + dy, x + dx); the 9C-wide GEMM runs on tcgen05
+//   k_up_dw_add           IDAUp: depthwise ConvTranspose2d(k=2f, s=f, p=f/2) + the skip addition
+//                         (lore/lore_dla_34.py:93-110)
+//   k_sigmoid_cols        hm.sigmoid_() (lore/lineless_table_process.py:599) on the first columns of the packed maps
+//   k_gather_patch3x3     3x3 zero-padded patches of the 64-channel feature map at the decoded cell / corner points,
+//                         so the `ax` / `cr` heads are evaluated only where the reference gathers them
+//   k_logi_combine        logi = ax(centre) + sum of cr(4 corners)
+#include "engine.h"
+
+namespace dv {
+
+static inline int grid_for(long long n, int block) { return static_cast<int>((n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------- stem input
+// in: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W] (already normalised) -> fp16 [N, H+6, W+8, 8], interior at (+3,+3).
+// The u8 path mirrors numpy: (x / 255. - mean) / std evaluated in float64, then .astype(float32).
+__global__ void __launch_bounds__(256)
+k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, double3 mean, double3 stdv,
+               int flip, __half* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * H * W;
+    if (idx >= total) return;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    float v0, v1, v2;
+    if (u8) {
+        const uint8_t* ip = u8 + idx * 3;
+        double c0 = ip[0], c1 = ip[1], c2 = ip[2];
+        if (flip) {
+            const double t = c0;
+            c0 = c2;
+            c2 = t;
+        }
+        v0 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c0, 255.0), mean.x), stdv.x));
+        v1 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c1, 255.0), mean.y), stdv.y));
+        v2 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c2, 255.0), mean.z), stdv.z));
+    } else {
+        const long long plane = static_cast<long long>(H) * W;
+        const float* ip = f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(y) * W + x;
+        v0 = ip[0];
+        v1 = ip[plane];
+        v2 = ip[2 * plane];
+    }
+    const __half2 a = __floats2half2_rn(v0, v1);
+    const __half2 b = __floats2half2_rn(v2, 0.f);
+    uint4 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    u.z = 0u;
+    u.w = 0u;
+    const int Hp = H + 6, Wp = W + 8;
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 8) = u;
+}
+
+int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
+                    int flip, __half* out) {
+    const long long total = static_cast<long long>(N) * H * W;
+    double3 m = make_double3(0, 0, 0), s = make_double3(1, 1, 1);
+    if (u8) {
+        // the reference holds mean / std as float32 arrays; float32 -> float64 promotion is exact
+        m = make_double3(mean3[0], mean3[1], mean3[2]);
+        s = make_double3(std3[0], std3[1], std3[2]);
+    }
+    e->launch_begin("k_img_to_stem8", "pre", 0.0, total * ((u8 ? 3.0 : 12.0) + 16.0));
+    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- 2x2 max-pool
+__global__ void __launch_bounds__(256)
+k_maxpool2x2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const __half* ip = in + ((static_cast<long long>(n) * H + 2 * oy) * W + 2 * ox) * ldi + c8 * 8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(ip));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(ip + ldi));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(ip + static_cast<long long>(W) * ldi));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(ip + static_cast<long long>(W) * ldi + ldi));
+    uint4 o;
+    const __half2 *ha = reinterpret_cast<const __half2*>(&a), *hb = reinterpret_cast<const __half2*>(&b);
+    const __half2 *hc = reinterpret_cast<const __half2*>(&c), *hd = reinterpret_cast<const __half2*>(&d);
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __hmax2(__hmax2(ha[i], hb[i]), __hmax2(hc[i], hd[i]));
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+}
+
+int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out) {
+    if ((in.C % 8) || (in.H & 1) || (in.W & 1) || out.C != in.C || out.H != in.H / 2 || out.W != in.W / 2)
+        return set_err(e, DV_ERR_UNSUPPORTED, "maxpool2x2: bad shapes");
+    const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    e->launch_begin("k_maxpool2x2", "maxpool", 0.0, 2.0 * (double)in.elems() * 1.25);
+    k_maxpool2x2<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), out.p, out.ldc());
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- DCN sampling
+// om: fp32 [M, 32] = conv_offset_mask output; columns 2k, 2k+1 = (dy, dx) of tap k, 18+k = mask logit (dcnv2.py:73-76).
+// One thread = (pixel, tap, 8 channels).  Sampling rule = torchvision deform_conv2d_kernel bilinear_interpolate.
+__global__ void __launch_bounds__(256)
+k_dcn_im2col(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, const float* __restrict__ om,
+             __half* __restrict__ col) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * H * W * 9 * cv;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int tap = static_cast<int>(t % 9);
+    const long long pix = t / 9;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    const float* o = om + pix * 32;
+    const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
+    const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
+    const float py = static_cast<float>(y + tap / 3 - 1) + dy;
+    const float px = static_cast<float>(x + tap % 3 - 1) + dx;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W)) {
+        const float fy = floorf(py), fx = floorf(px);
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+        const float w4[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+        const __half* base = in + static_cast<long long>(n) * H * W * ldi + c8 * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+            if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy) * W + xx) * ldi));
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    acc[2 * i] = fmaf(w4[k], f.x, acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(w4[k], f.y, acc[2 * i + 1]);
+                }
+            }
+        }
+    }
+    uint4 out;
+    __half2* ho = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * mask, acc[2 * i + 1] * mask);
+    *reinterpret_cast<uint4*>(col + pix * (9LL * C) + tap * C + c8 * 8) = out;
+}
+
+int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer) {
+    if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "dcn_im2col: C %% 8 != 0");
+    const long long total = static_cast<long long>(in.N) * in.H * in.W * 9 * (in.C / 8);
+    const double px = static_cast<double>(in.N) * in.H * in.W;
+    e->launch_begin("k_dcn_im2col", layer, px * 9 * in.C * 9.0, px * (in.C * 2.0 + 128.0 + 18.0 * in.C));
+    k_dcn_im2col<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), om, col);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- IDAUp upsample + add
+// out[n, oy, ox, c] = skip[n, oy, ox, c] + sum_{iy, ix} in[n, iy, ix, c] * w[ky][kx][c],  ky = oy + f/2 - iy*f in [0, 2f)
+// (ConvTranspose2d(o, o, 2f, stride=f, padding=f//2, groups=o)); w is fp32 [2f][2f][C].
+__global__ void __launch_bounds__(256)
+k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, const float* __restrict__ wt, int f,
+            const __half* __restrict__ skip, int lds, __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3, Ho = h * f, Wo = w * f, k2 = 2 * f, pad = f >> 1;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float acc[8];
+    {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(skip + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * lds + c8 * 8));
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 v = __half22float2(hh[i]);
+            acc[2 * i] = v.x;
+            acc[2 * i + 1] = v.y;
+        }
+    }
+    const int iy1 = (oy + pad) / f, ix1 = (ox + pad) / f;
+    for (int a = 0; a < 2; ++a) {
+        const int iy = iy1 - a, ky = oy + pad - iy * f;
+        if (iy < 0 || iy >= h || ky >= k2) continue;
+        for (int b = 0; b < 2; ++b) {
+            const int ix = ix1 - b, kx = ox + pad - ix * f;
+            if (ix < 0 || ix >= w || kx >= k2) continue;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8));
+            const float4* wp = reinterpret_cast<const float4*>(wt + (static_cast<long long>(ky) * k2 + kx) * C + c8 * 8);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+            const float2 v0 = __half22float2(hh[0]), v1 = __half22float2(hh[1]), v2 = __half22float2(hh[2]), v3 = __half22float2(hh[3]);
+            acc[0] = fmaf(v0.x, w0.x, acc[0]);
+            acc[1] = fmaf(v0.y, w0.y, acc[1]);
+            acc[2] = fmaf(v1.x, w0.z, acc[2]);
+            acc[3] = fmaf(v1.y, w0.w, acc[3]);
+            acc[4] = fmaf(v2.x, w1.x, acc[4]);
+            acc[5] = fmaf(v2.y, w1.y, acc[5]);
+            acc[6] = fmaf(v3.x, w1.z, acc[6]);
+            acc[7] = fmaf(v3.y, w1.w, acc[7]);
+        }
+    }
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+}
+
+int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer) {
+    if ((in.C % 8) || skip.C != in.C || out.C != in.C || skip.H != in.H * f || skip.W != in.W * f || out.H != skip.H ||
+        out.W != skip.W || (f != 2 && f != 4 && f != 8))
+        return set_err(e, DV_ERR_UNSUPPORTED, "up_dw_add: bad shapes");
+    const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    e->launch_begin("k_up_dw_add", layer, 8.0 * (double)out.elems(), 2.0 * ((double)in.elems() + 2.0 * (double)out.elems()));
+    k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.ldc(), out.p,
+                                                           out.ldc());
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- sigmoid on leading columns
+__global__ void __launch_bounds__(256) k_sigmoid_cols(float* __restrict__ maps, long long rows, int ld, int ncols) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= rows * ncols) return;
+    float* p = maps + (idx / ncols) * ld + (idx % ncols);
+    *p = 1.f / (1.f + expf(-*p));
+}
+
+int op_sigmoid_cols(Engine* e, float* maps, long long rows, int ld, int ncols) {
+    e->launch_begin("k_sigmoid_cols", "hm.sigmoid", 0.0, rows * ncols * 8.0);
+    k_sigmoid_cols<<<grid_for(rows * ncols, 256), 256, 0, e->stream>>>(maps, rows, ld, ncols);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- sparse `ax` / `cr` heads
+// counts[n] selected cells per image -> offsets (exclusive prefix), total rows, 4 x total (the `cr` GEMM's row count)
+__global__ void k_cell_offsets(const int32_t* __restrict__ counts, int N, int cap, int32_t* __restrict__ offsets,
+                               int32_t* __restrict__ totals, int32_t* __restrict__ overflow) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int n = 0; n < N; ++n) {
+        offsets[n] = acc;
+        acc += counts[n];
+    }
+    offsets[N] = acc;
+    if (acc > cap) {
+        *overflow = acc;
+        acc = cap;
+    }
+    totals[0] = acc;
+    totals[1] = 4 * acc;
+}
+
+// One CTA per (cell j, image n): rows of the two patch matrices.  feat: NHWC fp16 [N,H,W,C];
+// col_ax[row][tap*C + c] (row = offsets[n] + j), col_cr[4*row + k][...]; out-of-image taps are zero (conv padding 1).
+__global__ void __launch_bounds__(128)
+k_gather_patch3x3(const __half* __restrict__ feat, int H, int W, int C, int K, int cap, const int32_t* __restrict__ counts,
+                  const int32_t* __restrict__ offsets, const int32_t* __restrict__ ax_idx, const int32_t* __restrict__ cr_idx,
+                  __half* __restrict__ col_ax, __half* __restrict__ col_cr) {
+    const int j = blockIdx.x, n = blockIdx.y;
+    if (j >= counts[n]) return;
+    const int row = offsets[n] + j;
+    if (row >= cap) return;
+    const int cv = C >> 3;
+    const size_t o = static_cast<size_t>(n) * K + j;
+    for (int t = threadIdx.x; t < 5 * 9 * cv; t += blockDim.x) {
+        const int c8 = t % cv;
+        const int tap = (t / cv) % 9;
+        const int pt = t / (9 * cv);
+        const int pix = pt == 0 ? ax_idx[o] : cr_idx[o * 4 + pt - 1];
+        const int y = pix / W + tap / 3 - 1, x = pix % W + tap % 3 - 1;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < H && x >= 0 && x < W)
+            u = __ldg(reinterpret_cast<const uint4*>(feat + ((static_cast<long long>(n) * H + y) * W + x) * C + c8 * 8));
+        __half* dst = pt == 0 ? col_ax + static_cast<long long>(row) * 9 * C : col_cr + (4LL * row + pt - 1) * 9 * C;
+        *reinterpret_cast<uint4*>(dst + tap * C + c8 * 8) = u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_logi_combine(const float* __restrict__ ax, const float* __restrict__ cr, int C, const int32_t* __restrict__ totals,
+               float* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long row = idx / C;
+    if (row >= totals[0]) return;
+    const int c = static_cast<int>(idx % C);
+    const float* r = cr + 4 * row * C + c;
+    float s = __fadd_rn(0.f, r[0]);
+    s = __fadd_rn(s, r[C]);
+    s = __fadd_rn(s, r[2 * C]);
+    s = __fadd_rn(s, r[3 * C]);
+    out[idx] = __fadd_rn(ax[idx], s);
+}
+
+int op_cell_offsets(Engine* e, const int32_t* counts, int N, int cap, int32_t* offsets, int32_t* totals, int32_t* overflow) {
+    e->launch_begin("k_cell_offsets", "lore_feat", 0.0, N * 8.0);
+    k_cell_offsets<<<1, 32, 0, e->stream>>>(counts, N, cap, offsets, totals, overflow);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int32_t* counts, const int32_t* offsets,
+                       const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr) {
+    if ((feat.C % 8) || feat.ld != 0) return set_err(e, DV_ERR_UNSUPPORTED, "gather_patch3x3: dense C %% 8 == 0 input");
+    e->launch_begin("k_gather_patch3x3", "lore_feat", 0.0, (double)cap * 5 * 9 * feat.C * 4.0);
+    k_gather_patch3x3<<<dim3(K, feat.N), 128, 0, e->stream>>>(feat.p, feat.H, feat.W, feat.C, K, cap, counts, offsets, ax_idx, cr_idx,
+                                                              col_ax, col_cr);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int op_logi_combine(Engine* e, const float* ax, const float* cr, int C, int cap, const int32_t* totals, float* out) {
+    e->launch_begin("k_logi_combine", "lore_feat", 0.0, (double)cap * C * 24.0);
+    k_logi_combine<<<grid_for(static_cast<long long>(cap) * C, 256), 256, 0, e->stream>>>(ax, cr, C, totals, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dv

@@ -192,6 +192,60 @@ class Engine:
             return boxes, counts, int(ovf.value)
         return boxes, counts
 
+    LORE_MEAN = (0.408, 0.447, 0.470)  # TableLorePreProcessor.process (lore/processer_lore.py:67-70)
+    LORE_STD = (0.289, 0.274, 0.278)
+
+    def lore_detect_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 NCHW [N,3,H,W] (cuda, pre-processed) -> packed head maps fp32 [N,H/4,W/4,24] (hm after sigmoid)."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("lore expects 3 channels")
+        if out is None:
+            out = torch.empty((n, h // 4, w // 4, 24), dtype=torch.float32, device=x.device)
+        check(self._lib.dv_lore_detect_forward(self._h, _ptr(x), n, h, w, _ptr(out)), self._h, "dv_lore_detect_forward")
+        return out
+
+    def lore_detect_forward_u8(self, img: torch.Tensor, out: Optional[torch.Tensor] = None, flip: bool = False) -> torch.Tensor:
+        """uint8 HWC [N,H,W,3] (cuda; the warpAffine output) -> packed head maps; normalisation fused on the device."""
+        img = _require_cuda(img, torch.uint8, "img")
+        n, h, w, c = img.shape
+        if c != 3:
+            raise ValueError("lore expects HWC images with 3 channels")
+        if out is None:
+            out = torch.empty((n, h // 4, w // 4, 24), dtype=torch.float32, device=img.device)
+        mean = (C.c_float * 3)(*self.LORE_MEAN)
+        std = (C.c_float * 3)(*self.LORE_STD)
+        check(self._lib.dv_lore_detect_forward_u8(self._h, _ptr(img), n, h, w, mean, std, int(flip), _ptr(out)), self._h,
+              "dv_lore_detect_forward_u8")
+        return out
+
+    def lore_cell_features(self, dec: dict, max_rows: int, check_overflow: bool = False):
+        """Output of lore_decode -> (logi_feat fp32 [max_rows,256], offsets int32 [N+1]) from the resident feature map."""
+        n, k = dec["ax_idx"].shape
+        dev = dec["ax_idx"].device
+        feat = torch.zeros((max_rows, 256), dtype=torch.float32, device=dev)
+        offsets = torch.zeros((n + 1,), dtype=torch.int32, device=dev)
+        ovf = C.c_int32(0)
+        check(self._lib.dv_lore_cell_features(self._h, n, k, int(max_rows), _ptr(dec["counts"]), _ptr(dec["ax_idx"]), _ptr(dec["cr_idx"]),
+                                              _ptr(feat), _ptr(offsets), C.byref(ovf) if check_overflow else None), self._h,
+              "dv_lore_cell_features")
+        if check_overflow and ovf.value:
+            raise DocVisionError(f"lore_cell_features: {ovf.value} cells exceed max_rows={max_rows}")
+        return feat, offsets
+
+    def lore_process_forward(self, feat: torch.Tensor, offsets: torch.Tensor):
+        """feat fp32 [max_rows,256], offsets int32 [N+1] (device) -> (logic [max_rows,4], stacked [max_rows,4]) fp32."""
+        feat = _require_cuda(feat, torch.float32, "feat")
+        offsets = _require_cuda(offsets, torch.int32, "offsets")
+        rows = feat.shape[0]
+        n = offsets.shape[0] - 1
+        logic = torch.zeros((rows, 4), dtype=torch.float32, device=feat.device)
+        stacked = torch.zeros((rows, 4), dtype=torch.float32, device=feat.device)
+        check(self._lib.dv_lore_process_forward(self._h, _ptr(feat), rows, _ptr(offsets[n:]), _ptr(offsets), n, _ptr(logic),
+                                                _ptr(stacked)), self._h, "dv_lore_process_forward")
+        return logic, stacked
+
     def lore_decode(self, hm: torch.Tensor, reg: Optional[torch.Tensor], wh: Optional[torch.Tensor], st: Optional[torch.Tensor],
                     inv_affine, K: int = 3000, MK: int = 5000, wiz_rev: bool = True, vis_thresh: float = 0.2,
                     check_overflow: bool = False):

@@ -278,14 +278,17 @@ def _dla_tree(rng, sd, p, levels, cin, cout, stride, level_root=False, root_dim=
         _bn(rng, sd, p + ".project.1", cout)
 
 
-def _dcn(rng, sd, p, cin, cout, off_std=0.5):
+def _dcn(rng, sd, p, cin, cout, off_std=0.04):
     """DeformConv (lore_dla_34.py:65-85) = DCN (dcnv2.py:25-86) + BN + ReLU.  The reference zero-initialises
-    conv_offset_mask; here it is drawn so that offsets are O(off_std) pixels and the sampling path is exercised."""
+    conv_offset_mask; here it is drawn so that the sampling path is exercised with offsets of the size a trained
+    DCN produces (about one pixel: a per-tap bias of std 0.7 px plus a small data-dependent part) -- random O(1)
+    weights on these un-normalised synthetic activations would give offsets of tens of pixels, i.e. a network whose
+    output is chaotic in its own rounding noise."""
     _bn(rng, sd, p + ".actf.0", cout)
     sd[p + ".conv.weight"] = _conv(rng, cout, cin, 3, 3)
     sd[p + ".conv.bias"] = _b(rng, cout)
     sd[p + ".conv.conv_offset_mask.weight"] = (_conv(rng, 27, cin, 3, 3, gain=1.0) * off_std).astype(np.float32)
-    sd[p + ".conv.conv_offset_mask.bias"] = _b(rng, 27, 0.2)
+    sd[p + ".conv.conv_offset_mask.bias"] = np.concatenate([_b(rng, 18, 0.7), _b(rng, 9, 0.5)])
 
 
 def _bilinear_up(c, f):

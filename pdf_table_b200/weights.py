@@ -211,3 +211,133 @@ def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
     t["vit.ln.w"], t["vit.ln.b"] = f(v + ".layernorm.weight"), f(v + ".layernorm.bias")
     put("cls", pack_linear(f("vitstr.classifier.weight"), f("vitstr.classifier.bias")))
     return write_blob(t)
+
+
+# --------------------------------------------------------------------------- Lore (DLA-34 + DCNv2 detector)
+def pack_stem7x7_s1(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """7x7 stride-1 stem on a 3-channel image: K index = r*64 + s*8 + c (s padded 7->8, c padded 3->8), matching the
+    overlapping-window TMA view of the zero-bordered 8-channel input (csrc/igemm_host.cu, A_STEM stride 1)."""
+    w = _np(weight).astype(np.float32)
+    cout, cin, kh, kw = w.shape
+    assert (cin, kh, kw) == (3, 7, 7), w.shape
+    scale, shift = bn_affine(bn, cout)
+    w = w * scale[:, None, None, None]
+    packed = np.zeros((cout, 7, 8, 8), np.float16)
+    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1).astype(np.float16)
+    return packed.reshape(cout, 7 * 64), pad_bias(shift)
+
+
+def pack_split_linear(weight, bias=None) -> Tuple[np.ndarray, np.ndarray]:
+    """nn.Linear weight [out, in] -> split-fp16 operand [out, 3*in_pad] = [W_hi | W_lo | W_hi] with W_hi = fp16(W),
+    W_lo = fp16(W - W_hi): against activations stored as [hi | lo] the k-block walk (hi, hi, lo) accumulates
+    A_hi W_hi + A_hi W_lo + A_lo W_hi in fp32, i.e. the product to ~2^-21 relative (csrc/igemm_host.cu plan_linear)."""
+    w = _np(weight).astype(np.float32)
+    cout, cin = w.shape
+    cp = (cin + 63) // 64 * 64 if cin >= 64 else cin_pad_of(cin)
+    hi = np.zeros((cout, cp), np.float16)
+    lo = np.zeros((cout, cp), np.float16)
+    hi[:, :cin] = w.astype(np.float16)
+    lo[:, :cin] = (w - hi[:, :cin].astype(np.float32)).astype(np.float16)
+    b = np.zeros(cout, np.float32) if bias is None else _np(bias).astype(np.float32)
+    return np.concatenate([hi, lo, hi], 1), pad_bias(b)
+
+
+def _pad_rows(w: np.ndarray, b: np.ndarray, rows: int) -> Tuple[np.ndarray, np.ndarray]:
+    out = np.zeros((rows, w.shape[1]), w.dtype)
+    out[: w.shape[0]] = w
+    return out, b
+
+
+LORE_SMALL_HEADS = (("hm", 2), ("reg", 2), ("wh", 8), ("st", 8))  # channel order of the packed 24-wide map
+
+
+def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference `get_dla_dcn(34, heads)` (lore/lore_dla_34.py:193-206) -> engine blob.
+
+    BatchNorm is folded everywhere (incl. the BN after each DCN).  conv_offset_mask keeps its 27 outputs padded to 32
+    (fp32 epilogue).  The four small heads share one 3x3 conv (64 -> 4*256) and one block-diagonal 1x1 (1024 -> 24);
+    `ax` / `cr` keep separate weights because they are evaluated only at decoded points."""
+    t: Dict[str, np.ndarray] = {}
+    f = lambda k: _np(sd[k]).astype(np.float32)
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1")))
+    put("level0", pack_conv(sd["base.level0.0.weight"], None, _bn(sd, "base.level0.1")))
+    put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
+    for k in sd:
+        if not k.startswith("base.level") or k.startswith(("base.level0", "base.level1")):
+            continue
+        if k.endswith(".conv1.weight") or k.endswith(".conv2.weight"):
+            p, n = k[: -len(".weight")].rsplit(".", 1)
+            put(k[5: -len(".weight")], pack_conv(sd[k], None, _bn(sd, f"{p}.bn{n[-1]}")))
+        elif k.endswith(".root.conv.weight"):
+            p = k[: -len(".conv.weight")]
+            put(k[5: -len(".conv.weight")], pack_conv(sd[k], None, _bn(sd, p + ".bn")))
+        elif k.endswith(".project.0.weight"):
+            p = k[: -len(".0.weight")]
+            put(k[5: -len(".0.weight")], pack_conv(sd[k], None, _bn(sd, p + ".1")))
+    for k in sd:
+        if k.endswith(".conv.conv_offset_mask.weight"):
+            p = k[: -len(".conv.conv_offset_mask.weight")]  # e.g. dla_up.ida_0.proj_1
+            put(p + ".dcn", pack_conv(sd[p + ".conv.weight"], sd[p + ".conv.bias"], _bn(sd, p + ".actf.0")))
+            w, b = pack_conv(sd[k], sd[p + ".conv.conv_offset_mask.bias"])
+            put(p + ".om", _pad_rows(w, b, 32))
+        elif ".up_" in k and k.endswith(".weight"):
+            w = f(k)  # [C,1,2f,2f] -> fp32 [2f][2f][C]
+            t[k[: -len(".weight")] + ".w"] = np.ascontiguousarray(w[:, 0].transpose(1, 2, 0))
+    # small heads: one 3x3 conv and one block-diagonal 1x1
+    w3 = np.concatenate([f(f"{h}.0.weight") for h, _ in LORE_SMALL_HEADS], 0)
+    b3 = np.concatenate([f(f"{h}.0.bias") for h, _ in LORE_SMALL_HEADS], 0)
+    put("heads.conv", pack_conv(w3, b3))
+    w1 = np.zeros((24, 1024, 1, 1), np.float32)
+    b1 = np.zeros(24, np.float32)
+    row = 0
+    for i, (h, c) in enumerate(LORE_SMALL_HEADS):
+        w1[row: row + c, 256 * i: 256 * (i + 1)] = f(f"{h}.2.weight")
+        b1[row: row + c] = f(f"{h}.2.bias")
+        row += c
+    put("heads.out", pack_conv(w1, b1))
+    for h in ("ax", "cr"):
+        put(f"{h}.conv", pack_conv(f(f"{h}.0.weight"), f(f"{h}.0.bias")))
+        put(f"{h}.out", pack_conv(f(f"{h}.2.weight"), f(f"{h}.2.bias")))
+    return write_blob(t)
+
+
+def pack_lore_processor(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference LoreProcessModel (lore/lore_processor.py:399-514) -> engine blob.  Every Linear is
+    packed for the split-fp16 GEMM (the cell counts are tiny, the outputs are ROUNDED to integers downstream, so this
+    model runs at ~fp32 accuracy); q/k/v are concatenated, 1/sqrt(d_k) is folded into q."""
+    t: Dict[str, np.ndarray] = {}
+    f = lambda k: _np(sd[k]).astype(np.float32)
+
+    def put(name, w, b):
+        t[name + ".w"], t[name + ".b"] = pack_split_linear(w, b)
+
+    def transformer(src, dst):
+        put(dst + ".in", f(src + ".linear.weight"), f(src + ".linear.bias"))
+        L = 0
+        while f"{src}.encoder.layers.{L}.norm_1.alpha" in sd:
+            lp, dp = f"{src}.encoder.layers.{L}", f"{dst}.{L}"
+            for n in ("norm_1", "norm_2"):
+                t[f"{dp}.{n}.a"], t[f"{dp}.{n}.b"] = f(f"{lp}.{n}.alpha"), f(f"{lp}.{n}.bias")
+            sc = np.float32(1.0 / np.sqrt(32.0))
+            wq, bq = f(lp + ".attn.q_linear.weight") * sc, f(lp + ".attn.q_linear.bias") * sc
+            put(dp + ".qkv", np.concatenate([wq, f(lp + ".attn.k_linear.weight"), f(lp + ".attn.v_linear.weight")], 0),
+                np.concatenate([bq, f(lp + ".attn.k_linear.bias"), f(lp + ".attn.v_linear.bias")], 0))
+            put(dp + ".out", f(lp + ".attn.out.weight"), f(lp + ".attn.out.bias"))
+            put(dp + ".ff1", f(lp + ".ff.linear_1.weight"), f(lp + ".ff.linear_1.bias"))
+            put(dp + ".ff2", f(lp + ".ff.linear_2.weight"), f(lp + ".ff.linear_2.bias"))
+            L += 1
+        put(dst + ".dec0", f(src + ".decoder.linear.0.weight"), f(src + ".decoder.linear.0.bias"))
+        put(dst + ".dec2", f(src + ".decoder.linear.2.weight"), f(src + ".decoder.linear.2.bias"))
+        return L
+
+    n_axis = transformer("tsfm_axis", "axis")
+    n_stack = transformer("stacker.tsfm", "stack")
+    put("stack.enc0", f("stacker.logi_encoder.0.weight"), f("stacker.logi_encoder.0.bias"))
+    put("stack.enc2", f("stacker.logi_encoder.2.weight"), f("stacker.logi_encoder.2.bias"))
+    t["x_pos"], t["y_pos"] = f("x_position_embeddings.weight"), f("y_position_embeddings.weight")
+    t["meta"] = np.array([n_axis, n_stack, 256, 8], np.int32)
+    return write_blob(t)
