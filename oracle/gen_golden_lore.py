@@ -112,7 +112,32 @@ def gen_processor():
     np.savez_compressed(os.path.join(GOLDEN, "lore_processor_seed0.npz"), **out)
 
 
+def gen_preprocess():
+    """TableLorePreProcessor.__call__ (lore/processer_lore.py:132-160) on synthetic pages of several aspect ratios."""
+    import sys
+    import types
+
+    ref_import.setup()
+    m = types.ModuleType("pdftable.utils.ocr")  # drawing helpers only (save_result); not on the tensor path
+    m.OcrCommonUtils = type("OcrCommonUtils", (), {})
+    sys.modules["pdftable.utils.ocr"] = m
+    from pdftable.model.lore.configuration_lore import LoreConfig
+    from pdftable.model.lore.processer_lore import TableLorePreProcessor
+
+    pre = TableLorePreProcessor(LoreConfig(task_type="wtw"))
+    out = {"sizes": np.array([(600, 800), (1500, 1100), (333, 517), (1024, 1024)])}
+    for i, (h, w) in enumerate(out["sizes"]):
+        item = pre(synth.synthetic_page(3, int(h), int(w)))[0]
+        px = item["pixel_values"].numpy()[0]
+        out[f"meta{i}"] = item["meta"].numpy()[0]
+        out[f"patch{i}"] = px[:, 480:544, 480:544].copy()
+        out[f"sum{i}"] = np.array([px.astype(np.float64).sum(), np.abs(px.astype(np.float64)).sum()])
+    np.savez_compressed(os.path.join(GOLDEN, "lore_pre.npz"), **out)
+    print("lore_pre", [out[f"meta{i}"].tolist() for i in range(4)])
+
+
 if __name__ == "__main__":
+    gen_preprocess()
     gen_network()
     gen_processor()
     gen_decode()

@@ -22,7 +22,8 @@ import torch
 from . import weights
 from .engine import Engine
 
-__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "det_resize_for_test", "keepratio_resize"]
+__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "det_resize_for_test",
+           "keepratio_resize", "lore_affine", "lore_preprocess"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -238,3 +239,112 @@ class OcrRecognitionTask(BaseInferTask):
             else:
                 res.append("".join(self.label_mapping[int(v)] for v in seq))  # KeyError on id 1, as the reference
         return res
+
+
+def lore_affine(center, scale, out_w: int, out_h: int, inv: bool = False) -> np.ndarray:
+    """get_affine_transform(center, scale, rot=0, output_size=(out_w, out_h), inv) of the reference
+    (lore/lineless_table_process.py:403-438): the centre-anchored similarity between the source image and the network
+    frame, from three point pairs through cv2.getAffineTransform (float64 2x3)."""
+    import cv2
+
+    c = np.asarray(center, np.float32)
+    src_w = np.float32(scale)
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0] = c
+    src[1] = c + np.array([0.0, src_w * np.float32(-0.5)], np.float32)
+    dst[0] = [out_w * 0.5, out_h * 0.5]
+    dst[1] = np.array([out_w * 0.5, out_h * 0.5], np.float32) + np.array([0, out_w * -0.5], np.float32)
+    d = src[0] - src[1]
+    src[2] = src[1] + np.array([-d[1], d[0]], np.float32)
+    d = dst[0] - dst[1]
+    dst[2] = dst[1] + np.array([-d[1], d[0]], np.float32)
+    return cv2.getAffineTransform(dst, src) if inv else cv2.getAffineTransform(src, dst)
+
+
+def lore_preprocess(img: np.ndarray, resolution=(1024, 1024)):
+    """TableLorePreProcessor.process (lore/processer_lore.py:66-109) up to the uint8 warp: centre-anchored similarity
+    warp (scale = resolution / max(h, w)) with cv2.warpAffine (bilinear, zero border).  The normalisation and the CHW
+    layout run fused on the GPU.  Returns (uint8 [H,W,3], meta int64 [7] = update_meta :112-130)."""
+    import cv2
+
+    height, width = img.shape[:2]
+    inp_h, inp_w = resolution
+    c = np.array([width / 2.0, height / 2.0], dtype=np.float32)
+    s = max(height, width) * 1.0
+    trans = lore_affine(c, s, inp_w, inp_h)
+    warped = cv2.warpAffine(np.ascontiguousarray(img), trans, (inp_w, inp_h), flags=cv2.INTER_LINEAR)
+    meta = np.array([c[0], c[1], s, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64)  # .long(): cx, cy truncated
+    return warped, meta
+
+
+class OcrTableStructureTask(BaseInferTask):
+    """OcrTableStructureTask (ocr_pdf/ocr_table_structure_task.py:50-271) for model="Lore", task_type="wtw"
+    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers).
+    Returns list[dict{polygons [n,8] float32 source pixels, logi [n,4] integer-valued, inputs}] like the reference's
+    TableLorePostProcessor (lore/processer_lore.py:163-188).  `state_dict` = (detector, processor) state_dicts or paths
+    (the reference's model_best.pth / processor_best.pth, lore/modeling_lore.py:88-101)."""
+
+    K, MK = 3000, 5000  # process_detect_output (lore/lineless_table_process.py:593)
+
+    def __init__(self, task: str = "ocr_table_structure", model: str = "Lore", task_type: str = "wtw", state_dict=None,
+                 table_structure_merge: bool = False, max_cells_per_image: int = 1024, **kwargs):
+        if model != "Lore":
+            raise RuntimeError(f"model {model} not support")
+        if task_type != "wtw":
+            raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements the DLA-34 'wtw' configuration)")
+        if state_dict is None or len(state_dict) != 2:
+            raise RuntimeError("OcrTableStructureTask(predictor_type='b200') needs state_dict=(detector, processor)")
+        self.task_type, self.table_structure_merge = task_type, table_structure_merge
+        self.resolution, self.vis_thresh, self.wiz_rev = (1024, 1024), 0.2, True  # LoreConfig wtw (configuration_lore.py:86-100)
+        self.max_cells_per_image = max_cells_per_image
+        self._sd = (_load_state_dict(state_dict[0]), _load_state_dict(state_dict[1]))
+        super().__init__(task=task, model=model, **kwargs)
+
+    def _construct_model(self, model):
+        self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0]), device=self.device)
+        self.processor = Engine("lore_processor", weights.pack_lore_processor(self._sd[1]), device=self.device)
+        self.post = Engine("post", device=self.device)
+        self._sd = None
+
+    def _preprocess(self, inputs, **kwargs) -> Dict[str, Any]:
+        items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        images, metas = [], []
+        for it in items:
+            img = _read_image(it)
+            if img.ndim == 2:
+                img = np.stack([img] * 3, -1)
+            if not isinstance(it, np.ndarray):
+                img = img[:, :, ::-1]  # path / PIL inputs reach the network as BGR, ndarrays unchanged (processer_lore.py:51-60, 146)
+            warped, meta = lore_preprocess(img, self.resolution)
+            images.append(warped)
+            metas.append(meta)
+        return {"images": np.stack(images), "meta": np.stack(metas), "inputs": list(items)}
+
+    def _run_model(self, inputs, **kwargs):
+        dev = torch.device("cuda", self.device)
+        n = len(inputs["images"])
+        metas = inputs["meta"]
+        inv = np.stack([lore_affine([np.float32(m[0]), np.float32(m[1])], np.float32(m[2]), int(m[6]), int(m[5]), inv=True) for m in metas])
+        maps = self.predictor.lore_detect_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True))
+        dec = self.post.lore_decode(maps, None, None, None, inv, K=self.K, MK=self.MK, wiz_rev=self.wiz_rev, vis_thresh=self.vis_thresh)
+        feat, offsets = self.predictor.lore_cell_features(dec, max_rows=n * self.max_cells_per_image, check_overflow=True)
+        _, stacked = self.processor.lore_process_forward(feat, offsets)
+        counts = dec["counts"].cpu().numpy()
+        offs = offsets.cpu().numpy()
+        kmax = int(counts.max()) if n else 0
+        polygons = dec["polygons"][:, :max(kmax, 1)].cpu().numpy()
+        logits = stacked[: int(offs[-1])].cpu().numpy()
+        inputs["results"] = [{"pred_boxes": polygons[i, : counts[i]], "logits": logits[offs[i]: offs[i + 1]]} for i in range(n)]
+        return inputs
+
+    def _postprocess(self, inputs, **kwargs) -> List[Dict[str, Any]]:
+        out = []
+        for item, res in zip(inputs["inputs"], inputs["results"]):
+            boxes, logi = res["pred_boxes"], res["logits"]
+            if len(boxes) == 0:  # LoreModel.forward (lore/modeling_lore.py:171-173)
+                boxes, logi = np.zeros((1, 8), np.float32), np.zeros((1, 4), np.float32)
+            f = np.floor(logi)
+            logi = np.where(logi - f > 0.5, f + 1, f)  # process_logic_output (lineless_table_process.py:658-663)
+            out.append({"polygons": boxes, "logi": logi.astype(np.float32), "inputs": item})
+        return out

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import convnextvit_ref as ref
+from oracle import lore_decode_ref, lore_processor_ref
 from pdf_table_b200 import predictors, synth
 
 pytestmark = pytest.mark.gpu
@@ -48,3 +49,48 @@ def test_recognition_task_strings_match_reference_golden():
             assert res[i] == want
         else:  # a token whose fp32 top-2 margin is inside the fp16 error band may legitimately differ
             assert abs(len(res[i]) - len(want)) <= 3
+
+
+def test_table_structure_task_lore():
+    """OcrTableStructureTask(model="Lore") end to end: return convention, u8 path == fp32 path, the decode of the
+    engine's own maps equals the oracle decode bit for bit, and the logical locations follow the processor oracle."""
+    sd = synth.lore_dla34_state_dict(0)
+    sd["hm.2.bias"] = np.array([-0.3, -3.5], np.float32)  # random weights: shift the heat maps so that ~100 cells / corners pass the gates
+    psd = synth.lore_processor_state_dict(0)
+    task = predictors.OcrTableStructureTask(model="Lore", task_type="wtw", state_dict=(sd, psd), max_cells_per_image=3000)
+    pages = [synth.synthetic_page(7, 700, 900), synth.synthetic_page(8, 1024, 768)]
+    res = task(pages)
+    assert isinstance(res, list) and len(res) == 2
+    for r in res:
+        assert set(r) >= {"polygons", "logi", "inputs"}
+        assert r["polygons"].dtype == np.float32 and r["polygons"].shape[1] == 8 and r["logi"].shape == (len(r["polygons"]), 4)
+        assert np.array_equal(r["logi"], np.floor(r["logi"])) and (r["logi"] >= 0).all()
+    assert sum(len(r["polygons"]) for r in res) > 5
+    # explicit composition through the C ABI, fp32 input path
+    eng, post, proc = task.predictor, task.post, task.processor
+    mean = np.array(eng.LORE_MEAN, dtype=np.float32).reshape(1, 1, 3)
+    std = np.array(eng.LORE_STD, dtype=np.float32).reshape(1, 1, 3)
+    pre = [predictors.lore_preprocess(p) for p in pages]
+    x = np.stack([((w / 255. - mean) / std).astype(np.float32).transpose(2, 0, 1) for w, _ in pre])
+    maps = eng.lore_detect_forward(torch.from_numpy(x).cuda())
+    maps_u8 = eng.lore_detect_forward_u8(torch.from_numpy(np.stack([w for w, _ in pre])).cuda())
+    assert torch.equal(maps, maps_u8)  # the fused normalisation is bit-exact w.r.t. numpy's float64 expression
+    m = maps.cpu().numpy()
+    for i, (_, meta) in enumerate(pre):
+        z = np.zeros((1, 256, 256), np.float32)
+        want = lore_decode_ref.lore_decode(m[i, :, :, 0:2].transpose(2, 0, 1), m[i, :, :, 2:4].transpose(2, 0, 1),
+                                           m[i, :, :, 4:12].transpose(2, 0, 1), m[i, :, :, 12:20].transpose(2, 0, 1), z, z, meta)
+        np.testing.assert_array_equal(res[i]["polygons"], want["polygons"])
+    # logical locations: processor oracle on the engine's own cell features
+    dec = post.lore_decode(maps, None, None, None, np.stack([predictors.lore_affine([np.float32(mm[0]), np.float32(mm[1])], np.float32(mm[2]), 256, 256, True) for _, mm in pre]))
+    feat, offsets = eng.lore_cell_features(dec, max_rows=6000, check_overflow=True)
+    offs = offsets.cpu().numpy()
+    for i in range(2):
+        f = feat[offs[i]: offs[i + 1]].cpu()
+        if len(f) == 0:
+            continue
+        _, stacked = lore_processor_ref.lore_processor_forward(psd, f)
+        want_logi = lore_decode_ref.round_logic(stacked.numpy())
+        safe = np.abs((stacked.numpy() - np.floor(stacked.numpy())) - 0.5) > 2e-3
+        np.testing.assert_array_equal(res[i]["logi"][safe], want_logi[safe])
+        assert safe.mean() > 0.98

@@ -38,6 +38,19 @@ def test_keepratio_resize_rules():
         assert (want[:, got.shape[1]:] == 0).all()
 
 
+def test_lore_preprocess_matches_reference():
+    """lore_preprocess (uint8 warp + meta) followed by numpy's normalisation == TableLorePreProcessor's pixel_values."""
+    g = np.load(os.path.join(GOLDEN, "lore_pre.npz"))
+    mean = np.array([0.408, 0.447, 0.470], dtype=np.float32).reshape(1, 1, 3)
+    std = np.array([0.289, 0.274, 0.278], dtype=np.float32).reshape(1, 1, 3)
+    for i, (h, w) in enumerate(g["sizes"]):
+        warped, meta = predictors.lore_preprocess(synth.synthetic_page(3, int(h), int(w)))
+        np.testing.assert_array_equal(meta, g[f"meta{i}"])
+        x = ((warped / 255. - mean) / std).astype(np.float32).transpose(2, 0, 1)
+        np.testing.assert_array_equal(x[:, 480:544, 480:544], g[f"patch{i}"])
+        np.testing.assert_allclose([x.astype(np.float64).sum(), np.abs(x.astype(np.float64)).sum()], g[f"sum{i}"], rtol=1e-12)
+
+
 def test_error_behaviour_without_gpu():
     import torch
 
@@ -45,6 +58,10 @@ def test_error_behaviour_without_gpu():
         predictors.OcrDetectionTask(model="east", state_dict={})
     with pytest.raises(RuntimeError):
         predictors.OcrRecognitionTask(model="CRNN", state_dict={})
+    with pytest.raises(RuntimeError):
+        predictors.OcrTableStructureTask(model="CenterNet", state_dict=({}, {}))
+    with pytest.raises(RuntimeError):
+        predictors.OcrTableStructureTask(model="Lore", task_type="ptn", state_dict=({}, {}))
     with pytest.raises(TypeError):
         predictors._read_image(12345)
     if not torch.cuda.is_available():
