@@ -208,6 +208,25 @@ int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const 
                             float* logic_out, float* stacked_out);
 
 /*
+ * PicoDet "anchor decode": head outputs of the four FPN levels -> layout boxes, on the device.
+ * Replaces OcrLayoutTask._postprocess (ocr_layout_task.py:125-157) = OCRPicodetPostProcessor.__call__
+ * (picodet/processor_picodet.py:184-298) with hard_nms / iou_of / area_of (:301-360) and warp_boxes (:136-158).
+ *   scores_host_ptrs[4] : HOST array of 4 DEVICE pointers, level l: fp32 [n, HW_l, num_classes] sigmoid class scores
+ *   dfl_host_ptrs[4]    : HOST array of 4 DEVICE pointers, level l: fp32 [n, HW_l, 4*(reg_max+1)] raw DFL logits
+ *                         (the `export_post_process=False` contract of PicoHead.forward_eval, picodet/pico_head.py:1130-1138);
+ *                         HW_l = ceil(in_height/stride_l) * ceil(in_width/stride_l)
+ *   org_hw_host [n][2]  : original (height, width) of each page; scale_factor_host [n][2] = (ratio_h, ratio_w) of the resize
+ *   score_threshold 0.5, nms_threshold 0.5, nms_top_k 1000 (<= 1000), keep_top_k 100 (<= 100): PicodetConfig defaults
+ *   boxes_out [n][out_cap][6] float64 (device): rows (class id, score, x1, y1, x2, y2) in the reference's order (classes
+ *                         ascending, NMS pick order inside a class), original-image pixels; counts_out [n] int32.
+ * float32 / float64 exactly where the reference has them; softmax uses expf (numpy's SIMD exp may differ in the last ulp).
+ */
+int dv_picodet_decode(dv_handle h, const float* const* scores_host_ptrs, const float* const* dfl_host_ptrs, int n, int num_classes,
+                      int reg_max, const int* strides_host, int in_height, int in_width, const float* org_hw_host,
+                      const float* scale_factor_host, float score_threshold, double nms_threshold, int nms_top_k, int keep_top_k,
+                      int out_cap, double* boxes_out, int32_t* counts_out);
+
+/*
  * ConvNextViT text-line recogniser forward.
  * Replaces OcrRecognitionTask._run_model for model="ConvNextViT" (ocr_recognition_task.py:81-116) =
  * OCRRecognition.forward (ocr_recognition/modeling_ocr_recognition.py:137-149) -> ConvNextViT.forward

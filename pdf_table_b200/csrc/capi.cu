@@ -347,6 +347,16 @@ int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const 
     return lore_process_forward(h, feat, max_rows, n_rows_dev, offsets, n_images, logic_out, stacked_out);
 }
 
+int dv_picodet_decode(dv_handle h, const float* const* scores_host_ptrs, const float* const* dfl_host_ptrs, int n, int num_classes,
+                      int reg_max, const int* strides_host, int in_height, int in_width, const float* org_hw_host,
+                      const float* scale_factor_host, float score_threshold, double nms_threshold, int nms_top_k, int keep_top_k,
+                      int out_cap, double* boxes_out, int32_t* counts_out) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    return picodet_decode(h, scores_host_ptrs, dfl_host_ptrs, n, num_classes, reg_max, strides_host, in_height, in_width, org_hw_host,
+                          scale_factor_host, score_threshold, nms_threshold, nms_top_k, keep_top_k, out_cap, boxes_out, counts_out);
+}
+
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out) {
     if (!h) return DV_ERR_ARG;

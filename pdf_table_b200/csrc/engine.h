@@ -208,6 +208,11 @@ int lore_proc_create(Engine* e);
 int lore_process_forward(Engine* e, const float* feat, int cap_rows, const int32_t* rows_dev, const int32_t* offsets, int n_img,
                          float* logic_out, float* stacked_out);
 
+// picodet_decode.cu
+int picodet_decode(Engine* e, const float* const* scores, const float* const* dfl, int N, int C, int reg_max, const int* strides, int in_h,
+                   int in_w, const float* org_hw_host, const float* scale_host, float score_thr, double iou_thr, int nms_top_k,
+                   int keep_top_k, int out_cap, double* out, int32_t* counts);
+
 // ctc.cu
 int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,
                  int32_t* out_len, float* out_conf);

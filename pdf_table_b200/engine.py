@@ -297,6 +297,34 @@ class Engine:
                                             _ptr(dec["cr_idx"]), _ptr(out)), self._h, "dv_lore_gather_logi")
         return out
 
+    def picodet_decode(self, scores, dfl, org_hw, scale_factor, in_hw=(800, 608), strides=(8, 16, 32, 64), score_threshold: float = 0.5,
+                       nms_threshold: float = 0.5, nms_top_k: int = 1000, keep_top_k: int = 100):
+        """scores[l] fp32 [N,HW_l,C], dfl[l] fp32 [N,HW_l,4*(reg_max+1)] (cuda, 4 levels); org_hw [N,2] (h, w), scale_factor [N,2]
+        (ratio_h, ratio_w) -> (boxes float64 [N, C*keep_top_k, 6] rows (class, score, x1, y1, x2, y2), counts int32 [N])."""
+        if len(scores) != 4 or len(dfl) != 4:
+            raise ValueError("picodet_decode expects 4 levels")
+        scores = [_require_cuda(t, torch.float32, "scores") for t in scores]
+        dfl = [_require_cuda(t, torch.float32, "dfl") for t in dfl]
+        n, _, c = scores[0].shape
+        reg_max = dfl[0].shape[-1] // 4 - 1
+        for lvl, st in enumerate(strides):
+            hw = -(-in_hw[0] // st) * -(-in_hw[1] // st)
+            if tuple(scores[lvl].shape) != (n, hw, c) or tuple(dfl[lvl].shape) != (n, hw, 4 * (reg_max + 1)):
+                raise ValueError(f"level {lvl}: expected [{n},{hw},*] tensors")
+        cap = c * keep_top_k
+        out = torch.zeros((n, cap, 6), dtype=torch.float64, device=scores[0].device)
+        counts = torch.zeros((n,), dtype=torch.int32, device=scores[0].device)
+        sp = (C.c_void_p * 4)(*[t.data_ptr() for t in scores])
+        dp = (C.c_void_p * 4)(*[t.data_ptr() for t in dfl])
+        org = np.ascontiguousarray(np.asarray(org_hw, np.float32).reshape(n, 2))
+        sf = np.ascontiguousarray(np.asarray(scale_factor, np.float32).reshape(n, 2))
+        st = (C.c_int * 4)(*strides)
+        check(self._lib.dv_picodet_decode(self._h, sp, dp, n, c, reg_max, st, int(in_hw[0]), int(in_hw[1]),
+                                          org.ctypes.data_as(C.POINTER(C.c_float)), sf.ctypes.data_as(C.POINTER(C.c_float)),
+                                          float(score_threshold), float(nms_threshold), int(nms_top_k), int(keep_top_k), cap, _ptr(out),
+                                          _ptr(counts)), self._h, "dv_picodet_decode")
+        return out, counts
+
     def ctc_greedy(self, probs: torch.Tensor, blank: int = 0, return_raw: bool = False):
         """[B,T,C] fp32 (cuda) -> (ids [B,T] int32 left-packed / -1 padded, len [B] int32, conf [B] fp32)."""
         probs = _require_cuda(probs, torch.float32, "probs")

@@ -449,3 +449,47 @@ def lore_planted_maps(index: int, h: int = 128, w: int = 128, feat_dim: int = 25
         out["ax"] = rng.standard_normal((feat_dim, h, w)).astype(np.float32)
         out["cr"] = rng.standard_normal((feat_dim, h, w)).astype(np.float32)
     return out
+
+
+# --------------------------------------------------------------------------- planted PicoDet head outputs
+PICODET_STRIDES = (8, 16, 32, 64)
+
+
+def picodet_planted_outputs(index: int, num_classes: int = 5, in_h: int = 800, in_w: int = 608, reg_max: int = 7,
+                            n_objects: int = 12):
+    """Outputs of a PicoDet head (`export_post_process=False` contract, reference picodet/pico_head.py:1130-1138) for a
+    page with planted layout regions: per level l, `scores[l]` fp32 [1, HW_l, C] (sigmoid class scores) and
+    `boxes[l]` fp32 [1, HW_l, 4*(reg_max+1)] (raw DFL logits).  Anchors near the centre of a planted region get a high
+    score for its class and DFL logits peaked (softly, with noise) at distance/stride, so several anchors per object
+    predict overlapping boxes and the per-class NMS has real work; the rest is low-score noise."""
+    rng = np.random.default_rng(31000 + index)
+    scores, boxes = [], []
+    objs = []
+    for _ in range(n_objects):
+        bw, bh = rng.uniform(60, in_w * 0.8), rng.uniform(30, in_h * 0.4)
+        cx, cy = rng.uniform(bw / 2, in_w - bw / 2), rng.uniform(bh / 2, in_h - bh / 2)
+        objs.append((cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2, int(rng.integers(0, num_classes)), rng.uniform(0.55, 0.97)))
+    for stride in PICODET_STRIDES:
+        fh, fw = int(np.ceil(in_h / stride)), int(np.ceil(in_w / stride))
+        sc = (rng.random((fh * fw, num_classes)) * 0.3).astype(np.float32) ** 2
+        bx = (rng.standard_normal((fh * fw, 4 * (reg_max + 1))) * 0.5).astype(np.float32)
+        ys, xs = np.divmod(np.arange(fh * fw), fw)
+        pcx, pcy = (xs + 0.5) * stride, (ys + 0.5) * stride
+        for x0, y0, x1, y1, cls, peak in objs:
+            d = np.stack([pcx - x0, pcy - y0, x1 - pcx, y1 - pcy], 1) / stride  # l, t, r, b in stride units
+            ok = (d.min(1) > 0.3) & (d.max(1) < reg_max - 0.2)
+            # only anchors near the object's centre fire (like a trained head's centre prior)
+            near = (np.abs(pcx - (x0 + x1) / 2) < 0.2 * (x1 - x0)) & (np.abs(pcy - (y0 + y1) / 2) < 0.2 * (y1 - y0))
+            sel = np.flatnonzero(ok & near)
+            for a in sel:
+                sc[a, cls] = np.float32(np.clip(peak - rng.uniform(0, 0.25), 0.05, 0.99))
+                for side in range(4):
+                    t = d[a, side] + rng.normal(0, 0.08)
+                    lo = int(np.floor(t))
+                    logits = np.full(reg_max + 1, -4.0)
+                    logits[np.clip(lo, 0, reg_max)] = 4.0 + np.log(max(1e-3, 1 - (t - lo)))
+                    logits[np.clip(lo + 1, 0, reg_max)] = 4.0 + np.log(max(1e-3, t - lo))
+                    bx[a, side * (reg_max + 1):(side + 1) * (reg_max + 1)] = (logits + rng.normal(0, 0.1, reg_max + 1)).astype(np.float32)
+        scores.append(sc[None])
+        boxes.append(bx[None])
+    return scores, boxes

@@ -90,3 +90,23 @@ def test_lore_processor_oracle_matches_reference_golden():
 def test_round_logic_is_half_down():
     x = np.float32([0.5, 1.5, 2.5000002, 3.49, 0.0, 7.51])
     np.testing.assert_array_equal(lore_decode_ref.round_logic(x), np.float32([0, 1, 3, 3, 0, 8]))
+
+
+def test_picodet_oracle_matches_reference_golden():
+    from oracle import picodet_ref
+
+    g = np.load(os.path.join(GOLDEN, "picodet_post.npz"))
+    cases = [("en", 0, 5, (1100, 850), 12), ("ch", 1, 10, (1600, 1200), 20), ("table", 2, 1, (700, 1000), 4),
+             ("empty", 3, 5, (800, 608), 0), ("dense", 4, 5, (2000, 1500), 60)]
+    for name, idx, c, (oh, ow), nobj in cases:
+        s, b = synth.picodet_planted_outputs(idx, c, n_objects=nobj)
+        got = picodet_ref.picodet_decode(s, b, [oh, ow], [800.0 / oh, 608.0 / ow], [800, 608])[0]
+        np.testing.assert_array_equal(got, g[name], err_msg=name)
+    # SURVEY.md 8c known-answer case: one anchor (level 1, index 500) scoring 0.9 on class 3, DFL one-hot at bin 5
+    scores = [np.zeros((1, hw, 5), np.float32) for hw in (7600, 1900, 475, 130)]
+    boxes = [np.zeros((1, hw, 32), np.float32) for hw in (7600, 1900, 475, 130)]
+    scores[1][0, 500, 3] = 0.9
+    boxes[1][0, 500].reshape(4, 8)[:, 5] = 100.0
+    got = picodet_ref.picodet_decode(scores, boxes, [1600, 1216], [0.5, 0.5], [800, 608])[0]
+    assert got.shape == (1, 6) and got[0, 0] == 3
+    np.testing.assert_allclose(got[0, 2:], [48, 272, 368, 592], atol=1e-3)
