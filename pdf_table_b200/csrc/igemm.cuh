@@ -70,6 +70,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t hfull_bar[4];
+    __shared__ __align__(8) uint64_t hempty_bar[4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int4 s_delta[kMaxKB];
 
@@ -77,9 +79,12 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t row_bytes = 2u * p.BK;
-    const uint32_t a_bytes = 128u * row_bytes;
+    const bool halo = p.mode == A_HALO;
+    const uint32_t a_bytes = halo ? 0u : 128u * row_bytes;  // A_HALO: the ring holds weight tiles only
     const uint32_t b_bytes = static_cast<uint32_t>(p.BLOCK_N) * row_bytes;
     const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t halo_bytes = 18u * 16u * row_bytes;
+    const uint32_t ring_base = smem_base + (halo ? static_cast<uint32_t>(p.halo_stages) * halo_bytes : 0u);
     const int num_stages = p.num_stages;
     const int num_kb = p.num_kb;
     // data-dependent row count (A_FLAT): every role derives the same tile range from it
@@ -95,6 +100,10 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 4);
+        }
+        for (int i = 0; i < 4; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&hfull_bar[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&hempty_bar[i]), 1);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA);
@@ -112,8 +121,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, hstage = 0;
+            uint32_t phase = 0, hphase = 0;
             const int tiles_per_img = p.tiles_x * p.tiles_y;
             const int mode = p.mode;
             const int BK = p.BK, BLOCK_N = p.BLOCK_N;
@@ -127,6 +136,23 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                     const int ty = t / p.tiles_x;
                     y0 = ty * p.TH;
                     x0 = (t - ty * p.tiles_x) * p.TW;
+                }
+                if (halo) {
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        ptx::mbar_wait(ptx::smem_u32(&hempty_bar[hstage]), hphase ^ 1u);
+                        const uint32_t hb = ptx::smem_u32(&hfull_bar[hstage]);
+                        ptx::mbar_expect_tx(hb, halo_bytes);
+                        ptx::tma_load_5d(smem_base + hstage * halo_bytes, &p.tmA, hb, cb * BK, x0 - 1, y0 - 1, img, 0);
+                        if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                            const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+                            ptx::mbar_expect_tx(fb, b_bytes);
+                            ptx::tma_load_2d(ring_base + stage * b_bytes, &p.tmB, fb, (tap * p.ncb + cb) * BK, n_tile * BLOCK_N);
+                            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    continue;
                 }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int4 d = s_delta[kb];
@@ -153,8 +179,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, hstage = 0;
+            uint32_t phase = 0, hphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
@@ -165,6 +191,33 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+                if (halo) {
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        ptx::mbar_wait(ptx::smem_u32(&hfull_bar[hstage]), hphase);
+                        ptx::tc_fence_after();
+                        const uint32_t hbase = smem_base + hstage * halo_bytes;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                            ptx::tc_fence_after();
+                            // tap (r, s): the 16 x 8 output pixels read patch pixels (ly + r, lx + s); one patch row =
+                            // 16 pixels = one 8-row group stride
+                            const uint32_t a0 = hbase + static_cast<uint32_t>((tap / 3) * 16 + tap % 3) * row_bytes;
+                            const uint64_t bdesc = ptx::make_kmajor_desc(ring_base + stage * b_bytes, row_bytes);
+                            for (int k = 0; k < k_steps; ++k) {
+                                const uint64_t adesc = ptx::make_kmajor_desc_sbo(a0 + 32u * k, row_bytes, 16u * row_bytes, p.desc_base_off);
+                                ptx::umma_f16_ss(d_tmem, adesc, bdesc + 2ull * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                            }
+                            ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+                            if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                        }
+                        ptx::umma_commit(ptx::smem_u32(&hempty_bar[hstage]));  // patch free once its 9 x k_steps MMAs retire
+                        if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                     ptx::tc_fence_after();

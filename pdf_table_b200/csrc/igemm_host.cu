@@ -2,6 +2,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -94,12 +95,28 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.BLOCK_N = block_n;
     p.n_tiles = (cs.Cout + block_n - 1) / block_n;
     const int row_bytes = 2 * cs.BK;
-    const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
-    int stages = static_cast<int>((216 * 1024) / stage_bytes);
-    if (stages > 8) stages = 8;
-    if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
-    p.num_stages = stages;
-    plan->smem = stages * stage_bytes + 1024;
+    if (p.mode == A_HALO) {
+        // shared memory: halo-patch ring (18 x 16 pixels x BK channels each) + a ring of per-tap weight tiles
+        const size_t halo_bytes = static_cast<size_t>(18) * 16 * row_bytes, b_bytes = static_cast<size_t>(block_n) * row_bytes;
+        int hs = p.ncb > 1 ? 3 : 2;
+        int stages = static_cast<int>((216 * 1024 - hs * halo_bytes) / b_bytes);
+        if (stages < 3 && hs > 2) {
+            hs = 2;
+            stages = static_cast<int>((216 * 1024 - hs * halo_bytes) / b_bytes);
+        }
+        if (stages > 8) stages = 8;
+        if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
+        p.halo_stages = hs;
+        p.num_stages = stages;
+        plan->smem = hs * halo_bytes + stages * b_bytes + 1024;
+    } else {
+        const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
+        int stages = static_cast<int>((216 * 1024) / stage_bytes);
+        if (stages > 8) stages = 8;
+        if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
+        p.num_stages = stages;
+        plan->smem = stages * stage_bytes + 1024;
+    }
     p.bias = cs.bias;
     p.res = es.res;
     p.res_mode = es.res_mode;
@@ -264,7 +281,25 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         const uint64_t cb = static_cast<uint64_t>(in.ldc()) * 2;  // bytes between consecutive pixels
         if ((in.ldc() % 8) || (reinterpret_cast<uintptr_t>(in.p) & 15))
             return set_err(e, DV_ERR_UNSUPPORTED, "%s: input slice must be 16-byte aligned (ld %% 8, offset %% 8)", name);
-        if (cs.stride == 1) {
+        static const int halo_env = getenv("DV_HALO") ? atoi(getenv("DV_HALO")) : 0;  // opt-in until its pipeline depth is tuned (profiles/r1f)
+        static const int halo_baseoff = getenv("DV_HALO_BASEOFF") ? atoi(getenv("DV_HALO_BASEOFF")) : 0;  // measured on B200: the swizzle is a function of the absolute shared-memory address, shifted starts need NO base offset
+        if (cs.stride == 1 && cs.KH == 3 && cs.KW == 3 && cs.pad == 1 && halo_env) {
+            // halo-patch mode: 16 x 8 output pixels per tile, one {BK, 16, 18} box per channel block
+            p.mode = A_HALO;
+            p.TH = 16;
+            p.TW = 8;
+            p.tiles_y = (Ho + p.TH - 1) / p.TH;
+            p.tiles_x = (Wo + p.TW - 1) / p.TW;
+            p.m_tiles = in.N * p.tiles_x * p.tiles_y;
+            p.ncb = cin_blocks;
+            p.desc_base_off = halo_baseoff;
+            uint64_t dims[5] = {static_cast<uint64_t>(in.C), static_cast<uint64_t>(in.W),
+                                static_cast<uint64_t>(in.H), static_cast<uint64_t>(in.N), 1};
+            uint64_t str[4] = {cb, cb * in.W, cb * in.W * in.H, cb * in.W * in.H * in.N};
+            uint32_t box[5] = {static_cast<uint32_t>(cs.BK), 16, 18, 1, 1};
+            DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
+            for (int t = 0; t < 9 * cin_blocks; ++t) deltas.push_back(make_int4(0, 0, 0, 0));  // unused by the halo path
+        } else if (cs.stride == 1) {
             p.mode = A_PATCH;
             uint64_t dims[5] = {static_cast<uint64_t>(in.C), static_cast<uint64_t>(in.W),
                                 static_cast<uint64_t>(in.H), static_cast<uint64_t>(in.N), 1};

@@ -10,7 +10,10 @@ enum AMode : int {
     A_FLAT = 0,      // A is a plain [M, K] matrix (1x1 stride-1 conv, linear layers)
     A_PATCH = 1,     // stride-1 KHxKW conv, tensor map dims {C, W, H, N, 1}
     A_PATCH_S2 = 2,  // stride-2 conv, parity-split view dims {2C, W/2, 2, H/2, N}
-    A_STEM = 3       // 7x7 s2 conv on a 4-channel padded image, overlapping-window view
+    A_STEM = 3,      // 7x7 conv on the zero-bordered image, overlapping-window view
+    A_HALO = 4       // 3x3 stride-1 pad-1 conv: one (16+2)x(8+2) halo patch per channel block is staged ONCE in shared
+                     // memory (TMA box {BK, 16, 18}) and the nine taps are shifted UMMA descriptors into it; only the
+                     // per-tap weight tiles stream through the stage ring
 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_HSWISH = 4 };
 enum ResMode : int { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };
@@ -24,6 +27,9 @@ struct IGemmParams {
     int num_kb;
     int BK;         // 64 / 32 / 16 fp16 per k-block (row_bytes = 2*BK = swizzle span)
     int num_stages;
+    int halo_stages;  // A_HALO: depth of the halo-patch ring (each 18*16*2*BK bytes)
+    int ncb;          // A_HALO: channel blocks (Cin_pad / BK); k-block index of (tap, cb) = tap * ncb + cb
+    int desc_base_off;  // A_HALO: set the UMMA descriptor base-offset field from the start address
     int M;          // A_FLAT: number of rows
     int Nimg, Ho, Wo;
     int TH, TW, tiles_x, tiles_y;

@@ -163,6 +163,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     return d;
 }
 
+// Same, with an explicit stride between 8-row groups (SBO) and, when `base_off` is set, the matrix base offset
+// field [49,52) = (start >> 7) & 7 that the PTX ISA prescribes for a start address that is not aligned to the
+// swizzle pattern's repeat (used by the halo-patch convolution, whose tap tiles start s pixels into a patch row).
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t row_bytes, uint32_t sbo_bytes, int base_off) {
+    const uint64_t layout = (row_bytes == 128) ? 2ull : (row_bytes == 64) ? 4ull : 6ull;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    if (base_off) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
+    d |= layout << 61;
+    return d;
+}
+
 // Instruction descriptor: A,B = F16 (K-major), D = F32, M = 128, N = n.
 __device__ __forceinline__ uint32_t make_idesc_f16_m128(uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
