@@ -9,7 +9,7 @@
 //   unit, i.e. padding costs nothing and no im2col buffer ever exists in HBM.
 // * W tiles (BLOCK_N x BK, K-major) are fetched by TMA from the packed weight matrix.
 // * tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) accumulates in TMEM (fp32), issued by one thread.
-// * The epilogue (4 warps) reads TMEM with tcgen05.ld and fuses bias(+folded BN), residual add
+// * The epilogue (8 warps, two per TMEM lane quadrant) reads TMEM with tcgen05.ld and fuses bias(+folded BN), residual add
 //   (same resolution or nearest-2x-upsampled), activation, and the store pattern (plain NHWC slice,
 //   s x s nearest replication into a concat slice, or 2x2 pixel-shuffle for ConvTranspose 2x2 s2).
 // * Persistent CTAs (grid = min(tiles, #SM)), a num_stages-deep smem ring between TMA and MMA, and a
@@ -21,13 +21,28 @@
 
 namespace dv {
 
-static constexpr int kIGemmThreads = 192;
+static constexpr int kIGemmThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
 static constexpr int kMaxKB = 160;  // k-blocks per tile whose coordinate deltas are staged in smem
+static constexpr int kBiasSmem = 2048;  // bias values staged in smem (layers with more padded columns read global)
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
     if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.f);
-    if constexpr (ACT == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    if constexpr (ACT == ACT_GELU) {
+        // exact (erf) GELU = relu(x) - |x|/2 * erfc(|x|/sqrt2), erfc by Abramowitz-Stegun 7.1.26: one rcp, one ex2,
+        // five FMAs and NO selects (erff costs ~28 issue slots per element, 9 of them FSELs, and this epilogue is
+        // issue-bound).  |abs err| <= 3.4e-7 over [-12, 12] against float64, i.e. far below the fp16 rounding of the
+        // value that is stored.
+        const float ax = fabsf(x);
+        float t, e;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.f)));  // 0.3275911 / sqrt(2)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.72134752f) * x));       // exp(-x^2 / 2)
+        float p = fmaf(t, 1.061405429f, -1.453152027f);
+        p = fmaf(p, t, 1.421413741f);
+        p = fmaf(p, t, -0.284496736f);
+        p = fmaf(p, t, 0.254829592f);
+        return fmaf(-0.5f * ax, (p * t) * e, fmaxf(x, 0.f));
+    }
     if constexpr (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
     if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
     return x;
@@ -74,6 +89,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     __shared__ __align__(8) uint64_t hempty_bar[4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int4 s_delta[kMaxKB];
+    __shared__ __align__(16) float s_bias[kBiasSmem];  // the layer's bias, staged once (see the epilogue)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -92,6 +108,11 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const int m_tiles_rt = p.m_dyn != nullptr ? (M_rows + 127) >> 7 : p.m_tiles;
 
     for (int i = threadIdx.x; i < num_kb; i += kIGemmThreads) s_delta[i] = __ldg(&p.kb_delta[i]);
+    // ncu (profiles/r1g): the epilogue's first bias FADD of every chunk sat on the long scoreboard (an L1/L2 round trip
+    // per 32 columns with only two warps per scheduler to hide it) -> stage the whole bias vector in shared memory.
+    const bool bias_smem = p.bias != nullptr && p.n_tiles * p.BLOCK_N <= kBiasSmem;
+    if (bias_smem)
+        for (int i = threadIdx.x; i < p.n_tiles * p.BLOCK_N; i += kIGemmThreads) s_bias[i] = __ldg(p.bias + i);
     if (threadIdx.x == 0) {
         for (int i = 0; i < num_stages; ++i) {
             ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
@@ -99,7 +120,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[i]), 1);
-            ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 4);
+            ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 8);
         }
         for (int i = 0; i < 4; ++i) {
             ptx::mbar_init(ptx::smem_u32(&hfull_bar[i]), 1);
@@ -238,8 +259,12 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             }
         }
     } else {
-        // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
+        // ===================== epilogue (8 warps, TMEM lane quadrant = warp % 4) =====================
+        // Eight epilogue warps: warp w may only touch TMEM lanes 32*(w%4).., so the two warps of a quadrant split the
+        // accumulator's 32-column chunks between them (even / odd chunk).  The epilogue, not the MMA, bounds every
+        // GEMM of the recognisers (K <= 512: a GELU costs more issue slots than the 2*K/4096 MMA cycles it follows).
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -292,18 +317,37 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                    static_cast<uint32_t>(acc) * 256u;
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            // the arg-max epilogue needs one thread to see all columns of its row in ascending order: one warp per quadrant
+            const bool idle = ARGMAX && half == 1;
+            // Software-pipelined over 32-column chunks: the tcgen05.ld of the next chunk is in flight while the current
+            // chunk's bias / residual / activation / stores issue (two warps per scheduler cannot hide it otherwise).
+            constexpr int kStep = ARGMAX ? 32 : 64;
+            int c = ARGMAX ? 0 : half * 32;
+            uint32_t v[32];
+            bool have = !idle && c < BLOCK_N && n_tile * BLOCK_N + c < Cout;  // warp-uniform
+            if (have) ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
+            while (have) {
                 const int col0 = n_tile * BLOCK_N + c;
-                if (col0 >= Cout) break;  // warp-uniform
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
                 ptx::tmem_ld_wait();
-                if (!valid) continue;
-                const int ncol = min(32, Cout - col0);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (bias != nullptr) {
+                c += kStep;
+                have = c < BLOCK_N && n_tile * BLOCK_N + c < Cout;
+                if (have) ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
+                if (!valid) continue;
+                const int ncol = min(32, Cout - col0);
+                if (bias_smem) {
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = b4[j];
+                        f[4 * j] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
+                } else if (bias != nullptr) {
                     const float4* b4 = reinterpret_cast<const float4*>(bias + col0);  // padded to 256
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -423,7 +467,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 }
             }
             if constexpr (ARGMAX) {
-                if (n_tile == p.n_tiles - 1 && valid) {
+                if (n_tile == p.n_tiles - 1 && valid && !idle) {
                     p.arg_out[pix] = best_i;
                     if (p.max_out != nullptr) p.max_out[pix] = best_v;
                 }

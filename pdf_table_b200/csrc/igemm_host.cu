@@ -99,10 +99,10 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
         // shared memory: halo-patch ring (18 x 16 pixels x BK channels each) + a ring of per-tap weight tiles
         const size_t halo_bytes = static_cast<size_t>(18) * 16 * row_bytes, b_bytes = static_cast<size_t>(block_n) * row_bytes;
         int hs = p.ncb > 1 ? 3 : 2;
-        int stages = static_cast<int>((216 * 1024 - hs * halo_bytes) / b_bytes);
+        int stages = static_cast<int>((206 * 1024 - hs * halo_bytes) / b_bytes);
         if (stages < 3 && hs > 2) {
             hs = 2;
-            stages = static_cast<int>((216 * 1024 - hs * halo_bytes) / b_bytes);
+            stages = static_cast<int>((206 * 1024 - hs * halo_bytes) / b_bytes);
         }
         if (stages > 8) stages = 8;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
@@ -111,7 +111,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
         plan->smem = hs * halo_bytes + stages * b_bytes + 1024;
     } else {
         const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
-        int stages = static_cast<int>((216 * 1024) / stage_bytes);
+        int stages = static_cast<int>((206 * 1024) / stage_bytes);
         if (stages > 8) stages = 8;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
         p.num_stages = stages;
@@ -367,7 +367,7 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
         auto set = [&](IGemmKernel k) {
             if (attr_rc == cudaSuccess)
                 attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         };
         for (int act = 0; act <= ACT_HSWISH; ++act)
             for (int f = 0; f < 2; ++f) set(pick_kernel(act, f, 0, 0));
