@@ -10,6 +10,6 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; 
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/${TAG}_bench_ref.json
 if [ -z "$SKIP_NCU" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 54 -c 27 -o gpurun_out/${TAG}_conv -f python tools/probe_dbnet.py 32 960 1 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
