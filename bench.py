@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# rank 0 prints exactly ONE stdout line (the JSON): keep NCCL's own "NCCL version ..." banner off stdout
+os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -6,6 +6,8 @@
 // Reference: convnext_vit/modeling_convnext_vit.py:37-45, modeling_convnext.py:28-80, modeling_vit.py:32-180 and the
 // HF blocks they instantiate (ConvNextLayer: dwconv -> LN -> pwconv1 -> GELU -> pwconv2 -> layer_scale -> +res).
 // The residual stream stays fp32 in HBM (it is only C floats per token; the 4C-wide hidden tensors are fp16).
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace dv {
@@ -334,6 +336,128 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_attn75_mma: the same 75-token, 3-head attention on the legacy warp-level tensor path (mma.sync m16n8k16; the
+// problem -- 75 x 75 x 64 per head -- is far below one tcgen05 tile, and the CUDA-core version above had become the
+// second largest kernel of the recogniser).  One CTA per chunk, 15 warps: warp = (head, 16-query tile).  Q, K, V are
+// staged once as fp16 in padded shared memory; S = QK^T stays in registers (10 n-tiles), softmax in fp32 on the quad,
+// P is re-used in place as the fp16 A fragments of the PV product (the accumulator layout of m16n8 equals the A layout
+// of m16k16), V fragments come from ldmatrix.trans.
+constexpr int kAttnRow = 200;                 // halves per staged row (192 + 8 pad: conflict-free ldmatrix)
+constexpr int kAttnMmaThreads = 15 * 32;
+constexpr int kAttnMmaSmem = 3 * 80 * kAttnRow * 2;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kAttnMmaThreads, 1)
+k_attn75_mma(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* sQ = reinterpret_cast<__half*>(sm_raw);
+    __half* sK = sQ + 80 * kAttnRow;
+    __half* sV = sK + 80 * kAttnRow;
+    const int b = blockIdx.x;
+    const __half* base = qkv + static_cast<long long>(b) * 75 * 576;
+    for (int i = threadIdx.x; i < 80 * 72; i += kAttnMmaThreads) {  // 72 x 16 B per token row (q | k | v)
+        const int t = i / 72, c8 = i - t * 72;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (t < 75) u = __ldg(reinterpret_cast<const uint4*>(base + t * 576 + c8 * 8));
+        __half* dst = (c8 < 24 ? sQ : c8 < 48 ? sK : sV) + t * kAttnRow + (c8 % 24) * 8;
+        *reinterpret_cast<uint4*>(dst) = u;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = warp / 5, mt = warp - head * 5;
+    const uint32_t q_s = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
+    const uint32_t k_s = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+    const uint32_t v_s = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+    // ---- S = Q K^T (Q pre-scaled by 1/8 in the packed weights)
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int row = mt * 16 + (lane & 15), col = head * 64 + ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(q_s + (row * kAttnRow + col) * 2, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    float s[10][4];
+#pragma unroll
+    for (int nt = 0; nt < 10; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {  // 32 head dims per ldmatrix.x4
+            uint32_t b0, b1, b2, b3;
+            const int row = nt * 8 + (lane & 7), col = head * 64 + kp * 32 + (lane >> 3) * 8;
+            ldsm_x4(k_s + (row * kAttnRow + col) * 2, b0, b1, b2, b3);
+            mma16816(s[nt], qa[2 * kp], b0, b1);
+            mma16816(s[nt], qa[2 * kp + 1], b2, b3);
+        }
+    }
+    // ---- softmax over the 75 keys (rows r0 = lane/4 and r0 + 8 of the tile; a row lives on the 4 lanes of a quad)
+    const int cq = 2 * (lane & 3);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 10; ++nt) {
+        if (nt * 8 + cq >= 75) s[nt][0] = s[nt][2] = -INFINITY;
+        if (nt * 8 + cq + 1 >= 75) s[nt][1] = s[nt][3] = -INFINITY;
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pa[5][4];
+#pragma unroll
+    for (int nt = 0; nt < 10; ++nt) {
+        const float p0 = __expf(s[nt][0] - m0), p1 = __expf(s[nt][1] - m0);
+        const float p2 = __expf(s[nt][2] - m1), p3 = __expf(s[nt][3] - m1);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2] = pack_h2(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // ---- O = P V
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {  // two 8-wide dim tiles per ldmatrix.x4.trans
+            uint32_t b0, b1, b2, b3;
+            const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = head * 64 + dp * 16 + (lane >> 4) * 8;
+            ldsm_x4_trans(v_s + (row * kAttnRow + col) * 2, b0, b1, b2, b3);
+            mma16816(o[2 * dp], pa[kk], b0, b1);
+            mma16816(o[2 * dp + 1], pa[kk], b2, b3);
+        }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = mt * 16 + (lane >> 2), r1 = r0 + 8;
+    __half* out = ctx + static_cast<long long>(b) * 75 * 192 + head * 64 + cq;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+        if (r0 < 75) *reinterpret_cast<__half2*>(out + r0 * 192 + dt * 8) = __floats2half2_rn(o[dt][0] * i0, o[dt][1] * i0);
+        if (r1 < 75) *reinterpret_cast<__half2*>(out + r1 * 192 + dt * 8) = __floats2half2_rn(o[dt][2] * i1, o[dt][3] * i1);
+    }
+}
+
 template <int C, int H>
 int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, const float* lnw, const float* lnb,
               __half* out, const char* layer) {
@@ -394,12 +518,15 @@ int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* l
 
 int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer) {
     static bool attr_done = false;
+    static const bool use_mma = !(getenv("DV_ATTN_SIMT") && atoi(getenv("DV_ATTN_SIMT")));
     if (!attr_done) {
         DV_CUDA(e, cudaFuncSetAttribute(k_attn75, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        DV_CUDA(e, cudaFuncSetAttribute(k_attn75_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMmaSmem));
         attr_done = true;
     }
-    e->launch_begin("k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
-    k_attn75<<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
+    e->launch_begin(use_mma ? "k_attn75_mma" : "k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
+    if (use_mma) k_attn75_mma<<<B, kAttnMmaThreads, kAttnMmaSmem, e->stream>>>(qkv, ctx);
+    else k_attn75<<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
