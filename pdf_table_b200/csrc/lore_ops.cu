@@ -114,63 +114,69 @@ int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out) {
 
 // ---------------------------------------------------------------------------------------------- DCN sampling
 // om: fp32 [M, 32] = conv_offset_mask output; columns 2k, 2k+1 = (dy, dx) of tap k, 18+k = mask logit (dcnv2.py:73-76).
-// One thread = (pixel, tap, 8 channels).  Sampling rule = torchvision deform_conv2d_kernel bilinear_interpolate.
+// One thread = (pixel, 8 channels), looping over the nine taps; grid = (pixel blocks, image rows).  Sampling rule =
+// torchvision deform_conv2d_kernel bilinear_interpolate.  (The first version used one thread per (pixel, tap, 8 ch) with
+// a flat 64-bit index: ncu showed 450 instructions per thread, most of them index arithmetic, at 79 % issue
+// utilisation -- profiles/r1m.  32-bit 2-D indexing and the tap loop cut that about fivefold.)
 __global__ void __launch_bounds__(256)
-k_dcn_im2col(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, const float* __restrict__ om,
-             __half* __restrict__ col) {
-    const int cv = C >> 3;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    const long long total = static_cast<long long>(N) * H * W * 9 * cv;
-    if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
-    const int tap = static_cast<int>(t % 9);
-    const long long pix = t / 9;
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    const float* o = om + pix * 32;
-    const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
-    const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
-    const float py = static_cast<float>(y + tap / 3 - 1) + dy;
-    const float px = static_cast<float>(x + tap % 3 - 1) + dx;
-    float acc[8];
+k_dcn_im2col(const __half* __restrict__ in, int H, int W, int lcv, int ldi, const float* __restrict__ om, __half* __restrict__ col) {
+    const int cv = 1 << lcv, C = cv << 3;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int x = t >> lcv, c8 = t & (cv - 1);
+    if (x >= W) return;
+    const int row = blockIdx.y;  // n * H + y
+    const int y = row % H;
+    const int pix = row * W + x;
+    const float* o = om + static_cast<size_t>(pix) * 32;
+    const __half* base = in + static_cast<size_t>(row - y) * W * ldi + c8 * 8;  // image origin + channel group
+    __half* dst = col + static_cast<size_t>(pix) * 9 * C + c8 * 8;
+#pragma unroll 3
+    for (int tap = 0; tap < 9; ++tap) {
+        const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
+        const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
+        const float py = static_cast<float>(y + tap / 3 - 1) + dy;
+        const float px = static_cast<float>(x + tap % 3 - 1) + dx;
+        float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    if (py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W)) {
-        const float fy = floorf(py), fx = floorf(px);
-        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-        const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-        const float w4[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
-        const __half* base = in + static_cast<long long>(n) * H * W * ldi + c8 * 8;
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        if (py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W)) {
+            const float fy = floorf(py), fx = floorf(px);
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+            const float w4[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
-            if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(yy) * W + xx) * ldi));
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
+            for (int k = 0; k < 4; ++k) {
+                const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+                if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(yy * W + xx) * ldi));
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(h[i]);
-                    acc[2 * i] = fmaf(w4[k], f.x, acc[2 * i]);
-                    acc[2 * i + 1] = fmaf(w4[k], f.y, acc[2 * i + 1]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(h[i]);
+                        acc[2 * i] = fmaf(w4[k], f.x, acc[2 * i]);
+                        acc[2 * i + 1] = fmaf(w4[k], f.y, acc[2 * i + 1]);
+                    }
                 }
             }
         }
-    }
-    uint4 out;
-    __half2* ho = reinterpret_cast<__half2*>(&out);
+        uint4 out;
+        __half2* ho = reinterpret_cast<__half2*>(&out);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * mask, acc[2 * i + 1] * mask);
-    *reinterpret_cast<uint4*>(col + pix * (9LL * C) + tap * C + c8 * 8) = out;
+        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * mask, acc[2 * i + 1] * mask);
+        *reinterpret_cast<uint4*>(dst + tap * C) = out;
+    }
 }
 
 int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer) {
-    if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "dcn_im2col: C %% 8 != 0");
-    const long long total = static_cast<long long>(in.N) * in.H * in.W * 9 * (in.C / 8);
+    const int cv = in.C >> 3;
+    int lcv = 0;
+    while ((1 << lcv) < cv) ++lcv;
+    if ((in.C % 8) || (1 << lcv) != cv) return set_err(e, DV_ERR_UNSUPPORTED, "dcn_im2col: C must be 8 * 2^k");
+    if (static_cast<long long>(in.N) * in.H * in.W * 9 * in.C > 0x7fffffffLL * 4 || static_cast<long long>(in.N) * in.H > 65535)
+        return set_err(e, DV_ERR_UNSUPPORTED, "dcn_im2col: tensor too large (N*H <= 65535)");
     const double px = static_cast<double>(in.N) * in.H * in.W;
     e->launch_begin("k_dcn_im2col", layer, px * 9 * in.C * 9.0, px * (in.C * 2.0 + 128.0 + 18.0 * in.C));
-    k_dcn_im2col<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), om, col);
+    k_dcn_im2col<<<dim3((in.W * cv + 255) / 256, in.N * in.H), 256, 0, e->stream>>>(in.p, in.H, in.W, lcv, in.ldc(), om, col);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
