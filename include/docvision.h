@@ -54,6 +54,7 @@ const char* dv_last_error(dv_handle h);
  *                "convnext_vit"  ConvNextViT text-line recogniser (reference model/convnext_vit/
  *                                modeling_convnext_vit.py:20-45)
  *                "lore_dla34"    Lore table-structure detector, DLA-34 + DCNv2 (reference model/lore/lore_dla_34.py:193)
+ *                "picodet"       PicoDet layout detector as a graph program (reference model/picodet/{lcnet,csp_pan,pico_head}.py)
  *                "lore_processor" Lore logical-location transformers (reference model/lore/lore_processor.py:399)
  *   weight_blob: HOST pointer to a blob written by pdf_table_b200.weights.pack_* (may be NULL for "post")
  * Replaces: BaseInferTask._get_inference_model / DeployUtils.model_eval (base_infer_task.py:146-169,
@@ -206,6 +207,26 @@ int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t
  */
 int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
                             float* logic_out, float* stacked_out);
+
+/*
+ * PicoDet layout detector (model kind "picodet"): LCNet-x1.0 backbone + CSP-PAN neck + PicoHead, executed from the graph
+ * program that pdf_table_b200.picodet_graph lowers the reference modules to (picodet/lcnet.py:159-263,
+ * picodet/csp_pan.py:233-360, picodet/pico_head.py:37-167, 1108-1138).
+ * Replaces OcrLayoutTask._run_model (ocr_layout_task.py:84-123: the ONNX session of picodet_lcnet_x1_0_fgd_layout*) with
+ * the output contract of PicoHead.forward_eval(export_post_process=False) (pico_head.py:1130-1138).
+ *   in_nchw_f32 : [n,3,height,width] fp32, the output of OCRPicodetPreProcessor (picodet/processor_picodet.py:72-113); 800 x 608
+ *   _u8 variant : images_hwc_u8 [n,height,width,3] = the cv2.resize output; the channel flip (:94) and
+ *                 (x * scale - mean) / std in fp32 (:66-70) are fused into the stem kernel
+ *   scores_out_host_ptrs[4] : HOST array of 4 DEVICE pointers, level l: fp32 [n, HW_l, num_classes] sigmoid class scores
+ *   dfl_out_host_ptrs[4]    : HOST array of 4 DEVICE pointers, level l: fp32 [n, HW_l, 32] raw DFL logits
+ *                             (HW_l = ceil(height/s_l) * ceil(width/s_l), s = 8, 16, 32, 64) -- the inputs of dv_picodet_decode
+ */
+int dv_picodet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* const* scores_out_host_ptrs,
+                       float* const* dfl_out_host_ptrs);
+int dv_picodet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                          const float* std3_host, float scale, int flip, float* const* scores_out_host_ptrs,
+                          float* const* dfl_out_host_ptrs);
+int dv_picodet_num_classes(dv_handle h);
 
 /*
  * PicoDet "anchor decode": head outputs of the four FPN levels -> layout boxes, on the device.

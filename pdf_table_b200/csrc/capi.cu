@@ -1,6 +1,7 @@
 // C ABI (include/docvision.h) over the engine: handle lifetime, weight blob loading, entry points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/docvision.h"
@@ -144,6 +145,8 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = dbnet_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
+        } else if (e->kind == "picodet") {
+            rc = graph_create(e);
         } else if (e->kind == "lore_dla34") {
             rc = lore_create(e);
         } else if (e->kind == "lore_processor") {
@@ -232,6 +235,7 @@ double dv_model_flops(dv_handle h) {
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
     if (h->kind == "lore_dla34") return lore_flops(h);
+    if (h->kind == "picodet") return graph_flops(h);
     return 0.0;
 }
 
@@ -255,6 +259,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
     cudaSetDevice(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if (h->kind == "lore_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
+    if (h->kind == "picodet" && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
     return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
 }
 
@@ -356,6 +361,26 @@ int dv_picodet_decode(dv_handle h, const float* const* scores_host_ptrs, const f
     return picodet_decode(h, scores_host_ptrs, dfl_host_ptrs, n, num_classes, reg_max, strides_host, in_height, in_width, org_hw_host,
                           scale_factor_host, score_threshold, nms_threshold, nms_top_k, keep_top_k, out_cap, boxes_out, counts_out);
 }
+
+int dv_picodet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* const* scores_out_host_ptrs,
+                       float* const* dfl_out_host_ptrs) {
+    if (!h) return DV_ERR_ARG;
+    if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_picodet_forward: null input");
+    cudaSetDevice(h->device);
+    return picodet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 1.f, 0, n, height, width, scores_out_host_ptrs, dfl_out_host_ptrs);
+}
+
+int dv_picodet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                          const float* std3_host, float scale, int flip, float* const* scores_out_host_ptrs,
+                          float* const* dfl_out_host_ptrs) {
+    if (!h) return DV_ERR_ARG;
+    if (!images_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_picodet_forward_u8: null input");
+    cudaSetDevice(h->device);
+    return picodet_forward(h, nullptr, images_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, scores_out_host_ptrs,
+                           dfl_out_host_ptrs);
+}
+
+int dv_picodet_num_classes(dv_handle h) { return h ? graph_num_classes(h) : 0; }
 
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out) {

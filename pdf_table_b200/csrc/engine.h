@@ -208,6 +208,14 @@ int lore_proc_create(Engine* e);
 int lore_process_forward(Engine* e, const float* feat, int cap_rows, const int32_t* rows_dev, const int32_t* offsets, int n_img,
                          float* logic_out, float* stacked_out);
 
+// graph_net.cu (PicoDet as a graph program)
+int graph_create(Engine* e);
+double graph_flops(Engine* e);
+int graph_num_classes(Engine* e);
+int graph_debug_tensor(Engine* e, int tensor_id, float* out_nchw, int* dims4);
+int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip,
+                    int N, int H, int W, float* const* scores_out, float* const* dfl_out);
+
 // picodet_decode.cu
 int picodet_decode(Engine* e, const float* const* scores, const float* const* dfl, int N, int C, int reg_max, const int* strides, int in_h,
                    int in_w, const float* org_hw_host, const float* scale_host, float score_thr, double iou_thr, int nms_top_k,

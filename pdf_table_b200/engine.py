@@ -297,6 +297,40 @@ class Engine:
                                             _ptr(dec["cr_idx"]), _ptr(out)), self._h, "dv_lore_gather_logi")
         return out
 
+    PICODET_MEAN = (0.485, 0.456, 0.406)  # PicodetConfig norm_mean / norm_std (picodet/configuration_picodet.py:50-51)
+    PICODET_STD = (0.229, 0.224, 0.225)
+    PICODET_STRIDES = (8, 16, 32, 64)
+
+    def _picodet_outputs(self, n, h, w, dev):
+        c = int(self._lib.dv_picodet_num_classes(self._h))
+        hw = [-(-h // s) * -(-w // s) for s in self.PICODET_STRIDES]
+        scores = [torch.empty((n, m, c), dtype=torch.float32, device=dev) for m in hw]
+        dfl = [torch.empty((n, m, 32), dtype=torch.float32, device=dev) for m in hw]
+        return scores, dfl, (C.c_void_p * 4)(*[t.data_ptr() for t in scores]), (C.c_void_p * 4)(*[t.data_ptr() for t in dfl])
+
+    def picodet_forward(self, x: torch.Tensor):
+        """fp32 NCHW [N,3,H,W] (cuda, pre-processed) -> (scores[4] fp32 [N,HW_l,C], dfl[4] fp32 [N,HW_l,32])."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("picodet expects 3 channels")
+        scores, dfl, sp, dp = self._picodet_outputs(n, h, w, x.device)
+        check(self._lib.dv_picodet_forward(self._h, _ptr(x), n, h, w, sp, dp), self._h, "dv_picodet_forward")
+        return scores, dfl
+
+    def picodet_forward_u8(self, img: torch.Tensor, flip: bool = True):
+        """uint8 HWC [N,H,W,3] (cuda; the cv2.resize output) -> (scores[4], dfl[4]); flip + normalisation fused."""
+        img = _require_cuda(img, torch.uint8, "img")
+        n, h, w, c = img.shape
+        if c != 3:
+            raise ValueError("picodet expects HWC images with 3 channels")
+        scores, dfl, sp, dp = self._picodet_outputs(n, h, w, img.device)
+        mean = (C.c_float * 3)(*self.PICODET_MEAN)
+        std = (C.c_float * 3)(*self.PICODET_STD)
+        check(self._lib.dv_picodet_forward_u8(self._h, _ptr(img), n, h, w, mean, std, float(np.float32(1.0 / 255.0)), int(flip), sp, dp),
+              self._h, "dv_picodet_forward_u8")
+        return scores, dfl
+
     def picodet_decode(self, scores, dfl, org_hw, scale_factor, in_hw=(800, 608), strides=(8, 16, 32, 64), score_threshold: float = 0.5,
                        nms_threshold: float = 0.5, nms_top_k: int = 1000, keep_top_k: int = 100):
         """scores[l] fp32 [N,HW_l,C], dfl[l] fp32 [N,HW_l,4*(reg_max+1)] (cuda, 4 levels); org_hw [N,2] (h, w), scale_factor [N,2]

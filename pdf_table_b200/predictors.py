@@ -22,7 +22,7 @@ import torch
 from . import weights
 from .engine import Engine
 
-__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "det_resize_for_test",
+__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
            "keepratio_resize", "lore_affine", "lore_preprocess"]
 
 
@@ -347,4 +347,70 @@ class OcrTableStructureTask(BaseInferTask):
             f = np.floor(logi)
             logi = np.where(logi - f > 0.5, f + 1, f)  # process_logic_output (lineless_table_process.py:658-663)
             out.append({"polygons": boxes, "logi": logi.astype(np.float32), "inputs": item})
+        return out
+
+
+class OcrLayoutTask(BaseInferTask):
+    """OcrLayoutTask (ocr_pdf/ocr_layout_task.py:27-157) for model="picodet": LCNet-x1.0 + CSP-PAN + PicoHead on the engine,
+    anchor decode + per-class NMS on the GPU.  Returns list[list[dict{bbox float64[4], label, score, category_id}]] like the
+    reference (picodet/processor_picodet.py:288-297).  `state_dict` = (backbone, neck, head) state_dicts of the reference
+    modules (the hub ships only the ONNX export of this architecture)."""
+
+    LABELS = {  # PicodetConfig.label_config (picodet/configuration_picodet.py:83-108)
+        "ch": ["text", "title", "figure", "figure_caption", "table", "table_caption", "header", "footer", "reference", "equation"],
+        "en": ["text", "title", "list", "table", "figure"],
+        "table": ["table"],
+    }
+    IMG_H, IMG_W = 800, 608
+
+    def __init__(self, task: str = "ocr_layout", model: str = "picodet", task_type: str = "en", score_threshold: float = 0.5,
+                 nms_threshold: float = 0.5, state_dict=None, nms_top_k: int = 1000, keep_top_k: int = 100, **kwargs):
+        if model != "picodet":
+            raise RuntimeError(f"model {model} not support")
+        if task_type not in ("ch", "en", "table"):
+            task_type = "en"  # ocr_layout_task.py:36-37
+        if state_dict is None or len(state_dict) != 3:
+            raise RuntimeError("OcrLayoutTask(predictor_type='b200') needs state_dict=(backbone, neck, head)")
+        self.task_type, self.score_threshold, self.nms_threshold = task_type, score_threshold, nms_threshold
+        self.nms_top_k, self.keep_top_k = nms_top_k, keep_top_k
+        self.id2label = dict(enumerate(self.LABELS[task_type]))
+        self._sd = tuple(_load_state_dict(s) for s in state_dict)
+        super().__init__(task=task, model=model, **kwargs)
+
+    def _construct_model(self, model):
+        from .picodet_graph import pack_picodet
+
+        self.predictor = Engine("picodet", pack_picodet(*self._sd, num_classes=len(self.id2label)), device=self.device)
+        self.post = Engine("post", device=self.device)
+        self._sd = None
+
+    def _preprocess(self, inputs, **kwargs) -> Dict[str, Any]:
+        """OCRPicodetPreProcessor.__call__ (picodet/processor_picodet.py:72-113) up to the uint8 resize (the reference
+        flips the channels first and resizes afterwards; cv2.resize acts per channel, so resizing first and flipping on the
+        GPU gives the same pixels)."""
+        import cv2
+
+        items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        imgs, org, sf = [], [], []
+        for it in items:
+            img = _read_image(it)
+            h, w = img.shape[:2]
+            imgs.append(cv2.resize(np.ascontiguousarray(img), (self.IMG_W, self.IMG_H)))
+            org.append((h, w))
+            sf.append((float(self.IMG_H) / h, float(self.IMG_W) / w))
+        return {"images": np.stack(imgs), "org_shape": org, "scale_factor": sf, "inputs": list(items)}
+
+    def _run_model(self, inputs, **kwargs):
+        dev = torch.device("cuda", self.device)
+        scores, dfl = self.predictor.picodet_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True), flip=True)
+        boxes, counts = self.post.picodet_decode(scores, dfl, inputs["org_shape"], inputs["scale_factor"], (self.IMG_H, self.IMG_W),
+                                                 score_threshold=self.score_threshold, nms_threshold=self.nms_threshold,
+                                                 nms_top_k=self.nms_top_k, keep_top_k=self.keep_top_k)
+        inputs["boxes"], inputs["counts"] = boxes.cpu().numpy(), counts.cpu().numpy()
+        return inputs
+
+    def _postprocess(self, inputs, **kwargs) -> List[List[Dict[str, Any]]]:
+        out = []
+        for rows, n in zip(inputs["boxes"], inputs["counts"]):
+            out.append([{"bbox": r[2:].copy(), "label": self.id2label[int(r[0])], "score": r[1], "category_id": int(r[0])} for r in rows[:n]])
         return out

@@ -493,3 +493,82 @@ def picodet_planted_outputs(index: int, num_classes: int = 5, in_h: int = 800, i
         scores.append(sc[None])
         boxes.append(bx[None])
     return scores, boxes
+
+
+# --------------------------------------------------------------------------- PicoDet (LCNet-x1.0 + CSP-PAN + PicoHead)
+LCNET_CONFIG = {  # reference picodet/lcnet.py:25-46: k, in_c, out_c, stride, use_se
+    "blocks2": [[3, 16, 32, 1, False]],
+    "blocks3": [[3, 32, 64, 2, False], [3, 64, 64, 1, False]],
+    "blocks4": [[3, 64, 128, 2, False], [3, 128, 128, 1, False]],
+    "blocks5": [[3, 128, 256, 2, False]] + [[5, 256, 256, 1, False]] * 5,
+    "blocks6": [[5, 256, 512, 2, True], [5, 512, 512, 1, True]],
+}
+PICO_NECK_CH, PICO_NECK_K, PICO_HEAD_CONVS, PICO_REG_MAX = 128, 5, 4, 7
+
+
+def picodet_state_dicts(seed: int = 0, num_classes: int = 5):
+    """Seeded weights for the three PicoDet modules with the reference's key names / shapes:
+    LCNet(scale=1.0, feature_maps=[3,4,5]) (picodet/lcnet.py:159), CSPPAN(in=[128,256,512], out=128, kernel 5,
+    num_features=4, depthwise, hard_swish) (picodet/csp_pan.py:233), PicoHead(PicoFeat(128 -> 128, 4 strides, 4 convs,
+    share_cls_reg, use_se), fpn_stride [8,16,32,64], reg_max 7) (picodet/pico_head.py:37-167, 972-1160) -- the
+    hyper-parameters of PaddleDetection's picodet_lcnet_x1_0_layout.  Returns (backbone, neck, head)."""
+    rng = np.random.Generator(np.random.PCG64(4000 + seed))
+
+    def conv_bn(sd, p, cout, cin, k, groups=1, conv="conv", bn="bn", gain=1.0):
+        sd[f"{p}.{conv}.weight"] = _conv(rng, cout, cin // groups, k, k, gain)
+        _bn(rng, sd, f"{p}.{bn}", cout)
+
+    bb: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    conv_bn(bb, "conv1", 16, 3, 3)
+    for name, cfg in LCNET_CONFIG.items():
+        for i, (k, cin, cout, s, se) in enumerate(cfg):
+            p = f"{name}.{i}"
+            conv_bn(bb, p + ".dw_conv", cin, cin, k, groups=cin)
+            if se:
+                bb[p + ".se.conv1.weight"] = _conv(rng, cin // 4, cin, 1, 1, 1.0)
+                bb[p + ".se.conv1.bias"] = _b(rng, cin // 4)
+                bb[p + ".se.conv2.weight"] = _conv(rng, cin, cin // 4, 1, 1, 1.0)
+                bb[p + ".se.conv2.bias"] = _b(rng, cin, 0.5)
+            conv_bn(bb, p + ".pw_conv", cout, cin, 1)
+    nk: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    c = PICO_NECK_CH
+
+    def dp(p, ch, k):  # DPModule
+        nk[p + ".dwconv.weight"] = _conv(rng, ch, 1, k, k, 1.0)
+        _bn(rng, nk, p + ".bn1", ch)
+        nk[p + ".pwconv.weight"] = _conv(rng, ch, ch, 1, 1, 1.0)
+        _bn(rng, nk, p + ".bn2", ch)
+
+    def csp(p):
+        mid = c // 2
+        conv_bn(nk, p + ".main_conv", mid, 2 * c, 1)
+        conv_bn(nk, p + ".short_conv", mid, 2 * c, 1)
+        conv_bn(nk, p + ".final_conv", c, 2 * mid, 1)
+        conv_bn(nk, p + ".blocks.0.conv1", mid, mid, 1)
+        dp(p + ".blocks.0.conv2", mid, PICO_NECK_K)
+
+    for i, cin in enumerate((128, 256, 512)):
+        conv_bn(nk, f"conv_t.convs.{i}", c, cin, 1)
+    dp("first_top_conv", c, PICO_NECK_K)
+    dp("second_top_conv", c, PICO_NECK_K)
+    csp("top_down_blocks.0")
+    csp("top_down_blocks.1")
+    dp("downsamples.0", c, PICO_NECK_K)
+    dp("downsamples.1", c, PICO_NECK_K)
+    csp("bottom_up_blocks.0")
+    csp("bottom_up_blocks.1")
+    hd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for lvl in range(4):  # PicoSE: built, but with share_cls_reg its output is never read (pico_head.py:1117-1124)
+        hd[f"conv_feat.se.{lvl}.fc.weight"] = _conv(rng, c, c, 1, 1, 1.0)
+        hd[f"conv_feat.se.{lvl}.fc.bias"] = _b(rng, c)
+        conv_bn(hd, f"conv_feat.se.{lvl}.conv", c, c, 1, bn="norm")
+    for lvl in range(4):
+        for i in range(PICO_HEAD_CONVS):
+            conv_bn(hd, f"conv_feat.cls_conv_dw{lvl}_{i}", c, c, 5, groups=c, bn="norm")
+            conv_bn(hd, f"conv_feat.cls_conv_pw{lvl}_{i}", c, c, 1, bn="norm")
+    for lvl in range(4):
+        hd[f"head_cls{lvl}.weight"] = _conv(rng, num_classes + 4 * (PICO_REG_MAX + 1), c, 1, 1, 1.0)
+        bias = _b(rng, num_classes + 4 * (PICO_REG_MAX + 1), 0.5)
+        bias[:num_classes] -= 2.0  # class prior: most anchors are background
+        hd[f"head_cls{lvl}.bias"] = bias
+    return bb, nk, hd

@@ -110,3 +110,44 @@ def test_picodet_oracle_matches_reference_golden():
     got = picodet_ref.picodet_decode(scores, boxes, [1600, 1216], [0.5, 0.5], [800, 608])[0]
     assert got.shape == (1, 6) and got[0, 0] == 3
     np.testing.assert_allclose(got[0, 2:], [48, 272, 368, 592], atol=1e-3)
+
+
+def test_picodet_network_oracle_matches_reference_golden():
+    from oracle import picodet_net_ref
+
+    g = np.load(os.path.join(GOLDEN, "picodet_net_seed0.npz"))
+    bb, nk, hd = synth.picodet_state_dicts(0, 5)
+    s, d = picodet_net_ref.picodet_forward(bb, nk, hd, torch.from_numpy(g["x"]), 5)
+    for lvl in range(4):
+        np.testing.assert_allclose(s[lvl].numpy(), g[f"scores{lvl}"], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(d[lvl].numpy(), g[f"dfl{lvl}"], atol=1e-5, rtol=0)
+
+
+def test_picodet_graph_program_is_consistent():
+    """The lowered program: every op reads tensors / slices that an earlier op wrote, slices stay inside their buffers."""
+    from pdf_table_b200 import picodet_graph as G
+
+    bb, nk, hd = synth.picodet_state_dicts(0, 5)
+    blob, meta = G.build_picodet(bb, nk, hd, 5)
+    tensors, ops = blob["graph.tensors"], blob["graph.ops"]
+    written = {0: [(0, 3)]}
+    for code, in_t, in_coff, in_c, out_t, out_coff, out_c, k, stride, act, w, aux in ops:
+        assert in_coff + in_c <= tensors[in_t][0]
+        assert any(a <= in_coff and in_coff + in_c <= b for a, b in _merge(written.get(in_t, []))), (code, in_t, in_coff, in_c)
+        if code == G.OP_ADD:
+            assert aux in written
+        if code != G.OP_HEAD:
+            assert out_coff + out_c <= tensors[out_t][0]
+            written.setdefault(out_t, []).append((out_coff, out_coff + out_c))
+    assert len([o for o in ops if o[0] == G.OP_HEAD]) == 4
+    assert set(meta["features"]) == {"c3", "c4", "c5", "p3", "p4", "p5", "p6"}
+
+
+def _merge(iv):
+    out = []
+    for a, b in sorted(iv):
+        if out and a <= out[-1][1]:
+            out[-1] = (out[-1][0], max(out[-1][1], b))
+        else:
+            out.append((a, b))
+    return out

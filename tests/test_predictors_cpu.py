@@ -51,6 +51,21 @@ def test_lore_preprocess_matches_reference():
         np.testing.assert_allclose([x.astype(np.float64).sum(), np.abs(x.astype(np.float64)).sum()], g[f"sum{i}"], rtol=1e-12)
 
 
+def test_picodet_preprocess_matches_reference():
+    """cv2.resize on the un-flipped page, then flip + (x * scale - mean) / std in fp32 == OCRPicodetPreProcessor's image."""
+    import cv2
+
+    g = np.load(os.path.join(GOLDEN, "picodet_net_seed0.npz"))
+    page = synth.synthetic_page(9, 500, 380)
+    res = cv2.resize(page, (608, 800))
+    mean = np.array([0.485, 0.456, 0.406], np.float32).reshape(1, 1, 3)
+    std = np.array([0.229, 0.224, 0.225], np.float32).reshape(1, 1, 3)
+    x = ((res[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)
+    np.testing.assert_array_equal(x[:, 300:332, 200:232], g["pre_patch"])
+    np.testing.assert_allclose([x.astype(np.float64).sum(), np.abs(x.astype(np.float64)).sum()], g["pre_sum"], rtol=1e-12)
+    np.testing.assert_array_equal(g["pre_meta"], [500, 380, 800 / 500, 608 / 380, 800, 608])
+
+
 def test_error_behaviour_without_gpu():
     import torch
 
@@ -62,6 +77,8 @@ def test_error_behaviour_without_gpu():
         predictors.OcrTableStructureTask(model="CenterNet", state_dict=({}, {}))
     with pytest.raises(RuntimeError):
         predictors.OcrTableStructureTask(model="Lore", task_type="ptn", state_dict=({}, {}))
+    with pytest.raises(RuntimeError):
+        predictors.OcrLayoutTask(model="DocXLayout", state_dict=({}, {}, {}))
     with pytest.raises(TypeError):
         predictors._read_image(12345)
     if not torch.cuda.is_available():
