@@ -54,6 +54,7 @@ const char* dv_last_error(dv_handle h);
  *                "convnext_vit"  ConvNextViT text-line recogniser (reference model/convnext_vit/
  *                                modeling_convnext_vit.py:20-45)
  *                "lore_dla34"    Lore table-structure detector, DLA-34 + DCNv2 (reference model/lore/lore_dla_34.py:193)
+ *                "centernet_dla34" CenterNet table-structure detector (reference model/center_net/modeling_centernet.py:601)
  *                "picodet"       PicoDet layout detector as a graph program (reference model/picodet/{lcnet,csp_pan,pico_head}.py)
  *                "lore_processor" Lore logical-location transformers (reference model/lore/lore_processor.py:399)
  *   weight_blob: HOST pointer to a blob written by pdf_table_b200.weights.pack_* (may be NULL for "post")
@@ -207,6 +208,31 @@ int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t
  */
 int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
                             float* logic_out, float* stacked_out);
+
+/*
+ * CenterNet table-structure detector (model kind "centernet_dla34"): DLA-34 + plain IDA-up + heads hm / v2c / c2v / reg.
+ * Replaces OcrTableStructureTask._run_model for model="CenterNet" (ocr_table_structure_task.py:176-204) =
+ * DLASeg.forward (center_net/modeling_centernet.py:657-662).  Same calling convention as dv_lore_detect_forward; maps_out is
+ * the packed [n,height/4,width/4,24] fp32 map with channels hm0,hm1 (after sigmoid), reg0,reg1, c2v0-7, v2c0-7, 4 pad.
+ */
+int dv_centernet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out);
+int dv_centernet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                            const float* std3_host, int flip, float* maps_out);
+
+/*
+ * CenterNet decode: head maps -> table-cell polygons, on the device.
+ * Replaces OCRTableCenterNetPostProcessor.__call__ (center_net/processer_centernet.py:170-204): bbox_decode / gbox_decode
+ * (center_net/table_process.py:151-216: 3x3 max-pool NMS + top-K + gathers), bbox_post_process / gbox_post_process (:219-236),
+ * group_bbox_by_gbox (:278-333: cell corners snap to detected vertices), the score > threshold filter and the sort by
+ * 0.01 * mean_x + mean_y.  (table_process.nms :239-275 is a no-op in the reference: it receives the [1,K,10] batch array.)
+ *   hm, reg, c2v, v2c : layout 0 = four NCHW fp32 tensors [n,2|2|8|8,h,w]; layout 1 = the packed NHWC x24 map as `hm`
+ *   inv_affine_host   : HOST [n][6] doubles, get_affine_transform(c, s, 0, (out_w, out_h), inv=1) with the float meta
+ *   K, MK             : top-K cells / vertices (reference 1000 / 4000); score_threshold 0.3
+ *   polygons [n][K][8] fp32 (device), rows in the reference's final order; counts [n] int32
+ */
+int dv_centernet_decode(dv_handle h, const float* hm, const float* reg, const float* c2v, const float* v2c, int layout, int n, int height,
+                        int width, const double* inv_affine_host, int K, int MK, float score_threshold, float* polygons, int32_t* counts,
+                        int32_t* overflow_host);
 
 /*
  * PicoDet layout detector (model kind "picodet"): LCNet-x1.0 backbone + CSP-PAN neck + PicoHead, executed from the graph

@@ -52,6 +52,11 @@ SIGNATURES = {
     "dv_picodet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.c_float, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "dv_picodet_num_classes": (C.c_int, [C.c_void_p]),
+    "dv_centernet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dv_centernet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                          C.POINTER(C.c_float), C.c_int, C.c_void_p]),
+    "dv_centernet_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_double), C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "dv_convnextvit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_convnextvit_labels": (C.c_int, [C.c_void_p]),

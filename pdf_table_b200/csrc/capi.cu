@@ -147,7 +147,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = cnv_create(e);
         } else if (e->kind == "picodet") {
             rc = graph_create(e);
-        } else if (e->kind == "lore_dla34") {
+        } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34") {
             rc = lore_create(e);
         } else if (e->kind == "lore_processor") {
             rc = lore_proc_create(e);
@@ -234,7 +234,7 @@ double dv_model_flops(dv_handle h) {
     if (!h) return 0.0;
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
-    if (h->kind == "lore_dla34") return lore_flops(h);
+    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_flops(h);
     if (h->kind == "picodet") return graph_flops(h);
     return 0.0;
 }
@@ -258,7 +258,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
     if (!h || !name) return DV_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
-    if (h->kind == "lore_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
+    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if (h->kind == "picodet" && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
     return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
 }
@@ -314,6 +314,56 @@ int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* 
     }
     return lore_decode(h, m, n, height, width, inv_affine_host, K, MK, wiz_rev, vis_thresh, polygons, scores, dets_feat, ax_idx,
                        cr_idx, counts, rows, overflow_host);
+}
+
+static int make_lore_maps(dv_handle h, const float* hm, const float* reg, const float* wh, const float* st, int layout, int height, int width,
+                          LoreMaps* m) {
+    const long long hw = static_cast<long long>(height) * width;
+    if (layout == 0) {
+        m->hm = hm;
+        m->reg = reg;
+        m->wh = wh;
+        m->st = st;
+        const int ch[4] = {2, 2, 8, 8};
+        for (int i = 0; i < 4; ++i) {
+            m->img_stride[i] = ch[i] * hw;
+            m->chan_stride[i] = hw;
+            m->pix_stride[i] = 1;
+        }
+    } else if (layout == 1) {
+        if (!hm) return set_err(h, DV_ERR_ARG, "null packed map");
+        m->hm = hm;
+        m->reg = hm + 2;
+        m->wh = hm + 4;
+        m->st = hm + 12;
+        for (int i = 0; i < 4; ++i) {
+            m->img_stride[i] = 24 * hw;
+            m->chan_stride[i] = 1;
+            m->pix_stride[i] = 24;
+        }
+    } else {
+        return set_err(h, DV_ERR_ARG, "layout must be 0 (NCHW) or 1 (NHWC x24)");
+    }
+    return 0;
+}
+
+int dv_centernet_decode(dv_handle h, const float* hm, const float* reg, const float* c2v, const float* v2c, int layout, int n, int height,
+                        int width, const double* inv_affine_host, int K, int MK, float score_threshold, float* polygons, int32_t* counts,
+                        int32_t* overflow_host) {
+    if (!h) return DV_ERR_ARG;
+    cudaSetDevice(h->device);
+    LoreMaps m;
+    DV_TRY(make_lore_maps(h, hm, reg, c2v, v2c, layout, height, width, &m));
+    return centernet_decode(h, m, n, height, width, inv_affine_host, K, MK, score_threshold, polygons, counts, overflow_host);
+}
+
+int dv_centernet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out) {
+    return dv_lore_detect_forward(h, in_nchw_f32, n, height, width, maps_out);
+}
+
+int dv_centernet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
+                            const float* std3_host, int flip, float* maps_out) {
+    return dv_lore_detect_forward_u8(h, images_hwc_u8, n, height, width, mean3_host, std3_host, flip, maps_out);
 }
 
 int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, int channels, int height, int width, int K,

@@ -193,6 +193,8 @@ struct LoreMaps {
 int lore_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const double* trans_host, int K, int MK, int wiz_rev,
                 float vis_thresh, float* polygons, float* scores, int32_t* dets_feat, int32_t* ax_idx, int32_t* cr_idx,
                 int32_t* counts, int32_t* rows, int32_t* overflow_host);
+int centernet_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const double* trans_host, int K, int MK, float score_thr,
+                     float* polygons, int32_t* counts, int32_t* overflow_host);
 int lore_gather_logi(Engine* e, const float* ax, const float* cr, int N, int C, int H, int W, int K, const int32_t* counts,
                      const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat);
 

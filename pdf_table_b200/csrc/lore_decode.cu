@@ -343,6 +343,161 @@ k_lore_gather_logi(const float* __restrict__ ax, const float* __restrict__ cr, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CenterNet
+// OCRTableCenterNetPostProcessor (center_net/processer_centernet.py:170-204) after bbox_decode / gbox_decode (the peaks and
+// sort kernels above): inverse affine of cells (4 corners) and vertices (position + 4 predicted cell centres) to source
+// pixels, group_bbox_by_gbox (center_net/table_process.py:278-333), score > 0.3 filter, sort by 0.01 * mean_x + mean_y.
+__device__ __forceinline__ float affine_x(const double* t, float x, float y) {
+    return static_cast<float>(__dadd_rn(__dadd_rn(__dmul_rn(t[0], static_cast<double>(x)), __dmul_rn(t[1], static_cast<double>(y))), t[2]));
+}
+__device__ __forceinline__ float affine_y(const double* t, float x, float y) {
+    return static_cast<float>(__dadd_rn(__dadd_rn(__dmul_rn(t[3], static_cast<double>(x)), __dmul_rn(t[4], static_cast<double>(y))), t[5]));
+}
+
+__global__ void __launch_bounds__(256)
+k_cn_transform(int K, int MK, const int* __restrict__ cell_n, float* __restrict__ cell_box, const int* __restrict__ cor_n,
+               float* __restrict__ cor_xy, float* __restrict__ cor_box, const double* __restrict__ trans) {
+    const int n = blockIdx.y;
+    const double* t = trans + n * 6;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cell_n[n]) {
+        float* b = cell_box + (static_cast<size_t>(n) * K + i) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x = b[2 * k], y = b[2 * k + 1];
+            b[2 * k] = affine_x(t, x, y);
+            b[2 * k + 1] = affine_y(t, x, y);
+        }
+    }
+    if (i < cor_n[n]) {
+        float* xy = cor_xy + static_cast<size_t>(n) * 2 * MK;
+        float* cb = cor_box + static_cast<size_t>(n) * 8 * MK;
+        const float x = xy[i], y = xy[MK + i];
+        xy[i] = affine_x(t, x, y);
+        xy[MK + i] = affine_y(t, x, y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float cx = cb[static_cast<size_t>(2 * k) * MK + i], cy = cb[static_cast<size_t>(2 * k + 1) * MK + i];
+            cb[static_cast<size_t>(2 * k) * MK + i] = affine_x(t, cx, cy);
+            cb[static_cast<size_t>(2 * k + 1) * MK + i] = affine_y(t, cx, cy);
+        }
+    }
+}
+
+__device__ __forceinline__ float cross_f32(float ax, float ay, float bx, float by) {  // ax * by - ay * bx, numpy float32 steps
+    return __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+}
+
+// One warp per cell.  A corner j of cell k snaps to the FIRST (vertex, centre) pair in the reference's loop order whose
+// centre lies strictly inside the (original) cell, whose vertex is >= 2 px from that centre, for which j is the cell corner
+// nearest to the vertex, and that is closer than half the cell size.  (`sum(sign[k]) == 4: continue` never changes a result.)
+__global__ void __launch_bounds__(128)
+k_cn_group(int K, int MK, const int* __restrict__ cell_n, const float* __restrict__ cell_box, float* __restrict__ cell_rev,
+           const int* __restrict__ cor_n, const float* __restrict__ cor_xy, const float* __restrict__ cor_box) {
+    const int n = blockIdx.y, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= cell_n[n]) return;
+    const size_t o = static_cast<size_t>(n) * K + k;
+    float b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = cell_box[o * 8 + i];
+    const float w = __fmul_rn(__fadd_rn(fabsf(__fsub_rn(b[6], b[0])), fabsf(__fsub_rn(b[4], b[2]))), 0.5f);
+    const float h = __fmul_rn(__fadd_rn(fabsf(__fsub_rn(b[3], b[1])), fabsf(__fsub_rn(b[5], b[7]))), 0.5f);
+    const double lim = static_cast<double>(__fmul_rn(0.5f, fmaxf(w, h)));
+    const float* vxy = cor_xy + static_cast<size_t>(n) * 2 * MK;
+    const float* vb = cor_box + static_cast<size_t>(n) * 8 * MK;
+    const int nv = cor_n[n];
+    int best[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int v = lane; v < nv; v += 32) {
+        const float vx = vxy[v], vy = vxy[MK + v];
+        float dc[4];  // squared distances (float32 steps) from the vertex to the cell corners
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float dx = __fsub_rn(vx, b[2 * j]), dy = __fsub_rn(vy, b[2 * j + 1]);
+            dc[j] = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        }
+        int jm = 0;
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (dc[j] < dc[jm]) jm = j;
+        float dmin = dc[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (jm == j) dmin = dc[j];
+        if (!(sqrt(static_cast<double>(dmin)) < lim)) continue;
+        for (int i = 0; i < 4; ++i) {
+            const float cx = vb[static_cast<size_t>(2 * i) * MK + v], cy = vb[static_cast<size_t>(2 * i + 1) * MK + v];
+            const float dx = __fsub_rn(vx, cx), dy = __fsub_rn(vy, cy);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < 4.0f) continue;  // get_distance(vertex, centre) < 2
+            const float a0 = cross_f32(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]), __fsub_rn(cx, b[0]), __fsub_rn(cy, b[1]));
+            const float a1 = cross_f32(__fsub_rn(b[4], b[2]), __fsub_rn(b[5], b[3]), __fsub_rn(cx, b[2]), __fsub_rn(cy, b[3]));
+            const float a2 = cross_f32(__fsub_rn(b[6], b[4]), __fsub_rn(b[7], b[5]), __fsub_rn(cx, b[4]), __fsub_rn(cy, b[5]));
+            const float a3 = cross_f32(__fsub_rn(b[0], b[6]), __fsub_rn(b[1], b[7]), __fsub_rn(cx, b[6]), __fsub_rn(cy, b[7]));
+            const bool in = (a0 > 0 && a1 > 0 && a2 > 0 && a3 > 0) || (a0 < 0 && a1 < 0 && a2 < 0 && a3 < 0);
+            if (!in) continue;
+            const int key = v * 4 + i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (jm == j && key < best[j]) best[j] = key;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) best[j] = min(best[j], __shfl_xor_sync(0xffffffffu, best[j], off));
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float x = b[2 * j], y = b[2 * j + 1];
+            if (best[j] != 0x7fffffff) {
+                x = vxy[best[j] >> 2];
+                y = vxy[MK + (best[j] >> 2)];
+            }
+            cell_rev[o * 8 + 2 * j] = x;
+            cell_rev[o * 8 + 2 * j + 1] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_cn_finalize(int K, float score_thr, const int* __restrict__ cell_n, const float* __restrict__ cell_score, const float* __restrict__ cell_rev,
+              float* __restrict__ polygons, int32_t* __restrict__ counts) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ int s_cnt;
+    const int n = blockIdx.x;
+    const int cnt = cell_n[n];
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        unsigned long long key = 0ull;  // sorts last (descending sort of the inverted key)
+        if (i < cnt && cell_score[static_cast<size_t>(n) * K + i] > score_thr) {
+            const float* b = cell_rev + (static_cast<size_t>(n) * K + i) * 8;
+            // key = 0.01 * (sum(x) / 4) + sum(y) / 4 with Python's left-to-right float32 sums
+            const float sx = __fadd_rn(__fadd_rn(__fadd_rn(b[0], b[2]), b[4]), b[6]);
+            const float sy = __fadd_rn(__fadd_rn(__fadd_rn(b[1], b[3]), b[5]), b[7]);
+            const float kf = __fadd_rn(__fmul_rn(0.01f, __fmul_rn(sx, 0.25f)), __fmul_rn(sy, 0.25f));
+            unsigned u = __float_as_uint(kf);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map of float32 to unsigned
+            key = (static_cast<unsigned long long>(~u) << 32) | (0xffffffffu - static_cast<unsigned>(i));  // ascending key, then ascending i
+            atomicAdd(&s_cnt, 1);
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_desc(s_keys, n2);
+    const int keep = s_cnt;
+    for (int j = threadIdx.x; j < keep; j += blockDim.x) {
+        const int src = static_cast<int>(0xffffffffu - static_cast<unsigned>(s_keys[j] & 0xffffffffu));
+        const float4* b = reinterpret_cast<const float4*>(cell_rev + (static_cast<size_t>(n) * K + src) * 8);
+        float4* dst = reinterpret_cast<float4*>(polygons + (static_cast<size_t>(n) * K + j) * 8);
+        dst[0] = b[0];
+        dst[1] = b[1];
+    }
+    if (threadIdx.x == 0) counts[n] = keep;
+}
+
 int ensure_ws(Engine* e, LoreWs* ws, int N, int K, int MK) {
     if (ws->N >= N && ws->K == K && ws->MK == MK) return 0;
     for (void* p : ws->mem) cudaFree(p);
@@ -439,6 +594,54 @@ int lore_gather_logi(Engine* e, const float* ax, const float* cr, int N, int C, 
     k_lore_gather_logi<<<dim3(K, N), 256, 0, e->stream>>>(ax, cr, C, H * W, K, counts, ax_idx, cr_idx, logi_feat);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int centernet_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const double* trans_host, int K, int MK, float score_thr,
+                     float* polygons, int32_t* counts, int32_t* overflow_host) {
+    if (N == 0) return 0;
+    if (!maps.hm || !maps.reg || !maps.wh || !maps.st || !trans_host || !polygons || !counts || N < 0 || H <= 0 || W <= 0)
+        return set_err(e, DV_ERR_ARG, "centernet_decode: bad arguments");
+    if (K <= 0 || K > 4096 || MK <= 0 || MK > kCap) return set_err(e, DV_ERR_UNSUPPORTED, "centernet_decode: K in 1..4096, MK in 1..%d", kCap);
+    auto it = e->aux.find("lore_decode");
+    if (it == e->aux.end()) it = e->aux.emplace("lore_decode", std::unique_ptr<Model>(new LoreWs())).first;
+    LoreWs* ws = static_cast<LoreWs*>(it->second.get());
+    DV_TRY(ensure_ws(e, ws, N, K, MK));
+    static bool attr_done = false;
+    if (!attr_done) {
+        DV_CUDA(e, cudaFuncSetAttribute(k_lore_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8));
+        attr_done = true;
+    }
+    cudaStream_t s = e->stream;
+    DV_CUDA(e, cudaMemcpyAsync(ws->trans, trans_host, static_cast<size_t>(N) * 48, cudaMemcpyHostToDevice, s));
+    DV_CUDA(e, cudaMemsetAsync(ws->nkeys, 0, static_cast<size_t>(N) * 8, s));
+    DV_CUDA(e, cudaMemsetAsync(ws->overflow, 0, 4, s));
+    const MapView hm{maps.hm, maps.img_stride[0], maps.chan_stride[0], maps.pix_stride[0]};
+    const MapView reg{maps.reg, maps.img_stride[1], maps.chan_stride[1], maps.pix_stride[1]};
+    const MapView wh{maps.wh, maps.img_stride[2], maps.chan_stride[2], maps.pix_stride[2]};
+    const MapView st{maps.st, maps.img_stride[3], maps.chan_stride[3], maps.pix_stride[3]};
+    const double px = static_cast<double>(N) * H * W;
+    e->launch_begin("k_lore_peaks", "centernet_decode", 0.0, px * 2 * 4);
+    k_lore_peaks<<<dim3((H * W + 255) / 256, 2, N), 256, 0, s>>>(hm, H, W, score_thr, score_thr, ws->keys, ws->nkeys, ws->overflow);
+    e->launch_end();
+    e->launch_begin("k_lore_sort", "centernet_decode", 0.0, static_cast<double>(N) * (K + MK) * 20 * 4);
+    k_lore_sort<<<dim3(2, N), kSortThreads, kCap * 8, s>>>(reg, wh, st, W, K, MK, ws->keys, ws->nkeys, ws->cell_n, ws->cell_score, ws->cell_idx,
+                                                           ws->cell_box, ws->cell_rev, ws->cor_n, ws->cor_score, ws->cor_xy, ws->cor_box);
+    e->launch_end();
+    e->launch_begin("k_cn_transform", "centernet_decode", 0.0, static_cast<double>(N) * (K * 64.0 + MK * 80.0));
+    k_cn_transform<<<dim3((max(K, MK) + 255) / 256, N), 256, 0, s>>>(K, MK, ws->cell_n, ws->cell_box, ws->cor_n, ws->cor_xy, ws->cor_box, ws->trans);
+    e->launch_end();
+    e->launch_begin("k_cn_group", "centernet_decode", 0.0, static_cast<double>(N) * (K * 64.0 + MK * 40.0));
+    k_cn_group<<<dim3((K + 3) / 4, N), 128, 0, s>>>(K, MK, ws->cell_n, ws->cell_box, ws->cell_rev, ws->cor_n, ws->cor_xy, ws->cor_box);
+    e->launch_end();
+    e->launch_begin("k_cn_finalize", "centernet_decode", 0.0, static_cast<double>(N) * K * 72.0);
+    k_cn_finalize<<<N, kSortThreads, 4096 * 8, s>>>(K, score_thr, ws->cell_n, ws->cell_score, ws->cell_rev, polygons, counts);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    if (overflow_host) {
+        DV_CUDA(e, cudaMemcpyAsync(overflow_host, ws->overflow, 4, cudaMemcpyDeviceToHost, s));
+        DV_CUDA(e, cudaStreamSynchronize(s));
+    }
     return 0;
 }
 

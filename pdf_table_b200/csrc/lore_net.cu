@@ -26,6 +26,7 @@ int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out);
 int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer);
 int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer);
 int op_sigmoid_cols(Engine* e, float* maps, long long rows, int ld, int ncols);
+int op_copy_slice(Engine* e, const Tensor& in, const Tensor& out);
 int op_cell_offsets(Engine* e, const int32_t* counts, int N, int cap, int32_t* offsets, int32_t* totals, int32_t* overflow);
 int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int32_t* counts, const int32_t* offsets,
                        const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr);
@@ -37,7 +38,7 @@ constexpr int kCh[6] = {16, 32, 64, 128, 256, 512};
 constexpr int kLevels[6] = {1, 1, 1, 2, 2, 1};
 
 struct Step {
-    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID } kind;
+    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY } kind;
     ConvPlan plan;
     Tensor a, b, c;
     const float* wt = nullptr;
@@ -47,6 +48,7 @@ struct Step {
 
 struct LoreNet : Model {
     Engine* e = nullptr;
+    bool plain_up = false;  // CenterNet: DLAUp of plain IDAUp blocks (no DCN), heads hm / v2c / c2v / reg
     int N = 0, H = 0, W = 0;
     std::vector<void*> mem;
     std::vector<Step> steps;
@@ -280,6 +282,63 @@ int add_ida(LoreNet* m, const std::string& p, std::vector<Tensor>& layers, int s
     return 0;
 }
 
+// CenterNet IDAUp.forward (center_net/modeling_centernet.py:555-570): layers[k] = up_k(proj_k(layers[k])), then
+// x = node_k(cat[x, layers[k]]).  cat buffers: [x | up(proj(l_k))]; x of the first node is a copy of layers[0] (it is also
+// read by later IDAs and, for stride-2 convs, must stay dense), later x are written straight into the next cat by the node conv.
+int add_plain_ida(LoreNet* m, const std::string& p, std::vector<Tensor>& ls, int o, const int* up_f, std::vector<Tensor>* y) {
+    Engine* e = m->e;
+    const int n = static_cast<int>(ls.size());
+    const Tensor& l0 = ls[0];
+    std::vector<Tensor> cat(n);
+    for (int k = 1; k < n; ++k) DV_TRY(m->tensor(&cat[k], l0.N, l0.H, l0.W, 2 * o));
+    {
+        Step st;
+        st.kind = Step::COPY;
+        st.a = l0;
+        st.b = cat[1].slice(0, o);
+        m->steps.push_back(st);
+    }
+    for (int k = 1; k < n; ++k) {
+        Tensor t = ls[k];
+        const std::string pk = p + ".proj_" + std::to_string(k);
+        if (e->find(pk + ".w")) {
+            Tensor pr;
+            DV_TRY(m->tensor(&pr, t.N, t.H, t.W, o));
+            DV_TRY(add_conv(m, pk, t, o, 1, 1, epi(pr, ACT_RELU)));
+            t = pr;
+        } else if (t.C != o) {
+            return set_err(e, DV_ERR_WEIGHTS, "missing '%s'", pk.c_str());
+        }
+        const int f = up_f[k];
+        const BlobTensor* w = e->find(p + ".up_" + std::to_string(k) + ".w");
+        if (f == 1 || !w || w->dtype != 0 || w->nbytes != static_cast<uint64_t>(4 * f * f * o) * 4)
+            return set_err(e, DV_ERR_WEIGHTS, "missing / bad '%s.up_%d.w'", p.c_str(), k);
+        Step st;
+        st.kind = Step::UPADD;
+        st.a = t;
+        st.b = Tensor();  // no skip: plain up-sampling into the concatenation slice
+        st.c = cat[k].slice(o, o);
+        st.wt = reinterpret_cast<const float*>(w->dptr);
+        st.f = f;
+        st.name = p + ".up_" + std::to_string(k);
+        m->steps.push_back(st);
+    }
+    for (int k = 1; k < n; ++k) {
+        Tensor out;
+        DV_TRY(m->tensor(&out, l0.N, l0.H, l0.W, o));
+        DV_TRY(add_conv(m, p + ".node_" + std::to_string(k), cat[k], o, 3, 1, epi(out, ACT_RELU)));
+        if (k + 1 < n) {
+            Step st;
+            st.kind = Step::COPY;
+            st.a = out;
+            st.b = cat[k + 1].slice(0, o);
+            m->steps.push_back(st);
+        }
+        y->push_back(out);
+    }
+    return 0;
+}
+
 int build(Engine* e, LoreNet* m, int N, int H, int W) {
     if ((H % 32) || (W % 32)) return set_err(e, DV_ERR_ARG, "lore: H and W must be multiples of 32 (got %dx%d)", H, W);
     for (void* p : m->mem) cudaFree(p);
@@ -294,13 +353,15 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
     DV_TRY(m->tensor(&m->stem_in, N, H + 6, W + 8, 8, /*zero=*/true));
     // DCN scratch: the largest sampling matrix is 9*64 channels at stride 4 (or 9*128 at stride 8: same size)
     m->om_rows = static_cast<size_t>(N) * (H / 4) * (W / 4);
-    m->col_elems = m->om_rows * 9 * 64;
+    m->col_elems = m->plain_up ? 0 : m->om_rows * 9 * 64;
     {
         void* p = nullptr;
-        DV_TRY(m->alloc(m->mem, &p, m->om_rows * 32 * sizeof(float)));
-        m->om = reinterpret_cast<float*>(p);
-        DV_TRY(m->alloc(m->mem, &p, m->col_elems * sizeof(__half)));
-        m->col = reinterpret_cast<__half*>(p);
+        if (!m->plain_up) {
+            DV_TRY(m->alloc(m->mem, &p, m->om_rows * 32 * sizeof(float)));
+            m->om = reinterpret_cast<float*>(p);
+            DV_TRY(m->alloc(m->mem, &p, m->col_elems * sizeof(__half)));
+            m->col = reinterpret_cast<__half*>(p);
+        }
         DV_TRY(m->alloc(m->mem, &p, m->om_rows * 24 * sizeof(float)));
         m->maps = reinterpret_cast<float*>(p);
     }
@@ -319,9 +380,21 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         DV_TRY(add_level(m, lvl, x, &layers[lvl - 2]));
         x = layers[lvl - 2];
     }
+    if (m->plain_up) {
+        // CenterNet DLAUp.forward (center_net/modeling_centernet.py:589-597): ida_i over layers[-i-2:], layers[-i-1:] = y
+        const int up2[4] = {1, 2, 2, 2};
+        const int outs[3] = {256, 128, 64};
+        for (int i = 0; i < 3; ++i) {
+            std::vector<Tensor> ls(layers.end() - i - 2, layers.end());
+            std::vector<Tensor> y;
+            DV_TRY(add_plain_ida(m, "dla_up.ida_" + std::to_string(i), ls, outs[i], up2, &y));
+            for (size_t k = 0; k < y.size(); ++k) layers[layers.size() - y.size() + k] = y[k];
+            m->feat = y.back();
+        }
+    }
     // DLAUp.forward (lore_dla_34.py:130-137): channels [64,128,256,512], scales [1,2,4,8]
     std::vector<Tensor> out(1, layers[3]);
-    {
+    if (!m->plain_up) {
         const int up2[4] = {1, 2, 2, 2};
         DV_TRY(add_ida(m, "dla_up.ida_0", layers, 2, 4, 256, up2));
         out.insert(out.begin(), layers[3]);
@@ -331,12 +404,12 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         out.insert(out.begin(), layers[3]);
     }
     // DLASeg.forward (:176-189): y = out[0:3]; ida_up(y, 0, 3) with up factors [1,2,4]
-    std::vector<Tensor> y(out.begin(), out.begin() + 3);
-    {
+    if (!m->plain_up) {
+        std::vector<Tensor> y(out.begin(), out.begin() + 3);
         const int upf[3] = {1, 2, 4};
         DV_TRY(add_ida(m, "ida_up", y, 0, 3, 64, upf));
+        m->feat = y[2];
     }
-    m->feat = y[2];
     m->named["feat"] = m->feat;
     // small heads
     Tensor hid;
@@ -424,6 +497,7 @@ int build_feat(Engine* e, LoreNet* m, int K, int cap) {
 int lore_create(Engine* e) {
     LoreNet* m = new LoreNet();
     m->e = e;
+    m->plain_up = e->kind == "centernet_dla34";
     e->model.reset(m);
     return 0;
 }
@@ -453,7 +527,7 @@ int lore_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4) 
 int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, int flip, int N,
                         int H, int W, float* maps_out) {
     LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
-    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_dla34 model");
+    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_dla34 / centernet_dla34 model");
     if (N <= 0 || H <= 0 || W <= 0) return set_err(e, DV_ERR_ARG, "lore_detect_forward: bad arguments");
     if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
     if (!in_nchw && !in_u8) return set_err(e, DV_ERR_ARG, "lore_detect_forward: no input");
@@ -469,6 +543,7 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
             case Step::IM2COL: DV_TRY(op_dcn_im2col(e, st.a, m->om, m->col, st.name.c_str())); break;
             case Step::UPADD: DV_TRY(op_up_dw_add(e, st.a, st.wt, st.f, st.b, st.c, st.name.c_str())); break;
             case Step::SIGMOID: DV_TRY(op_sigmoid_cols(e, maps, static_cast<long long>(N) * (H / 4) * (W / 4), 24, 2)); break;
+            case Step::COPY: DV_TRY(op_copy_slice(e, st.a, st.b)); break;
         }
     }
     return 0;

@@ -199,7 +199,7 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
     const int oy = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
     float acc[8];
-    {
+    if (skip != nullptr) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(skip + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * lds + c8 * 8));
         const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -208,6 +208,9 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
             acc[2 * i] = v.x;
             acc[2 * i + 1] = v.y;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     }
     const int iy1 = (oy + pad) / f, ix1 = (ox + pad) / f;
     for (int a = 0; a < 2; ++a) {
@@ -238,14 +241,36 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
 }
 
+// skip.p == nullptr: plain up-sampling (CenterNet's IDAUp concatenates instead of adding)
 int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer) {
-    if ((in.C % 8) || skip.C != in.C || out.C != in.C || skip.H != in.H * f || skip.W != in.W * f || out.H != skip.H ||
-        out.W != skip.W || (f != 2 && f != 4 && f != 8))
+    if ((in.C % 8) || out.C != in.C || out.H != in.H * f || out.W != in.W * f || (f != 2 && f != 4 && f != 8) ||
+        (skip.p != nullptr && (skip.C != in.C || skip.H != out.H || skip.W != out.W)))
         return set_err(e, DV_ERR_UNSUPPORTED, "up_dw_add: bad shapes");
     const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
     e->launch_begin("k_up_dw_add", layer, 8.0 * (double)out.elems(), 2.0 * ((double)in.elems() + 2.0 * (double)out.elems()));
-    k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.ldc(), out.p,
+    k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.p ? skip.ldc() : 0, out.p,
                                                            out.ldc());
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- slice copy
+__global__ void __launch_bounds__(256)
+k_copy_slice(const __half* __restrict__ in, long long pixels, int C, int ldi, __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= pixels * cv) return;
+    const long long px = idx / cv;
+    const int c8 = static_cast<int>(idx % cv);
+    *reinterpret_cast<uint4*>(out + px * ldo + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(in + px * ldi + c8 * 8));
+}
+
+int op_copy_slice(Engine* e, const Tensor& in, const Tensor& out) {
+    if ((in.C % 8) || out.C != in.C || out.H != in.H || out.W != in.W || out.N != in.N) return set_err(e, DV_ERR_UNSUPPORTED, "copy_slice: bad shapes");
+    const long long pixels = static_cast<long long>(in.N) * in.H * in.W;
+    e->launch_begin("k_copy_slice", "concat", 0.0, pixels * in.C * 4.0);
+    k_copy_slice<<<grid_for(pixels * (in.C / 8), 256), 256, 0, e->stream>>>(in.p, pixels, in.C, in.ldc(), out.p, out.ldc());
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -246,6 +246,25 @@ class Engine:
                                                 _ptr(stacked)), self._h, "dv_lore_process_forward")
         return logic, stacked
 
+    def centernet_decode(self, hm: torch.Tensor, reg, c2v, v2c, inv_affine, K: int = 1000, MK: int = 4000, score_threshold: float = 0.3):
+        """CenterNet head maps (four NCHW tensors, or one packed NHWC [N,H,W,24] tensor as `hm` with the others None) ->
+        (polygons fp32 [N,K,8] in source pixels, counts int32 [N])."""
+        hm = _require_cuda(hm, torch.float32, "hm")
+        if reg is None:
+            n, h, w, c = hm.shape
+            layout = 1
+        else:
+            reg, c2v, v2c = (_require_cuda(t, torch.float32, nm) for t, nm in ((reg, "reg"), (c2v, "c2v"), (v2c, "v2c")))
+            n, c, h, w = hm.shape
+            layout = 0
+        tr = np.ascontiguousarray(np.asarray(inv_affine, np.float64).reshape(n, 6))
+        polygons = torch.empty((n, K, 8), dtype=torch.float32, device=hm.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=hm.device)
+        check(self._lib.dv_centernet_decode(self._h, _ptr(hm), _ptr(reg), _ptr(c2v), _ptr(v2c), layout, n, h, w,
+                                            tr.ctypes.data_as(C.POINTER(C.c_double)), int(K), int(MK), float(score_threshold), _ptr(polygons),
+                                            _ptr(counts), None), self._h, "dv_centernet_decode")
+        return polygons, counts
+
     def lore_decode(self, hm: torch.Tensor, reg: Optional[torch.Tensor], wh: Optional[torch.Tensor], st: Optional[torch.Tensor],
                     inv_affine, K: int = 3000, MK: int = 5000, wiz_rev: bool = True, vis_thresh: float = 0.2,
                     check_overflow: bool = False):

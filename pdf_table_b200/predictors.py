@@ -280,7 +280,8 @@ def lore_preprocess(img: np.ndarray, resolution=(1024, 1024)):
 
 class OcrTableStructureTask(BaseInferTask):
     """OcrTableStructureTask (ocr_pdf/ocr_table_structure_task.py:50-271) for model="Lore", task_type="wtw"
-    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers).
+    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers) and model="CenterNet"
+    (DLA-34 + plain IDA-up, vertex grouping; returns list[dict{polygons [n,8]}] like OCRTableCenterNetPostProcessor).
     Returns list[dict{polygons [n,8] float32 source pixels, logi [n,4] integer-valued, inputs}] like the reference's
     TableLorePostProcessor (lore/processer_lore.py:163-188).  `state_dict` = (detector, processor) state_dicts or paths
     (the reference's model_best.pth / processor_best.pth, lore/modeling_lore.py:88-101)."""
@@ -289,27 +290,32 @@ class OcrTableStructureTask(BaseInferTask):
 
     def __init__(self, task: str = "ocr_table_structure", model: str = "Lore", task_type: str = "wtw", state_dict=None,
                  table_structure_merge: bool = False, max_cells_per_image: int = 1024, **kwargs):
-        if model != "Lore":
+        if model not in ("Lore", "CenterNet"):
             raise RuntimeError(f"model {model} not support")
-        if task_type != "wtw":
+        if model == "Lore" and task_type != "wtw":
             raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements the DLA-34 'wtw' configuration)")
-        if state_dict is None or len(state_dict) != 2:
-            raise RuntimeError("OcrTableStructureTask(predictor_type='b200') needs state_dict=(detector, processor)")
+        if model == "Lore" and (state_dict is None or len(state_dict) != 2):
+            raise RuntimeError("OcrTableStructureTask(model='Lore', predictor_type='b200') needs state_dict=(detector, processor)")
+        if model == "CenterNet" and state_dict is None:
+            raise RuntimeError("OcrTableStructureTask(model='CenterNet', predictor_type='b200') needs state_dict= (a DLASeg state_dict or a path)")
         self.task_type, self.table_structure_merge = task_type, table_structure_merge
         self.resolution, self.vis_thresh, self.wiz_rev = (1024, 1024), 0.2, True  # LoreConfig wtw (configuration_lore.py:86-100)
         self.max_cells_per_image = max_cells_per_image
-        self._sd = (_load_state_dict(state_dict[0]), _load_state_dict(state_dict[1]))
+        self._sd = (_load_state_dict(state_dict[0]), _load_state_dict(state_dict[1])) if model == "Lore" else _load_state_dict(state_dict)
         super().__init__(task=task, model=model, **kwargs)
 
     def _construct_model(self, model):
-        self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0]), device=self.device)
-        self.processor = Engine("lore_processor", weights.pack_lore_processor(self._sd[1]), device=self.device)
         self.post = Engine("post", device=self.device)
+        if model == "CenterNet":
+            self.predictor = Engine("centernet_dla34", weights.pack_centernet_dla34(self._sd), device=self.device)
+        else:
+            self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0]), device=self.device)
+            self.processor = Engine("lore_processor", weights.pack_lore_processor(self._sd[1]), device=self.device)
         self._sd = None
 
     def _preprocess(self, inputs, **kwargs) -> Dict[str, Any]:
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
-        images, metas = [], []
+        images, metas, cs = [], [], []
         for it in items:
             img = _read_image(it)
             if img.ndim == 2:
@@ -319,9 +325,24 @@ class OcrTableStructureTask(BaseInferTask):
             warped, meta = lore_preprocess(img, self.resolution)
             images.append(warped)
             metas.append(meta)
-        return {"images": np.stack(images), "meta": np.stack(metas), "inputs": list(items)}
+            h, w = img.shape[:2]
+            cs.append((np.array([w / 2.0, h / 2.0], dtype=np.float32), max(h, w) * 1.0))
+        return {"images": np.stack(images), "meta": np.stack(metas), "cs": cs, "inputs": list(items)}
+
+    def _run_centernet(self, inputs):
+        """OCRTableCenterNetPreProcessor keeps the float centre / scale in its meta (center_net/processer_centernet.py:108-139);
+        the pixels are the same warp as Lore's."""
+        dev = torch.device("cuda", self.device)
+        inv = np.stack([lore_affine(c, s, self.resolution[1] // 4, self.resolution[0] // 4, inv=True) for c, s in inputs["cs"]])
+        maps = self.predictor.lore_detect_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True))
+        polygons, counts = self.post.centernet_decode(maps, None, None, None, inv)
+        polygons, counts = polygons.cpu().numpy(), counts.cpu().numpy()
+        inputs["results"] = [{"polygons": polygons[i, : counts[i]].copy()} for i in range(len(counts))]
+        return inputs
 
     def _run_model(self, inputs, **kwargs):
+        if self.model == "CenterNet":
+            return self._run_centernet(inputs)
         dev = torch.device("cuda", self.device)
         n = len(inputs["images"])
         metas = inputs["meta"]
@@ -339,6 +360,8 @@ class OcrTableStructureTask(BaseInferTask):
         return inputs
 
     def _postprocess(self, inputs, **kwargs) -> List[Dict[str, Any]]:
+        if self.model == "CenterNet":  # {"polygons": np.array(box_list), ...inputs} (processer_centernet.py:198-203)
+            return [{"polygons": res["polygons"], "inputs": item} for item, res in zip(inputs["inputs"], inputs["results"])]
         out = []
         for item, res in zip(inputs["inputs"], inputs["results"]):
             boxes, logi = res["pred_boxes"], res["logits"]

@@ -572,3 +572,52 @@ def picodet_state_dicts(seed: int = 0, num_classes: int = 5):
         bias[:num_classes] -= 2.0  # class prior: most anchors are background
         hd[f"head_cls{lvl}.bias"] = bias
     return bb, nk, hd
+
+
+# --------------------------------------------------------------------------- CenterNet table structure (DLA-34, plain IDA-up)
+CENTERNET_HEADS = (("hm", 2), ("v2c", 8), ("c2v", 8), ("reg", 2))
+
+
+def centernet_dla34_state_dict(seed: int = 0, perturb_up: bool = True) -> "OrderedDict[str, np.ndarray]":
+    """Keys / shapes of the reference CenterNet `DLASeg()` (center_net/modeling_centernet.py:601-668: dla34 base, DLAUp of
+    plain IDAUp blocks :508-599 with node_kernel 3, heads hm 2 / v2c 8 / c2v 8 / reg 2 with head_conv 256)."""
+    rng = np.random.Generator(np.random.PCG64(5000 + seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    ch = DLA_CHANNELS
+    sd["base.base_layer.0.weight"] = _conv(rng, ch[0], 3, 7, 7)
+    _bn(rng, sd, "base.base_layer.1", ch[0])
+    sd["base.level0.0.weight"] = _conv(rng, ch[0], ch[0], 3, 3)
+    _bn(rng, sd, "base.level0.1", ch[0])
+    sd["base.level1.0.weight"] = _conv(rng, ch[1], ch[0], 3, 3)
+    _bn(rng, sd, "base.level1.1", ch[1])
+    _dla_tree(rng, sd, "base.level2", DLA_LEVELS[2], ch[1], ch[2], 2, level_root=False)
+    _dla_tree(rng, sd, "base.level3", DLA_LEVELS[3], ch[2], ch[3], 2, level_root=True)
+    _dla_tree(rng, sd, "base.level4", DLA_LEVELS[4], ch[3], ch[4], 2, level_root=True)
+    _dla_tree(rng, sd, "base.level5", DLA_LEVELS[5], ch[4], ch[5], 2, level_root=True)
+    channels = list(ch[2:])
+    in_channels = list(channels)
+    scales = np.array([1, 2, 4, 8], dtype=int)
+    for i in range(len(channels) - 1):
+        j = -i - 2
+        o, cin, up_f = channels[j], in_channels[j:], scales[j:] // scales[j]
+        p = f"dla_up.ida_{i}"
+        for k, c in enumerate(cin):
+            if c != o:
+                sd[f"{p}.proj_{k}.0.weight"] = _conv(rng, o, c, 1, 1, gain=0.5)
+                _bn(rng, sd, f"{p}.proj_{k}.1", o)
+            if int(up_f[k]) != 1:
+                w = _bilinear_up(o, int(up_f[k]))
+                if perturb_up:
+                    w = (w * rng.uniform(0.8, 1.2, w.shape)).astype(np.float32)
+                sd[f"{p}.up_{k}.weight"] = w
+        for k in range(1, len(cin)):
+            sd[f"{p}.node_{k}.0.weight"] = _conv(rng, o, 2 * o, 3, 3, gain=0.5)  # keeps the un-normalised synthetic activations O(1)
+            _bn(rng, sd, f"{p}.node_{k}.1", o)
+        scales[j + 1:] = scales[j]
+        in_channels[j + 1:] = [channels[j] for _ in channels[j + 1:]]
+    for head, classes in CENTERNET_HEADS:
+        sd[f"{head}.0.weight"] = _conv(rng, 256, ch[2], 3, 3, gain=0.5)
+        sd[f"{head}.0.bias"] = _b(rng, 256)
+        sd[f"{head}.2.weight"] = _conv(rng, classes, 256, 1, 1, gain=1.0)
+        sd[f"{head}.2.bias"] = _b(rng, classes) if head != "hm" else np.full(classes, -2.19, np.float32)
+    return sd

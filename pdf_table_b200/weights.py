@@ -341,3 +341,44 @@ def pack_lore_processor(sd: Mapping[str, "np.ndarray"]) -> bytes:
     t["x_pos"], t["y_pos"] = f("x_position_embeddings.weight"), f("y_position_embeddings.weight")
     t["meta"] = np.array([n_axis, n_stack, 256, 8], np.int32)
     return write_blob(t)
+
+
+# --------------------------------------------------------------------------- CenterNet (DLA-34, plain IDA-up)
+def pack_centernet_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference CenterNet `DLASeg()` (center_net/modeling_centernet.py:601-668) -> engine blob.  The base
+    uses the Lore packing; IDAUp proj / node convs are folded with their BatchNorm; the four heads share one 3x3 conv and one
+    block-diagonal 1x1 whose 24 output channels are ordered hm, reg, c2v, v2c (the packed map dv_centernet_decode reads)."""
+    t: Dict[str, np.ndarray] = {}
+    f = lambda k: _np(sd[k]).astype(np.float32)
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1")))
+    put("level0", pack_conv(sd["base.level0.0.weight"], None, _bn(sd, "base.level0.1")))
+    put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
+    for k in sd:
+        if k.startswith("base.level") and not k.startswith(("base.level0", "base.level1")):
+            if k.endswith(".conv1.weight") or k.endswith(".conv2.weight"):
+                p, n = k[: -len(".weight")].rsplit(".", 1)
+                put(k[5: -len(".weight")], pack_conv(sd[k], None, _bn(sd, f"{p}.bn{n[-1]}")))
+            elif k.endswith(".root.conv.weight"):
+                put(k[5: -len(".conv.weight")], pack_conv(sd[k], None, _bn(sd, k[: -len(".conv.weight")] + ".bn")))
+            elif k.endswith(".project.0.weight"):
+                put(k[5: -len(".0.weight")], pack_conv(sd[k], None, _bn(sd, k[: -len(".0.weight")] + ".1")))
+        elif k.startswith("dla_up.") and k.endswith(".0.weight"):  # proj_k / node_k: conv + BN + ReLU
+            p = k[: -len(".0.weight")]
+            put(p, pack_conv(sd[k], None, _bn(sd, p + ".1")))
+        elif k.startswith("dla_up.") and ".up_" in k and k.endswith(".weight"):
+            t[k[: -len(".weight")] + ".w"] = np.ascontiguousarray(f(k)[:, 0].transpose(1, 2, 0))
+    order = (("hm", 2), ("reg", 2), ("c2v", 8), ("v2c", 8))
+    put("heads.conv", pack_conv(np.concatenate([f(f"{h}.0.weight") for h, _ in order], 0), np.concatenate([f(f"{h}.0.bias") for h, _ in order], 0)))
+    w1 = np.zeros((24, 1024, 1, 1), np.float32)
+    b1 = np.zeros(24, np.float32)
+    row = 0
+    for i, (h, c) in enumerate(order):
+        w1[row: row + c, 256 * i: 256 * (i + 1)] = f(f"{h}.2.weight")
+        b1[row: row + c] = f(f"{h}.2.bias")
+        row += c
+    put("heads.out", pack_conv(w1, b1))
+    return write_blob(t)

@@ -151,3 +151,17 @@ def _merge(iv):
         else:
             out.append((a, b))
     return out
+
+
+def test_centernet_oracle_matches_reference_golden():
+    from oracle import centernet_ref
+
+    g = np.load(os.path.join(GOLDEN, "centernet_dla34_seed0.npz"))
+    out = centernet_ref.centernet_dla34_forward(synth.centernet_dla34_state_dict(0), torch.from_numpy(g["x"]))
+    for k in ("hm", "v2c", "c2v", "reg"):
+        np.testing.assert_allclose(out[k].numpy(), g[k], atol=2e-5 * max(1.0, float(np.abs(g[k]).max())), rtol=0, err_msg=k)
+    d = np.load(os.path.join(GOLDEN, "centernet_decode.npz"))
+    for name, idx, h, w, (sh, sw) in [("c0", 20, 128, 128, (600, 800)), ("c1", 21, 128, 160, (1024, 1280)), ("c2", 22, 256, 256, (1500, 1100))]:
+        m = synth.lore_planted_maps(idx, h, w, with_feat=False)
+        got = centernet_ref.centernet_decode(m["hm"], m["reg"], m["wh"], m["st"], [sw / 2.0, sh / 2.0], max(sh, sw) * 1.0, h, w)
+        np.testing.assert_array_equal(got, d[name], err_msg=name)
