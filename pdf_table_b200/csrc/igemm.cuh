@@ -23,6 +23,8 @@ namespace dv {
 
 static constexpr int kIGemmThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
 static constexpr int kMaxKB = 160;  // k-blocks per tile whose coordinate deltas are staged in smem
+static constexpr int kMaxStages = 32;  // TMA -> MMA ring depth.  Small-K layers (BK 16 / 32: 5-16 KB stages) are latency-bound on
+                                       // bytes in flight: with the former cap of 8 a Cin=16 conv kept 40 KB per SM in flight
 static constexpr int kBiasSmem = 2048;  // bias values staged in smem (layers with more padded columns read global)
 
 template <int ACT>
@@ -81,8 +83,8 @@ template <int ACT, bool OUT_F32, bool RES_F32, bool ARGMAX>
 __global__ void __launch_bounds__(kIGemmThreads, 1)
 conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8];
-    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ __align__(8) uint64_t hfull_bar[4];

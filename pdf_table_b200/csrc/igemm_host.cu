@@ -104,7 +104,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
             hs = 2;
             stages = static_cast<int>((206 * 1024 - hs * halo_bytes) / b_bytes);
         }
-        if (stages > 8) stages = 8;
+        if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
         p.halo_stages = hs;
         p.num_stages = stages;
@@ -112,7 +112,7 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     } else {
         const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
         int stages = static_cast<int>((206 * 1024) / stage_bytes);
-        if (stages > 8) stages = 8;
+        if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
         p.num_stages = stages;
         plan->smem = stages * stage_bytes + 1024;
