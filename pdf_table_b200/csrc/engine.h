@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "igemm_params.h"
+#include "win_conv_params.h"
 
 namespace dv {
 
@@ -154,6 +155,17 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
                 ConvPlan* plan, const char* name, int lda = 0);
 int launch_conv(Engine* e, const ConvPlan& plan);
+// conv_win_tcgen05 (win_conv.cuh): small-channel window convolution with a load/store producer
+struct WinConvPlan {
+    WinConvParams prm;
+    int grid = 0;
+    size_t smem = 0;
+    double flops = 0, bytes = 0;
+    std::string name;
+};
+int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho, int Wo, const __half* w, const float* bias, int Cout,
+                  int act, const Tensor& out_padded, int opad, WinConvPlan* plan, const char* name);
+int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops = 0);
 
 // ops.cu (simple HBM-bound kernels)
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);

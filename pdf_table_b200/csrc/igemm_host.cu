@@ -9,6 +9,7 @@
 
 #include "engine.h"
 #include "igemm.cuh"
+#include "win_conv.cuh"
 
 namespace dv {
 
@@ -386,6 +387,80 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
     cudaError_t st = cudaGetLastError();
     if (st != cudaSuccess)
         return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ conv_win_tcgen05
+int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho, int Wo, const __half* w, const float* bias, int Cout,
+                  int act, const Tensor& out_padded, int opad, WinConvPlan* plan, const char* name) {
+    WinConvParams& p = plan->prm;
+    memset(&p, 0, sizeof(p));
+    const int cpp = in_padded.C;
+    if ((cpp != 8 && cpp != 16) || in_padded.ld != 0 || (stride != 1 && stride != 2) || KR < 1 || KR > 7)
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: window conv needs a dense 8 / 16 channel padded input, stride 1 / 2, <= 7 filter rows", name);
+    const int wpx = 64 / cpp;  // pixels per 128-byte window
+    if (in_padded.W < stride * (Wo - 1) + wpx || in_padded.H < stride * (Ho - 1) + KR)
+        return set_err(e, DV_ERR_ARG, "%s: padded input too small (%dx%d for %dx%d outputs)", name, in_padded.H, in_padded.W, Ho, Wo);
+    if (Cout % 8 || Cout > 64 || (act != ACT_NONE && act != ACT_RELU)) return set_err(e, DV_ERR_UNSUPPORTED, "%s: window conv needs Cout %% 8 == 0, <= 64, ReLU / none", name);
+    if (out_padded.C != Cout || out_padded.H < Ho + 2 * opad || out_padded.W < Wo + opad || out_padded.N != in_padded.N)
+        return set_err(e, DV_ERR_ARG, "%s: bad output tensor", name);
+    p.in = in_padded.p;
+    p.Hp = in_padded.H;
+    p.Wp = in_padded.W;
+    p.cpp = cpp;
+    p.stride = stride;
+    p.KR = KR;
+    p.Nimg = in_padded.N;
+    p.Ho = Ho;
+    p.Wo = Wo;
+    choose_patch(Ho, Wo, &p.TH, &p.TW);
+    p.tiles_y = (Ho + p.TH - 1) / p.TH;
+    p.tiles_x = (Wo + p.TW - 1) / p.TW;
+    p.m_tiles = p.Nimg * p.tiles_x * p.tiles_y;
+    p.BLOCK_N = Cout <= 16 ? 16 : Cout <= 32 ? 32 : 64;
+    p.Cout = Cout;
+    p.act = act;
+    p.bias = bias;
+    p.out = out_padded.p;
+    p.oHp = out_padded.H;
+    p.oWp = out_padded.W;
+    p.opad = opad;
+    p.out_ld = out_padded.ldc();
+    const size_t b_bytes = static_cast<size_t>(p.BLOCK_N) * 128;
+    int stages = static_cast<int>((200 * 1024 - KR * b_bytes) / (128 * 128));
+    if (stages > 12) stages = 12;
+    if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: no room for the A ring", name);
+    p.num_stages = stages;
+    plan->smem = KR * b_bytes + static_cast<size_t>(stages) * 128 * 128 + 1024;
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(KR) * 64, static_cast<uint64_t>(Cout)};
+        uint64_t str[1] = {static_cast<uint64_t>(KR) * 64 * 2};
+        uint32_t box[2] = {64, static_cast<uint32_t>(p.BLOCK_N)};
+        DV_TRY(encode_map(e, &p.tmB, w, 2, dims, str, box, 128, name));
+    }
+    plan->grid = p.m_tiles < e->num_sms ? p.m_tiles : e->num_sms;
+    plan->name = name;
+    const double px = static_cast<double>(p.Nimg) * Ho * Wo;
+    plan->flops = 2.0 * px * KR * 64 * Cout;  // as issued (window padding included)
+    plan->bytes = 2.0 * static_cast<double>(in_padded.elems()) + 2.0 * px * Cout + 2.0 * KR * 64 * Cout;
+    return 0;
+}
+
+int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops) {
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] {
+        attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_win_tcgen05<ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+        if (attr_rc == cudaSuccess)
+            attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_win_tcgen05<ACT_NONE>), cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    });
+    if (attr_rc != cudaSuccess) return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_win_tcgen05): %s", cudaGetErrorString(attr_rc));
+    e->launch_begin("conv_win_tcgen05", plan.name, algorithmic_flops > 0 ? algorithmic_flops : plan.flops, plan.bytes);
+    if (plan.prm.act == ACT_RELU) conv_win_tcgen05<ACT_RELU><<<plan.grid, kWinThreads, plan.smem, e->stream>>>(plan.prm);
+    else conv_win_tcgen05<ACT_NONE><<<plan.grid, kWinThreads, plan.smem, e->stream>>>(plan.prm);
+    e->launch_end();
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
     return 0;
 }
 

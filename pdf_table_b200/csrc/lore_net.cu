@@ -16,6 +16,8 @@
 //  * The two wide heads (ax, cr: 256 channels each, 56 of the network's 338 GFLOP per image, 134 MB of fp32 maps)
 //    are never evaluated densely: the reference only ever gathers them at the selected cells' centres / corners, so
 //    lore_cell_features() builds the 3x3 patches at those points and runs the two head GEMMs on (5 x cells) rows.
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace dv {
@@ -38,8 +40,10 @@ constexpr int kCh[6] = {16, 32, 64, 128, 256, 512};
 constexpr int kLevels[6] = {1, 1, 1, 2, 2, 1};
 
 struct Step {
-    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY } kind;
+    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY, WINCONV } kind;
     ConvPlan plan;
+    WinConvPlan win;
+    double win_flops = 0;
     Tensor a, b, c;
     const float* wt = nullptr;
     int f = 0;
@@ -366,11 +370,34 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         m->maps = reinterpret_cast<float*>(p);
     }
     Tensor b0, l0, l1;
-    DV_TRY(m->tensor(&b0, N, H, W, 16));
     DV_TRY(m->tensor(&l0, N, H, W, 16));
     DV_TRY(m->tensor(&l1, N, H / 2, W / 2, 32));
-    DV_TRY(add_conv(m, "base", m->stem_in, 16, 7, 1, epi(b0, ACT_RELU), /*stem=*/true));
-    DV_TRY(add_conv(m, "level0", b0, 16, 3, 1, epi(l0, ACT_RELU)));
+    static const bool use_win = !(getenv("DV_WINCONV") && atoi(getenv("DV_WINCONV")) == 0);
+    if (use_win) {
+        // the two full-resolution 16-channel layers run on conv_win_tcgen05 (load/store producer, resident filter):
+        // base writes into a zero-bordered buffer (interior at +1,+1) so that level0 reads 4-pixel x 16-channel windows
+        DV_TRY(m->tensor(&b0, N, H + 2, W + 8, 16, /*zero=*/true));
+        const char* names[2] = {"base", "level0.win"};
+        for (int i = 0; i < 2; ++i) {
+            const BlobTensor* w = e->find(std::string(names[i]) + ".w");
+            const BlobTensor* b = e->find(std::string(names[i]) + ".b");
+            const uint32_t kcols = i == 0 ? 448 : 192;
+            if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->dims[0] != 16 || w->dims[1] != kcols)
+                return set_err(e, DV_ERR_WEIGHTS, "missing / bad '%s' (re-pack the weights with this version)", names[i]);
+            Step st;
+            st.kind = Step::WINCONV;
+            st.name = i == 0 ? "base" : "level0";
+            DV_TRY(plan_win_conv(e, i == 0 ? m->stem_in : b0, 1, i == 0 ? 7 : 3, H, W, reinterpret_cast<const __half*>(w->dptr),
+                                 reinterpret_cast<const float*>(b->dptr), 16, ACT_RELU, i == 0 ? b0 : l0, i == 0 ? 1 : 0, &st.win, st.name.c_str()));
+            st.win_flops = 2.0 * N * H * W * (i == 0 ? 147.0 : 144.0) * 16;
+            m->flops += st.win_flops;
+            m->steps.push_back(st);
+        }
+    } else {
+        DV_TRY(m->tensor(&b0, N, H, W, 16));
+        DV_TRY(add_conv(m, "base", m->stem_in, 16, 7, 1, epi(b0, ACT_RELU), /*stem=*/true));
+        DV_TRY(add_conv(m, "level0", b0, 16, 3, 1, epi(l0, ACT_RELU)));
+    }
     DV_TRY(add_conv(m, "level1", l0, 32, 3, 2, epi(l1, ACT_RELU)));
     m->named["level0"] = l0;
     m->named["level1"] = l1;
@@ -544,6 +571,7 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
             case Step::UPADD: DV_TRY(op_up_dw_add(e, st.a, st.wt, st.f, st.b, st.c, st.name.c_str())); break;
             case Step::SIGMOID: DV_TRY(op_sigmoid_cols(e, maps, static_cast<long long>(N) * (H / 4) * (W / 4), 24, 2)); break;
             case Step::COPY: DV_TRY(op_copy_slice(e, st.a, st.b)); break;
+            case Step::WINCONV: DV_TRY(launch_win_conv(e, st.win, st.win_flops)); break;
         }
     }
     return 0;

@@ -1,0 +1,20 @@
+// Parameter block of conv_win_tcgen05 (kernel in win_conv.cuh, planner in igemm_host.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace dv {
+
+struct WinConvParams {
+    CUtensorMap tmB;        // weights [Cout][KR*64] K-major, box {64, BLOCK_N}
+    const __half* in;       // zero-bordered image [N][Hp][Wp][cpp] (cpp = 8 or 16 channels per pixel)
+    int Hp, Wp, cpp, stride;
+    int KR;                 // filter rows = k-blocks (K = 64 each: 128 B / (2*cpp) pixels x cpp channels)
+    int Nimg, Ho, Wo, TH, TW, tiles_x, tiles_y, m_tiles;
+    int BLOCK_N, Cout, num_stages, act;
+    const float* bias;      // padded to a multiple of 256
+    __half* out;            // [N][oHp][oWp][out_ld], written at (+opad, +opad)
+    int oHp, oWp, opad, out_ld;
+};
+
+}  // namespace dv
