@@ -166,6 +166,7 @@ struct WinConvPlan {
 int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho, int Wo, const __half* w, const float* bias, int Cout,
                   int act, const Tensor& out_padded, int opad, WinConvPlan* plan, const char* name);
 int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops = 0);
+bool win_patch_enabled();
 
 // ops.cu (simple HBM-bound kernels)
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);

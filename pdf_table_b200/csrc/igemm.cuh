@@ -143,7 +143,9 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
 
     if (warp == 0) {
         // ===================== TMA producer (one thread) =====================
-        if (lane == 0) {
+        // elect_one_sync (not `lane == 0`): the compiler then knows exactly one thread runs the role and emits the uniform-
+        // datapath TMA / MMA instructions back to back instead of wrapping each in an ELECT / BRA.U.ANY loop
+        if (ptx::elect_one_sync()) {
             int stage = 0, hstage = 0;
             uint32_t phase = 0, hphase = 0;
             const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -201,7 +203,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (ptx::elect_one_sync()) {
             int stage = 0, hstage = 0;
             uint32_t phase = 0, hphase = 0;
             int acc = 0;

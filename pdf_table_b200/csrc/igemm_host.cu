@@ -391,6 +391,14 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
 }
 
 // ------------------------------------------------------------------------------------------------ conv_win_tcgen05
+// Patch mode (default for stride 1; DV_WINPATCH=0 selects the replicated-window mode): see win_conv_params.h.  Verified on
+// B200: an un-swizzled K-major descriptor with LBO = 16 B and 16-byte row pitch (overlapping core matrices) reads the
+// staged patch as the implicit im2col matrix.
+bool win_patch_enabled() {
+    static const bool on = !(getenv("DV_WINPATCH") && atoi(getenv("DV_WINPATCH")) == 0);
+    return on;
+}
+
 int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho, int Wo, const __half* w, const float* bias, int Cout,
                   int act, const Tensor& out_padded, int opad, WinConvPlan* plan, const char* name) {
     WinConvParams& p = plan->prm;
@@ -413,7 +421,15 @@ int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho
     p.Nimg = in_padded.N;
     p.Ho = Ho;
     p.Wo = Wo;
-    choose_patch(Ho, Wo, &p.TH, &p.TW);
+    p.patch = (win_patch_enabled() && stride == 1) ? 1 : 0;
+    if (p.patch) {
+        p.TH = 16;
+        p.TW = 8;
+        p.planes = cpp / 8;
+        p.PR = p.TH + KR - 1;
+    } else {
+        choose_patch(Ho, Wo, &p.TH, &p.TW);
+    }
     p.tiles_y = (Ho + p.TH - 1) / p.TH;
     p.tiles_x = (Wo + p.TW - 1) / p.TW;
     p.m_tiles = p.Nimg * p.tiles_x * p.tiles_y;
@@ -427,11 +443,12 @@ int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho
     p.opad = opad;
     p.out_ld = out_padded.ldc();
     const size_t b_bytes = static_cast<size_t>(p.BLOCK_N) * 128;
-    int stages = static_cast<int>((200 * 1024 - KR * b_bytes) / (128 * 128));
+    const size_t a_stage = p.patch ? static_cast<size_t>(p.planes) * p.PR * 256 : 128 * 128;
+    int stages = static_cast<int>((200 * 1024 - KR * b_bytes) / a_stage);
     if (stages > 12) stages = 12;
     if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: no room for the A ring", name);
     p.num_stages = stages;
-    plan->smem = KR * b_bytes + static_cast<size_t>(stages) * 128 * 128 + 1024;
+    plan->smem = KR * b_bytes + static_cast<size_t>(stages) * a_stage + 1024;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(KR) * 64, static_cast<uint64_t>(Cout)};
         uint64_t str[1] = {static_cast<uint64_t>(KR) * 64 * 2};
@@ -439,7 +456,7 @@ int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho
         DV_TRY(encode_map(e, &p.tmB, w, 2, dims, str, box, 128, name));
     }
     plan->grid = p.m_tiles < e->num_sms ? p.m_tiles : e->num_sms;
-    plan->name = name;
+    plan->name = std::string(name) + (p.patch ? "[patch]" : "");
     const double px = static_cast<double>(p.Nimg) * Ho * Wo;
     plan->flops = 2.0 * px * KR * 64 * Cout;  // as issued (window padding included)
     plan->bytes = 2.0 * static_cast<double>(in_padded.elems()) + 2.0 * px * Cout + 2.0 * KR * 64 * Cout;

@@ -377,7 +377,7 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         // the two full-resolution 16-channel layers run on conv_win_tcgen05 (load/store producer, resident filter):
         // base writes into a zero-bordered buffer (interior at +1,+1) so that level0 reads 4-pixel x 16-channel windows
         DV_TRY(m->tensor(&b0, N, H + 2, W + 8, 16, /*zero=*/true));
-        const char* names[2] = {"base", "level0.win"};
+        const char* names[2] = {"base", win_patch_enabled() ? "level0.winp" : "level0.win"};
         for (int i = 0; i < 2; ++i) {
             const BlobTensor* w = e->find(std::string(names[i]) + ".w");
             const BlobTensor* b = e->find(std::string(names[i]) + ".b");

@@ -178,6 +178,17 @@ __device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uin
     return d;
 }
 
+// Un-swizzled (interleaved) K-major descriptor: core matrix = 8 rows x 16 B stored contiguously (row i at +16 i bytes);
+// lbo = byte stride between core matrices adjacent in K, sbo = between adjacent 8-row groups.
+__device__ __forceinline__ uint64_t make_kmajor_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+
 // Instruction descriptor: A,B = F16 (K-major), D = F32, M = 128, N = n.
 __device__ __forceinline__ uint32_t make_idesc_f16_m128(uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);

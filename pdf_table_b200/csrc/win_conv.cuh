@@ -38,6 +38,8 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[64];
+    __shared__ uint64_t s_adesc[28], s_bdesc[28];  // patch mode: per-(filter row, K16 slice) descriptors, tabulated once
+    __shared__ uint32_t s_dsel[28], s_accum[28];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -45,7 +47,10 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
     const uint32_t a_base = smem_base + static_cast<uint32_t>(p.KR) * b_bytes;  // B (resident) first, then the A ring
     constexpr uint32_t kABytes = 128u * 128u;
     const int num_stages = p.num_stages;
-    const uint32_t tmem_cols = p.BLOCK_N <= 16 ? 32u : p.BLOCK_N <= 32 ? 64u : 128u;  // 2 accumulators, power of two >= 32
+    // 2 tile buffers x kSplit partial accumulators (filter rows are dealt round-robin to kSplit INDEPENDENT accumulation
+    // chains, summed by the epilogue: a chain of dependent tcgen05.mma costs ~150 clk per instruction regardless of N)
+    constexpr uint32_t kSplit = 2;
+    const uint32_t tmem_cols = p.BLOCK_N <= 16 ? 64u : p.BLOCK_N <= 32 ? 128u : 256u;
 
     if (threadIdx.x < 64) s_bias[threadIdx.x] = threadIdx.x < p.BLOCK_N && p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
     if (threadIdx.x == 0) {
@@ -70,7 +75,8 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const uint32_t acc_cols = tmem_cols >> 1;
+    const uint32_t acc_cols = tmem_cols >> 1;            // per tile buffer
+    const uint32_t part_cols = acc_cols / kSplit;        // per partial accumulator (>= BLOCK_N)
 
     if (warp < 4) {
         // ===================== producers: thread t owns A row t of every stage =====================
@@ -78,6 +84,44 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
         // (fence.proxy.async + mbarrier arrive) once its group has landed.  A first version with ld.global -> registers ->
         // st.shared exposed one L2 round trip per k-block (base: 2.95 ms, slower than TMA).
         constexpr int kDepth = 4;
+        if (p.patch) {
+            const int chunks = p.planes * p.PR * 16;
+            const uint32_t stage_bytes = static_cast<uint32_t>(chunks) * 16u;
+            int stage = 0, pub_stage = 0, issued = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img;
+                const int t = tile - img * tiles_per_img;
+                const int ty = t / p.tiles_x;
+                const int y0 = ty * p.TH, x0 = (t - ty * p.tiles_x) * p.TW;
+                ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+                const uint32_t sbase = a_base + static_cast<uint32_t>(stage) * stage_bytes;
+                for (int i = threadIdx.x; i < chunks; i += 128) {
+                    const int plane = i / (p.PR * 16);
+                    const int rem = i - plane * p.PR * 16;
+                    const int prow = rem >> 4, px = rem & 15;
+                    const int y = y0 + prow, x = x0 + px;
+                    const uint32_t nb = (y < p.Hp && x < p.Wp) ? 16u : 0u;
+                    const __half* g = p.in + ((static_cast<long long>(img) * p.Hp + min(y, p.Hp - 1)) * p.Wp + min(x, p.Wp - 1)) * p.cpp + plane * 8;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + static_cast<uint32_t>(i) * 16u), "l"(g), "r"(nb)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                if (++issued > kDepth) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kDepth) : "memory");
+                    ptx::fence_proxy_async_smem();
+                    ptx::mbar_arrive(ptx::smem_u32(&full_bar[pub_stage]));
+                    if (++pub_stage == num_stages) pub_stage = 0;
+                }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            ptx::fence_proxy_async_smem();
+            for (int k = issued > kDepth ? kDepth : issued; k > 0; --k) {
+                ptx::mbar_arrive(ptx::smem_u32(&full_bar[pub_stage]));
+                if (++pub_stage == num_stages) pub_stage = 0;
+            }
+        } else {
         const int m = threadIdx.x;
         const int ly = m / p.TW, lx = m - ly * p.TW;
         const uint32_t row_off = static_cast<uint32_t>(m) * 128u;
@@ -119,9 +163,10 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
             ptx::mbar_arrive(ptx::smem_u32(&full_bar[pub_stage]));
             if (++pub_stage == num_stages) pub_stage = 0;
         }
+        }
     } else if (warp == 4) {
         // ===================== weight loader + MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (ptx::elect_one_sync()) {
             const uint32_t wb = ptx::smem_u32(&w_bar);
             ptx::mbar_expect_tx(wb, static_cast<uint32_t>(p.KR) * b_bytes);
             for (int r = 0; r < p.KR; ++r) ptx::tma_load_2d(smem_base + r * b_bytes, &p.tmB, wb, r * 64, 0);
@@ -129,17 +174,46 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
+            const uint32_t patch_stage_bytes = static_cast<uint32_t>(p.planes * p.PR) * 256u;
+            const int n_mma = p.KR * 4;
+            if (p.patch) {
+                const int per_plane = 4 / p.planes;  // MMAs (2 pixels x 8 channels each) per plane and filter row
+                for (int r = 0; r < p.KR; ++r)
+                    for (int k = 0; k < 4; ++k) {
+                        const int plane = k / per_plane, j = k - plane * per_plane;
+                        const uint32_t off = static_cast<uint32_t>(plane * p.PR) * 256u + static_cast<uint32_t>(r * 16 + 2 * j) * 16u;
+                        s_adesc[r * 4 + k] = ptx::make_kmajor_desc_noswz(off, 16u, 256u);  // + (stage base >> 4) per tile
+                        s_bdesc[r * 4 + k] = ptx::make_kmajor_desc(smem_base + r * b_bytes, 128) + 2ull * k;
+                        s_dsel[r * 4 + k] = static_cast<uint32_t>(r & 1) * part_cols;
+                        s_accum[r * 4 + k] = ((r >> 1) | k) != 0 ? 1u : 0u;
+                    }
+            }
             for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
+                if (p.patch) {
+                    ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+                    ptx::tc_fence_after();
+                    // descriptors differ from tile to tile only by the stage base: everything else was tabulated once
+                    const uint64_t abase = static_cast<uint64_t>((a_base + static_cast<uint32_t>(stage) * patch_stage_bytes) >> 4);
+                    for (int i = 0; i < n_mma; ++i)
+                        ptx::umma_f16_ss(d_tmem + s_dsel[i], s_adesc[i] + abase, s_bdesc[i], idesc, s_accum[i]);
+                    ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
+                    if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+                    ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int r = 0; r < p.KR; ++r) {
                     ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
                     ptx::tc_fence_after();
                     const uint64_t adesc = ptx::make_kmajor_desc(a_base + static_cast<uint32_t>(stage) * kABytes, 128);
                     const uint64_t bdesc = ptx::make_kmajor_desc(smem_base + r * b_bytes, 128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16_ss(d_tmem, adesc + 2ull * k, bdesc + 2ull * k, idesc, (r | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16_ss(d_tmem + static_cast<uint32_t>(r & 1) * part_cols, adesc + 2ull * k, bdesc + 2ull * k, idesc, ((r >> 1) | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(ptx::smem_u32(&empty_bar[stage]));
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
@@ -166,10 +240,15 @@ conv_win_tcgen05(const __grid_constant__ WinConvParams p) {
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc) * acc_cols;
             for (int c = 0; c < p.BLOCK_N; c += 16) {
-                uint32_t v[16];
+                uint32_t v[16], v2[16];
                 ptx::tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c), v);
+                ptx::tmem_ld_32x32b_x16(t_row + part_cols + static_cast<uint32_t>(c), v2);
                 ptx::tmem_ld_wait();
                 if (!valid || c >= p.Cout) continue;
+                if (p.KR > 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                }
                 uint4 o[2];
                 __half2* h2 = reinterpret_cast<__half2*>(o);
 #pragma unroll

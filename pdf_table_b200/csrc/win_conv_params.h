@@ -15,6 +15,10 @@ struct WinConvParams {
     const float* bias;      // padded to a multiple of 256
     __half* out;            // [N][oHp][oWp][out_ld], written at (+opad, +opad)
     int oHp, oWp, opad, out_ld;
+    // patch mode (stride 1): the (TH+KR-1) x 16-pixel input patch of a 16 x 8 tile is staged ONCE, as `planes` planes of
+    // [row][pixel][8 channels]; the A operand of filter row r / pixel pair j is an UN-swizzled K-major descriptor into it with
+    // LBO = 16 B (next pixel = next 8-element K chunk) and rows 16 B apart (next output pixel): overlapping windows, no copies
+    int patch, planes, PR;
 };
 
 }  // namespace dv

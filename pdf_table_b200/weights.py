@@ -240,6 +240,20 @@ def pack_win3x3_c16(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
     return packed.reshape(cout, 3 * 64), pad_bias(shift)
 
 
+def pack_win3x3_c16_planar(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """As pack_win3x3_c16 for the PATCH mode of conv_win_tcgen05, whose staged patch is two planes of 8 channels:
+    K index = r*64 + plane*32 + s*8 + c8."""
+    w = _np(weight).astype(np.float32)
+    cout, cin, kh, kw = w.shape
+    assert (cin, kh, kw) == (16, 3, 3), w.shape
+    scale, shift = bn_affine(bn, cout)
+    w = (w * scale[:, None, None, None]).transpose(0, 2, 3, 1)  # [cout, r, s, c]
+    packed = np.zeros((cout, 3, 2, 4, 8), np.float16)
+    for plane in range(2):
+        packed[:, :, plane, :3, :] = w[:, :, :, plane * 8:(plane + 1) * 8].astype(np.float16)
+    return packed.reshape(cout, 3 * 64), pad_bias(shift)
+
+
 def pack_split_linear(weight, bias=None) -> Tuple[np.ndarray, np.ndarray]:
     """nn.Linear weight [out, in] -> split-fp16 operand [out, 3*in_pad] = [W_hi | W_lo | W_hi] with W_hi = fp16(W),
     W_lo = fp16(W - W_hi): against activations stored as [hi | lo] the k-block walk (hi, hi, lo) accumulates
@@ -279,6 +293,7 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
     put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1")))
     put("level0", pack_conv(sd["base.level0.0.weight"], None, _bn(sd, "base.level0.1")))
     put("level0.win", pack_win3x3_c16(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
+    put("level0.winp", pack_win3x3_c16_planar(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
     put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
     for k in sd:
         if not k.startswith("base.level") or k.startswith(("base.level0", "base.level1")):
@@ -371,6 +386,7 @@ def pack_centernet_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
     put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1")))
     put("level0", pack_conv(sd["base.level0.0.weight"], None, _bn(sd, "base.level0.1")))
     put("level0.win", pack_win3x3_c16(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
+    put("level0.winp", pack_win3x3_c16_planar(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
     put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
     for k in sd:
         if k.startswith("base.level") and not k.startswith(("base.level0", "base.level1")):
