@@ -115,55 +115,114 @@ int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out) {
 // ---------------------------------------------------------------------------------------------- DCN sampling
 // om: fp32 [M, 32] = conv_offset_mask output; columns 2k, 2k+1 = (dy, dx) of tap k, 18+k = mask logit (dcnv2.py:73-76).
 // One thread = (pixel, 8 channels), looping over the nine taps; grid = (pixel blocks, image rows).  Sampling rule =
-// torchvision deform_conv2d_kernel bilinear_interpolate.  (The first version used one thread per (pixel, tap, 8 ch) with
-// a flat 64-bit index: ncu showed 450 instructions per thread, most of them index arithmetic, at 79 % issue
-// utilisation -- profiles/r1m.  32-bit 2-D indexing and the tap loop cut that about fivefold.)
+// torchvision deform_conv2d_kernel bilinear_interpolate.
+//
+// History of this kernel, all from ncu (profiles/r1m, r1x): v1 was one thread per (pixel, tap, 8 ch) with flat 64-bit
+// indices -- 450 instructions per thread, mostly index arithmetic.  v2 looped over the taps with 32-bit 2-D indices
+// (5x fewer), but every one of the C/8 threads of a pixel still recomputed the same sigmoid, floor, clamps and corner
+// weights, and each fp16 sample cost a convert plus an FFMA: 1861 instructions per thread at 78 % issue utilisation.
+// v3 (this one): the (pixel, tap) jobs of a warp are computed ONCE, spread over its lanes, and handed to the channel
+// threads by three shuffles (corner-0 offset with the two clamped steps in its top bits, and the four mask-scaled
+// weights as two half2), and the blend uses the mixed-precision FHFMA (fp16 sample x fp16 weight + fp32 accumulator).
+// The weights are therefore rounded to fp16 (2^-11 relative) before the blend; the output is fp16 as before.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+    return c;
+}
+
 __global__ void __launch_bounds__(256)
 k_dcn_im2col(const __half* __restrict__ in, int H, int W, int lcv, int ldi, const float* __restrict__ om, __half* __restrict__ col) {
     const int cv = 1 << lcv, C = cv << 3;
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int t = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
     const int x = t >> lcv, c8 = t & (cv - 1);
-    if (x >= W) return;
+    const bool active = x < W;
     const int row = blockIdx.y;  // n * H + y
     const int y = row % H;
-    const int pix = row * W + x;
-    const float* o = om + static_cast<size_t>(pix) * 32;
-    const __half* base = in + static_cast<size_t>(row - y) * W * ldi + c8 * 8;  // image origin + channel group
-    __half* dst = col + static_cast<size_t>(pix) * 9 * C + c8 * 8;
-#pragma unroll 3
-    for (int tap = 0; tap < 9; ++tap) {
-        const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
-        const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
-        const float py = static_cast<float>(y + tap / 3 - 1) + dy;
-        const float px = static_cast<float>(x + tap % 3 - 1) + dx;
-        float acc[8];
+    const int lppw = lcv >= 5 ? 0 : 5 - lcv;  // log2(pixels per warp)
+    const int xw = (t - lane) >> lcv;         // first pixel of this warp
+    const int pw = lcv >= 5 ? 0 : lane >> lcv;
+    const int njobs = 9 << lppw;
+
+    // ---- the warp's (tap, pixel) jobs, job = tap * ppw + pixel-in-warp, lane `job & 31` of round `job >> 5`
+    uint32_t jp[2] = {0u, 0u}, jw01[2] = {0u, 0u}, jw23[2] = {0u, 0u};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        if (py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W)) {
+    for (int r = 0; r < 2; ++r) {
+        const int job = r * 32 + lane;
+        const int tap = job >> lppw, jx = xw + (job & ((1 << lppw) - 1));
+        if (job < njobs && jx < W) {
+            const float* o = om + static_cast<size_t>(row * W + jx) * 32;
+            const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
+            const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
+            const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;
+            const float py = static_cast<float>(y + ky - 1) + dy;
+            const float px = static_cast<float>(jx + kx - 1) + dx;
+            const bool inside = py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W);
             const float fy = floorf(py), fx = floorf(px);
             const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
             const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-            const float w4[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+            const bool oky0 = inside && y0 >= 0 && y0 <= H - 1, oky1 = inside && y0 + 1 >= 0 && y0 + 1 <= H - 1;
+            const bool okx0 = x0 >= 0 && x0 <= W - 1, okx1 = x0 + 1 >= 0 && x0 + 1 <= W - 1;
+            const float w00 = (oky0 && okx0) ? hy * hx * mask : 0.f, w01 = (oky0 && okx1) ? hy * lx * mask : 0.f;
+            const float w10 = (oky1 && okx0) ? ly * hx * mask : 0.f, w11 = (oky1 && okx1) ? ly * lx * mask : 0.f;
+            // clamped addresses (zero weight where clamped)
+            const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+            const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
+            jp[r] = static_cast<uint32_t>(cy0 * W + cx0) | (static_cast<uint32_t>(cx1 - cx0) << 30) |
+                    (static_cast<uint32_t>(cy1 - cy0) << 31);
+            const __half2 h01 = __floats2half2_rn(w00, w01), h23 = __floats2half2_rn(w10, w11);
+            jw01[r] = *reinterpret_cast<const uint32_t*>(&h01);
+            jw23[r] = *reinterpret_cast<const uint32_t*>(&h23);
+        }
+        if (njobs <= 32) break;
+    }
+
+    const __half* base = in + static_cast<size_t>(row - y) * W * ldi + c8 * 8;  // image origin + channel group
+    __half* dst = col + static_cast<size_t>(row * W + x) * 9 * C + c8 * 8;
+    const int rstep = W * ldi;
+    // three taps per round: their twelve 16-byte corner loads are issued before any is consumed
+#pragma unroll 1
+    for (int t0 = 0; t0 < 9; t0 += 3) {
+        uint4 u[3][4];
+        uint32_t w01[3], w23[3];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
-                if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) {
-                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(yy * W + xx) * ldi));
-                    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = __half22float2(h[i]);
-                        acc[2 * i] = fmaf(w4[k], f.x, acc[2 * i]);
-                        acc[2 * i + 1] = fmaf(w4[k], f.y, acc[2 * i + 1]);
-                    }
-                }
+        for (int q = 0; q < 3; ++q) {
+            const int job = ((t0 + q) << lppw) + pw;
+            const bool r1 = (job >> 5) != 0;  // uniform over the warp
+            const uint32_t p = __shfl_sync(0xffffffffu, r1 ? jp[1] : jp[0], job & 31);
+            w01[q] = __shfl_sync(0xffffffffu, r1 ? jw01[1] : jw01[0], job & 31);
+            w23[q] = __shfl_sync(0xffffffffu, r1 ? jw23[1] : jw23[0], job & 31);
+            const __half* b00 = base + static_cast<size_t>(p & 0x3fffffffu) * ldi;
+            const int sx = (p & 0x40000000u) ? ldi : 0, sy = (p & 0x80000000u) ? rstep : 0;
+            if (active) {
+                u[q][0] = __ldg(reinterpret_cast<const uint4*>(b00));
+                u[q][1] = __ldg(reinterpret_cast<const uint4*>(b00 + sx));
+                u[q][2] = __ldg(reinterpret_cast<const uint4*>(b00 + sy));
+                u[q][3] = __ldg(reinterpret_cast<const uint4*>(b00 + sy + sx));
             }
         }
-        uint4 out;
-        __half2* ho = reinterpret_cast<__half2*>(&out);
+        if (!active) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * mask, acc[2 * i + 1] * mask);
-        *reinterpret_cast<uint4*>(dst + tap * C) = out;
+        for (int q = 0; q < 3; ++q) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t wp = (k < 2) ? w01[q] : w23[q];
+                const unsigned short wk = static_cast<unsigned short>((k & 1) ? (wp >> 16) : (wp & 0xffffu));
+                const uint32_t* h = reinterpret_cast<const uint32_t*>(&u[q][k]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[2 * i] = fhfma(static_cast<unsigned short>(h[i] & 0xffffu), wk, acc[2 * i]);
+                    acc[2 * i + 1] = fhfma(static_cast<unsigned short>(h[i] >> 16), wk, acc[2 * i + 1]);
+                }
+            }
+            uint4 out;
+            __half2* ho = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+            *reinterpret_cast<uint4*>(dst + (t0 + q) * C) = out;
+        }
     }
 }
 
