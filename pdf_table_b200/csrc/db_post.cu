@@ -197,33 +197,37 @@ struct Pt {
 };
 
 // icvFetchContour + CHAIN_APPROX_SIMPLE (see oracle/cv_geom_ref.py trace_border). Returns the vertex count or -1.
-__device__ int trace_border(const uint8_t* fg, int H, int W, int x0, int y0, bool hole, short2* out, int cap) {
+// Whole warp: the walk's state is replicated in every lane; the up-to-eight sequential neighbour probes of one step
+// (each a dependent global load in the scalar form: 25 % of the kernel's samples, profiles/r1x) are issued by lanes
+// 0..7 at once and the first hit in scan order is picked from the ballot.  Lane 0 writes the vertices.
+__device__ int trace_border(const uint8_t* fg, int H, int W, int x0, int y0, bool hole, short2* out, int cap, int lane) {
     auto px = [&](int x, int y) -> bool { return x >= 0 && x < W && y >= 0 && y < H && fg[y * W + x] != 0; };
-    int s_end = hole ? 0 : 4, s = s_end;
-    bool found;
-    do {
-        s = (s - 1) & 7;
-        found = px(x0 + c_dx[s], y0 + c_dy[s]);
-    } while (!found && s != s_end);
-    if (!found) {
-        out[0] = make_short2(static_cast<short>(x0), static_cast<short>(y0));
-        return 1;
+    const int l8 = lane & 7;
+    const int s_end = hole ? 0 : 4;
+    int s;
+    {  // clockwise scan s_end-1, s_end-2, ..., s_end
+        const int sl = (s_end - 1 - l8) & 7;
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x0 + c_dx[sl], y0 + c_dy[sl]));
+        if (hit == 0u) {
+            if (lane == 0) out[0] = make_short2(static_cast<short>(x0), static_cast<short>(y0));
+            return 1;
+        }
+        s = (s_end - 1 - (__ffs(hit) - 1)) & 7;
     }
     const int i1x = x0 + c_dx[s], i1y = y0 + c_dy[s];
     int n = 0;
     int x3 = x0, y3 = y0, ptx = x0, pty = y0, prev_s = s ^ 4;
     for (;;) {
-        int x4, y4;
-        for (;;) {
-            ++s;
-            x4 = x3 + c_dx[s & 7];
-            y4 = y3 + c_dy[s & 7];
-            if (px(x4, y4)) break;
-        }
-        s &= 7;
+        // counter-clockwise scan s+1, s+2, ...: the pixel we came from is a neighbour, so one of the eight hits
+        const int sl = (s + 1 + l8) & 7;
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x3 + c_dx[sl], y3 + c_dy[sl]));
+        if (hit == 0u) return -1;  // unreachable on a consistent map; never spin
+        s = (s + 1 + (__ffs(hit) - 1)) & 7;
+        const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
         if (s != prev_s) {
             if (n >= cap) return -1;
-            out[n++] = make_short2(static_cast<short>(ptx), static_cast<short>(pty));
+            if (lane == 0) out[n] = make_short2(static_cast<short>(ptx), static_cast<short>(pty));
+            ++n;
             prev_s = s;
         }
         ptx += c_dx[s];
@@ -538,34 +542,6 @@ __device__ void mini_box_order(const float2* pt, float2* box) {
 
 // ---- cv2.fillPoly membership for a convex quad with integer vertices (tools/fillpoly_proto.py): pixel on the
 // 8-connected Bresenham line of an edge (cv::LineIterator, left-to-right) or inside a 16.16 fixed-point scan-line span
-__device__ __forceinline__ bool on_line(int px, int py, int x1, int y1, int x2, int y2) {
-    int dx = x2 - x1, dy = y2 - y1;
-    if (dx < 0) {
-        int t = x1; x1 = x2; x2 = t;
-        t = y1; y1 = y2; y2 = t;
-        dx = -dx;
-        dy = -dy;
-    }
-    int ystep = 1;
-    if (dy < 0) {
-        dy = -dy;
-        ystep = -1;
-    }
-    if (dy > dx) {
-        const int j = (py - y1) * ystep;
-        if (j < 0 || j > dy) return false;
-        const int T = 2 * dx * j - dy;
-        const int k = T <= 0 ? 0 : (T + 2 * dy - 1) / (2 * dy);
-        return px == x1 + k;
-    }
-    const int i = px - x1;
-    if (i < 0 || i > dx) return false;
-    if (dx == 0) return py == y1;
-    const int T = 2 * dy * i - dx;
-    const int k = T <= 0 ? 0 : (T + 2 * dx - 1) / (2 * dx);
-    return py == y1 + ystep * k;
-}
-
 struct QuadFill {
     int vx[4], vy[4];
     long long ex[4], edx[4];  // edge start x (16.16) at y0 and per-row increment
@@ -585,10 +561,48 @@ __device__ void quad_fill_setup(QuadFill& q) {
         if (y0 < y1) { q.ey0[e] = y0; q.ey1[e] = y1; q.ex[e] = X0; } else { q.ey0[e] = y1; q.ey1[e] = y0; q.ex[e] = X1; }
     }
 }
-__device__ bool quad_fill_test(const QuadFill& q, int px, int py) {
+// Row form of the line membership (per-pixel definition: oracle/db_post_ref.py, tools/fillpoly_rows.py on_line): the
+// pixels of an edge's Bresenham line in row py are one inclusive column interval -- a single pixel for a y-major edge,
+// and for an x-major edge the run of columns i with k(i) == kk, i.e. floor(dx (2kk-1) / 2dy) < i <= floor(dx (2kk+1) / 2dy)
+// (checked exhaustively against the per-pixel predicate by tools/fillpoly_rows.py).
+__device__ __forceinline__ void line_row_interval(int py, int x1, int y1, int x2, int y2, int& lo, int& hi) {
+    lo = 1;
+    hi = 0;
+    int dx = x2 - x1, dy = y2 - y1;
+    if (dx < 0) {
+        int t = x1; x1 = x2; x2 = t;
+        t = y1; y1 = y2; y2 = t;
+        dx = -dx;
+        dy = -dy;
+    }
+    int ystep = 1;
+    if (dy < 0) {
+        dy = -dy;
+        ystep = -1;
+    }
+    const int kk = (py - y1) * ystep;
+    if (kk < 0 || kk > dy) return;
+    if (dy > dx) {
+        const int T = 2 * dx * kk - dy;
+        const int k = T <= 0 ? 0 : (T + 2 * dy - 1) / (2 * dy);
+        lo = hi = x1 + k;
+        return;
+    }
+    if (dy == 0) {  // horizontal edge (or a single point when dx == 0)
+        lo = x1;
+        hi = x1 + dx;
+        return;
+    }
+    const int a = kk == 0 ? 0 : (dx * (2 * kk - 1)) / (2 * dy) + 1;
+    const int b = min((dx * (2 * kk + 1)) / (2 * dy), dx);
+    lo = x1 + a;
+    hi = x1 + b;
+}
+__device__ void quad_fill_row(const QuadFill& q, int py, int* lo, int* hi) {
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int j = (i + 3) & 3;
-        if (on_line(px, py, q.vx[j], q.vy[j], q.vx[i], q.vy[i])) return true;
+        line_row_interval(py, q.vx[j], q.vy[j], q.vx[i], q.vy[i], lo[i], hi[i]);
     }
     long long xa = 0, xb = 0;
     int cnt = 0;
@@ -599,14 +613,16 @@ __device__ bool quad_fill_test(const QuadFill& q, int px, int py) {
             ++cnt;
         }
     }
-    if (cnt < 2) return false;
+    lo[4] = 1;
+    hi[4] = 0;
+    if (cnt < 2) return;
     if (xa > xb) {
         const long long t = xa;
         xa = xb;
         xb = t;
     }
-    const long long a = (xa + 32768) >> 16, b = xb >> 16;
-    return px >= a && px <= b;
+    lo[4] = static_cast<int>((xa + 32768) >> 16);
+    hi[4] = static_cast<int>(xb >> 16);
 }
 
 // ---- Clipper 6.4.2 ClipperOffset (jtRound, etClosedPolygon) of a quad, see oracle/db_post_ref.py
@@ -782,14 +798,13 @@ k_db_contour_boxes(const float* __restrict__ prob, int H, int W, const uint8_t* 
     const uint8_t* fgp = fg + static_cast<long long>(n) * H * W;
     const float* pp = prob + static_cast<long long>(n) * H * W;
     // ---- 1. trace the border
-    int nv = 0;
-    if (lane == 0) {
+    int nv;
+    {
         const int ry = root / W, rx = root - ry * W;
         const bool hole = fgp[root] == 0;
-        nv = trace_border(fgp, H, W, hole ? rx - 1 : rx, ry, hole, wm.verts, kMaxV);
-        if (nv < 0) atomicAdd(overflow, 1);
+        nv = trace_border(fgp, H, W, hole ? rx - 1 : rx, ry, hole, wm.verts, kMaxV, lane);
+        if (nv < 0 && lane == 0) atomicAdd(overflow, 1);
     }
-    nv = __shfl_sync(0xffffffffu, nv, 0);
     if (nv <= 0) return;
     __syncwarp();
     // ---- 2. first minAreaRect -> mini box
@@ -826,13 +841,38 @@ k_db_contour_boxes(const float* __restrict__ prob, int H, int W, const uint8_t* 
     }
     quad_fill_setup(q);
     const int bw = xmax - xmin + 1, bh = ymax - ymin + 1;
+    // Row by row: the mask's membership in a row is the union of five inclusive column intervals (the four edge lines
+    // and the scan-line span), computed once per row; the per-pixel work is then a few compares and one load.
+    // (ncu, profiles/r1x: the per-pixel form of this test was 55 % of this kernel's samples.)
     double sum = 0.0;
     int cnt = 0;
-    for (int i = lane; i < bw * bh; i += 32) {
-        const int py = i / bw, px = i - py * bw;
-        if (quad_fill_test(q, px, py)) {
-            sum += static_cast<double>(pp[(ymin + py) * W + xmin + px]);
-            ++cnt;
+    for (int py = 0; py < bh; ++py) {
+        int lo[5], hi[5];
+        quad_fill_row(q, py, lo, hi);
+        int mn = bw, mx = -1;
+#pragma unroll
+        for (int e = 0; e < 5; ++e)
+            if (lo[e] <= hi[e]) {
+                mn = min(mn, lo[e]);
+                mx = max(mx, hi[e]);
+            }
+        mn = max(mn, 0);
+        mx = min(mx, bw - 1);
+        const float* prow = pp + (ymin + py) * W + xmin;
+        for (int px = mn + lane; px <= mx; px += 64) {
+            const int p1 = px + 32;
+            bool in0 = false, in1 = false;
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                in0 |= px >= lo[e] && px <= hi[e];
+                in1 |= p1 >= lo[e] && p1 <= hi[e];
+            }
+            in1 &= p1 <= mx;
+            const float v0 = in0 ? __ldg(prow + px) : 0.f;  // both loads in flight before either is summed
+            const float v1 = in1 ? __ldg(prow + p1) : 0.f;
+            sum += static_cast<double>(v0);
+            sum += static_cast<double>(v1);
+            cnt += static_cast<int>(in0) + static_cast<int>(in1);
         }
     }
 #pragma unroll
