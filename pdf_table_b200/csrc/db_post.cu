@@ -189,8 +189,11 @@ k_db_rank(int H, int W, const int* __restrict__ label, const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ geometry (lane 0)
-__device__ __constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__device__ __constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// 8-neighbour steps of cv2's chain code, s = 0..7: dx = {1, 1, 0, -1, -1, -1, 0, 1}, dy = {0, -1, -1, -1, 0, 1, 1, 1},
+// packed two bits per entry (value + 1) so that a step is three ALU ops instead of an indexed constant load whose
+// scoreboard wait sat on the border walk's critical path (profiles/r1y_contour_ncu.txt)
+__device__ __forceinline__ int c_dx(int s) { return static_cast<int>((0x901Au >> (2 * s)) & 3u) - 1; }
+__device__ __forceinline__ int c_dy(int s) { return static_cast<int>((0xA901u >> (2 * s)) & 3u) - 1; }
 
 struct Pt {
     int x, y;
@@ -207,31 +210,31 @@ __device__ int trace_border(const uint8_t* fg, int H, int W, int x0, int y0, boo
     int s;
     {  // clockwise scan s_end-1, s_end-2, ..., s_end
         const int sl = (s_end - 1 - l8) & 7;
-        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x0 + c_dx[sl], y0 + c_dy[sl]));
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x0 + c_dx(sl), y0 + c_dy(sl)));
         if (hit == 0u) {
             if (lane == 0) out[0] = make_short2(static_cast<short>(x0), static_cast<short>(y0));
             return 1;
         }
         s = (s_end - 1 - (__ffs(hit) - 1)) & 7;
     }
-    const int i1x = x0 + c_dx[s], i1y = y0 + c_dy[s];
+    const int i1x = x0 + c_dx(s), i1y = y0 + c_dy(s);
     int n = 0;
     int x3 = x0, y3 = y0, ptx = x0, pty = y0, prev_s = s ^ 4;
     for (;;) {
         // counter-clockwise scan s+1, s+2, ...: the pixel we came from is a neighbour, so one of the eight hits
         const int sl = (s + 1 + l8) & 7;
-        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x3 + c_dx[sl], y3 + c_dy[sl]));
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < 8 && px(x3 + c_dx(sl), y3 + c_dy(sl)));
         if (hit == 0u) return -1;  // unreachable on a consistent map; never spin
         s = (s + 1 + (__ffs(hit) - 1)) & 7;
-        const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
+        const int x4 = x3 + c_dx(s), y4 = y3 + c_dy(s);
         if (s != prev_s) {
             if (n >= cap) return -1;
             if (lane == 0) out[n] = make_short2(static_cast<short>(ptx), static_cast<short>(pty));
             ++n;
             prev_s = s;
         }
-        ptx += c_dx[s];
-        pty += c_dy[s];
+        ptx += c_dx(s);
+        pty += c_dy(s);
         if (x4 == x0 && y4 == y0 && x3 == i1x && y3 == i1y) break;
         x3 = x4;
         y3 = y4;
@@ -844,6 +847,15 @@ k_db_contour_boxes(const float* __restrict__ prob, int H, int W, const uint8_t* 
     // Row by row: the mask's membership in a row is the union of five inclusive column intervals (the four edge lines
     // and the scan-line span), computed once per row; the per-pixel work is then a few compares and one load.
     // (ncu, profiles/r1x: the per-pixel form of this test was 55 % of this kernel's samples.)
+    {  // pull the box's rows of the probability map towards L1 first: the row loop below otherwise pays one full
+       // memory latency per row (21 % of the kernel's samples after the row-interval rewrite)
+        const int lpr = (bw * 4 + 127) / 128 + 1;  // 128-byte lines per row (rows are not line-aligned)
+        for (int i = lane; i < bh * lpr; i += 32) {
+            const int py = i / lpr, l = i - py * lpr;
+            const float* a = pp + (ymin + py) * W + min(xmin + l * 32, xmax);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        }
+    }
     double sum = 0.0;
     int cnt = 0;
     for (int py = 0; py < bh; ++py) {

@@ -29,13 +29,21 @@ for w in WANT:
 kid = sys.argv[2] if len(sys.argv) > 2 else "1"
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{kid}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-if len(rows) > 2:
-    h = rows[1]
+
+
+def num(x):
+    try:
+        return int(x)
+    except ValueError:
+        return 0
+
+
+h = next((r for r in rows if "Source" in r and "# Samples" in r), None)
+if h is not None:
     isrc, ismp, iex = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
     st = [i for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
-    data = rows[2:]
-    tot = sum(int(r[ismp] or 0) for r in data)
-    print("total samples", tot)
-    for r in sorted(data, key=lambda r: -int(r[ismp] or 0))[:22]:
-        top = sorted(((h[i], int(r[i] or 0)) for i in st if int(r[i] or 0) > 0), key=lambda kv: -kv[1])[:3]
+    data = [r for r in rows[rows.index(h) + 1:] if len(r) == len(h)]  # ncu emits ragged separator rows
+    print("total samples", sum(num(r[ismp]) for r in data))
+    for r in sorted(data, key=lambda r: -num(r[ismp]))[:22]:
+        top = sorted(((h[i], num(r[i])) for i in st if num(r[i]) > 0), key=lambda kv: -kv[1])[:3]
         print(r[ismp].rjust(6), r[iex].rjust(9), r[isrc][:64].ljust(64), top)
