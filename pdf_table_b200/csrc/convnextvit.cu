@@ -34,8 +34,9 @@ constexpr int kDims[4] = {96, 192, 256, 512};
 constexpr int kVitLayers = 12, kVitDim = 192, kVitMlp = 768, kTok = 75, kStitched = 201;
 
 struct Step {
-    enum Kind { PATCHIFY, DWLN, LN, GEMM, ATTN } kind;
+    enum Kind { PATCHIFY, DWLN, LN, GEMM, ATTN, MLP } kind;
     ConvPlan plan;            // GEMM
+    MlpPlan mlp;              // MLP (fused pwconv1 -> GELU -> pwconv2 + residual)
     const float *w = nullptr, *b = nullptr, *lnw = nullptr, *lnb = nullptr;
     const float* fin = nullptr;  // fp32 input
     __half* hout = nullptr;
@@ -117,6 +118,10 @@ int add_gemm(Engine* e, Pass* ps, const std::string& name, const __half* A, long
     return 0;
 }
 
+// x += W2 GELU(W1 h + b1) + b2 in one launch where mlp_fused_tcgen05 covers the width, else the two GEMMs
+int add_mlp(Engine* e, Pass* ps, const std::string& n1, const std::string& n2, const __half* h, __half* g, long long rows, int C,
+            float* x);
+
 EpiSpec epi_f16(__half* out, int ld, int act) {
     EpiSpec es;
     es.out = out;
@@ -138,6 +143,24 @@ EpiSpec epi_stream(float* out, int ld, const float* res, int res_mod = 0) {
         es.res_mod = res_mod;
     }
     return es;
+}
+
+int add_mlp(Engine* e, Pass* ps, const std::string& n1, const std::string& n2, const __half* h, __half* g, long long rows, int C,
+            float* x) {
+    if (!mlp_fused_supported(C)) {
+        DV_TRY(add_gemm(e, ps, n1, h, rows, C, 4 * C, epi_f16(g, 4 * C, ACT_GELU)));
+        return add_gemm(e, ps, n2, g, rows, 4 * C, C, epi_stream(x, C, x));
+    }
+    ConvSpec c1, c2;
+    DV_TRY(get_linear(e, n1, C, 4 * C, &c1));
+    DV_TRY(get_linear(e, n2, 4 * C, C, &c2));
+    Step st;
+    st.kind = Step::MLP;
+    st.name = n1 + "+" + n2.substr(n2.rfind('.') + 1);
+    DV_TRY(plan_mlp(e, h, static_cast<int>(rows), C, c1.w, c1.bias, c2.w, c2.bias, x, &st.mlp, st.name.c_str()));
+    ps->flops += st.mlp.flops;
+    ps->steps.push_back(st);
+    return 0;
 }
 
 int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
@@ -209,8 +232,7 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
             if (rc) return rc;
             ps->steps.push_back(st);
             ps->flops += 2.0 * 49 * rows * C;
-            DV_TRY(add_gemm(e, ps, bp + ".pw1", h, rows, C, 4 * C, epi_f16(g, 4 * C, ACT_GELU)));
-            DV_TRY(add_gemm(e, ps, bp + ".pw2", g, rows, 4 * C, C, epi_stream(x, C, x)));
+            DV_TRY(add_mlp(e, ps, bp + ".pw1", bp + ".pw2", h, g, rows, C, x));
         }
     }
     // ---- ViT: features [B,1,75,512] -> cast -> 1x1 projection + position embeddings
@@ -258,8 +280,7 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
         ln2.lnb = f32(e, lp + ".ln2.b", kVitDim, &rc);
         if (rc) return rc;
         ps->steps.push_back(ln2);
-        DV_TRY(add_gemm(e, ps, lp + ".fc1", h, T, kVitDim, kVitMlp, epi_f16(g, kVitMlp, ACT_GELU)));
-        DV_TRY(add_gemm(e, ps, lp + ".fc2", g, T, kVitMlp, kVitDim, epi_stream(xv, kVitDim, xv)));
+        DV_TRY(add_mlp(e, ps, lp + ".fc1", lp + ".fc2", h, g, T, kVitDim, xv));
     }
     {
         Step st;
@@ -302,6 +323,7 @@ int run_pass(Engine* e, Pass* ps, const float* chunks, const uint8_t* crops_u8, 
                                   st.name.c_str()));
                 break;
             case Step::ATTN: DV_TRY(op_attn75(e, st.hin, ps->B, st.hout, st.name.c_str())); break;
+            case Step::MLP: DV_TRY(launch_mlp(e, st.mlp)); break;
             case Step::GEMM:
                 if (static_cast<int>(i) == ps->cls_step) {
                     st.plan.prm.out = logits;

@@ -12,6 +12,7 @@
 
 #include "igemm_params.h"
 #include "win_conv_params.h"
+#include "mlp_params.h"
 
 namespace dv {
 
@@ -167,6 +168,19 @@ int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho
                   int act, const Tensor& out_padded, int opad, WinConvPlan* plan, const char* name);
 int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops = 0);
 bool win_patch_enabled();
+
+// mlp_fused_tcgen05 (mlp_fused.cuh): pwconv1 -> GELU -> pwconv2 + residual (ConvNeXt) / fc1 -> GELU -> fc2 + residual (ViT)
+struct MlpPlan {
+    MlpParams prm;
+    int C = 0, grid = 0;
+    size_t smem = 0;
+    double flops = 0, bytes = 0;
+    std::string name;
+};
+bool mlp_fused_supported(int C);  // C in {96, 192, 256}; DV_MLP_FUSED=0 disables the kernel
+int plan_mlp(Engine* e, const __half* h, int M, int C, const __half* w1, const float* b1, const __half* w2, const float* b2,
+             float* x, MlpPlan* plan, const char* name);
+int launch_mlp(Engine* e, const MlpPlan& plan);
 
 // ops.cu (simple HBM-bound kernels)
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);

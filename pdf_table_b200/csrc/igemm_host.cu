@@ -10,6 +10,7 @@
 #include "engine.h"
 #include "igemm.cuh"
 #include "win_conv.cuh"
+#include "mlp_fused.cuh"
 
 namespace dv {
 
@@ -479,6 +480,74 @@ int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops
     cudaError_t st = cudaGetLastError();
     if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ mlp_fused_tcgen05
+bool mlp_fused_supported(int C) {
+    static const bool on = !(getenv("DV_MLP_FUSED") && atoi(getenv("DV_MLP_FUSED")) == 0);
+    return on && (C == 96 || C == 192 || C == 256);
+}
+
+template <int C>
+static int launch_mlp_c(Engine* e, const MlpPlan& plan) {
+    static cudaError_t attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(mlp_fused_tcgen05<C>),
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, MlpCfg<C>::SMEM);
+    if (attr_rc != cudaSuccess)
+        return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(mlp_fused_tcgen05<%d>, %d): %s", C, MlpCfg<C>::SMEM,
+                       cudaGetErrorString(attr_rc));
+    e->launch_begin("mlp_fused_tcgen05", plan.name, plan.flops, plan.bytes);
+    mlp_fused_tcgen05<C><<<plan.grid, kMlpThreads, MlpCfg<C>::SMEM, e->stream>>>(plan.prm);
+    e->launch_end();
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
+    return 0;
+}
+
+int plan_mlp(Engine* e, const __half* h, int M, int C, const __half* w1, const float* b1, const __half* w2, const float* b2,
+             float* x, MlpPlan* plan, const char* name) {
+    if (!(C == 96 || C == 192 || C == 256)) return set_err(e, DV_ERR_UNSUPPORTED, "%s: fused MLP needs C in {96, 192, 256}", name);
+    if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2) |
+         reinterpret_cast<uintptr_t>(x)) & 15)
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: fused MLP operands must be 16-byte aligned", name);
+    MlpParams& p = plan->prm;
+    memset(&p, 0, sizeof(p));
+    const uint64_t um = static_cast<uint64_t>(M), uc = static_cast<uint64_t>(C);
+    {
+        uint64_t dims[2] = {uc, um}, str[1] = {uc * 2};
+        uint32_t box[2] = {64, 128};
+        DV_TRY(encode_map(e, &p.tmA, h, 2, dims, str, box, 128, name));
+    }
+    {
+        uint64_t dims[2] = {uc, 4 * uc}, str[1] = {uc * 2};
+        uint32_t box[2] = {64, 64};
+        DV_TRY(encode_map(e, &p.tmW1, w1, 2, dims, str, box, 128, name));
+    }
+    {
+        uint64_t dims[2] = {4 * uc, uc}, str[1] = {4 * uc * 2};
+        uint32_t box[2] = {64, static_cast<uint32_t>(C)};
+        DV_TRY(encode_map(e, &p.tmW2, w2, 2, dims, str, box, 128, name));
+    }
+    p.b1 = b1;
+    p.b2 = b2;
+    p.x = x;
+    p.M = M;
+    p.m_tiles = (M + 127) / 128;
+    plan->C = C;
+    plan->grid = p.m_tiles < e->num_sms ? p.m_tiles : e->num_sms;
+    plan->smem = C == 96 ? MlpCfg<96>::SMEM : C == 192 ? MlpCfg<192>::SMEM : MlpCfg<256>::SMEM;
+    plan->flops = 2.0 * M * C * 4.0 * C * 2.0;
+    plan->bytes = static_cast<double>(M) * C * (2.0 + 4.0 + 4.0) + 16.0 * C * C;  // h read, x read + written, both weights once
+    plan->name = name;
+    return 0;
+}
+
+int launch_mlp(Engine* e, const MlpPlan& plan) {
+    switch (plan.C) {
+        case 96: return launch_mlp_c<96>(e, plan);
+        case 192: return launch_mlp_c<192>(e, plan);
+        case 256: return launch_mlp_c<256>(e, plan);
+    }
+    return set_err(e, DV_ERR_UNSUPPORTED, "launch %s: fused MLP C = %d", plan.name.c_str(), plan.C);
 }
 
 }  // namespace dv

@@ -1,0 +1,253 @@
+// mlp_fused_tcgen05: x += W2 * GELU(W1 * h + b1) + b2 in ONE kernel -- the pwconv1 -> GELU -> pwconv2 (+ layer_scale,
+// folded into W2 / b2 at pack time) + residual tail of HF ConvNextLayer (modeling_convnext.py, used by
+// convnext_vit/modeling_convnext.py:28-80) and the intermediate -> GELU -> output MLP of the ViT layers
+// (modeling_vit.py:32-180).  As two conv_igemm_tcgen05 launches this pair was 43 % of the recogniser: the 4C-wide hidden
+// tensor (8C bytes per token) was written by one epilogue-bound GEMM and read back by a second, HBM-bound one
+// (profiles/r1t_layers_rec.txt).  Here the hidden tensor never leaves the SM:
+//
+//   per 128-token tile, per 64-column chunk j of the hidden dimension (NC = 4C / 64 chunks)
+//     GEMM1  acc1[b]  = h_tile[128 x C] * W1[64j .. 64j+64, :]^T      tcgen05.mma M128 N64, K = C (zero-padded to 64s)
+//     epi1   G[g]     = fp16(GELU(acc1[b] + b1))                      tcgen05.ld -> registers -> st.shared, written in
+//                                                                     the 128-byte-swizzled K-major layout a UMMA
+//                                                                     descriptor reads (16-byte chunk ^= row & 7)
+//     GEMM2  acc2    += G[g][128 x 64] * W2[:, 64j .. 64j+64]^T       tcgen05.mma M128 N=C, K = 64
+//   final  x_tile    += acc2 + b2                                     fp32 residual stream, in place
+//
+// Warp roles (320 threads): warp 0 = TMA producer (h tile once per tile, W1 / W2 chunk rings, 2 deep), warp 1 = MMA
+// issuer, warps 2-9 = epilogue (two per TMEM lane quadrant, 32 of a chunk's 64 columns each).  The MMA warp issues
+// GEMM1(j+1) BEFORE GEMM2(j), so the tensor pipe works on the next chunk while the epilogue warps run GELU on this one.
+// TMEM: acc2 at columns [0, C), acc1 double-buffered at 256 + 64 b.
+#pragma once
+#include <cuda.h>
+
+#include "igemm.cuh"
+#include "mlp_params.h"
+
+namespace dv {
+
+constexpr int kMlpThreads = 320;
+
+template <int C>
+struct MlpCfg {
+    static constexpr int KB1 = (C + 63) / 64;          // k-blocks of GEMM1 (TMA zero-fills columns >= C)
+    static constexpr int NC = 4 * C / 64;              // hidden chunks
+    static constexpr int A_BYTES = KB1 * 128 * 128;    // h tile: KB1 atoms of 128 rows x 128 B
+    static constexpr int W1_SLOT = KB1 * 64 * 128;     // KB1 atoms of 64 rows x 128 B
+    static constexpr int W2_SLOT = C * 128;            // one atom of C rows x 128 B
+    static constexpr int G_BYTES = 128 * 128;          // one atom of 128 rows x 128 B
+    static constexpr int GBUF = (C <= 192) ? 2 : 1;    // C = 256: shared memory holds one hidden buffer only
+    static constexpr int SMEM = A_BYTES + 2 * W1_SLOT + 2 * W2_SLOT + GBUF * G_BYTES + 5 * C * 4 + 1024;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
+    using Cfg = MlpCfg<C>;
+    constexpr int KB1 = Cfg::KB1, NC = Cfg::NC, GBUF = Cfg::GBUF;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full, a_empty, acc2_full, acc2_empty;
+    __shared__ __align__(8) uint64_t w1_full[2], w1_empty[2], w2_full[2], w2_empty[2], acc1_full[2], acc1_empty[2];
+    __shared__ __align__(8) uint64_t g_full[2], g_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base;
+    const uint32_t sW1 = sA + Cfg::A_BYTES;
+    const uint32_t sW2 = sW1 + 2 * Cfg::W1_SLOT;
+    const uint32_t sG = sW2 + 2 * Cfg::W2_SLOT;
+    float* s_b1 = reinterpret_cast<float*>(smem_raw + (sG + GBUF * Cfg::G_BYTES - ptx::smem_u32(smem_raw)));
+    float* s_b2 = s_b1 + 4 * C;
+
+    for (int i = threadIdx.x; i < 4 * C; i += kMlpThreads) s_b1[i] = __ldg(p.b1 + i);
+    for (int i = threadIdx.x; i < C; i += kMlpThreads) s_b2[i] = __ldg(p.b2 + i);
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(ptx::smem_u32(&a_full), 1);
+        ptx::mbar_init(ptx::smem_u32(&a_empty), 1);
+        ptx::mbar_init(ptx::smem_u32(&acc2_full), 1);
+        ptx::mbar_init(ptx::smem_u32(&acc2_empty), 8);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&w1_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&w1_empty[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&w2_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&w2_empty[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&acc1_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&acc1_empty[i]), 8);
+            ptx::mbar_init(ptx::smem_u32(&g_full[i]), 8);
+            ptx::mbar_init(ptx::smem_u32(&g_empty[i]), 1);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&p.tmA);
+        ptx::prefetch_tmap(&p.tmW1);
+        ptx::prefetch_tmap(&p.tmW2);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&tmem_base_smem), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int m_tiles = p.m_tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (ptx::elect_one_sync()) {
+            uint32_t n = 0, t = 0;  // chunk / tile counters (ring slot = n & 1, phase = (n >> 1) & 1)
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+                ptx::mbar_wait(ptx::smem_u32(&a_empty), (t & 1u) ^ 1u);
+                const uint32_t ab = ptx::smem_u32(&a_full);
+                ptx::mbar_expect_tx(ab, Cfg::A_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < KB1; ++kb) ptx::tma_load_2d(sA + kb * 16384, &p.tmA, ab, kb * 64, tile * 128);
+                for (int j = 0; j < NC; ++j, ++n) {
+                    const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
+                    ptx::mbar_wait(ptx::smem_u32(&w1_empty[s]), ph ^ 1u);
+                    const uint32_t b1b = ptx::smem_u32(&w1_full[s]);
+                    ptx::mbar_expect_tx(b1b, Cfg::W1_SLOT);
+#pragma unroll
+                    for (int kb = 0; kb < KB1; ++kb)
+                        ptx::tma_load_2d(sW1 + s * Cfg::W1_SLOT + kb * 8192, &p.tmW1, b1b, kb * 64, j * 64);
+                    ptx::mbar_wait(ptx::smem_u32(&w2_empty[s]), ph ^ 1u);
+                    const uint32_t b2b = ptx::smem_u32(&w2_full[s]);
+                    ptx::mbar_expect_tx(b2b, Cfg::W2_SLOT);
+                    ptx::tma_load_2d(sW2 + s * Cfg::W2_SLOT, &p.tmW2, b2b, j * 64, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (ptx::elect_one_sync()) {
+            const uint32_t idesc1 = ptx::make_idesc_f16_m128(64), idesc2 = ptx::make_idesc_f16_m128(C);
+            uint32_t n1 = 0, n2 = 0, t = 0;
+            auto gemm1 = [&]() {
+                const uint32_t s = n1 & 1u, ph = (n1 >> 1) & 1u;
+                ptx::mbar_wait(ptx::smem_u32(&w1_full[s]), ph);
+                ptx::mbar_wait(ptx::smem_u32(&acc1_empty[s]), ph ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d = tmem_base + 256u + s * 64u;
+#pragma unroll
+                for (int kb = 0; kb < KB1; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16_ss(d, ptx::make_kmajor_desc(sA + kb * 16384 + k * 32, 128),
+                                         ptx::make_kmajor_desc(sW1 + s * Cfg::W1_SLOT + kb * 8192 + k * 32, 128), idesc1,
+                                         (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(ptx::smem_u32(&w1_empty[s]));
+                ptx::umma_commit(ptx::smem_u32(&acc1_full[s]));
+                ++n1;
+            };
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+                ptx::mbar_wait(ptx::smem_u32(&a_full), t & 1u);
+                gemm1();
+                for (int j = 0; j < NC; ++j, ++n2) {
+                    if (j + 1 < NC) gemm1();
+                    else ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
+                    const uint32_t s = n2 & 1u, ph = (n2 >> 1) & 1u;
+                    const uint32_t gs = n2 % GBUF, gph = (n2 / GBUF) & 1u;
+                    ptx::mbar_wait(ptx::smem_u32(&w2_full[s]), ph);
+                    ptx::mbar_wait(ptx::smem_u32(&g_full[gs]), gph);
+                    if (j == 0) ptx::mbar_wait(ptx::smem_u32(&acc2_empty), (t & 1u) ^ 1u);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16_ss(tmem_base, ptx::make_kmajor_desc(sG + gs * Cfg::G_BYTES + k * 32, 128),
+                                         ptx::make_kmajor_desc(sW2 + s * Cfg::W2_SLOT + k * 32, 128), idesc2,
+                                         (j | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(ptx::smem_u32(&w2_empty[s]));
+                    ptx::umma_commit(ptx::smem_u32(&g_empty[gs]));
+                    if (j == NC - 1) ptx::umma_commit(ptx::smem_u32(&acc2_full));
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps =====================
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // this thread's four 16-byte pieces of its row of G: chunk index (half * 4 + i) ^ (row & 7) inside the 128-byte row
+        const uint32_t g_row = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
+        uint32_t n = 0, t = 0;
+        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
+            for (int j = 0; j < NC; ++j, ++n) {
+                const uint32_t b = n & 1u, ph = (n >> 1) & 1u;
+                const uint32_t gs = n % GBUF, gph = (n / GBUF) & 1u;
+                ptx::mbar_wait(ptx::smem_u32(&acc1_full[b]), ph);
+                ptx::tc_fence_after();
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + 256u + b * 64u + static_cast<uint32_t>(half * 32), v);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc1_empty[b]));  // TMEM buffer free: GEMM1(j+2) may start
+                const float4* bb = reinterpret_cast<const float4*>(s_b1 + j * 64 + half * 32);
+                uint4 o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4 bv = bb[i * 2 + e];
+                        f[e * 4 + 0] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 0]) + bv.x);
+                        f[e * 4 + 1] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 1]) + bv.y);
+                        f[e * 4 + 2] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 2]) + bv.z);
+                        f[e * 4 + 3] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 3]) + bv.w);
+                    }
+                    __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+                    __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+                    o[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                      *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                }
+                ptx::mbar_wait(ptx::smem_u32(&g_empty[gs]), gph ^ 1u);  // GEMM2 of the chunk that used this buffer is done
+                const uint32_t gb = sG + gs * Cfg::G_BYTES + g_row;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t addr = gb + ((static_cast<uint32_t>(half * 4 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[i].x), "r"(o[i].y), "r"(o[i].z),
+                                 "r"(o[i].w)
+                                 : "memory");
+                }
+                ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&g_full[gs]));
+            }
+            // ---- final: x += acc2 + b2 (this warp: columns [half * C/2, (half + 1) * C/2) of its 32 rows)
+            ptx::mbar_wait(ptx::smem_u32(&acc2_full), t & 1u);
+            ptx::tc_fence_after();
+            const long long grow = static_cast<long long>(tile) * 128 + row;
+            float* xr = p.x + grow * C;
+            const bool valid = grow < p.M;
+#pragma unroll 1
+            for (int c = half * (C / 2); c < (half + 1) * (C / 2); c += 16) {
+                uint32_t v[16];
+                ptx::tmem_ld_32x32b_x16(t_lane + static_cast<uint32_t>(c), v);
+                ptx::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 r = *reinterpret_cast<const float4*>(xr + c + i * 4);
+                        const float4 bv = *reinterpret_cast<const float4*>(s_b2 + c + i * 4);
+                        r.x += __uint_as_float(v[i * 4 + 0]) + bv.x;
+                        r.y += __uint_as_float(v[i * 4 + 1]) + bv.y;
+                        r.z += __uint_as_float(v[i * 4 + 2]) + bv.z;
+                        r.w += __uint_as_float(v[i * 4 + 3]) + bv.w;
+                        *reinterpret_cast<float4*>(xr + c + i * 4) = r;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc2_empty));
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace dv
