@@ -50,6 +50,52 @@ __device__ __forceinline__ float apply_act(float x) {
     return x;
 }
 
+// The same GELU on two values at once with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot for
+// two IEEE operations, so the result is bit-identical to apply_act<ACT_GELU> on each value): 8.5 instead of 16 issue
+// slots per element in an epilogue that is issue-bound.  Returns gelu(x0 + b0), gelu(x1 + b1).
+namespace f32x2 {
+__device__ __forceinline__ uint64_t pk(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+}  // namespace f32x2
+__device__ __forceinline__ void gelu_bias_x2(float v0, float v1, float b0, float b1, float& y0, float& y1) {
+    using namespace f32x2;
+    float x0, x1;
+    upk(add(pk(v0, v1), pk(b0, b1)), x0, x1);
+    const uint64_t X = pk(x0, x1), AX = pk(fabsf(x0), fabsf(x1));
+    float u0, u1, t0, t1, s0, s1, e0, e1;
+    upk(fma(pk(0.23164189f, 0.23164189f), AX, pk(1.f, 1.f)), u0, u1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+    upk(mul(mul(X, pk(-0.72134752f, -0.72134752f)), X), s0, s1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+    const uint64_t T = pk(t0, t1);
+    uint64_t P = fma(T, pk(1.061405429f, 1.061405429f), pk(-1.453152027f, -1.453152027f));
+    P = fma(P, T, pk(1.421413741f, 1.421413741f));
+    P = fma(P, T, pk(-0.284496736f, -0.284496736f));
+    P = fma(P, T, pk(0.254829592f, 0.254829592f));
+    upk(fma(mul(AX, pk(-0.5f, -0.5f)), mul(mul(P, T), pk(e0, e1)), pk(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);
+}
+
 // Shape contract enforced by the planner (igemm_host.cu): out_ld, out_coff, res_ld and Cout are multiples
 // of 8 (fp16 out) / 4 (fp32 out), so the epilogue only ever issues 16-byte vector accesses, predicated
 // per vector on the channel bound.  Keeping the epilogue this small matters: it is executed by only four

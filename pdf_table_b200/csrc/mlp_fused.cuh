@@ -13,9 +13,11 @@
 //     GEMM2  acc2    += G[g][128 x 64] * W2[:, 64j .. 64j+64]^T       tcgen05.mma M128 N=C, K = 64
 //   final  x_tile    += acc2 + b2                                     fp32 residual stream, in place
 //
-// Warp roles (320 threads): warp 0 = TMA producer (h tile once per tile, W1 / W2 chunk rings, 2 deep), warp 1 = MMA
-// issuer, warps 2-9 = epilogue (two per TMEM lane quadrant, 32 of a chunk's 64 columns each).  The MMA warp issues
-// GEMM1(j+1) BEFORE GEMM2(j), so the tensor pipe works on the next chunk while the epilogue warps run GELU on this one.
+// Warp roles (608 threads): warp 0 = TMA producer of the h tile (once per tile) and the W1 chunk ring, warp 2 = TMA
+// producer of the W2 chunk ring (both rings 2 deep), warp 1 = MMA issuer, warps 3-18 = epilogue (four per TMEM lane quadrant, 16 of a chunk's 64 columns each; with eight epilogue warps
+// the kernel issued 1.3 instructions per clock -- two warps per scheduler cannot hide the MUFU / TMEM latencies of the
+// GELU, profiles/r1z_mlp_ncu.txt).  The MMA warp issues
+// GEMM1(j+2) BEFORE GEMM2(j), so the tensor pipe works on the next chunks while the epilogue warps run GELU on this one.
 // TMEM: acc2 at columns [0, C), acc1 double-buffered at 256 + 64 b.
 #pragma once
 #include <cuda.h>
@@ -25,7 +27,8 @@
 
 namespace dv {
 
-constexpr int kMlpThreads = 320;
+constexpr int kMlpEpiWarps = 16;  // four per TMEM lane quadrant, 16 of a chunk's 64 columns each
+constexpr int kMlpThreads = 96 + 32 * kMlpEpiWarps;
 
 template <int C>
 struct MlpCfg {
@@ -65,15 +68,15 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
         ptx::mbar_init(ptx::smem_u32(&a_full), 1);
         ptx::mbar_init(ptx::smem_u32(&a_empty), 1);
         ptx::mbar_init(ptx::smem_u32(&acc2_full), 1);
-        ptx::mbar_init(ptx::smem_u32(&acc2_empty), 8);
+        ptx::mbar_init(ptx::smem_u32(&acc2_empty), kMlpEpiWarps);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(&w1_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&w1_empty[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&w2_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&w2_empty[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&acc1_full[i]), 1);
-            ptx::mbar_init(ptx::smem_u32(&acc1_empty[i]), 8);
-            ptx::mbar_init(ptx::smem_u32(&g_full[i]), 8);
+            ptx::mbar_init(ptx::smem_u32(&acc1_empty[i]), kMlpEpiWarps);
+            ptx::mbar_init(ptx::smem_u32(&g_full[i]), kMlpEpiWarps);
             ptx::mbar_init(ptx::smem_u32(&g_empty[i]), 1);
         }
         ptx::fence_barrier_init();
@@ -92,7 +95,7 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
     const int m_tiles = p.m_tiles;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== h tile + W1 producer =====================
         if (ptx::elect_one_sync()) {
             uint32_t n = 0, t = 0;  // chunk / tile counters (ring slot = n & 1, phase = (n >> 1) & 1)
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
@@ -109,6 +112,19 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
 #pragma unroll
                     for (int kb = 0; kb < KB1; ++kb)
                         ptx::tma_load_2d(sW1 + s * Cfg::W1_SLOT + kb * 8192, &p.tmW1, b1b, kb * 64, j * 64);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== W2 producer =====================
+        // A separate thread: W2's slot is released by GEMM2(j) (end of chunk j's GELU) while W1's is released two chunks
+        // earlier; one in-order producer made every W1 load queue behind a W2 wait and the chunk period became one TMA
+        // latency + the GEMMs (2.9 us per chunk at C = 192, whatever the epilogue did).
+        if (ptx::elect_one_sync()) {
+            uint32_t n = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                for (int j = 0; j < NC; ++j, ++n) {
+                    const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
                     ptx::mbar_wait(ptx::smem_u32(&w2_empty[s]), ph ^ 1u);
                     const uint32_t b2b = ptx::smem_u32(&w2_full[s]);
                     ptx::mbar_expect_tx(b2b, Cfg::W2_SLOT);
@@ -140,10 +156,16 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
             };
             for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
                 ptx::mbar_wait(ptx::smem_u32(&a_full), t & 1u);
+                // GEMM1 runs two chunks ahead of GEMM2: its accumulator buffer is released as soon as the epilogue has pulled
+                // chunk j into registers, whereas GEMM2(j) has to wait for the end of that chunk's GELU.  (Issuing GEMM1(j+1)
+                // behind GEMM2(j-1) made every chunk's accumulator arrive one GEMM late: measured 0.11 -> 0.15 ms per layer.)
+                gemm1();
                 gemm1();
                 for (int j = 0; j < NC; ++j, ++n2) {
-                    if (j + 1 < NC) gemm1();
-                    else ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
+                    if (j + 2 < NC) {
+                        gemm1();
+                        if (j + 3 == NC) ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
+                    }
                     const uint32_t s = n2 & 1u, ph = (n2 >> 1) & 1u;
                     const uint32_t gs = n2 % GBUF, gph = (n2 / GBUF) & 1u;
                     ptx::mbar_wait(ptx::smem_u32(&w2_full[s]), ph);
@@ -162,37 +184,57 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
             }
         }
     } else {
-        // ===================== epilogue: 8 warps =====================
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        // ===================== epilogue: 16 warps =====================
+        const int q = warp & 3, part = (warp - 3) >> 2;
         const int row = q * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        // this thread's four 16-byte pieces of its row of G: chunk index (half * 4 + i) ^ (row & 7) inside the 128-byte row
+        // this thread's two 16-byte pieces of its row of G: chunk index (part * 2 + i) ^ (row & 7) inside the 128-byte row
         const uint32_t g_row = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
         uint32_t n = 0, t = 0;
+        constexpr int QC = C / 4;  // columns of the final update owned by this warp
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
-            for (int j = 0; j < NC; ++j, ++n) {
+            const long long grow = static_cast<long long>(tile) * 128 + row;
+            float* xr = p.x + grow * C + part * QC;
+            const bool valid = grow < p.M;
+            // the residual rows are needed ~NC chunks from now: start them towards L2 so the final update pays an L2
+            // hit instead of a DRAM round trip
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < QC * 4; k += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + k / 4));
+            }
+            uint32_t v[16];
+            {
                 const uint32_t b = n & 1u, ph = (n >> 1) & 1u;
-                const uint32_t gs = n % GBUF, gph = (n / GBUF) & 1u;
                 ptx::mbar_wait(ptx::smem_u32(&acc1_full[b]), ph);
                 ptx::tc_fence_after();
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_lane + 256u + b * 64u + static_cast<uint32_t>(half * 32), v);
+                ptx::tmem_ld_32x32b_x16(t_lane + 256u + b * 64u + static_cast<uint32_t>(part * 16), v);
+            }
+            for (int j = 0; j < NC; ++j, ++n) {
+                const uint32_t b = n & 1u;
+                const uint32_t gs = n % GBUF, gph = (n / GBUF) & 1u;
                 ptx::tmem_ld_wait();
+                float a[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(v[i]);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc1_empty[b]));  // TMEM buffer free: GEMM1(j+2) may start
-                const float4* bb = reinterpret_cast<const float4*>(s_b1 + j * 64 + half * 32);
-                uint4 o[4];
+                if (j + 1 < NC) {  // the next chunk's accumulator is complete already: fetch it under the GELU math
+                    const uint32_t nb = (n + 1) & 1u, nph = ((n + 1) >> 1) & 1u;
+                    ptx::mbar_wait(ptx::smem_u32(&acc1_full[nb]), nph);
+                    ptx::tc_fence_after();
+                    ptx::tmem_ld_32x32b_x16(t_lane + 256u + nb * 64u + static_cast<uint32_t>(part * 16), v);
+                }
+                const float4* bb = reinterpret_cast<const float4*>(s_b1 + j * 64 + part * 16);
+                uint4 o[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float4 bv = bb[i * 2 + e];
-                        f[e * 4 + 0] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 0]) + bv.x);
-                        f[e * 4 + 1] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 1]) + bv.y);
-                        f[e * 4 + 2] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 2]) + bv.z);
-                        f[e * 4 + 3] = apply_act<ACT_GELU>(__uint_as_float(v[i * 8 + e * 4 + 3]) + bv.w);
+                        gelu_bias_x2(a[i * 8 + e * 4 + 0], a[i * 8 + e * 4 + 1], bv.x, bv.y, f[e * 4 + 0], f[e * 4 + 1]);
+                        gelu_bias_x2(a[i * 8 + e * 4 + 2], a[i * 8 + e * 4 + 3], bv.z, bv.w, f[e * 4 + 2], f[e * 4 + 3]);
                     }
                     __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
                     __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
@@ -202,8 +244,8 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                 ptx::mbar_wait(ptx::smem_u32(&g_empty[gs]), gph ^ 1u);  // GEMM2 of the chunk that used this buffer is done
                 const uint32_t gb = sG + gs * Cfg::G_BYTES + g_row;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t addr = gb + ((static_cast<uint32_t>(half * 4 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t addr = gb + ((static_cast<uint32_t>(part * 2 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[i].x), "r"(o[i].y), "r"(o[i].z),
                                  "r"(o[i].w)
                                  : "memory");
@@ -212,27 +254,38 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&g_full[gs]));
             }
-            // ---- final: x += acc2 + b2 (this warp: columns [half * C/2, (half + 1) * C/2) of its 32 rows)
+            // ---- final: x += acc2 + b2 (this warp: columns [part * C/4, (part + 1) * C/4) of its 32 rows); the residual
+            // loads are all in flight before the wait for the last GEMM2
+            constexpr int BATCH = QC > 32 ? QC / 2 : QC;  // 24 / 24 / 32 columns at a time (register budget: 96 per thread)
+            float4 r[BATCH / 4];
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < BATCH / 4; ++i) r[i] = *reinterpret_cast<const float4*>(xr + i * 4);
+            }
             ptx::mbar_wait(ptx::smem_u32(&acc2_full), t & 1u);
             ptx::tc_fence_after();
-            const long long grow = static_cast<long long>(tile) * 128 + row;
-            float* xr = p.x + grow * C;
-            const bool valid = grow < p.M;
-#pragma unroll 1
-            for (int c = half * (C / 2); c < (half + 1) * (C / 2); c += 16) {
-                uint32_t v[16];
-                ptx::tmem_ld_32x32b_x16(t_lane + static_cast<uint32_t>(c), v);
+#pragma unroll
+            for (int c0 = 0; c0 < QC; c0 += BATCH) {
+                if (c0 > 0 && valid) {
+#pragma unroll
+                    for (int i = 0; i < BATCH / 4; ++i) r[i] = *reinterpret_cast<const float4*>(xr + c0 + i * 4);
+                }
+                // all of the batch's accumulator columns with ONE wait (one TMEM round trip per 8 columns before: 27 % of the
+                // kernel's samples sat on these loads, profiles/r1z_mlp_ncu.txt)
+                uint32_t w[BATCH / 8][8];
+#pragma unroll
+                for (int c = 0; c < BATCH; c += 8) ptx::tmem_ld_32x32b_x8(t_lane + static_cast<uint32_t>(part * QC + c0 + c), w[c / 8]);
                 ptx::tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 r = *reinterpret_cast<const float4*>(xr + c + i * 4);
-                        const float4 bv = *reinterpret_cast<const float4*>(s_b2 + c + i * 4);
-                        r.x += __uint_as_float(v[i * 4 + 0]) + bv.x;
-                        r.y += __uint_as_float(v[i * 4 + 1]) + bv.y;
-                        r.z += __uint_as_float(v[i * 4 + 2]) + bv.z;
-                        r.w += __uint_as_float(v[i * 4 + 3]) + bv.w;
-                        *reinterpret_cast<float4*>(xr + c + i * 4) = r;
+                    for (int i = 0; i < BATCH / 4; ++i) {
+                        float4 rr = r[i];
+                        const float4 bv = *reinterpret_cast<const float4*>(s_b2 + part * QC + c0 + i * 4);
+                        rr.x += __uint_as_float(w[i / 2][(i & 1) * 4 + 0]) + bv.x;
+                        rr.y += __uint_as_float(w[i / 2][(i & 1) * 4 + 1]) + bv.y;
+                        rr.z += __uint_as_float(w[i / 2][(i & 1) * 4 + 2]) + bv.z;
+                        rr.w += __uint_as_float(w[i / 2][(i & 1) * 4 + 3]) + bv.w;
+                        *reinterpret_cast<float4*>(xr + c0 + i * 4) = rr;
                     }
                 }
             }
