@@ -484,8 +484,8 @@ int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops
 
 // ------------------------------------------------------------------------------------------------ mlp_fused_tcgen05
 bool mlp_fused_supported(int C) {
-    static const bool on = !(getenv("DV_MLP_FUSED") && atoi(getenv("DV_MLP_FUSED")) == 0);
-    return on && (C == 96 || C == 192 || C == 256);
+    const char* s = getenv("DV_MLP_FUSED");  // read at plan time (not cached): the A/B test builds one engine each way
+    return !(s && atoi(s) == 0) && (C == 96 || C == 192 || C == 256);
 }
 
 template <int C>

@@ -27,7 +27,7 @@
 
 namespace dv {
 
-constexpr int kMlpEpiWarps = 16;  // four per TMEM lane quadrant, 16 of a chunk's 64 columns each
+constexpr int kMlpEpiWarps = 16;  // two groups of eight: two warps per TMEM lane quadrant, 32 of a chunk's 64 columns each
 constexpr int kMlpThreads = 96 + 32 * kMlpEpiWarps;
 
 template <int C>
@@ -75,8 +75,8 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
             ptx::mbar_init(ptx::smem_u32(&w2_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&w2_empty[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&acc1_full[i]), 1);
-            ptx::mbar_init(ptx::smem_u32(&acc1_empty[i]), kMlpEpiWarps);
-            ptx::mbar_init(ptx::smem_u32(&g_full[i]), kMlpEpiWarps);
+            ptx::mbar_init(ptx::smem_u32(&acc1_empty[i]), kMlpEpiWarps / 2);
+            ptx::mbar_init(ptx::smem_u32(&g_full[i]), kMlpEpiWarps / 2);
             ptx::mbar_init(ptx::smem_u32(&g_empty[i]), 1);
         }
         ptx::fence_barrier_init();
@@ -167,9 +167,9 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                         if (j + 3 == NC) ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
                     }
                     const uint32_t s = n2 & 1u, ph = (n2 >> 1) & 1u;
-                    const uint32_t gs = n2 % GBUF, gph = (n2 / GBUF) & 1u;
+                    const uint32_t gs = n2 % GBUF;  // hidden buffer; its barriers are indexed by chunk parity (= epilogue group)
                     ptx::mbar_wait(ptx::smem_u32(&w2_full[s]), ph);
-                    ptx::mbar_wait(ptx::smem_u32(&g_full[gs]), gph);
+                    ptx::mbar_wait(ptx::smem_u32(&g_full[s]), ph);
                     if (j == 0) ptx::mbar_wait(ptx::smem_u32(&acc2_empty), (t & 1u) ^ 1u);
                     ptx::tc_fence_after();
 #pragma unroll
@@ -178,19 +178,25 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                                          ptx::make_kmajor_desc(sW2 + s * Cfg::W2_SLOT + k * 32, 128), idesc2,
                                          (j | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(ptx::smem_u32(&w2_empty[s]));
-                    ptx::umma_commit(ptx::smem_u32(&g_empty[gs]));
+                    ptx::umma_commit(ptx::smem_u32(&g_empty[s]));
                     if (j == NC - 1) ptx::umma_commit(ptx::smem_u32(&acc2_full));
                 }
             }
         }
     } else {
-        // ===================== epilogue: 16 warps =====================
-        const int q = warp & 3, part = (warp - 3) >> 2;
+        // ===================== epilogue: 16 warps in two groups =====================
+        // Group g (two warps per TMEM lane quadrant, 32 columns each) owns the chunks j = g (mod 2), i.e. accumulator
+        // buffer g and (GBUF = 2) hidden buffer g.  The groups run half a chunk out of step, so one group's barrier
+        // waits, TMEM round trip, shared-memory stores and proxy fence are covered by the other group's GELU math: with
+        // all warps walking every chunk together those phases were exposed on every scheduler at once (issue slots
+        // 44 % used, profiles/r1z_mlp_ncu.txt).
+        const int q = warp & 3, sub = (warp - 3) >> 2, grp = sub & 1, half = sub >> 1;
+        const int part = sub;  // column quarter of the final update
         const int row = q * 32 + lane;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        // this thread's two 16-byte pieces of its row of G: chunk index (part * 2 + i) ^ (row & 7) inside the 128-byte row
+        // this thread's four 16-byte pieces of its row of G: chunk index (half * 4 + i) ^ (row & 7) inside the 128-byte row
         const uint32_t g_row = static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
-        uint32_t n = 0, t = 0;
+        uint32_t t = 0;
         constexpr int QC = C / 4;  // columns of the final update owned by this warp
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
             const long long grow = static_cast<long long>(tile) * 128 + row;
@@ -202,57 +208,52 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
 #pragma unroll
                 for (int k = 0; k < QC * 4; k += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + k / 4));
             }
-            uint32_t v[16];
-            {
+            for (int j = grp; j < NC; j += 2) {
+                const uint32_t n = t * NC + j;  // global chunk counter (NC is even: n = grp mod 2)
                 const uint32_t b = n & 1u, ph = (n >> 1) & 1u;
+                const uint32_t gs = n % GBUF;
                 ptx::mbar_wait(ptx::smem_u32(&acc1_full[b]), ph);
                 ptx::tc_fence_after();
-                ptx::tmem_ld_32x32b_x16(t_lane + 256u + b * 64u + static_cast<uint32_t>(part * 16), v);
-            }
-            for (int j = 0; j < NC; ++j, ++n) {
-                const uint32_t b = n & 1u;
-                const uint32_t gs = n % GBUF, gph = (n / GBUF) & 1u;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(t_lane + 256u + b * 64u + static_cast<uint32_t>(half * 32), v);
                 ptx::tmem_ld_wait();
-                float a[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(v[i]);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc1_empty[b]));  // TMEM buffer free: GEMM1(j+2) may start
-                if (j + 1 < NC) {  // the next chunk's accumulator is complete already: fetch it under the GELU math
-                    const uint32_t nb = (n + 1) & 1u, nph = ((n + 1) >> 1) & 1u;
-                    ptx::mbar_wait(ptx::smem_u32(&acc1_full[nb]), nph);
-                    ptx::tc_fence_after();
-                    ptx::tmem_ld_32x32b_x16(t_lane + 256u + nb * 64u + static_cast<uint32_t>(part * 16), v);
-                }
-                const float4* bb = reinterpret_cast<const float4*>(s_b1 + j * 64 + part * 16);
-                uint4 o[2];
+                const float4* bb = reinterpret_cast<const float4*>(s_b1 + j * 64 + half * 32);
+                uint4 o[4];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float4 bv = bb[i * 2 + e];
-                        gelu_bias_x2(a[i * 8 + e * 4 + 0], a[i * 8 + e * 4 + 1], bv.x, bv.y, f[e * 4 + 0], f[e * 4 + 1]);
-                        gelu_bias_x2(a[i * 8 + e * 4 + 2], a[i * 8 + e * 4 + 3], bv.z, bv.w, f[e * 4 + 2], f[e * 4 + 3]);
+                        gelu_bias_x2(__uint_as_float(v[i * 8 + e * 4 + 0]), __uint_as_float(v[i * 8 + e * 4 + 1]), bv.x, bv.y,
+                                     f[e * 4 + 0], f[e * 4 + 1]);
+                        gelu_bias_x2(__uint_as_float(v[i * 8 + e * 4 + 2]), __uint_as_float(v[i * 8 + e * 4 + 3]), bv.z, bv.w,
+                                     f[e * 4 + 2], f[e * 4 + 3]);
                     }
                     __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
                     __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
                     o[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
                 }
-                ptx::mbar_wait(ptx::smem_u32(&g_empty[gs]), gph ^ 1u);  // GEMM2 of the chunk that used this buffer is done
+                // GEMM2 of the chunk that last used this hidden buffer must be done.  The g barriers are indexed by chunk
+                // parity; with two buffers that is this group's own barrier (chunk n - 2), with one buffer the other
+                // group's (chunk n - 1) -- either way a group waits on consecutive phases of one barrier, never skipping one.
+                if constexpr (GBUF == 2) ptx::mbar_wait(ptx::smem_u32(&g_empty[b]), ph ^ 1u);
+                else if (n > 0) ptx::mbar_wait(ptx::smem_u32(&g_empty[b ^ 1u]), ((n - 1) >> 1) & 1u);
                 const uint32_t gb = sG + gs * Cfg::G_BYTES + g_row;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t addr = gb + ((static_cast<uint32_t>(part * 2 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t addr = gb + ((static_cast<uint32_t>(half * 4 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[i].x), "r"(o[i].y), "r"(o[i].z),
                                  "r"(o[i].w)
                                  : "memory");
                 }
                 ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&g_full[gs]));
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&g_full[b]));
             }
             // ---- final: x += acc2 + b2 (this warp: columns [part * C/4, (part + 1) * C/4) of its 32 rows); the residual
             // loads are all in flight before the wait for the last GEMM2

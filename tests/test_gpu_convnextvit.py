@@ -134,3 +134,25 @@ def test_convnextvit_u8_preprocess_fused(rec):
         eng.sync()
         np.testing.assert_array_equal(logits_a.cpu().numpy(), logits_b.cpu().numpy())
         np.testing.assert_array_equal(ids_a.cpu().numpy(), ids_b.cpu().numpy())
+
+
+def test_fused_mlp_equals_two_gemm_path(monkeypatch):
+    """mlp_fused_tcgen05 (pwconv1 -> GELU -> pwconv2 + residual in one kernel) performs the same fp16 x fp16 -> fp32 MMAs,
+    the same GELU and the same fp16 rounding of the hidden tensor as the two conv_igemm_tcgen05 launches it replaces:
+    the logits must be bit-identical, including a ragged last 128-token tile (5 crops -> 1125 / 9000 rows)."""
+    sd = synth.convnext_vit_state_dict(0)
+    blob = weights.pack_convnext_vit(sd)
+    rng = np.random.default_rng(11)
+    chunks = torch.from_numpy(rng.random((15, 3, 32, 300), dtype=np.float32)).cuda()
+    out = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("DV_MLP_FUSED", fused)
+        eng = Engine("convnext_vit", blob)
+        eng.profile_begin()
+        ids, logits = eng.convnextvit_forward(chunks, return_logits=True)
+        kernels = {r["kernel"] for r in eng.profile_report()}
+        assert ("mlp_fused_tcgen05" in kernels) == (fused == "1")
+        out[fused] = (ids.cpu().numpy(), logits.cpu().numpy())
+        eng.close()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert np.array_equal(out["0"][1], out["1"][1])

@@ -12,4 +12,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$
 if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 54 -c 27 -o gpurun_out/${TAG}_conv -f python tools/probe_dbnet.py 32 960 1 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_fused -s 0 -c 7 -o gpurun_out/${TAG}_mlp -f python tools/layer_profile.py rec > gpurun_out/${TAG}_ncu_mlp.log 2>&1; echo "ncu mlp rc=$?"
 fi
