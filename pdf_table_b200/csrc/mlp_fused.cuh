@@ -14,10 +14,8 @@
 //   final  x_tile    += acc2 + b2                                     fp32 residual stream, in place
 //
 // Warp roles (608 threads): warp 0 = TMA producer of the h tile (once per tile) and the W1 chunk ring, warp 2 = TMA
-// producer of the W2 chunk ring (both rings 2 deep), warp 1 = MMA issuer, warps 3-18 = epilogue (four per TMEM lane quadrant, 16 of a chunk's 64 columns each; with eight epilogue warps
-// the kernel issued 1.3 instructions per clock -- two warps per scheduler cannot hide the MUFU / TMEM latencies of the
-// GELU, profiles/r1z_mlp_ncu.txt).  The MMA warp issues
-// GEMM1(j+2) BEFORE GEMM2(j), so the tensor pipe works on the next chunks while the epilogue warps run GELU on this one.
+// producer of the W2 chunk ring (both rings 2 deep), warp 1 = MMA issuer (event-driven: whichever of GEMM1(next) /
+// GEMM2(next) has its operands first), warps 3-18 = epilogue in two groups of eight that alternate chunks.
 // TMEM: acc2 at columns [0, C), acc1 double-buffered at 256 + 64 b.
 #pragma once
 #include <cuda.h>
@@ -136,51 +134,55 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
         // ===================== MMA issuer =====================
         if (ptx::elect_one_sync()) {
             const uint32_t idesc1 = ptx::make_idesc_f16_m128(64), idesc2 = ptx::make_idesc_f16_m128(C);
-            uint32_t n1 = 0, n2 = 0, t = 0;
-            auto gemm1 = [&]() {
-                const uint32_t s = n1 & 1u, ph = (n1 >> 1) & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&w1_full[s]), ph);
-                ptx::mbar_wait(ptx::smem_u32(&acc1_empty[s]), ph ^ 1u);
-                ptx::tc_fence_after();
-                const uint32_t d = tmem_base + 256u + s * 64u;
+            // Event-driven issue: GEMM1(n1) goes out as soon as its weights and its accumulator buffer are there (the buffer
+            // is released when the epilogue has pulled chunk n1 - 2 into registers), GEMM2(n2) as soon as its hidden tile is
+            // written -- whichever is ready first.  A fixed program order (GEMM1(j+2) behind GEMM2(j-1)) left the epilogue
+            // waiting on acc1_full for 20 % of its time (profiles/r1z_mlp_ncu.txt, v6).
+            const uint32_t my_tiles = m_tiles > static_cast<int>(blockIdx.x) ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+            const uint32_t total = my_tiles * NC;
+            uint32_t n1 = 0, n2 = 0, spins = 0;
+            while (n2 < total) {
+                bool did = false;
+                if (n1 < total) {
+                    const uint32_t s = n1 & 1u, ph = (n1 >> 1) & 1u, j1 = n1 % NC, t1 = n1 / NC;
+                    if (ptx::mbar_test_wait(ptx::smem_u32(&w1_full[s]), ph) && ptx::mbar_test_wait(ptx::smem_u32(&acc1_empty[s]), ph ^ 1u) &&
+                        (j1 != 0 || ptx::mbar_test_wait(ptx::smem_u32(&a_full), t1 & 1u))) {
+                        ptx::tc_fence_after();
+                        const uint32_t d = tmem_base + 256u + s * 64u;
 #pragma unroll
-                for (int kb = 0; kb < KB1; ++kb)
+                        for (int kb = 0; kb < KB1; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16_ss(d, ptx::make_kmajor_desc(sA + kb * 16384 + k * 32, 128),
-                                         ptx::make_kmajor_desc(sW1 + s * Cfg::W1_SLOT + kb * 8192 + k * 32, 128), idesc1,
-                                         (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(ptx::smem_u32(&w1_empty[s]));
-                ptx::umma_commit(ptx::smem_u32(&acc1_full[s]));
-                ++n1;
-            };
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++t) {
-                ptx::mbar_wait(ptx::smem_u32(&a_full), t & 1u);
-                // GEMM1 runs two chunks ahead of GEMM2: its accumulator buffer is released as soon as the epilogue has pulled
-                // chunk j into registers, whereas GEMM2(j) has to wait for the end of that chunk's GELU.  (Issuing GEMM1(j+1)
-                // behind GEMM2(j-1) made every chunk's accumulator arrive one GEMM late: measured 0.11 -> 0.15 ms per layer.)
-                gemm1();
-                gemm1();
-                for (int j = 0; j < NC; ++j, ++n2) {
-                    if (j + 2 < NC) {
-                        gemm1();
-                        if (j + 3 == NC) ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_f16_ss(d, ptx::make_kmajor_desc(sA + kb * 16384 + k * 32, 128),
+                                                 ptx::make_kmajor_desc(sW1 + s * Cfg::W1_SLOT + kb * 8192 + k * 32, 128), idesc1,
+                                                 (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit(ptx::smem_u32(&w1_empty[s]));
+                        ptx::umma_commit(ptx::smem_u32(&acc1_full[s]));
+                        if (j1 == NC - 1) ptx::umma_commit(ptx::smem_u32(&a_empty));  // every GEMM1 of this tile has been issued
+                        ++n1;
+                        did = true;
                     }
-                    const uint32_t s = n2 & 1u, ph = (n2 >> 1) & 1u;
-                    const uint32_t gs = n2 % GBUF;  // hidden buffer; its barriers are indexed by chunk parity (= epilogue group)
-                    ptx::mbar_wait(ptx::smem_u32(&w2_full[s]), ph);
-                    ptx::mbar_wait(ptx::smem_u32(&g_full[s]), ph);
-                    if (j == 0) ptx::mbar_wait(ptx::smem_u32(&acc2_empty), (t & 1u) ^ 1u);
-                    ptx::tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16_ss(tmem_base, ptx::make_kmajor_desc(sG + gs * Cfg::G_BYTES + k * 32, 128),
-                                         ptx::make_kmajor_desc(sW2 + s * Cfg::W2_SLOT + k * 32, 128), idesc2,
-                                         (j | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(ptx::smem_u32(&w2_empty[s]));
-                    ptx::umma_commit(ptx::smem_u32(&g_empty[s]));
-                    if (j == NC - 1) ptx::umma_commit(ptx::smem_u32(&acc2_full));
                 }
+                if (n2 < n1) {
+                    const uint32_t s = n2 & 1u, ph = (n2 >> 1) & 1u, j2 = n2 % NC, t2 = n2 / NC;
+                    const uint32_t gs = n2 % GBUF;  // hidden buffer; its barriers are indexed by chunk parity (= epilogue group)
+                    if (ptx::mbar_test_wait(ptx::smem_u32(&w2_full[s]), ph) && ptx::mbar_test_wait(ptx::smem_u32(&g_full[s]), ph) &&
+                        (j2 != 0 || ptx::mbar_test_wait(ptx::smem_u32(&acc2_empty), (t2 & 1u) ^ 1u))) {
+                        ptx::tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_f16_ss(tmem_base, ptx::make_kmajor_desc(sG + gs * Cfg::G_BYTES + k * 32, 128),
+                                             ptx::make_kmajor_desc(sW2 + s * Cfg::W2_SLOT + k * 32, 128), idesc2,
+                                             (j2 | static_cast<uint32_t>(k)) != 0 ? 1u : 0u);
+                        ptx::umma_commit(ptx::smem_u32(&w2_empty[s]));
+                        ptx::umma_commit(ptx::smem_u32(&g_empty[s]));
+                        if (j2 == NC - 1) ptx::umma_commit(ptx::smem_u32(&acc2_full));
+                        ++n2;
+                        did = true;
+                    }
+                }
+                if (did) spins = 0;
+                else if (++spins > (1u << 28)) __trap();  // protocol bug: fail the launch instead of hanging the GPU
             }
         }
     } else {
