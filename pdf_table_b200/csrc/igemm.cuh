@@ -138,6 +138,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     __shared__ uint32_t tmem_base_smem;
     __shared__ int4 s_delta[kMaxKB];
     __shared__ __align__(16) float s_bias[kBiasSmem];  // the layer's bias, staged once (see the epilogue)
+    __shared__ float s_argv[ARGMAX ? 128 : 1];         // arg-max epilogue: the second warp's candidate per row
+    __shared__ int s_argi[ARGMAX ? 128 : 1];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -367,14 +369,14 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                    static_cast<uint32_t>(acc) * 256u;
-            // the arg-max epilogue needs one thread to see all columns of its row in ascending order: one warp per quadrant
-            const bool idle = ARGMAX && half == 1;
+            // arg-max epilogue: each of the two warps of a quadrant keeps the first maximum of ITS 32-column chunks (visited
+            // in ascending order); the pair is merged after the last n-tile (ties -> lower index = torch.argmax)
             // Software-pipelined over 32-column chunks: the tcgen05.ld of the next chunk is in flight while the current
             // chunk's bias / residual / activation / stores issue (two warps per scheduler cannot hide it otherwise).
-            constexpr int kStep = ARGMAX ? 32 : 64;
-            int c = ARGMAX ? 0 : half * 32;
+            constexpr int kStep = 64;
+            int c = half * 32;
             uint32_t v[32];
-            bool have = !idle && c < BLOCK_N && n_tile * BLOCK_N + c < Cout;  // warp-uniform
+            bool have = c < BLOCK_N && n_tile * BLOCK_N + c < Cout;  // warp-uniform
             if (have) ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
             while (have) {
                 const int col0 = n_tile * BLOCK_N + c;
@@ -517,9 +519,23 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 }
             }
             if constexpr (ARGMAX) {
-                if (n_tile == p.n_tiles - 1 && valid && !idle) {
-                    p.arg_out[pix] = best_i;
-                    if (p.max_out != nullptr) p.max_out[pix] = best_v;
+                if (n_tile == p.n_tiles - 1) {
+                    if (half == 1) {
+                        s_argv[row] = best_v;
+                        s_argi[row] = best_i;
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of quadrant q
+                    if (half == 0 && valid) {
+                        const float ov = s_argv[row];
+                        const int oi = s_argi[row];
+                        if (ov > best_v || (ov == best_v && oi < best_i)) {
+                            best_v = ov;
+                            best_i = oi;
+                        }
+                        p.arg_out[pix] = best_i;
+                        if (p.max_out != nullptr) p.max_out[pix] = best_v;
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // s_arg* may be rewritten for the next m-tile
                 }
             }
             ptx::tc_fence_before();

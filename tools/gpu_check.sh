@@ -11,6 +11,12 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/${TAG}_bench_ref.json
 if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 54 -c 27 -o gpurun_out/${TAG}_conv -f python tools/probe_dbnet.py 32 960 1 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_fused -s 0 -c 7 -o gpurun_out/${TAG}_mlp -f python tools/layer_profile.py rec > gpurun_out/${TAG}_ncu_mlp.log 2>&1; echo "ncu mlp rc=$?"
+# full captures: summarised ON THE BOX (raw metric CSV + headline / wait-site text), the .ncu-rep files stay there -- gpurun
+# merges at most 64 MiB back and 30 full-set kernels with sources are more than that
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 54 -c 27 -o /tmp/${TAG}_conv -f python tools/probe_dbnet.py 32 960 1 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu -i /tmp/${TAG}_conv.ncu-rep --page raw --csv > gpurun_out/${TAG}_conv_full.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_fused -s 0 -c 7 -o /tmp/${TAG}_mlp -f python tools/layer_profile.py rec > gpurun_out/${TAG}_ncu_mlp.log 2>&1; echo "ncu mlp rc=$?"
+ncu -i /tmp/${TAG}_mlp.ncu-rep --page raw --csv > gpurun_out/${TAG}_mlp_full.csv 2>/dev/null
+{ python tools/ncu_keys.py /tmp/${TAG}_mlp.ncu-rep 4; python tools/ncu_sync_sites.py /tmp/${TAG}_mlp.ncu-rep 4 60; } > gpurun_out/${TAG}_mlp_ncu.txt 2>&1
 fi
+du -sm gpurun_out | tail -1
