@@ -91,39 +91,18 @@ k_cnv_patchify_ln(const void* __restrict__ in_raw, int crop_w, int B, const floa
 constexpr int kStrip = 15;  // 75 = 5 strips
 constexpr int kTileW = kStrip + 6;
 
-// Two channels per thread on the packed fp32 instructions (fma.rn.f32x2 = two IEEE FMAs in one issue slot, bit-identical
-// to two fmaf): the scalar version executed 751 FFMA + ~400 other instructions per thread and ran at 72 % of what its
-// instruction mix allows (33.7 of 47 TFLOP/s, issue-bound); with pairs the same thread count of instructions covers two
-// channels, so the FP32 pipe rather than the scheduler becomes the limit.
-__device__ __forceinline__ uint64_t f2_as_u64(float2 v) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
-    return r;
-}
-__device__ __forceinline__ float2 u64_as_f2(uint64_t v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 template <int C, int H>
-__global__ void __launch_bounds__(C* H / 2)
+__global__ void __launch_bounds__(C* H)
 k_dwconv7_ln(const float* __restrict__ x, const float* __restrict__ w /*[49][C]*/, const float* __restrict__ bias,
              const float* __restrict__ lnw, const float* __restrict__ lnb, __half* __restrict__ out) {
     extern __shared__ float tile[];  // [H][kTileW][C]
-    constexpr int NT = C * H / 2;
     const int b = blockIdx.x / 5;
     const int x0 = (blockIdx.x - b * 5) * kStrip;
     const int tid = threadIdx.x;
     const float* xb = x + static_cast<long long>(b) * H * 75 * C;
     // ---- stage (zero-filled outside the image); C % 4 == 0 -> float4
     constexpr int C4 = C / 4;
-    for (int i = tid; i < H * kTileW * C4; i += NT) {
+    for (int i = tid; i < H * kTileW * C4; i += C * H) {
         const int c4 = i % C4;
         const int col = (i / C4) % kTileW;
         const int row = i / (C4 * kTileW);
@@ -133,38 +112,36 @@ k_dwconv7_ln(const float* __restrict__ x, const float* __restrict__ w /*[49][C]*
         *reinterpret_cast<float4*>(tile + (static_cast<long long>(row) * kTileW + col) * C + c4 * 4) = v;
     }
     __syncthreads();
-    constexpr int C2 = C / 2;
-    const int c2 = tid % C2;  // channels 2 c2, 2 c2 + 1
-    const int y = tid / C2;
-    uint64_t acc[kStrip];
-    const uint64_t bv = f2_as_u64(__ldg(reinterpret_cast<const float2*>(bias) + c2));
+    const int c = tid % C;
+    const int y = tid / C;
+    float acc[kStrip];
+    const float bv = bias[c];
 #pragma unroll
     for (int i = 0; i < kStrip; ++i) acc[i] = bv;
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
         const int iy = y + r - 3;
         if (iy < 0 || iy >= H) continue;  // zero padding rows
-        uint64_t wr[7];
+        float wr[7];
 #pragma unroll
-        for (int s = 0; s < 7; ++s) wr[s] = f2_as_u64(__ldg(reinterpret_cast<const float2*>(w + (r * 7 + s) * C) + c2));
-        const float2* trow = reinterpret_cast<const float2*>(tile + static_cast<long long>(iy) * kTileW * C) + c2;
+        for (int s = 0; s < 7; ++s) wr[s] = __ldg(w + (r * 7 + s) * C + c);
+        const float* trow = tile + static_cast<long long>(iy) * kTileW * C + c;
 #pragma unroll
         for (int col = 0; col < kTileW; ++col) {
-            const uint64_t v = f2_as_u64(trow[col * C2]);
+            const float v = trow[col * C];
 #pragma unroll
             for (int s = 0; s < 7; ++s) {
                 const int o = col - s;  // output column fed by tile column `col` through tap s
-                if (o >= 0 && o < kStrip) acc[o] = fma_f32x2(v, wr[s], acc[o]);
+                if (o >= 0 && o < kStrip) acc[o] = fmaf(v, wr[s], acc[o]);
             }
         }
     }
     __syncthreads();  // everyone is done reading the tile -> reuse it as [H][kStrip][C] conv outputs
 #pragma unroll
-    for (int i = 0; i < kStrip; ++i)
-        *reinterpret_cast<float2*>(tile + (static_cast<long long>(y) * kStrip + i) * C + 2 * c2) = u64_as_f2(acc[i]);
+    for (int i = 0; i < kStrip; ++i) tile[(static_cast<long long>(y) * kStrip + i) * C + c] = acc[i];
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = NT / 32;
+    constexpr int NW = C * H / 32;
     constexpr int CPL = C / 32;
     for (int p = warp; p < H * kStrip; p += NW) {
         const float* tp = tile + static_cast<long long>(p) * C;
@@ -492,7 +469,7 @@ int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, 
     }
     const double elems = static_cast<double>(B) * H * 75 * C;
     e->launch_begin("k_dwconv7_ln", layer, 2.0 * 49 * elems, elems * (4 + 2));
-    k_dwconv7_ln<C, H><<<B * 5, C * H / 2, smem, e->stream>>>(x, w, b, lnw, lnb, out);
+    k_dwconv7_ln<C, H><<<B * 5, C * H, smem, e->stream>>>(x, w, b, lnw, lnb, out);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
