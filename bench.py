@@ -44,6 +44,23 @@ STD = (0.229, 0.224, 0.225)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def measured_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu pass over this same
+    bench command (profiles/*_dram_traffic.json, the newest file); None when no capture covers the kernel."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_dram_traffic.json")))
+    for f in reversed(files):
+        try:
+            with open(f) as fh:
+                k = json.load(fh)["kernels"].get(kernel)
+        except (OSError, ValueError, KeyError):
+            continue
+        if k:
+            return k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"], "profiles/" + os.path.basename(f)
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -587,17 +604,20 @@ def main():
         tot_ms = sum(k["ms"] for k in agg.values())
         top = max(agg, key=lambda k: agg[k]["ms"])
         tk = agg[top]
+        traffic, traffic_src = measured_traffic(top)
         if tk["flops"] > 0:
             ach = tk["flops"] / (tk["ms"] / 1e3) / 1e12
             roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": tk["bytes"] / tk["n"],
                     "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                     "launches": tk["n"], "avg_launch_ms": tk["ms"] / tk["n"], "share_of_step": tk["ms"] / tot_ms,
                     "hbm_achieved_gbs": tk["bytes"] / (tk["ms"] / 1e3) / 1e9}
         else:
             ach = tk["bytes"] / (tk["ms"] / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src, "launches": tk["n"],
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": tk["bytes"] / tk["n"], "peak_source": peak_src, "launches": tk["n"],
                     "avg_launch_ms": tk["ms"] / tk["n"], "share_of_step": tk["ms"] / tot_ms}
         kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["n"] / args.steps,
                        "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] else None,
