@@ -298,6 +298,14 @@ int dv_convnextvit_labels(dv_handle h);
 /* crops per internal pass (default 96): sizes the activation workspace so the widest tensor stays near L2 */
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops);
 /*
+ * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
+ * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
+ * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i
+ * left-aligned with widths[i] valid columns (device int32 [b]); out: device fp32 [b, 3, height, width].  Bit-exact.
+ */
+int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
+                        float* out_nchw_f32);
+/*
  * Collapse per-step arg-max ids: keep[t] = ids[t] != blank && (t == 0 || ids[t] != ids[t-1]).
  * Replaces the loop of OCRRecognitionPostProcessor.__call__ (processor_ocr_recognition.py:152-162) and, given
  * scores, the confidence of BaseRecLabelDecode.decode (ocr_rec_pp/rec_postprocess.py:126-161).

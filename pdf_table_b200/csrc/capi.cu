@@ -455,6 +455,15 @@ int dv_convnextvit_set_pass_crops(dv_handle h, int crops) {
     return cnv_set_pass_crops(h, crops);
 }
 
+int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
+                        float* out_nchw_f32) {
+    if (!h) return DV_ERR_ARG;
+    if (!crops_hwc_u8 || !widths || !out_nchw_f32 || b <= 0 || height <= 0 || width <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_pp_rec_normalise: null pointer / empty batch");
+    cudaSetDevice(h->device);
+    return op_pp_rec_norm(h, crops_hwc_u8, widths, b, height, width, out_nchw_f32);
+}
+
 int dv_ctc_collapse(dv_handle h, const int32_t* ids, const float* scores, int b, int t, int blank,
                     int32_t* out_ids, int32_t* out_len, float* out_conf) {
     if (!h) return DV_ERR_ARG;

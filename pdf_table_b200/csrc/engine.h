@@ -184,6 +184,7 @@ int launch_mlp(Engine* e, const MlpPlan& plan);
 
 // ops.cu (simple HBM-bound kernels)
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);
+int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out);
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out);
 int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out);

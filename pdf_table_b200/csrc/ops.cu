@@ -65,6 +65,39 @@ __global__ void k_u8_to_stem(const uint8_t* __restrict__ in, int N, int H, int W
     *reinterpret_cast<uint2*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4) = u;
 }
 
+// PP-OCR recogniser pre-process after the host cv2.resize: PPOcrRecPreProcessor.resize_norm_img
+// (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32) -> HWC->CHW -> / 255 -> -= 0.5 -> /= 0.5, all float32, then
+// zero padding of the columns >= resized_w up to the batch width.  in: uint8 [B, H, W, 3] (each crop left-aligned, bytes
+// beyond its width ignored), widths [B]; out: fp32 [B, 3, H, W].  One thread per pixel: 3 bytes read, 3 planes written.
+__global__ void k_pp_rec_norm(const uint8_t* __restrict__ in, const int32_t* __restrict__ widths, int B, int H, int W,
+                              float* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long plane = static_cast<long long>(H) * W;
+    if (idx >= plane * B) return;
+    const int b = static_cast<int>(idx / plane);
+    const long long r = idx - b * plane;
+    const int x = static_cast<int>(r % W);
+    float v[3] = {0.f, 0.f, 0.f};
+    if (x < __ldg(widths + b)) {
+        const uint8_t* ip = in + idx * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(ip[c]), 255.f), 0.5f), 0.5f);  // numpy's op order, no contraction
+    }
+    float* op = out + static_cast<long long>(b) * 3 * plane + r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) op[c * plane] = v[c];
+}
+
+int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out) {
+    const long long total = static_cast<long long>(B) * H * W;
+    e->launch_begin("k_pp_rec_norm", "pp_rec_pre", 0.0, total * (3.0 + 12.0));
+    k_pp_rec_norm<<<grid_for(total, 256), 256, 0, e->stream>>>(in, widths, B, H, W, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out) {
     const long long total = static_cast<long long>(N) * H * W;

@@ -150,6 +150,18 @@ class Engine:
     def set_pass_crops(self, crops: int):
         check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
 
+    def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
+        """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
+        crops = _require_cuda(crops, torch.uint8, "crops")
+        widths = _require_cuda(widths, torch.int32, "widths")
+        b, hh, ww, c = crops.shape
+        if c != 3 or widths.numel() != b:
+            raise ValueError("crops must be [B,H,W,3] with one width per crop")
+        out = torch.empty((b, 3, hh, ww), dtype=torch.float32, device=crops.device)
+        check(self._lib.dv_pp_rec_normalise(self._h, _ptr(crops), _ptr(widths), b, hh, ww, _ptr(out)), self._h,
+              "dv_pp_rec_normalise")
+        return out
+
     def ctc_collapse(self, ids: torch.Tensor, scores: Optional[torch.Tensor] = None, blank: int = 0):
         """[B,T] int32 per-step arg-max (+ optional [B,T] fp32 scores) -> (ids left-packed/-1 padded, len, conf)."""
         ids = _require_cuda(ids, torch.int32, "ids")

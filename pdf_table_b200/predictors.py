@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -81,6 +81,74 @@ def keepratio_resize(img: np.ndarray, target_height: int = 32, target_width: int
     else:
         cur_w = int(target_height * cur_ratio)
     return cv2.resize(img, (cur_w, target_height))
+
+
+def pp_rec_batch_plan(shapes, rec_image_shape=(3, 48, 320), rec_batch_num: int = 6, limited_min_width: int = 16,
+                      limited_max_width: int = 1280):
+    """The host rule of PPOcrRecPreProcessor (ocr_rec_pp/processor_ocr_rec_pp.py:44-59, 100-121): crops sorted by aspect
+    ratio (``np.argsort``, as the reference), batches of ``rec_batch_num``; per batch W = int(48 * max(max ratio, 320/48))
+    clamped to [min, max]; per crop resized_w = min(W, max(ceil(48 * ratio), min)).  shapes: [(h, w)].
+    Returns (indices, [(batch_beg_img_no, W, [resized_w ...])])."""
+    import math
+
+    _, img_h, img_w0 = rec_image_shape
+    indices = np.argsort(np.array([w / float(h) for h, w in shapes]))
+    plan = []
+    for beg in range(0, len(shapes), rec_batch_num):
+        ids = indices[beg:beg + rec_batch_num]
+        max_wh_ratio = 0
+        for i in ids:
+            h, w = shapes[i]
+            max_wh_ratio = max(max_wh_ratio, w * 1.0 / h)
+        max_wh_ratio = max(max_wh_ratio, img_w0 / img_h)
+        img_w = max(min(int(img_h * max_wh_ratio), limited_max_width), limited_min_width)
+        widths = []
+        for i in ids:
+            h, w = shapes[i]
+            ratio_w = max(math.ceil(img_h * (w / float(h))), limited_min_width)
+            widths.append(img_w if ratio_w > img_w else int(ratio_w))
+        plan.append((beg, img_w, widths))
+    return indices, plan
+
+
+class PPOcrRecPreProcessor:
+    """Counterpart of PPOcrRecPreProcessor (ocr_rec_pp/processor_ocr_rec_pp.py:25-135): same call, same
+    return value (a list of ``{'image', 'indices', 'batch_beg_img_no'}``), with ``image`` a CUDA fp32 [B,3,48,W] tensor.
+    ``cv2.resize`` stays on the host exactly as in the reference; the float conversion, HWC->CHW, /255, -0.5, /0.5 and the
+    zero padding run in one kernel (``dv_pp_rec_normalise``), bit-exact."""
+
+    def __init__(self, engine: Engine, rec_image_shape=(3, 48, 320), rec_batch_num: int = 6, limited_max_width: int = 1280,
+                 limited_min_width: int = 16):
+        self.engine = engine
+        self.rec_image_shape = tuple(rec_image_shape)
+        self.rec_batch_num = rec_batch_num
+        self.limited_max_width, self.limited_min_width = limited_max_width, limited_min_width
+
+    def __call__(self, inputs):
+        import cv2
+
+        if not isinstance(inputs, list):
+            inputs = [inputs]
+        imgs = []
+        for item in inputs:
+            img = _read_image(item)
+            if img.ndim == 2:
+                img = cv2.cvtColor(img, cv2.COLOR_GRAY2RGB)
+            imgs.append(img)
+        img_c, img_h, _ = self.rec_image_shape
+        indices, plan = pp_rec_batch_plan([im.shape[:2] for im in imgs], self.rec_image_shape, self.rec_batch_num,
+                                          self.limited_min_width, self.limited_max_width)
+        dev = torch.device("cuda", self.engine.device)
+        out = []
+        for beg, img_w, widths in plan:
+            assert imgs[indices[beg]].shape[2] == img_c
+            stage = np.zeros((len(widths), img_h, img_w, 3), np.uint8)
+            for k, rw in enumerate(widths):
+                stage[k, :, :rw] = cv2.resize(imgs[indices[beg + k]], (rw, img_h))
+            image = self.engine.pp_rec_normalise(torch.from_numpy(stage).to(dev),
+                                                 torch.tensor(widths, dtype=torch.int32, device=dev))
+            out.append({"image": image, "indices": indices, "batch_beg_img_no": beg})
+        return out
 
 
 def _load_state_dict(sd_or_path) -> Mapping[str, Any]:
