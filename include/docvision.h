@@ -298,6 +298,16 @@ int dv_convnextvit_labels(dv_handle h);
 /* crops per internal pass (default 96): sizes the activation workspace so the widest tensor stays near L2 */
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops);
 /*
+ * det -> rec glue: the perspective crops of OcrCommonUtils.crop_image
+ * (utils/ocr/ocr_common_utils.py:214-262), i.e. cv2.warpPerspective(page, T, (w, h)) with its defaults (INTER_LINEAR,
+ * BORDER_CONSTANT 0), n crops of one page in one launch, bit-exact against cv2 (OpenCV 4.13 fixed-point remap).
+ * page_hwc_u8: device uint8 [height, width, 3].  minv: device double [n, 9] = cv2.invert(T) per crop (the host keeps
+ * getPerspectiveTransform / invert, as the reference).  sizes: device int32 [n, 2] = (w, h) of each crop.  offsets:
+ * device int64 [n] byte offset of crop i in `out` (h*w*3 bytes each, HWC).  max_pixels = max w*h.
+ */
+int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, int width, const double* minv, const int32_t* sizes,
+                           const int64_t* offsets, int n, int max_pixels, uint8_t* out);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

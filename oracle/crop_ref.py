@@ -1,0 +1,90 @@
+"""TEST INFRASTRUCTURE ONLY (never imported by the product path).
+
+CPU restatement of the det -> rec crop extraction, SURVEY.md 8(f)-1:
+  * crop_geometry / crop_image: OcrCommonUtils.crop_image (utils/ocr/ocr_common_utils.py:214-262) -- corner ordering,
+    float32 corner arrays, crop size from the mid-line distances, cv2.getPerspectiveTransform, cv2.warpPerspective;
+  * warp_perspective: what the CUDA kernel implements, a numpy restatement of cv2.warpPerspective's INTER_LINEAR /
+    BORDER_CONSTANT path on uint8 (OpenCV imgwarp.cpp WarpPerspectiveInvoker + remapBilinear, fixed point 1/32 pixel,
+    15-bit weights).
+Pinned: crop_image against the reference's own function (oracle/gen_golden_crop.py -> tests/golden/crop.npz), and
+warp_perspective against cv2.warpPerspective itself at test time (tests/test_crop_cpu.py).
+"""
+from __future__ import annotations
+
+import math
+
+import cv2
+import numpy as np
+
+
+def crop_geometry(position):
+    """position: [4,2] quad -> (corners float32 [4,2], corners_trans float32 [4,2], (w, h)); ocr_common_utils.py:227-257."""
+    position = np.asarray(position).tolist()
+    for i in range(4):
+        for j in range(i + 1, 4):
+            if position[i][0] > position[j][0]:
+                position[i], position[j] = position[j], position[i]
+    if position[0][1] > position[1][1]:
+        position[0], position[1] = position[1], position[0]
+    if position[2][1] > position[3][1]:
+        position[2], position[3] = position[3], position[2]
+    x1, y1 = position[0]
+    x2, y2 = position[2]
+    x3, y3 = position[3]
+    x4, y4 = position[1]
+
+    def distance(xa, ya, xb, yb):
+        return math.sqrt(pow(xa - xb, 2) + pow(ya - yb, 2))
+
+    corners = np.zeros((4, 2), np.float32)
+    corners[0] = [x1, y1]
+    corners[1] = [x2, y2]
+    corners[2] = [x4, y4]
+    corners[3] = [x3, y3]
+    img_width = distance((x1 + x4) / 2, (y1 + y4) / 2, (x2 + x3) / 2, (y2 + y3) / 2)
+    img_height = distance((x1 + x2) / 2, (y1 + y2) / 2, (x4 + x3) / 2, (y4 + y3) / 2)
+    trans = np.zeros((4, 2), np.float32)
+    trans[0] = [0, 0]
+    trans[1] = [img_width - 1, 0]
+    trans[2] = [0, img_height - 1]
+    trans[3] = [img_width - 1, img_height - 1]
+    return corners, trans, (int(img_width), int(img_height))
+
+
+def crop_image(img, position):
+    corners, trans, size = crop_geometry(position)
+    return cv2.warpPerspective(img, cv2.getPerspectiveTransform(corners, trans), size)
+
+
+def warp_perspective(img, transform, w, h):
+    """== cv2.warpPerspective(img, transform, (w, h)) for uint8 HWC (defaults: INTER_LINEAR, BORDER_CONSTANT 0)."""
+    m = cv2.invert(np.asarray(transform, np.float64))[1].ravel()
+    sh, sw = img.shape[:2]
+    bh0 = min(16, h)
+    bw0 = min(1024 // bh0, w)
+    ys = np.arange(h, dtype=np.float64)[:, None]
+    xs = np.arange(w)
+    xb = (xs // bw0 * bw0).astype(np.float64)[None, :]
+    x1 = (xs % bw0).astype(np.float64)[None, :]
+    x0 = m[0] * xb + m[1] * ys + m[2]
+    y0 = m[3] * xb + m[4] * ys + m[5]
+    w0 = m[6] * xb + m[7] * ys + m[8]
+    wd = w0 + m[6] * x1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        wi = np.where(wd != 0, 32.0 / wd, 0.0)
+    fx = np.maximum(-2147483648.0, np.minimum(2147483647.0, (x0 + m[0] * x1) * wi))
+    fy = np.maximum(-2147483648.0, np.minimum(2147483647.0, (y0 + m[3] * x1) * wi))
+    xi = np.rint(fx).astype(np.int64)
+    yi = np.rint(fy).astype(np.int64)
+    sx = np.clip(xi >> 5, -32768, 32767)
+    sy = np.clip(yi >> 5, -32768, 32767)
+    ax, ay = xi & 31, yi & 31
+
+    def fetch(yy, xx):
+        ok = (yy >= 0) & (yy < sh) & (xx >= 0) & (xx < sw)
+        v = img[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)].astype(np.int64)
+        return np.where(ok[..., None], v, 0)
+
+    acc = (fetch(sy, sx) * ((32 - ax) * (32 - ay) * 32)[..., None] + fetch(sy, sx + 1) * (ax * (32 - ay) * 32)[..., None]
+           + fetch(sy + 1, sx) * ((32 - ax) * ay * 32)[..., None] + fetch(sy + 1, sx + 1) * (ax * ay * 32)[..., None])
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)

@@ -455,6 +455,16 @@ int dv_convnextvit_set_pass_crops(dv_handle h, int crops) {
     return cnv_set_pass_crops(h, crops);
 }
 
+int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, int width, const double* minv, const int32_t* sizes,
+                           const int64_t* offsets, int n, int max_pixels, uint8_t* out) {
+    if (!h) return DV_ERR_ARG;
+    if (n == 0) return 0;
+    if (!page_hwc_u8 || !minv || !sizes || !offsets || !out || n < 0 || height <= 0 || width <= 0 || max_pixels <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_warp_perspective_u8: null pointer / bad size");
+    cudaSetDevice(h->device);
+    return op_warp_perspective_u8(h, page_hwc_u8, height, width, minv, sizes, reinterpret_cast<const long long*>(offsets), n, max_pixels, out);
+}
+
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
                         float* out_nchw_f32) {
     if (!h) return DV_ERR_ARG;

@@ -150,6 +150,31 @@ class Engine:
     def set_pass_crops(self, crops: int):
         check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
 
+    def warp_perspective_u8(self, page: torch.Tensor, minv: np.ndarray, sizes: np.ndarray):
+        """uint8 HWC page (cuda) + per-crop inverse homographies [n,3,3] float64 and sizes [n,2] = (w, h) (host) -> list of
+        uint8 [h,w,3] cuda tensors (views of one packed buffer): cv2.warpPerspective(page, T, (w, h)) for each crop."""
+        page = _require_cuda(page, torch.uint8, "page")
+        hh, ww, c = page.shape
+        minv = np.ascontiguousarray(minv, dtype=np.float64).reshape(-1, 9)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32).reshape(-1, 2)
+        n = sizes.shape[0]
+        if c != 3 or minv.shape[0] != n:
+            raise ValueError("page must be [H,W,3]; one 3x3 matrix and one (w, h) per crop")
+        if n == 0:
+            return []
+        if (sizes <= 0).any():
+            raise ValueError("crop sizes must be positive")
+        nbytes = sizes[:, 0].astype(np.int64) * sizes[:, 1] * 3
+        offsets = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
+        dev = page.device
+        out = torch.empty((int(nbytes.sum()),), dtype=torch.uint8, device=dev)
+        d_m = torch.from_numpy(minv).to(dev)
+        d_s = torch.from_numpy(sizes).to(dev)
+        d_o = torch.from_numpy(offsets).to(dev)
+        check(self._lib.dv_warp_perspective_u8(self._h, _ptr(page), hh, ww, _ptr(d_m), _ptr(d_s), _ptr(d_o), n,
+                                               int((nbytes // 3).max()), _ptr(out)), self._h, "dv_warp_perspective_u8")
+        return [out[int(o):int(o + b)].view(int(s[1]), int(s[0]), 3) for o, b, s in zip(offsets, nbytes, sizes)]
+
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
         crops = _require_cuda(crops, torch.uint8, "crops")

@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -81,6 +81,55 @@ def keepratio_resize(img: np.ndarray, target_height: int = 32, target_width: int
     else:
         cur_w = int(target_height * cur_ratio)
     return cv2.resize(img, (cur_w, target_height))
+
+
+def crop_geometry(position):
+    """The host part of OcrCommonUtils.crop_image (utils/ocr/ocr_common_utils.py:227-257): order the four corners (by x,
+    then the left pair and the right pair by y), take the crop size from the distances between opposite edge mid-points
+    (python float maths), and build the float32 source / destination corner arrays of the homography.
+    Returns (corners [4,2] float32, corners_trans [4,2] float32, (w, h))."""
+    import math
+
+    position = np.asarray(position).tolist()
+    for i in range(4):
+        for j in range(i + 1, 4):
+            if position[i][0] > position[j][0]:
+                position[i], position[j] = position[j], position[i]
+    if position[0][1] > position[1][1]:
+        position[0], position[1] = position[1], position[0]
+    if position[2][1] > position[3][1]:
+        position[2], position[3] = position[3], position[2]
+    (x1, y1), (x4, y4), (x2, y2), (x3, y3) = position[0], position[1], position[2], position[3]
+    corners = np.zeros((4, 2), np.float32)
+    corners[0], corners[1], corners[2], corners[3] = [x1, y1], [x2, y2], [x4, y4], [x3, y3]
+    img_width = math.sqrt(pow((x1 + x4) / 2 - (x2 + x3) / 2, 2) + pow((y1 + y4) / 2 - (y2 + y3) / 2, 2))
+    img_height = math.sqrt(pow((x1 + x2) / 2 - (x4 + x3) / 2, 2) + pow((y1 + y2) / 2 - (y4 + y3) / 2, 2))
+    trans = np.zeros((4, 2), np.float32)
+    trans[1], trans[2], trans[3] = [img_width - 1, 0], [0, img_height - 1], [img_width - 1, img_height - 1]
+    return corners, trans, (int(img_width), int(img_height))
+
+
+def crop_images(engine: Engine, page: torch.Tensor, positions) -> List[Optional[torch.Tensor]]:
+    """OcrCommonUtils.crop_image for every detected quad of one page, on the GPU: the homography is
+    solved on the host with cv2.getPerspectiveTransform exactly as the reference does (and inverted with cv2.invert, which
+    is what cv2.warpPerspective does first); the warp itself -- all crops of the page -- is one launch of
+    ``dv_warp_perspective_u8``, bit-exact against cv2.  page: uint8 [H,W,3] cuda.  Returns one uint8 [h,w,3] cuda tensor per
+    quad, or None where the reference's cv2 call would raise (a crop of zero width or height)."""
+    import cv2
+
+    minv, sizes, keep = [], [], []
+    for k, pos in enumerate(positions):
+        corners, trans, (w, h) = crop_geometry(pos)
+        if w <= 0 or h <= 0:
+            continue
+        minv.append(cv2.invert(cv2.getPerspectiveTransform(corners, trans))[1])
+        sizes.append((w, h))
+        keep.append(k)
+    out: List[Optional[torch.Tensor]] = [None] * len(positions)
+    if keep:
+        for k, crop in zip(keep, engine.warp_perspective_u8(page, np.stack(minv), np.array(sizes, np.int32))):
+            out[k] = crop
+    return out
 
 
 def pp_rec_batch_plan(shapes, rec_image_shape=(3, 48, 320), rec_batch_num: int = 6, limited_min_width: int = 16,

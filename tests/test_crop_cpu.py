@@ -1,0 +1,55 @@
+"""SURVEY.md 8(f)-1, det -> rec crop extraction.  CPU side: the oracle's crop_image against the golden crops produced by the
+reference's own OcrCommonUtils.crop_image, the numpy restatement of cv2.warpPerspective (what the CUDA kernel implements)
+against cv2 itself, and the host corner-ordering rule."""
+import math
+import os
+
+import cv2
+import numpy as np
+
+from oracle import crop_ref as ref
+from oracle import gen_golden_crop as gen
+from pdf_table_b200 import predictors
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crop.npz")
+
+
+def test_oracle_crop_image_matches_reference_golden():
+    g = np.load(GOLDEN)
+    img = gen.page()
+    for k in range(int(g["n"])):
+        assert np.array_equal(ref.crop_image(img, g[f"quad{k}"]), g[f"crop{k}"]), k
+
+
+def test_warp_restatement_equals_cv2_on_golden_quads():
+    g = np.load(GOLDEN)
+    img = gen.page()
+    for k in range(int(g["n"])):
+        corners, trans, (w, h) = ref.crop_geometry(g[f"quad{k}"])
+        t = cv2.getPerspectiveTransform(corners, trans)
+        assert np.array_equal(ref.warp_perspective(img, t, w, h), g[f"crop{k}"]), k
+
+
+def test_warp_restatement_equals_cv2_on_random_quads():
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        hh, ww = int(rng.integers(60, 400)), int(rng.integers(60, 500))
+        img = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        cx, cy = rng.uniform(0, ww), rng.uniform(0, hh)  # centres anywhere: many quads hang over the border
+        bw, bh, ang = rng.uniform(4, 300), rng.uniform(2, 70), rng.uniform(-0.8, 0.8)
+        c, s = math.cos(ang), math.sin(ang)
+        pts = np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+        pts += rng.uniform(-2, 2, pts.shape)
+        corners, trans, (w, h) = ref.crop_geometry(pts)
+        if w < 1 or h < 1:
+            continue
+        t = cv2.getPerspectiveTransform(corners, trans)
+        assert np.array_equal(ref.warp_perspective(img, t, w, h), cv2.warpPerspective(img, t, (w, h))), trial
+
+
+def test_host_crop_geometry_matches_oracle():
+    g = np.load(GOLDEN)
+    for k in range(int(g["n"])):
+        a, b = predictors.crop_geometry(g[f"quad{k}"]), ref.crop_geometry(g[f"quad{k}"])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+        assert a[2] == (g[f"crop{k}"].shape[1], g[f"crop{k}"].shape[0])
