@@ -308,6 +308,16 @@ int dv_convnextvit_set_pass_crops(dv_handle h, int crops);
 int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, int width, const double* minv, const int32_t* sizes,
                            const int64_t* offsets, int n, int max_pixels, uint8_t* out);
 /*
+ * cv2.resize(crop, (dst_widths[i], dst_h)) with the default INTER_LINEAR on uint8 HWC crops, bit-exact against cv2 (OpenCV 4.13:
+ * 11-bit coefficients, the 2x2 box average for an exact 2x reduction).  Replaces the resize of
+ * OCRRecognitionPreprocessor.keepratio_resize (ocr_recognition/processor_ocr_recognition.py:44-62) for crops that are
+ * already on the device.  src_packed / src_offsets (int64 [n], bytes) / src_sizes (int32 [n,2] = (w, h)): the packed crops as
+ * dv_warp_perspective_u8 writes them.  out: device uint8 [n, dst_h, dst_w_pad, 3], columns >= dst_widths[i] zero -- the layout
+ * dv_convnextvit_forward_u8 reads.
+ */
+int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* src_offsets, const int32_t* src_sizes,
+                        const int32_t* dst_widths, int n, int dst_h, int dst_w_pad, uint8_t* out);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

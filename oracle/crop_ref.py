@@ -6,6 +6,8 @@ CPU restatement of the det -> rec crop extraction, SURVEY.md 8(f)-1:
   * warp_perspective: what the CUDA kernel implements, a numpy restatement of cv2.warpPerspective's INTER_LINEAR /
     BORDER_CONSTANT path on uint8 (OpenCV imgwarp.cpp WarpPerspectiveInvoker + remapBilinear, fixed point 1/32 pixel,
     15-bit weights).
+  * resize_linear: numpy restatement of cv2.resize's default INTER_LINEAR on uint8 (OpenCV resize.cpp, 11-bit coefficients,
+    the 2x2 box average for an exact 2x reduction) -- what k_resize_linear_u8 implements; checked against cv2 itself.
 Pinned: crop_image against the reference's own function (oracle/gen_golden_crop.py -> tests/golden/crop.npz), and
 warp_perspective against cv2.warpPerspective itself at test time (tests/test_crop_cpu.py).
 """
@@ -88,3 +90,29 @@ def warp_perspective(img, transform, w, h):
     acc = (fetch(sy, sx) * ((32 - ax) * (32 - ay) * 32)[..., None] + fetch(sy, sx + 1) * (ax * (32 - ay) * 32)[..., None]
            + fetch(sy + 1, sx) * ((32 - ax) * ay * 32)[..., None] + fetch(sy + 1, sx + 1) * (ax * ay * 32)[..., None])
     return ((acc + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def resize_linear(img, dw, dh):
+    """== cv2.resize(img, (dw, dh)) for uint8 HWC (default INTER_LINEAR)."""
+    sh, sw = img.shape[:2]
+    src = img.astype(np.int64)
+    if sw == 2 * dw and sh == 2 * dh:  # cv2 turns an exact 2x INTER_LINEAR reduction into the INTER_AREA fast path
+        return ((src[0::2, 0::2] + src[0::2, 1::2] + src[1::2, 0::2] + src[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    def coeffs(dn, sn, clamp):
+        scale = 1.0 / (dn / sn)
+        f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = f - s.astype(np.float32)
+        if clamp:  # columns: the fraction is dropped at the borders; rows keep it and clip the row indices instead
+            lo, hi = s < 0, s >= sn - 1
+            f = np.where(lo | hi, np.float32(0), f)
+            s = np.where(lo, 0, np.where(hi, sn - 1, s))
+        return s, np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int64), np.rint(f * np.float32(2048)).astype(np.int64)
+
+    sx, a0, a1 = coeffs(dw, sw, True)
+    sy, b0, b1 = coeffs(dh, sh, False)
+    hrow = src[:, sx] * a0[None, :, None] + src[:, np.minimum(sx + 1, sw - 1)] * a1[None, :, None]
+    s0, s1 = hrow[np.clip(sy, 0, sh - 1)], hrow[np.clip(sy + 1, 0, sh - 1)]
+    out = (((b0[:, None, None] * (s0 >> 4)) >> 16) + ((b1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)

@@ -465,6 +465,16 @@ int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, 
     return op_warp_perspective_u8(h, page_hwc_u8, height, width, minv, sizes, reinterpret_cast<const long long*>(offsets), n, max_pixels, out);
 }
 
+int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* src_offsets, const int32_t* src_sizes,
+                        const int32_t* dst_widths, int n, int dst_h, int dst_w_pad, uint8_t* out) {
+    if (!h) return DV_ERR_ARG;
+    if (n == 0) return 0;
+    if (!src_packed || !src_offsets || !src_sizes || !dst_widths || !out || n < 0 || dst_h <= 0 || dst_w_pad <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_resize_linear_u8: null pointer / bad size");
+    cudaSetDevice(h->device);
+    return op_resize_linear_u8(h, src_packed, reinterpret_cast<const long long*>(src_offsets), src_sizes, dst_widths, n, dst_h, dst_w_pad, out);
+}
+
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
                         float* out_nchw_f32) {
     if (!h) return DV_ERR_ARG;

@@ -59,7 +59,82 @@ k_warp_perspective_u8(const uint8_t* __restrict__ img, int H, int W, const doubl
     o[2] = static_cast<uint8_t>((acc[2] + (1 << 14)) >> 15);
 }
 
+// cv2.resize(src, (dw, dh)) with its default INTER_LINEAR on uint8 HWC, bit for bit (OpenCV resize.cpp: resizeGeneric_ with
+// HResizeLinear<uchar,int,short,2048> and the VResizeLinear<uchar,int,short,FixedPtCast<22>> specialisation; checked against
+// cv2 4.13 on 26 M elements, tools/resize_restatement.py):
+//   scale = 1.0 / (dst / (double) src);  f = (float)((d + 0.5) * scale - 0.5);  s = floor(f);  f -= s
+//   columns: s < 0 -> (s, f) = (0, 0);  s >= sw - 1 -> (sw - 1, 0)          rows: f kept, the two row indices are clipped
+//   a = cvRound((1 - f) * 2048), cvRound(f * 2048)  (round half to even)
+//   H(row, dx) = p[s] * a0 + p[min(s + 1, sw - 1)] * a1
+//   dst = (((b0 * (H(r0) >> 4)) >> 16) + ((b1 * (H(r1) >> 4)) >> 16) + 2) >> 2
+// and the one special case cv2 makes for INTER_LINEAR: an exact 2x reduction in both directions is the 2x2 box average
+// (a + b + c + d + 2) >> 2 (INTER_AREA fast path).  Crops come packed (the warp kernel's output); crop i is written to
+// out[i] = [dst_h, dst_w_pad, 3] with columns >= dst_widths[i] zero (the recogniser's zero padding).
+__global__ void __launch_bounds__(256)
+k_resize_linear_u8(const uint8_t* __restrict__ src, const long long* __restrict__ src_off, const int32_t* __restrict__ src_sizes,
+                   const int32_t* __restrict__ dst_widths, int dst_h, int dst_w_pad, uint8_t* __restrict__ out) {
+    const int crop = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= dst_h * dst_w_pad) return;
+    const int dy = idx / dst_w_pad, dx = idx - dy * dst_w_pad;
+    uint8_t* o = out + (static_cast<long long>(crop) * dst_h * dst_w_pad + idx) * 3;
+    const int dw = dst_widths[crop];
+    if (dx >= dw) {
+        o[0] = o[1] = o[2] = 0;
+        return;
+    }
+    const int sw = src_sizes[2 * crop], sh = src_sizes[2 * crop + 1];
+    const uint8_t* s = src + src_off[crop];
+    if (sw == 2 * dw && sh == 2 * dst_h) {
+        const uint8_t* p = s + (static_cast<long long>(2 * dy) * sw + 2 * dx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p[c] + p[3 + c] + p[sw * 3 + c] + p[sw * 3 + 3 + c] + 2) >> 2);
+        return;
+    }
+    const double scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dw), static_cast<double>(sw)));
+    const double scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dst_h), static_cast<double>(sh)));
+    float fx = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dx), 0.5), scale_x), 0.5));
+    int sx = static_cast<int>(floorf(fx));
+    fx = __fsub_rn(fx, static_cast<float>(sx));
+    if (sx < 0) {
+        sx = 0;
+        fx = 0.f;
+    }
+    if (sx >= sw - 1) {
+        sx = sw - 1;
+        fx = 0.f;
+    }
+    float fy = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dy), 0.5), scale_y), 0.5));
+    const int sy = static_cast<int>(floorf(fy));
+    fy = __fsub_rn(fy, static_cast<float>(sy));
+    const int a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+    const int b0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+    const int sx1 = min(sx + 1, sw - 1);
+    const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
+    const uint8_t* p0 = s + static_cast<long long>(r0) * sw * 3;
+    const uint8_t* p1 = s + static_cast<long long>(r1) * sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = p0[sx * 3 + c] * a0 + p0[sx1 * 3 + c] * a1;
+        const int h1 = p1[sx * 3 + c] * a0 + p1[sx1 * 3 + c] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+    }
+}
+
 }  // namespace
+
+int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off, const int32_t* src_sizes, const int32_t* dst_widths,
+                        int n, int dst_h, int dst_w_pad, uint8_t* out) {
+    if (n <= 0) return 0;
+    if (n > 65535) return set_err(e, DV_ERR_UNSUPPORTED, "resize_linear: more than 65535 crops per call");
+    const int px = dst_h * dst_w_pad;
+    e->launch_begin("k_resize_linear_u8", "crop", 0.0, static_cast<double>(n) * px * 3.0 * 5.0);
+    k_resize_linear_u8<<<dim3((px + 255) / 256, n), 256, 0, e->stream>>>(src, src_off, src_sizes, dst_widths, dst_h, dst_w_pad, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
 
 int op_warp_perspective_u8(Engine* e, const uint8_t* img, int H, int W, const double* minv, const int32_t* sizes,
                            const long long* offsets, int n, int max_pixels, uint8_t* out) {

@@ -186,6 +186,8 @@ int launch_mlp(Engine* e, const MlpPlan& plan);
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);
 int op_warp_perspective_u8(Engine* e, const uint8_t* img, int H, int W, const double* minv, const int32_t* sizes,
                            const long long* offsets, int n, int max_pixels, uint8_t* out);
+int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off, const int32_t* src_sizes, const int32_t* dst_widths,
+                        int n, int dst_h, int dst_w_pad, uint8_t* out);
 int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out);
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out);

@@ -150,9 +150,10 @@ class Engine:
     def set_pass_crops(self, crops: int):
         check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
 
-    def warp_perspective_u8(self, page: torch.Tensor, minv: np.ndarray, sizes: np.ndarray):
+    def warp_perspective_u8(self, page: torch.Tensor, minv: np.ndarray, sizes: np.ndarray, return_packed: bool = False):
         """uint8 HWC page (cuda) + per-crop inverse homographies [n,3,3] float64 and sizes [n,2] = (w, h) (host) -> list of
-        uint8 [h,w,3] cuda tensors (views of one packed buffer): cv2.warpPerspective(page, T, (w, h)) for each crop."""
+        uint8 [h,w,3] cuda tensors (views of one packed buffer): cv2.warpPerspective(page, T, (w, h)) for each crop.
+        return_packed: also return (packed buffer, device offsets int64 [n], device sizes int32 [n,2]) for resize_linear_u8."""
         page = _require_cuda(page, torch.uint8, "page")
         hh, ww, c = page.shape
         minv = np.ascontiguousarray(minv, dtype=np.float64).reshape(-1, 9)
@@ -173,7 +174,22 @@ class Engine:
         d_o = torch.from_numpy(offsets).to(dev)
         check(self._lib.dv_warp_perspective_u8(self._h, _ptr(page), hh, ww, _ptr(d_m), _ptr(d_s), _ptr(d_o), n,
                                                int((nbytes // 3).max()), _ptr(out)), self._h, "dv_warp_perspective_u8")
-        return [out[int(o):int(o + b)].view(int(s[1]), int(s[0]), 3) for o, b, s in zip(offsets, nbytes, sizes)]
+        views = [out[int(o):int(o + b)].view(int(s[1]), int(s[0]), 3) for o, b, s in zip(offsets, nbytes, sizes)]
+        return (views, (out, d_o, d_s)) if return_packed else views
+
+    def resize_linear_u8(self, packed, dst_widths: np.ndarray, dst_h: int, dst_w_pad: int) -> torch.Tensor:
+        """cv2.resize(crop_i, (dst_widths[i], dst_h)) (INTER_LINEAR) for the packed crops of warp_perspective_u8
+        (``packed`` = its (buffer, offsets, sizes) triple) -> uint8 [n, dst_h, dst_w_pad, 3], zero beyond each width."""
+        buf, d_o, d_s = packed
+        n = d_s.shape[0]
+        dst_widths = np.ascontiguousarray(dst_widths, dtype=np.int32).reshape(-1)
+        if dst_widths.shape[0] != n or (dst_widths <= 0).any() or (dst_widths > dst_w_pad).any():
+            raise ValueError("one positive width <= dst_w_pad per crop")
+        out = torch.empty((n, dst_h, dst_w_pad, 3), dtype=torch.uint8, device=buf.device)
+        d_w = torch.from_numpy(dst_widths).to(buf.device)
+        check(self._lib.dv_resize_linear_u8(self._h, _ptr(buf), _ptr(d_o), _ptr(d_s), _ptr(d_w), n, dst_h, dst_w_pad, _ptr(out)),
+              self._h, "dv_resize_linear_u8")
+        return out
 
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""

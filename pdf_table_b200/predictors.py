@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -130,6 +130,34 @@ def crop_images(engine: Engine, page: torch.Tensor, positions) -> List[Optional[
         for k, crop in zip(keep, engine.warp_perspective_u8(page, np.stack(minv), np.array(sizes, np.int32))):
             out[k] = crop
     return out
+
+
+def crops_for_recognition(engine: Engine, page: torch.Tensor, positions, target_height: int = 32, target_width: int = 804):
+    """det -> rec on the device: OcrCommonUtils.crop_image for every quad (``crop_images``) followed by
+    OCRRecognitionPreprocessor.keepratio_resize (ocr_recognition/processor_ocr_recognition.py:44-62) of every crop, both
+    bit-exact against cv2, without the crops ever visiting the host.  Returns (crops uint8 [n, 32, Wc, 3] cuda, zero padded
+    to the widest crop -- the input of ``Engine.convnextvit_forward_u8`` --, widths [n], kept quad indices); quads whose crop
+    or resized width is empty (the reference's cv2 calls raise there and the orchestrator skips the crop) are dropped."""
+    import cv2
+
+    minv, sizes, widths, keep = [], [], [], []
+    for k, pos in enumerate(positions):
+        corners, trans, (w, h) = crop_geometry(pos)
+        if w <= 0 or h <= 0:
+            continue
+        cur_ratio = w / float(h)
+        cur_w = target_width if cur_ratio > float(target_width) / target_height else int(target_height * cur_ratio)
+        if cur_w <= 0:
+            continue
+        minv.append(cv2.invert(cv2.getPerspectiveTransform(corners, trans))[1])
+        sizes.append((w, h))
+        widths.append(cur_w)
+        keep.append(k)
+    if not keep:
+        return torch.empty((0, target_height, 0, 3), dtype=torch.uint8, device=page.device), [], []
+    _, packed = engine.warp_perspective_u8(page, np.stack(minv), np.array(sizes, np.int32), return_packed=True)
+    out = engine.resize_linear_u8(packed, np.array(widths, np.int32), target_height, max(widths))
+    return out, widths, keep
 
 
 def pp_rec_batch_plan(shapes, rec_image_shape=(3, 48, 320), rec_batch_num: int = 6, limited_min_width: int = 16,

@@ -53,3 +53,22 @@ def test_host_crop_geometry_matches_oracle():
         a, b = predictors.crop_geometry(g[f"quad{k}"]), ref.crop_geometry(g[f"quad{k}"])
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
         assert a[2] == (g[f"crop{k}"].shape[1], g[f"crop{k}"].shape[0])
+
+
+def test_resize_restatement_equals_cv2():
+    rng = np.random.default_rng(12)
+    for trial in range(80):
+        hh, ww = int(rng.integers(1, 150)), int(rng.integers(1, 1200))
+        if trial % 8 == 0:
+            hh, ww = 64, 2 * int(rng.integers(10, 300))  # exact 2x reduction: cv2's box-average special case
+        img = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        ratio = ww / float(hh)
+        dw = 804 if ratio > 804 / 32 else int(32 * ratio)  # keepratio_resize
+        if dw < 1:
+            continue
+        assert np.array_equal(ref.resize_linear(img, dw, 32), cv2.resize(img, (dw, 32))), (trial, hh, ww)
+    for trial in range(30):  # PP-OCR rec sizes (height 48, width 16 .. 1280)
+        hh, ww = int(rng.integers(2, 120)), int(rng.integers(2, 900))
+        img = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        dw = int(rng.integers(16, 1281))
+        assert np.array_equal(ref.resize_linear(img, dw, 48), cv2.resize(img, (dw, 48))), (trial, hh, ww, dw)
