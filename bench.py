@@ -488,7 +488,7 @@ def _workload_config():
         "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
         "db_post_stage": "db_boxes on planted probability maps (analytic text-line blobs, ~40 per page): with random weights the "
                          "detector's own map is texture noise",
-        "not_yet_on_gpu": "perspective crop extraction (crops are planted, not cut from the detected boxes)",
+        "not_in_timed_step": "perspective crop extraction: the warp / resize kernels exist and are bit-exact against cv2 (tests/test_gpu_crop.py) but the per-quad homography solve is host cv2, so the recogniser reads planted crops",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
         "parallelism": "page-sharded replicas, one process per GPU",
