@@ -375,6 +375,23 @@ class OcrRecognitionTask(BaseInferTask):
         inputs["ids"], inputs["len"] = out.cpu().numpy(), ln.cpu().numpy()
         return inputs
 
+    def recognize_page(self, page, positions) -> List[Optional[str]]:
+        """All detected quads of one page: what the reference's orchestrator does per box (OcrCommonUtils.crop_image, then
+        this task on the crop -- ocr_pdf/ocr_system_task.py:300-313), with the crops cut and resized on the device
+        (``crops_for_recognition``) so that only the page goes up and only token ids come back.  page: uint8 HWC ndarray or
+        cuda tensor.  Returns one string per quad (None where the reference's crop would be empty)."""
+        dev = torch.device("cuda", self.device)
+        page_dev = page if isinstance(page, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(page)).to(dev)
+        crops, _, keep = crops_for_recognition(self.post, page_dev, positions)
+        out: List[Optional[str]] = [None] * len(positions)
+        if keep:
+            ids = self.predictor.convnextvit_forward_u8(crops)
+            tok, ln, _ = self.post.ctc_collapse(ids)
+            texts = self._postprocess({"ids": tok.cpu().numpy(), "len": ln.cpu().numpy()})
+            for k, t in zip(keep, texts):
+                out[k] = t
+        return out
+
     def _postprocess(self, inputs, **kwargs) -> List[str]:
         res = []
         for row, n in zip(inputs["ids"], inputs["len"]):

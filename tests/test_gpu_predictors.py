@@ -94,3 +94,30 @@ def test_table_structure_task_lore():
         safe = np.abs((stacked.numpy() - np.floor(stacked.numpy())) - 0.5) > 2e-3
         np.testing.assert_array_equal(res[i]["logi"][safe], want_logi[safe])
         assert safe.mean() > 0.98
+
+
+def test_recognition_task_recognize_page_equals_per_crop_calls():
+    """det -> rec on the device: recognize_page(page, quads) returns exactly what the reference's flow returns -- crop every
+    quad with OcrCommonUtils.crop_image (cv2 on the host) and call the task on the crops."""
+    import math
+
+    import cv2
+
+    vocab = [chr(0x4E00 + i) for i in range(2, 7644)]
+    task = predictors.OcrRecognitionTask(model="ConvNextViT", state_dict=synth.convnext_vit_state_dict(0), vocab=vocab)
+    page = synth.synthetic_page(5, 480, 640)
+    rng = np.random.default_rng(3)
+    quads = []
+    for k in range(12):
+        cx, cy, bw, bh, ang = rng.uniform(100, 540), rng.uniform(60, 420), rng.uniform(40, 300), rng.uniform(12, 40), rng.uniform(-0.3, 0.3)
+        c, s = math.cos(ang), math.sin(ang)
+        quads.append((np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]]) @ np.array([[c, s], [-s, c]])
+                      + [cx, cy]).astype(np.float32))
+    quads.append(np.array([[10, 10], [10.4, 10], [10.4, 30], [10, 30]], np.float32))  # zero-width crop: the reference's cv2 call raises
+    got = task.recognize_page(page, quads)
+    assert len(got) == len(quads) and got[-1] is None
+    host_crops = []
+    for q in quads[:-1]:
+        corners, trans, size = predictors.crop_geometry(q)
+        host_crops.append(cv2.warpPerspective(page, cv2.getPerspectiveTransform(corners, trans), size))
+    assert got[:-1] == task(host_crops)
