@@ -52,7 +52,7 @@ __device__ __forceinline__ float apply_act(float x) {
 
 // The same GELU on two values at once with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2: one issue slot for
 // two IEEE operations, so the result is bit-identical to apply_act<ACT_GELU> on each value): 8.5 instead of 16 issue
-// slots per element in an epilogue that is issue-bound.  Returns gelu(x0 + b0), gelu(x1 + b1).
+// slots per element in an epilogue that is issue-bound.  gelu_bias_x2 returns gelu(v0 + b0), gelu(v1 + b1).
 namespace f32x2 {
 __device__ __forceinline__ uint64_t pk(float a, float b) {
     uint64_t r;
@@ -76,10 +76,8 @@ __device__ __forceinline__ uint64_t add(uint64_t a, uint64_t b) {
     return d;
 }
 }  // namespace f32x2
-__device__ __forceinline__ void gelu_bias_x2(float v0, float v1, float b0, float b1, float& y0, float& y1) {
+__device__ __forceinline__ void gelu_x2(float x0, float x1, float& y0, float& y1) {
     using namespace f32x2;
-    float x0, x1;
-    upk(add(pk(v0, v1), pk(b0, b1)), x0, x1);
     const uint64_t X = pk(x0, x1), AX = pk(fabsf(x0), fabsf(x1));
     float u0, u1, t0, t1, s0, s1, e0, e1;
     upk(fma(pk(0.23164189f, 0.23164189f), AX, pk(1.f, 1.f)), u0, u1);
@@ -94,6 +92,11 @@ __device__ __forceinline__ void gelu_bias_x2(float v0, float v1, float b0, float
     P = fma(P, T, pk(-0.284496736f, -0.284496736f));
     P = fma(P, T, pk(0.254829592f, 0.254829592f));
     upk(fma(mul(AX, pk(-0.5f, -0.5f)), mul(mul(P, T), pk(e0, e1)), pk(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);
+}
+__device__ __forceinline__ void gelu_bias_x2(float v0, float v1, float b0, float b1, float& y0, float& y1) {
+    float x0, x1;
+    f32x2::upk(f32x2::add(f32x2::pk(v0, v1), f32x2::pk(b0, b1)), x0, x1);
+    gelu_x2(x0, x1, y0, y1);
 }
 
 // Shape contract enforced by the planner (igemm_host.cu): out_ld, out_coff, res_ld and Cout are multiples
@@ -442,7 +445,14 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
+                for (int j = 0; j < 32; j += 2) {
+                    if constexpr (ACT == ACT_GELU) {
+                        gelu_x2(f[j], f[j + 1], f[j], f[j + 1]);  // packed fp32: half the issue slots, same bits
+                    } else {
+                        f[j] = apply_act<ACT>(f[j]);
+                        f[j + 1] = apply_act<ACT>(f[j + 1]);
+                    }
+                }
                 if constexpr (ARGMAX) {
                     // torch.argmax semantics: first maximum wins (columns are visited in ascending order)
 #pragma unroll
