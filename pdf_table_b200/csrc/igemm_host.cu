@@ -532,6 +532,7 @@ int plan_mlp(Engine* e, const __half* h, int M, int C, const __half* w1, const f
     p.x = x;
     p.M = M;
     p.m_tiles = (M + 127) / 128;
+    p.dbg = getenv("DV_MLP_DEBUG") ? atoi(getenv("DV_MLP_DEBUG")) : 0;
     plan->C = C;
     plan->grid = p.m_tiles < e->num_sms ? p.m_tiles : e->num_sms;
     plan->smem = C == 96 ? MlpCfg<96>::SMEM : C == 192 ? MlpCfg<192>::SMEM : MlpCfg<256>::SMEM;

@@ -106,6 +106,10 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                     const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
                     ptx::mbar_wait(ptx::smem_u32(&w1_empty[s]), ph ^ 1u);
                     const uint32_t b1b = ptx::smem_u32(&w1_full[s]);
+                    if (p.dbg == 2 && n >= 2) {  // tuning aid: no weight traffic after the first two chunks (stale weights)
+                        ptx::mbar_arrive(b1b);
+                        continue;
+                    }
                     ptx::mbar_expect_tx(b1b, Cfg::W1_SLOT);
 #pragma unroll
                     for (int kb = 0; kb < KB1; ++kb)
@@ -125,6 +129,10 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                     const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
                     ptx::mbar_wait(ptx::smem_u32(&w2_empty[s]), ph ^ 1u);
                     const uint32_t b2b = ptx::smem_u32(&w2_full[s]);
+                    if (p.dbg == 2 && n >= 2) {
+                        ptx::mbar_arrive(b2b);
+                        continue;
+                    }
                     ptx::mbar_expect_tx(b2b, Cfg::W2_SLOT);
                     ptx::tma_load_2d(sW2 + s * Cfg::W2_SLOT, &p.tmW2, b2b, j * 64, 0);
                 }
@@ -204,12 +212,6 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
             const long long grow = static_cast<long long>(tile) * 128 + row;
             float* xr = p.x + grow * C + part * QC;
             const bool valid = grow < p.M;
-            // the residual rows are needed ~NC chunks from now: start them towards L2 so the final update pays an L2
-            // hit instead of a DRAM round trip
-            if (valid) {
-#pragma unroll
-                for (int k = 0; k < QC * 4; k += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + k / 4));
-            }
             for (int j = grp; j < NC; j += 2) {
                 const uint32_t n = t * NC + j;  // global chunk counter (NC is even: n = grp mod 2)
                 const uint32_t b = n & 1u, ph = (n >> 1) & 1u;
@@ -230,6 +232,13 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float4 bv = bb[i * 2 + e];
+                        if (p.dbg == 1 || p.dbg >= 3) {  // tuning aid: the kernel without its GELU math
+                            f[e * 4 + 0] = __uint_as_float(v[i * 8 + e * 4 + 0]) + bv.x;
+                            f[e * 4 + 1] = __uint_as_float(v[i * 8 + e * 4 + 1]) + bv.y;
+                            f[e * 4 + 2] = __uint_as_float(v[i * 8 + e * 4 + 2]) + bv.z;
+                            f[e * 4 + 3] = __uint_as_float(v[i * 8 + e * 4 + 3]) + bv.w;
+                            continue;
+                        }
                         gelu_bias_x2(__uint_as_float(v[i * 8 + e * 4 + 0]), __uint_as_float(v[i * 8 + e * 4 + 1]), bv.x, bv.y,
                                      f[e * 4 + 0], f[e * 4 + 1]);
                         gelu_bias_x2(__uint_as_float(v[i * 8 + e * 4 + 2]), __uint_as_float(v[i * 8 + e * 4 + 3]), bv.z, bv.w,
@@ -248,33 +257,35 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                 const uint32_t gb = sG + gs * Cfg::G_BYTES + g_row;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (p.dbg == 3) break;  // tuning aid: no hidden-tile stores
                     const uint32_t addr = gb + ((static_cast<uint32_t>(half * 4 + i) ^ static_cast<uint32_t>(row & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[i].x), "r"(o[i].y), "r"(o[i].z),
                                  "r"(o[i].w)
                                  : "memory");
                 }
-                ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+                if (p.dbg != 3) ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&g_full[b]));
             }
             // ---- final: x += acc2 + b2 (this warp: columns [part * C/4, (part + 1) * C/4) of its 32 rows); the residual
             // loads are all in flight before the wait for the last GEMM2
-            constexpr int BATCH = QC > 32 ? QC / 2 : QC;  // 24 / 24 / 32 columns at a time (register budget: 96 per thread)
-            float4 r[BATCH / 4];
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < BATCH / 4; ++i) r[i] = *reinterpret_cast<const float4*>(xr + i * 4);
+            // x += acc2 + b2 as fire-and-forget vector reductions (red.global.add.v4.f32): the fp32 sum is formed at L2, bit for
+            // bit the value a load / add / store would give, but no thread ever waits for x.  With the read-modify-write
+            // form this stage was 40 % of the kernel (0.111 -> 0.068 ms at C = 192 with it stubbed out, tools note in
+            // profiles/r2f_mlp_stage_costs.md): sixteen warps stalled on two DRAM round trips per tile.
+            if (p.dbg == 4) {  // tuning aid: no residual update
+                ptx::mbar_wait(ptx::smem_u32(&acc2_full), t & 1u);
+                ptx::tc_fence_after();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&acc2_empty));
+                continue;
             }
             ptx::mbar_wait(ptx::smem_u32(&acc2_full), t & 1u);
             ptx::tc_fence_after();
+            constexpr int BATCH = QC > 32 ? QC / 2 : QC;  // 24 / 24 / 32 columns per TMEM round trip
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += BATCH) {
-                if (c0 > 0 && valid) {
-#pragma unroll
-                    for (int i = 0; i < BATCH / 4; ++i) r[i] = *reinterpret_cast<const float4*>(xr + c0 + i * 4);
-                }
-                // all of the batch's accumulator columns with ONE wait (one TMEM round trip per 8 columns before: 27 % of the
-                // kernel's samples sat on these loads, profiles/r1z_mlp_ncu.txt)
                 uint32_t w[BATCH / 8][8];
 #pragma unroll
                 for (int c = 0; c < BATCH; c += 8) ptx::tmem_ld_32x32b_x8(t_lane + static_cast<uint32_t>(part * QC + c0 + c), w[c / 8]);
@@ -282,13 +293,11 @@ mlp_fused_tcgen05(const __grid_constant__ MlpParams p) {
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < BATCH / 4; ++i) {
-                        float4 rr = r[i];
                         const float4 bv = *reinterpret_cast<const float4*>(s_b2 + part * QC + c0 + i * 4);
-                        rr.x += __uint_as_float(w[i / 2][(i & 1) * 4 + 0]) + bv.x;
-                        rr.y += __uint_as_float(w[i / 2][(i & 1) * 4 + 1]) + bv.y;
-                        rr.z += __uint_as_float(w[i / 2][(i & 1) * 4 + 2]) + bv.z;
-                        rr.w += __uint_as_float(w[i / 2][(i & 1) * 4 + 3]) + bv.w;
-                        *reinterpret_cast<float4*>(xr + c0 + i * 4) = rr;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xr + c0 + i * 4),
+                                     "f"(__uint_as_float(w[i / 2][(i & 1) * 4 + 0]) + bv.x), "f"(__uint_as_float(w[i / 2][(i & 1) * 4 + 1]) + bv.y),
+                                     "f"(__uint_as_float(w[i / 2][(i & 1) * 4 + 2]) + bv.z), "f"(__uint_as_float(w[i / 2][(i & 1) * 4 + 3]) + bv.w)
+                                     : "memory");
                     }
                 }
             }

@@ -13,6 +13,7 @@ struct MlpParams {
     const float* b2;   // [C]
     float* x;          // [M, C] fp32 residual stream, updated in place
     int M, m_tiles;
+    int dbg;           // tuning aid (DV_MLP_DEBUG): 1 = skip the GELU math (pipeline floor), results are then wrong
 };
 
 }  // namespace dv
