@@ -414,7 +414,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                     }
                 }
                 if constexpr (RES_F32) {
-                    if (res_mode != RES_NONE) {
+                    if (res_mode != RES_NONE && !p.res_red) {
                         const float4* rp =
                             reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + res_pix * res_ld + col0);
 #pragma unroll
@@ -489,6 +489,15 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                             const long long opix = opix0 + static_cast<long long>(dy) * orow_stride + dx;
                             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * out_ld +
                                                                    out_coff + ocol);
+                            if (RES_F32 && p.res_red) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (j * 4 < ncol)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + j), "f"(o[j].x), "f"(o[j].y),
+                                                     "f"(o[j].z), "f"(o[j].w)
+                                                     : "memory");
+                                continue;
+                            }
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 if (j * 4 < ncol) op[j] = o[j];

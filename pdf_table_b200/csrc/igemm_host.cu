@@ -140,6 +140,10 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.out_f32 = es.out_f32;
     p.m_dyn = es.m_dyn;
     p.split_off = es.split_off;
+    p.res_red = (es.res_f32 && es.out_f32 && es.res != nullptr && es.res == es.out && es.res_mode == RES_SAME && es.res_mod == 0 &&
+                 es.res_ld == es.out_ld && es.out_coff == 0 && es.out_mode == OUT_NHWC && es.act == ACT_NONE && es.arg_out == nullptr &&
+                 !(getenv("DV_RES_RED") && atoi(getenv("DV_RES_RED")) == 0))
+                    ? 1 : 0;
     if (es.m_dyn && p.mode != A_FLAT) return set_err(e, DV_ERR_ARG, "%s: m_dyn needs a flat GEMM", name);
     if (es.split_off && (es.out_f32 || es.out_mode != OUT_NHWC || (es.split_off % 8)))
         return set_err(e, DV_ERR_ARG, "%s: split store needs fp16 NHWC output and split_off %% 8 == 0", name);

@@ -39,6 +39,8 @@ struct IGemmParams {
     const void* res;  // fp16 (or fp32 when the kernel is instantiated with RES_F32)
     int res_mode, res_ld;
     int res_mod;      // > 0: residual row = output row % res_mod (broadcast table, e.g. position embeddings)
+    int res_red;      // fp32 stream updated in place (res == out, same layout): the epilogue issues red.global.add.v4.f32
+                      // instead of load / add / store, so no thread waits for the residual (same fp32 sum, formed at L2)
     int n_inner;      // tile order: a CTA walks all n-tiles of its m-tiles (required by the arg-max epilogue)
     int32_t* arg_out;  // ARGMAX epilogue: per-row arg-max over all Cout columns
     float* max_out;    // ARGMAX epilogue: per-row maximum (may be null)
