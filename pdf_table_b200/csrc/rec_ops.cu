@@ -363,22 +363,43 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Persistent and double-buffered: a CTA walks chunks b = blockIdx.x, + gridDim.x, ... and the q | k | v rows of the NEXT chunk
+// arrive by cp.async while the current one is computed.  (One CTA per chunk with a synchronous staging loop spent most of
+// its ~9 us on the load round trip: 128 registers x 480 threads allow one CTA per SM, so nothing else covered it.)
 __global__ void __launch_bounds__(kAttnMmaThreads, 1)
-k_attn75_mma(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
+k_attn75_mma(const __half* __restrict__ qkv, __half* __restrict__ ctx, int B) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    __half* sQ = reinterpret_cast<__half*>(sm_raw);
+    constexpr int kStageHalves = 3 * 80 * kAttnRow;
+    __half* stage0 = reinterpret_cast<__half*>(sm_raw);
+    // rows 75..79 of every staged matrix are zero padding: written once, never touched by the copies
+    for (int i = threadIdx.x; i < 2 * 3 * 5 * (kAttnRow / 8); i += kAttnMmaThreads) {
+        const int m = i / (5 * (kAttnRow / 8)), r = i - m * (5 * (kAttnRow / 8));
+        *reinterpret_cast<uint4*>(stage0 + m * 80 * kAttnRow + 75 * kAttnRow + r * 8) = make_uint4(0, 0, 0, 0);
+    }
+    auto prefetch = [&](int chunk, int st) {
+        if (chunk < B) {
+            const __half* base = qkv + static_cast<long long>(chunk) * 75 * 576;
+            __half* sq = stage0 + st * kStageHalves;
+            for (int i = threadIdx.x; i < 75 * 72; i += kAttnMmaThreads) {  // 72 x 16 B per token row (q | k | v)
+                const int t = i / 72, c8 = i - t * 72;
+                const __half* dst = sq + (c8 / 24) * 80 * kAttnRow + t * kAttnRow + (c8 % 24) * 8;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+                             "l"(base + t * 576 + c8 * 8)
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // an empty group keeps the wait count uniform
+    };
+    prefetch(blockIdx.x, 0);
+    int it = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    const int st = it & 1;
+    prefetch(b + gridDim.x, st ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    __half* sQ = stage0 + st * kStageHalves;
     __half* sK = sQ + 80 * kAttnRow;
     __half* sV = sK + 80 * kAttnRow;
-    const int b = blockIdx.x;
-    const __half* base = qkv + static_cast<long long>(b) * 75 * 576;
-    for (int i = threadIdx.x; i < 80 * 72; i += kAttnMmaThreads) {  // 72 x 16 B per token row (q | k | v)
-        const int t = i / 72, c8 = i - t * 72;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (t < 75) u = __ldg(reinterpret_cast<const uint4*>(base + t * 576 + c8 * 8));
-        __half* dst = (c8 < 24 ? sQ : c8 < 48 ? sK : sV) + t * kAttnRow + (c8 % 24) * 8;
-        *reinterpret_cast<uint4*>(dst) = u;
-    }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = warp / 5, mt = warp - head * 5;
     const uint32_t q_s = static_cast<uint32_t>(__cvta_generic_to_shared(sQ));
@@ -456,6 +477,8 @@ k_attn75_mma(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
         if (r0 < 75) *reinterpret_cast<__half2*>(out + r0 * 192 + dt * 8) = __floats2half2_rn(o[dt][0] * i0, o[dt][1] * i0);
         if (r1 < 75) *reinterpret_cast<__half2*>(out + r1 * 192 + dt * 8) = __floats2half2_rn(o[dt][2] * i1, o[dt][3] * i1);
     }
+    __syncthreads();  // this stage is overwritten by the prefetch of the iteration after next
+    }
 }
 
 template <int C, int H>
@@ -521,11 +544,11 @@ int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* laye
     static const bool use_mma = !(getenv("DV_ATTN_SIMT") && atoi(getenv("DV_ATTN_SIMT")));
     if (!attr_done) {
         DV_CUDA(e, cudaFuncSetAttribute(k_attn75, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        DV_CUDA(e, cudaFuncSetAttribute(k_attn75_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMmaSmem));
+        DV_CUDA(e, cudaFuncSetAttribute(k_attn75_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAttnMmaSmem));
         attr_done = true;
     }
     e->launch_begin(use_mma ? "k_attn75_mma" : "k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
-    if (use_mma) k_attn75_mma<<<B, kAttnMmaThreads, kAttnMmaSmem, e->stream>>>(qkv, ctx);
+    if (use_mma) k_attn75_mma<<<B < e->num_sms ? B : e->num_sms, kAttnMmaThreads, 2 * kAttnMmaSmem, e->stream>>>(qkv, ctx, B);
     else k_attn75<<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
