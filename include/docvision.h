@@ -318,6 +318,20 @@ int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, 
 int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* src_offsets, const int32_t* src_sizes,
                         const int32_t* dst_widths, int n, int dst_h, int dst_w_pad, uint8_t* out);
 /*
+ * The whole det -> rec glue on the device, no host round trip: for each detected quad
+ * OcrCommonUtils.crop_image (utils/ocr/ocr_common_utils.py:214-262: corner ordering, crop size, cv2.getPerspectiveTransform,
+ * cv2.warpPerspective) followed by OCRRecognitionPreprocessor.keepratio_resize (processor_ocr_recognition.py:44-62), bit-exact
+ * against the cv2 calls of the reference (OpenCV 4.13 arithmetic restated: float products + LU with partial pivoting for the
+ * homography, closed-form 3x3 inverse, fixed-point remap and resize).  pages: device uint8 [n_pages, height, width, 3];
+ * quads: device float32 [n, 4, 2] in any corner order (dv_db_boxes output); page_idx: device int32 [n] or NULL (all page 0).
+ * out: device uint8 [n, dst_h, dst_w_pad, 3] = the input of dv_convnextvit_forward_u8 (dst_h 32, dst_w_pad 804);
+ * dst_widths: device int32 [n], 0 where the reference's cv2 call would raise (empty crop / singular quad; the row block is
+ * zero).  minv_ws (double [n, 9]) and sizes_ws (int32 [n, 2] = crop (w, h)) are caller-owned workspaces, readable afterwards.
+ */
+int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* quads,
+                          const int32_t* page_idx, int n, int dst_h, int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws,
+                          int32_t* sizes_ws);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

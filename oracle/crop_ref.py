@@ -116,3 +116,53 @@ def resize_linear(img, dw, dh):
     s0, s1 = hrow[np.clip(sy, 0, sh - 1)], hrow[np.clip(sy + 1, 0, sh - 1)]
     out = (((b0[:, None, None] * (s0 >> 4)) >> 16) + ((b1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def get_perspective_transform(src, dst):
+    """== cv2.getPerspectiveTransform(src, dst) (OpenCV 4.13): the 8x8 system whose four -x*X products are formed in float32
+    (Point2f arithmetic), solved by cv::hal::LU64f (partial pivoting, d = -1/pivot, back substitution) in double."""
+    src = np.asarray(src, np.float32)
+    dst = np.asarray(dst, np.float32)
+    a = np.zeros((8, 8))
+    b = np.zeros(8)
+    for i in range(4):
+        sx, sy, dx, dy = src[i, 0], src[i, 1], dst[i, 0], dst[i, 1]  # float32 scalars: the products below round to float32
+        a[i, 0] = a[i + 4, 3] = sx
+        a[i, 1] = a[i + 4, 4] = sy
+        a[i, 2] = a[i + 4, 5] = 1
+        a[i, 6], a[i, 7], a[i + 4, 6], a[i + 4, 7] = np.float32(-sx * dx), np.float32(-sy * dx), np.float32(-sx * dy), np.float32(-sy * dy)
+        b[i], b[i + 4] = dx, dy
+    for i in range(8):
+        k = i
+        for j in range(i + 1, 8):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if abs(a[k, i]) < np.finfo(np.float64).eps * 100:
+            return None
+        if k != i:
+            a[[i, k], i:] = a[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        d = -1 / a[i, i]
+        for j in range(i + 1, 8):
+            alpha = a[j, i] * d
+            for c in range(i + 1, 8):
+                a[j, c] += alpha * a[i, c]
+            b[j] += alpha * b[i]
+    for i in range(7, -1, -1):
+        s = b[i]
+        for c in range(i + 1, 8):
+            s -= a[i, c] * b[c]
+        b[i] = s / a[i, i]
+    return np.append(b, 1.0).reshape(3, 3)
+
+
+def invert3(t):
+    """== cv2.invert(t)[1] for a 3x3 double matrix (the closed-form cofactor path)."""
+    s = np.asarray(t, np.float64)
+    d = s[0, 0] * (s[1, 1] * s[2, 2] - s[1, 2] * s[2, 1]) - s[0, 1] * (s[1, 0] * s[2, 2] - s[1, 2] * s[2, 0]) + s[0, 2] * (s[1, 0] * s[2, 1] - s[1, 1] * s[2, 0])
+    if d == 0:
+        return None
+    d = 1.0 / d
+    return np.array([(s[1, 1] * s[2, 2] - s[1, 2] * s[2, 1]) * d, (s[0, 2] * s[2, 1] - s[0, 1] * s[2, 2]) * d, (s[0, 1] * s[1, 2] - s[0, 2] * s[1, 1]) * d,
+                     (s[1, 2] * s[2, 0] - s[1, 0] * s[2, 2]) * d, (s[0, 0] * s[2, 2] - s[0, 2] * s[2, 0]) * d, (s[0, 2] * s[1, 0] - s[0, 0] * s[1, 2]) * d,
+                     (s[1, 0] * s[2, 1] - s[1, 1] * s[2, 0]) * d, (s[0, 1] * s[2, 0] - s[0, 0] * s[2, 1]) * d, (s[0, 0] * s[1, 1] - s[0, 1] * s[1, 0]) * d]).reshape(3, 3)

@@ -475,6 +475,18 @@ int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* s
     return op_resize_linear_u8(h, src_packed, reinterpret_cast<const long long*>(src_offsets), src_sizes, dst_widths, n, dst_h, dst_w_pad, out);
 }
 
+int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* quads,
+                          const int32_t* page_idx, int n, int dst_h, int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws,
+                          int32_t* sizes_ws) {
+    if (!h) return DV_ERR_ARG;
+    if (n == 0) return 0;
+    if (!pages_hwc_u8 || !quads || !out || !dst_widths || !minv_ws || !sizes_ws || n < 0 || n_pages <= 0 || height <= 0 || width <= 0 ||
+        dst_h <= 0 || dst_w_pad <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_crop_quads_for_rec: null pointer / bad size");
+    cudaSetDevice(h->device);
+    return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, quads, page_idx, n, dst_h, dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
+}
+
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
                         float* out_nchw_f32) {
     if (!h) return DV_ERR_ARG;

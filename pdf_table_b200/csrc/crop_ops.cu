@@ -122,7 +122,240 @@ k_resize_linear_u8(const uint8_t* __restrict__ src, const long long* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole det -> rec glue without the host: (1) k_quad_homography = the host part of OcrCommonUtils.crop_image
+// (utils/ocr/ocr_common_utils.py:227-257) + cv2.getPerspectiveTransform + cv2.invert per quad, one thread each, in double
+// with explicit _rn intrinsics (no contraction); (2) k_crop_resize_fused = warp + keep-ratio resize in one pass, the resize
+// taps evaluating the warp on the fly, so no variable-size intermediate crop exists and nothing about the launch depends on
+// data the host has not seen.
+//   cv2.getPerspectiveTransform (OpenCV 4.13, imgwarp.cpp) restated: the 8x8 system with rows (x_i, y_i, 1, 0, 0, 0,
+//   -x_i X_i, -y_i X_i | X_i) and (0, 0, 0, x_i, y_i, 1, -x_i Y_i, -y_i Y_i | Y_i), where the four products are formed in
+//   FLOAT (Point2f arithmetic) before the conversion to double -- this is what made the textbook double system differ from
+//   cv2 by 1e-9 --, solved by cv::hal::LU64f: partial pivoting on |a|, d = -1 / pivot, row_j += (a_ji d) row_i, then back
+//   substitution s -= a_ik x_k, x_i = s / a_ii.  cv2.invert of the 3x3: the closed-form cofactor path.  Both checked bit for
+//   bit against cv2 (tools/homography_restatement.py: 500 / 500 and 3000 / 3000 random quads).
+__device__ __forceinline__ double dfms(double a, double b, double c, double d) {  // a*b - c*d, two roundings + one
+    return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d));
+}
+
+__global__ void k_quad_homography(const float* __restrict__ quads /*[n][4][2]*/, int n, int dst_h, int dst_w_max,
+                                  double* __restrict__ minv /*[n][9]*/, int32_t* __restrict__ sizes /*[n][2]*/,
+                                  int32_t* __restrict__ dst_widths /*[n]*/) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double px[4], py[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        px[i] = static_cast<double>(quads[q * 8 + 2 * i]);
+        py[i] = static_cast<double>(quads[q * 8 + 2 * i + 1]);
+    }
+    // corner order: the reference's exchange sort on x, then the left and the right pair on y
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j)
+            if (px[i] > px[j]) {
+                double t = px[i]; px[i] = px[j]; px[j] = t;
+                t = py[i]; py[i] = py[j]; py[j] = t;
+            }
+    if (py[0] > py[1]) {
+        double t = px[0]; px[0] = px[1]; px[1] = t;
+        t = py[0]; py[0] = py[1]; py[1] = t;
+    }
+    if (py[2] > py[3]) {
+        double t = px[2]; px[2] = px[3]; px[3] = t;
+        t = py[2]; py[2] = py[3]; py[3] = t;
+    }
+    const double x1 = px[0], y1 = py[0], x2 = px[2], y2 = py[2], x3 = px[3], y3 = py[3], x4 = px[1], y4 = py[1];
+    auto dist = [](double xa, double ya, double xb, double yb) {
+        const double dx = __dsub_rn(xa, xb), dy = __dsub_rn(ya, yb);
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    };
+    const double img_w = dist(__ddiv_rn(__dadd_rn(x1, x4), 2.0), __ddiv_rn(__dadd_rn(y1, y4), 2.0), __ddiv_rn(__dadd_rn(x2, x3), 2.0),
+                              __ddiv_rn(__dadd_rn(y2, y3), 2.0));
+    const double img_h = dist(__ddiv_rn(__dadd_rn(x1, x2), 2.0), __ddiv_rn(__dadd_rn(y1, y2), 2.0), __ddiv_rn(__dadd_rn(x4, x3), 2.0),
+                              __ddiv_rn(__dadd_rn(y4, y3), 2.0));
+    const int w = static_cast<int>(img_w), h = static_cast<int>(img_h);
+    sizes[2 * q] = w;
+    sizes[2 * q + 1] = h;
+    dst_widths[q] = 0;
+    if (w <= 0 || h <= 0) return;
+    const double ratio = __ddiv_rn(static_cast<double>(w), static_cast<double>(h));
+    const int cur_w = ratio > __ddiv_rn(static_cast<double>(dst_w_max), static_cast<double>(dst_h))
+                          ? dst_w_max
+                          : static_cast<int>(__dmul_rn(static_cast<double>(dst_h), ratio));
+    if (cur_w <= 0) return;
+    // float32 corner arrays: src = (x1,y1), (x2,y2), (x4,y4), (x3,y3);  dst = (0,0), (W-1,0), (0,H-1), (W-1,H-1)
+    const float sx[4] = {static_cast<float>(x1), static_cast<float>(x2), static_cast<float>(x4), static_cast<float>(x3)};
+    const float sy[4] = {static_cast<float>(y1), static_cast<float>(y2), static_cast<float>(y4), static_cast<float>(y3)};
+    const float tw = static_cast<float>(__dsub_rn(img_w, 1.0)), th = static_cast<float>(__dsub_rn(img_h, 1.0));
+    const float dxs[4] = {0.f, tw, 0.f, tw}, dys[4] = {0.f, 0.f, th, th};
+    double A[8][8], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) A[i][k] = A[i + 4][k] = 0.0;
+        A[i][0] = A[i + 4][3] = static_cast<double>(sx[i]);
+        A[i][1] = A[i + 4][4] = static_cast<double>(sy[i]);
+        A[i][2] = A[i + 4][5] = 1.0;
+        A[i][6] = static_cast<double>(__fmul_rn(-sx[i], dxs[i]));  // products in float, as Point2f arithmetic
+        A[i][7] = static_cast<double>(__fmul_rn(-sy[i], dxs[i]));
+        A[i + 4][6] = static_cast<double>(__fmul_rn(-sx[i], dys[i]));
+        A[i + 4][7] = static_cast<double>(__fmul_rn(-sy[i], dys[i]));
+        b[i] = static_cast<double>(dxs[i]);
+        b[i + 4] = static_cast<double>(dys[i]);
+    }
+    for (int i = 0; i < 8; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 8; ++j)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (fabs(A[k][i]) < 2.220446049250313e-16 * 100) return;  // singular (a degenerate quad): cv2 gives no usable transform
+        if (k != i) {
+            for (int j = i; j < 8; ++j) {
+                const double t = A[i][j]; A[i][j] = A[k][j]; A[k][j] = t;
+            }
+            const double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        const double d = __ddiv_rn(-1.0, A[i][i]);
+        for (int j = i + 1; j < 8; ++j) {
+            const double alpha = __dmul_rn(A[j][i], d);
+            for (int c = i + 1; c < 8; ++c) A[j][c] = __dadd_rn(A[j][c], __dmul_rn(alpha, A[i][c]));
+            b[j] = __dadd_rn(b[j], __dmul_rn(alpha, b[i]));
+        }
+    }
+    for (int i = 7; i >= 0; --i) {
+        double s = b[i];
+        for (int c = i + 1; c < 8; ++c) s = __dsub_rn(s, __dmul_rn(A[i][c], b[c]));
+        b[i] = __ddiv_rn(s, A[i][i]);
+    }
+    // T = [b0 b1 b2; b3 b4 b5; b6 b7 1]; cv2.invert (3x3 closed form)
+    const double S00 = b[0], S01 = b[1], S02 = b[2], S10 = b[3], S11 = b[4], S12 = b[5], S20 = b[6], S21 = b[7], S22 = 1.0;
+    double det = __dadd_rn(__dsub_rn(__dmul_rn(S00, dfms(S11, S22, S12, S21)), __dmul_rn(S01, dfms(S10, S22, S12, S20))),
+                           __dmul_rn(S02, dfms(S10, S21, S11, S20)));
+    if (det == 0.0) return;
+    det = __ddiv_rn(1.0, det);
+    double* M = minv + 9 * q;
+    M[0] = __dmul_rn(dfms(S11, S22, S12, S21), det);
+    M[1] = __dmul_rn(dfms(S02, S21, S01, S22), det);
+    M[2] = __dmul_rn(dfms(S01, S12, S02, S11), det);
+    M[3] = __dmul_rn(dfms(S12, S20, S10, S22), det);
+    M[4] = __dmul_rn(dfms(S00, S22, S02, S20), det);
+    M[5] = __dmul_rn(dfms(S02, S10, S00, S12), det);
+    M[6] = __dmul_rn(dfms(S10, S21, S11, S20), det);
+    M[7] = __dmul_rn(dfms(S01, S20, S00, S21), det);
+    M[8] = __dmul_rn(dfms(S00, S11, S01, S10), det);
+    dst_widths[q] = cur_w;
+}
+
+// one pixel of cv2.warpPerspective(page, T, (w, h)) -- the body of k_warp_perspective_u8
+__device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ img, int H, int W, const double* __restrict__ M, int w, int h,
+                                           int x, int y, int (&v)[3]) {
+    const int bh0 = min(16, h);
+    const int bw0 = min(1024 / bh0, w);
+    const int xb = x / bw0 * bw0, x1 = x - xb;
+    const double dxb = static_cast<double>(xb), dy = static_cast<double>(y), dx1 = static_cast<double>(x1);
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dxb), __dmul_rn(M[1], dy)), M[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], dxb), __dmul_rn(M[4], dy)), M[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], dxb), __dmul_rn(M[7], dy)), M[8]);
+    double Wd = __dadd_rn(W0, __dmul_rn(M[6], dx1));
+    Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), Wd)));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), Wd)));
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int ax = X & 31, ay = Y & 31;
+    const int wt[4] = {(32 - ax) * (32 - ay) * 32, ax * (32 - ay) * 32, (32 - ax) * ay * 32, ax * ay * 32};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = sy + (t >> 1), xx = sx + (t & 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const uint8_t* p = img + (static_cast<long long>(yy) * W + xx) * 3;
+            acc[0] += p[0] * wt[t];
+            acc[1] += p[1] * wt[t];
+            acc[2] += p[2] * wt[t];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (acc[c] + (1 << 14)) >> 15;
+}
+
+__global__ void __launch_bounds__(256)
+k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32_t* __restrict__ page_idx, const double* __restrict__ minv,
+                    const int32_t* __restrict__ sizes, const int32_t* __restrict__ dst_widths, int dst_h, int dst_w_pad,
+                    uint8_t* __restrict__ out) {
+    const int crop = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= dst_h * dst_w_pad) return;
+    const int dy = idx / dst_w_pad, dx = idx - dy * dst_w_pad;
+    uint8_t* o = out + (static_cast<long long>(crop) * dst_h * dst_w_pad + idx) * 3;
+    const int dw = dst_widths[crop];
+    if (dx >= dw) {  // zero padding; a skipped quad (dw == 0) is an all-zero row block
+        o[0] = o[1] = o[2] = 0;
+        return;
+    }
+    const int sw = sizes[2 * crop], sh = sizes[2 * crop + 1];
+    const uint8_t* img = pages + static_cast<long long>(page_idx ? page_idx[crop] : 0) * H * W * 3;
+    const double* M = minv + 9 * crop;
+    int p00[3], p01[3], p10[3], p11[3];
+    if (sw == 2 * dw && sh == 2 * dst_h) {
+        warp_pixel(img, H, W, M, sw, sh, 2 * dx, 2 * dy, p00);
+        warp_pixel(img, H, W, M, sw, sh, 2 * dx + 1, 2 * dy, p01);
+        warp_pixel(img, H, W, M, sw, sh, 2 * dx, 2 * dy + 1, p10);
+        warp_pixel(img, H, W, M, sw, sh, 2 * dx + 1, 2 * dy + 1, p11);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p00[c] + p01[c] + p10[c] + p11[c] + 2) >> 2);
+        return;
+    }
+    const double scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dw), static_cast<double>(sw)));
+    const double scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dst_h), static_cast<double>(sh)));
+    float fx = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dx), 0.5), scale_x), 0.5));
+    int sx = static_cast<int>(floorf(fx));
+    fx = __fsub_rn(fx, static_cast<float>(sx));
+    if (sx < 0) {
+        sx = 0;
+        fx = 0.f;
+    }
+    if (sx >= sw - 1) {
+        sx = sw - 1;
+        fx = 0.f;
+    }
+    float fy = static_cast<float>(__dsub_rn(__dmul_rn(__dadd_rn(static_cast<double>(dy), 0.5), scale_y), 0.5));
+    const int sy = static_cast<int>(floorf(fy));
+    fy = __fsub_rn(fy, static_cast<float>(sy));
+    const int a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)), a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+    const int b0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)), b1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+    const int sx1 = min(sx + 1, sw - 1);
+    const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
+    warp_pixel(img, H, W, M, sw, sh, sx, r0, p00);
+    warp_pixel(img, H, W, M, sw, sh, sx1, r0, p01);
+    warp_pixel(img, H, W, M, sw, sh, sx, r1, p10);
+    warp_pixel(img, H, W, M, sw, sh, sx1, r1, p11);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = p00[c] * a0 + p01[c] * a1;
+        const int h1 = p10[c] * a0 + p11[c] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+    }
+}
+
 }  // namespace
+
+int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx, int n, int dst_h,
+                          int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
+    if (n <= 0) return 0;
+    if (n > 65535) return set_err(e, DV_ERR_UNSUPPORTED, "crop_quads_for_rec: more than 65535 quads per call");
+    e->launch_begin("k_quad_homography", "crop", 0.0, n * 120.0);
+    k_quad_homography<<<(n + 63) / 64, 64, 0, e->stream>>>(quads, n, dst_h, dst_w_pad, minv_ws, sizes_ws, dst_widths);
+    e->launch_end();
+    const int px = dst_h * dst_w_pad;
+    e->launch_begin("k_crop_resize_fused", "crop", 0.0, static_cast<double>(n) * px * 3.0 * 2.0);
+    k_crop_resize_fused<<<dim3((px + 255) / 256, n), 256, 0, e->stream>>>(pages, H, W, page_idx, minv_ws, sizes_ws, dst_widths, dst_h, dst_w_pad, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
 
 int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off, const int32_t* src_sizes, const int32_t* dst_widths,
                         int n, int dst_h, int dst_w_pad, uint8_t* out) {

@@ -191,6 +191,32 @@ class Engine:
               self._h, "dv_resize_linear_u8")
         return out
 
+    def crop_quads_for_rec(self, pages: torch.Tensor, quads: torch.Tensor, page_idx: Optional[torch.Tensor] = None, dst_h: int = 32,
+                           dst_w_pad: int = 804):
+        """pages uint8 [P,H,W,3] (or [H,W,3]) + quads float32 [n,4,2] (+ page index int32 [n]), all cuda -> (crops uint8
+        [n,dst_h,dst_w_pad,3], widths int32 [n] (0 = skipped), crop sizes int32 [n,2], inverse homographies float64 [n,3,3]),
+        all on the device: crop_image + keepratio_resize of the reference for every quad, no host round trip."""
+        pages = _require_cuda(pages, torch.uint8, "pages")
+        if pages.dim() == 3:
+            pages = pages.unsqueeze(0)
+        quads = _require_cuda(quads, torch.float32, "quads").reshape(-1, 8)
+        n = quads.shape[0]
+        pp, hh, ww, c = pages.shape
+        if c != 3:
+            raise ValueError("pages must be [P,H,W,3]")
+        if page_idx is not None:
+            page_idx = _require_cuda(page_idx, torch.int32, "page_idx")
+            if page_idx.numel() != n:
+                raise ValueError("one page index per quad")
+        dev = pages.device
+        out = torch.empty((n, dst_h, dst_w_pad, 3), dtype=torch.uint8, device=dev)
+        widths = torch.empty((n,), dtype=torch.int32, device=dev)
+        minv = torch.empty((n, 3, 3), dtype=torch.float64, device=dev)
+        sizes = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        check(self._lib.dv_crop_quads_for_rec(self._h, _ptr(pages), pp, hh, ww, _ptr(quads), _ptr(page_idx), n, dst_h, dst_w_pad,
+                                              _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_quads_for_rec")
+        return out, widths, sizes, minv
+
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
         crops = _require_cuda(crops, torch.uint8, "crops")

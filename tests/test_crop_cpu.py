@@ -72,3 +72,19 @@ def test_resize_restatement_equals_cv2():
         img = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
         dw = int(rng.integers(16, 1281))
         assert np.array_equal(ref.resize_linear(img, dw, 48), cv2.resize(img, (dw, 48))), (trial, hh, ww, dw)
+
+
+def test_homography_restatement_equals_cv2():
+    """cv2.getPerspectiveTransform and cv2.invert restated (what k_quad_homography computes per quad) -- bit for bit."""
+    rng = np.random.default_rng(4)
+    for trial in range(150):
+        cx, cy = rng.uniform(0, 960), rng.uniform(0, 960)
+        bw, bh, ang = rng.uniform(4, 600), rng.uniform(3, 100), rng.uniform(-0.8, 0.8)
+        c, s = math.cos(ang), math.sin(ang)
+        pts = np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+        if trial % 2:
+            pts = np.rint(pts + rng.uniform(-2, 2, pts.shape))
+        corners, trans, _ = ref.crop_geometry(pts.astype(np.float32))
+        t = cv2.getPerspectiveTransform(corners, trans)
+        assert np.array_equal(ref.get_perspective_transform(corners, trans), t), trial
+        assert np.array_equal(ref.invert3(t), cv2.invert(t)[1]), trial

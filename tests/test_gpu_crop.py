@@ -92,3 +92,42 @@ def test_crops_for_recognition_match_host_pipeline(eng):
         assert not got[row, :, w:].any()
         exact2x += int(crop.shape[0] == 64 and crop.shape[1] == 2 * w)
     assert len(keep) > 100 and exact2x > 0
+
+
+def test_device_only_glue_matches_cv2(eng):
+    """dv_crop_quads_for_rec: geometry + homography + inverse + warp + keep-ratio resize with no host step, against the
+    reference's host calls (crop_geometry rule, cv2.getPerspectiveTransform, cv2.invert, cv2.warpPerspective, cv2.resize)."""
+    rng = np.random.default_rng(33)
+    pages = rng.integers(0, 256, (2, 500, 700, 3), dtype=np.uint8)
+    quads, pidx = [], []
+    for k in range(160):
+        cx, cy = rng.uniform(0, 700), rng.uniform(0, 500)
+        bw, bh, ang = rng.uniform(3, 650), rng.uniform(2, 90), rng.uniform(-0.6, 0.6)
+        if k % 9 == 0:
+            bw, bh, ang = 2 * float(rng.integers(20, 150)) + 0.2, 64.2, 0.0
+        c, s = math.cos(ang), math.sin(ang)
+        p = np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]]) @ np.array([[c, s], [-s, c]]) + [cx, cy]
+        p = np.roll(p, k % 4, axis=0)
+        quads.append((np.rint(p) if k % 3 == 0 else p).astype(np.float32))
+        pidx.append(k % 2)
+    quads.append(np.array([[10, 10], [10.4, 10], [10.4, 30], [10, 30]], np.float32))  # zero-width crop
+    pidx.append(0)
+    q = torch.from_numpy(np.stack(quads)).cuda()
+    out, widths, sizes, minv = eng.crop_quads_for_rec(torch.from_numpy(pages).cuda(), q, torch.tensor(pidx, dtype=torch.int32, device="cuda"))
+    out, widths, sizes, minv = out.cpu().numpy(), widths.cpu().numpy(), sizes.cpu().numpy(), minv.cpu().numpy()
+    assert widths[-1] == 0 and not out[-1].any()
+    checked = 0
+    for k, quad in enumerate(quads[:-1]):
+        corners, trans, (w, h) = predictors.crop_geometry(quad)
+        assert (sizes[k, 0], sizes[k, 1]) == (w, h), k
+        if w <= 0 or h <= 0:
+            assert widths[k] == 0
+            continue
+        t = cv2.getPerspectiveTransform(corners, trans)
+        assert np.array_equal(minv[k], cv2.invert(t)[1]), k
+        want = predictors.keepratio_resize(cv2.warpPerspective(pages[pidx[k]], t, (w, h)))
+        assert widths[k] == want.shape[1], k
+        assert np.array_equal(out[k, :, : widths[k]], want), k
+        assert not out[k, :, widths[k]:].any()
+        checked += 1
+    assert checked > 140
