@@ -166,7 +166,8 @@ def make_ctc_probs(rank: int, n_crops: int) -> np.ndarray:
 class Cascade:
     """The B200 arm: product code only (pdf_table_b200), no oracle imports."""
 
-    stages = ["det_preprocess_u8", "dbnet_r18_forward", "db_boxes(planted prob maps)", "rec_preprocess_u8(fused)",
+    stages = ["det_preprocess_u8", "dbnet_r18_forward", "db_boxes(planted prob maps)", "crop_boxes_for_rec(homography + warp + keep-ratio resize)",
+              "rec_preprocess_u8(fused)",
               "convnextvit_forward+argmax",
               "ctc_collapse", "ctc_greedy_decode(planted PP-OCR probs)"]
 
@@ -182,7 +183,6 @@ class Cascade:
         self.n_crops = PAGES_PER_GPU * CROPS_PER_PAGE
         self.pages_host = torch.from_numpy(make_pages(rank, self.n_pages)).pin_memory()
         self.probs_host = torch.from_numpy(make_ctc_probs(rank, self.n_crops)).pin_memory()
-        self.crops_host = torch.from_numpy(make_crops(rank, self.n_crops)).pin_memory()
         self.planted_maps = torch.from_numpy(make_prob_maps(rank, self.n_pages)).to(torch.device("cuda", device))
         self.src_hw = [(PAGE_H, PAGE_W)] * self.n_pages
         self.box_host = torch.empty((self.n_pages, 1000, 8), dtype=torch.float32).pin_memory()
@@ -190,8 +190,11 @@ class Cascade:
         dev = torch.device("cuda", device)
         self.pages_dev = self.pages_host.to(dev)
         self.probs_dev = self.probs_host.to(dev)
-        self.crops_dev = self.crops_host.to(dev)
-        self.crops_stage = torch.empty_like(self.crops_dev)
+        # det -> rec glue on the device: CROPS_PER_PAGE crop slots per page cut from the db_boxes quads (slots beyond a page's box
+        # count are zero crops), written straight into the recogniser's padded uint8 input
+        self.rec_crops = torch.empty((self.n_crops, 32, 804, 3), dtype=torch.uint8, device=dev)
+        self.crop_ws = (torch.empty((self.n_crops,), dtype=torch.int32, device=dev), torch.empty((self.n_crops, 2), dtype=torch.int32, device=dev),
+                        torch.empty((self.n_crops, 3, 3), dtype=torch.float64, device=dev))
         self.tok_ids = torch.empty((self.n_crops, 201), dtype=torch.int32, device=dev)
         self.rec_ids_host = torch.empty((self.n_crops, 201), dtype=torch.int32).pin_memory()
         self.rec_len_host = torch.empty((self.n_crops,), dtype=torch.int32).pin_memory()
@@ -208,7 +211,8 @@ class Cascade:
         """Inputs resident in HBM."""
         self.det.dbnet_forward_u8(self.pages_dev, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
         self.boxes = self.post.db_boxes(self.planted_maps, self.src_hw)
-        self.rec.convnextvit_forward_u8(self.crops_dev, ids=self.tok_ids)
+        self.post.crop_boxes_for_rec(self.pages_dev, self.boxes[0], self.boxes[1], CROPS_PER_PAGE, out=self.rec_crops, ws=self.crop_ws)
+        self.rec.convnextvit_forward_u8(self.rec_crops, ids=self.tok_ids)
         self.rec_out = self.post.ctc_collapse(self.tok_ids)
         return self.post.ctc_greedy(self.probs_dev)
 
@@ -216,12 +220,12 @@ class Cascade:
         """Host (pinned) buffers in, host results out: H2D + D2H inside."""
         self.pages_stage.copy_(self.pages_host, non_blocking=True)
         self.probs_stage.copy_(self.probs_host, non_blocking=True)
-        self.crops_stage.copy_(self.crops_host, non_blocking=True)
         self.det.dbnet_forward_u8(self.pages_stage, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
         boxes, counts = self.post.db_boxes(self.planted_maps, self.src_hw)
         self.box_host.copy_(boxes, non_blocking=True)
         self.cnt_host.copy_(counts, non_blocking=True)
-        self.rec.convnextvit_forward_u8(self.crops_stage, ids=self.tok_ids)
+        self.post.crop_boxes_for_rec(self.pages_stage, boxes, counts, CROPS_PER_PAGE, out=self.rec_crops, ws=self.crop_ws)
+        self.rec.convnextvit_forward_u8(self.rec_crops, ids=self.tok_ids)
         r_ids, r_len, _ = self.post.ctc_collapse(self.tok_ids)
         self.rec_ids_host.copy_(r_ids, non_blocking=True)
         self.rec_len_host.copy_(r_len, non_blocking=True)
@@ -233,7 +237,7 @@ class Cascade:
 
     @property
     def h2d_bytes(self):
-        return self.pages_host.numel() + self.probs_host.numel() * 4 + self.crops_host.numel()
+        return self.pages_host.numel() + self.probs_host.numel() * 4
 
     @property
     def d2h_bytes(self):
@@ -362,8 +366,22 @@ def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, s
         x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
         dbnet_ref.dbnet_r18_forward(sd, x)
     if sample_maps is not None:
-        for m in sample_maps:
-            db_post_ref.db_postprocess(m[0], np.array([PAGE_H, PAGE_W, 1.0, 1.0]), (PAGE_H, PAGE_W, 3))
+        from oracle import crop_ref
+
+        cut = []
+        for pg, m in zip(sample_pages, sample_maps):
+            boxes = db_post_ref.db_postprocess(m[0], np.array([PAGE_H, PAGE_W, 1.0, 1.0]), (PAGE_H, PAGE_W, 3))
+            page_crops = []
+            for b in boxes[:CROPS_PER_PAGE]:  # OcrCommonUtils.crop_image per detected quad (ocr_system_task.py:300-313)
+                try:
+                    page_crops.append(crop_ref.crop_image(pg, b.reshape(4, 2)))
+                except Exception:  # an empty crop: cv2 raises, the reference's orchestrator skips the box
+                    pass
+            # the B200 arm runs CROPS_PER_PAGE recogniser slots per page (zero crops beyond the box count): same work here
+            page_crops += [np.zeros((32, 320, 3), np.uint8)] * (CROPS_PER_PAGE - len(page_crops))
+            cut += page_crops
+        if sample_crops is not None:
+            sample_crops = cut[:len(sample_crops)]
     if sample_crops is not None:
         for i in range(0, len(sample_crops), 16):  # batches of 16 crops (48 chunks)
             chunks = convnextvit_ref.preprocess(list(sample_crops[i:i + 16]))
@@ -453,8 +471,8 @@ def run_reference(args, rank: int):
         cpu_reference_step(pages, probs, sd, crops, rec_sd, maps)
     dt = (time.perf_counter() - t0) / args.steps
     v = n_pages / dt
-    sample = (f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step, each with {CROPS_PER_PAGE} text-line crops through ConvNextViT "
-              "(+ planted CTC decode)" + (", PicoDet layout and Lore table structure on one table crop per page" if FULL else "") + ", torch fp32 on host cores")
+    sample = (f"{n_pages} of {PAGES_PER_GPU} pages 960x960 per step, each with {CROPS_PER_PAGE} text-line crop slots cut from the page at the detected quads "
+              "(crop_image + keepratio_resize) through ConvNextViT (+ planted CTC decode)" + (", PicoDet layout and Lore table structure on one table crop per page" if FULL else "") + ", torch fp32 on host cores")
     line = {
         "impl": "reference", "metric": "pages_per_sec", "value": v, "unit": "pages/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -483,12 +501,12 @@ def _workload_config():
         "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
         "stages": Cascade.stages,
         "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
-        "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} planted "
-                     "uint8 32x320 crops per page, seeded random weights",
+        "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} crop slots per "
+                     "page cut on the device from the db_boxes quads of that page (crop_image + keepratio_resize, bit-exact vs cv2; slots beyond "
+                     "a page's box count are zero crops and cost the same recogniser work), seeded random weights",
         "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
         "db_post_stage": "db_boxes on planted probability maps (analytic text-line blobs, ~40 per page): with random weights the "
                          "detector's own map is texture noise",
-        "not_in_timed_step": "perspective crop extraction: the warp / resize kernels exist and are bit-exact against cv2 (tests/test_gpu_crop.py) but the per-quad homography solve is host cv2, so the recogniser reads planted crops",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
         "parallelism": "page-sharded replicas, one process per GPU",
@@ -627,7 +645,7 @@ def main():
             ns = 2 if FULL else 4
             v, cores, secs = time_cpu_baseline(ns)
             cpu = {"value": v, "unit": "pages/s", "cores": cores, "kind": "port",
-                   "sample": f"{ns} of {PAGES_PER_GPU} pages with {ns * CROPS_PER_PAGE} crops (" + ("layout + det + rec + decode + table structure" if FULL else "det + rec + decode") +
+                   "sample": f"{ns} of {PAGES_PER_GPU} pages with {ns * CROPS_PER_PAGE} crop slots (" + ("layout + det + crop + rec + decode + table structure" if FULL else "det + crop + rec + decode") +
                              f"), oracle/ restatement in torch fp32, {secs:.1f} s"}
         line = {
             "metric": "pages_per_sec", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,

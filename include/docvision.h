@@ -332,6 +332,14 @@ int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
                           const int32_t* page_idx, int n, int dst_h, int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws,
                           int32_t* sizes_ws);
 /*
+ * The same, reading dv_db_boxes' outputs directly: boxes device float32 [n_pages, box_stride, 8], box_counts device int32
+ * [n_pages]; every page gets per_page crop slots (slot k = box k of that page, skipped with width 0 when k >= its count), so
+ * the detector's result never visits the host between detection and recognition.  out: [n_pages * per_page, dst_h, dst_w_pad, 3].
+ */
+int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* boxes,
+                          const int32_t* box_counts, int box_stride, int per_page, int dst_h, int dst_w_pad, uint8_t* out,
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

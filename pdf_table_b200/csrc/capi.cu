@@ -484,7 +484,20 @@ int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
         dst_h <= 0 || dst_w_pad <= 0)
         return set_err(h, DV_ERR_ARG, "dv_crop_quads_for_rec: null pointer / bad size");
     cudaSetDevice(h->device);
-    return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, quads, page_idx, n, dst_h, dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
+    return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, quads, page_idx, nullptr, 0, 0, n, dst_h, dst_w_pad, out, dst_widths, minv_ws,
+                                 sizes_ws);
+}
+
+int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* boxes,
+                          const int32_t* box_counts, int box_stride, int per_page, int dst_h, int dst_w_pad, uint8_t* out,
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
+    if (!h) return DV_ERR_ARG;
+    if (!pages_hwc_u8 || !boxes || !box_counts || !out || !dst_widths || !minv_ws || !sizes_ws || n_pages <= 0 || height <= 0 || width <= 0 ||
+        box_stride <= 0 || per_page <= 0 || per_page > box_stride || dst_h <= 0 || dst_w_pad <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_crop_boxes_for_rec: null pointer / bad size");
+    cudaSetDevice(h->device);
+    return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, boxes, nullptr, box_counts, box_stride, per_page, n_pages * per_page, dst_h,
+                                 dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
 }
 
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,

@@ -138,16 +138,28 @@ __device__ __forceinline__ double dfms(double a, double b, double c, double d) {
     return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d));
 }
 
-__global__ void k_quad_homography(const float* __restrict__ quads /*[n][4][2]*/, int n, int dst_h, int dst_w_max,
-                                  double* __restrict__ minv /*[n][9]*/, int32_t* __restrict__ sizes /*[n][2]*/,
-                                  int32_t* __restrict__ dst_widths /*[n]*/) {
+// quads: [n][4][2], or -- with box_counts -- the dv_db_boxes output [pages][box_stride][8] read as per_page slots per page
+// (slot k of page p = box k if k < box_counts[p], else skipped)
+__global__ void k_quad_homography(const float* __restrict__ quads, const int32_t* __restrict__ box_counts, int box_stride, int per_page,
+                                  int n, int dst_h, int dst_w_max, double* __restrict__ minv /*[n][9]*/,
+                                  int32_t* __restrict__ sizes /*[n][2]*/, int32_t* __restrict__ dst_widths /*[n]*/) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
+    const float* src = quads + static_cast<long long>(q) * 8;
+    if (box_counts != nullptr) {
+        const int pg = q / per_page, k = q - pg * per_page;
+        if (k >= box_counts[pg]) {
+            sizes[2 * q] = sizes[2 * q + 1] = 0;
+            dst_widths[q] = 0;
+            return;
+        }
+        src = quads + (static_cast<long long>(pg) * box_stride + k) * 8;
+    }
     double px[4], py[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        px[i] = static_cast<double>(quads[q * 8 + 2 * i]);
-        py[i] = static_cast<double>(quads[q * 8 + 2 * i + 1]);
+        px[i] = static_cast<double>(src[2 * i]);
+        py[i] = static_cast<double>(src[2 * i + 1]);
     }
     // corner order: the reference's exchange sort on x, then the left and the right pair on y
 #pragma unroll
@@ -281,7 +293,8 @@ __device__ __forceinline__ void warp_pixel(const uint8_t* __restrict__ img, int 
 }
 
 __global__ void __launch_bounds__(256)
-k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32_t* __restrict__ page_idx, const double* __restrict__ minv,
+k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32_t* __restrict__ page_idx, int per_page,
+                    const double* __restrict__ minv,
                     const int32_t* __restrict__ sizes, const int32_t* __restrict__ dst_widths, int dst_h, int dst_w_pad,
                     uint8_t* __restrict__ out) {
     const int crop = blockIdx.y;
@@ -295,7 +308,7 @@ k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32
         return;
     }
     const int sw = sizes[2 * crop], sh = sizes[2 * crop + 1];
-    const uint8_t* img = pages + static_cast<long long>(page_idx ? page_idx[crop] : 0) * H * W * 3;
+    const uint8_t* img = pages + static_cast<long long>(page_idx ? page_idx[crop] : (per_page > 0 ? crop / per_page : 0)) * H * W * 3;
     const double* M = minv + 9 * crop;
     int p00[3], p01[3], p10[3], p11[3];
     if (sw == 2 * dw && sh == 2 * dst_h) {
@@ -342,16 +355,19 @@ k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32
 
 }  // namespace
 
-int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx, int n, int dst_h,
-                          int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
+int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
+                          const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
     if (n <= 0) return 0;
     if (n > 65535) return set_err(e, DV_ERR_UNSUPPORTED, "crop_quads_for_rec: more than 65535 quads per call");
     e->launch_begin("k_quad_homography", "crop", 0.0, n * 120.0);
-    k_quad_homography<<<(n + 63) / 64, 64, 0, e->stream>>>(quads, n, dst_h, dst_w_pad, minv_ws, sizes_ws, dst_widths);
+    k_quad_homography<<<(n + 63) / 64, 64, 0, e->stream>>>(quads, box_counts, box_stride, per_page, n, dst_h, dst_w_pad, minv_ws, sizes_ws,
+                                                           dst_widths);
     e->launch_end();
     const int px = dst_h * dst_w_pad;
     e->launch_begin("k_crop_resize_fused", "crop", 0.0, static_cast<double>(n) * px * 3.0 * 2.0);
-    k_crop_resize_fused<<<dim3((px + 255) / 256, n), 256, 0, e->stream>>>(pages, H, W, page_idx, minv_ws, sizes_ws, dst_widths, dst_h, dst_w_pad, out);
+    k_crop_resize_fused<<<dim3((px + 255) / 256, n), 256, 0, e->stream>>>(pages, H, W, page_idx, box_counts ? per_page : 0, minv_ws, sizes_ws,
+                                                                          dst_widths, dst_h, dst_w_pad, out);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -217,6 +217,29 @@ class Engine:
                                               _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_quads_for_rec")
         return out, widths, sizes, minv
 
+    def crop_boxes_for_rec(self, pages: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor, per_page: int, dst_h: int = 32,
+                           dst_w_pad: int = 804, out: Optional[torch.Tensor] = None, ws=None):
+        """crop_quads_for_rec on db_boxes' own outputs: boxes float32 [P,S,8] + counts int32 [P] (cuda) -> per_page crop slots per
+        page, (crops uint8 [P*per_page,dst_h,dst_w_pad,3], widths int32 [P*per_page], sizes, minv).  ``out`` / ``ws`` = (widths,
+        sizes, minv) may be passed in to reuse buffers (no allocation on the hot path)."""
+        pages = _require_cuda(pages, torch.uint8, "pages")
+        boxes = _require_cuda(boxes, torch.float32, "boxes")
+        counts = _require_cuda(counts, torch.int32, "counts")
+        pp, hh, ww, c = pages.shape
+        if c != 3 or boxes.dim() != 3 or boxes.shape[0] != pp or boxes.shape[2] != 8 or counts.numel() != pp:
+            raise ValueError("pages [P,H,W,3], boxes [P,S,8], counts [P]")
+        n = pp * per_page
+        dev = pages.device
+        if out is None:
+            out = torch.empty((n, dst_h, dst_w_pad, 3), dtype=torch.uint8, device=dev)
+        if ws is None:
+            ws = (torch.empty((n,), dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.int32, device=dev),
+                  torch.empty((n, 3, 3), dtype=torch.float64, device=dev))
+        widths, sizes, minv = ws
+        check(self._lib.dv_crop_boxes_for_rec(self._h, _ptr(pages), pp, hh, ww, _ptr(boxes), _ptr(counts), boxes.shape[1], per_page, dst_h,
+                                              dst_w_pad, _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_boxes_for_rec")
+        return out, widths, sizes, minv
+
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
         crops = _require_cuda(crops, torch.uint8, "crops")

@@ -382,14 +382,17 @@ class OcrRecognitionTask(BaseInferTask):
         cuda tensor.  Returns one string per quad (None where the reference's crop would be empty)."""
         dev = torch.device("cuda", self.device)
         page_dev = page if isinstance(page, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(page)).to(dev)
-        crops, _, keep = crops_for_recognition(self.post, page_dev, positions)
         out: List[Optional[str]] = [None] * len(positions)
-        if keep:
-            ids = self.predictor.convnextvit_forward_u8(crops)
-            tok, ln, _ = self.post.ctc_collapse(ids)
-            texts = self._postprocess({"ids": tok.cpu().numpy(), "len": ln.cpu().numpy()})
-            for k, t in zip(keep, texts):
-                out[k] = t
+        if len(positions) == 0:
+            return out
+        quads = torch.from_numpy(np.stack([np.asarray(p, np.float32).reshape(4, 2) for p in positions])).to(dev)
+        # geometry, homography, warp and keep-ratio resize all on the device (dv_crop_quads_for_rec); width 0 = skipped quad
+        crops, widths, _, _ = self.post.crop_quads_for_rec(page_dev, quads)
+        ids = self.predictor.convnextvit_forward_u8(crops)
+        tok, ln, _ = self.post.ctc_collapse(ids)
+        texts = self._postprocess({"ids": tok.cpu().numpy(), "len": ln.cpu().numpy()})
+        for k, (t, w) in enumerate(zip(texts, widths.cpu().numpy())):
+            out[k] = t if w > 0 else None
         return out
 
     def _postprocess(self, inputs, **kwargs) -> List[str]:
