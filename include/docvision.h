@@ -340,6 +340,14 @@ int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
                           const int32_t* box_counts, int box_stride, int per_page, int dst_h, int dst_w_pad, uint8_t* out,
                           int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
 /*
+ * cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) with a zero border on a uint8 HWC image, bit-exact against cv2
+ * (OpenCV 4.13 fixed point): the warp of TableLorePreProcessor.process (lore/processer_lore.py:80-91) for an
+ * image that is already on the device.  m_inv6_host: HOST pointer to the six doubles of the INVERTED matrix (cv2 inverts M
+ * first; predictors.invert_affine is that formula).  out: device uint8 [out_h, out_w, 3].
+ */
+int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int width, const double* m_inv6_host, int out_w, int out_h,
+                      uint8_t* out);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

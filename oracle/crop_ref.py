@@ -166,3 +166,40 @@ def invert3(t):
     return np.array([(s[1, 1] * s[2, 2] - s[1, 2] * s[2, 1]) * d, (s[0, 2] * s[2, 1] - s[0, 1] * s[2, 2]) * d, (s[0, 1] * s[1, 2] - s[0, 2] * s[1, 1]) * d,
                      (s[1, 2] * s[2, 0] - s[1, 0] * s[2, 2]) * d, (s[0, 0] * s[2, 2] - s[0, 2] * s[2, 0]) * d, (s[0, 2] * s[1, 0] - s[0, 0] * s[1, 2]) * d,
                      (s[1, 0] * s[2, 1] - s[1, 1] * s[2, 0]) * d, (s[0, 1] * s[2, 0] - s[0, 0] * s[2, 1]) * d, (s[0, 0] * s[1, 1] - s[0, 1] * s[1, 0]) * d]).reshape(3, 3)
+
+
+def warp_affine(img, m23, w, h):
+    """== cv2.warpAffine(img, m23, (w, h), flags=cv2.INTER_LINEAR) for uint8 HWC (border constant 0): OpenCV's
+    WarpAffineInvoker (matrix inverted first, 10-bit fixed-point coordinates, rounding offset 16) + the bilinear remap."""
+    m = np.asarray(m23, np.float64).copy().ravel()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0] = a11
+    m[1] *= -d
+    m[3] *= -d
+    m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    sh, sw = img.shape[:2]
+    xs = np.arange(w, dtype=np.float64)
+    ys = np.arange(h, dtype=np.float64)
+    adelta = np.rint(m[0] * xs * 1024).astype(np.int64)
+    bdelta = np.rint(m[3] * xs * 1024).astype(np.int64)
+    x0 = np.rint((m[1] * ys + m[2]) * 1024).astype(np.int64) + 16
+    y0 = np.rint((m[4] * ys + m[5]) * 1024).astype(np.int64) + 16
+    xi = (x0[:, None] + adelta[None, :]) >> 5
+    yi = (y0[:, None] + bdelta[None, :]) >> 5
+    sx = np.clip(xi >> 5, -32768, 32767)
+    sy = np.clip(yi >> 5, -32768, 32767)
+    ax, ay = xi & 31, yi & 31
+
+    def fetch(yy, xx):
+        ok = (yy >= 0) & (yy < sh) & (xx >= 0) & (xx < sw)
+        v = img[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)].astype(np.int64)
+        return np.where(ok[..., None], v, 0)
+
+    acc = (fetch(sy, sx) * ((32 - ax) * (32 - ay) * 32)[..., None] + fetch(sy, sx + 1) * (ax * (32 - ay) * 32)[..., None]
+           + fetch(sy + 1, sx) * ((32 - ax) * ay * 32)[..., None] + fetch(sy + 1, sx + 1) * (ax * ay * 32)[..., None])
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)

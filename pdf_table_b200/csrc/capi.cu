@@ -500,6 +500,15 @@ int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
                                  dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
 }
 
+int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int width, const double* m_inv6_host, int out_w, int out_h,
+                      uint8_t* out) {
+    if (!h) return DV_ERR_ARG;
+    if (!img_hwc_u8 || !m_inv6_host || !out || height <= 0 || width <= 0 || out_w <= 0 || out_h <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_warp_affine_u8: null pointer / bad size");
+    cudaSetDevice(h->device);
+    return op_warp_affine_u8(h, img_hwc_u8, height, width, m_inv6_host, out_w, out_h, out);
+}
+
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
                         float* out_nchw_f32) {
     if (!h) return DV_ERR_ARG;

@@ -355,6 +355,55 @@ k_crop_resize_fused(const uint8_t* __restrict__ pages, int H, int W, const int32
 
 }  // namespace
 
+// cv2.warpAffine(img, M, (w, h), flags=INTER_LINEAR) (border constant 0) on uint8 HWC, bit for bit (OpenCV imgwarp.cpp
+// WarpAffineInvoker: 10-bit fixed-point coordinates X = (cvRound((m1 y + m2) 1024) + 16 + cvRound(m0 x 1024)) >> 5, then the same
+// 1/32-pixel bilinear remap as the perspective warp; the numpy restatement oracle/crop_ref.py warp_affine is checked against cv2 4.13 in
+// tests/test_crop_cpu.py::test_warp_affine_restatement_equals_cv2, this kernel against cv2 in tests/test_gpu_crop.py).  `m` is
+// the INVERTED 2x3 matrix (the host inverts with cv2's own formula, predictors.invert_affine).  Replaces the warp of
+// TableLorePreProcessor.process (lore/processer_lore.py:80-91).
+struct Affine6 {
+    double m[6];
+};
+__global__ void __launch_bounds__(256)
+k_warp_affine_u8(const uint8_t* __restrict__ img, int H, int W, Affine6 a, int w, int h, uint8_t* __restrict__ out) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= w * h) return;
+    const int y = idx / w, x = idx - y * w;
+    const double dx = static_cast<double>(x), dy = static_cast<double>(y);
+    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(a.m[0], dx), 1024.0));
+    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(a.m[3], dx), 1024.0));
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(a.m[1], dy), a.m[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(a.m[4], dy), a.m[5]), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int ax = X & 31, ay = Y & 31;
+    const int wt[4] = {(32 - ax) * (32 - ay) * 32, ax * (32 - ay) * 32, (32 - ax) * ay * 32, ax * ay * 32};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = sy + (t >> 1), xx = sx + (t & 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const uint8_t* p = img + (static_cast<long long>(yy) * W + xx) * 3;
+            acc[0] += p[0] * wt[t];
+            acc[1] += p[1] * wt[t];
+            acc[2] += p[2] * wt[t];
+        }
+    }
+    uint8_t* o = out + static_cast<long long>(idx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((acc[c] + (1 << 14)) >> 15);
+}
+
+int op_warp_affine_u8(Engine* e, const uint8_t* img, int H, int W, const double* m_inv6, int w, int h, uint8_t* out) {
+    Affine6 a;
+    for (int i = 0; i < 6; ++i) a.m[i] = m_inv6[i];
+    e->launch_begin("k_warp_affine_u8", "pre", 0.0, static_cast<double>(w) * h * 3.0 * 5.0);
+    k_warp_affine_u8<<<(w * h + 255) / 256, 256, 0, e->stream>>>(img, H, W, a, w, h, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
                           int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {

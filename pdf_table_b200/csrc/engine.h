@@ -191,6 +191,7 @@ int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off,
 int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
                           int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
+int op_warp_affine_u8(Engine* e, const uint8_t* img, int H, int W, const double* m_inv6, int w, int h, uint8_t* out);
 int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out);
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out);

@@ -240,6 +240,18 @@ class Engine:
                                               dst_w_pad, _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_boxes_for_rec")
         return out, widths, sizes, minv
 
+    def warp_affine_u8(self, img: torch.Tensor, m_inv: np.ndarray, out_w: int, out_h: int) -> torch.Tensor:
+        """uint8 HWC image (cuda) + the inverted 2x3 matrix (host float64) -> uint8 [out_h,out_w,3]: cv2.warpAffine, bilinear."""
+        img = _require_cuda(img, torch.uint8, "img")
+        hh, ww, c = img.shape
+        if c != 3:
+            raise ValueError("img must be [H,W,3]")
+        m = np.ascontiguousarray(m_inv, dtype=np.float64).reshape(6)
+        out = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=img.device)
+        check(self._lib.dv_warp_affine_u8(self._h, _ptr(img), hh, ww, m.ctypes.data_as(C.c_void_p), out_w, out_h, _ptr(out)), self._h,
+              "dv_warp_affine_u8")
+        return out
+
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
         crops = _require_cuda(crops, torch.uint8, "crops")

@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -440,6 +440,37 @@ def lore_preprocess(img: np.ndarray, resolution=(1024, 1024)):
     trans = lore_affine(c, s, inp_w, inp_h)
     warped = cv2.warpAffine(np.ascontiguousarray(img), trans, (inp_w, inp_h), flags=cv2.INTER_LINEAR)
     meta = np.array([c[0], c[1], s, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64)  # .long(): cx, cy truncated
+    return warped, meta
+
+
+def invert_affine(m) -> np.ndarray:
+    """The inversion cv2.warpAffine applies to its 2x3 matrix before mapping destination pixels (imgwarp.cpp, the branch
+    without WARP_INVERSE_MAP), in the same double operations."""
+    m = np.asarray(m, np.float64).copy().ravel()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0] = a11
+    m[1] *= -d
+    m[3] *= -d
+    m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m.reshape(2, 3)
+
+
+def lore_preprocess_device(engine: Engine, img, resolution=(1024, 1024)):
+    """lore_preprocess with the warp on the device (``dv_warp_affine_u8``, bit-exact against cv2.warpAffine): img is a uint8 HWC
+    ndarray or cuda tensor; only the raw image goes up.  Returns (uint8 [H,W,3] cuda tensor, meta int64 [7])."""
+    dev = torch.device("cuda", engine.device)
+    t = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img)).to(dev)
+    height, width = int(t.shape[0]), int(t.shape[1])
+    inp_h, inp_w = resolution
+    c = np.array([width / 2.0, height / 2.0], dtype=np.float32)
+    s = max(height, width) * 1.0
+    warped = engine.warp_affine_u8(t, invert_affine(lore_affine(c, s, inp_w, inp_h)), inp_w, inp_h)
+    meta = np.array([c[0], c[1], s, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64)
     return warped, meta
 
 

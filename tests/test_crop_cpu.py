@@ -88,3 +88,19 @@ def test_homography_restatement_equals_cv2():
         t = cv2.getPerspectiveTransform(corners, trans)
         assert np.array_equal(ref.get_perspective_transform(corners, trans), t), trial
         assert np.array_equal(ref.invert3(t), cv2.invert(t)[1]), trial
+
+
+def test_warp_affine_restatement_equals_cv2():
+    """cv2.warpAffine restated (what k_warp_affine_u8 implements), incl. the Lore pre-process matrices, and the host inversion."""
+    rng = np.random.default_rng(6)
+    for trial in range(25):
+        hh, ww = int(rng.integers(50, 500)), int(rng.integers(50, 700))
+        img = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+        if trial % 3 == 0:  # the centre-anchored similarity of TableLorePreProcessor
+            m = predictors.lore_affine(np.array([ww / 2.0, hh / 2.0], np.float32), max(hh, ww) * 1.0, 256, 256)
+            w, h = 256, 256
+        else:
+            s, th = rng.uniform(0.3, 3.0), rng.uniform(-0.4, 0.4)
+            m = np.array([[s * math.cos(th), -s * math.sin(th), rng.uniform(-50, 50)], [s * math.sin(th), s * math.cos(th), rng.uniform(-50, 50)]])
+            w, h = int(rng.integers(32, 300)), int(rng.integers(32, 300))
+        assert np.array_equal(ref.warp_affine(img, m, w, h), cv2.warpAffine(img, m, (w, h), flags=cv2.INTER_LINEAR)), trial

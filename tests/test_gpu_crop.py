@@ -131,3 +131,25 @@ def test_device_only_glue_matches_cv2(eng):
         assert not out[k, :, widths[k]:].any()
         checked += 1
     assert checked > 140
+
+
+def test_lore_preprocess_on_device_equals_host(eng):
+    """a10 with the warp on the device: lore_preprocess_device == lore_preprocess (cv2.warpAffine on the host), pixels and meta,
+    for an up-scaled and a down-scaled page; and the raw kernel against cv2.warpAffine for rotated / sheared matrices."""
+    from pdf_table_b200 import synth
+
+    for seed, (hh, ww) in enumerate([(300, 520), (1400, 1100), (1024, 1024)]):
+        img = synth.synthetic_page(60 + seed, hh, ww)
+        want, meta = predictors.lore_preprocess(img)
+        got, meta_d = predictors.lore_preprocess_device(eng, img)
+        assert np.array_equal(meta, meta_d)
+        assert np.array_equal(got.cpu().numpy(), want)
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (333, 517, 3), dtype=np.uint8)
+    dev = torch.from_numpy(img).cuda()
+    for trial in range(12):
+        s, th = rng.uniform(0.3, 3.0), rng.uniform(-0.4, 0.4)
+        m = np.array([[s * math.cos(th), -s * math.sin(th) + 0.1, rng.uniform(-60, 60)], [s * math.sin(th), s * math.cos(th), rng.uniform(-60, 60)]])
+        w, h = int(rng.integers(32, 400)), int(rng.integers(32, 400))
+        got = eng.warp_affine_u8(dev, predictors.invert_affine(m), w, h).cpu().numpy()
+        assert np.array_equal(got, cv2.warpAffine(img, m, (w, h), flags=cv2.INTER_LINEAR)), trial
