@@ -216,9 +216,10 @@ class Cascade:
         self.rec_out = self.post.ctc_collapse(self.tok_ids)
         return self.post.ctc_greedy(self.probs_dev)
 
-    def step_e2e(self):
+    def step_e2e(self, upload_pages: bool = True):
         """Host (pinned) buffers in, host results out: H2D + D2H inside."""
-        self.pages_stage.copy_(self.pages_host, non_blocking=True)
+        if upload_pages:  # False only when a subclass has already uploaded this step's pages
+            self.pages_stage.copy_(self.pages_host, non_blocking=True)
         self.probs_stage.copy_(self.probs_host, non_blocking=True)
         self.det.dbnet_forward_u8(self.pages_stage, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
         boxes, counts = self.post.db_boxes(self.planted_maps, self.src_hw)
@@ -259,6 +260,8 @@ class Cascade:
 
 
 FULL = False
+TABLES = "planted"  # --tables: "device" cuts the table crops from the resident pages (dv_crop_tables_for_tsr)
+TABLE_BBOX = [24.3, 130.6, 936.4, 830.5]  # the layout box every page's table is cut at with --tables device
 LORE_HM_BIAS = (-0.3, -3.5)  # seeded random weights: shift the Lore heat maps so that ~100 cells / corners per table pass the gates
 TABLES_PER_PAGE = 1
 
@@ -301,6 +304,19 @@ class FullCascade(Cascade):
         self.n_tables = self.n_pages * TABLES_PER_PAGE
         self.layout_host = torch.from_numpy(make_layout_pages(self.pages_host.numpy())).pin_memory()
         imgs, self.lore_inv = make_table_crops(rank, self.n_tables)
+        self.tables_on_device = TABLES == "device"
+        if self.tables_on_device:
+            # the table loop of ocr_system_task.py:184-198 on the device: crop_image_by_box + the Lore warp of every page's table
+            # region in one launch from the resident page; the matrices (68 bytes per table) are the only table input that goes up
+            from pdf_table_b200 import predictors
+
+            x0, y0, cw, ch = predictors.table_crop_rect(TABLE_BBOX, PAGE_H, PAGE_W)
+            c, sc = np.array([cw / 2.0, ch / 2.0], dtype=np.float32), max(ch, cw) * 1.0
+            meta = np.array([c[0], c[1], sc]).astype(np.int64)  # update_meta truncates the centre (processer_lore.py:112-130)
+            self.table_rects = np.array([[p, x0, y0, cw, ch] for p in range(self.n_pages) for _ in range(TABLES_PER_PAGE)], np.int32)
+            self.table_minv = np.stack([predictors.invert_affine(predictors.lore_affine(c, sc, 1024, 1024))] * self.n_tables)
+            self.lore_inv = np.stack([predictors.lore_affine([np.float32(meta[0]), np.float32(meta[1])], np.float32(meta[2]), 256, 256, True)] * self.n_tables)
+            imgs = imgs[:1]  # the planted crops are not used
         self.tables_host = torch.from_numpy(imgs).pin_memory()
         self.layout_dev, self.tables_dev = self.layout_host.to(dev), self.tables_host.to(dev)
         self.layout_stage, self.tables_stage = torch.empty_like(self.layout_dev), torch.empty_like(self.tables_dev)
@@ -313,7 +329,9 @@ class FullCascade(Cascade):
         self.tcnt_host = torch.empty((self.n_tables,), dtype=torch.int32).pin_memory()
         self.logi_host = torch.empty((self.n_tables * 1024, 4), dtype=torch.float32).pin_memory()
 
-    def _tsr_layout(self, layout_u8, tables_u8):
+    def _tsr_layout(self, layout_u8, tables_u8, pages_u8=None):
+        if self.tables_on_device:
+            tables_u8 = self.post.crop_tables_for_tsr(pages_u8, self.table_rects, self.table_minv, 1024, 1024)
         scores, dfl = self.layout.picodet_forward_u8(layout_u8, flip=True)
         self.lay = self.post.picodet_decode(scores, dfl, self.org_hw, self.layout_sf, (800, 608))
         self.lore.lore_detect_forward_u8(tables_u8, out=self.lore_maps)
@@ -323,22 +341,27 @@ class FullCascade(Cascade):
 
     def step_device(self):
         out = super().step_device()
-        self._tsr_layout(self.layout_dev, self.tables_dev)
+        self._tsr_layout(self.layout_dev, self.tables_dev, self.pages_dev)
         return out
 
     def step_e2e(self):
         self.layout_stage.copy_(self.layout_host, non_blocking=True)
-        self.tables_stage.copy_(self.tables_host, non_blocking=True)
-        self._tsr_layout(self.layout_stage, self.tables_stage)
+        if self.tables_on_device:
+            self.pages_stage.copy_(self.pages_host, non_blocking=True)  # this step's pages: uploaded here, not again below
+        else:
+            self.tables_stage.copy_(self.tables_host, non_blocking=True)
+        self._tsr_layout(self.layout_stage, self.tables_stage, self.pages_stage)
         self.lay_host.copy_(self.lay[0], non_blocking=True)
         self.lay_cnt_host.copy_(self.lay[1], non_blocking=True)
         self.poly_host.copy_(self.dec["polygons"][:, :1024], non_blocking=True)
         self.tcnt_host.copy_(self.dec["counts"], non_blocking=True)
         self.logi_host.copy_(self.logi, non_blocking=True)
-        super().step_e2e()
+        super().step_e2e(upload_pages=not self.tables_on_device)
 
     @property
     def h2d_bytes(self):
+        if self.tables_on_device:
+            return super().h2d_bytes + self.layout_host.numel() + self.table_rects.nbytes + self.table_minv.nbytes
         return super().h2d_bytes + self.layout_host.numel() + self.tables_host.numel()
 
     @property
@@ -491,8 +514,14 @@ def workload_config():
                            "32 synthetic pages 960x960 per GPU, one 1024x1024 table crop per page")
         cfg["stages"] = FullCascade.stages
         cfg["layout_model"] = "PicoDet LCNet-x1.0 + CSP-PAN + PicoHead on 800x608 (in-tree modules, seeded random weights)"
-        cfg["tsr_model"] = ("Lore DLA-34 + DCNv2 (wtw) + processor, one planted table crop per page (on-GPU crop extraction from the layout "
-                            "boxes is not built yet), heat-map bias shifted so ~100 cells per table are selected")
+        cfg["tsr_model"] = ("Lore DLA-34 + DCNv2 (wtw) + processor, " +
+                            ("one table per page cut from the resident page at a fixed layout box and warped into the network frame on the "
+                             "device (dv_crop_tables_for_tsr: crop_image_by_box + cv2.warpAffine, bit-exact vs cv2)" if TABLES == "device" else
+                             "one planted (host-warped) table crop per page; --tables device cuts them on the device instead") +
+                            ", heat-map bias shifted so ~100 cells per table are selected")
+        if TABLES == "device":
+            cfg["stages"] = [("crop_tables_for_tsr(slice + warpAffine)" if st == "lore_preprocess_u8(fused)" else st) for st in cfg["stages"]]
+            cfg["stages"].insert(cfg["stages"].index("lore_dla34_dcn_forward"), "lore_preprocess_u8(fused)")
     return cfg
 
 
@@ -524,7 +553,12 @@ def main():
     ap.add_argument("--cascade", default="ocr", choices=["ocr", "full"],
                     help="ocr = BASELINE configs[1] (DB detect + recognise, the default line); full = configs[4] per GPU: PicoDet layout -> DB -> "
                          "recognise -> Lore table structure on one table crop per page")
+    ap.add_argument("--tables", default="planted", choices=["planted", "device"],
+                    help="--cascade full only: planted = host-warped 1024x1024 table crops are uploaded (the measured r2k line); device = the table "
+                         "region of every resident page is cut and warped on the device (dv_crop_tables_for_tsr), no table pixels go up")
     args = ap.parse_args()
+    global TABLES
+    TABLES = args.tables
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

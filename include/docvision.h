@@ -348,6 +348,19 @@ int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
 int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int width, const double* m_inv6_host, int out_w, int out_h,
                       uint8_t* out);
 /*
+ * Layout -> table-structure glue: the table loop of the orchestrator (ocr_pdf/ocr_system_task.py:184-198),
+ * i.e. OcrCommonUtils.crop_image_by_box (utils/ocr/ocr_common_utils.py:269-284) followed by the cv2.warpAffine of
+ * TableLorePreProcessor.process (lore/processer_lore.py:80-91), for all tables of a batch of resident pages in one launch and
+ * without the JPEG write / re-read of the reference (the device path sees the page's exact pixels).
+ *   pages_hwc_u8 : device uint8 [n_pages][height][width][3]
+ *   rects        : device int32 [n][5] = page, x0, y0, crop_w, crop_h -- the slice img[y0:y0+crop_h, x0:x0+crop_w]
+ *   m_inv        : device double [n][6], the INVERTED 2x3 matrix of each crop (as for dv_warp_affine_u8)
+ *   out          : device uint8 [n][out_h][out_w][3] = cv2.warpAffine(crop, M, (out_w, out_h), INTER_LINEAR), bit-exact; a rect
+ *                  that is not inside its page gives a zero image.  This is the batch dv_lore_detect_forward_u8 reads.
+ */
+int dv_crop_tables_for_tsr(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const int32_t* rects,
+                           const double* m_inv, int n, int out_w, int out_h, uint8_t* out);
+/*
  * PP-OCR recogniser pre-process after the host cv2.resize: replaces the numpy tail of
  * PPOcrRecPreProcessor.resize_norm_img (ocr_rec_pp/processor_ocr_rec_pp.py:56-63): astype(float32), HWC -> CHW, / 255,
  * -= 0.5, /= 0.5 and the zero padding to the batch width.  crops_hwc_u8: device uint8 [b, height, width, 3], crop i

@@ -168,9 +168,8 @@ def invert3(t):
                      (s[1, 0] * s[2, 1] - s[1, 1] * s[2, 0]) * d, (s[0, 1] * s[2, 0] - s[0, 0] * s[2, 1]) * d, (s[0, 0] * s[1, 1] - s[0, 1] * s[1, 0]) * d]).reshape(3, 3)
 
 
-def warp_affine(img, m23, w, h):
-    """== cv2.warpAffine(img, m23, (w, h), flags=cv2.INTER_LINEAR) for uint8 HWC (border constant 0): OpenCV's
-    WarpAffineInvoker (matrix inverted first, 10-bit fixed-point coordinates, rounding offset 16) + the bilinear remap."""
+def invert_affine(m23):
+    """The inversion cv2.warpAffine applies to its 2x3 matrix when WARP_INVERSE_MAP is not set (OpenCV imgwarp.cpp), same doubles."""
     m = np.asarray(m23, np.float64).copy().ravel()
     d = m[0] * m[4] - m[1] * m[3]
     d = 1.0 / d if d != 0 else 0.0
@@ -182,6 +181,13 @@ def warp_affine(img, m23, w, h):
     b1 = -m[0] * m[2] - m[1] * m[5]
     b2 = -m[3] * m[2] - m[4] * m[5]
     m[2], m[5] = b1, b2
+    return m.reshape(2, 3)
+
+
+def warp_affine(img, m23, w, h):
+    """== cv2.warpAffine(img, m23, (w, h), flags=cv2.INTER_LINEAR) for uint8 HWC (border constant 0): OpenCV's
+    WarpAffineInvoker (matrix inverted first, 10-bit fixed-point coordinates, rounding offset 16) + the bilinear remap."""
+    m = invert_affine(m23).ravel()
     sh, sw = img.shape[:2]
     xs = np.arange(w, dtype=np.float64)
     ys = np.arange(h, dtype=np.float64)

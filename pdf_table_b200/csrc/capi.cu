@@ -505,8 +505,20 @@ int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int wi
     if (!h) return DV_ERR_ARG;
     if (!img_hwc_u8 || !m_inv6_host || !out || height <= 0 || width <= 0 || out_w <= 0 || out_h <= 0)
         return set_err(h, DV_ERR_ARG, "dv_warp_affine_u8: null pointer / bad size");
+    if (static_cast<long long>(out_w) * out_h > 0x7fffffffLL / 4) return set_err(h, DV_ERR_ARG, "dv_warp_affine_u8: output too large");
     cudaSetDevice(h->device);
     return op_warp_affine_u8(h, img_hwc_u8, height, width, m_inv6_host, out_w, out_h, out);
+}
+
+int dv_crop_tables_for_tsr(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const int32_t* rects,
+                           const double* m_inv, int n, int out_w, int out_h, uint8_t* out) {
+    if (!h) return DV_ERR_ARG;
+    if (n < 0 || n > 65535 || n_pages <= 0 || height <= 0 || width <= 0 || out_w <= 0 || out_h <= 0)
+        return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: bad size (0 <= n <= 65535)");
+    if (n > 0 && (!pages_hwc_u8 || !rects || !m_inv || !out)) return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: null pointer");
+    if (static_cast<long long>(out_w) * out_h > 0x7fffffffLL / 4) return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: output too large");
+    cudaSetDevice(h->device);
+    return op_warp_affine_rects_u8(h, pages_hwc_u8, n_pages, height, width, rects, m_inv, n, out_w, out_h, out);
 }
 
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,

@@ -404,6 +404,62 @@ int op_warp_affine_u8(Engine* e, const uint8_t* img, int H, int W, const double*
     return 0;
 }
 
+// Layout -> table-structure glue: the warp above for MANY axis-aligned sub-rectangles of resident pages in one launch
+// (blockIdx.y = table).  Each table is the slice pages[page][y0:y0+ch, x0:x0+cw] (OcrCommonUtils.crop_image_by_box,
+// utils/ocr/ocr_common_utils.py:269-284) warped by its own inverted matrix exactly as cv2.warpAffine would warp the cut-out
+// crop: the slice is addressed in place through the page pitch, samples outside the slice are the zero border.  A rect that
+// does not lie inside its page yields a zero image (the host helper predictors.table_crop_rect never produces one).
+__global__ void __launch_bounds__(256)
+k_warp_affine_rects_u8(const uint8_t* __restrict__ pages, int n_pages, int H, int W, const int32_t* __restrict__ rects,
+                       const double* __restrict__ minv, int w, int h, uint8_t* __restrict__ out) {
+    const int k = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= w * h) return;
+    const int32_t* r = rects + k * 5;
+    const int pg = r[0], x0 = r[1], y0 = r[2], cw = r[3], ch = r[4];
+    uint8_t* o = out + (static_cast<long long>(k) * w * h + idx) * 3;
+    if (pg < 0 || pg >= n_pages || x0 < 0 || y0 < 0 || cw <= 0 || ch <= 0 || x0 > W - cw || y0 > H - ch) {
+        o[0] = o[1] = o[2] = 0;
+        return;
+    }
+    const double* m = minv + k * 6;
+    const long long pitch = static_cast<long long>(W) * 3;
+    const uint8_t* img = pages + (static_cast<long long>(pg) * H + y0) * pitch + static_cast<long long>(x0) * 3;
+    const int y = idx / w, x = idx - y * w;
+    const double dx = static_cast<double>(x), dy = static_cast<double>(y);
+    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], dx), 1024.0));
+    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], dx), 1024.0));
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], dy), m[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], dy), m[5]), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int ax = X & 31, ay = Y & 31;
+    const int wt[4] = {(32 - ax) * (32 - ay) * 32, ax * (32 - ay) * 32, (32 - ax) * ay * 32, ax * ay * 32};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = sy + (t >> 1), xx = sx + (t & 1);
+        if (yy >= 0 && yy < ch && xx >= 0 && xx < cw) {
+            const uint8_t* p = img + yy * pitch + xx * 3;
+            acc[0] += p[0] * wt[t];
+            acc[1] += p[1] * wt[t];
+            acc[2] += p[2] * wt[t];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((acc[c] + (1 << 14)) >> 15);
+}
+
+int op_warp_affine_rects_u8(Engine* e, const uint8_t* pages, int n_pages, int H, int W, const int32_t* rects, const double* minv,
+                            int n, int w, int h, uint8_t* out) {
+    if (n == 0) return 0;
+    e->launch_begin("k_warp_affine_rects_u8", "pre", 0.0, static_cast<double>(n) * w * h * 3.0 * 5.0);
+    k_warp_affine_rects_u8<<<dim3((w * h + 255) / 256, n), 256, 0, e->stream>>>(pages, n_pages, H, W, rects, minv, w, h, out);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
                           int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {

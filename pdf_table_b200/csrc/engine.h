@@ -192,6 +192,8 @@ int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const f
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
                           int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
 int op_warp_affine_u8(Engine* e, const uint8_t* img, int H, int W, const double* m_inv6, int w, int h, uint8_t* out);
+int op_warp_affine_rects_u8(Engine* e, const uint8_t* pages, int n_pages, int H, int W, const int32_t* rects, const double* minv,
+                            int n, int w, int h, uint8_t* out);
 int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out);
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
                   float scale, int flip, __half* out);

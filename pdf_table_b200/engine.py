@@ -252,6 +252,26 @@ class Engine:
               "dv_warp_affine_u8")
         return out
 
+    def crop_tables_for_tsr(self, pages: torch.Tensor, rects: np.ndarray, m_inv: np.ndarray, out_w: int, out_h: int) -> torch.Tensor:
+        """uint8 pages [P,H,W,3] (cuda), rects int32 [n,5] = page, x0, y0, w, h and inverted matrices float64 [n,2,3] (host; 68
+        bytes per table go up) -> uint8 [n,out_h,out_w,3]: every table slice warped as cv2.warpAffine warps the cut-out crop."""
+        pages = _require_cuda(pages, torch.uint8, "pages")
+        if pages.dim() != 4 or pages.shape[3] != 3:
+            raise ValueError("pages must be [P,H,W,3]")
+        rects = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 5)
+        m = np.ascontiguousarray(m_inv, dtype=np.float64).reshape(-1, 6)
+        n = rects.shape[0]
+        if m.shape[0] != n:
+            raise ValueError("one inverted matrix per rect")
+        out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=pages.device)
+        if n == 0:
+            return out
+        rects_d = torch.from_numpy(rects).to(pages.device)
+        m_d = torch.from_numpy(m).to(pages.device)
+        check(self._lib.dv_crop_tables_for_tsr(self._h, _ptr(pages), pages.shape[0], pages.shape[1], pages.shape[2], _ptr(rects_d), _ptr(m_d), n,
+                                               out_w, out_h, _ptr(out)), self._h, "dv_crop_tables_for_tsr")
+        return out
+
     def pp_rec_normalise(self, crops: torch.Tensor, widths: torch.Tensor) -> torch.Tensor:
         """uint8 [B,H,W,3] resized crops (left-aligned, widths int32 [B]) -> fp32 [B,3,H,W]: (x/255 - 0.5)/0.5, zero padded."""
         crops = _require_cuda(crops, torch.uint8, "crops")

@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -474,6 +474,18 @@ def lore_preprocess_device(engine: Engine, img, resolution=(1024, 1024)):
     return warped, meta
 
 
+def table_crop_rect(bbox, height: int, width: int):
+    """The slice OcrCommonUtils.crop_image_by_box takes (utils/ocr/ocr_common_utils.py:279-280, diff=0):
+    img[round(y1):round(y2), round(x1):round(x2)] with Python's round (half to even) and numpy's slice clamping, as
+    (x0, y0, crop_w, crop_h).  Raises ValueError for an empty slice (the reference fails in cv2.imwrite on it)."""
+    x1, y1, x2, y2 = (float(v) for v in bbox)
+    ys, ye, _ = slice(round(y1), round(y2)).indices(height)
+    xs, xe, _ = slice(round(x1), round(x2)).indices(width)
+    if ye <= ys or xe <= xs:
+        raise ValueError(f"empty table crop for bbox {list(bbox)} on a {height}x{width} page")
+    return xs, ys, xe - xs, ye - ys
+
+
 class OcrTableStructureTask(BaseInferTask):
     """OcrTableStructureTask (ocr_pdf/ocr_table_structure_task.py:50-271) for model="Lore", task_type="wtw"
     (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers) and model="CenterNet"
@@ -525,12 +537,53 @@ class OcrTableStructureTask(BaseInferTask):
             cs.append((np.array([w / 2.0, h / 2.0], dtype=np.float32), max(h, w) * 1.0))
         return {"images": np.stack(images), "meta": np.stack(metas), "cs": cs, "inputs": list(items)}
 
+    def _images_on_device(self, images) -> torch.Tensor:
+        """The warped uint8 batch: uploaded when the host pre-process made it, used in place when recognize_tables did."""
+        if isinstance(images, torch.Tensor):
+            return images
+        return torch.from_numpy(images).to(torch.device("cuda", self.device), non_blocking=True)
+
+    def recognize_tables(self, pages, layout_tables) -> List[list]:
+        """The table loop of the reference's orchestrator (ocr_pdf/ocr_system_task.py:184-198) for pages that are already on
+        the device: per layout table, OcrCommonUtils.crop_image_by_box + this task on the crop -- here all crops of all pages
+        are cut and warped into the network frame by ONE launch (``dv_crop_tables_for_tsr``: slice + cv2.warpAffine, bit-exact
+        on the page's pixels; the reference's lossy JPEG write / re-read of the crop is not reproduced), so only 68 bytes per
+        table go up and only the decoded cells come back.
+        pages: uint8 HWC ndarray / cuda tensor [H,W,3] or a batch [P,H,W,3], in the channel order the crops should reach the
+        network in (the reference re-reads its JPEG as RGB and flips it to BGR, processer_lore.py:51-60, 146).
+        layout_tables: dicts with "bbox" = [x1,y1,x2,y2] (and "page" when pages is a batch), e.g. the table rows of
+        OcrLayoutTask's result.  Returns [[bbox, result], ...] in input order like ``outputs`` there (:189-198), result being
+        what ``self(crop)[0]`` returns for that crop (its "inputs" is the bbox)."""
+        dev = torch.device("cuda", self.device)
+        t = pages if isinstance(pages, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pages)).to(dev)
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        n_pages, height, width = int(t.shape[0]), int(t.shape[1]), int(t.shape[2])
+        if len(layout_tables) == 0:
+            return []
+        inp_h, inp_w = self.resolution
+        rects, minv, metas, cs = [], [], [], []
+        for tb in layout_tables:
+            pg = int(tb.get("page", 0))
+            if not 0 <= pg < n_pages:
+                raise ValueError(f"table page {pg} outside the batch of {n_pages} pages")
+            x0, y0, cw, ch = table_crop_rect(tb["bbox"], height, width)
+            c = np.array([cw / 2.0, ch / 2.0], dtype=np.float32)
+            sc = max(ch, cw) * 1.0
+            rects.append([pg, x0, y0, cw, ch])
+            minv.append(invert_affine(lore_affine(c, sc, inp_w, inp_h)))
+            metas.append(np.array([c[0], c[1], sc, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64))
+            cs.append((c, sc))
+        warped = self.post.crop_tables_for_tsr(t, np.array(rects, np.int32), np.stack(minv), inp_w, inp_h)
+        items = [tb["bbox"] for tb in layout_tables]
+        res = self._postprocess(self._run_model({"images": warped, "meta": np.stack(metas), "cs": cs, "inputs": items}))
+        return [[bbox, r] for bbox, r in zip(items, res)]
+
     def _run_centernet(self, inputs):
         """OCRTableCenterNetPreProcessor keeps the float centre / scale in its meta (center_net/processer_centernet.py:108-139);
         the pixels are the same warp as Lore's."""
-        dev = torch.device("cuda", self.device)
         inv = np.stack([lore_affine(c, s, self.resolution[1] // 4, self.resolution[0] // 4, inv=True) for c, s in inputs["cs"]])
-        maps = self.predictor.lore_detect_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True))
+        maps = self.predictor.lore_detect_forward_u8(self._images_on_device(inputs["images"]))
         polygons, counts = self.post.centernet_decode(maps, None, None, None, inv)
         polygons, counts = polygons.cpu().numpy(), counts.cpu().numpy()
         inputs["results"] = [{"polygons": polygons[i, : counts[i]].copy()} for i in range(len(counts))]
@@ -539,11 +592,10 @@ class OcrTableStructureTask(BaseInferTask):
     def _run_model(self, inputs, **kwargs):
         if self.model == "CenterNet":
             return self._run_centernet(inputs)
-        dev = torch.device("cuda", self.device)
         n = len(inputs["images"])
         metas = inputs["meta"]
         inv = np.stack([lore_affine([np.float32(m[0]), np.float32(m[1])], np.float32(m[2]), int(m[6]), int(m[5]), inv=True) for m in metas])
-        maps = self.predictor.lore_detect_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True))
+        maps = self.predictor.lore_detect_forward_u8(self._images_on_device(inputs["images"]))
         dec = self.post.lore_decode(maps, None, None, None, inv, K=self.K, MK=self.MK, wiz_rev=self.wiz_rev, vis_thresh=self.vis_thresh)
         feat, offsets = self.predictor.lore_cell_features(dec, max_rows=n * self.max_cells_per_image, check_overflow=True)
         _, stacked = self.processor.lore_process_forward(feat, offsets)

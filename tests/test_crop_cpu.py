@@ -6,6 +6,7 @@ import os
 
 import cv2
 import numpy as np
+import pytest
 
 from oracle import crop_ref as ref
 from oracle import gen_golden_crop as gen
@@ -104,3 +105,35 @@ def test_warp_affine_restatement_equals_cv2():
             m = np.array([[s * math.cos(th), -s * math.sin(th), rng.uniform(-50, 50)], [s * math.sin(th), s * math.cos(th), rng.uniform(-50, 50)]])
             w, h = int(rng.integers(32, 300)), int(rng.integers(32, 300))
         assert np.array_equal(ref.warp_affine(img, m, w, h), cv2.warpAffine(img, m, (w, h), flags=cv2.INTER_LINEAR)), trial
+
+
+def test_table_crop_rect_is_the_numpy_slice_of_crop_image_by_box():
+    """predictors.table_crop_rect == the slice img[round(y1):round(y2), round(x1):round(x2)] of OcrCommonUtils.crop_image_by_box,
+    incl. half-to-even rounding, clamping at the far borders and the empty cases (negative start wraps in numpy -> empty)."""
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (70, 90, 3), dtype=np.uint8)
+    cases = [[0.5, 1.5, 2.5, 3.5], [10.0, 5.0, 200.0, 300.0], [-3.0, 2.0, 50.0, 40.0], [30.0, 30.0, 30.4, 60.0], [89.6, 0.0, 95.0, 70.0]]
+    cases += [list(rng.uniform(-5, 100, 4)) for _ in range(200)]
+    empty = 0
+    for x1, y1, x2, y2 in cases:
+        want = img[round(y1):round(y2), round(x1):round(x2)]
+        if want.size == 0:
+            empty += 1
+            with pytest.raises(ValueError):
+                predictors.table_crop_rect([x1, y1, x2, y2], 70, 90)
+            continue
+        x0, y0, cw, ch = predictors.table_crop_rect([x1, y1, x2, y2], 70, 90)
+        assert np.array_equal(img[y0:y0 + ch, x0:x0 + cw], want)
+    assert 0 < empty < len(cases)
+
+
+def test_warp_of_a_page_slice_equals_warp_of_the_crop():
+    """What k_warp_affine_rects_u8 computes, restated: warping the slice in place (page pitch, zero border at the slice's edges)
+    is cv2.warpAffine of the cut-out crop with the crop's own Lore matrix."""
+    page = np.random.default_rng(12).integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    for bbox in ([20.2, 30.7, 380.5, 290.1], [0.0, 0.0, 400.0, 300.0], [350.0, 10.0, 400.0, 300.0]):
+        x0, y0, cw, ch = predictors.table_crop_rect(bbox, 300, 400)
+        crop = np.ascontiguousarray(page[y0:y0 + ch, x0:x0 + cw])
+        m = predictors.lore_affine(np.array([cw / 2.0, ch / 2.0], np.float32), max(ch, cw) * 1.0, 256, 256)
+        assert np.array_equal(ref.warp_affine(page[y0:y0 + ch, x0:x0 + cw], m, 256, 256), cv2.warpAffine(crop, m, (256, 256), flags=cv2.INTER_LINEAR))
+        assert np.array_equal(predictors.invert_affine(m), ref.invert_affine(m))
