@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kDepths[4] = {3, 3, 8, 3};
 constexpr int kDims[4] = {96, 192, 256, 512};
-constexpr int kVitLayers = 12, kVitDim = 192, kVitMlp = 768, kTok = 75, kStitched = 201;
+constexpr int kVitLayers = 12, kVitDim = 192, kTok = 75, kStitched = 201;  // MLP width 4 * kVitDim (mlp_fused)
 
 struct Step {
     enum Kind { PATCHIFY, DWLN, LN, GEMM, ATTN, MLP } kind;

@@ -96,7 +96,7 @@ struct EpiSpec {
 };
 
 struct ConvPlan {
-    IGemmParams prm;
+    IGemmParams prm{};
     int grid = 0;
     size_t smem = 0;
     double flops = 0;  // algorithmic 2*M*K*N (unpadded)
