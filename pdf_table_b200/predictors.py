@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -81,6 +81,26 @@ def keepratio_resize(img: np.ndarray, target_height: int = 32, target_width: int
     else:
         cur_w = int(target_height * cur_ratio)
     return cv2.resize(img, (cur_w, target_height))
+
+
+def sort_det_boxes(det_result: np.ndarray) -> np.ndarray:
+    """The reading-order sort the orchestrator applies to the detector's boxes before recognition
+    (ocr_pdf/ocr_system_task.py:158-162): key = 0.01 * mean x + mean y on the python floats of ``tolist()``, stable."""
+    rows = np.asarray(det_result).tolist()
+    rows = sorted(rows, key=lambda x: 0.01 * sum(x[::2]) / 4 + sum(x[1::2]) / 4)
+    return np.array(rows)
+
+
+def order_point(coor) -> np.ndarray:
+    """OcrCommonUtils.order_point (utils/ocr/ocr_common_utils.py:287-305): the four corners sorted by their angle around the
+    centroid (numpy's default argsort), rotated so that the first one lies left of the centroid; float32 [4,2]."""
+    arr = np.array(coor).reshape([4, 2])
+    centroid = np.sum(arr, 0) / arr.shape[0]
+    theta = np.arctan2(arr[:, 1] - centroid[1], arr[:, 0] - centroid[0])
+    pts = arr[np.argsort(theta)].reshape([4, -1])
+    if pts[0][0] > centroid[0]:
+        pts = np.concatenate([pts[3:], pts[:3]])
+    return pts.reshape([4, 2]).astype("float32")
 
 
 def crop_geometry(position):

@@ -1,0 +1,98 @@
+"""The model-calling methods of the reference's orchestrator, OcrSystemTask (model/ocr_pdf/ocr_system_task.py), over the
+b200 predictors -- the callers either side of the hot path: text_detection (:146-166), text_recognition
+(:300-330), layout_analysis (:214-225) and the table loop of table_structure_detection (:179-198).  Same names, arguments and
+return conventions ``(result, metric)``; what changes is where the pixels live: a page goes to the device once, every
+text-line crop and every table crop is cut from the resident page by a kernel (OcrRecognitionTask.recognize_page,
+OcrTableStructureTask.recognize_tables) and only boxes, token ids and cells come back.
+
+Everything else of the orchestrator (PDF parsing, cell / text matching, HTML export, file outputs) stays the reference's:
+these methods return exactly what its next steps consume.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .predictors import order_point, sort_det_boxes
+
+__all__ = ["OcrSystemTask", "get_layout_by_type"]
+
+
+def get_layout_by_type(layout_result: List[Dict[str, Any]], label: str = "figure", score_threshold: float = 0.8) -> List[Dict[str, Any]]:
+    """TableProcessUtils.get_layout_by_type (model/pdf_table/table_common.py:1286-1299): the layout boxes of one label at or
+    above the score threshold, sorted by their top edge (stable)."""
+    results = [item for item in layout_result if item["label"].lower() == label.lower() and item["score"] >= score_threshold]
+    results.sort(key=lambda x: x["bbox"][1])
+    return results
+
+
+class OcrSystemTask:
+    """Holds already constructed predictors (any may be None; using a missing one raises RuntimeError, where the reference
+    would lazily construct its default model)."""
+
+    def __init__(self, text_detector=None, text_recognizer=None, table_structure_recognizer=None, layout_detector=None):
+        self.text_detector = text_detector
+        self.text_recognizer = text_recognizer
+        self.table_structure_recognizer = table_structure_recognizer
+        self.layout_detector = layout_detector
+
+    @staticmethod
+    def _need(task, name: str):
+        if task is None:
+            raise RuntimeError(f"OcrSystemTask: no {name} was given")
+        return task
+
+    def page_to_device(self, image_full) -> torch.Tensor:
+        """uint8 HWC ndarray (or cuda tensor) -> the resident page all crops are cut from."""
+        if isinstance(image_full, torch.Tensor):
+            return image_full
+        task = self.text_recognizer or self.table_structure_recognizer or self.text_detector or self.layout_detector
+        dev = torch.device("cuda", self._need(task, "predictor").device)
+        return torch.from_numpy(np.ascontiguousarray(image_full)).to(dev)
+
+    def text_detection(self, image) -> Tuple[np.ndarray, Dict[str, float]]:
+        """:146-166: detect, then sort the boxes into reading order.  Returns (float64 [n,8], metric)."""
+        start = time.time()
+        det_result = self._need(self.text_detector, "text_detector")(image)[0]
+        use_time = time.time() - start
+        return sort_det_boxes(det_result), {"use_time": use_time}
+
+    def text_recognition(self, det_result, image_full) -> Tuple[List[Dict[str, Any]], Dict[str, Any]]:
+        """:300-330: per box order_point -> crop_image -> recognise; here all crops of the page in one device pass.  A crop the
+        reference fails on (empty crop: it logs the exception and keeps "") yields "" as there.  Returns (list of
+        {"index", "text", "bbox"}, metric)."""
+        rec = self._need(self.text_recognizer, "text_recognizer")
+        start = time.time()
+        det_result = np.asarray(det_result)
+        pts = [order_point(det_result[i]) for i in range(det_result.shape[0])]
+        texts = rec.recognize_page(self.page_to_device(image_full), pts) if pts else []
+        output = [{"index": i + 1, "text": "" if t is None else t, "bbox": p} for i, (t, p) in enumerate(zip(texts, pts))]
+        total_use_time = time.time() - start
+        if not output:  # the reference divides by len(use_times) here (:322) -> ZeroDivisionError on a page without boxes
+            raise ZeroDivisionError("text_recognition: no detected boxes")
+        metric = {"use_time": total_use_time, "avg_use_time": total_use_time / len(output), "total": len(output)}
+        return output, metric
+
+    def layout_analysis(self, image) -> Tuple[List[Dict[str, Any]], Dict[str, float]]:
+        """:214-225."""
+        start = time.time()
+        layout_result = self._need(self.layout_detector, "layout_detector")(image)[0]
+        return layout_result, {"use_time": time.time() - start}
+
+    def table_structure_detection(self, image, image_full=None, layout_result: Optional[List[Dict[str, Any]]] = None):
+        """:179-203: with a layout result, every "table" box (score >= 0.2, top to bottom) is cropped from image_full and
+        recognised; returns (outputs = [[bbox, one_result], ...] -- the argument of the reference's
+        TableProcessUtils.convert_table_sep_to_merge (:199) --, metric).  Without one the recogniser runs on the whole image
+        and its first result is returned, as there (:202-203)."""
+        tsr = self._need(self.table_structure_recognizer, "table_structure_recognizer")
+        start = time.time()
+        if layout_result:
+            layout_tables = get_layout_by_type(layout_result=layout_result, label="table", score_threshold=0.2)
+            page = self.page_to_device(image if image_full is None else image_full)
+            outputs = tsr.recognize_tables(page, [{"bbox": t["bbox"]} for t in layout_tables])
+            return outputs, {"use_time": time.time() - start}
+        result = tsr(image)
+        return result[0], {"use_time": time.time() - start}

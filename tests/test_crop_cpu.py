@@ -137,3 +137,24 @@ def test_warp_of_a_page_slice_equals_warp_of_the_crop():
         m = predictors.lore_affine(np.array([cw / 2.0, ch / 2.0], np.float32), max(ch, cw) * 1.0, 256, 256)
         assert np.array_equal(ref.warp_affine(page[y0:y0 + ch, x0:x0 + cw], m, 256, 256), cv2.warpAffine(crop, m, (256, 256), flags=cv2.INTER_LINEAR))
         assert np.array_equal(predictors.invert_affine(m), ref.invert_affine(m))
+
+
+def test_order_point_matches_reference_golden():
+    """predictors.order_point == OcrCommonUtils.order_point on the 300 quads of tests/golden/glue.npz (oracle/gen_golden_glue.py)."""
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "glue.npz"))
+    for q, f32, want in zip(g["quads"], g["is_f32"], g["ordered"]):
+        got = predictors.order_point(q.astype(np.float32) if f32 else q)
+        assert got.dtype == np.float32 and np.array_equal(got, want)
+
+
+def test_sort_det_boxes_is_the_orchestrator_sort():
+    """Reading order: ascending 0.01 * mean x + mean y, ties keep the detector's order (python's stable sort)."""
+    rng = np.random.default_rng(13)
+    boxes = rng.integers(0, 960, (40, 8)).astype(np.float32)
+    boxes[7] = boxes[3]  # an exact tie
+    got = predictors.sort_det_boxes(boxes)
+    key = [0.01 * sum(r[::2]) / 4 + sum(r[1::2]) / 4 for r in boxes.tolist()]
+    order = sorted(range(40), key=lambda i: (key[i], i))
+    assert np.array_equal(got, boxes[order].astype(np.float64))
+    assert order.index(3) + 1 == order.index(7)
+    assert predictors.sort_det_boxes(np.zeros((0, 8), np.float32)).shape[0] == 0
