@@ -165,3 +165,48 @@ def test_centernet_oracle_matches_reference_golden():
         m = synth.lore_planted_maps(idx, h, w, with_feat=False)
         got = centernet_ref.centernet_decode(m["hm"], m["reg"], m["wh"], m["st"], [sw / 2.0, sh / 2.0], max(sh, sw) * 1.0, h, w)
         np.testing.assert_array_equal(got, d[name], err_msg=name)
+
+
+def test_point_in_polygon_restatement_agrees_with_cv2():
+    """The strict point-in-polygon test that stands in for shapely's Point.within(Polygon) (absent from the image, parity
+    unpinned) cross-checked against an independent implementation, cv2.pointPolygonTest (+1 inside, 0 on the boundary, -1
+    outside): random convex and concave quads, random points, and points planted exactly on vertices and (integer quads) edges."""
+    import cv2
+
+    rng = np.random.default_rng(21)
+    checked = boundary = 0
+    for trial in range(300):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 4))
+        rad = rng.uniform(20, 100, 4) if trial % 3 else np.array([90.0, 25.0, 90.0, 90.0])  # every third quad is concave
+        quad = (np.stack([np.cos(ang), np.sin(ang)], 1) * rad[:, None] + 200).astype(np.float32)
+        if trial % 2:
+            quad = np.rint(quad).astype(np.float32)  # integer corners: exact boundary hits exist
+        pts = [tuple(rng.uniform(80, 320, 2)) for _ in range(30)]
+        pts += [tuple(map(float, quad[k])) for k in range(4)]                              # vertices
+        if trial % 2:  # edge mid-points: exactly on the edge only for integer corners (cv2 forms its differences in float32)
+            pts += [tuple(map(float, (quad[k].astype(np.float64) + quad[(k + 1) % 4]) / 2)) for k in range(4)]
+        for px, py in pts:
+            want = cv2.pointPolygonTest(quad.reshape(-1, 1, 2), (float(px), float(py)), False)
+            if want != 0 and abs(cv2.pointPolygonTest(quad.reshape(-1, 1, 2), (float(px), float(py)), True)) < 1e-3:
+                continue  # closer to the boundary than cv2's float32 arithmetic resolves
+            got = lore_decode_ref.point_strictly_in_polygon(float(px), float(py), quad)
+            if want == 0:
+                boundary += 1
+            assert got == (want > 0), (trial, px, py, want)
+            checked += 1
+    assert checked > 10000 and boundary > 500
+
+
+def test_polygon_area_and_length_stand_in_agrees_with_cv2():
+    """shapely's Polygon.area / .length stand-in (DB unclip distance, parity unpinned) against cv2.contourArea / cv2.arcLength."""
+    import cv2
+
+    from oracle import db_post_ref
+
+    rng = np.random.default_rng(22)
+    for trial in range(200):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 4))
+        quad = np.rint(np.stack([np.cos(ang), np.sin(ang)], 1) * rng.uniform(5, 300, 4)[:, None] + 400).astype(np.int32)
+        poly = db_post_ref.ShapelyPolygonStandIn(quad)
+        assert poly.area == cv2.contourArea(quad.reshape(-1, 1, 2))  # integer shoelace sums are exact in both
+        assert abs(poly.length - cv2.arcLength(quad.reshape(-1, 1, 2).astype(np.float32), True)) <= 1e-4 * max(poly.length, 1.0)
