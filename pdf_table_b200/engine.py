@@ -191,6 +191,20 @@ class Engine:
               self._h, "dv_resize_linear_u8")
         return out
 
+    def resize_pages_u8(self, pages: torch.Tensor, dst_w: int, dst_h: int) -> torch.Tensor:
+        """uint8 [n,H,W,3] (cuda) -> uint8 [n,dst_h,dst_w,3]: cv2.resize(page, (dst_w, dst_h)) (INTER_LINEAR) for same-size pages,
+        through dv_resize_linear_u8 (the pages are the packed sources: offset i*H*W*3, size (W, H) each)."""
+        pages = _require_cuda(pages, torch.uint8, "pages")
+        if pages.dim() != 4 or pages.shape[3] != 3:
+            raise ValueError("pages must be [n,H,W,3]")
+        n, hh, ww, _ = pages.shape
+        if n == 0 or dst_w <= 0 or dst_h <= 0:
+            raise ValueError("resize_pages_u8: empty batch / bad size")
+        dev = pages.device
+        offs = (torch.arange(n, dtype=torch.int64) * (hh * ww * 3)).to(dev)
+        sizes = torch.tensor([[ww, hh]] * n, dtype=torch.int32).to(dev)
+        return self.resize_linear_u8((pages, offs, sizes), np.full((n,), dst_w, np.int32), dst_h, dst_w)
+
     def crop_quads_for_rec(self, pages: torch.Tensor, quads: torch.Tensor, page_idx: Optional[torch.Tensor] = None, dst_h: int = 32,
                            dst_w_pad: int = 804):
         """pages uint8 [P,H,W,3] (or [H,W,3]) + quads float32 [n,4,2] (+ page index int32 [n]), all cuda -> (crops uint8

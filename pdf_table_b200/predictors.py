@@ -23,7 +23,7 @@ from . import weights
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point", "det_resize_shape", "det_resize_for_test_device"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -55,6 +55,14 @@ def det_resize_for_test(img: np.ndarray, limit_side_len: int = 960, limit_type: 
         pad[:h, :w, :] = img
         img = pad
         h, w = img.shape[:2]
+    resize_h, resize_w = det_resize_shape(h, w, limit_side_len, limit_type)
+    if (resize_h, resize_w) != (h, w):
+        img = cv2.resize(img, (int(resize_w), int(resize_h)))
+    return img, [resize_h / float(h), resize_w / float(w)]
+
+
+def det_resize_shape(h: int, w: int, limit_side_len: int = 960, limit_type: str = "max"):
+    """The size rule of DetResizeForTest.resize_image_type0 (db_pp/image_operators.py:283-305) -> (resize_h, resize_w)."""
     if limit_type == "max":
         ratio = float(limit_side_len) / max(h, w) if max(h, w) > limit_side_len else 1.0
     elif limit_type == "min":
@@ -65,9 +73,22 @@ def det_resize_for_test(img: np.ndarray, limit_side_len: int = 960, limit_type: 
         raise Exception("not support limit type, image ")
     resize_h = max(int(round(int(h * ratio) / 32) * 32), 32)
     resize_w = max(int(round(int(w * ratio) / 32) * 32), 32)
+    return resize_h, resize_w
+
+
+def det_resize_for_test_device(engine: Engine, page: torch.Tensor, limit_side_len: int = 960, limit_type: str = "max"):
+    """det_resize_for_test for a page that is already on the device (uint8 HWC cuda tensor): the same size rule, the
+    cv2.resize by ``dv_resize_linear_u8`` (bit-exact against cv2).  Returns (uint8 cuda tensor, [ratio_h, ratio_w])."""
+    h, w = int(page.shape[0]), int(page.shape[1])
+    if h + w < 64:
+        pad = torch.zeros((max(32, h), max(32, w), page.shape[2]), dtype=torch.uint8, device=page.device)
+        pad[:h, :w, :] = page
+        page = pad
+        h, w = int(page.shape[0]), int(page.shape[1])
+    resize_h, resize_w = det_resize_shape(h, w, limit_side_len, limit_type)
     if (resize_h, resize_w) != (h, w):
-        img = cv2.resize(img, (int(resize_w), int(resize_h)))
-    return img, [resize_h / float(h), resize_w / float(w)]
+        page = engine.resize_pages_u8(page.unsqueeze(0), resize_w, resize_h)[0]
+    return page, [resize_h / float(h), resize_w / float(w)]
 
 
 def keepratio_resize(img: np.ndarray, target_height: int = 32, target_width: int = 804) -> np.ndarray:
@@ -325,6 +346,15 @@ class OcrDetectionTask(BaseInferTask):
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
         pages, shapes, orgs = [], [], []
         for it in items:
+            if isinstance(it, torch.Tensor):  # a page that is already on the device (uint8 HWC): resized there, nothing goes up
+                if not it.is_cuda or it.dtype != torch.uint8 or it.dim() != 3:
+                    raise TypeError("tensor inputs must be uint8 HWC cuda tensors")
+                src_h, src_w = int(it.shape[0]), int(it.shape[1])
+                res, (ratio_h, ratio_w) = det_resize_for_test_device(self.predictor, it, self.limit_side_len, self.limit_type)
+                pages.append(res.contiguous())
+                shapes.append(np.array([src_h, src_w, ratio_h, ratio_w]))
+                orgs.append(tuple(it.shape))
+                continue
             img = _read_image(it)
             src_h, src_w = img.shape[:2]
             res, (ratio_h, ratio_w) = det_resize_for_test(img, self.limit_side_len, self.limit_type)
@@ -337,10 +367,11 @@ class OcrDetectionTask(BaseInferTask):
         dev = torch.device("cuda", self.device)
         groups: Dict[tuple, List[int]] = {}
         for i, p in enumerate(inputs["pages"]):
-            groups.setdefault(p.shape[:2], []).append(i)
+            groups.setdefault((int(p.shape[0]), int(p.shape[1])), []).append(i)
         boxes_out: List[Optional[np.ndarray]] = [None] * len(inputs["pages"])
         for (h, w), idx in groups.items():  # one launch sequence per distinct resized shape
-            batch = torch.from_numpy(np.stack([inputs["pages"][i] for i in idx])).to(dev, non_blocking=True)
+            members = [inputs["pages"][i] for i in idx]
+            batch = torch.stack([m if isinstance(m, torch.Tensor) else torch.from_numpy(m).to(dev, non_blocking=True) for m in members])
             prob = self.predictor.dbnet_forward_u8(batch, self.MEAN, self.STD, 1.0 / 255.0, flip=True)
             src = [(inputs["shape_list"][i][0], inputs["shape_list"][i][1]) for i in idx]
             boxes, counts = self.predictor.db_boxes(prob, src, self.thresh, self.box_thresh, self.unclip_ratio, self.max_candidates)
@@ -684,16 +715,30 @@ class OcrLayoutTask(BaseInferTask):
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
         imgs, org, sf = [], [], []
         for it in items:
-            img = _read_image(it)
-            h, w = img.shape[:2]
-            imgs.append(cv2.resize(np.ascontiguousarray(img), (self.IMG_W, self.IMG_H)))
+            if isinstance(it, torch.Tensor):  # a page that is already on the device (uint8 HWC): resized there
+                if not it.is_cuda or it.dtype != torch.uint8 or it.dim() != 3:
+                    raise TypeError("tensor inputs must be uint8 HWC cuda tensors")
+                h, w = int(it.shape[0]), int(it.shape[1])
+                imgs.append(self.post.resize_pages_u8(it.unsqueeze(0), self.IMG_W, self.IMG_H)[0])
+            else:
+                img = _read_image(it)
+                h, w = img.shape[:2]
+                imgs.append(cv2.resize(np.ascontiguousarray(img), (self.IMG_W, self.IMG_H)))
             org.append((h, w))
             sf.append((float(self.IMG_H) / h, float(self.IMG_W) / w))
-        return {"images": np.stack(imgs), "org_shape": org, "scale_factor": sf, "inputs": list(items)}
+        if any(isinstance(m, torch.Tensor) for m in imgs):
+            dev = torch.device("cuda", self.device)
+            images = torch.stack([m if isinstance(m, torch.Tensor) else torch.from_numpy(m).to(dev) for m in imgs])
+        else:
+            images = np.stack(imgs)
+        return {"images": images, "org_shape": org, "scale_factor": sf, "inputs": list(items)}
 
     def _run_model(self, inputs, **kwargs):
         dev = torch.device("cuda", self.device)
-        scores, dfl = self.predictor.picodet_forward_u8(torch.from_numpy(inputs["images"]).to(dev, non_blocking=True), flip=True)
+        images = inputs["images"]
+        if not isinstance(images, torch.Tensor):
+            images = torch.from_numpy(images).to(dev, non_blocking=True)
+        scores, dfl = self.predictor.picodet_forward_u8(images, flip=True)
         boxes, counts = self.post.picodet_decode(scores, dfl, inputs["org_shape"], inputs["scale_factor"], (self.IMG_H, self.IMG_W),
                                                  score_threshold=self.score_threshold, nms_threshold=self.nms_threshold,
                                                  nms_top_k=self.nms_top_k, keep_top_k=self.keep_top_k)

@@ -158,3 +158,19 @@ def test_sort_det_boxes_is_the_orchestrator_sort():
     assert np.array_equal(got, boxes[order].astype(np.float64))
     assert order.index(3) + 1 == order.index(7)
     assert predictors.sort_det_boxes(np.zeros((0, 8), np.float32)).shape[0] == 0
+
+
+def test_resize_restatement_equals_cv2_on_page_shapes():
+    """What dv_resize_linear_u8 implements, at the shapes of the page pre-processors: DetResizeForTest's
+    down-scale to a multiple of 32, its slight re-scale of a page that is already below the limit, an up-scale, an exact 2x
+    reduction (cv2's box-average special case) and PicoDet's non-uniform resize to 608 x 800."""
+    rng = np.random.default_rng(14)
+    for (sh, sw), dst in [((1400, 1100), None), ((700, 900), None), ((333, 517), (800, 608)), ((1920, 1216), (960, 608)),
+                          ((1600, 1216), (800, 608)), ((200, 150), (800, 608))]:
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        if dst is not None:
+            dh, dw = dst
+        else:
+            dh, dw = predictors.det_resize_shape(sh, sw, 960, "max")
+            assert dh % 32 == 0 and dw % 32 == 0 and max(dh, dw) <= 960
+        assert np.array_equal(ref.resize_linear(img, dw, dh), cv2.resize(img, (dw, dh))), (sh, sw, dh, dw)
