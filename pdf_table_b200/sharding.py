@@ -1,6 +1,7 @@
 """Multi-GPU plumbing of the hot path: pages / crops are independent, so every rank (one process per
 GPU) runs the whole cascade on its own contiguous shard with replicated weights, and the only exchange is ONE
-all-gather per batch of the packed decoded results (boxes + counts + token ids + lengths).  No other collective.
+all-gather per batch of the packed decoded results (boxes + counts + token ids + lengths, and the table cells --
+polygons + counts + logical coordinates -- when table structure ran).  No other collective.
 
 The reference has no distributed inference at all (single process, cuda:0, batch 1: base_infer_task.py:69,
 ocr_system_task.py:309-312); this module is the B200-side replacement for its serial page loop (cli/main.py:116-144).
@@ -24,50 +25,77 @@ def shard_sizes(n_items: int, world: int) -> List[int]:
 
 
 FIELDS = ("boxes", "box_counts", "ids", "id_lens")
+TABLE_FIELDS = ("cells", "cell_counts", "cell_logi")  # table structure: polygons [tables, max_cells, 8] f32, counts, logi [.., 4] f32
+_KIND = {"boxes": 0, "box_counts": 0, "ids": 1, "id_lens": 1, "cells": 2, "cell_counts": 2, "cell_logi": 2}  # rows = pages / crops / tables
 
 
-def pack_results(res: Dict[str, torch.Tensor], max_pages: int, max_crops: int) -> torch.Tensor:
-    """Fixed-size int32 record of one rank's results (float32 boxes are bit-cast), padded to the largest shard so a
-    single all_gather_into_tensor suffices.  Layout: [n_pages, n_crops, boxes..., box_counts..., ids..., id_lens...]."""
-    boxes, counts, ids, lens = (res[k] for k in FIELDS)
-    n_pages, max_boxes = boxes.shape[0], boxes.shape[1]
-    n_crops, t = ids.shape
-    dev = boxes.device
-    out = torch.zeros(2 + max_pages * max_boxes * 8 + max_pages + max_crops * t + max_crops, dtype=torch.int32, device=dev)
-    out[0], out[1] = n_pages, n_crops
-    o = 2
-    out[o:o + n_pages * max_boxes * 8] = boxes.reshape(-1).view(torch.int32)
-    o += max_pages * max_boxes * 8
-    out[o:o + n_pages] = counts
-    o += max_pages
-    out[o:o + n_crops * t] = ids.reshape(-1)
-    o += max_crops * t
-    out[o:o + n_crops] = lens
+def _fields(res: Dict[str, torch.Tensor]) -> Tuple[str, ...]:
+    """The record's fields: the four detection / recognition ones always, the three table-structure ones when given."""
+    has = [k in res for k in TABLE_FIELDS]
+    if any(has) and not all(has):
+        raise ValueError(f"table-structure results need all of {TABLE_FIELDS}")
+    return FIELDS + (TABLE_FIELDS if all(has) else ())
+
+
+def _row_len(t: torch.Tensor) -> int:
+    n = 1
+    for d in t.shape[1:]:
+        n *= int(d)
+    return n
+
+
+def pack_results(res: Dict[str, torch.Tensor], max_pages: int, max_crops: int, max_tables: int = 0) -> torch.Tensor:
+    """Fixed-size int32 record of one rank's results (float32 tensors are bit-cast), every field padded to the largest shard
+    so a single all_gather_into_tensor suffices.  Layout: [n_pages, n_crops, n_tables, field blocks in _fields() order]; a
+    field's block is max_rows x (product of its trailing dims) words, the first n_rows rows valid."""
+    names = _fields(res)
+    maxes = (max_pages, max_crops, max_tables)
+    counts = [res["boxes"].shape[0], res["ids"].shape[0], res["cells"].shape[0] if "cells" in res else 0]
+    for k in names:
+        if res[k].shape[0] != counts[_KIND[k]] or counts[_KIND[k]] > maxes[_KIND[k]]:
+            raise ValueError(f"field '{k}': {res[k].shape[0]} rows, expected {counts[_KIND[k]]} <= {maxes[_KIND[k]]}")
+    dev = res["boxes"].device
+    out = torch.zeros(3 + sum(maxes[_KIND[k]] * _row_len(res[k]) for k in names), dtype=torch.int32, device=dev)
+    out[0], out[1], out[2] = counts
+    o = 3
+    for k in names:
+        t = res[k].contiguous()
+        if t.dtype == torch.float32:
+            t = t.view(torch.int32)
+        elif t.dtype != torch.int32:
+            raise TypeError(f"field '{k}' must be float32 or int32, got {t.dtype}")
+        out[o:o + t.numel()] = t.reshape(-1)
+        o += maxes[_KIND[k]] * _row_len(res[k])
     return out
 
 
-def unpack_results(buf: torch.Tensor, max_pages: int, max_crops: int, max_boxes: int, t: int) -> Dict[str, torch.Tensor]:
-    n_pages, n_crops = int(buf[0]), int(buf[1])
-    o = 2
-    boxes = buf[o:o + n_pages * max_boxes * 8].view(torch.float32).reshape(n_pages, max_boxes, 8)
-    o += max_pages * max_boxes * 8
-    counts = buf[o:o + n_pages]
-    o += max_pages
-    ids = buf[o:o + n_crops * t].reshape(n_crops, t)
-    o += max_crops * t
-    lens = buf[o:o + n_crops]
-    return {"boxes": boxes, "box_counts": counts, "ids": ids, "id_lens": lens}
+def unpack_results(buf: torch.Tensor, like: Dict[str, torch.Tensor], max_pages: int, max_crops: int, max_tables: int = 0) -> Dict[str, torch.Tensor]:
+    """Inverse of pack_results for one rank's record; `like` = this rank's own results (trailing dims and dtypes are the
+    same on every rank)."""
+    names = _fields(like)
+    maxes = (max_pages, max_crops, max_tables)
+    counts = [int(buf[0]), int(buf[1]), int(buf[2])]
+    out = {}
+    o = 3
+    for k in names:
+        row, n = _row_len(like[k]), counts[_KIND[k]]
+        t = buf[o:o + n * row]
+        if like[k].dtype == torch.float32:
+            t = t.view(torch.float32)
+        out[k] = t.reshape((n,) + tuple(like[k].shape[1:]))
+        o += maxes[_KIND[k]] * row
+    return out
 
 
-def all_gather_results(res: Dict[str, torch.Tensor], page_sizes: Sequence[int], crop_sizes: Sequence[int], group=None) -> Dict[str, torch.Tensor]:
-    """ONE collective: every rank ends up with the results of all pages / crops in global order."""
+def all_gather_results(res: Dict[str, torch.Tensor], page_sizes: Sequence[int], crop_sizes: Sequence[int], group=None,
+                       table_sizes: Sequence[int] = ()) -> Dict[str, torch.Tensor]:
+    """ONE collective: every rank ends up with the results of all pages / crops (/ tables) in global order (rank-major)."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    max_pages, max_crops = max(page_sizes), max(crop_sizes)
-    max_boxes, t = res["boxes"].shape[1], res["ids"].shape[1]
-    mine = pack_results(res, max_pages, max_crops)
+    max_pages, max_crops, max_tables = max(page_sizes), max(crop_sizes), max(table_sizes) if len(table_sizes) else 0
+    mine = pack_results(res, max_pages, max_crops, max_tables)
     gathered = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
-    parts = [unpack_results(gathered[r * mine.numel():(r + 1) * mine.numel()], max_pages, max_crops, max_boxes, t) for r in range(world)]
-    return {k: torch.cat([p[k] for p in parts], 0) for k in FIELDS}
+    parts = [unpack_results(gathered[r * mine.numel():(r + 1) * mine.numel()], res, max_pages, max_crops, max_tables) for r in range(world)]
+    return {k: torch.cat([p[k] for p in parts], 0) for k in _fields(res)}
