@@ -1,0 +1,79 @@
+"""CPU interpreter of the engine's graph programs (pdf_table_b200/picodet_graph.py -> csrc/graph_net.cu) -- TEST INFRASTRUCTURE.
+
+Executes the lowered program (tensor table, op list, packed weights) with plain PyTorch fp32 ops, one op at a time with the
+semantics of the CUDA executor (graph_net.cu: k_stem3x3s2, k_dwconv, the 1x1 conv_igemm plans, k_se_scale / k_se_apply,
+k_up2, k_add, k_head_split), so that the LOWERING -- BatchNorm folding, weight packing, concatenations as channel slices, the
+order of the ops -- can be checked on CPU against the oracle restatement of the reference modules (oracle/picodet_net_ref.py,
+itself pinned against picodet/lcnet.py, csp_pan.py, pico_head.py).  Nothing here is product code.
+
+`fp16_activations=True` rounds every op output to fp16 as the device buffers do (weights of the 1x1 convs are fp16 in the blob
+already); with False the only difference from the oracle is the fp16 rounding of those weights.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+OP_STEM, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD = range(7)
+ACT_NONE, ACT_HSWISH = 0, 4
+
+
+def _act(x: torch.Tensor, act: int) -> torch.Tensor:
+    if act == ACT_NONE:
+        return x
+    if act == ACT_HSWISH:
+        return F.hardswish(x)
+    raise ValueError(f"activation code {act} is not used by graph programs")
+
+
+def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: bool = False) -> Tuple[List[torch.Tensor], Dict[int, Tuple[torch.Tensor, torch.Tensor]]]:
+    """blob: the tensor dict of build_picodet; x: fp32 [N,3,H,W] (pre-processed).  Returns (tensors NCHW fp32 by id,
+    {level: (scores [N,HW,C], dfl [N,HW,R])})."""
+    tensors, ops, meta = blob["graph.tensors"], blob["graph.ops"], blob["graph.meta"]
+    num_classes, reg_bins = int(meta[0]), int(meta[1])
+    n, _, hh, ww = x.shape
+    rnd = (lambda t: t.half().float()) if fp16_activations else (lambda t: t)
+    tens: List[torch.Tensor] = [x.float()]
+    for c, down in tensors[1:]:
+        tens.append(torch.zeros((n, int(c), -(-hh // int(down)), -(-ww // int(down))), dtype=torch.float32))
+    heads: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def wt(wid: int, field: str) -> torch.Tensor:
+        return torch.from_numpy(np.asarray(blob[f"w{wid}.{field}"]).astype(np.float32))
+
+    for code, in_t, in_coff, in_c, out_t, out_coff, out_c, k, stride, act, w, aux in (tuple(int(v) for v in op) for op in ops):
+        src = tens[in_t][:, in_coff:in_coff + in_c]
+        if code == OP_STEM:  # sw [(ky*3 + kx)*3 + cin][cout]
+            wk = wt(w, "sw").reshape(3, 3, 3, 16).permute(3, 2, 0, 1).contiguous()
+            out = _act(F.conv2d(src, wk, wt(w, "sb"), stride=2, padding=1), act)
+        elif code == OP_DW:  # dw [k*k][C]
+            wk = wt(w, "dw").t().reshape(in_c, 1, k, k).contiguous()
+            out = _act(F.conv2d(src, wk, wt(w, "db"), stride=stride, padding=k // 2, groups=in_c), act)
+        elif code in (OP_PW, OP_HEAD):  # w fp16 [Cout][Cin_pad], b fp32 padded
+            wk = wt(w, "w")[:, :in_c].reshape(-1, in_c, 1, 1)
+            out = _act(F.conv2d(src, wk, wt(w, "b")[:wk.shape[0]]), act)
+            if code == OP_HEAD:  # k_head_split: fp32 raw -> sigmoid class scores + raw DFL logits, pixel-major
+                raw = out.permute(0, 2, 3, 1).reshape(n, -1, out.shape[1])
+                heads[aux] = (torch.sigmoid(raw[..., :num_classes]), raw[..., num_classes:num_classes + reg_bins])
+                continue
+        elif code == OP_SE:
+            avg = src.mean((2, 3))
+            hid = F.relu(avg @ wt(w, "s1w").t() + wt(w, "s1b"))
+            scale = torch.clamp((hid @ wt(w, "s2w").t() + wt(w, "s2b")) / 6.0 + 0.5, 0.0, 1.0)
+            out = src * scale[:, :, None, None]
+        elif code == OP_UP2:  # nearest, to the destination tensor's own size
+            dst = tens[out_t]
+            iy = torch.clamp(torch.arange(dst.shape[2]) * src.shape[2] // dst.shape[2], max=src.shape[2] - 1)
+            ix = torch.clamp(torch.arange(dst.shape[3]) * src.shape[3] // dst.shape[3], max=src.shape[3] - 1)
+            out = src[:, :, iy][:, :, :, ix]
+        elif code == OP_ADD:
+            out = tens[in_t] + tens[aux]
+        else:
+            raise ValueError(f"unknown opcode {code}")
+        dst = tens[out_t]
+        assert out.shape[1] == out_c and out.shape[2:] == dst.shape[2:], (code, tuple(out.shape), tuple(dst.shape), out_c)
+        dst[:, out_coff:out_coff + out_c] = rnd(out)
+    return tens, heads

@@ -210,3 +210,28 @@ def test_polygon_area_and_length_stand_in_agrees_with_cv2():
         poly = db_post_ref.ShapelyPolygonStandIn(quad)
         assert poly.area == cv2.contourArea(quad.reshape(-1, 1, 2))  # integer shoelace sums are exact in both
         assert abs(poly.length - cv2.arcLength(quad.reshape(-1, 1, 2).astype(np.float32), True)) <= 1e-4 * max(poly.length, 1.0)
+
+
+def test_picodet_lowering_computes_the_reference_function():
+    """The graph program + packed weights that the engine executes (picodet_graph.build_picodet), run op by op on CPU with the
+    executor's semantics (oracle/graph_interp.py), reproduce the oracle restatement of LCNet + CSP-PAN + PicoHead: features of
+    every stage and the eight head outputs.  Checks BatchNorm folding, packing, slice-concatenations and op order on CPU."""
+    from oracle import graph_interp, picodet_net_ref
+    from pdf_table_b200 import picodet_graph as G
+
+    bb, nk, hd = synth.picodet_state_dicts(0, 5)
+    blob, meta = G.build_picodet(bb, nk, hd, 5)
+    x = torch.from_numpy(np.random.default_rng(31).standard_normal((2, 3, 320, 256)).astype(np.float32))
+    ws, wd, feats = picodet_net_ref.picodet_forward(bb, nk, hd, x, 5, return_features=True)
+    for fp16_act, tol in ((False, 2e-4), (True, 6e-4)):  # fp16 weights only (measured 7e-5) / + fp16 activation buffers as on the device (2.4e-4)
+        tens, heads = graph_interp.run_program(blob, x, fp16_activations=fp16_act)
+        for name, tid in meta["features"].items():
+            want = feats[name]
+            rel = float((tens[tid] - want).abs().max()) / max(1.0, float(want.abs().max()))
+            assert rel < tol, (fp16_act, name, rel)
+        assert sorted(heads) == [0, 1, 2, 3]
+        for lvl in range(4):
+            s, d = heads[lvl]
+            assert s.shape == ws[lvl].shape and d.shape == wd[lvl].shape
+            assert float((s - ws[lvl]).abs().max()) < tol
+            assert float((d - wd[lvl]).abs().max()) < tol * max(1.0, float(wd[lvl].abs().max()))
