@@ -371,7 +371,10 @@ class OcrDetectionTask(BaseInferTask):
         boxes_out: List[Optional[np.ndarray]] = [None] * len(inputs["pages"])
         for (h, w), idx in groups.items():  # one launch sequence per distinct resized shape
             members = [inputs["pages"][i] for i in idx]
-            batch = torch.stack([m if isinstance(m, torch.Tensor) else torch.from_numpy(m).to(dev, non_blocking=True) for m in members])
+            if any(isinstance(m, torch.Tensor) for m in members):  # pages resized on the device (mixed groups: the others go up one by one)
+                batch = torch.stack([m if isinstance(m, torch.Tensor) else torch.from_numpy(m).to(dev) for m in members])
+            else:
+                batch = torch.from_numpy(np.stack(members)).to(dev, non_blocking=True)
             prob = self.predictor.dbnet_forward_u8(batch, self.MEAN, self.STD, 1.0 / 255.0, flip=True)
             src = [(inputs["shape_list"][i][0], inputs["shape_list"][i][1]) for i in idx]
             boxes, counts = self.predictor.db_boxes(prob, src, self.thresh, self.box_thresh, self.unclip_ratio, self.max_candidates)
