@@ -117,3 +117,30 @@ def test_clipper_offset_known_answers():
     a = set(clipper_offset_round(rect, 5.0))
     b = set(clipper_offset_round(rect[::-1], 5.0))
     assert a == b
+
+
+def test_packed_dbnet_blob_computes_the_reference_function():
+    """The host half of the weight path on CPU: pack_dbnet_r18 (BatchNorm folding, K-major tap order, channel padding, the 7x7
+    stem and 2x2 transposed-conv layouts) -> write_blob -> parsed back with the container format csrc/capi.cu reads -> the
+    network run FROM THE PACKED TENSORS (oracle/blob_ref.py) equals the oracle forward up to the fp16 rounding of the weights."""
+    from oracle import blob_ref
+    from pdf_table_b200 import weights
+
+    sd = synth.dbnet_r18_state_dict(0)
+    blob = weights.pack_dbnet_r18(sd)
+    t = blob_ref.read_blob(blob)
+    assert t["stem.w"].dtype == np.float16 and t["stem.w"].shape == (64, 7 * 32) and t["layer2.0.down.w"].shape == (128, 64)
+    assert t["bin.deconv1.w"].shape == (256, 64) and t["bin.deconv2.w"].shape == (64, 4)
+    x = torch.from_numpy(np.random.default_rng(41).standard_normal((2, 3, 96, 128)).astype(np.float32))
+    want = dbnet_ref.dbnet_r18_forward(sd, x)
+    got = blob_ref.dbnet_r18_from_blob(t, x)
+    err = float((got - want).abs().max())
+    assert got.shape == want.shape == (2, 1, 96, 128) and err < 4e-3, err  # measured 2.4e-3: the fp16 rounding of the weights
+    # the check discriminates: the same tensors with two taps of one 3x3 layer swapped are an order of magnitude further away
+    bad = dict(t)
+    w = t["layer1.0.conv1.w"].reshape(64, 9, 64).copy()
+    w[:, [0, 8]] = w[:, [8, 0]]
+    bad["layer1.0.conv1.w"] = w.reshape(64, 9 * 64)
+    assert float((blob_ref.dbnet_r18_from_blob(bad, x) - want).abs().max()) > 10 * err
+    with pytest.raises(ValueError):
+        blob_ref.read_blob(blob[:4096])
