@@ -83,3 +83,61 @@ def dbnet_r18_from_blob(t: Dict[str, np.ndarray], x: torch.Tensor) -> torch.Tens
     w2 = torch.from_numpy(t["bin.deconv2.w"].astype(np.float32)).reshape(64, 1, 2, 2)
     b = F.conv_transpose2d(b, w2, torch.from_numpy(t["bin.deconv2.b"].copy()), stride=2)
     return torch.sigmoid(b)
+
+
+def _unpack_linear(t, name: str, cin: int):
+    w = t[name + ".w"].astype(np.float32)
+    return w[:, :cin].copy(), t[name + ".b"][:w.shape[0]].copy()
+
+
+def convnext_vit_state_dict_from_blob(t: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """t = read_blob(pack_convnext_vit(sd)) -> a state_dict with the REFERENCE's keys that computes what the packed tensors
+    compute: layer_scale folded into pwconv2 (so layer_scale_parameter = 1 here), the 1/8 attention scale folded into the
+    query projection (undone: x 8, exact), q | k | v split again, the (2,1) down-sampling conv and the patch projection back
+    in conv layout, position embeddings with a zero CLS row.  Feeding it to oracle/convnextvit_ref.convnextvit_forward checks
+    the packer on CPU; the only difference from the original state_dict is the fp16 rounding of the GEMM weights."""
+    sd: Dict[str, np.ndarray] = {}
+    p = "cnn_model.embeddings"
+    sd[p + ".patch_embeddings.weight"] = np.ascontiguousarray(t["patch.w"].T).reshape(96, 1, 4, 4)
+    sd[p + ".patch_embeddings.bias"] = t["patch.b"].copy()
+    sd[p + ".layernorm.weight"], sd[p + ".layernorm.bias"] = t["patch.ln.w"].copy(), t["patch.ln.b"].copy()
+    blk = 0
+    dims = (96, 192, 256, 512)
+    for s, (depth, dim) in enumerate(zip((3, 3, 8, 3), dims)):
+        sp = f"cnn_model.encoder.stages.{s}"
+        if s > 0:
+            cin = dims[s - 1]
+            sd[sp + ".downsampling_layer.0.weight"], sd[sp + ".downsampling_layer.0.bias"] = t[f"ds{s}.ln.w"].copy(), t[f"ds{s}.ln.b"].copy()
+            w = t[f"ds{s}.conv.w"].astype(np.float32).reshape(dim, 2, -1)[:, :, :cin]  # [C'][tap = kh][C]
+            sd[sp + ".downsampling_layer.1.weight"] = np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(dim, cin, 2, 1)
+            sd[sp + ".downsampling_layer.1.bias"] = t[f"ds{s}.conv.b"][:dim].copy()
+        for j in range(depth):
+            lp = f"{sp}.layers.{j}"
+            sd[lp + ".dwconv.weight"] = np.ascontiguousarray(t[f"blk{blk}.dw.w"].T).reshape(dim, 1, 7, 7)
+            sd[lp + ".dwconv.bias"] = t[f"blk{blk}.dw.b"].copy()
+            sd[lp + ".layernorm.weight"], sd[lp + ".layernorm.bias"] = t[f"blk{blk}.ln.w"].copy(), t[f"blk{blk}.ln.b"].copy()
+            sd[lp + ".pwconv1.weight"], sd[lp + ".pwconv1.bias"] = _unpack_linear(t, f"blk{blk}.pw1", dim)
+            sd[lp + ".pwconv2.weight"], sd[lp + ".pwconv2.bias"] = _unpack_linear(t, f"blk{blk}.pw2", 4 * dim)
+            sd[lp + ".layer_scale_parameter"] = np.ones(dim, np.float32)
+            blk += 1
+    v = "vitstr.vit"
+    w, b = _unpack_linear(t, "vit.proj", 512)
+    sd[v + ".embeddings.patch_embeddings.projection.weight"], sd[v + ".embeddings.patch_embeddings.projection.bias"] = w.reshape(192, 512, 1, 1), b
+    sd[v + ".embeddings.position_embeddings"] = np.concatenate([np.zeros((1, 192), np.float32), t["vit.pos"]], 0)[None]
+    L = 0
+    while f"vit{L}.qkv.w" in t:
+        lp = f"{v}.encoder.layer.{L}"
+        w, b = _unpack_linear(t, f"vit{L}.qkv", 192)
+        for k, name in enumerate(("query", "key", "value")):
+            scale = np.float32(8.0) if k == 0 else np.float32(1.0)
+            sd[f"{lp}.attention.attention.{name}.weight"] = w[k * 192:(k + 1) * 192] * scale
+            sd[f"{lp}.attention.attention.{name}.bias"] = b[k * 192:(k + 1) * 192] * scale
+        sd[lp + ".attention.output.dense.weight"], sd[lp + ".attention.output.dense.bias"] = _unpack_linear(t, f"vit{L}.proj", 192)
+        sd[lp + ".intermediate.dense.weight"], sd[lp + ".intermediate.dense.bias"] = _unpack_linear(t, f"vit{L}.fc1", 192)
+        sd[lp + ".output.dense.weight"], sd[lp + ".output.dense.bias"] = _unpack_linear(t, f"vit{L}.fc2", 768)
+        sd[lp + ".layernorm_before.weight"], sd[lp + ".layernorm_before.bias"] = t[f"vit{L}.ln1.w"].copy(), t[f"vit{L}.ln1.b"].copy()
+        sd[lp + ".layernorm_after.weight"], sd[lp + ".layernorm_after.bias"] = t[f"vit{L}.ln2.w"].copy(), t[f"vit{L}.ln2.b"].copy()
+        L += 1
+    sd[v + ".layernorm.weight"], sd[v + ".layernorm.bias"] = t["vit.ln.w"].copy(), t["vit.ln.b"].copy()
+    sd["vitstr.classifier.weight"], sd["vitstr.classifier.bias"] = _unpack_linear(t, "cls", 192)
+    return sd

@@ -144,3 +144,29 @@ def test_packed_dbnet_blob_computes_the_reference_function():
     assert float((blob_ref.dbnet_r18_from_blob(bad, x) - want).abs().max()) > 10 * err
     with pytest.raises(ValueError):
         blob_ref.read_blob(blob[:4096])
+
+
+def test_packed_convnextvit_blob_computes_the_reference_function():
+    """pack_convnext_vit on CPU: the packed tensors (layer_scale and attention scale folded, q | k | v concatenated, the (2,1)
+    down-sampling conv and the projections K-major, position table without the CLS row) turned back into a reference-keyed
+    state_dict (oracle/blob_ref.py) give the oracle's logits up to the fp16 rounding of the GEMM weights -- which is most of
+    the engine's own distance from the fp32 oracle (6e-3 of its 8.5e-3)."""
+    from oracle import blob_ref
+    from oracle import convnextvit_ref as ref
+    from pdf_table_b200 import weights
+
+    sd = synth.convnext_vit_state_dict(0)
+    t = blob_ref.read_blob(weights.pack_convnext_vit(sd))
+    sd2 = blob_ref.convnext_vit_state_dict_from_blob(t)
+    assert set(sd) - set(sd2) <= {"cnn_model.layernorm.bias", "cnn_model.layernorm.weight", "vitstr.vit.embeddings.cls_token"}  # unused by the forward
+    chunks = ref.preprocess([synth.synthetic_text_crop(700 + i, 32, 320) for i in range(2)])
+    want = ref.convnextvit_forward(sd, chunks)
+    got = ref.convnextvit_forward(sd2, chunks)
+    err = float((got - want).abs().max())
+    assert err < 1.2e-2, err  # measured 6.1e-3 on logits with sigma 2.06
+    assert float((got.argmax(-1) == want.argmax(-1)).float().mean()) >= 0.999
+    # discriminates: forgetting to undo the folded attention scale moves the logits by far more
+    bad = dict(sd2)
+    k = "vitstr.vit.encoder.layer.0.attention.attention.query.weight"
+    bad[k] = sd2[k] / np.float32(8.0)
+    assert float((ref.convnextvit_forward(bad, chunks) - want).abs().max()) > 5 * err
