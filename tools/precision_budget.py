@@ -25,12 +25,20 @@ def main():
     lin0, conv0 = F.linear, F.conv2d
     r16 = lambda x: x.half().float()
 
-    def run(act16: bool, w16: bool):
+    def run(act16: bool, w16: bool, split: bool = False):
         def lin(x, w, b=None):
+            if split:  # split-fp16 (the Lore processor's mode): A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulation
+                xh, wh = r16(x), r16(w)
+                xl, wl = r16(x - xh), r16(w - wh)
+                return lin0(xh, wh, b) + lin0(xh, wl) + lin0(xl, wh)
             return lin0(r16(x) if act16 else x, r16(w) if w16 else w, b)
 
         def conv(x, w, b=None, *a, **k):
             if k.get("groups", 1) == 1 and w.shape[1] > 1:  # the GEMM-type convs; depthwise / patchify run in fp32 on CUDA cores
+                if split:
+                    xh, wh = r16(x), r16(w)
+                    xl, wl = r16(x - xh), r16(w - wh)
+                    return conv0(xh, wh, b, *a, **k) + conv0(xh, wl, None, *a, **k) + conv0(xl, wh, None, *a, **k)
                 return conv0(r16(x) if act16 else x, r16(w) if w16 else w, b, *a, **k)
             return conv0(x, w, b, *a, **k)
 
@@ -41,8 +49,10 @@ def main():
             F.linear, F.conv2d = lin0, conv0
 
     print(f"ConvNextViT, {n} crops ({chunks.shape[0]} chunks), logit sigma {float(want.std()):.2f}")
-    for name, (a, w) in {"fp16 weights only": (False, True), "fp16 activations only": (True, False), "both (the engine's operand precision)": (True, True)}.items():
-        got = run(a, w)
+    modes = {"fp16 weights only": (False, True, False), "fp16 activations only": (True, False, False),
+             "both (the engine's operand precision)": (True, True, False), "split-fp16 on both operands (3 MMAs)": (True, True, True)}
+    for name, (a, w, sp) in modes.items():
+        got = run(a, w, sp)
         d = got - want
         print(f"  {name:40s} max|dlogit| = {float(d.abs().max()):.2e}   rms = {float(d.pow(2).mean().sqrt()):.2e}   "
               f"arg-max equal = {float((got.argmax(-1) == want.argmax(-1)).float().mean()):.5f}")
