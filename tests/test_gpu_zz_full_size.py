@@ -1,7 +1,7 @@
 """BASELINE configs[1] at FULL size on the GPU (32 pages 960 x 960, 1280 text-line crops) through properties that need no
 oracle run of that size: determinism, independence of an item's result from the batch it is processed in, equal inputs ->
 equal outputs inside one batch, permutation equivariance.  The small-size parity tests pin the values; these pin that nothing
-changes when the batch grows to the size the benchmark is quoted on.  (Named zz: the newest GPU tests run last.)"""
+changes when the batch grows to the size the benchmark is quoted on."""
 import numpy as np
 import pytest
 import torch

@@ -1,6 +1,6 @@
 """SURVEY.md 8(f)-2 on the GPU: the page pre-processors' cv2.resize for pages that are already on the device
 (Engine.resize_pages_u8 over dv_resize_linear_u8, bit-exact against cv2) and the detection / layout predictors fed with cuda
-tensors instead of ndarrays -- identical results, nothing but the raw page goes up.  (Named zz: the newest GPU tests run last.)"""
+tensors instead of ndarrays -- identical results, nothing but the raw page goes up."""
 import numpy as np
 import pytest
 import torch
