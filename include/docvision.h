@@ -128,6 +128,17 @@ int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blan
 int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, const double* src_hw_host, float thresh,
                 double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
                 int32_t* overflow_host);
+/*
+ * The same for the reference's in-tree DBNet back-end (model="db"): replaces OCRDetectionPostProcessor.__call__
+ * (db_net/processor_ocr_dbnet.py:113-127) = boxes_from_bitmap (db_net/ocr_detection_utils.py:168-205).  Differences from
+ * dv_db_boxes: the reference's constants there are box_thresh 0.3 / unclip 1.5 / 1000 contours (pass them); the mini box is
+ * truncated to int32 BEFORE it is scaled (np.round(box / width * dest_width), float64) and clipped to [0, dest]; corners keep
+ * get_mini_boxes' order (top-left, top-right, bottom-right, bottom-left of the x-sorted pairs) and no
+ * filter_tag_det_res step follows.  src_hw_host = org_shape (height, width) of each page.
+ */
+int dv_db_boxes_dbnet(dv_handle h, const float* prob, int n, int height, int width, const double* src_hw_host, float thresh,
+                      double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
+                      int32_t* overflow_host);
 
 /*
  * Lore / CenterNet "heat-map 3x3 max-pool NMS + top-K gather": head maps -> sorted table cells, on the device.

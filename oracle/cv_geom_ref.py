@@ -217,18 +217,14 @@ def rotating_calipers(hp):
     minarea = F(np.finfo(np.float32).max)
     buf = None
     for k in range(n):
-        dp = [
-            F(F(+base_a * vx[seq[0]]) + F(base_b * vy[seq[0]])),
-            F(F(-base_b * vx[seq[1]]) + F(base_a * vy[seq[1]])),
-            F(F(-base_a * vx[seq[2]]) - F(base_b * vy[seq[2]])),
-            F(F(+base_b * vx[seq[3]]) - F(base_a * vy[seq[3]])),
-        ]
-        maxcos = F(dp[0] * inv[seq[0]])
+        # OpenCV >= 4.5.2: the caliper side with the smallest angle to its polygon edge is found by cross-product signs of the
+        # edge vectors rotated into a common frame (firstVecIsRight), not by comparing cosines
+        rot = [(vx[seq[0]], vy[seq[0]]), (vy[seq[1]], F(-vx[seq[1]])), (F(-vx[seq[2]]), F(-vy[seq[2]])), (F(-vy[seq[3]]), vx[seq[3]])]
         main = 0
         for i in range(1, 4):
-            c = F(dp[i] * inv[seq[i]])
-            if c > maxcos:
-                main, maxcos = i, c
+            tx, ty = rot[i][1], F(-rot[i][0])  # rotate90CW(rot[i])
+            if F(F(tx * rot[main][0]) + F(ty * rot[main][1])) < 0:
+                main = i
         pi = seq[main]
         lead_x = F(vx[pi] * inv[pi])
         lead_y = F(vy[pi] * inv[pi])
@@ -264,40 +260,38 @@ def rotating_calipers(hp):
 
 
 def min_area_rect(points):
-    """cv::minAreaRect for integer points -> ((cx, cy), (w, h), angle) as float32 (angle in degrees)."""
-    hull = convex_hull(points, clockwise=True)  # minAreaRect calls convexHull(points, hull, true, true)
+    """cv::minAreaRect of OpenCV 4.13 for integer points -> ((cx, cy), (w, h), angle) as float32 (angle in degrees).
+    Two facts measured against cv2 4.13 (tools/min_area_rect_probe.py; pinned by tests/test_oracle_cpu.py): the calipers walk
+    the COUNTER-clockwise hull, and the angle is brought into [-90, 0) in double by quarter turns that swap width and height,
+    then rounded to float once."""
+    hull = convex_hull(points, clockwise=False)
     n = len(hull)
-    cx = cy = w = h = ang = F(0)
+    cx = cy = w = h = F(0)
+    ang = 0.0
     if n > 2:
         o = rotating_calipers(hull)
         cx = F(o[0] + F(F(o[2] + o[4]) * F(0.5)))
         cy = F(o[1] + F(F(o[3] + o[5]) * F(0.5)))
         w = F(math.sqrt(float(o[2]) * float(o[2]) + float(o[3]) * float(o[3])))
         h = F(math.sqrt(float(o[4]) * float(o[4]) + float(o[5]) * float(o[5])))
-        ang = F(math.atan2(float(o[3]), float(o[2])))
+        ang = math.atan2(float(o[3]), float(o[2]))
     elif n == 2:
         cx = F(F(F(hull[0][0]) + F(hull[1][0])) * F(0.5))
         cy = F(F(F(hull[0][1]) + F(hull[1][1])) * F(0.5))
         dx = float(F(hull[1][0]) - F(hull[0][0]))
         dy = float(F(hull[1][1]) - F(hull[0][1]))
         w = F(math.sqrt(dx * dx + dy * dy))
-        ang = F(math.atan2(dy, dx))
+        ang = math.atan2(dy, dx)
     elif n == 1:
         cx, cy = F(hull[0][0]), F(hull[0][1])
-    ang = F(float(ang) * 180 / math.pi)
-    # cv2 >= 4.5 reports the angle in [-90, 0): observed rule (tests/test_oracle_cpu.py) -- a non-negative angle is
-    # moved down by 90 degrees with width and height swapped
-    if n > 2 and ang >= 0:
-        ang = F(ang - F(90))
+    ang = ang * 180 / math.pi
+    while ang >= 0.0:
+        ang -= 90.0
         w, h = h, w
-    elif n <= 2:
-        # degenerate hulls: cv2 returns (0, len) / -90 for n == 2 and -90 for n == 1 in this build
-        if n == 2 and ang >= 0:
-            ang = F(ang - F(90))
-            w, h = h, w
-        elif n == 1:
-            ang = F(-90)
-    return (cx, cy), (w, h), ang
+    while ang < -90.0:
+        ang += 90.0
+        w, h = h, w
+    return (cx, cy), (w, h), F(ang)
 
 
 def box_points(rect):

@@ -247,3 +247,39 @@ def db_postprocess(pred: np.ndarray, shape_list: np.ndarray, org_shape, thresh=0
     src_h, src_w = shape_list[0], shape_list[1]
     boxes, _ = boxes_from_bitmap(pred, seg, src_w, src_h, box_thresh, unclip_ratio, max_candidates)
     return filter_tag_det_res(boxes, org_shape).reshape(-1, 8)
+
+
+def dbnet_boxes_from_bitmap(pred, bitmap, dest_width, dest_height, box_thresh=0.3, unclip_ratio=1.5, max_candidates=1000):
+    """boxes_from_bitmap of the in-tree DBNet back-end (db_net/ocr_detection_utils.py:168-205): as the db_pp one up to the second
+    mini box, then the box is TRUNCATED to int32, scaled with np.round(box / width * dest) in float64, clipped to [0, dest]
+    and returned as a flat list of python ints; no clockwise re-ordering / size filter follows."""
+    height, width = bitmap.shape
+    contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    boxes, scores = [], []
+    for contour in contours[:max_candidates]:
+        points, sside = get_mini_boxes(contour)
+        if sside < 3:
+            continue
+        points = np.array(points)
+        score = box_score_fast(pred, points.reshape(-1, 2))
+        if box_thresh > score:
+            continue
+        box = unclip(points, unclip_ratio).reshape(-1, 1, 2)
+        box, sside = get_mini_boxes(box)
+        if sside < 3 + 2:
+            continue
+        box = np.array(box).astype(np.int32)
+        box[:, 0] = np.clip(np.round(box[:, 0] / width * dest_width), 0, dest_width)
+        box[:, 1] = np.clip(np.round(box[:, 1] / height * dest_height), 0, dest_height)
+        boxes.append(box.reshape(-1).tolist())
+        scores.append(score)
+    return boxes, scores
+
+
+def dbnet_postprocess(pred: np.ndarray, org_shape, thresh=0.2) -> np.ndarray:
+    """OCRDetectionPostProcessor.__call__ (db_net/processor_ocr_dbnet.py:113-127): pred fp32 [H,W] of one page, org_shape =
+    (height, width) -> det_polygons int64 [n, 8]."""
+    pred = np.asarray(pred, np.float32)
+    height, width = int(org_shape[0]), int(org_shape[1])
+    boxes, _ = dbnet_boxes_from_bitmap(pred, pred > thresh, width, height)
+    return np.array(boxes, dtype=np.int64).reshape(-1, 8)

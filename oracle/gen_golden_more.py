@@ -139,3 +139,63 @@ def gen_det_pre():
 
 
 GENERATORS = {"convnextvit": gen_convnextvit, "db_post": gen_db_post, "det_pre": gen_det_pre}
+
+
+def _ref_dbnet_proc():
+    """The reference's in-tree DBNet processors (db_net/processor_ocr_dbnet.py, db_net/ocr_detection_utils.py) with a stand-in
+    config module and the two missing wheels replaced by the restatements of oracle/db_post_ref.py."""
+    ref_import.setup()
+    from . import db_post_ref
+
+    sys.modules["pyclipper"] = db_post_ref.PyclipperStandIn
+    sg = sys.modules.get("shapely.geometry") or types.ModuleType("shapely.geometry")
+    sg.Polygon = db_post_ref.ShapelyPolygonStandIn
+    sys.modules["shapely.geometry"] = sg
+    name = "pdftable.model.db_net.configuration_dbnet"
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.DbNetConfig = type("DbNetConfig", (), {})
+        sys.modules[name] = m
+    import pdftable.model.db_net.ocr_detection_utils as utils
+    import pdftable.model.db_net.processor_ocr_dbnet as mod
+
+    utils.pyclipper = db_post_ref.PyclipperStandIn
+    utils.Polygon = db_post_ref.ShapelyPolygonStandIn
+    return mod
+
+
+DBNET_POST_CASES = [
+    # name, map index, map h, map w, n_lines, org_h, org_w
+    ("same", 0, 736, 992, 40, 736, 992),
+    ("scaled", 2, 640, 960, 30, 1000, 1500),
+    ("small", 3, 160, 224, 6, 160, 224),
+    ("tall", 4, 960, 320, 12, 2875, 960),
+]
+
+
+def gen_dbnet_proc():
+    """Reference OCRDetectionPreprocessor / OCRDetectionPostProcessor (the model="db" back-end): resize rule on odd page sizes,
+    the normalised tensor of one small page, and det_polygons on planted probability maps."""
+    mod = _ref_dbnet_proc()
+    cfg = types.SimpleNamespace(img_width=736, thresh=0.2, return_polygon=False)
+    pre, post = mod.OCRDetectionPreprocessor(cfg), mod.OCRDetectionPostProcessor(cfg)
+    mod.logger.info = lambda *a, **k: None
+    shapes = [(960, 960), (1000, 1500), (2875, 960), (700, 500), (480, 1919), (736, 736), (100, 150)]
+    rows = []
+    for h, w in shapes:
+        img = (np.arange(h * w * 3, dtype=np.int64) % 251).astype(np.uint8).reshape(h, w, 3)
+        r = pre.resize(img)
+        rows.append([h, w, r.shape[0], r.shape[1]])
+    page = synth.synthetic_page(5, 100, 150)
+    d = pre(page)
+    out = {"table": np.array(rows, np.int64), "page_chw": d["image"].numpy().astype(np.float32), "page_org_shape": np.array(d["org_shape"], np.int64)}
+    for name, idx, h, w, n_lines, org_h, org_w in DBNET_POST_CASES:
+        prob = synth.synthetic_prob_map(idx, h, w, n_lines)
+        res = post({"results": torch.from_numpy(prob)[None, None], "org_shape": [org_h, org_w]})
+        out["post_" + name] = np.asarray(res["det_polygons"]).reshape(-1, 8).astype(np.int64)
+        print("dbnet_proc", name, out["post_" + name].shape)
+    np.savez_compressed(os.path.join(GOLDEN, "dbnet_proc.npz"), **out)
+    print("dbnet_proc", np.array(rows)[:, 2:].tolist(), d["image"].shape)
+
+
+GENERATORS["dbnet_proc"] = gen_dbnet_proc

@@ -34,6 +34,8 @@ SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_db_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_float, C.c_double,
                               C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "dv_db_boxes_dbnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_float, C.c_double,
+                                    C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "dv_lore_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),

@@ -166,7 +166,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
 
 int dv_destroy(dv_handle h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     cudaDeviceSynchronize();
     h->model.reset();
     h->aux.clear();
@@ -203,7 +203,7 @@ int dv_profile_begin(dv_handle h) {
 
 long long dv_profile_report(dv_handle h, char* buf_host, size_t cap) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     h->profiling = false;
     DV_CUDA(h, cudaStreamSynchronize(h->stream));
     std::string js = "[";
@@ -242,7 +242,7 @@ double dv_model_flops(dv_handle h) {
 int dv_dbnet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* prob_out) {
     if (!h) return DV_ERR_ARG;
     if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return dbnet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0.f, 0, n, height, width, prob_out);
 }
 
@@ -250,13 +250,13 @@ int dv_dbnet_forward_u8(dv_handle h, const uint8_t* pages_hwc_u8, int n, int hei
                         const float* mean3_host, const float* std3_host, float scale, int flip, float* prob_out) {
     if (!h) return DV_ERR_ARG;
     if (!pages_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward_u8: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return dbnet_forward(h, nullptr, pages_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, prob_out);
 }
 
 int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int* dims4_host) {
     if (!h || !name) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if (h->kind == "picodet" && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
@@ -266,7 +266,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
 int dv_ctc_greedy(dv_handle h, const float* probs, int b, int t, int c, int blank, int32_t* out_ids,
                   int32_t* out_len, float* out_conf, int32_t* raw_ids, float* raw_max) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return ctc_greedy(h, probs, b, t, c, blank, out_ids, out_len, out_conf, raw_ids, raw_max);
 }
 
@@ -274,9 +274,18 @@ int dv_db_boxes(dv_handle h, const float* prob, int n, int height, int width, co
                 double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
                 int32_t* overflow_host) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return db_boxes(h, prob, n, height, width, src_hw_host, thresh, box_thresh, unclip_ratio, max_candidates, boxes_out,
                     counts_out, overflow_host);
+}
+
+int dv_db_boxes_dbnet(dv_handle h, const float* prob, int n, int height, int width, const double* src_hw_host, float thresh,
+                      double box_thresh, double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out,
+                      int32_t* overflow_host) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return db_boxes(h, prob, n, height, width, src_hw_host, thresh, box_thresh, unclip_ratio, max_candidates, boxes_out,
+                    counts_out, overflow_host, /*variant=*/1);
 }
 
 int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* wh, const float* st, int layout, int n,
@@ -284,7 +293,7 @@ int dv_lore_decode(dv_handle h, const float* hm, const float* reg, const float* 
                    float* polygons, float* scores, int32_t* dets_feat, int32_t* ax_idx, int32_t* cr_idx, int32_t* counts,
                    int32_t* rows, int32_t* overflow_host) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     LoreMaps m;
     const long long hw = static_cast<long long>(height) * width;
     if (layout == 0) {
@@ -351,7 +360,7 @@ int dv_centernet_decode(dv_handle h, const float* hm, const float* reg, const fl
                         int width, const double* inv_affine_host, int K, int MK, float score_threshold, float* polygons, int32_t* counts,
                         int32_t* overflow_host) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     LoreMaps m;
     DV_TRY(make_lore_maps(h, hm, reg, c2v, v2c, layout, height, width, &m));
     return centernet_decode(h, m, n, height, width, inv_affine_host, K, MK, score_threshold, polygons, counts, overflow_host);
@@ -369,14 +378,14 @@ int dv_centernet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, in
 int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, int channels, int height, int width, int K,
                         const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx, float* logi_feat) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return lore_gather_logi(h, ax, cr, n, channels, height, width, K, counts, ax_idx, cr_idx, logi_feat);
 }
 
 int dv_lore_detect_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out) {
     if (!h) return DV_ERR_ARG;
     if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_lore_detect_forward: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return lore_detect_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0, n, height, width, maps_out);
 }
 
@@ -384,21 +393,21 @@ int dv_lore_detect_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, 
                               const float* std3_host, int flip, float* maps_out) {
     if (!h) return DV_ERR_ARG;
     if (!images_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_lore_detect_forward_u8: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return lore_detect_forward(h, nullptr, images_hwc_u8, mean3_host, std3_host, flip, n, height, width, maps_out);
 }
 
 int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
                           float* logi_feat, int32_t* offsets_out, int32_t* overflow_host) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return lore_cell_features(h, n, K, max_rows, counts, ax_idx, cr_idx, logi_feat, offsets_out, overflow_host);
 }
 
 int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
                             float* logic_out, float* stacked_out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return lore_process_forward(h, feat, max_rows, n_rows_dev, offsets, n_images, logic_out, stacked_out);
 }
 
@@ -407,7 +416,7 @@ int dv_picodet_decode(dv_handle h, const float* const* scores_host_ptrs, const f
                       const float* scale_factor_host, float score_threshold, double nms_threshold, int nms_top_k, int keep_top_k,
                       int out_cap, double* boxes_out, int32_t* counts_out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return picodet_decode(h, scores_host_ptrs, dfl_host_ptrs, n, num_classes, reg_max, strides_host, in_height, in_width, org_hw_host,
                           scale_factor_host, score_threshold, nms_threshold, nms_top_k, keep_top_k, out_cap, boxes_out, counts_out);
 }
@@ -416,7 +425,7 @@ int dv_picodet_forward(dv_handle h, const float* in_nchw_f32, int n, int height,
                        float* const* dfl_out_host_ptrs) {
     if (!h) return DV_ERR_ARG;
     if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_picodet_forward: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return picodet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 1.f, 0, n, height, width, scores_out_host_ptrs, dfl_out_host_ptrs);
 }
 
@@ -425,7 +434,7 @@ int dv_picodet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int 
                           float* const* dfl_out_host_ptrs) {
     if (!h) return DV_ERR_ARG;
     if (!images_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_picodet_forward_u8: null input");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return picodet_forward(h, nullptr, images_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, scores_out_host_ptrs,
                            dfl_out_host_ptrs);
 }
@@ -435,7 +444,7 @@ int dv_picodet_num_classes(dv_handle h) { return h ? graph_num_classes(h) : 0; }
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     if (n_crops > 0 && !chunks_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_convnextvit_forward: null input");
     return cnv_forward(h, chunks_nchw_f32, nullptr, 0, n_crops, logits_out, ids_out, max_out);
 }
@@ -443,7 +452,7 @@ int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crop
 int dv_convnextvit_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, int n_crops, int crop_w, float* logits_out,
                               int32_t* ids_out, float* max_out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     if (n_crops > 0 && !crops_hwc_u8) return set_err(h, DV_ERR_ARG, "dv_convnextvit_forward_u8: null input");
     return cnv_forward(h, nullptr, crops_hwc_u8, crop_w, n_crops, logits_out, ids_out, max_out);
 }
@@ -461,7 +470,7 @@ int dv_warp_perspective_u8(dv_handle h, const uint8_t* page_hwc_u8, int height, 
     if (n == 0) return 0;
     if (!page_hwc_u8 || !minv || !sizes || !offsets || !out || n < 0 || height <= 0 || width <= 0 || max_pixels <= 0)
         return set_err(h, DV_ERR_ARG, "dv_warp_perspective_u8: null pointer / bad size");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_warp_perspective_u8(h, page_hwc_u8, height, width, minv, sizes, reinterpret_cast<const long long*>(offsets), n, max_pixels, out);
 }
 
@@ -471,7 +480,7 @@ int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* s
     if (n == 0) return 0;
     if (!src_packed || !src_offsets || !src_sizes || !dst_widths || !out || n < 0 || dst_h <= 0 || dst_w_pad <= 0)
         return set_err(h, DV_ERR_ARG, "dv_resize_linear_u8: null pointer / bad size");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_resize_linear_u8(h, src_packed, reinterpret_cast<const long long*>(src_offsets), src_sizes, dst_widths, n, dst_h, dst_w_pad, out);
 }
 
@@ -483,7 +492,7 @@ int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
     if (!pages_hwc_u8 || !quads || !out || !dst_widths || !minv_ws || !sizes_ws || n < 0 || n_pages <= 0 || height <= 0 || width <= 0 ||
         dst_h <= 0 || dst_w_pad <= 0)
         return set_err(h, DV_ERR_ARG, "dv_crop_quads_for_rec: null pointer / bad size");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, quads, page_idx, nullptr, 0, 0, n, dst_h, dst_w_pad, out, dst_widths, minv_ws,
                                  sizes_ws);
 }
@@ -495,7 +504,7 @@ int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
     if (!pages_hwc_u8 || !boxes || !box_counts || !out || !dst_widths || !minv_ws || !sizes_ws || n_pages <= 0 || height <= 0 || width <= 0 ||
         box_stride <= 0 || per_page <= 0 || per_page > box_stride || dst_h <= 0 || dst_w_pad <= 0)
         return set_err(h, DV_ERR_ARG, "dv_crop_boxes_for_rec: null pointer / bad size");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, boxes, nullptr, box_counts, box_stride, per_page, n_pages * per_page, dst_h,
                                  dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
 }
@@ -506,7 +515,7 @@ int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int wi
     if (!img_hwc_u8 || !m_inv6_host || !out || height <= 0 || width <= 0 || out_w <= 0 || out_h <= 0)
         return set_err(h, DV_ERR_ARG, "dv_warp_affine_u8: null pointer / bad size");
     if (static_cast<long long>(out_w) * out_h > 0x7fffffffLL / 4) return set_err(h, DV_ERR_ARG, "dv_warp_affine_u8: output too large");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_warp_affine_u8(h, img_hwc_u8, height, width, m_inv6_host, out_w, out_h, out);
 }
 
@@ -517,7 +526,7 @@ int dv_crop_tables_for_tsr(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages
         return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: bad size (0 <= n <= 65535)");
     if (n > 0 && (!pages_hwc_u8 || !rects || !m_inv || !out)) return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: null pointer");
     if (static_cast<long long>(out_w) * out_h > 0x7fffffffLL / 4) return set_err(h, DV_ERR_ARG, "dv_crop_tables_for_tsr: output too large");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_warp_affine_rects_u8(h, pages_hwc_u8, n_pages, height, width, rects, m_inv, n, out_w, out_h, out);
 }
 
@@ -526,14 +535,14 @@ int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t*
     if (!h) return DV_ERR_ARG;
     if (!crops_hwc_u8 || !widths || !out_nchw_f32 || b <= 0 || height <= 0 || width <= 0)
         return set_err(h, DV_ERR_ARG, "dv_pp_rec_normalise: null pointer / empty batch");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_pp_rec_norm(h, crops_hwc_u8, widths, b, height, width, out_nchw_f32);
 }
 
 int dv_ctc_collapse(dv_handle h, const int32_t* ids, const float* scores, int b, int t, int blank,
                     int32_t* out_ids, int32_t* out_len, float* out_conf) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return ctc_collapse(h, ids, scores, b, t, blank, out_ids, out_len, out_conf);
 }
 
@@ -542,7 +551,7 @@ int dv_conv2d_nhwc_f16(dv_handle h, const void* in_nhwc_f16, int n, int height, 
                        int stride, int pad, const void* residual_nhwc_f16, int act, void* out_nhwc_f16) {
     if (!h) return DV_ERR_ARG;
     if (!in_nhwc_f16 || !weight_packed_f16 || !out_nhwc_f16) return set_err(h, DV_ERR_ARG, "dv_conv2d: null pointer");
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     Tensor in;
     in.p = const_cast<__half*>(reinterpret_cast<const __half*>(in_nhwc_f16));
     in.N = n;
@@ -590,12 +599,12 @@ int dv_conv2d_nhwc_f16(dv_handle h, const void* in_nhwc_f16, int n, int height, 
 
 int dv_nchw_f32_to_nhwc_f16(dv_handle h, const float* in, int n, int c, int height, int width, void* out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_nchw_f32_to_nhwc_f16(h, in, n, c, height, width, reinterpret_cast<__half*>(out));
 }
 int dv_nhwc_f16_to_nchw_f32(dv_handle h, const void* in, int n, int c, int height, int width, float* out) {
     if (!h) return DV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     return op_nhwc_f16_to_nchw_f32(h, reinterpret_cast<const __half*>(in), n, c, height, width, out);
 }
 

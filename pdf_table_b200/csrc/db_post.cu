@@ -302,9 +302,12 @@ __device__ int sklansky(const unsigned long long* P, int start, int end, int* st
     return --stacksize;
 }
 
-// cv::convexHull(points, clockwise=true, returnPoints=true) as called by cv::minAreaRect.
+// cv::convexHull(points, clockwise=false, returnPoints=true) as called by cv::minAreaRect of OpenCV 4.13 (the hull the
+// rotating calipers walk is COUNTER-clockwise there: with the clockwise hull of older releases the calipers stop on a
+// different but equivalent edge in ~90 % of rotated rectangles and the float32 result differs in its last bits; measured
+// against cv2 4.13 in tools/min_area_rect_probe.py).
 // P: sorted keys [total]; stack: int[total+2]; hull: int[total] (receives ORIGINAL indices). Returns hull size.
-__device__ int convex_hull_cw(const unsigned long long* P, int total, int* stack, int* hull) {
+__device__ int convex_hull_ccw(const unsigned long long* P, int total, int* stack, int* hull) {
     int nout = 0;
     int miny = 0, maxy = 0;
     for (int i = 1; i < total; ++i) {
@@ -316,9 +319,17 @@ __device__ int convex_hull_cw(const unsigned long long* P, int total, int* stack
         hull[nout++] = 0;
     } else {
         int* tl = stack;
-        const int tl_count = sklansky(P, 0, maxy, tl, -1, 1);
+        int tl_count = sklansky(P, 0, maxy, tl, -1, 1);
         int* tr = stack + tl_count;
-        const int tr_count = sklansky(P, total - 1, maxy, tr, -1, -1);
+        int tr_count = sklansky(P, total - 1, maxy, tr, -1, -1);
+        {  // counter-clockwise: swap the two upper chains
+            int* t = tl;
+            tl = tr;
+            tr = t;
+            const int c = tl_count;
+            tl_count = tr_count;
+            tr_count = c;
+        }
         for (int i = 0; i < tl_count - 1; ++i) hull[nout++] = tl[i];
         for (int i = tr_count - 1; i > 0; --i) hull[nout++] = tr[i];
         const int stop_idx = tr_count > 2 ? tr[1] : tl_count > 2 ? tl[tl_count - 2] : -1;
@@ -326,14 +337,6 @@ __device__ int convex_hull_cw(const unsigned long long* P, int total, int* stack
         int bl_count = sklansky(P, 0, miny, bl, 1, -1);
         int* br = stack + bl_count;
         int br_count = sklansky(P, total - 1, miny, br, 1, 1);
-        {  // clockwise: swap the two lower chains
-            int* t = bl;
-            bl = br;
-            br = t;
-            const int c = bl_count;
-            bl_count = br_count;
-            br_count = c;
-        }
         if (stop_idx >= 0) {
             const int check_idx = bl_count > 2 ? bl[1] : (bl_count + br_count > 2 ? br[2 - bl_count] : -1);
             if (check_idx == stop_idx ||
@@ -386,6 +389,7 @@ struct RRect {
 // work = 3*n floats of scratch.
 __device__ RRect min_area_rect_hull(const float2* hp, int n, float* work) {
     RRect r{0.f, 0.f, 0.f, 0.f, 0.f};
+    double ang = 0.0;
     if (n > 2) {
         float* inv = work;
         float* vx = work + n;
@@ -426,19 +430,17 @@ __device__ RRect min_area_rect_hull(const float2* hp, int n, float* work) {
         int b_left = 0, b_bottom = 0;
         float b_a = 0.f, b_w = 0.f, b_b = 0.f, b_h = 0.f;
         for (int k = 0; k < n; ++k) {
-            float dp[4];
-            dp[0] = __fadd_rn(__fmul_rn(base_a, vx[seq[0]]), __fmul_rn(base_b, vy[seq[0]]));
-            dp[1] = __fadd_rn(__fmul_rn(-base_b, vx[seq[1]]), __fmul_rn(base_a, vy[seq[1]]));
-            dp[2] = __fsub_rn(__fmul_rn(-base_a, vx[seq[2]]), __fmul_rn(base_b, vy[seq[2]]));
-            dp[3] = __fsub_rn(__fmul_rn(base_b, vx[seq[3]]), __fmul_rn(base_a, vy[seq[3]]));
-            float maxcos = __fmul_rn(dp[0], inv[seq[0]]);
+            // OpenCV >= 4.5.2 (rotcalipers.cpp firstVecIsRight): the caliper side with the smallest angle to its polygon edge
+            // is found from cross-product signs of the edge vectors rotated into a common frame, not by comparing cosines
+            float rvx[4], rvy[4];
+            rvx[0] = vx[seq[0]];  rvy[0] = vy[seq[0]];
+            rvx[1] = vy[seq[1]];  rvy[1] = -vx[seq[1]];
+            rvx[2] = -vx[seq[2]]; rvy[2] = -vy[seq[2]];
+            rvx[3] = -vy[seq[3]]; rvy[3] = vx[seq[3]];
             int main_element = 0;
             for (int i = 1; i < 4; ++i) {
-                const float cosalpha = __fmul_rn(dp[i], inv[seq[i]]);
-                if (cosalpha > maxcos) {
-                    main_element = i;
-                    maxcos = cosalpha;
-                }
+                const float tx = rvy[i], ty = -rvx[i];  // rotate90CW
+                if (__fadd_rn(__fmul_rn(tx, rvx[main_element]), __fmul_rn(ty, rvy[main_element])) < 0.f) main_element = i;
             }
             {
                 const int pindex = seq[main_element];
@@ -482,28 +484,34 @@ __device__ RRect min_area_rect_hull(const float2* hp, int n, float* work) {
         r.cy = __fadd_rn(oy, __fmul_rn(__fadd_rn(o1y, o2y), 0.5f));
         r.w = static_cast<float>(sqrt(static_cast<double>(o1x) * o1x + static_cast<double>(o1y) * o1y));
         r.h = static_cast<float>(sqrt(static_cast<double>(o2x) * o2x + static_cast<double>(o2y) * o2y));
-        r.ang = static_cast<float>(atan2(static_cast<double>(o1y), static_cast<double>(o1x)));
+        ang = atan2(static_cast<double>(o1y), static_cast<double>(o1x));
     } else if (n == 2) {
         r.cx = __fmul_rn(__fadd_rn(hp[0].x, hp[1].x), 0.5f);
         r.cy = __fmul_rn(__fadd_rn(hp[0].y, hp[1].y), 0.5f);
         const double dx = static_cast<double>(__fsub_rn(hp[1].x, hp[0].x));
         const double dy = static_cast<double>(__fsub_rn(hp[1].y, hp[0].y));
         r.w = static_cast<float>(sqrt(dx * dx + dy * dy));
-        r.ang = static_cast<float>(atan2(dy, dx));
+        ang = atan2(dy, dx);
     } else if (n == 1) {
         r.cx = hp[0].x;
         r.cy = hp[0].y;
     }
-    r.ang = static_cast<float>(static_cast<double>(r.ang) * 180 / 3.1415926535897932384626433832795);
-    // angle range [-90, 0) of current OpenCV (observed rule, see oracle/cv_geom_ref.py)
-    if (n >= 2 && r.ang >= 0.f) {
-        r.ang = __fsub_rn(r.ang, 90.f);
+    // OpenCV 4.13: the angle is brought into [-90, 0) in DOUBLE by quarter turns, each swapping width and height, and is
+    // rounded to float once (observed rule, pinned against cv2 by tests/test_oracle_cpu.py through oracle/cv_geom_ref.py)
+    ang = ang * 180 / 3.1415926535897932384626433832795;
+    while (ang >= 0.0) {
+        ang -= 90.0;
         const float t = r.w;
         r.w = r.h;
         r.h = t;
-    } else if (n == 1) {
-        r.ang = -90.f;
     }
+    while (ang < -90.0) {
+        ang += 90.0;
+        const float t = r.w;
+        r.w = r.h;
+        r.h = t;
+    }
+    r.ang = static_cast<float>(ang);
     return r;
 }
 
@@ -769,7 +777,7 @@ __device__ RRect min_area_rect_pts(WarpMem& wm, int n, int lane) {
     warp_sort_keys(wm.keys, n, lane);
     RRect r{0.f, 0.f, 0.f, 0.f, 0.f};
     if (lane == 0) {
-        const int hn = convex_hull_cw(wm.keys, n, wm.stack, wm.hull);
+        const int hn = convex_hull_ccw(wm.keys, n, wm.stack, wm.hull);
         for (int i = 0; i < hn; ++i) {
             const short2 v = wm.verts[wm.hull[i]];
             wm.hp[i] = make_float2(static_cast<float>(v.x), static_cast<float>(v.y));
@@ -781,7 +789,7 @@ __device__ RRect min_area_rect_pts(WarpMem& wm, int n, int lane) {
 
 __global__ void __launch_bounds__(32)
 k_db_contour_boxes(const float* __restrict__ prob, int H, int W, const uint8_t* __restrict__ fg, const int* __restrict__ slot_root,
-                   const double* __restrict__ src_hw, double box_thresh, double unclip_ratio, float* __restrict__ slot_box,
+                   const double* __restrict__ src_hw, double box_thresh, double unclip_ratio, int variant, float* __restrict__ slot_box,
                    int* __restrict__ slot_valid, int* __restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int slot = blockIdx.x, n = blockIdx.y, lane = threadIdx.x;
@@ -925,6 +933,21 @@ k_db_contour_boxes(const float* __restrict__ prob, int H, int W, const uint8_t* 
     mini_box_order(pt, box);
     if (fminf(r.w, r.h) < 5.f) return;
     const double src_h = src_hw[n * 2], src_w = src_hw[n * 2 + 1];
+    if (variant == 1) {
+        // the in-tree DBNet back-end (db_net/ocr_detection_utils.py:190-205): box.astype(np.int32) FIRST (truncation), then
+        // np.clip(np.round(box / width * dest), 0, dest) in float64 stored back into the int32 box; corner order of
+        // get_mini_boxes is kept and filter_tag_det_res does not exist there
+        float* ob = slot_box + (static_cast<long long>(n) * kMaxSlots + slot) * 8;
+        for (int i = 0; i < 4; ++i) {
+            const double xi = static_cast<double>(static_cast<int>(box[i].x)), yi = static_cast<double>(static_cast<int>(box[i].y));
+            const double vx = fmin(fmax(rint(__dmul_rn(__ddiv_rn(xi, static_cast<double>(W)), src_w)), 0.0), src_w);
+            const double vy = fmin(fmax(rint(__dmul_rn(__ddiv_rn(yi, static_cast<double>(H)), src_h)), 0.0), src_h);
+            ob[2 * i] = static_cast<float>(static_cast<int>(vx));
+            ob[2 * i + 1] = static_cast<float>(static_cast<int>(vy));
+        }
+        slot_valid[n * kMaxSlots + slot] = 1;
+        return;
+    }
     float bx[4], by[4];
     for (int i = 0; i < 4; ++i) {
         // np.clip(np.round(box / width * dest_width), 0, dest_width): float32 division, float64 product, rint
@@ -1024,7 +1047,7 @@ int ensure_ws(Engine* e, DbWs* ws, int N, int H, int W) {
 }  // namespace
 
 int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* src_hw_host, float thresh, double box_thresh,
-             double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host) {
+             double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host, int variant) {
     if (N == 0) return 0;
     if (!prob || !src_hw_host || !boxes_out || !counts_out || N < 0 || H <= 0 || W <= 0)
         return set_err(e, DV_ERR_ARG, "db_boxes: bad arguments");
@@ -1036,10 +1059,10 @@ int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* sr
     if (it == e->aux.end()) it = e->aux.emplace("db_post", std::unique_ptr<Model>(new DbWs())).first;
     DbWs* ws = static_cast<DbWs*>(it->second.get());
     DV_TRY(ensure_ws(e, ws, N, H, W));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_db_contour_boxes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWarpSmem)));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     cudaStream_t s = e->stream;
     const size_t npx = static_cast<size_t>(N) * H * W;
@@ -1071,7 +1094,7 @@ int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* sr
     e->launch_end();
     e->launch_begin("k_db_contour_boxes", "db_post", 0.0, px * 1.0);
     k_db_contour_boxes<<<dim3(max_candidates, N), 32, kWarpSmem, s>>>(prob, H, W, ws->fg, ws->slot_root, ws->src_hw, box_thresh,
-                                                                      unclip_ratio, ws->slot_box, ws->slot_valid, ws->overflow);
+                                                                      unclip_ratio, variant, ws->slot_box, ws->slot_valid, ws->overflow);
     e->launch_end();
     e->launch_begin("k_db_compact", "db_post", 0.0, static_cast<double>(N) * kMaxSlots * 36);
     k_db_compact<<<N, 32, 0, s>>>(ws->slot_box, ws->slot_valid, max_candidates, boxes_out, counts_out);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <string>
@@ -117,6 +118,28 @@ struct Model {
     virtual ~Model() {}
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it is called, so the
+// "already opted in" flag of a launch site is kept per device (bit d = device d); setting the attribute twice from two
+// racing threads is harmless, the flag only has to be race-free.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool need(int dev) const { return ((done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0; }
+    void mark(int dev) { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
+// The dv_* entry points select the handle's device and restore the caller's current device on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 struct Engine {
     int device = 0;
     int num_sms = 148;
@@ -219,7 +242,7 @@ double cnv_flops(Engine* e);
 
 // db_post.cu
 int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* src_hw_host, float thresh, double box_thresh,
-             double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host);
+             double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host, int variant = 0);
 
 // lore_decode.cu
 // The four small Lore head maps as strided fp32 views: element (n, c, pixel) of map m = ptr[n*img + c*chan + pixel*pix].

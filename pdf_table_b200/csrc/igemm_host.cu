@@ -367,11 +367,11 @@ static IGemmKernel pick_kernel(int act, int out_f32, int res_f32, int argmax) {
 }
 
 int launch_conv(Engine* e, const ConvPlan& plan) {
-    static std::once_flag once;
-    static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [] {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
+        cudaError_t attr_rc = cudaSuccess;
         auto set = [&](IGemmKernel k) {
-            if (attr_rc == cudaSuccess)
+            if (attr_rc == cudaSuccess && k != nullptr)
                 attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         };
@@ -379,9 +379,10 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
             for (int f = 0; f < 2; ++f) set(pick_kernel(act, f, 0, 0));
         set(pick_kernel(ACT_NONE, 1, 1, 0));
         set(pick_kernel(ACT_NONE, 1, 0, 1));
-    });
-    if (attr_rc != cudaSuccess)
-        return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
+        if (attr_rc != cudaSuccess)
+            return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_tcgen05): %s", cudaGetErrorString(attr_rc));
+        attr_once.mark(e->device);
+    }
     IGemmKernel k = pick_kernel(plan.prm.act, plan.prm.out_f32, plan.res_f32, plan.prm.arg_out != nullptr);
     if (!k)
         return set_err(e, DV_ERR_ARG, "launch %s: unsupported epilogue (act %d, out_f32 %d, res_f32 %d, argmax %d)",
@@ -469,14 +470,14 @@ int plan_win_conv(Engine* e, const Tensor& in_padded, int stride, int KR, int Ho
 }
 
 int launch_win_conv(Engine* e, const WinConvPlan& plan, double algorithmic_flops) {
-    static std::once_flag once;
-    static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [] {
-        attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_win_tcgen05<ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
+        cudaError_t attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_win_tcgen05<ACT_RELU>), cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         if (attr_rc == cudaSuccess)
             attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_win_tcgen05<ACT_NONE>), cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
-    });
-    if (attr_rc != cudaSuccess) return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_win_tcgen05): %s", cudaGetErrorString(attr_rc));
+        if (attr_rc != cudaSuccess) return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(conv_win_tcgen05): %s", cudaGetErrorString(attr_rc));
+        attr_once.mark(e->device);
+    }
     e->launch_begin("conv_win_tcgen05", plan.name, algorithmic_flops > 0 ? algorithmic_flops : plan.flops, plan.bytes);
     if (plan.prm.act == ACT_RELU) conv_win_tcgen05<ACT_RELU><<<plan.grid, kWinThreads, plan.smem, e->stream>>>(plan.prm);
     else conv_win_tcgen05<ACT_NONE><<<plan.grid, kWinThreads, plan.smem, e->stream>>>(plan.prm);
@@ -494,11 +495,15 @@ bool mlp_fused_supported(int C) {
 
 template <int C>
 static int launch_mlp_c(Engine* e, const MlpPlan& plan) {
-    static cudaError_t attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(mlp_fused_tcgen05<C>),
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, MlpCfg<C>::SMEM);
-    if (attr_rc != cudaSuccess)
-        return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(mlp_fused_tcgen05<%d>, %d): %s", C, MlpCfg<C>::SMEM,
-                       cudaGetErrorString(attr_rc));
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
+        cudaError_t attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(mlp_fused_tcgen05<C>),
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, MlpCfg<C>::SMEM);
+        if (attr_rc != cudaSuccess)
+            return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(mlp_fused_tcgen05<%d>, %d): %s", C, MlpCfg<C>::SMEM,
+                           cudaGetErrorString(attr_rc));
+        attr_once.mark(e->device);
+    }
     e->launch_begin("mlp_fused_tcgen05", plan.name, plan.flops, plan.bytes);
     mlp_fused_tcgen05<C><<<plan.grid, kMlpThreads, MlpCfg<C>::SMEM, e->stream>>>(plan.prm);
     e->launch_end();

@@ -543,10 +543,10 @@ int lore_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const doub
     if (it == e->aux.end()) it = e->aux.emplace("lore_decode", std::unique_ptr<Model>(new LoreWs())).first;
     LoreWs* ws = static_cast<LoreWs*>(it->second.get());
     DV_TRY(ensure_ws(e, ws, N, K, MK));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_lore_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     cudaStream_t s = e->stream;
     DV_CUDA(e, cudaMemcpyAsync(ws->trans, trans_host, static_cast<size_t>(N) * 48, cudaMemcpyHostToDevice, s));
@@ -607,10 +607,10 @@ int centernet_decode(Engine* e, const LoreMaps& maps, int N, int H, int W, const
     if (it == e->aux.end()) it = e->aux.emplace("lore_decode", std::unique_ptr<Model>(new LoreWs())).first;
     LoreWs* ws = static_cast<LoreWs*>(it->second.get());
     DV_TRY(ensure_ws(e, ws, N, K, MK));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_lore_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     cudaStream_t s = e->stream;
     DV_CUDA(e, cudaMemcpyAsync(ws->trans, trans_host, static_cast<size_t>(N) * 48, cudaMemcpyHostToDevice, s));

@@ -284,10 +284,10 @@ int picodet_decode(Engine* e, const float* const* scores, const float* const* df
     cudaStream_t s = e->stream;
     DV_CUDA(e, cudaMemcpyAsync(ws->meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, s));
     DV_CUDA(e, cudaStreamSynchronize(s));  // `meta` is a stack-lifetime staging buffer
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_pico_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxAnchors * 8));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     int n2 = 1;
     while (n2 < max_hw) n2 <<= 1;

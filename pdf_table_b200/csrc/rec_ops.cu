@@ -485,10 +485,10 @@ template <int C, int H>
 int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, const float* lnw, const float* lnb,
               __half* out, const char* layer) {
     const size_t smem = static_cast<size_t>(H) * kTileW * C * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_dwconv7_ln<C, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     const double elems = static_cast<double>(B) * H * 75 * C;
     e->launch_begin("k_dwconv7_ln", layer, 2.0 * 49 * elems, elems * (4 + 2));
@@ -540,12 +540,12 @@ int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* l
 }
 
 int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer) {
-    static bool attr_done = false;
+    static DeviceOnce attr_once;
     static const bool use_mma = !(getenv("DV_ATTN_SIMT") && atoi(getenv("DV_ATTN_SIMT")));
-    if (!attr_done) {
+    if (attr_once.need(e->device)) {
         DV_CUDA(e, cudaFuncSetAttribute(k_attn75, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         DV_CUDA(e, cudaFuncSetAttribute(k_attn75_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAttnMmaSmem));
-        attr_done = true;
+        attr_once.mark(e->device);
     }
     e->launch_begin(use_mma ? "k_attn75_mma" : "k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
     if (use_mma) k_attn75_mma<<<B < e->num_sms ? B : e->num_sms, kAttnMmaThreads, 2 * kAttnMmaSmem, e->stream>>>(qkv, ctx, B);

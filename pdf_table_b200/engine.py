@@ -25,23 +25,55 @@ def _require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+class _StreamBoundLib:
+    """The ctypes library as seen by one Engine: every dv_* call first points the handle at torch's CURRENT stream of the
+    handle's device (dv_set_stream when it changed), so kernels are ordered with the torch copies / allocations issued
+    around them even when the caller switches streams with ``torch.cuda.stream(s)`` after constructing the engine."""
+
+    __slots__ = ("_lib", "_engine", "_cache")
+
+    def __init__(self, lib, engine):
+        self._lib, self._engine, self._cache = lib, engine, {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._lib, name)
+            eng = self._engine
+
+            def fn(*args, _raw=raw, _eng=eng):
+                _eng._bind_stream()
+                return _raw(*args)
+
+            self._cache[name] = fn
+        return fn
+
+
 class Engine:
     """One handle per (model kind, device).  Not thread-safe; distinct handles are independent."""
 
     def __init__(self, kind: str = "post", blob: Optional[bytes] = None, device: int = 0):
-        self._lib = _lib.load()
+        self._raw = _lib.load()
         self._h = C.c_void_p()
         self.kind = kind
         self.device = device
+        self._stream = None
         buf = (C.c_char * len(blob)).from_buffer_copy(blob) if blob else None
-        rc = self._lib.dv_create(kind.encode(), buf, len(blob) if blob else 0, device, C.byref(self._h))
+        rc = self._raw.dv_create(kind.encode(), buf, len(blob) if blob else 0, device, C.byref(self._h))
         check(rc, None, f"dv_create({kind})")
+        self._lib = _StreamBoundLib(self._raw, self)
         self.use_current_stream()
+
+    def _bind_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream and self._h.value:
+            check(self._raw.dv_set_stream(self._h, C.c_void_p(s)), self._h, "dv_set_stream")
+            self._stream = s
 
     # ------------------------------------------------------------------ lifetime / streams
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._lib.dv_destroy(self._h)
+            self._raw.dv_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -51,8 +83,9 @@ class Engine:
             pass
 
     def use_current_stream(self):
-        s = torch.cuda.current_stream(self.device).cuda_stream
-        check(self._lib.dv_set_stream(self._h, C.c_void_p(s)), self._h, "dv_set_stream")
+        """Bind the handle to torch's current stream of its device (also done implicitly before every call)."""
+        self._stream = None
+        self._bind_stream()
 
     def sync(self):
         check(self._lib.dv_sync(self._h), self._h, "dv_sync")
@@ -322,9 +355,13 @@ class Engine:
 
     # ------------------------------------------------------------------ post-processing kernels
     def db_boxes(self, prob: torch.Tensor, src_hw, thresh: float = 0.2, box_thresh: float = 0.6, unclip_ratio: float = 1.5,
-                 max_candidates: int = 1000, check_overflow: bool = False):
+                 max_candidates: int = 1000, check_overflow: bool = False, variant: str = "db_pp"):
         """prob fp32 [N,1,H,W] (cuda); src_hw = [(src_h, src_w)] per page -> (boxes fp32 [N,max_candidates,8], counts
-        int32 [N]) on the device.  Boxes follow the reference's order and corner convention."""
+        int32 [N]) on the device.  Boxes follow the reference's order and corner convention.  variant "db_pp" =
+        PPOcrDetectionPostProcessor (dv_db_boxes), "db" = the in-tree DBNet back-end's OCRDetectionPostProcessor
+        (dv_db_boxes_dbnet: int32 truncation before scaling, no clockwise re-ordering / size filter)."""
+        if variant not in ("db_pp", "db"):
+            raise ValueError(f"db_boxes variant {variant!r}")
         prob = _require_cuda(prob, torch.float32, "prob")
         n, c, h, w = prob.shape
         if c != 1:
@@ -333,9 +370,10 @@ class Engine:
         boxes = torch.empty((n, max_candidates, 8), dtype=torch.float32, device=prob.device)
         counts = torch.empty((n,), dtype=torch.int32, device=prob.device)
         ovf = C.c_int32(0)
-        check(self._lib.dv_db_boxes(self._h, _ptr(prob), n, h, w, src.ctypes.data_as(C.POINTER(C.c_double)), float(thresh),
-                                    float(box_thresh), float(unclip_ratio), int(max_candidates), _ptr(boxes), _ptr(counts),
-                                    C.byref(ovf) if check_overflow else None), self._h, "dv_db_boxes")
+        fn = self._lib.dv_db_boxes if variant == "db_pp" else self._lib.dv_db_boxes_dbnet
+        check(fn(self._h, _ptr(prob), n, h, w, src.ctypes.data_as(C.POINTER(C.c_double)), float(thresh),
+                 float(box_thresh), float(unclip_ratio), int(max_candidates), _ptr(boxes), _ptr(counts),
+                 C.byref(ovf) if check_overflow else None), self._h, "dv_db_boxes")
         if check_overflow:
             return boxes, counts, int(ovf.value)
         return boxes, counts

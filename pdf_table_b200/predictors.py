@@ -20,10 +20,11 @@ import numpy as np
 import torch
 
 from . import weights
+from ._lib import DocVisionError
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point", "det_resize_shape", "det_resize_for_test_device"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -269,6 +270,50 @@ class PPOcrRecPreProcessor:
         return out
 
 
+TRANSFER = {"h2d": 0, "d2h": 0}  # bytes moved by the predictors since the last reset (bench.py reports them per step)
+
+
+def _d2h_async(t: torch.Tensor) -> torch.Tensor:
+    """Device -> pinned host copy on the current stream without waiting for it (torch allocates the destination from its
+    caching pinned-memory pool); the caller synchronises an event recorded afterwards before reading."""
+    TRANSFER["d2h"] += t.numel() * t.element_size()
+    return t.to("cpu", non_blocking=True)
+
+
+def _d2h(t: torch.Tensor) -> np.ndarray:
+    TRANSFER["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
+def _h2d(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """Host tensor -> device on the current stream (asynchronous when the source is pinned memory)."""
+    TRANSFER["h2d"] += t.numel() * t.element_size()
+    return t.to(dev, non_blocking=True)
+
+
+def _to_device_u8(img, dev: torch.device) -> torch.Tensor:
+    """uint8 ndarray (pageable or a view of pinned memory) or tensor -> cuda tensor, asynchronously when the source is pinned."""
+    if isinstance(img, torch.Tensor):
+        return img if img.is_cuda else _h2d(img, dev)
+    return _h2d(torch.from_numpy(np.ascontiguousarray(img)), dev)
+
+
+def order_points_batch(quads: np.ndarray) -> np.ndarray:
+    """``order_point`` for n quads at once ([n,8] or [n,4,2] -> float32 [n,4,2]): the same numpy operations applied along a
+    batch axis (sum / divide for the centroid, arctan2, the default argsort per quad, the rotation when the first corner is
+    right of the centroid), so each row is bit-identical to the per-quad function (checked in tests/test_system_cpu.py)."""
+    arr = np.asarray(quads).reshape(-1, 4, 2)
+    if arr.shape[0] == 0:
+        return np.zeros((0, 4, 2), np.float32)
+    centroid = np.sum(arr, 1) / 4
+    theta = np.arctan2(arr[:, :, 1] - centroid[:, 1:2], arr[:, :, 0] - centroid[:, 0:1])
+    idx = np.argsort(theta, axis=1)
+    pts = np.take_along_axis(arr, idx[:, :, None], axis=1)
+    rot = pts[:, 0, 0] > centroid[:, 0]
+    pts[rot] = np.concatenate([pts[rot][:, 3:], pts[rot][:, :3]], axis=1)
+    return pts.astype("float32")
+
+
 def _load_state_dict(sd_or_path) -> Mapping[str, Any]:
     if isinstance(sd_or_path, (str, os.PathLike)):
         sd = torch.load(sd_or_path, map_location="cpu")
@@ -315,24 +360,48 @@ class BaseInferTask:
         return self._postprocess(self._run_model(self._preprocess(inputs), **kwargs), **kwargs)
 
 
+def dbnet_resize_shape(height: int, width: int, image_short_side: int = 736):
+    """OCRDetectionPreprocessor.resize (db_net/processor_ocr_dbnet.py:47-57): the short side becomes image_short_side, the
+    other one keeps the aspect ratio rounded UP to a multiple of 32.  Returns (new_height, new_width)."""
+    if height < width:
+        new_height = image_short_side
+        new_width = int(math.ceil(new_height / height * width / 32) * 32)
+    else:
+        new_width = image_short_side
+        new_height = int(math.ceil(new_width / width * height / 32) * 32)
+    return new_height, new_width
+
+
 class OcrDetectionTask(BaseInferTask):
-    """OcrDetectionTask (ocr_pdf/ocr_detection_task.py:30-141).  model="db" / "db_pp" select the pre/post-processing
-    constants of the two reference back-ends; the network is the in-tree DBNet-R18 (db_net/dbnet.py:715) either way
-    (the PP-OCR det ONNX graph is not part of the reference repository).
+    """OcrDetectionTask (ocr_pdf/ocr_detection_task.py:30-141).  The network is the in-tree DBNet-R18 (db_net/dbnet.py:715)
+    for both models (the PP-OCR det ONNX graph is not part of the reference repository); ``model`` selects the
+    pre / post-processing of the reference back-end:
+
+    * ``"db_pp"`` -- PPOcrDetectionPreprocessor / PPOcrDetectionPostProcessor (db_pp/processor_ocr_db_pp.py): DetResizeForTest
+      (max side 960, multiples of 32), ``(x / 255 - mean) / std`` with the ImageNet statistics, box_thresh 0.6, boxes re-ordered
+      clockwise, clipped and size-filtered (filter_tag_det_res).  Running DBNet-R18 weights under it is a stand-in for the
+      PP-OCRv4 detector, not something the reference does.
+    * ``"db"`` -- OCRDetectionPreprocessor / OCRDetectionPostProcessor (db_net/processor_ocr_dbnet.py:31-127): short side 736 with
+      the other side rounded up to a multiple of 32, ``(x - [123.68, 116.78, 103.94]) / 255`` on the BGR-flipped image, box
+      score >= 0.3, the mini box truncated to int32 then ``round(x / width * dest)``, no re-ordering or size filter
+      (db_net/ocr_detection_utils.py:168-205).  This is the pipeline a real DBNet-R18 checkpoint was trained for.
+
     Returns list[np.ndarray [n, 8]] like the reference (:135-141)."""
 
     MEAN = (0.485, 0.456, 0.406)
     STD = (0.229, 0.224, 0.225)
+    DB_MEAN = (123.68, 116.78, 103.94)  # OCRDetectionPreprocessor.normalize (db_net/processor_ocr_dbnet.py:59-62)
 
     def __init__(self, task: str = "ocr_detection", model: str = "db_pp", backbone: str = "resnet18", thresh: float = 0.2,
-                 state_dict=None, box_thresh: float = 0.6, unclip_ratio: float = 1.5, max_candidates: int = 1000,
-                 limit_side_len: int = 960, limit_type: str = "max", **kwargs):
+                 state_dict=None, box_thresh: Optional[float] = None, unclip_ratio: float = 1.5, max_candidates: int = 1000,
+                 limit_side_len: int = 960, limit_type: str = "max", image_short_side: int = 736, **kwargs):
         if model not in ("db", "db_pp"):
             raise RuntimeError(f"model {model} not support")  # ocr_detection_task.py:58
         if state_dict is None:
             raise RuntimeError("OcrDetectionTask(predictor_type='b200') needs state_dict= (a DBModel state_dict or a path)")
-        self.thresh, self.box_thresh, self.unclip_ratio, self.max_candidates = thresh, box_thresh, unclip_ratio, max_candidates
-        self.limit_side_len, self.limit_type = limit_side_len, limit_type
+        self.thresh, self.unclip_ratio, self.max_candidates = thresh, unclip_ratio, max_candidates
+        self.box_thresh = box_thresh if box_thresh is not None else (0.3 if model == "db" else 0.6)
+        self.limit_side_len, self.limit_type, self.image_short_side = limit_side_len, limit_type, image_short_side
         self._sd = _load_state_dict(state_dict)
         super().__init__(task=task, model=model, **kwargs)
 
@@ -340,52 +409,117 @@ class OcrDetectionTask(BaseInferTask):
         self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd), device=self.device)
         self._sd = None
 
+    def _norm(self):
+        """(mean, std, scale) of the fused normalisation kernel: (x * scale - mean) / std in float32."""
+        if self.model == "db":
+            return self.DB_MEAN, (255.0, 255.0, 255.0), 1.0
+        return self.MEAN, self.STD, 1.0 / 255.0
+
+    def _resize_host(self, img: np.ndarray):
+        import cv2
+
+        if self.model == "db":
+            new_h, new_w = dbnet_resize_shape(img.shape[0], img.shape[1], self.image_short_side)
+            return cv2.resize(img, (new_w, new_h)), [new_h / float(img.shape[0]), new_w / float(img.shape[1])]
+        return det_resize_for_test(img, self.limit_side_len, self.limit_type)
+
+    def _resize_device(self, page: torch.Tensor):
+        if self.model == "db":
+            new_h, new_w = dbnet_resize_shape(int(page.shape[0]), int(page.shape[1]), self.image_short_side)
+            res = page if (new_h, new_w) == tuple(page.shape[:2]) else self.predictor.resize_pages_u8(page.unsqueeze(0), new_w, new_h)[0]
+            return res, [new_h / float(page.shape[0]), new_w / float(page.shape[1])]
+        return det_resize_for_test_device(self.predictor, page, self.limit_side_len, self.limit_type)
+
     def _preprocess(self, inputs) -> Dict[str, Any]:
-        """PPOcrDetectionPreprocessor.__call__ (db_pp/processor_ocr_db_pp.py:103-145) up to the uint8 resize; the
-        channel flip, NormalizeImage and ToCHWImage run fused on the GPU (dv_dbnet_forward_u8)."""
-        items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        """PPOcrDetectionPreprocessor.__call__ (db_pp/processor_ocr_db_pp.py:103-145) / OCRDetectionPreprocessor.__call__
+        (db_net/processor_ocr_dbnet.py:64-99) up to the uint8 resize; the channel flip, the normalisation and the CHW layout
+        run fused on the GPU (dv_dbnet_forward_u8).  cv2.resize acts per channel, so resizing before the flip gives the same
+        pixels as the reference's flip-then-resize."""
+        if isinstance(inputs, np.ndarray) and inputs.ndim == 4:
+            items = list(inputs)
+        else:
+            items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
         pages, shapes, orgs = [], [], []
         for it in items:
             if isinstance(it, torch.Tensor):  # a page that is already on the device (uint8 HWC): resized there, nothing goes up
                 if not it.is_cuda or it.dtype != torch.uint8 or it.dim() != 3:
                     raise TypeError("tensor inputs must be uint8 HWC cuda tensors")
                 src_h, src_w = int(it.shape[0]), int(it.shape[1])
-                res, (ratio_h, ratio_w) = det_resize_for_test_device(self.predictor, it, self.limit_side_len, self.limit_type)
+                res, (ratio_h, ratio_w) = self._resize_device(it)
                 pages.append(res.contiguous())
                 shapes.append(np.array([src_h, src_w, ratio_h, ratio_w]))
                 orgs.append(tuple(it.shape))
                 continue
             img = _read_image(it)
             src_h, src_w = img.shape[:2]
-            res, (ratio_h, ratio_w) = det_resize_for_test(img, self.limit_side_len, self.limit_type)
+            res, (ratio_h, ratio_w) = self._resize_host(img)
             pages.append(np.ascontiguousarray(res))
             shapes.append(np.array([src_h, src_w, ratio_h, ratio_w]))
             orgs.append(img.shape)
         return {"pages": pages, "shape_list": shapes, "org_shape": orgs, "inputs": inputs}
 
-    def _run_model(self, inputs, **kwargs):
+    def _run_model(self, inputs, prob_override=None, **kwargs):
+        """Launches DBNet + the whole box post-process per group of equally sized pages and starts the device -> host copies;
+        nothing here waits for the GPU except the overflow read-back of dv_db_boxes.  ``prob_override`` (bench / tests with
+        seeded random weights, whose probability map is texture noise): callable(prob [n,1,h,w] cuda, page indices) ->
+        the map the box stage should read instead; the network still runs."""
         dev = torch.device("cuda", self.device)
         groups: Dict[tuple, List[int]] = {}
         for i, p in enumerate(inputs["pages"]):
             groups.setdefault((int(p.shape[0]), int(p.shape[1])), []).append(i)
-        boxes_out: List[Optional[np.ndarray]] = [None] * len(inputs["pages"])
+        mean, std, scale = self._norm()
+        pending = []
         for (h, w), idx in groups.items():  # one launch sequence per distinct resized shape
             members = [inputs["pages"][i] for i in idx]
-            if any(isinstance(m, torch.Tensor) for m in members):  # pages resized on the device (mixed groups: the others go up one by one)
-                batch = torch.stack([m if isinstance(m, torch.Tensor) else torch.from_numpy(m).to(dev) for m in members])
+            if len(members) > 1 and all(isinstance(m, torch.Tensor) for m in members) and _is_batch_view(members):
+                batch = _batch_of(members)
+            elif any(isinstance(m, torch.Tensor) for m in members):  # pages resized on the device (mixed groups: the others go up one by one)
+                batch = torch.stack([m if isinstance(m, torch.Tensor) else _to_device_u8(m, dev) for m in members])
             else:
-                batch = torch.from_numpy(np.stack(members)).to(dev, non_blocking=True)
-            prob = self.predictor.dbnet_forward_u8(batch, self.MEAN, self.STD, 1.0 / 255.0, flip=True)
+                batch = torch.empty((len(members), h, w, 3), dtype=torch.uint8, device=dev)
+                for j, m in enumerate(members):
+                    TRANSFER["h2d"] += m.nbytes
+                    batch[j].copy_(torch.from_numpy(m), non_blocking=True)
+            prob = self.predictor.dbnet_forward_u8(batch, mean, std, scale, flip=True)
+            if prob_override is not None:
+                prob = prob_override(prob, idx)
             src = [(inputs["shape_list"][i][0], inputs["shape_list"][i][1]) for i in idx]
-            boxes, counts = self.predictor.db_boxes(prob, src, self.thresh, self.box_thresh, self.unclip_ratio, self.max_candidates)
-            boxes, counts = boxes.cpu().numpy(), counts.cpu().numpy()
-            for j, i in enumerate(idx):
-                boxes_out[i] = boxes[j, : counts[j]].copy()
-        inputs["det_polygons"] = boxes_out
+            boxes, counts, overflow = self.predictor.db_boxes(prob, src, self.thresh, self.box_thresh, self.unclip_ratio, self.max_candidates,
+                                                              check_overflow=True, variant=self.model)
+            if overflow:
+                import warnings
+
+                warnings.warn(f"OcrDetectionTask: {overflow} contour(s) with more than 2048 vertices were skipped by dv_db_boxes "
+                              "(the reference's cv2 path has no such limit)", RuntimeWarning)
+            pending.append((idx, boxes, counts, _d2h_async(boxes), _d2h_async(counts)))
+        ev = torch.cuda.Event()
+        ev.record()
+        inputs["pending"], inputs["event"] = pending, ev
         return inputs
 
     def _postprocess(self, inputs, **kwargs) -> List[np.ndarray]:
-        return inputs["det_polygons"]
+        inputs["event"].synchronize()
+        boxes_out: List[Optional[np.ndarray]] = [None] * len(inputs["pages"])
+        for idx, _, _, boxes_h, counts_h in inputs["pending"]:
+            boxes, counts = boxes_h.numpy(), counts_h.numpy()
+            for j, i in enumerate(idx):
+                b = boxes[j, : counts[j]].copy()
+                boxes_out[i] = b.astype(np.int64) if self.model == "db" else b  # np.array(lists of python ints) there (:126)
+        inputs["det_polygons"] = boxes_out
+        return boxes_out
+
+
+def _is_batch_view(members) -> bool:
+    """True when the cuda tensors are consecutive slices of one contiguous batch (what ``list(batch)`` / ``batch[i]`` give)."""
+    first = members[0]
+    step = first.numel() * first.element_size()
+    return all(m.is_contiguous() and m.shape == first.shape and m.data_ptr() == first.data_ptr() + k * step for k, m in enumerate(members)) \
+        and first._base is not None and all(m._base is first._base for m in members)
+
+
+def _batch_of(members) -> torch.Tensor:
+    first = members[0]
+    return torch.as_strided(first, (len(members),) + tuple(first.shape), (first.numel(),) + tuple(first.stride()))
 
 
 class OcrRecognitionTask(BaseInferTask):
@@ -417,46 +551,114 @@ class OcrRecognitionTask(BaseInferTask):
                 img = np.stack([img] * 3, -1)
             crops.append(keepratio_resize(img))
         wmax = max(c.shape[1] for c in crops)
-        batch = np.zeros((len(crops), 32, wmax, 3), np.uint8)  # zero padding of the reference's mask (:57-61)
+        # zero padding of the reference's mask (:57-61), staged in pinned memory so that the upload does not block the host
+        stage = torch.zeros((len(crops), 32, wmax, 3), dtype=torch.uint8, pin_memory=True)
+        batch = stage.numpy()
         for i, c in enumerate(crops):
             batch[i, :, : c.shape[1]] = c
-        return {"crops": batch, "inputs": inputs}
+        return {"crops": stage, "inputs": inputs}
+
+    CALL_CHUNK = 512  # crops per pre-process / launch round of __call__
+
+    def __call__(self, inputs, **kwargs):
+        """post(run(pre(x))) like the reference; a long list is walked in chunks of CALL_CHUNK crops so that the host
+        pre-processing (cv2.resize, padding) of chunk k+1 overlaps the device work of chunk k (nothing waits for the GPU
+        before the final _postprocess)."""
+        items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        if len(items) <= self.CALL_CHUNK:
+            return self._postprocess(self._run_model(self._preprocess(inputs), **kwargs), **kwargs)
+        runs = [self._run_model(self._preprocess(list(items[i:i + self.CALL_CHUNK])), **kwargs) for i in range(0, len(items), self.CALL_CHUNK)]
+        out: List[str] = []
+        for r in runs:
+            out += self._postprocess(r, **kwargs)
+        return out
 
     def _run_model(self, inputs, **kwargs):
         dev = torch.device("cuda", self.device)
-        ids = self.predictor.convnextvit_forward_u8(torch.from_numpy(inputs["crops"]).to(dev, non_blocking=True))
+        crops = inputs["crops"]
+        ids = self.predictor.convnextvit_forward_u8(_h2d(crops if isinstance(crops, torch.Tensor) else torch.from_numpy(crops), dev))
         out, ln, _ = self.post.ctc_collapse(ids)
-        inputs["ids"], inputs["len"] = out.cpu().numpy(), ln.cpu().numpy()
+        inputs["ids_dev"], inputs["len_dev"] = out, ln
+        inputs["ids"], inputs["len"] = _d2h_async(out), _d2h_async(ln)
+        inputs["event"] = torch.cuda.Event()
+        inputs["event"].record()
         return inputs
 
     def recognize_page(self, page, positions) -> List[Optional[str]]:
         """All detected quads of one page: what the reference's orchestrator does per box (OcrCommonUtils.crop_image, then
         this task on the crop -- ocr_pdf/ocr_system_task.py:300-313), with the crops cut and resized on the device
-        (``crops_for_recognition``) so that only the page goes up and only token ids come back.  page: uint8 HWC ndarray or
+        (``dv_crop_quads_for_rec``) so that only the page goes up and only token ids come back.  page: uint8 HWC ndarray or
         cuda tensor.  Returns one string per quad (None where the reference's crop would be empty)."""
+        return self.recognize_pages([page], [positions])[0]
+
+    def launch_pages(self, pages, positions_per_page) -> Dict[str, Any]:
+        """The asynchronous half of ``recognize_pages``: uploads what is not resident, enqueues crop + recognise + collapse for
+        the quads of ALL pages as one batch and starts the device -> host copies; returns the pending record for
+        ``collect_pages``.  pages: uint8 cuda tensor [P,H,W,3], or a list of equally sized HWC ndarrays / cuda tensors."""
         dev = torch.device("cuda", self.device)
-        page_dev = page if isinstance(page, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(page)).to(dev)
-        out: List[Optional[str]] = [None] * len(positions)
-        if len(positions) == 0:
-            return out
-        quads = torch.from_numpy(np.stack([np.asarray(p, np.float32).reshape(4, 2) for p in positions])).to(dev)
-        # geometry, homography, warp and keep-ratio resize all on the device (dv_crop_quads_for_rec); width 0 = skipped quad
-        crops, widths, _, _ = self.post.crop_quads_for_rec(page_dev, quads)
+        if isinstance(pages, torch.Tensor) and pages.dim() == 4:
+            batch = pages
+        else:
+            members = [_to_device_u8(p, dev) for p in pages]
+            if len({tuple(m.shape) for m in members}) > 1:
+                raise ValueError("recognize_pages: pages of one call must have the same shape (call once per shape)")
+            batch = _batch_of(members) if len(members) > 1 and _is_batch_view(members) else torch.stack(members)
+        n_per = [len(p) for p in positions_per_page]
+        if len(n_per) != int(batch.shape[0]):
+            raise ValueError("one list of quads per page")
+        rec = {"n_per": n_per, "event": None}
+        total = sum(n_per)
+        if total == 0:
+            return rec
+        quads = np.concatenate([np.asarray(p, np.float32).reshape(-1, 4, 2) for p in positions_per_page if len(p)])
+        page_idx = np.repeat(np.arange(len(n_per), dtype=np.int32), n_per)
+        q_dev = _h2d(torch.from_numpy(quads), dev)
+        pi_dev = _h2d(torch.from_numpy(page_idx), dev)
+        # geometry, homography, warp and keep-ratio resize all on the device; width 0 = skipped quad
+        crops, widths, _, _ = self.post.crop_quads_for_rec(batch, q_dev, pi_dev)
         ids = self.predictor.convnextvit_forward_u8(crops)
         tok, ln, _ = self.post.ctc_collapse(ids)
-        texts = self._postprocess({"ids": tok.cpu().numpy(), "len": ln.cpu().numpy()})
-        for k, (t, w) in enumerate(zip(texts, widths.cpu().numpy())):
-            out[k] = t if w > 0 else None
+        rec.update(ids_dev=tok, len_dev=ln, widths_dev=widths, ids=_d2h_async(tok), len=_d2h_async(ln), widths=_d2h_async(widths))
+        rec["event"] = torch.cuda.Event()
+        rec["event"].record()
+        return rec
+
+    def collect_pages(self, rec) -> List[List[Optional[str]]]:
+        """Waits for ``launch_pages``' copies and maps ids to text: one list of strings per page (None = empty crop)."""
+        out: List[List[Optional[str]]] = []
+        if rec["event"] is None:
+            return [[] for _ in rec["n_per"]]
+        rec["event"].synchronize()
+        texts = self._postprocess({"ids": rec["ids"].numpy(), "len": rec["len"].numpy()})
+        widths = rec["widths"].numpy()
+        o = 0
+        for n in rec["n_per"]:
+            out.append([t if w > 0 else None for t, w in zip(texts[o:o + n], widths[o:o + n])])
+            o += n
         return out
 
+    def recognize_pages(self, pages, positions_per_page) -> List[List[Optional[str]]]:
+        """``recognize_page`` for a batch of equally sized pages: every quad of every page goes through ONE crop launch and one
+        recogniser pass (the page index of each quad rides along), instead of one pass per page."""
+        return self.collect_pages(self.launch_pages(pages, positions_per_page))
+
     def _postprocess(self, inputs, **kwargs) -> List[str]:
+        if inputs.get("event") is not None:
+            inputs["event"].synchronize()
+        ids = inputs["ids"].numpy() if isinstance(inputs["ids"], torch.Tensor) else inputs["ids"]
+        lens = inputs["len"].numpy() if isinstance(inputs["len"], torch.Tensor) else inputs["len"]
         res = []
-        for row, n in zip(inputs["ids"], inputs["len"]):
+        for row, n in zip(ids, lens):
             seq = row[:n]
             if self.label_mapping is None:
                 res.append(" ".join(str(int(v)) for v in seq))
-            else:
-                res.append("".join(self.label_mapping[int(v)] for v in seq))  # KeyError on id 1, as the reference
+                continue
+            try:
+                res.append("".join(self.label_mapping[int(v)] for v in seq))
+            except KeyError:
+                # the reference's post-processor raises KeyError here (label id 1 / an id outside the vocab file) and its
+                # orchestrator catches the exception PER CROP and keeps "" (ocr_system_task.py:309-320): same outcome, per row
+                res.append("")
         return res
 
 
@@ -551,7 +753,7 @@ class OcrTableStructureTask(BaseInferTask):
     K, MK = 3000, 5000  # process_detect_output (lore/lineless_table_process.py:593)
 
     def __init__(self, task: str = "ocr_table_structure", model: str = "Lore", task_type: str = "wtw", state_dict=None,
-                 table_structure_merge: bool = False, max_cells_per_image: int = 1024, **kwargs):
+                 table_structure_merge: bool = False, max_cells_per_image: int = 3000, **kwargs):
         if model not in ("Lore", "CenterNet"):
             raise RuntimeError(f"model {model} not support")
         if model == "Lore" and task_type != "wtw":
@@ -562,6 +764,8 @@ class OcrTableStructureTask(BaseInferTask):
             raise RuntimeError("OcrTableStructureTask(model='CenterNet', predictor_type='b200') needs state_dict= (a DLASeg state_dict or a path)")
         self.task_type, self.table_structure_merge = task_type, table_structure_merge
         self.resolution, self.vis_thresh, self.wiz_rev = (1024, 1024), 0.2, True  # LoreConfig wtw (configuration_lore.py:86-100)
+        # capacity of the cell-feature / processor buffers per image; the decode keeps at most K = 3000 cells per image
+        # (process_detect_output), so the default can never overflow.  A smaller cap saves workspace; exceeding it raises.
         self.max_cells_per_image = max_cells_per_image
         self._sd = (_load_state_dict(state_dict[0]), _load_state_dict(state_dict[1])) if model == "Lore" else _load_state_dict(state_dict)
         super().__init__(task=task, model=model, **kwargs)
@@ -576,7 +780,12 @@ class OcrTableStructureTask(BaseInferTask):
         self._sd = None
 
     def _preprocess(self, inputs, **kwargs) -> Dict[str, Any]:
+        """TableLorePreProcessor.process (lore/processer_lore.py:66-109): the raw image goes up and the centre-anchored
+        cv2.warpAffine runs on the device (dv_warp_affine_u8, bit-exact against cv2 -- tests/test_gpu_crop.py); the
+        normalisation is fused into the network's first kernel.  host_warp=True (constructor kwarg) keeps the cv2 call on
+        the host as the reference does."""
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        dev = torch.device("cuda", self.device)
         images, metas, cs = [], [], []
         for it in items:
             img = _read_image(it)
@@ -584,18 +793,22 @@ class OcrTableStructureTask(BaseInferTask):
                 img = np.stack([img] * 3, -1)
             if not isinstance(it, np.ndarray):
                 img = img[:, :, ::-1]  # path / PIL inputs reach the network as BGR, ndarrays unchanged (processer_lore.py:51-60, 146)
-            warped, meta = lore_preprocess(img, self.resolution)
+            if self.kwargs.get("host_warp", False):
+                warped, meta = lore_preprocess(img, self.resolution)
+                warped = _to_device_u8(warped, dev)
+            else:
+                warped, meta = lore_preprocess_device(self.post, _to_device_u8(img, dev), self.resolution)
             images.append(warped)
             metas.append(meta)
             h, w = img.shape[:2]
             cs.append((np.array([w / 2.0, h / 2.0], dtype=np.float32), max(h, w) * 1.0))
-        return {"images": np.stack(images), "meta": np.stack(metas), "cs": cs, "inputs": list(items)}
+        return {"images": torch.stack(images), "meta": np.stack(metas), "cs": cs, "inputs": list(items)}
 
     def _images_on_device(self, images) -> torch.Tensor:
         """The warped uint8 batch: uploaded when the host pre-process made it, used in place when recognize_tables did."""
-        if isinstance(images, torch.Tensor):
+        if isinstance(images, torch.Tensor) and images.is_cuda:
             return images
-        return torch.from_numpy(images).to(torch.device("cuda", self.device), non_blocking=True)
+        return _h2d(images if isinstance(images, torch.Tensor) else torch.from_numpy(images), torch.device("cuda", self.device))
 
     def recognize_tables(self, pages, layout_tables) -> List[list]:
         """The table loop of the reference's orchestrator (ocr_pdf/ocr_system_task.py:184-198) for pages that are already on
@@ -608,13 +821,17 @@ class OcrTableStructureTask(BaseInferTask):
         layout_tables: dicts with "bbox" = [x1,y1,x2,y2] (and "page" when pages is a batch), e.g. the table rows of
         OcrLayoutTask's result.  Returns [[bbox, result], ...] in input order like ``outputs`` there (:189-198), result being
         what ``self(crop)[0]`` returns for that crop (its "inputs" is the bbox)."""
+        return self.collect_tables(self.launch_tables(pages, layout_tables))
+
+    def launch_tables(self, pages, layout_tables) -> Optional[Dict[str, Any]]:
+        """The asynchronous half of ``recognize_tables`` (crop + warp + network + decode + processor enqueued, copies started)."""
         dev = torch.device("cuda", self.device)
-        t = pages if isinstance(pages, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pages)).to(dev)
+        t = pages if isinstance(pages, torch.Tensor) else _h2d(torch.from_numpy(np.ascontiguousarray(pages)), dev)
         if t.dim() == 3:
             t = t.unsqueeze(0)
         n_pages, height, width = int(t.shape[0]), int(t.shape[1]), int(t.shape[2])
         if len(layout_tables) == 0:
-            return []
+            return None
         inp_h, inp_w = self.resolution
         rects, minv, metas, cs = [], [], [], []
         for tb in layout_tables:
@@ -630,8 +847,13 @@ class OcrTableStructureTask(BaseInferTask):
             cs.append((c, sc))
         warped = self.post.crop_tables_for_tsr(t, np.array(rects, np.int32), np.stack(minv), inp_w, inp_h)
         items = [tb["bbox"] for tb in layout_tables]
-        res = self._postprocess(self._run_model({"images": warped, "meta": np.stack(metas), "cs": cs, "inputs": items}))
-        return [[bbox, r] for bbox, r in zip(items, res)]
+        return self._run_model({"images": warped, "meta": np.stack(metas), "cs": cs, "inputs": items})
+
+    def collect_tables(self, pending) -> List[list]:
+        if pending is None:
+            return []
+        res = self._postprocess(pending)
+        return [[bbox, r] for bbox, r in zip(pending["inputs"], res)]
 
     def _run_centernet(self, inputs):
         """OCRTableCenterNetPreProcessor keeps the float centre / scale in its meta (center_net/processer_centernet.py:108-139);
@@ -639,11 +861,15 @@ class OcrTableStructureTask(BaseInferTask):
         inv = np.stack([lore_affine(c, s, self.resolution[1] // 4, self.resolution[0] // 4, inv=True) for c, s in inputs["cs"]])
         maps = self.predictor.lore_detect_forward_u8(self._images_on_device(inputs["images"]))
         polygons, counts = self.post.centernet_decode(maps, None, None, None, inv)
-        polygons, counts = polygons.cpu().numpy(), counts.cpu().numpy()
-        inputs["results"] = [{"polygons": polygons[i, : counts[i]].copy()} for i in range(len(counts))]
+        inputs["dev"] = {"polygons": polygons, "counts": counts}
+        inputs["host"] = {"polygons": _d2h_async(polygons), "counts": _d2h_async(counts)}
+        inputs["event"] = torch.cuda.Event()
+        inputs["event"].record()
         return inputs
 
     def _run_model(self, inputs, **kwargs):
+        """Enqueues detector -> decode -> cell features -> processor on the current stream (no host round trip between them:
+        the row counts stay on the device) and starts the device -> host copies of the fixed-capacity result buffers."""
         if self.model == "CenterNet":
             return self._run_centernet(inputs)
         n = len(inputs["images"])
@@ -651,21 +877,38 @@ class OcrTableStructureTask(BaseInferTask):
         inv = np.stack([lore_affine([np.float32(m[0]), np.float32(m[1])], np.float32(m[2]), int(m[6]), int(m[5]), inv=True) for m in metas])
         maps = self.predictor.lore_detect_forward_u8(self._images_on_device(inputs["images"]))
         dec = self.post.lore_decode(maps, None, None, None, inv, K=self.K, MK=self.MK, wiz_rev=self.wiz_rev, vis_thresh=self.vis_thresh)
-        feat, offsets = self.predictor.lore_cell_features(dec, max_rows=n * self.max_cells_per_image, check_overflow=True)
+        cap = n * min(self.max_cells_per_image, self.K)
+        feat, offsets = self.predictor.lore_cell_features(dec, max_rows=cap)
         _, stacked = self.processor.lore_process_forward(feat, offsets)
-        counts = dec["counts"].cpu().numpy()
-        offs = offsets.cpu().numpy()
-        kmax = int(counts.max()) if n else 0
-        polygons = dec["polygons"][:, :max(kmax, 1)].cpu().numpy()
-        logits = stacked[: int(offs[-1])].cpu().numpy()
-        inputs["results"] = [{"pred_boxes": polygons[i, : counts[i]], "logits": logits[offs[i]: offs[i + 1]]} for i in range(n)]
+        inputs["dev"] = {"polygons": dec["polygons"], "counts": dec["counts"], "offsets": offsets, "logi": stacked}
+        inputs["cap"] = cap
+        inputs["host"] = {"counts": _d2h_async(dec["counts"]), "offsets": _d2h_async(offsets)}
+        inputs["event"] = torch.cuda.Event()
+        inputs["event"].record()
         return inputs
+
+    def _collect_lore(self, inputs):
+        """Second half of the Lore run: the counts are on the host now, so only the used part of the polygon / coordinate
+        buffers is copied back."""
+        inputs["event"].synchronize()
+        counts = inputs["host"]["counts"].numpy()
+        offs = inputs["host"]["offsets"].numpy()
+        n = len(counts)
+        if n and int(counts.sum()) > inputs["cap"]:
+            raise DocVisionError(f"lore: {int(counts.sum())} cells exceed the buffer capacity {inputs['cap']} "
+                                 f"(max_cells_per_image={self.max_cells_per_image}); construct the task with a larger cap")
+        kmax = int(counts.max()) if n else 0
+        polygons = _d2h(inputs["dev"]["polygons"][:, :max(kmax, 1)])
+        logits = _d2h(inputs["dev"]["logi"][: int(offs[-1])])
+        return [{"pred_boxes": polygons[i, : counts[i]], "logits": logits[offs[i]: offs[i + 1]]} for i in range(n)]
 
     def _postprocess(self, inputs, **kwargs) -> List[Dict[str, Any]]:
         if self.model == "CenterNet":  # {"polygons": np.array(box_list), ...inputs} (processer_centernet.py:198-203)
-            return [{"polygons": res["polygons"], "inputs": item} for item, res in zip(inputs["inputs"], inputs["results"])]
+            inputs["event"].synchronize()
+            polygons, counts = inputs["host"]["polygons"].numpy(), inputs["host"]["counts"].numpy()
+            return [{"polygons": polygons[i, : counts[i]].copy(), "inputs": item} for i, item in enumerate(inputs["inputs"])]
         out = []
-        for item, res in zip(inputs["inputs"], inputs["results"]):
+        for item, res in zip(inputs["inputs"], self._collect_lore(inputs)):
             boxes, logi = res["pred_boxes"], res["logits"]
             if len(boxes) == 0:  # LoreModel.forward (lore/modeling_lore.py:171-173)
                 boxes, logi = np.zeros((1, 8), np.float32), np.zeros((1, 4), np.float32)
@@ -717,6 +960,12 @@ class OcrLayoutTask(BaseInferTask):
 
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
         imgs, org, sf = [], [], []
+        if len(items) > 1 and all(isinstance(it, torch.Tensor) and it.is_cuda and it.dtype == torch.uint8 and it.dim() == 3 for it in items) \
+                and _is_batch_view(list(items)):  # the pages of one resident batch: ONE resize launch for all of them
+            h, w = int(items[0].shape[0]), int(items[0].shape[1])
+            images = self.post.resize_pages_u8(_batch_of(list(items)), self.IMG_W, self.IMG_H)
+            return {"images": images, "org_shape": [(h, w)] * len(items), "scale_factor": [(float(self.IMG_H) / h, float(self.IMG_W) / w)] * len(items),
+                    "inputs": list(items)}
         for it in items:
             if isinstance(it, torch.Tensor):  # a page that is already on the device (uint8 HWC): resized there
                 if not it.is_cuda or it.dtype != torch.uint8 or it.dim() != 3:
@@ -740,16 +989,19 @@ class OcrLayoutTask(BaseInferTask):
         dev = torch.device("cuda", self.device)
         images = inputs["images"]
         if not isinstance(images, torch.Tensor):
-            images = torch.from_numpy(images).to(dev, non_blocking=True)
+            images = _h2d(torch.from_numpy(images), dev)
         scores, dfl = self.predictor.picodet_forward_u8(images, flip=True)
         boxes, counts = self.post.picodet_decode(scores, dfl, inputs["org_shape"], inputs["scale_factor"], (self.IMG_H, self.IMG_W),
                                                  score_threshold=self.score_threshold, nms_threshold=self.nms_threshold,
                                                  nms_top_k=self.nms_top_k, keep_top_k=self.keep_top_k)
-        inputs["boxes"], inputs["counts"] = boxes.cpu().numpy(), counts.cpu().numpy()
+        inputs["boxes"], inputs["counts"] = _d2h_async(boxes), _d2h_async(counts)
+        inputs["event"] = torch.cuda.Event()
+        inputs["event"].record()
         return inputs
 
     def _postprocess(self, inputs, **kwargs) -> List[List[Dict[str, Any]]]:
+        inputs["event"].synchronize()
         out = []
-        for rows, n in zip(inputs["boxes"], inputs["counts"]):
+        for rows, n in zip(inputs["boxes"].numpy(), inputs["counts"].numpy()):
             out.append([{"bbox": r[2:].copy(), "label": self.id2label[int(r[0])], "score": r[1], "category_id": int(r[0])} for r in rows[:n]])
         return out

@@ -69,12 +69,13 @@ def pack_results(res: Dict[str, torch.Tensor], max_pages: int, max_crops: int, m
     return out
 
 
-def unpack_results(buf: torch.Tensor, like: Dict[str, torch.Tensor], max_pages: int, max_crops: int, max_tables: int = 0) -> Dict[str, torch.Tensor]:
+def unpack_results(buf: torch.Tensor, like: Dict[str, torch.Tensor], max_pages: int, max_crops: int, max_tables: int = 0,
+                   counts: Sequence[int] = ()) -> Dict[str, torch.Tensor]:
     """Inverse of pack_results for one rank's record; `like` = this rank's own results (trailing dims and dtypes are the
-    same on every rank)."""
+    same on every rank).  `counts` = the record's three header words when the caller has already read them."""
     names = _fields(like)
     maxes = (max_pages, max_crops, max_tables)
-    counts = [int(buf[0]), int(buf[1]), int(buf[2])]
+    counts = [int(c) for c in counts] if len(counts) == 3 else [int(buf[0]), int(buf[1]), int(buf[2])]
     out = {}
     o = 3
     for k in names:
@@ -97,5 +98,6 @@ def all_gather_results(res: Dict[str, torch.Tensor], page_sizes: Sequence[int], 
     mine = pack_results(res, max_pages, max_crops, max_tables)
     gathered = torch.empty(world * mine.numel(), dtype=torch.int32, device=mine.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
-    parts = [unpack_results(gathered[r * mine.numel():(r + 1) * mine.numel()], res, max_pages, max_crops, max_tables) for r in range(world)]
+    heads = gathered.view(world, mine.numel())[:, :3].cpu().tolist()  # ONE device -> host read for all ranks' row counts
+    parts = [unpack_results(gathered[r * mine.numel():(r + 1) * mine.numel()], res, max_pages, max_crops, max_tables, heads[r]) for r in range(world)]
     return {k: torch.cat([p[k] for p in parts], 0) for k in _fields(res)}

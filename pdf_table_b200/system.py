@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from .predictors import order_point, sort_det_boxes
+from .predictors import _h2d, order_point, order_points_batch, sort_det_boxes
 
 __all__ = ["OcrSystemTask", "get_layout_by_type"]
 
@@ -52,6 +52,86 @@ class OcrSystemTask:
         task = self.text_recognizer or self.table_structure_recognizer or self.text_detector or self.layout_detector
         dev = torch.device("cuda", self._need(task, "predictor").device)
         return torch.from_numpy(np.ascontiguousarray(image_full)).to(dev)
+
+    # ------------------------------------------------------------------ the page loop, batched
+    def predict_pages(self, pages, layout_tables=None, det_kwargs: Optional[Dict[str, Any]] = None,
+                      keep_device_record: bool = False) -> List[Dict[str, Any]]:
+        """The reference's per-page sequence (cli/main.py:116-144 -> ocr_system_task.py:549-734: layout_analysis,
+        text_detection, text_recognition, table_structure_detection) for a BATCH of equally sized pages, with the host steps
+        of one stage overlapped with the device work of another:
+
+            upload pages once -> [GPU] layout + detection -> host: layout records, table boxes -> [GPU] table structure (all
+            tables of all pages, cut from the resident pages) || host: reading-order sort + order_point of the detected boxes
+            -> [GPU] crop + recognise (all quads of all pages) || host: nothing left -> collect texts, cells.
+
+        pages: uint8 [P,H,W,3] ndarray (may be a view of pinned memory: the upload is then asynchronous) or a list of equally
+        sized HWC ndarrays.  layout_tables: optional per-page lists of table boxes [x1,y1,x2,y2] that replace the layout
+        detector's own "table" rows (what the reference passes in as ``layout_result``).  det_kwargs: passed to the text
+        detector's ``_run_model`` (e.g. ``prob_override``).  Returns one dict per page:
+        {"layout": [...], "det": float64 [n,8] in reading order, "ocr": [{"index","text","bbox"}], "tables": [[bbox, result]]}.
+        With keep_device_record the packed device-side results of the batch stay in ``self.device_record`` (the record the
+        multi-GPU all-gather exchanges, sharding.FIELDS)."""
+        det, rec = self._need(self.text_detector, "text_detector"), self._need(self.text_recognizer, "text_recognizer")
+        dev = torch.device("cuda", det.device)
+        if isinstance(pages, np.ndarray) and pages.ndim == 4:
+            batch = _h2d(torch.from_numpy(pages), dev)
+        else:
+            batch = torch.stack([_h2d(torch.from_numpy(np.ascontiguousarray(p)), dev) for p in pages])
+        n_pages = int(batch.shape[0])
+        page_list = list(batch)
+        # ---- stage 1 (GPU): layout + detection enqueued back to back
+        lay_run = None
+        if self.layout_detector is not None:
+            lay_run = self.layout_detector._run_model(self.layout_detector._preprocess(page_list))
+        det_run = det._run_model(det._preprocess(page_list), **(det_kwargs or {}))
+        # ---- host: layout records -> table boxes; stage 2 (GPU): table structure
+        layouts = self.layout_detector._postprocess(lay_run) if lay_run is not None else [[] for _ in range(n_pages)]
+        tsr_run = None
+        tables_flat: List[Dict[str, Any]] = []
+        if self.table_structure_recognizer is not None:
+            for p in range(n_pages):
+                if layout_tables is not None:
+                    boxes = [{"bbox": b} for b in layout_tables[p]]
+                else:
+                    boxes = get_layout_by_type(layout_result=layouts[p], label="table", score_threshold=0.2)
+                tables_flat += [{"bbox": t["bbox"], "page": p} for t in boxes]
+            tsr_run = self.table_structure_recognizer.launch_tables(batch, tables_flat)
+        # ---- host (while the tables run): reading order + corner order of the detected boxes; stage 3 (GPU): recognition
+        dets = [sort_det_boxes(d) if len(d) else np.zeros((0, 8)) for d in det._postprocess(det_run)]
+        pts = [order_points_batch(d) for d in dets]
+        rec_run = rec.launch_pages(batch, pts)
+        # ---- collect
+        tables = self.table_structure_recognizer.collect_tables(tsr_run) if tsr_run is not None else []
+        texts = rec.collect_pages(rec_run)
+        out = []
+        for p in range(n_pages):
+            ocr = [{"index": i + 1, "text": "" if t is None else t, "bbox": q} for i, (t, q) in enumerate(zip(texts[p], pts[p]))]
+            out.append({"layout": layouts[p], "det": dets[p], "ocr": ocr, "tables": []})
+        for tb, res in zip(tables_flat, tables):
+            out[tb["page"]]["tables"].append(res)
+        if keep_device_record:
+            self.device_record = self._device_record(det_run, rec_run, tsr_run, n_pages)
+        return out
+
+    @staticmethod
+    def _device_record(det_run, rec_run, tsr_run, n_pages: int) -> Dict[str, torch.Tensor]:
+        """The packed per-batch results that stay on the device (sharding.FIELDS / TABLE_FIELDS): boxes + counts of the pages
+        (single shape group), collapsed token ids + lengths of all crops, cells + counts + logical coordinates of all tables."""
+        _, boxes, counts, _, _ = det_run["pending"][0]
+        rec = {"boxes": boxes[:, :64].contiguous(), "box_counts": counts}
+        if rec_run.get("event") is not None:
+            rec["ids"], rec["id_lens"] = rec_run["ids_dev"], rec_run["len_dev"]
+        else:
+            rec["ids"] = torch.zeros((0, 201), dtype=torch.int32, device=boxes.device)
+            rec["id_lens"] = torch.zeros((0,), dtype=torch.int32, device=boxes.device)
+        if tsr_run is not None and "logi" in tsr_run["dev"]:
+            d = tsr_run["dev"]
+            # the logical coordinates are packed by the per-image offsets: re-pad them to 256 rows per table (index plumbing)
+            idx = d["offsets"][:-1].long()[:, None] + torch.arange(256, device=d["logi"].device)[None, :]
+            rec["cells"] = d["polygons"][:, :256].contiguous()
+            rec["cell_counts"] = d["counts"]
+            rec["cell_logi"] = d["logi"][idx.clamp_(max=int(d["logi"].shape[0]) - 1)]
+        return rec
 
     def text_detection(self, image) -> Tuple[np.ndarray, Dict[str, float]]:
         """:146-166: detect, then sort the boxes into reading order.  Returns (float64 [n,8], metric)."""

@@ -14,17 +14,25 @@ def _run(*args, env=None):
 
 
 def test_reference_arm_json_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "pages_per_sec" and d["unit"] == "pages/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["config"]["workload"].startswith("BASELINE configs[1]") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("BASELINE configs[4]") and "model" not in d["config"]  # the default line = the full cascade
+    assert d["blocks"]["rec_sweep"]["unit"] == "crops/s" and d["blocks"]["rec_sweep"]["value"] > 0 and d["blocks"]["lore"]["unit"] == "images/s"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_ocr_cascade():
+    r = _run("--impl", "reference", "--cascade", "ocr", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["config"]["workload"].startswith("BASELINE configs[1]") and d["value"] > 0 and "lore" not in d["blocks"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -1,11 +1,10 @@
 """db_boxes (threshold + box seed) vs the reference-generated golden boxes and the CPU oracle.
 
-Parity statement (DESIGN.md "DB post-process"): contour discovery, border tracing, convex hull, the fillPoly mask,
-the Clipper offset and all integer box arithmetic are restated exactly; cv2.minAreaRect's float32 rounding is
-restated to the last bit in most but not all cases (oracle/cv_geom_ref.py), and because the reference truncates those
-floats to integers before the offset, a last-bit difference can move a box corner by one pixel.  The test therefore
-requires: same number of boxes in the same order, every corner within 1 px, and at least 90 % of boxes identical
-(IoU == 1); it prints the measured identical fraction."""
+Parity statement (DESIGN.md "DB post-process"): contour discovery, border tracing, convex hull, cv2.minAreaRect (OpenCV
+4.13: counter-clockwise hull, cross-product edge selection, double angle normalisation -- bit-identical to cv2 on every
+probed contour, tests/test_oracle_cpu.py), boxPoints, the fillPoly mask, the Clipper offset and all integer box arithmetic
+are restated exactly.  The tests therefore require IDENTICAL integer output: same number of boxes, same order, every
+corner equal."""
 import os
 
 import numpy as np
@@ -33,8 +32,8 @@ def _compare(got, want, name):
     if len(want) == 0:
         return 1.0
     dev = np.abs(got - want).max(axis=1)
-    assert dev.max() <= 1.0, f"{name}: corner deviation {dev.max()} px\n{got[dev.argmax()]}\n{want[dev.argmax()]}"
-    return float((dev == 0).mean())
+    assert dev.max() == 0.0, f"{name}: corner deviation {dev.max()} px in {int((dev > 0).sum())} of {len(dev)} boxes\n{got[dev.argmax()]}\n{want[dev.argmax()]}"
+    return 1.0
 
 
 def test_db_boxes_reference_golden(post_engine):
@@ -47,7 +46,21 @@ def test_db_boxes_reference_golden(post_engine):
     print("db_boxes vs reference golden (name, boxes, identical fraction):", fracs)
     tot = sum(n for _, n, _ in fracs)
     ident = sum(n * f for _, n, f in fracs)
-    assert ident / tot >= 0.9
+    assert ident == tot
+
+
+def test_db_boxes_dbnet_backend_reference_golden(post_engine):
+    """model="db": dv_db_boxes_dbnet vs the reference's in-tree DBNet post-processor (tests/golden/dbnet_proc.npz)."""
+    from oracle.gen_golden_more import DBNET_POST_CASES
+
+    g = np.load(os.path.join(GOLDEN, "dbnet_proc.npz"))
+    for name, idx, h, w, n_lines, org_h, org_w in DBNET_POST_CASES:
+        prob = synth.synthetic_prob_map(idx, h, w, n_lines)
+        got = _run(post_engine, prob, org_h, org_w, box_thresh=0.3, variant="db")
+        want = g["post_" + name]
+        assert got.shape == want.shape, f"{name}: {got.shape[0]} boxes vs {want.shape[0]}"
+        np.testing.assert_array_equal(got.astype(np.int64), want, err_msg=name)
+        np.testing.assert_array_equal(got.astype(np.int64), db_post_ref.dbnet_postprocess(prob, (org_h, org_w)))
 
 
 def test_db_boxes_vs_oracle_batch(post_engine):
@@ -64,7 +77,7 @@ def test_db_boxes_vs_oracle_batch(post_engine):
         tot += len(want)
         ident += f * len(want)
     print(f"db_boxes batch: {tot} boxes, identical fraction {ident / tot:.3f}")
-    assert ident / tot >= 0.9
+    assert ident == tot and tot > 50
 
 
 def test_db_boxes_edge_cases(post_engine):

@@ -99,6 +99,47 @@ def test_db_post_oracle_matches_reference_golden():
         assert len(got) > 0
 
 
+def test_dbnet_backend_post_oracle_matches_reference_golden():
+    """oracle/db_post_ref.dbnet_postprocess == the reference's in-tree DBNet post-processor (model="db") run in the build container."""
+    from oracle import db_post_ref
+    from oracle.gen_golden_more import DBNET_POST_CASES
+
+    g = np.load(os.path.join(GOLDEN, "dbnet_proc.npz"))
+    for name, idx, h, w, n_lines, org_h, org_w in DBNET_POST_CASES:
+        got = db_post_ref.dbnet_postprocess(synth.synthetic_prob_map(idx, h, w, n_lines), (org_h, org_w))
+        np.testing.assert_array_equal(got, g["post_" + name])
+        assert len(got) > 3
+
+
+def test_min_area_rect_twin_is_bit_identical_to_cv2():
+    """oracle/cv_geom_ref.min_area_rect / box_points -- the numpy twin of the device code in csrc/db_post.cu -- against the cv2
+    of this image, every bit of (centre, size, angle) and of the four box points: random filled quads and discs through
+    findContours, plus the degenerate hulls (1 and 2 points, collinear points)."""
+    import sys
+
+    import cv2
+
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    import min_area_rect_probe as probe
+    from oracle import cv_geom_ref as G
+
+    n = 0
+    for c in probe.contours(300, seed=3):
+        r = cv2.minAreaRect(c)
+        m = G.min_area_rect([(int(p[0]), int(p[1])) for p in c.reshape(-1, 2)])
+        got = np.array([m[0][0], m[0][1], m[1][0], m[1][1], m[2]], np.float32)
+        want = np.array([r[0][0], r[0][1], r[1][0], r[1][1], r[2]], np.float32)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all(), (c.reshape(-1, 2).tolist(), got, want)
+        assert (G.box_points(m).view(np.uint32) == cv2.boxPoints(r).view(np.uint32)).all()
+        n += 1
+    assert n >= 300
+    for pts in ([[3, 4], [10, 9]], [[3, 4], [3, 9]], [[3, 4], [9, 4]], [[5, 5]], [[3, 4], [10, 2]], [[3, 4], [5, 6], [7, 8]],
+                [[0, 0], [4, 0], [4, 1], [0, 1]]):
+        r = cv2.minAreaRect(np.array(pts, np.int32).reshape(-1, 1, 2))
+        m = G.min_area_rect([tuple(p) for p in pts])
+        assert (r[0][0], r[0][1], r[1][0], r[1][1], r[2]) == (float(m[0][0]), float(m[0][1]), float(m[1][0]), float(m[1][1]), float(m[2])), pts
+
+
 def test_clipper_offset_known_answers():
     """Round-join offset of an axis-aligned rectangle: every point lies within 1 of distance d from the source
     rectangle, the axis extremes are exactly +-d, and tiny deltas use the reduced arc tolerance."""

@@ -86,3 +86,21 @@ def test_error_behaviour_without_gpu():
 
         with pytest.raises(DocVisionError):  # no silent CPU fallback
             predictors.OcrDetectionTask(model="db_pp", state_dict=synth.dbnet_r18_state_dict(0))
+
+
+def test_dbnet_backend_preprocess_matches_reference():
+    """model="db": OCRDetectionPreprocessor's resize rule and its (x - mean) / 255 normalisation of the BGR-flipped page
+    (tests/golden/dbnet_proc.npz, generated from the reference class by oracle/gen_golden_more.py:gen_dbnet_proc).  The second
+    half is the arithmetic contract of the fused kernel: (x * 1 - mean) / 255 in float32."""
+    import cv2
+
+    g = np.load(os.path.join(GOLDEN, "dbnet_proc.npz"))
+    for h, w, rh, rw in g["table"]:
+        assert predictors.dbnet_resize_shape(int(h), int(w), 736) == (int(rh), int(rw))
+    page = synth.synthetic_page(5, 100, 150)
+    assert list(g["page_org_shape"]) == [100, 150]
+    nh, nw = predictors.dbnet_resize_shape(100, 150, 736)
+    res = cv2.resize(page, (nw, nh))  # resize before the flip == flip before the resize (cv2.resize acts per channel)
+    mean = np.array(predictors.OcrDetectionTask.DB_MEAN, np.float32)
+    x = (res[:, :, ::-1].astype(np.float32) * np.float32(1.0) - mean) / np.float32(255.0)
+    np.testing.assert_array_equal(x.transpose(2, 0, 1), g["page_chw"])

@@ -84,3 +84,18 @@ def test_layout_analysis_returns_first_result():
 
     result, metric = system.OcrSystemTask(layout_detector=_Lay()).layout_analysis("p")
     assert result[0]["label"] == "text" and set(metric) == {"use_time"}
+
+
+def test_order_points_batch_equals_order_point():
+    """The vectorised corner ordering the batched orchestrator uses must give the per-quad reference function's result bit for bit."""
+    import os
+
+    rng = np.random.default_rng(5)
+    quads = [rng.uniform(0, 900, (200, 4, 2)), rng.integers(0, 60, (200, 4, 2)).astype(np.float64),  # integer grids: ties in the angles
+             np.load(os.path.join(os.path.dirname(__file__), "golden", "glue.npz"))["quads"]]
+    for q in quads:
+        got = predictors.order_points_batch(q)
+        assert got.dtype == np.float32 and got.shape == (len(q), 4, 2)
+        for k in range(len(q)):
+            assert np.array_equal(got[k], predictors.order_point(q[k])), k
+    assert predictors.order_points_batch(np.zeros((0, 8))).shape == (0, 4, 2)
