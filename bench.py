@@ -159,7 +159,7 @@ def make_prob_maps(rank: int, n: int) -> np.ndarray:
     random weights the detector's own output is texture noise, so the box stage runs on analytic text-line blobs."""
     from pdf_table_b200 import synth
 
-    distinct = [synth.synthetic_prob_map(rank * 1000 + i, PAGE_H, PAGE_W, CROPS_PER_PAGE) for i in range(4)]
+    distinct = [synth.synthetic_prob_map_lines(rank * 1000 + i, PAGE_H, PAGE_W, CROPS_PER_PAGE) for i in range(4)]
     return np.stack([distinct[i % 4] for i in range(n)])[:, None]
 
 
@@ -698,10 +698,10 @@ def workload_config():
         "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
         "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
         "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} crop slots per "
-                     "page cut on the device from the db_boxes quads of that page (crop_image + keepratio_resize, bit-exact vs cv2; slots beyond "
-                     "a page's box count are zero crops and cost the same recogniser work), seeded random weights",
+                     "page cut on the device from the db_boxes quads of that page (crop_image + keepratio_resize, bit-exact vs cv2; the planted "
+                     "maps yield exactly that many boxes), seeded random weights",
         "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
-        "db_post_stage": "db_boxes on planted probability maps (analytic text-line blobs, ~40 per page): with random weights the "
+        "db_post_stage": "db_boxes on planted probability maps (40 analytic text-line blobs per page, every one a box; + specks): with random weights the "
                          "detector's own map is texture noise; the network still runs and its map is discarded",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",

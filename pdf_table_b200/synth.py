@@ -246,6 +246,38 @@ def synthetic_prob_map(index: int, h: int = 960, w: int = 960, n_lines: int = 40
     return prob
 
 
+def synthetic_prob_map_lines(index: int, h: int = 960, w: int = 960, n_lines: int = 40) -> np.ndarray:
+    """A DB-like probability map whose every blob becomes a box: n_lines soft-edged text-line rectangles on a jittered
+    column / row grid (slightly rotated, peak 0.8-0.98, none touching), plus specks that the size / score filters reject.
+    The bench plants it so that the number of detected boxes per page is the workload's crop count."""
+    rng = np.random.default_rng(515151 + index)
+    prob = np.zeros((h, w), np.float32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    cols = 4
+    rows = (n_lines + cols - 1) // cols
+    cw, rh = w / cols, h / rows
+    for k in range(n_lines):
+        r, c = divmod(k, cols)
+        bw, bh = rng.uniform(0.55, 0.8) * cw, rng.uniform(0.28, 0.42) * rh
+        cx = (c + 0.5) * cw + rng.uniform(-0.06, 0.06) * cw
+        cy = (r + 0.5) * rh + rng.uniform(-0.1, 0.1) * rh
+        ang = rng.uniform(-0.035, 0.035)
+        peak, soft = rng.uniform(0.8, 0.98), rng.uniform(1.0, 2.5)
+        cs, sn = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+        rad = int(np.hypot(bw, bh) / 2 + soft + 2)
+        x0, x1, y0, y1 = max(0, int(cx) - rad), min(w, int(cx) + rad + 1), max(0, int(cy) - rad), min(h, int(cy) + rad + 1)
+        dx, dy = xx[y0:y1, x0:x1] - np.float32(cx), yy[y0:y1, x0:x1] - np.float32(cy)
+        u, v = dx * cs + dy * sn, -dx * sn + dy * cs
+        d = np.minimum(np.float32(bw / 2) - np.abs(u), np.float32(bh / 2) - np.abs(v))
+        val = np.float32(peak) * np.clip(np.float32(0.5) + d / np.float32(soft), 0, 1)
+        prob[y0:y1, x0:x1] = np.maximum(prob[y0:y1, x0:x1], val.astype(np.float32))
+    for _ in range(20):  # specks between the lines: tiny components that fail min_size
+        sx, sy = int(rng.uniform(2, w - 4)), int(rng.uniform(2, h - 4))
+        if prob[max(0, sy - 6):sy + 8, max(0, sx - 6):sx + 8].max() == 0:
+            prob[sy:sy + 2, sx:sx + 2] = np.float32(rng.uniform(0.3, 0.9))
+    return prob
+
+
 # --------------------------------------------------------------------------- Lore (DLA-34 + DCNv2 detector, wtw)
 DLA_LEVELS = (1, 1, 1, 2, 2, 1)
 DLA_CHANNELS = (16, 32, 64, 128, 256, 512)
