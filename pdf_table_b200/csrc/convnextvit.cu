@@ -22,10 +22,10 @@ namespace dv {
 int op_cnv_patchify_ln(Engine* e, const float* chunks, const uint8_t* crops_u8, int crop_w, int B, const float* w,
                        const float* bias, const float* lnw, const float* lnb, float* out);
 int op_dwconv7_ln(Engine* e, const float* x, int B, int H, int C, const float* w, const float* b, const float* lnw,
-                  const float* lnb, __half* out, const char* layer);
+                  const float* lnb, __half* out, const char* layer, int split);
 int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* lnw, const float* lnb, float eps,
-               int normalise, int map, int H, __half* out, const char* layer);
-int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer);
+               int normalise, int map, int H, __half* out, const char* layer, int split);
+int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer, int split);
 
 namespace {
 
@@ -67,7 +67,13 @@ struct Pass {
     }
 };
 
+// fp32x mode (the blob carries a "precision" entry, weights.pack_convnext_vit(precise=True)): every GEMM operand is a
+// split-fp16 pair -- activations [hi | lo], weights [W_hi | W_lo | W_hi] -- and conv_igemm_tcgen05 accumulates
+// A_hi W_hi + A_hi W_lo + A_lo W_hi in fp32 TMEM (3x the MMAs, products to ~2^-21); the MLP runs as two GEMMs (the hidden
+// tensor is a split pair in HBM), attention on the fp32 CUDA-core kernel.  Logits land within 1e-3 of the fp32 oracle
+// (tests/test_gpu_convnextvit.py) where the default fp16-operand mode is 8.5e-3 away.
 struct CnvModel : Model {
+    bool precise = false;
     int labels = 0;
     int pass_crops = 384;
     std::map<int, std::unique_ptr<Pass>> passes;
@@ -83,18 +89,25 @@ const float* f32(Engine* e, const std::string& name, size_t min_elems, int* rc) 
     return reinterpret_cast<const float*>(t->dptr);
 }
 
+bool is_precise(Engine* e) {
+    CnvModel* m = dynamic_cast<CnvModel*>(e->model.get());
+    return m && m->precise;
+}
+
 int get_linear(Engine* e, const std::string& name, int K, int N, ConvSpec* cs) {
     const BlobTensor* w = e->find(name + ".w");
     const BlobTensor* b = e->find(name + ".b");
+    const bool split = is_precise(e);
     if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2)
         return set_err(e, DV_ERR_WEIGHTS, "missing weights for '%s'", name.c_str());
-    if (static_cast<int>(w->dims[0]) != N || static_cast<int>(w->dims[1]) != K)
-        return set_err(e, DV_ERR_WEIGHTS, "'%s': weight [%u,%u] != [%d,%d]", name.c_str(), w->dims[0], w->dims[1], N, K);
+    if (static_cast<int>(w->dims[0]) != N || static_cast<int>(w->dims[1]) != (split ? 3 * K : K))
+        return set_err(e, DV_ERR_WEIGHTS, "'%s': weight [%u,%u] != [%d,%d]", name.c_str(), w->dims[0], w->dims[1], N, split ? 3 * K : K);
     if (b->dims[0] < static_cast<uint32_t>((N + 255) / 256 * 256))
         return set_err(e, DV_ERR_WEIGHTS, "'%s': bias not padded to 256", name.c_str());
     cs->KH = cs->KW = 1;
     cs->Cin = K;
-    cs->Cin_pad = K;
+    cs->Cin_pad = split ? 3 * K : K;
+    cs->split = split;
     cs->Cout = N;
     cs->BK = (K % 64 == 0) ? 64 : (K % 32 == 0) ? 32 : 16;
     cs->w = reinterpret_cast<const __half*>(w->dptr);
@@ -122,10 +135,12 @@ int add_gemm(Engine* e, Pass* ps, const std::string& name, const __half* A, long
 int add_mlp(Engine* e, Pass* ps, const std::string& n1, const std::string& n2, const __half* h, __half* g, long long rows, int C,
             float* x);
 
-EpiSpec epi_f16(__half* out, int ld, int act) {
+// fp16 GEMM output of N columns; split: rows of [hi(N) | lo(N)]
+EpiSpec epi_f16(__half* out, int n, int act, bool split) {
     EpiSpec es;
     es.out = out;
-    es.out_ld = ld;
+    es.out_ld = split ? 2 * n : n;
+    es.split_off = split ? n : 0;
     es.act = act;
     return es;
 }
@@ -147,8 +162,8 @@ EpiSpec epi_stream(float* out, int ld, const float* res, int res_mod = 0) {
 
 int add_mlp(Engine* e, Pass* ps, const std::string& n1, const std::string& n2, const __half* h, __half* g, long long rows, int C,
             float* x) {
-    if (!mlp_fused_supported(C)) {
-        DV_TRY(add_gemm(e, ps, n1, h, rows, C, 4 * C, epi_f16(g, 4 * C, ACT_GELU)));
+    if (!mlp_fused_supported(C) || is_precise(e)) {
+        DV_TRY(add_gemm(e, ps, n1, h, rows, C, 4 * C, epi_f16(g, 4 * C, ACT_GELU, is_precise(e))));
         return add_gemm(e, ps, n2, g, rows, 4 * C, C, epi_stream(x, C, x));
     }
     ConvSpec c1, c2;
@@ -168,14 +183,16 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
     ps->crops = crops;
     const int B = ps->B = crops * 3;
     const long long unit = 57600LL * B;  // tokens x channels of the widest stream tensor (600 x 96 per chunk)
+    const bool split = m->precise;
+    const int sp = split ? 2 : 1;  // fp16 operand buffers hold [hi | lo] pairs in fp32x mode
     float *xa, *xb, *xv;
     __half *h, *h2, *g;
     DV_TRY(ps->alloc(reinterpret_cast<void**>(&xa), unit * 4));
     DV_TRY(ps->alloc(reinterpret_cast<void**>(&xb), unit * 4));
     DV_TRY(ps->alloc(reinterpret_cast<void**>(&xv), static_cast<size_t>(B) * kTok * kVitDim * 4));
-    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h), unit * 2));
-    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h2), static_cast<size_t>(B) * kTok * kVitDim * 2));
-    DV_TRY(ps->alloc(reinterpret_cast<void**>(&g), unit * 4 * 2));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h), unit * 2 * sp));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&h2), static_cast<size_t>(B) * kTok * kVitDim * 2 * sp));
+    DV_TRY(ps->alloc(reinterpret_cast<void**>(&g), unit * 4 * 2 * sp));
     int rc = 0;
     {
         Step st;
@@ -265,7 +282,7 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
         ln1.hout = h;
         if (rc) return rc;
         ps->steps.push_back(ln1);
-        DV_TRY(add_gemm(e, ps, lp + ".qkv", h, T, kVitDim, 3 * kVitDim, epi_f16(g, 3 * kVitDim, ACT_NONE)));
+        DV_TRY(add_gemm(e, ps, lp + ".qkv", h, T, kVitDim, 3 * kVitDim, epi_f16(g, 3 * kVitDim, ACT_NONE, split)));
         Step at;
         at.kind = Step::ATTN;
         at.name = lp + ".attn";
@@ -309,6 +326,7 @@ int build_pass(Engine* e, CnvModel* m, Pass* ps, int crops) {
 
 int run_pass(Engine* e, Pass* ps, const float* chunks, const uint8_t* crops_u8, int crop_w, float* logits, int32_t* ids,
              float* maxv) {
+    const int split = is_precise(e) ? 1 : 0;
     for (size_t i = 0; i < ps->steps.size(); ++i) {
         Step& st = ps->steps[i];
         switch (st.kind) {
@@ -316,13 +334,13 @@ int run_pass(Engine* e, Pass* ps, const float* chunks, const uint8_t* crops_u8, 
                 DV_TRY(op_cnv_patchify_ln(e, chunks, crops_u8, crop_w, ps->B, st.w, st.b, st.lnw, st.lnb, st.fout));
                 break;
             case Step::DWLN:
-                DV_TRY(op_dwconv7_ln(e, st.fin, ps->B, st.H, st.C, st.w, st.b, st.lnw, st.lnb, st.hout, st.name.c_str()));
+                DV_TRY(op_dwconv7_ln(e, st.fin, ps->B, st.H, st.C, st.w, st.b, st.lnw, st.lnb, st.hout, st.name.c_str(), split));
                 break;
             case Step::LN:
                 DV_TRY(op_ln_rows(e, st.fin, st.rows, st.C, st.lnw, st.lnb, st.eps, st.normalise, st.map, st.H, st.hout,
-                                  st.name.c_str()));
+                                  st.name.c_str(), split));
                 break;
-            case Step::ATTN: DV_TRY(op_attn75(e, st.hin, ps->B, st.hout, st.name.c_str())); break;
+            case Step::ATTN: DV_TRY(op_attn75(e, st.hin, ps->B, st.hout, st.name.c_str(), split)); break;
             case Step::MLP: DV_TRY(launch_mlp(e, st.mlp)); break;
             case Step::GEMM:
                 if (static_cast<int>(i) == ps->cls_step) {
@@ -344,6 +362,7 @@ int cnv_create(Engine* e) {
     e->model.reset(m);
     const BlobTensor* w = e->find("cls.w");
     if (!w || w->ndim != 2) return set_err(e, DV_ERR_WEIGHTS, "convnext_vit: missing classifier weights");
+    m->precise = e->find("precision") != nullptr;  // fp32x blob: split-fp16 weight triples
     m->labels = static_cast<int>(w->dims[0]);
     if (m->labels % 4) return set_err(e, DV_ERR_UNSUPPORTED, "convnext_vit: num_labels %% 4 != 0");
     if (const char* s = getenv("DV_REC_PASS_CROPS")) {

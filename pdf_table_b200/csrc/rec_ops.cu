@@ -14,6 +14,14 @@ namespace dv {
 
 namespace {
 
+// fp32x (split-fp16) operands: a value is stored as hi = fp16(v) and lo = fp16(v - hi); hi + lo carries ~21 significand bits
+// and the consumer GEMM forms A_hi W_hi + A_hi W_lo + A_lo W_hi (igemm_host.cu plan_linear, ConvSpec::split).
+__device__ __forceinline__ void store_split(__half* hi_ptr, int lo_off, float v) {
+    const __half h = __float2half_rn(v);
+    *hi_ptr = h;
+    if (lo_off) hi_ptr[lo_off] = __float2half_rn(v - __half2float(h));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -94,7 +102,7 @@ constexpr int kTileW = kStrip + 6;
 template <int C, int H>
 __global__ void __launch_bounds__(C* H)
 k_dwconv7_ln(const float* __restrict__ x, const float* __restrict__ w /*[49][C]*/, const float* __restrict__ bias,
-             const float* __restrict__ lnw, const float* __restrict__ lnb, __half* __restrict__ out) {
+             const float* __restrict__ lnw, const float* __restrict__ lnb, __half* __restrict__ out, int split) {
     extern __shared__ float tile[];  // [H][kTileW][C]
     const int b = blockIdx.x / 5;
     const int x0 = (blockIdx.x - b * 5) * kStrip;
@@ -161,11 +169,12 @@ k_dwconv7_ln(const float* __restrict__ x, const float* __restrict__ w /*[49][C]*
         }
         const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-6f);
         const int py = p / kStrip, pxs = p - py * kStrip;
-        __half* op = out + ((static_cast<long long>(b) * H + py) * 75 + x0 + pxs) * C;
+        // split: rows of [hi(C) | lo(C)]
+        __half* op = out + ((static_cast<long long>(b) * H + py) * 75 + x0 + pxs) * (split ? 2 * C : C);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             const int cc = lane + 32 * j;
-            op[cc] = __float2half_rn(v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
+            store_split(op + cc, split ? C : 0, v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
         }
     }
 }
@@ -181,7 +190,7 @@ enum { LN_IDENT = 0, LN_DOWN = 1, LN_STITCH = 2 };
 template <int C>
 __global__ void __launch_bounds__(256)
 k_ln_rows(const float* __restrict__ in, long long rows, const float* __restrict__ lnw, const float* __restrict__ lnb,
-          float eps, int normalise, int map, int H, __half* __restrict__ out) {
+          float eps, int normalise, int map, int H, __half* __restrict__ out, int split) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
     if (row >= rows) return;
@@ -222,7 +231,8 @@ k_ln_rows(const float* __restrict__ in, long long rows, const float* __restrict_
         v[j] = ip[lane + 32 * j];
         s += v[j];
     }
-    __half* op = out + orow * old + ocoff;
+    const int lo_off = split ? old : 0;  // split: output rows are [hi(old) | lo(old)]
+    __half* op = out + orow * (split ? 2 * old : old) + ocoff;
     if (normalise) {
         const float mean = warp_sum(s) * (1.f / C);
         float q = 0.f;
@@ -235,11 +245,11 @@ k_ln_rows(const float* __restrict__ in, long long rows, const float* __restrict_
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
             const int cc = lane + 32 * j;
-            op[cc] = __float2half_rn(v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
+            store_split(op + cc, lo_off, v[j] * rstd * __ldg(lnw + cc) + __ldg(lnb + cc));
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) op[lane + 32 * j] = __float2half_rn(v[j]);
+        for (int j = 0; j < CPL; ++j) store_split(op + lane + 32 * j, lo_off, v[j]);
     }
 }
 
@@ -251,6 +261,8 @@ k_ln_rows(const float* __restrict__ in, long long rows, const float* __restrict_
 constexpr int kAttnThreads = 288;
 constexpr int kAttnSmem = (2 * 75 * 192 + 75 * kAttnThreads) * 4;
 
+// SPLIT (fp32x mode): qkv rows are [hi(576) | lo(576)] and ctx rows [hi(192) | lo(192)]; q, k, v = hi + lo in fp32.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
     extern __shared__ float sm[];
@@ -258,10 +270,11 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
     float* sV = sm + 75 * 192;      // [75][192]
     float* sS = sm + 2 * 75 * 192;  // [75][288]
     const int b = blockIdx.x;
-    const __half* base = qkv + static_cast<long long>(b) * 75 * 576;
+    constexpr int RS = SPLIT ? 1152 : 576;  // halves per qkv row
+    const __half* base = qkv + static_cast<long long>(b) * 75 * RS;
     for (int i = threadIdx.x; i < 75 * 48; i += kAttnThreads) {  // 48 x 8 halves = K|V of one token
         const int t = i / 48, c8 = i - t * 48;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + t * 576 + 192 + c8 * 8));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + t * RS + 192 + c8 * 8));
         const __half2* h = reinterpret_cast<const __half2*>(&u);
         float* dst = (c8 < 24 ? sK + t * 192 + c8 * 8 : sV + t * 192 + (c8 - 24) * 8);
 #pragma unroll
@@ -270,6 +283,16 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
             dst[2 * e] = f.x;
             dst[2 * e + 1] = f.y;
         }
+        if constexpr (SPLIT) {
+            const uint4 ul = __ldg(reinterpret_cast<const uint4*>(base + t * RS + 576 + 192 + c8 * 8));
+            const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hl[e]);
+                dst[2 * e] += f.x;
+                dst[2 * e + 1] += f.y;
+            }
+        }
     }
     __syncthreads();
     const int head = threadIdx.x / 96;
@@ -277,7 +300,7 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
     if (qi >= 75) return;
     float q[64];
     {
-        const uint4* qp = reinterpret_cast<const uint4*>(base + qi * 576 + head * 64);
+        const uint4* qp = reinterpret_cast<const uint4*>(base + qi * RS + head * 64);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint4 u = __ldg(qp + i);
@@ -287,6 +310,16 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
                 const float2 f = __half22float2(h[e]);
                 q[i * 8 + 2 * e] = f.x;
                 q[i * 8 + 2 * e + 1] = f.y;
+            }
+            if constexpr (SPLIT) {
+                const uint4 ul = __ldg(qp + 72 + i);  // + 576 halves
+                const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hl[e]);
+                    q[i * 8 + 2 * e] += f.x;
+                    q[i * 8 + 2 * e + 1] += f.y;
+                }
             }
         }
     }
@@ -325,14 +358,23 @@ k_attn75(const __half* __restrict__ qkv, __half* __restrict__ ctx) {
         }
     }
     const float inv = 1.f / denom;
-    uint4* op = reinterpret_cast<uint4*>(ctx + (static_cast<long long>(b) * 75 + qi) * 192 + head * 64);
+    uint4* op = reinterpret_cast<uint4*>(ctx + (static_cast<long long>(b) * 75 + qi) * (SPLIT ? 384 : 192) + head * 64);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        uint4 u;
+        uint4 u, ul;
         __half2* h = reinterpret_cast<__half2*>(&u);
+        __half2* hl = reinterpret_cast<__half2*>(&ul);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[i * 8 + 2 * e] * inv, o[i * 8 + 2 * e + 1] * inv);
+        for (int e = 0; e < 4; ++e) {
+            const float v0 = o[i * 8 + 2 * e] * inv, v1 = o[i * 8 + 2 * e + 1] * inv;
+            h[e] = __floats2half2_rn(v0, v1);
+            if constexpr (SPLIT) {
+                const float2 f = __half22float2(h[e]);
+                hl[e] = __floats2half2_rn(v0 - f.x, v1 - f.y);
+            }
+        }
         op[i] = u;
+        if constexpr (SPLIT) op[24 + i] = ul;  // + 192 halves
     }
 }
 
@@ -483,7 +525,7 @@ k_attn75_mma(const __half* __restrict__ qkv, __half* __restrict__ ctx, int B) {
 
 template <int C, int H>
 int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, const float* lnw, const float* lnb,
-              __half* out, const char* layer) {
+              __half* out, const char* layer, int split) {
     const size_t smem = static_cast<size_t>(H) * kTileW * C * sizeof(float);
     static DeviceOnce attr_once;
     if (attr_once.need(e->device)) {
@@ -491,8 +533,8 @@ int launch_dw(Engine* e, const float* x, int B, const float* w, const float* b, 
         attr_once.mark(e->device);
     }
     const double elems = static_cast<double>(B) * H * 75 * C;
-    e->launch_begin("k_dwconv7_ln", layer, 2.0 * 49 * elems, elems * (4 + 2));
-    k_dwconv7_ln<C, H><<<B * 5, C * H, smem, e->stream>>>(x, w, b, lnw, lnb, out);
+    e->launch_begin("k_dwconv7_ln", layer, 2.0 * 49 * elems, elems * (4 + (split ? 4 : 2)));
+    k_dwconv7_ln<C, H><<<B * 5, C * H, smem, e->stream>>>(x, w, b, lnw, lnb, out, split);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -515,23 +557,23 @@ int op_cnv_patchify_ln(Engine* e, const float* chunks, const uint8_t* crops_u8, 
 }
 
 int op_dwconv7_ln(Engine* e, const float* x, int B, int H, int C, const float* w, const float* b, const float* lnw,
-                  const float* lnb, __half* out, const char* layer) {
-    if (C == 96 && H == 8) return launch_dw<96, 8>(e, x, B, w, b, lnw, lnb, out, layer);
-    if (C == 192 && H == 4) return launch_dw<192, 4>(e, x, B, w, b, lnw, lnb, out, layer);
-    if (C == 256 && H == 2) return launch_dw<256, 2>(e, x, B, w, b, lnw, lnb, out, layer);
-    if (C == 512 && H == 1) return launch_dw<512, 1>(e, x, B, w, b, lnw, lnb, out, layer);
+                  const float* lnb, __half* out, const char* layer, int split) {
+    if (C == 96 && H == 8) return launch_dw<96, 8>(e, x, B, w, b, lnw, lnb, out, layer, split);
+    if (C == 192 && H == 4) return launch_dw<192, 4>(e, x, B, w, b, lnw, lnb, out, layer, split);
+    if (C == 256 && H == 2) return launch_dw<256, 2>(e, x, B, w, b, lnw, lnb, out, layer, split);
+    if (C == 512 && H == 1) return launch_dw<512, 1>(e, x, B, w, b, lnw, lnb, out, layer, split);
     return set_err(e, DV_ERR_UNSUPPORTED, "dwconv7_ln: unsupported (C=%d, H=%d)", C, H);
 }
 
 int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* lnw, const float* lnb, float eps,
-               int normalise, int map, int H, __half* out, const char* layer) {
+               int normalise, int map, int H, __half* out, const char* layer, int split) {
     const int grid = static_cast<int>((rows + 7) / 8);
-    e->launch_begin("k_ln_rows", layer, 0.0, static_cast<double>(rows) * C * 6);
+    e->launch_begin("k_ln_rows", layer, 0.0, static_cast<double>(rows) * C * (split ? 8 : 6));
     switch (C) {
-        case 96: k_ln_rows<96><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
-        case 192: k_ln_rows<192><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
-        case 256: k_ln_rows<256><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
-        case 512: k_ln_rows<512><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out); break;
+        case 96: k_ln_rows<96><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out, split); break;
+        case 192: k_ln_rows<192><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out, split); break;
+        case 256: k_ln_rows<256><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out, split); break;
+        case 512: k_ln_rows<512><<<grid, 256, 0, e->stream>>>(in, rows, lnw, lnb, eps, normalise, map, H, out, split); break;
         default: e->launch_end(); return set_err(e, DV_ERR_UNSUPPORTED, "ln_rows: C=%d", C);
     }
     e->launch_end();
@@ -539,17 +581,20 @@ int op_ln_rows(Engine* e, const float* in, long long rows, int C, const float* l
     return 0;
 }
 
-int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer) {
+int op_attn75(Engine* e, const __half* qkv, int B, __half* ctx, const char* layer, int split) {
     static DeviceOnce attr_once;
-    static const bool use_mma = !(getenv("DV_ATTN_SIMT") && atoi(getenv("DV_ATTN_SIMT")));
+    static const bool mma_env = !(getenv("DV_ATTN_SIMT") && atoi(getenv("DV_ATTN_SIMT")));
+    const bool use_mma = mma_env && !split;  // fp32x mode: q, k, v = hi + lo in fp32 on the CUDA cores
     if (attr_once.need(e->device)) {
-        DV_CUDA(e, cudaFuncSetAttribute(k_attn75, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        DV_CUDA(e, cudaFuncSetAttribute(k_attn75<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        DV_CUDA(e, cudaFuncSetAttribute(k_attn75<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         DV_CUDA(e, cudaFuncSetAttribute(k_attn75_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kAttnMmaSmem));
         attr_once.mark(e->device);
     }
     e->launch_begin(use_mma ? "k_attn75_mma" : "k_attn75", layer, 4.0 * 75 * 75 * 192 * B, static_cast<double>(B) * 75 * (576 + 192) * 2);
     if (use_mma) k_attn75_mma<<<B < e->num_sms ? B : e->num_sms, kAttnMmaThreads, 2 * kAttnMmaSmem, e->stream>>>(qkv, ctx, B);
-    else k_attn75<<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
+    else if (split) k_attn75<true><<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
+    else k_attn75<false><<<B, kAttnThreads, kAttnSmem, e->stream>>>(qkv, ctx);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

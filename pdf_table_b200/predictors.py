@@ -326,13 +326,18 @@ def _load_state_dict(sd_or_path) -> Mapping[str, Any]:
 class BaseInferTask:
     """Counterpart of BaseInferTask (ocr_pdf/base_infer_task.py:30-125, 311-315)."""
 
+    SUPPORTS_FP32X = False
+
     def __init__(self, task: str = "", model: str = "", predictor_type: str = "b200", device: Union[int, str] = 0,
                  output_dir: Optional[str] = None, debug: bool = False, lang: str = "en", precision: str = "fp16", **kwargs):
         if predictor_type != "b200":
             raise RuntimeError(f"predictor_type '{predictor_type}' is served by the reference itself; this package only "
                                "provides 'b200'")
-        if precision != "fp16":
-            raise RuntimeError("the b200 predictor computes with fp16 operands / fp32 accumulation (the reference default)")
+        if precision not in ("fp16", "fp32x") or (precision == "fp32x" and not self.SUPPORTS_FP32X):
+            raise RuntimeError(f"precision '{precision}' not supported by this predictor: 'fp16' = fp16 operands / fp32 accumulation "
+                               "(the reference default); 'fp32x' = split-fp16 operand pairs, ~fp32 products (logits within 1e-3 of "
+                               "the fp32 graph) where the model implements it")
+        self.precision = precision
         self.task, self.model, self._predictor_type = task, model, predictor_type
         self.device = int(str(device).replace("cuda:", "")) if not isinstance(device, int) else device
         self.output_dir, self.debug, self.lang, self.kwargs = output_dir, debug, lang, kwargs
@@ -527,6 +532,8 @@ class OcrRecognitionTask(BaseInferTask):
     Returns list[str] like the reference (:118-136).  `vocab` is the character list of the checkpoint's vocab file
     (label ids start at 2 because do_chunking is set, ocr_recognition/processor_ocr_recognition.py:137-145)."""
 
+    SUPPORTS_FP32X = True
+
     def __init__(self, task: str = "ocr_recognition", model: str = "ConvNextViT", task_type: str = "general", state_dict=None,
                  vocab: Optional[Sequence[str]] = None, **kwargs):
         if model != "ConvNextViT":
@@ -539,7 +546,7 @@ class OcrRecognitionTask(BaseInferTask):
         self.post = Engine("post", device=self.device)
 
     def _construct_model(self, model):
-        self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd), device=self.device)
+        self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
 
     def _preprocess(self, inputs) -> Dict[str, Any]:

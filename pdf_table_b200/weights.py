@@ -62,6 +62,39 @@ def pack_conv(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray]:
     return packed.reshape(cout, kh * kw * cp), pad_bias(b)
 
 
+def split_packed(packed_f32: np.ndarray, taps: int = 1) -> np.ndarray:
+    """fp32 K-major weight matrix [Cout, taps * Cin_pad] -> the split-fp16 operand [Cout, taps * 3 * Cin_pad]: per filter tap
+    [W_hi | W_lo | W_hi] with W_hi = fp16(W), W_lo = fp16(W - W_hi).  Against activations stored as [hi | lo] channel pairs the
+    k-block walk (hi, hi, lo) of conv_igemm_tcgen05 accumulates A_hi W_hi + A_hi W_lo + A_lo W_hi in fp32: the product to
+    ~2^-21 relative at 3x the MMAs (the "fp32x" precision mode)."""
+    cout, k = packed_f32.shape
+    w = packed_f32.reshape(cout, taps, k // taps).astype(np.float32)
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float32)).astype(np.float16)
+    return np.concatenate([hi, lo, hi], 2).reshape(cout, taps * 3 * (k // taps))
+
+
+def conv_matrix_f32(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray, int]:
+    """pack_conv before the fp16 cast: (fp32 [Cout, KH*KW*Cin_pad], fp32 bias padded to 256, taps)."""
+    w = _np(weight).astype(np.float32)
+    cout, cin, kh, kw = w.shape
+    scale, shift = bn_affine(bn, cout)
+    b = np.zeros(cout, np.float32) if bias is None else _np(bias).astype(np.float32)
+    w = w * scale[:, None, None, None]
+    b = b * scale + shift
+    cp = cin_pad_of(cin)
+    packed = np.zeros((cout, kh * kw, cp), np.float32)
+    packed[:, :, :cin] = w.transpose(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    return packed.reshape(cout, kh * kw * cp), pad_bias(b), kh * kw
+
+
+def pack_conv_split(weight, bias=None, bn=None, flat: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """pack_conv for the fp32x mode.  flat: the conv is run as ONE flat GEMM over a re-laid-out input whose row already holds
+    all taps (K = taps * Cin), so the hi / lo / hi triple spans the whole K instead of each tap."""
+    w, b, taps = conv_matrix_f32(weight, bias, bn)
+    return split_packed(w, 1 if flat else taps), b
+
+
 def pack_linear(weight, bias=None) -> Tuple[np.ndarray, np.ndarray]:
     """nn.Linear weight [out, in] -> same packing as a 1x1 conv."""
     w = _np(weight).astype(np.float32)
@@ -158,8 +191,10 @@ def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"]) -> bytes:
 
 
 # --------------------------------------------------------------------------- ConvNextViT
-def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
-    """state_dict of the reference ConvNextViT (convnext_vit/modeling_convnext_vit.py:20-45).
+def pack_convnext_vit(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> bytes:
+    """state_dict of the reference ConvNextViT (convnext_vit/modeling_convnext_vit.py:20-45).  precise=True packs every GEMM
+    weight as a split-fp16 triple (``split_packed``) and marks the blob with a "precision" entry: the engine then runs its
+    fp32x mode (csrc/convnextvit.cu).
 
     layer_scale is folded into pwconv2 (gamma * (W x + b)), the attention scale 1/sqrt(64) (an exact power of
     two) into the query projection, q/k/v are concatenated into one [576,192] GEMM, the (2,1) down-sampling conv
@@ -171,6 +206,16 @@ def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
     def put(name, wb):
         t[name + ".w"], t[name + ".b"] = wb
 
+    def lin(weight, bias=None):
+        w = _np(weight).astype(np.float32)
+        return pack_conv_split(w[:, :, None, None], bias) if precise else pack_linear(w, bias)
+
+    def conv_flat(weight, bias=None):  # (2,1) / 1x1 convs that the engine runs as one flat GEMM
+        return pack_conv_split(weight, bias, flat=True) if precise else pack_conv(weight, bias)
+
+    if precise:
+        t["precision"] = np.array([1], np.int32)
+
     p = "cnn_model.embeddings"
     t["patch.w"] = np.ascontiguousarray(f(p + ".patch_embeddings.weight").reshape(96, 16).T)  # [16][96], k = dy*4+dx
     t["patch.b"] = f(p + ".patch_embeddings.bias")
@@ -181,18 +226,18 @@ def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
         sp = f"cnn_model.encoder.stages.{s}"
         if s > 0:
             t[f"ds{s}.ln.w"], t[f"ds{s}.ln.b"] = f(sp + ".downsampling_layer.0.weight"), f(sp + ".downsampling_layer.0.bias")
-            put(f"ds{s}.conv", pack_conv(f(sp + ".downsampling_layer.1.weight"), f(sp + ".downsampling_layer.1.bias")))
+            put(f"ds{s}.conv", conv_flat(f(sp + ".downsampling_layer.1.weight"), f(sp + ".downsampling_layer.1.bias")))
         for j in range(depth):
             lp = f"{sp}.layers.{j}"
             gamma = f(lp + ".layer_scale_parameter")
             t[f"blk{blk}.dw.w"] = np.ascontiguousarray(f(lp + ".dwconv.weight").reshape(dim, 49).T)  # [49][C]
             t[f"blk{blk}.dw.b"] = f(lp + ".dwconv.bias")
             t[f"blk{blk}.ln.w"], t[f"blk{blk}.ln.b"] = f(lp + ".layernorm.weight"), f(lp + ".layernorm.bias")
-            put(f"blk{blk}.pw1", pack_linear(f(lp + ".pwconv1.weight"), f(lp + ".pwconv1.bias")))
-            put(f"blk{blk}.pw2", pack_linear(f(lp + ".pwconv2.weight") * gamma[:, None], f(lp + ".pwconv2.bias") * gamma))
+            put(f"blk{blk}.pw1", lin(f(lp + ".pwconv1.weight"), f(lp + ".pwconv1.bias")))
+            put(f"blk{blk}.pw2", lin(f(lp + ".pwconv2.weight") * gamma[:, None], f(lp + ".pwconv2.bias") * gamma))
             blk += 1
     v = "vitstr.vit"
-    put("vit.proj", pack_conv(f(v + ".embeddings.patch_embeddings.projection.weight"),
+    put("vit.proj", conv_flat(f(v + ".embeddings.patch_embeddings.projection.weight"),
                               f(v + ".embeddings.patch_embeddings.projection.bias")))
     t["vit.pos"] = np.ascontiguousarray(f(v + ".embeddings.position_embeddings")[0, 1:, :])
     L = 0
@@ -200,16 +245,16 @@ def pack_convnext_vit(sd: Mapping[str, "np.ndarray"]) -> bytes:
         lp = f"{v}.encoder.layer.{L}"
         a = lp + ".attention.attention"
         wq, bq = f(a + ".query.weight") * np.float32(0.125), f(a + ".query.bias") * np.float32(0.125)
-        put(f"vit{L}.qkv", pack_linear(np.concatenate([wq, f(a + ".key.weight"), f(a + ".value.weight")], 0),
+        put(f"vit{L}.qkv", lin(np.concatenate([wq, f(a + ".key.weight"), f(a + ".value.weight")], 0),
                                        np.concatenate([bq, f(a + ".key.bias"), f(a + ".value.bias")], 0)))
-        put(f"vit{L}.proj", pack_linear(f(lp + ".attention.output.dense.weight"), f(lp + ".attention.output.dense.bias")))
-        put(f"vit{L}.fc1", pack_linear(f(lp + ".intermediate.dense.weight"), f(lp + ".intermediate.dense.bias")))
-        put(f"vit{L}.fc2", pack_linear(f(lp + ".output.dense.weight"), f(lp + ".output.dense.bias")))
+        put(f"vit{L}.proj", lin(f(lp + ".attention.output.dense.weight"), f(lp + ".attention.output.dense.bias")))
+        put(f"vit{L}.fc1", lin(f(lp + ".intermediate.dense.weight"), f(lp + ".intermediate.dense.bias")))
+        put(f"vit{L}.fc2", lin(f(lp + ".output.dense.weight"), f(lp + ".output.dense.bias")))
         t[f"vit{L}.ln1.w"], t[f"vit{L}.ln1.b"] = f(lp + ".layernorm_before.weight"), f(lp + ".layernorm_before.bias")
         t[f"vit{L}.ln2.w"], t[f"vit{L}.ln2.b"] = f(lp + ".layernorm_after.weight"), f(lp + ".layernorm_after.bias")
         L += 1
     t["vit.ln.w"], t["vit.ln.b"] = f(v + ".layernorm.weight"), f(v + ".layernorm.bias")
-    put("cls", pack_linear(f("vitstr.classifier.weight"), f("vitstr.classifier.bias")))
+    put("cls", lin(f("vitstr.classifier.weight"), f("vitstr.classifier.bias")))
     return write_blob(t)
 
 

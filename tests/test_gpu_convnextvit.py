@@ -156,3 +156,47 @@ def test_fused_mlp_equals_two_gemm_path(monkeypatch):
         eng.close()
     assert np.array_equal(out["0"][0], out["1"][0])
     assert np.array_equal(out["0"][1], out["1"][1])
+
+
+# ---------------------------------------------------------------------------------------------- fp32x (split-fp16) mode
+PRECISE_TOL = 1e-3  # BASELINE north_star: "logits within 1e-3 fp32"
+
+
+@pytest.fixture(scope="module")
+def rec_precise():
+    sd = synth.convnext_vit_state_dict(0)
+    eng = Engine("convnext_vit", weights.pack_convnext_vit(sd, precise=True))
+    yield eng, sd
+    eng.close()
+
+
+def test_convnextvit_fp32x_meets_the_north_star_tolerance(rec_precise):
+    """precision="fp32x": every GEMM operand is a split-fp16 pair (hi + lo), three tcgen05 MMAs per product, fp32 TMEM
+    accumulation -> logits within 1e-3 of the fp32 oracle and the arg-max ids IDENTICAL to the oracle's (no margin band)."""
+    eng, sd = rec_precise
+    g = np.load(os.path.join(GOLDEN, "convnextvit_seed0.npz"))
+    n = int(g["n_crops"])
+    chunks = ref.preprocess([g[f"crop{i}"] for i in range(n)])
+    ids, logits, mx = eng.convnextvit_forward(chunks.cuda(), return_logits=True, return_max=True)
+    eng.sync()
+    err = np.abs(logits.cpu()[:, :, ::32].numpy() - g["logits_sub"]).max()
+    print(f"convnextvit fp32x golden: max |dlogit| = {err:.3e}")
+    assert err <= PRECISE_TOL
+    np.testing.assert_array_equal(ids.cpu().numpy(), g["argmax"])  # the reference module's own arg-max, every token
+    out, ln, _ = eng.ctc_collapse(ids)
+    out, ln = out.cpu().numpy(), ln.cpu().numpy()
+    for i in range(n):
+        np.testing.assert_array_equal(out[i, : ln[i]], g[f"ids{i}"])  # == the reference post-processor's strings
+    # a seeded batch spanning several passes (4 + 3 crops), the uint8 entry point included
+    eng.set_pass_crops(4)
+    rng = np.random.default_rng(21)
+    crops = (rng.random((7, 32, 300 + 252 * 2, 3)) * 255).astype(np.uint8)
+    chunks = ref.preprocess(list(crops))
+    want = ref.convnextvit_forward(sd, chunks)
+    ids8, logits8 = eng.convnextvit_forward_u8(torch.from_numpy(crops).cuda(), return_logits=True)
+    eng.sync()
+    err = float((logits8.cpu() - want).abs().max())
+    print(f"convnextvit fp32x 7 crops: max |dlogit| = {err:.3e} (logit std {float(want.std()):.2f})")
+    assert err <= PRECISE_TOL
+    np.testing.assert_array_equal(ids8.cpu().numpy(), want.argmax(-1).numpy())
+    eng.set_pass_crops(96)

@@ -121,3 +121,15 @@ def test_recognition_task_recognize_page_equals_per_crop_calls():
         corners, trans, size = predictors.crop_geometry(q)
         host_crops.append(cv2.warpPerspective(page, cv2.getPerspectiveTransform(corners, trans), size))
     assert got[:-1] == task(host_crops)
+
+
+def test_recognition_task_fp32x_strings_identical_to_reference_golden():
+    """precision="fp32x": the strings equal the reference post-processor's on every golden crop, unconditionally."""
+    g = np.load(os.path.join(GOLDEN, "convnextvit_seed0.npz"))
+    n = int(g["n_crops"])
+    vocab = [chr(0x4E00 + i) for i in range(2, 7644)]
+    task = predictors.OcrRecognitionTask(model="ConvNextViT", state_dict=synth.convnext_vit_state_dict(0), vocab=vocab, precision="fp32x")
+    res = task([g[f"crop{i}"] for i in range(n)])
+    assert res == ["".join(chr(0x4E00 + int(v)) for v in g[f"ids{i}"]) for i in range(n)]
+    with pytest.raises(RuntimeError):
+        predictors.OcrLayoutTask(model="picodet", state_dict=synth.picodet_state_dicts(0, 5), precision="fp32x")
