@@ -14,7 +14,13 @@ struct Step {
     Tensor a, b;
 };
 
+// fp32x mode (blob entry "precision", weights.pack_dbnet_r18(precise=True)): every activation tensor is a split-fp16 pair
+// ([hi(C) | lo(C)] per pixel; the padded stem image as two image batches), every weight a [W_hi | W_lo | W_hi] triple per
+// filter tap, and conv_igemm_tcgen05 walks (hi, hi, lo) k-blocks per tap: three MMAs per product, fp32 TMEM accumulation.
+// The probability map lands within 1e-3 of the fp32 oracle (tests/test_gpu_dbnet.py) where the fp16-operand default is 2.4e-3.
 struct DbNet : Model {
+    bool precise = false;
+    const float* final_w32 = nullptr;
     int N = 0, H = 0, W = 0;
     std::vector<Step> steps;
     Tensor stem_in;  // padded [N, H+6, W+8, 4]
@@ -33,14 +39,16 @@ int get_conv(Engine* e, const std::string& name, ConvSpec* cs) {
         return set_err(e, DV_ERR_WEIGHTS, "bad dtype/rank for '%s'", name.c_str());
     cs->w = reinterpret_cast<const __half*>(w->dptr);
     cs->bias = reinterpret_cast<const float*>(b->dptr);
-    const int taps = cs->KH * cs->KW;
+    const int parts = cs->split ? 3 : 1;
+    const int taps = cs->KH * cs->KW * parts;
     if (cs->stem) {
-        if (w->dims[0] != 64 || w->dims[1] != 224)
-            return set_err(e, DV_ERR_WEIGHTS, "'%s': stem weight must be [64,224]", name.c_str());
+        if (w->dims[0] != 64 || static_cast<int>(w->dims[1]) != 224 * parts)
+            return set_err(e, DV_ERR_WEIGHTS, "'%s': stem weight must be [64,%d]", name.c_str(), 224 * parts);
     } else if (static_cast<int>(w->dims[0]) != cs->Cout || (w->dims[1] % taps) != 0)
         return set_err(e, DV_ERR_WEIGHTS, "'%s': weight shape [%u,%u] does not match Cout=%d taps=%d", name.c_str(),
                        w->dims[0], w->dims[1], cs->Cout, taps);
     cs->Cin_pad = cs->stem ? 32 : static_cast<int>(w->dims[1]) / taps;
+    if (cs->split && !cs->stem && cs->KH == 1 && cs->stride == 1) cs->Cin_pad *= 3;  // flat GEMM: plan_linear counts all three parts
     if (!cs->stem) cs->BK = (cs->Cin_pad % 64 == 0) ? 64 : (cs->Cin_pad % 32 == 0) ? 32 : 16;
     if (b->dims[0] < static_cast<uint32_t>((cs->Cout + 255) / 256 * 256))
         return set_err(e, DV_ERR_WEIGHTS, "'%s': bias not padded to 256", name.c_str());
@@ -53,9 +61,12 @@ int alloc_tensor(Engine* e, DbNet* m, Tensor* t, int N, int H, int W, int C, boo
     t->W = W;
     t->C = C;
     void* p = nullptr;
-    DV_TRY(e->dalloc(&p, t->elems() * sizeof(__half), zero));
+    DV_TRY(e->dalloc(&p, t->elems() * sizeof(__half) * (m->precise ? 2 : 1), zero));
     t->p = reinterpret_cast<__half*>(p);
-    (void)m;
+    if (m->precise) {  // [hi(C) | lo(C)] per pixel
+        t->ld = 2 * C;
+        t->lo = C;
+    }
     return 0;
 }
 #define NAMED(m, name, t) (m)->named[(name)] = (t)
@@ -69,6 +80,7 @@ int add_conv(Engine* e, DbNet* m, const std::string& name, const Tensor& in, int
     cs.Cin = stem ? 3 : in.C;
     cs.Cout = cout;
     cs.stem = stem;
+    cs.split = m->precise;
     if (stem) cs.BK = 32;
     DV_TRY(get_conv(e, name, &cs));
     Step st;
@@ -82,12 +94,14 @@ int add_conv(Engine* e, DbNet* m, const std::string& name, const Tensor& in, int
 EpiSpec epi(Tensor& out, int act, const Tensor* res = nullptr, int res_mode = RES_NONE) {
     EpiSpec es;
     es.out = out.p;
-    es.out_ld = out.C;
+    es.out_ld = out.ldc();
+    es.split_off = static_cast<int>(out.lo);
     es.act = act;
     if (res) {
         es.res = res->p;
         es.res_mode = res_mode;
-        es.res_ld = res->C;
+        es.res_ld = res->ldc();
+        es.res_lo = static_cast<int>(res->lo);
     }
     return es;
 }
@@ -100,7 +114,17 @@ int build(Engine* e, DbNet* m, int N, int H, int W) {
     m->steps.clear();
     m->named.clear();
     m->flops = 0;
-    DV_TRY(alloc_tensor(e, m, &m->stem_in, N, H + 6, W + 8, 4, /*zero=*/true));
+    {  // the padded stem image is never a [hi | lo] pixel pair: fp32x keeps the lo copy as a second image batch behind it
+        const bool pr = m->precise;
+        m->precise = false;
+        int rc = alloc_tensor(e, m, &m->stem_in, pr ? 2 * N : N, H + 6, W + 8, 4, /*zero=*/true);
+        m->precise = pr;
+        if (rc) return rc;
+        if (pr) {
+            m->stem_in.N = N;
+            m->stem_in.lo = static_cast<long long>(N) * (H + 6) * (W + 8) * 4;
+        }
+    }
     Tensor c1, p1;
     DV_TRY(alloc_tensor(e, m, &c1, N, H / 2, W / 2, 64));
     DV_TRY(alloc_tensor(e, m, &p1, N, H / 4, W / 4, 64));
@@ -160,7 +184,8 @@ int build(Engine* e, DbNet* m, int N, int H, int W) {
         for (int i = 0; i < 4; ++i) {
             EpiSpec es;
             es.out = fuse.p;
-            es.out_ld = 256;
+            es.out_ld = fuse.ldc();
+            es.split_off = static_cast<int>(fuse.lo);
             es.out_coff = 64 * i;
             es.out_mode = rep[i] > 1 ? OUT_REPL : OUT_NHWC;
             es.rep = rep[i];
@@ -180,7 +205,8 @@ int build(Engine* e, DbNet* m, int N, int H, int W) {
     {
         EpiSpec es;
         es.out = b2.p;
-        es.out_ld = 64;
+        es.out_ld = b2.ldc();
+        es.split_off = static_cast<int>(b2.lo);
         es.out_mode = OUT_SHUF2;
         es.act = ACT_RELU;
         DV_TRY(add_conv(e, m, "bin.deconv1", b1, 256, 1, 1, 0, es, b1.H, b1.W));
@@ -193,6 +219,11 @@ int build(Engine* e, DbNet* m, int N, int H, int W) {
         NAMED(m, "b1", b1);
         NAMED(m, "b2", b2);
         m->final_w = reinterpret_cast<const __half*>(w->dptr);
+        if (m->precise) {
+            const BlobTensor* w32 = e->find("bin.deconv2.w32");
+            if (!w32 || w32->dtype != 0 || w32->nbytes < 256 * 4) return set_err(e, DV_ERR_WEIGHTS, "missing bin.deconv2.w32 (fp32x blob)");
+            m->final_w32 = reinterpret_cast<const float*>(w32->dptr);
+        }
         DV_CUDA(e, cudaMemcpy(&m->final_b, b->dptr, sizeof(float), cudaMemcpyDeviceToHost));
         m->last = b2;
         Step st;
@@ -207,7 +238,9 @@ int build(Engine* e, DbNet* m, int N, int H, int W) {
 }  // namespace
 
 int dbnet_create(Engine* e) {
-    e->model.reset(new DbNet());
+    DbNet* m = new DbNet();
+    m->precise = e->find("precision") != nullptr;
+    e->model.reset(m);
     return 0;
 }
 
@@ -223,7 +256,7 @@ int dbnet_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4)
         dims4[2] = t.H;
         dims4[3] = t.W;
     }
-    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw);
+    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw, t.ldc(), static_cast<int>(t.lo));
     return 0;
 }
 
@@ -244,9 +277,9 @@ int dbnet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const f
         DV_TRY(build(e, m, N, H, W));
     }
     if (in_nchw) {
-        DV_TRY(op_nchw_f32_to_stem(e, in_nchw, N, H, W, m->stem_in.p));
+        DV_TRY(op_nchw_f32_to_stem(e, in_nchw, N, H, W, m->stem_in.p, m->stem_in.lo));
     } else if (in_u8) {
-        DV_TRY(op_u8_to_stem(e, in_u8, N, H, W, mean3, std3, scale, flip, m->stem_in.p));
+        DV_TRY(op_u8_to_stem(e, in_u8, N, H, W, mean3, std3, scale, flip, m->stem_in.p, m->stem_in.lo));
     } else {
         return set_err(e, DV_ERR_ARG, "dbnet_forward: no input");
     }
@@ -254,7 +287,7 @@ int dbnet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const f
         switch (st.kind) {
             case Step::CONV: DV_TRY(launch_conv(e, st.plan)); break;
             case Step::MAXPOOL: DV_TRY(op_maxpool3x3s2(e, st.a, st.b)); break;
-            case Step::DECONV_FINAL: DV_TRY(op_deconv2x2_c1_sigmoid(e, st.a, m->final_w, m->final_b, prob_out)); break;
+            case Step::DECONV_FINAL: DV_TRY(op_deconv2x2_c1_sigmoid(e, st.a, m->final_w, m->final_w32, m->final_b, prob_out)); break;
         }
     }
     return 0;

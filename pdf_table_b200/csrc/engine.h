@@ -60,6 +60,9 @@ struct Tensor {
     __half* p = nullptr;
     int N = 0, H = 0, W = 0, C = 0;
     int ld = 0;
+    // fp32x mode: > 0 = the tensor is a split-fp16 pair, element (.., c) = hi at p[.. + c] plus lo at p[.. + c + lo]
+    // (lo = C inside a [hi | lo] pixel of ld = 2C; for the padded stem image the lo copy is a second image batch)
+    long long lo = 0;
     int ldc() const { return ld ? ld : C; }
     size_t elems() const { return static_cast<size_t>(N) * H * W * C; }
     Tensor slice(int coff, int c) const {
@@ -94,6 +97,7 @@ struct EpiSpec {
     int out_ld = 0, out_coff = 0, rep = 1, out_f32 = 0;
     const int* m_dyn = nullptr;  // A_FLAT: device row count (see IGemmParams::m_dyn)
     int split_off = 0;           // fp16 out: also store the fp16 residual at column + split_off
+    int res_lo = 0;              // fp16 residual stored as a split pair: its lo half sits res_lo columns further
 };
 
 struct ConvPlan {
@@ -177,7 +181,7 @@ struct Engine {
 int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
               ConvPlan* plan, const char* name);
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
-                ConvPlan* plan, const char* name, int lda = 0);
+                ConvPlan* plan, const char* name, int lda = 0, int lo_off = 0);
 int launch_conv(Engine* e, const ConvPlan& plan);
 // conv_win_tcgen05 (win_conv.cuh): small-channel window convolution with a load/store producer
 struct WinConvPlan {
@@ -206,7 +210,7 @@ int plan_mlp(Engine* e, const __half* h, int M, int C, const __half* w1, const f
 int launch_mlp(Engine* e, const MlpPlan& plan);
 
 // ops.cu (simple HBM-bound kernels)
-int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out);
+int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out, long long lo = 0);
 int op_warp_perspective_u8(Engine* e, const uint8_t* img, int H, int W, const double* minv, const int32_t* sizes,
                            const long long* offsets, int n, int max_pixels, uint8_t* out);
 int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off, const int32_t* src_sizes, const int32_t* dst_widths,
@@ -219,11 +223,11 @@ int op_warp_affine_rects_u8(Engine* e, const uint8_t* pages, int n_pages, int H,
                             int n, int w, int h, uint8_t* out);
 int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, int H, int W, float* out);
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
-                  float scale, int flip, __half* out);
+                  float scale, int flip, __half* out, long long lo = 0);
 int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out);
-int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, float bias, float* out);
+int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, const float* w32, float bias, float* out);
 int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out);
-int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out);
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld = 0, int lo = 0);
 
 // dbnet.cu
 int dbnet_create(Engine* e);

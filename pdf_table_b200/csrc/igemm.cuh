@@ -22,7 +22,7 @@
 namespace dv {
 
 static constexpr int kIGemmThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
-static constexpr int kMaxKB = 160;  // k-blocks per tile whose coordinate deltas are staged in smem
+static constexpr int kMaxKB = 224;  // k-blocks per tile whose coordinate deltas are staged in smem (3x3 x 512 channels x 3 split parts = 216)
 static constexpr int kMaxStages = 32;  // TMA -> MMA ring depth.  Small-K layers (BK 16 / 32: 5-16 KB stages) are latency-bound on
                                        // bytes in flight: with the former cap of 8 a Cin=16 conv kept 40 KB per SM in flight
 static constexpr int kBiasSmem = 2048;  // bias values staged in smem (layers with more padded columns read global)
@@ -243,8 +243,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         case A_PATCH_S2:
                             ptx::tma_load_5d(sa, &p.tmA, fb, d.x, x0 + d.y, d.z, y0 + d.w, img);
                             break;
-                        default:  // A_STEM: dims {32, Wo, 7, Ho, N}
-                            ptx::tma_load_5d(sa, &p.tmA, fb, 0, x0, d.z, y0, img);
+                        default:  // A_STEM: dims {32, Wo, 7, Ho, N}; d.w = image offset of the lo copy (fp32x mode)
+                            ptx::tma_load_5d(sa, &p.tmA, fb, 0, x0, d.z, y0, img + d.w);
                             break;
                     }
                     ptx::tma_load_2d(sb, &p.tmB, fb, kb * BK, n_tile * BLOCK_N);
@@ -443,6 +443,22 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                             }
                         }
                     }
+                    if (p.res_split_off > 0) {  // split residual: + its lo half
+                        const uint4* rl = reinterpret_cast<const uint4*>(res + res_pix * res_ld + col0 + p.res_split_off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j * 8 < ncol) {
+                                const uint4 u = __ldg(rl + j);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 t2 = __half22float2(h2[e]);
+                                    f[j * 8 + e * 2] += t2.x;
+                                    f[j * 8 + e * 2 + 1] += t2.y;
+                                }
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -503,12 +519,25 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                                 if (j * 4 < ncol) op[j] = o[j];
                         }
                 } else {
-                    uint4 o[4];
+                    uint4 o[4], ol[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         __half2* h2 = reinterpret_cast<__half2*>(&o[j]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                    }
+                    const int split_off = p.split_off;
+                    if (split_off > 0) {  // residual halves of the split-fp16 representation (any store pattern)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&o[j]);
+                            __half2* l2 = reinterpret_cast<__half2*>(&ol[j]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 hi = __half22float2(h2[e]);
+                                l2[e] = __floats2half2_rn(f[j * 8 + e * 2] - hi.x, f[j * 8 + e * 2 + 1] - hi.y);
+                            }
+                        }
                     }
                     for (int dy = 0; dy < reps; ++dy)
                         for (int dx = 0; dx < reps; ++dx) {
@@ -518,23 +547,13 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 if (j * 8 < ncol) op[j] = o[j];
-                        }
-                    if (p.split_off > 0) {  // residual halves of the split-fp16 representation
+                            if (split_off > 0) {
+                                uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix * out_ld + out_coff + ocol + split_off);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __half2* h2 = reinterpret_cast<__half2*>(&o[j]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 hi = __half22float2(h2[e]);
-                                h2[e] = __floats2half2_rn(f[j * 8 + e * 2] - hi.x, f[j * 8 + e * 2 + 1] - hi.y);
+                                for (int j = 0; j < 4; ++j)
+                                    if (j * 8 < ncol) lp[j] = ol[j];
                             }
                         }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + opix0 * out_ld + out_coff +
-                                                             ocol + p.split_off);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 8 < ncol) op[j] = o[j];
-                    }
                 }
             }
             if constexpr (ARGMAX) {

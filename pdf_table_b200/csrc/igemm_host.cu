@@ -140,13 +140,16 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.out_f32 = es.out_f32;
     p.m_dyn = es.m_dyn;
     p.split_off = es.split_off;
+    p.res_split_off = es.res_lo;
+    if (es.res_lo && (es.res_f32 || es.res_mode == RES_NONE || (es.res_lo % 8)))
+        return set_err(e, DV_ERR_ARG, "%s: split residual needs an fp16 residual and res_lo %% 8 == 0", name);
     p.res_red = (es.res_f32 && es.out_f32 && es.res != nullptr && es.res == es.out && es.res_mode == RES_SAME && es.res_mod == 0 &&
                  es.res_ld == es.out_ld && es.out_coff == 0 && es.out_mode == OUT_NHWC && es.act == ACT_NONE && es.arg_out == nullptr &&
                  !(getenv("DV_RES_RED") && atoi(getenv("DV_RES_RED")) == 0))
                     ? 1 : 0;
     if (es.m_dyn && p.mode != A_FLAT) return set_err(e, DV_ERR_ARG, "%s: m_dyn needs a flat GEMM", name);
-    if (es.split_off && (es.out_f32 || es.out_mode != OUT_NHWC || (es.split_off % 8)))
-        return set_err(e, DV_ERR_ARG, "%s: split store needs fp16 NHWC output and split_off %% 8 == 0", name);
+    if (es.split_off && (es.out_f32 || (es.split_off % 8)))
+        return set_err(e, DV_ERR_ARG, "%s: split store needs fp16 output and split_off %% 8 == 0", name);
     if (num_kb > kMaxKB) return set_err(e, DV_ERR_UNSUPPORTED, "%s: %d k-blocks > %d", name, num_kb, kMaxKB);
     {
         const int al = es.out_f32 ? 4 : 8;
@@ -180,8 +183,9 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
         if (es.out_mode == OUT_REPL) out_elems *= (double)es.rep * es.rep;
         plan->bytes += (double)ktot * cs.Cout * 2 + out_elems * (es.out_f32 ? 4 : 2);
         if (es.arg_out != nullptr) plan->bytes += m_rows * 8 - (es.out == nullptr ? out_elems * 4 : 0);
-        if (es.res_mode == RES_SAME) plan->bytes += (es.res_mod > 0 ? (double)es.res_mod : m_rows) * cs.Cout * (es.res_f32 ? 4 : 2);
-        if (es.res_mode == RES_UP2) plan->bytes += m_rows * cs.Cout * 2 / 4;
+        if (es.split_off) plan->bytes += out_elems * 2;
+        if (es.res_mode == RES_SAME) plan->bytes += (es.res_mod > 0 ? (double)es.res_mod : m_rows) * cs.Cout * (es.res_f32 ? 4 : (es.res_lo ? 4 : 2));
+        if (es.res_mode == RES_UP2) plan->bytes += m_rows * cs.Cout * (es.res_lo ? 4 : 2) / 4;
     }
     const int total = p.n_inner ? p.m_tiles : p.m_tiles * p.n_tiles;
     plan->grid = total < e->num_sms ? total : e->num_sms;
@@ -190,13 +194,16 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
 }
 
 int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, const EpiSpec& es,
-                ConvPlan* plan, const char* name, int lda) {
+                ConvPlan* plan, const char* name, int lda, int lo_off) {
     memset(&plan->prm, 0, sizeof(plan->prm));
     plan->bytes = 0;
     IGemmParams& p = plan->prm;
     if (K % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: K %% 8 != 0", name);
-    // split-fp16: A holds [hi | lo] (2K columns); the k-block list walks hi, hi, lo against W = [W_hi | W_lo | W_hi]
-    const int a_cols = cs.split ? 2 * K : K;
+    // split-fp16: A holds [hi | lo] (lo_off columns apart, K by default); the k-block list walks hi, hi, lo against
+    // W = [W_hi | W_lo | W_hi]
+    if (cs.split && lo_off == 0) lo_off = K;
+    if (cs.split && (lo_off < K || (lo_off % 8))) return set_err(e, DV_ERR_ARG, "%s: bad lo offset %d", name, lo_off);
+    const int a_cols = cs.split ? lo_off + K : K;
     if (lda == 0) lda = a_cols;
     if ((lda % 8) || lda < a_cols || (reinterpret_cast<uintptr_t>(A) & 15))
         return set_err(e, DV_ERR_UNSUPPORTED, "%s: A row stride %d / alignment", name, lda);
@@ -226,7 +233,7 @@ int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, co
         int col = kb * cs.BK;
         if (cs.split) {
             const int part = kb / kb_per, k = (kb - part * kb_per) * cs.BK;
-            col = part == 2 ? K + k : k;
+            col = part == 2 ? lo_off + k : k;
         }
         deltas[kb] = make_int4(col, 0, 0, 0);
     }
@@ -238,7 +245,8 @@ int plan_linear(Engine* e, const __half* A, int M, int K, const ConvSpec& cs, co
 int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es, int Ho, int Wo,
               ConvPlan* plan, const char* name) {
     if (cs.flat || (cs.KH == 1 && cs.KW == 1 && cs.stride == 1 && cs.pad == 0 && !cs.stem)) {
-        int rc = plan_linear(e, in.p, in.N * in.H * in.W, in.C, cs, es, plan, name, in.ldc());
+        if (cs.split != (in.lo > 0)) return set_err(e, DV_ERR_ARG, "%s: split weights need a split input (and vice versa)", name);
+        int rc = plan_linear(e, in.p, in.N * in.H * in.W, in.C, cs, es, plan, name, in.ldc(), static_cast<int>(in.lo));
         if (rc == 0) {
             plan->prm.Nimg = in.N;
             plan->prm.Ho = in.H;
@@ -269,27 +277,38 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         const uint64_t pitch = static_cast<uint64_t>(in.W) * cpp * 2;
         if (in.W < st * (Wo - 1) + 8 || in.H < st * (Ho - 1) + 7 || (pitch % 16))
             return set_err(e, DV_ERR_ARG, "%s: padded stem input too small", name);
+        // fp32x: the lo copy of the padded image is a second batch of N images right behind the first
+        if (cs.split != (in.lo > 0) || (in.lo && in.lo != static_cast<long long>(in.N) * in.H * in.W * cpp))
+            return set_err(e, DV_ERR_ARG, "%s: split stem needs the lo images stacked behind the hi images", name);
         uint64_t dims[5] = {static_cast<uint64_t>(win), static_cast<uint64_t>(Wo), 7, static_cast<uint64_t>(Ho),
-                            static_cast<uint64_t>(in.N)};
+                            static_cast<uint64_t>(in.N) * (cs.split ? 2 : 1)};
         uint64_t str[4] = {16, pitch, static_cast<uint64_t>(st) * pitch, pitch * in.H};
         uint32_t box[5] = {static_cast<uint32_t>(win), static_cast<uint32_t>(p.TW), 1, static_cast<uint32_t>(p.TH), 1};
         DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
-        num_kb = 7;
-        for (int r = 0; r < 7; ++r) deltas.push_back(make_int4(0, 0, r, 0));
-        plan->flops = 2.0 * in.N * Ho * Wo * 147.0 * cs.Cout;
-        plan->bytes = 2.0 * in.N * in.H * in.W * cpp;
+        for (int r = 0; r < 7; ++r)
+            for (int part = 0; part < (cs.split ? 3 : 1); ++part) deltas.push_back(make_int4(0, 0, r, part == 2 ? in.N : 0));
+        num_kb = static_cast<int>(deltas.size());
+        plan->flops = 2.0 * in.N * Ho * Wo * 147.0 * cs.Cout * (cs.split ? 3 : 1);
+        plan->bytes = 2.0 * in.N * in.H * in.W * cpp * (cs.split ? 2 : 1);
     } else {
         if (in.C != cs.Cin) return set_err(e, DV_ERR_ARG, "%s: Cin mismatch %d vs %d", name, in.C, cs.Cin);
         if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "%s: Cin %% 8 != 0", name);
+        // cs.Cin_pad = packed channels per (tap, part): split weights hold 3 parts [W_hi | W_lo | W_hi] per tap
         const int cin_blocks = cs.Cin_pad / cs.BK;
         if (cin_blocks * cs.BK != cs.Cin_pad || cs.Cin_pad < cs.Cin)
             return set_err(e, DV_ERR_WEIGHTS, "%s: bad Cin_pad", name);
+        const int parts = cs.split ? 3 : 1;
+        const int lo = static_cast<int>(in.lo);
+        if (cs.split != (in.lo > 0)) return set_err(e, DV_ERR_ARG, "%s: split weights need a split input (and vice versa)", name);
+        if (cs.split && ((in.C % cs.BK) || (lo % 8) || lo < in.C || lo + in.C > in.ldc()))
+            return set_err(e, DV_ERR_UNSUPPORTED, "%s: split conv needs BK | Cin and the lo half inside the pixel", name);
+        const int c_extent = cs.split ? lo + in.C : in.C;  // channels the A map must reach from the slice start
         const uint64_t cb = static_cast<uint64_t>(in.ldc()) * 2;  // bytes between consecutive pixels
         if ((in.ldc() % 8) || (reinterpret_cast<uintptr_t>(in.p) & 15))
             return set_err(e, DV_ERR_UNSUPPORTED, "%s: input slice must be 16-byte aligned (ld %% 8, offset %% 8)", name);
         static const int halo_env = getenv("DV_HALO") ? atoi(getenv("DV_HALO")) : 0;  // opt-in until its pipeline depth is tuned (profiles/r1f)
         static const int halo_baseoff = getenv("DV_HALO_BASEOFF") ? atoi(getenv("DV_HALO_BASEOFF")) : 0;  // measured on B200: the swizzle is a function of the absolute shared-memory address, shifted starts need NO base offset
-        if (cs.stride == 1 && cs.KH == 3 && cs.KW == 3 && cs.pad == 1 && halo_env) {
+        if (cs.stride == 1 && cs.KH == 3 && cs.KW == 3 && cs.pad == 1 && halo_env && !cs.split) {
             // halo-patch mode: 16 x 8 output pixels per tile, one {BK, 16, 18} box per channel block
             p.mode = A_HALO;
             p.TH = 16;
@@ -307,7 +326,7 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
             for (int t = 0; t < 9 * cin_blocks; ++t) deltas.push_back(make_int4(0, 0, 0, 0));  // unused by the halo path
         } else if (cs.stride == 1) {
             p.mode = A_PATCH;
-            uint64_t dims[5] = {static_cast<uint64_t>(in.C), static_cast<uint64_t>(in.W),
+            uint64_t dims[5] = {static_cast<uint64_t>(c_extent), static_cast<uint64_t>(in.W),
                                 static_cast<uint64_t>(in.H), static_cast<uint64_t>(in.N), 1};
             uint64_t str[4] = {cb, cb * in.W, cb * in.W * in.H, cb * in.W * in.H * in.N};
             uint32_t box[5] = {static_cast<uint32_t>(cs.BK), static_cast<uint32_t>(p.TW),
@@ -315,13 +334,15 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
             DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
             for (int r = 0; r < cs.KH; ++r)
                 for (int s = 0; s < cs.KW; ++s)
-                    for (int c = 0; c < cin_blocks; ++c)
-                        deltas.push_back(make_int4(c * cs.BK, s - cs.pad, r - cs.pad, 0));
+                    for (int part = 0; part < parts; ++part)
+                        for (int c = 0; c < cin_blocks; ++c)
+                            deltas.push_back(make_int4((part == 2 ? lo : 0) + c * cs.BK, s - cs.pad, r - cs.pad, 0));
         } else if (cs.stride == 2) {
-            if ((in.H & 1) || (in.W & 1) || (cs.Cin % cs.BK) || in.ld != 0)
+            if ((in.H & 1) || (in.W & 1) || (cs.Cin % cs.BK) || (in.ld != 0 && in.ld != c_extent))
                 return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride-2 needs even H,W, BK | Cin and a dense input", name);
             p.mode = A_PATCH_S2;
-            uint64_t dims[5] = {static_cast<uint64_t>(2 * in.C), static_cast<uint64_t>(in.W / 2), 2,
+            const int pix_c = in.ldc();  // channels per pixel (2C for a split pair)
+            uint64_t dims[5] = {static_cast<uint64_t>(2 * pix_c), static_cast<uint64_t>(in.W / 2), 2,
                                 static_cast<uint64_t>(in.H / 2), static_cast<uint64_t>(in.N)};
             uint64_t str[4] = {2 * cb, cb * in.W, 2 * cb * in.W, cb * in.W * in.H};
             uint32_t box[5] = {static_cast<uint32_t>(cs.BK), static_cast<uint32_t>(p.TW), 1,
@@ -329,17 +350,18 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
             DV_TRY(encode_map(e, &p.tmA, in.p, 5, dims, str, box, row_bytes, name));
             for (int r = 0; r < cs.KH; ++r)
                 for (int s = 0; s < cs.KW; ++s)
-                    for (int c = 0; c < cin_blocks; ++c) {
-                        const int xi = s - cs.pad, yi = r - cs.pad;
-                        const int px = xi & 1, py = yi & 1;
-                        deltas.push_back(make_int4(px * in.C + c * cs.BK, (xi - px) / 2, py, (yi - py) / 2));
-                    }
+                    for (int part = 0; part < parts; ++part)
+                        for (int c = 0; c < cin_blocks; ++c) {
+                            const int xi = s - cs.pad, yi = r - cs.pad;
+                            const int px = xi & 1, py = yi & 1;
+                            deltas.push_back(make_int4(px * pix_c + (part == 2 ? lo : 0) + c * cs.BK, (xi - px) / 2, py, (yi - py) / 2));
+                        }
         } else {
             return set_err(e, DV_ERR_UNSUPPORTED, "%s: stride %d", name, cs.stride);
         }
         num_kb = static_cast<int>(deltas.size());
-        plan->flops = 2.0 * in.N * Ho * Wo * (double)cs.KH * cs.KW * cs.Cin * cs.Cout;
-        plan->bytes = 2.0 * in.N * in.H * in.W * in.C;
+        plan->flops = 2.0 * in.N * Ho * Wo * (double)cs.KH * cs.KW * cs.Cin * cs.Cout * parts;
+        plan->bytes = 2.0 * in.N * in.H * in.W * in.C * (cs.split ? 2 : 1);
     }
     return finish_plan(e, plan, cs, es, num_kb, deltas, name);
 }

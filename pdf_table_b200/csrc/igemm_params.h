@@ -53,6 +53,8 @@ struct IGemmParams {
     // fp16 output only, > 0: also store lo = fp16(v - fp32(fp16(v))) at column + split_off, so the consumer
     // GEMM can run the 3-term split-fp16 product (plan_linear_split) at ~fp32 accuracy.
     int split_off;
+    // fp16 residual stored as a split pair: > 0 = add the lo half found res_split_off columns after the hi half
+    int res_split_off;
 };
 
 }  // namespace dv

@@ -7,7 +7,25 @@ namespace dv {
 static inline int grid_for(long long n, int block) { return static_cast<int>((n + block - 1) / block); }
 
 // fp32 NCHW [N,3,H,W] -> zero-bordered fp16 [N,H+6,W+8,4] (interior at +3,+3; channel 3 = 0)
-__global__ void k_nchw_f32_to_stem(const float* __restrict__ in, int N, int H, int W, __half* __restrict__ out) {
+// fp32x: lo > 0 = also write the residual halves fp16(v - hi) into a second image batch `lo` elements further
+__device__ __forceinline__ void store_stem_px(__half* op, long long lo, float v0, float v1, float v2) {
+    const __half2 a = __floats2half2_rn(v0, v1);
+    const __half2 b = __floats2half2_rn(v2, 0.f);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(op) = u;
+    if (lo > 0) {
+        const float2 fa = __half22float2(a);
+        const __half2 la = __floats2half2_rn(v0 - fa.x, v1 - fa.y);
+        const __half2 lb = __floats2half2_rn(v2 - __low2float(b), 0.f);
+        u.x = *reinterpret_cast<const uint32_t*>(&la);
+        u.y = *reinterpret_cast<const uint32_t*>(&lb);
+        *reinterpret_cast<uint2*>(op + lo) = u;
+    }
+}
+
+__global__ void k_nchw_f32_to_stem(const float* __restrict__ in, int N, int H, int W, __half* __restrict__ out, long long lo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * H * W;
     if (idx >= total) return;
@@ -16,19 +34,14 @@ __global__ void k_nchw_f32_to_stem(const float* __restrict__ in, int N, int H, i
     const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
     const long long plane = static_cast<long long>(H) * W;
     const float* ip = in + static_cast<long long>(n) * 3 * plane + static_cast<long long>(y) * W + x;
-    const __half2 a = __floats2half2_rn(ip[0], ip[plane]);
-    const __half2 b = __floats2half2_rn(ip[2 * plane], 0.f);
     const int Hp = H + 6, Wp = W + 8;
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&a);
-    u.y = *reinterpret_cast<const uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4) = u;
+    store_stem_px(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4, lo, ip[0], ip[plane], ip[2 * plane]);
 }
 
-int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out) {
+int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out, long long lo) {
     const long long total = static_cast<long long>(N) * H * W;
-    e->launch_begin("k_nchw_f32_to_stem", "pre", 0.0, total * (12.0 + 8.0));
-    k_nchw_f32_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, H, W, out);
+    e->launch_begin("k_nchw_f32_to_stem", "pre", 0.0, total * (12.0 + (lo ? 16.0 : 8.0)));
+    k_nchw_f32_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, H, W, out, lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -38,7 +51,7 @@ int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half*
 // (reference db_pp/image_operators.py:93-102): (x * scale - mean[c]) / std[c] in fp32, applied to the
 // channel-flipped image (processor_ocr_db_pp.py:124) when flip != 0.
 __global__ void k_u8_to_stem(const uint8_t* __restrict__ in, int N, int H, int W, float3 mean, float3 stdv,
-                             float scale, int flip, __half* __restrict__ out) {
+                             float scale, int flip, __half* __restrict__ out, long long lo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * H * W;
     if (idx >= total) return;
@@ -56,13 +69,8 @@ __global__ void k_u8_to_stem(const uint8_t* __restrict__ in, int N, int H, int W
     const float v0 = __fdiv_rn(__fsub_rn(__fmul_rn(c0, scale), mean.x), stdv.x);
     const float v1 = __fdiv_rn(__fsub_rn(__fmul_rn(c1, scale), mean.y), stdv.y);
     const float v2 = __fdiv_rn(__fsub_rn(__fmul_rn(c2, scale), mean.z), stdv.z);
-    const __half2 a = __floats2half2_rn(v0, v1);
-    const __half2 b = __floats2half2_rn(v2, 0.f);
     const int Hp = H + 6, Wp = W + 8;
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&a);
-    u.y = *reinterpret_cast<const uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4) = u;
+    store_stem_px(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 4, lo, v0, v1, v2);
 }
 
 // PP-OCR recogniser pre-process after the host cv2.resize: PPOcrRecPreProcessor.resize_norm_img
@@ -99,12 +107,12 @@ int op_pp_rec_norm(Engine* e, const uint8_t* in, const int32_t* widths, int B, i
 }
 
 int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float* mean3, const float* std3,
-                  float scale, int flip, __half* out) {
+                  float scale, int flip, __half* out, long long lo) {
     const long long total = static_cast<long long>(N) * H * W;
-    e->launch_begin("k_u8_to_stem", "pre", 0.0, total * (3.0 + 8.0));
+    e->launch_begin("k_u8_to_stem", "pre", 0.0, total * (3.0 + (lo ? 16.0 : 8.0)));
     k_u8_to_stem<<<grid_for(total, 256), 256, 0, e->stream>>>(
         in, N, H, W, make_float3(mean3[0], mean3[1], mean3[2]), make_float3(std3[0], std3[1], std3[2]), scale,
-        flip, out);
+        flip, out, lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -147,8 +155,67 @@ __global__ void k_maxpool3x3s2(const __half* __restrict__ in, int N, int H, int 
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + c8 * 8) = o;
 }
 
+// fp32x variant: pixels are [hi(C) | lo(C)] pairs; the maximum is taken over hi + lo in fp32 and stored as a pair again
+__global__ void k_maxpool3x3s2_split(const __half* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo,
+                                     __half* __restrict__ out) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+    if (idx >= total) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+        const int iy = 2 * oy - 1 + r;
+        if (iy < 0 || iy >= H) continue;
+        for (int s = 0; s < 3; ++s) {
+            const int ix = 2 * ox - 1 + s;
+            if (ix < 0 || ix >= W) continue;
+            const __half* ip = in + ((static_cast<long long>(n) * H + iy) * W + ix) * 2 * C + c8 * 8;
+            const uint4 uh = __ldg(reinterpret_cast<const uint4*>(ip));
+            const uint4 ul = __ldg(reinterpret_cast<const uint4*>(ip + C));
+            const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+            const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = __half22float2(hh[i]), b = __half22float2(hl[i]);
+                m[2 * i] = fmaxf(m[2 * i], a.x + b.x);
+                m[2 * i + 1] = fmaxf(m[2 * i + 1], a.y + b.y);
+            }
+        }
+    }
+    uint4 oh, ol;
+    __half2* ph = reinterpret_cast<__half2*>(&oh);
+    __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ph[i] = __floats2half2_rn(m[2 * i], m[2 * i + 1]);
+        const float2 f = __half22float2(ph[i]);
+        pl[i] = __floats2half2_rn(m[2 * i] - f.x, m[2 * i + 1] - f.y);
+    }
+    __half* op = out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * 2 * C + c8 * 8;
+    *reinterpret_cast<uint4*>(op) = oh;
+    *reinterpret_cast<uint4*>(op + C) = ol;
+}
+
 int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out) {
     if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "maxpool: C %% 8 != 0");
+    if (in.lo > 0) {
+        if (in.lo != in.C || in.ldc() != 2 * in.C || out.lo != out.C || out.ldc() != 2 * out.C)
+            return set_err(e, DV_ERR_UNSUPPORTED, "maxpool: split tensors must be dense [hi | lo] pixels");
+        const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+        e->launch_begin("k_maxpool3x3s2", "maxpool", 0.0, 4.0 * (double)in.elems() + 4.0 * (double)out.N * out.H * out.W * in.C);
+        k_maxpool3x3s2_split<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, out.H, out.W, out.p);
+        e->launch_end();
+        DV_CUDA(e, cudaGetLastError());
+        return 0;
+    }
     const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
     e->launch_begin("k_maxpool3x3s2", "maxpool", 0.0, 2.0 * (double)in.elems() + 2.0 * (double)out.N * out.H * out.W * in.C);
     k_maxpool3x3s2<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, out.H, out.W, out.p);
@@ -159,10 +226,12 @@ int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out) {
 
 // ConvTranspose2d(64 -> 1, k=2, s=2) + bias + sigmoid: each input pixel produces a 2x2 block of the
 // fp32 probability map (reference db_net/dbnet.py:539). One thread per input pixel; weights w[c][dy*2+dx].
+// SPLIT (fp32x): input pixels are [hi(64) | lo(64)] pairs and the weights come as fp32 (w32).
+template <bool SPLIT>
 __global__ void k_deconv2x2_c1_sigmoid(const __half* __restrict__ in, long long npix, int H, int W,
-                                       const __half* __restrict__ w, float bias, float* __restrict__ out) {
+                                       const __half* __restrict__ w, const float* __restrict__ w32, float bias, float* __restrict__ out) {
     __shared__ float sw[64 * 4];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sw[i] = __half2float(w[i]);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sw[i] = SPLIT ? w32[i] : __half2float(w[i]);
     __syncthreads();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= npix) return;
@@ -170,14 +239,22 @@ __global__ void k_deconv2x2_c1_sigmoid(const __half* __restrict__ in, long long 
     const int y = static_cast<int>((idx / W) % H);
     const long long n = idx / (static_cast<long long>(W) * H);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const uint4* ip = reinterpret_cast<const uint4*>(in + idx * 64);
+    const uint4* ip = reinterpret_cast<const uint4*>(in + idx * (SPLIT ? 128 : 64));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint4 u = __ldg(ip + j);
         const __half2* h = reinterpret_cast<const __half2*>(&u);
+        uint4 ul = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (SPLIT) ul = __ldg(ip + 8 + j);
+        const __half2* hl = reinterpret_cast<const __half2*>(&ul);
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 f = __half22float2(h[e2]);
+            float2 f = __half22float2(h[e2]);
+            if constexpr (SPLIT) {
+                const float2 g = __half22float2(hl[e2]);
+                f.x += g.x;
+                f.y += g.y;
+            }
             const int c = j * 8 + e2 * 2;
             a0 = fmaf(f.x, sw[c * 4 + 0], a0);
             a1 = fmaf(f.x, sw[c * 4 + 1], a1);
@@ -199,11 +276,13 @@ __global__ void k_deconv2x2_c1_sigmoid(const __half* __restrict__ in, long long 
     *reinterpret_cast<float2*>(op + W2) = make_float2(s2, s3);
 }
 
-int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, float bias, float* out) {
+int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, const float* w32, float bias, float* out) {
     if (in.C != 64) return set_err(e, DV_ERR_UNSUPPORTED, "deconv2x2_c1: C != 64");
+    if (in.lo > 0 && (in.lo != 64 || in.ldc() != 128 || !w32)) return set_err(e, DV_ERR_UNSUPPORTED, "deconv2x2_c1: split input needs [hi | lo] pixels and fp32 weights");
     const long long npix = static_cast<long long>(in.N) * in.H * in.W;
-    e->launch_begin("k_deconv2x2_c1_sigmoid", "bin.deconv2", 2.0 * npix * 64 * 4, npix * (128.0 + 16.0));
-    k_deconv2x2_c1_sigmoid<<<grid_for(npix, 128), 128, 0, e->stream>>>(in.p, npix, in.H, in.W, w, bias, out);
+    e->launch_begin("k_deconv2x2_c1_sigmoid", "bin.deconv2", 2.0 * npix * 64 * 4, npix * ((in.lo ? 256.0 : 128.0) + 16.0));
+    if (in.lo > 0) k_deconv2x2_c1_sigmoid<true><<<grid_for(npix, 128), 128, 0, e->stream>>>(in.p, npix, in.H, in.W, w, w32, bias, out);
+    else k_deconv2x2_c1_sigmoid<false><<<grid_for(npix, 128), 128, 0, e->stream>>>(in.p, npix, in.H, in.W, w, w32, bias, out);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -224,7 +303,7 @@ __global__ void k_nchw_f32_to_nhwc_f16(const float* __restrict__ in, int N, int 
     out[idx] = __float2half_rn(in[((static_cast<long long>(n) * C + c) * H + y) * W + x]);
 }
 __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int C, int H, int W,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, int ld, int lo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * C * H * W;
     if (idx >= total) return;
@@ -234,7 +313,8 @@ __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int
     t /= H;
     const int c = static_cast<int>(t % C);
     const int n = static_cast<int>(t / C);
-    out[idx] = __half2float(in[((static_cast<long long>(n) * H + y) * W + x) * C + c]);
+    const __half* ip = in + ((static_cast<long long>(n) * H + y) * W + x) * ld + c;
+    out[idx] = __half2float(ip[0]) + (lo ? __half2float(ip[lo]) : 0.f);
 }
 int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out) {
     const long long total = static_cast<long long>(N) * C * H * W;
@@ -244,10 +324,10 @@ int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
-int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out) {
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld, int lo) {
     const long long total = static_cast<long long>(N) * C * H * W;
     e->launch_begin("k_nhwc_f16_to_nchw_f32", "layout", 0.0, total * 6.0);
-    k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out);
+    k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out, ld ? ld : C, lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -393,6 +393,7 @@ class OcrDetectionTask(BaseInferTask):
 
     Returns list[np.ndarray [n, 8]] like the reference (:135-141)."""
 
+    SUPPORTS_FP32X = True
     MEAN = (0.485, 0.456, 0.406)
     STD = (0.229, 0.224, 0.225)
     DB_MEAN = (123.68, 116.78, 103.94)  # OCRDetectionPreprocessor.normalize (db_net/processor_ocr_dbnet.py:59-62)
@@ -411,7 +412,7 @@ class OcrDetectionTask(BaseInferTask):
         super().__init__(task=task, model=model, **kwargs)
 
     def _construct_model(self, model):
-        self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd), device=self.device)
+        self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
 
     def _norm(self):

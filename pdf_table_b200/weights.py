@@ -101,20 +101,22 @@ def pack_linear(weight, bias=None) -> Tuple[np.ndarray, np.ndarray]:
     return pack_conv(w[:, :, None, None], bias)
 
 
-def pack_stem7x7(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+def pack_stem7x7(weight, bn=None, split: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """7x7 stride-2 stem on a 3-channel image: K index = r*32 + s*4 + c (s padded 7->8, c padded 3->4),
-    matching the overlapping-window TMA view of the padded 4-channel input (csrc/igemm_host.cu, A_STEM)."""
+    matching the overlapping-window TMA view of the padded 4-channel input (csrc/igemm_host.cu, A_STEM).
+    split: fp32x triples per filter row (``split_packed``)."""
     w = _np(weight).astype(np.float32)
     cout, cin, kh, kw = w.shape
     assert (cin, kh, kw) == (3, 7, 7), w.shape
     scale, shift = bn_affine(bn, cout)
     w = w * scale[:, None, None, None]
-    packed = np.zeros((cout, 7, 8, 4), np.float16)
-    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1).astype(np.float16)
-    return packed.reshape(cout, 7 * 32), pad_bias(shift)
+    packed = np.zeros((cout, 7, 8, 4), np.float32)
+    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1)
+    packed = packed.reshape(cout, 7 * 32)
+    return (split_packed(packed, 7) if split else packed.astype(np.float16)), pad_bias(shift)
 
 
-def pack_deconv2x2(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+def pack_deconv2x2(weight, bias=None, bn=None, split: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """ConvTranspose2d(k=2,s=2) weight [Cin,Cout,2,2] -> GEMM weight [(dy*2+dx)*Cout + co][Cin_pad]
     whose output is pixel-shuffled by the epilogue (OUT_SHUF2)."""
     w = _np(weight).astype(np.float32)
@@ -124,10 +126,11 @@ def pack_deconv2x2(weight, bias=None, bn=None) -> Tuple[np.ndarray, np.ndarray]:
     b = np.zeros(cout, np.float32) if bias is None else _np(bias).astype(np.float32)
     b = b * scale + shift
     cp = cin_pad_of(cin)
-    packed = np.zeros((4, cout, cp), np.float16)
+    packed = np.zeros((4, cout, cp), np.float32)
     # w[ci, co, dy, dx] -> [q=dy*2+dx, co, ci]
-    packed[:, :, :cin] = (w * scale[None, :, None, None]).transpose(2, 3, 1, 0).reshape(4, cout, cin).astype(np.float16)
-    return packed.reshape(4 * cout, cp), pad_bias(np.tile(b, 4))
+    packed[:, :, :cin] = (w * scale[None, :, None, None]).transpose(2, 3, 1, 0).reshape(4, cout, cin)
+    packed = packed.reshape(4 * cout, cp)
+    return (split_packed(packed, 1) if split else packed.astype(np.float16)), pad_bias(np.tile(b, 4))
 
 
 def write_blob(tensors: Mapping[str, np.ndarray]) -> bytes:
@@ -162,14 +165,18 @@ def _bn(sd, prefix):
     return {k: _np(sd[f"{prefix}.{k}"]) for k in ("weight", "bias", "running_mean", "running_var")}
 
 
-def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"]) -> bytes:
-    """state_dict of the reference DBModel (db_net/dbnet.py:715-728; keys backbone.* / decoder.*)."""
+def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> bytes:
+    """state_dict of the reference DBModel (db_net/dbnet.py:715-728; keys backbone.* / decoder.*).  precise=True packs every
+    weight as a split-fp16 triple per filter tap and marks the blob with a "precision" entry (fp32x mode, csrc/dbnet.cu)."""
     t: Dict[str, np.ndarray] = {}
 
     def put(name, wb):
         t[name + ".w"], t[name + ".b"] = wb
 
-    put("stem", pack_stem7x7(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1")))
+    pack_conv = pack_conv_split if precise else globals()["pack_conv"]
+    if precise:
+        t["precision"] = np.array([1], np.int32)
+    put("stem", pack_stem7x7(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1"), split=precise))
     for L in range(1, 5):
         for B in range(2):
             p = f"backbone.layer{L}.{B}"
@@ -183,9 +190,11 @@ def pack_dbnet_r18(sd: Mapping[str, "np.ndarray"]) -> bytes:
         put(n, pack_conv(sd[f"decoder.{n}.0.weight"], sd.get(f"decoder.{n}.0.bias")))
     put("out2", pack_conv(sd["decoder.out2.weight"], sd.get("decoder.out2.bias")))
     put("bin.conv", pack_conv(sd["decoder.binarize.0.weight"], sd.get("decoder.binarize.0.bias"), _bn(sd, "decoder.binarize.1")))
-    put("bin.deconv1", pack_deconv2x2(sd["decoder.binarize.3.weight"], sd["decoder.binarize.3.bias"], _bn(sd, "decoder.binarize.4")))
+    put("bin.deconv1", pack_deconv2x2(sd["decoder.binarize.3.weight"], sd["decoder.binarize.3.bias"], _bn(sd, "decoder.binarize.4"), split=precise))
     w2 = _np(sd["decoder.binarize.6.weight"]).astype(np.float32)  # [64,1,2,2]
     t["bin.deconv2.w"] = w2.reshape(64, 4).astype(np.float16)
+    if precise:
+        t["bin.deconv2.w32"] = np.ascontiguousarray(w2.reshape(64, 4))
     t["bin.deconv2.b"] = _np(sd["decoder.binarize.6.bias"]).astype(np.float32).reshape(1)
     return write_blob(t)
 

@@ -74,3 +74,46 @@ def test_dbnet_u8_preprocess_fused(dbnet):
     a = eng.dbnet_forward(x.cuda()).cpu().numpy()
     b = eng.dbnet_forward_u8(torch.from_numpy(page[None]).cuda(), mean, std, 1.0 / 255.0, True).cpu().numpy()
     np.testing.assert_array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- fp32x (split-fp16) mode
+PRECISE_TOL = 1e-3  # BASELINE north_star: "logits within 1e-3 fp32", read on the probability map
+
+
+@pytest.fixture(scope="module")
+def dbnet_precise():
+    sd = synth.dbnet_r18_state_dict(0)
+    eng = Engine("dbnet_r18", weights.pack_dbnet_r18(sd, precise=True))
+    yield eng, sd
+    eng.close()
+
+
+def test_dbnet_fp32x_meets_the_north_star_tolerance(dbnet_precise):
+    """precision="fp32x": split-fp16 activation pairs and weight triples through every conv (stem, 3x3 s1 / s2, 1x1, the two
+    transposed convs, the nearest-up-sampled residuals and concat stores) -> |dprob| <= 1e-3 against the reference module's
+    golden output and the fp32 oracle; the binarised map at the CLI threshold is identical outside a 1e-3 band."""
+    eng, sd = dbnet_precise
+    g = np.load(os.path.join(GOLDEN, "dbnet_r18_seed0.npz"))
+    x = torch.from_numpy(g["x"])
+    err = np.abs(eng.dbnet_forward(x.cuda()).cpu().numpy() - g["prob"])
+    print("dbnet fp32x golden: max |dprob| = %.3e" % err.max())
+    assert err.max() <= PRECISE_TOL, f"max |dprob| = {err.max()}\n" + _layerwise_report(eng, sd, x)
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((3, 3, 160, 224)).astype(np.float32))
+    want = dbnet_ref.dbnet_r18_forward(sd, x).numpy()
+    got = eng.dbnet_forward(x.cuda()).cpu().numpy()
+    err = np.abs(got - want)
+    print("dbnet fp32x batch: max |dprob| = %.3e, mean = %.3e" % (err.max(), err.mean()))
+    assert err.max() <= PRECISE_TOL, f"max |dprob| = {err.max()}\n" + _layerwise_report(eng, sd, x)
+    disagree = (got > 0.2) != (want > 0.2)
+    assert (np.abs(want[disagree] - 0.2) <= PRECISE_TOL).all()
+    # the uint8 page entry point (fused normalisation -> hi / lo stem images) takes the same path
+    page = synth.synthetic_page(0, 96, 128)
+    mean = np.array([0.485, 0.456, 0.406], np.float32)
+    std = np.array([0.229, 0.224, 0.225], np.float32)
+    img = (page[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean.reshape(1, 1, 3)) / std.reshape(1, 1, 3)
+    xs = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
+    a = eng.dbnet_forward(xs.cuda()).cpu().numpy()
+    b = eng.dbnet_forward_u8(torch.from_numpy(page[None]).cuda(), mean, std, 1.0 / 255.0, True).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(a - dbnet_ref.dbnet_r18_forward(sd, xs).numpy()).max() <= PRECISE_TOL
