@@ -58,6 +58,7 @@ LORE_HM_BIAS = (-0.3, -3.5)  # seeded random weights: shift the Lore heat maps s
 TABLES_PER_PAGE = 1
 SWEEP_CROPS, SWEEP_H, SWEEP_W = 4096, 32, 320   # BASELINE configs[3]
 LORE_BATCH = 16                                 # BASELINE configs[2]
+PP_REC_CLASSES = 97                             # en dictionary of the PP-OCRv4 recogniser
 FULL = True
 
 
@@ -483,6 +484,82 @@ def block_rec_sweep(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_s
             "kernels": kernel_table(agg, args.steps)}
 
 
+def block_pp_rec(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_src):
+    """BASELINE metric, first quantity on its own model: text-line crops/s through the PP-OCRv4 recogniser (SVTR-LCNet: a4 -> a5
+    -> a6) on 4096 synthetic crops at the nominal 48x320 shape, dealt round-robin over the N GPUs (strong scaling), one
+    all-gather of the decoded ids per batch inside the timed step."""
+    from pdf_table_b200 import predictors, sharding, synth
+
+    dev = torch.device("cuda", wl.device)
+    counts = [len(range(r, SWEEP_CROPS, world)) for r in range(world)]
+    n = counts[rank]
+    vocab = [chr(33 + i) for i in range(PP_REC_CLASSES - 2)]
+    task = predictors.OcrRecognitionTask(model="PP-OCRv4", state_dict=synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES), vocab=vocab, device=wl.device)
+    rec, post = task.predictor, task.post
+    import cv2
+
+    crops_np = np.stack([cv2.resize(c, (320, 48)) for c in make_sweep_crops(n, rank, world)])  # 48 x 320: ratio 6.67 = the nominal shape
+    crops_list = list(crops_np)
+    crops_dev = torch.from_numpy(crops_np).to(dev)
+    widths_dev = torch.full((n,), 320, dtype=torch.int32, device=dev)
+    none = {"boxes": torch.zeros((0, 1, 8), dtype=torch.float32, device=dev), "box_counts": torch.zeros((0,), dtype=torch.int32, device=dev)}
+    t_steps = rec.rec_time_steps(48, 320)
+
+    def gather(out, ln):
+        if dist is not None:
+            sharding.all_gather_results({**none, "ids": out, "id_lens": ln}, [0] * world, counts)
+
+    def step_device():
+        ids, maxp = rec.rec_forward_u8(crops_dev, widths_dev)
+        out, ln, _ = post.ctc_collapse(ids, maxp)
+        gather(out, ln)
+        return out, ln
+
+    last = [None]
+
+    def step_e2e():  # the public call: a list of numpy crops in, strings out (aspect sort, batch plan and cv2.resize on the host)
+        texts = task(crops_list)
+        if dist is not None:
+            gather(*last[0])
+        return texts
+
+    engines = (rec, post)
+    l0 = sum(e.launch_count for e in engines)
+    last[0] = step_device()
+    launches = sum(e.launch_count for e in engines) - l0
+    for _ in range(max(args.warmup, 3) - 1):
+        step_device()
+    dev_ms = timed_steps(step_device, wl.flush_l2, args.steps, barrier)
+    step_e2e()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_ms = timed_loop(step_e2e, e2e_steps, barrier) * args.steps / e2e_steps
+    for e in engines:
+        e.profile_begin()
+    for _ in range(args.steps):
+        wl.flush_l2()
+        step_device()
+    recs = []
+    for e in engines:
+        recs += e.profile_report()
+    agg = aggregate(recs)
+    dev_ms, e2e_ms = max_over_ranks(dist, [dev_ms, e2e_ms], dev)
+    total = SWEEP_CROPS * args.steps
+    return {"metric": "text_line_crops_per_sec", "value": total / (dev_ms / 1e3), "unit": "crops/s", "ms_per_step": dev_ms / args.steps,
+            "scaling": "strong", "higher_is_better": True, "dtype": "f16",
+            "config": {"workload": f"BASELINE metric (PP-OCRv4 rec): SVTR-LCNet recogniser, {SWEEP_CROPS} synthetic text-line crops 48x320 dealt "
+                                   f"round-robin over {world} GPU(s); T = {t_steps} steps, {PP_REC_CLASSES} classes (en dictionary)",
+                       "rec_model": "PP-OCRv4 rec = PPLCNetV3-0.95 + SVTR neck + CTC head, the published architecture the hub ONNX was exported from "
+                                    "(the ONNX file itself is not in the reference tree), seeded random weights",
+                       "crops_per_gpu": counts, "stages": ["rec_preprocess_u8(fused: /255, -0.5, /0.5, zero pad)", "pplcnetv3_svtr_forward",
+                                                           "softmax+argmax+max", "ctc_greedy_decode"] + (["all_gather(ids)"] if world > 1 else []),
+                       "model_gflop_per_crop": rec.model_flops / max(n, 1) / 1e9},
+            "e2e": {"value": total / (e2e_ms / 1e3), "unit": "crops/s", "h2d_bytes_per_step": int(crops_np.nbytes + 4 * n) * world,
+                    "d2h_bytes_per_step": int(n * t_steps * 4 + n * 8) * world, "ms_per_step": e2e_ms / args.steps,
+                    "api": "OcrRecognitionTask(model='PP-OCRv4').__call__(list of numpy crops) -> list[str]"},
+            "roofline": roofline_of(agg, peaks, peak_src, "pp_rec"), "gpu_launches": int(launches * args.steps),
+            "kernels": kernel_table(agg, args.steps)}
+
+
 def block_lore(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_src):
     """BASELINE configs[2]: Lore (DLA-34 + DCNv2, wtw), 16 x 1024x1024 table crops per GPU: detect + decode + cell features +
     processor.  e2e through OcrTableStructureTask.__call__ on numpy crops (host cv2.warpAffine pre-process included)."""
@@ -651,9 +728,28 @@ class CpuArm:
                 (", PicoDet layout and Lore table structure on one table crop per page" if FULL else "") + ", oracle/ restatement in torch fp32 on the host cores")
 
 
+def cpu_pp_rec(n: int):
+    import cv2
+
+    from oracle import ctc_ref, pp_rec_ref
+    from pdf_table_b200 import synth
+
+    if "pp_rec" not in _FULL_CPU:
+        _FULL_CPU["pp_rec"] = {k: torch.from_numpy(v) for k, v in synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES).items()}
+    crops = np.stack([cv2.resize(c, (320, 48)) for c in make_sweep_crops(n)])
+    for i in range(0, n, 6):  # batches of six, as PPOcrRecPreProcessor forms them
+        x = ((crops[i:i + 6].astype("float32").transpose(0, 3, 1, 2) / 255 - 0.5) / 0.5).astype(np.float32)
+        ctc_ref.ctc_greedy_ids(pp_rec_ref.pp_rec_forward(_FULL_CPU["pp_rec"], torch.from_numpy(x)).numpy())
+
+
 def cpu_blocks():
-    """Bounded CPU samples of the two secondary workloads (once each, not per step)."""
+    """Bounded CPU samples of the secondary workloads (once each, not per step)."""
     out = {}
+    cpu_pp_rec(6)
+    t0 = time.perf_counter()
+    cpu_pp_rec(96)
+    dt = time.perf_counter() - t0
+    out["pp_rec"] = {"value": 96 / dt, "unit": "crops/s", "kind": "port", "sample": f"96 of {SWEEP_CROPS} crops 48x320 once in batches of 6, {dt:.1f} s"}
     t0 = time.perf_counter()
     cpu_rec_sweep(32)
     dt = time.perf_counter() - t0
@@ -801,6 +897,7 @@ def main():
     peaks, peak_src = load_peaks()
     blocks = {}
     if not args.no_blocks:
+        blocks["pp_rec"] = block_pp_rec(wl, rank, world, dist, args, barrier, peaks, peak_src)
         blocks["rec_sweep"] = block_rec_sweep(wl, rank, world, dist, args, barrier, peaks, peak_src)
         if FULL:
             blocks["lore"] = block_lore(wl, rank, world, dist, args, barrier, peaks, peak_src)

@@ -266,6 +266,26 @@ int dv_picodet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int 
 int dv_picodet_num_classes(dv_handle h);
 
 /*
+ * PP-OCR text-line recogniser (SURVEY.md a5, 8(b) `dv_rec_forward`): the PP-OCRv4 "SVTR-LCNet" network -- PPLCNetV3-0.95
+ * backbone, SVTR neck (2 global-mixer blocks, 8 heads), CTC head -- for model kind "pp_rec" (weights packed by
+ * pdf_table_b200/pp_rec_graph.py).  Replaces the ONNX session run of OcrRecognitionTask._run_model for
+ * model="PP-OCRv4" (ocr_pdf/ocr_recognition_task.py:84-116, the hub model of ocr_pdf/ocr_table_model_config.py:166-204)
+ * together with the arg-max / max half of CTCLabelDecode.__call__ (ocr_rec_pp/rec_postprocess.py:175-183).
+ *   in_nchw_f32 : device fp32 [n,3,height,width] = PPOcrRecPreProcessor's batch (height 48; a4 / dv_pp_rec_normalise)
+ *   probs_out   : device fp32 [n,T,C] softmax probabilities, or NULL (the [n,T,C] tensor is then never written)
+ *   ids_out     : device int32 [n,T] per-step arg-max, or NULL;   maxp_out : device fp32 [n,T] per-step max probability, or NULL
+ *                 (feed both to dv_ctc_collapse for the decoded ids and the mean confidence)
+ *   T = dv_rec_time_steps(h, height, width) (= width / 8 for widths that are multiples of 8), C = dv_rec_num_classes(h).
+ * dv_rec_forward_u8: uint8 HWC crops [n,height,width,3] already resized to `height`, left aligned, valid up to widths[n]
+ * (device int32 [n], NULL = full width); (x / 255 - 0.5) / 0.5 and the zero padding beyond each width are fused into the stem.
+ */
+int dv_rec_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* probs_out, int32_t* ids_out, float* maxp_out);
+int dv_rec_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int n, int height, int width, float* probs_out,
+                      int32_t* ids_out, float* maxp_out);
+int dv_rec_time_steps(dv_handle h, int height, int width);
+int dv_rec_num_classes(dv_handle h);
+
+/*
  * PicoDet "anchor decode": head outputs of the four FPN levels -> layout boxes, on the device.
  * Replaces OcrLayoutTask._postprocess (ocr_layout_task.py:125-157) = OCRPicodetPostProcessor.__call__
  * (picodet/processor_picodet.py:184-298) with hard_nms / iou_of / area_of (:301-360) and warp_boxes (:136-158).

@@ -17,8 +17,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_STEM, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD = range(7)
-ACT_NONE, ACT_HSWISH = 0, 4
+OP_STEM, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC = range(12)
+ACT_NONE, ACT_HSWISH, ACT_SWISH = 0, 4, 5
 
 
 def _act(x: torch.Tensor, act: int) -> torch.Tensor:
@@ -26,6 +26,8 @@ def _act(x: torch.Tensor, act: int) -> torch.Tensor:
         return x
     if act == ACT_HSWISH:
         return F.hardswish(x)
+    if act == ACT_SWISH:
+        return x * torch.sigmoid(x)
     raise ValueError(f"activation code {act} is not used by graph programs")
 
 
@@ -37,9 +39,14 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
     n, _, hh, ww = x.shape
     rnd = (lambda t: t.half().float()) if fp16_activations else (lambda t: t)
     tens: List[torch.Tensor] = [x.float()]
-    for c, down in tensors[1:]:
-        tens.append(torch.zeros((n, int(c), -(-hh // int(down)), -(-ww // int(down))), dtype=torch.float32))
+    for row in tensors[1:]:
+        c, dh, dw, ph, pw = (int(row[0]), int(row[1]), int(row[1]), 1, 1) if len(row) == 2 else (int(v) for v in row)
+        tens.append(torch.zeros((n, c, (-(-hh // dh)) // ph, (-(-ww // dw)) // pw), dtype=torch.float32))
     heads: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def post_affine(t, wid):
+        pa = blob.get(f"w{wid}.pa")
+        return t if pa is None else t * float(pa[0]) + float(pa[1])
 
     def wt(wid: int, field: str) -> torch.Tensor:
         return torch.from_numpy(np.asarray(blob[f"w{wid}.{field}"]).astype(np.float32))
@@ -51,10 +58,18 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
             out = _act(F.conv2d(src, wk, wt(w, "sb"), stride=2, padding=1), act)
         elif code == OP_DW:  # dw [k*k][C]
             wk = wt(w, "dw").t().reshape(in_c, 1, k, k).contiguous()
-            out = _act(F.conv2d(src, wk, wt(w, "db"), stride=stride, padding=k // 2, groups=in_c), act)
-        elif code in (OP_PW, OP_HEAD):  # w fp16 [Cout][Cin_pad], b fp32 padded
+            st = stride if stride < 256 else (stride & 255, stride >> 8)
+            out = post_affine(_act(F.conv2d(src, wk, wt(w, "db"), stride=st, padding=k // 2, groups=in_c), act), w)
+        elif code in (OP_PW, OP_HEAD, OP_CTC):  # w fp16 [Cout][Cin_pad], b fp32 padded
             wk = wt(w, "w")[:, :in_c].reshape(-1, in_c, 1, 1)
-            out = _act(F.conv2d(src, wk, wt(w, "b")[:wk.shape[0]]), act)
+            out = F.conv2d(src, wk, wt(w, "b")[:wk.shape[0]])
+            if code == OP_PW and aux >= 0:
+                out = out + tens[aux]
+            out = post_affine(_act(out, act), w) if code == OP_PW else _act(out, act)
+            if code == OP_CTC:  # k_softmax_rows over the first num_classes columns
+                logits = out.permute(0, 2, 3, 1).reshape(n, -1, out.shape[1])[..., :num_classes]
+                heads["logits"], heads["probs"] = logits, torch.softmax(logits, -1)
+                continue
             if code == OP_HEAD:  # k_head_split: fp32 raw -> sigmoid class scores + raw DFL logits, pixel-major
                 raw = out.permute(0, 2, 3, 1).reshape(n, -1, out.shape[1])
                 heads[aux] = (torch.sigmoid(raw[..., :num_classes]), raw[..., num_classes:num_classes + reg_bins])
@@ -71,6 +86,18 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
             out = src[:, :, iy][:, :, :, ix]
         elif code == OP_ADD:
             out = tens[in_t] + tens[aux]
+        elif code == OP_AVGPOOL:
+            out = F.avg_pool2d(src, [k & 255, k >> 8])
+        elif code == OP_UNFOLD3:  # [N,C,1,T] -> [N,3C,1,T], channel = tap * C + c
+            pad = F.pad(src, (1, 1))
+            out = torch.cat([pad[..., t:t + src.shape[-1]] for t in range(3)], 1)
+        elif code == OP_LN:
+            out = F.layer_norm(src.permute(0, 2, 3, 1), (in_c,), wt(w, "lnw"), wt(w, "lnb"), eps=float(blob[f"w{w}.eps"][0])).permute(0, 3, 1, 2)
+        elif code == OP_ATTN:  # qkv [N,3D,1,T]: q | k | v, head-major; the scale is folded into q
+            d, t_len = out_c, src.shape[-1]
+            qkv = src[:, :, 0].transpose(1, 2).reshape(n, t_len, 3, k, d // k).permute(2, 0, 3, 1, 4)
+            attn = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2), -1)
+            out = (attn @ qkv[2]).permute(0, 2, 1, 3).reshape(n, t_len, d).transpose(1, 2)[:, :, None]
         else:
             raise ValueError(f"unknown opcode {code}")
         dst = tens[out_t]

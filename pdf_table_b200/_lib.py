@@ -54,6 +54,10 @@ SIGNATURES = {
     "dv_picodet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.c_float, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "dv_picodet_num_classes": (C.c_int, [C.c_void_p]),
+    "dv_rec_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dv_rec_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dv_rec_time_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "dv_rec_num_classes": (C.c_int, [C.c_void_p]),
     "dv_centernet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dv_centernet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                           C.POINTER(C.c_float), C.c_int, C.c_void_p]),

@@ -145,7 +145,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = dbnet_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
-        } else if (e->kind == "picodet") {
+        } else if (e->kind == "picodet" || e->kind == "pp_rec") {
             rc = graph_create(e);
         } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34") {
             rc = lore_create(e);
@@ -440,6 +440,22 @@ int dv_picodet_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int 
 }
 
 int dv_picodet_num_classes(dv_handle h) { return h ? graph_num_classes(h) : 0; }
+
+int dv_rec_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* probs_out, int32_t* ids_out, float* maxp_out) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return rec_forward(h, in_nchw_f32, nullptr, nullptr, n, height, width, probs_out, ids_out, maxp_out);
+}
+
+int dv_rec_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int n, int height, int width, float* probs_out,
+                      int32_t* ids_out, float* maxp_out) {
+    if (!h || !crops_hwc_u8) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return rec_forward(h, nullptr, crops_hwc_u8, widths, n, height, width, probs_out, ids_out, maxp_out);
+}
+
+int dv_rec_time_steps(dv_handle h, int height, int width) { return h ? rec_time_steps(h, height, width) : 0; }
+int dv_rec_num_classes(dv_handle h) { return h ? graph_num_classes(h) : 0; }
 
 int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crops, float* logits_out,
                            int32_t* ids_out, float* max_out) {

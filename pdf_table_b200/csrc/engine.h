@@ -98,6 +98,8 @@ struct EpiSpec {
     const int* m_dyn = nullptr;  // A_FLAT: device row count (see IGemmParams::m_dyn)
     int split_off = 0;           // fp16 out: also store the fp16 residual at column + split_off
     int res_lo = 0;              // fp16 residual stored as a split pair: its lo half sits res_lo columns further
+    int post_affine = 0;         // y = act(x) * post_scale + post_bias
+    float post_scale = 1.f, post_bias = 0.f;
 };
 
 struct ConvPlan {
@@ -282,6 +284,10 @@ int graph_num_classes(Engine* e);
 int graph_debug_tensor(Engine* e, int tensor_id, float* out_nchw, int* dims4);
 int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip,
                     int N, int H, int W, float* const* scores_out, float* const* dfl_out);
+
+int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, int N, int H, int W, float* probs, int32_t* ids,
+                float* maxp);
+int rec_time_steps(Engine* e, int H, int W);
 
 // picodet_decode.cu
 int picodet_decode(Engine* e, const float* const* scores, const float* const* dfl, int N, int C, int reg_max, const int* strides, int in_h,

@@ -10,6 +10,15 @@
 //   OP_UP2   nearest 2x up-sampling into a concatenation slice                     (CSPPAN.forward :322-325)
 //   OP_ADD   element-wise sum                                                      (the extra top level :343-345)
 //   OP_HEAD  1x1 conv 128 -> C + 32 (fp32) -> sigmoid(class scores) [N,HW,C] + raw DFL logits [N,HW,32]
+// and, for the PP-OCRv4 recogniser (pdf_table_b200/pp_rec_graph.py: PPLCNetV3-0.95 + SVTR neck + CTC head, SURVEY.md a5;
+// CPU mirror oracle/pp_rec_ref.py):
+//   OP_DW / OP_PW also take a post-activation affine (LearnableAffineBlock scalars, `w{id}.pa`), OP_DW a (sh, sw) stride,
+//            OP_PW a residual tensor (aux) and the Swish activation
+//   OP_AVGPOOL  kh x kw average pool, stride = kernel (the eval tail avg_pool2d(x, [3, 2]))
+//   OP_UNFOLD3  [N,1,T,C] -> [N,1,T,3C] = [x[t-1] | x[t] | x[t+1]] (zeros outside): the (1,3) convs of the SVTR neck as GEMMs
+//   OP_LN       LayerNorm over the channels of each position
+//   OP_ATTN     softmax(q k^T) v per (image, head) over the T positions of a text line (global mixer, 8 heads x 15)
+//   OP_CTC      Linear -> fp32 logits -> softmax: probabilities [N,T,C] (optional) + per-step arg-max / max probability
 // Every tensor is NHWC fp16; an operand may be a channel slice (coff, c) of a wider buffer, which is how the CSP
 // concatenations exist without copies.  The plan (buffers, TMA descriptors) is built once per input shape.
 #include "engine.h"
@@ -18,11 +27,12 @@ namespace dv {
 
 namespace {
 
-enum { OP_STEM = 0, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD };
+enum { OP_STEM = 0, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC };
 
 __device__ __forceinline__ float act_f(float x, int act) {
     if (act == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
     if (act == ACT_RELU) return fmaxf(x, 0.f);
+    if (act == ACT_SWISH) return x / (1.f + __expf(-x));
     return x;
 }
 
@@ -30,7 +40,7 @@ __device__ __forceinline__ float act_f(float x, int act) {
 __global__ void __launch_bounds__(128)
 k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, int Ho, int Wo, float3 mean,
             float3 stdv, float scale, int flip, const float* __restrict__ w, const float* __restrict__ bias, int act,
-            __half* __restrict__ out) {
+            __half* __restrict__ out, const int32_t* __restrict__ widths) {
     __shared__ float sw[27 * 16];
     __shared__ float sb[16];
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
@@ -49,17 +59,24 @@ k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N
             const int ix = 2 * ox - 1 + s;
             if (ix < 0 || ix >= W) continue;
             float v[3];
-            if (u8) {
+            if (u8 && widths != nullptr && ix >= widths[n]) {
+                v[0] = v[1] = v[2] = 0.f;  // PP rec: zero padding AFTER the normalisation (resize_norm_img)
+            } else if (u8) {
                 const uint8_t* ip = u8 + ((static_cast<long long>(n) * H + iy) * W + ix) * 3;
                 float c0 = ip[0], c1 = ip[1], c2 = ip[2];
-                if (flip) {
+                if (flip & 1) {
                     const float t = c0;
                     c0 = c2;
                     c2 = t;
                 }
-                v[0] = __fdiv_rn(__fsub_rn(__fmul_rn(c0, scale), mean.x), stdv.x);
-                v[1] = __fdiv_rn(__fsub_rn(__fmul_rn(c1, scale), mean.y), stdv.y);
-                v[2] = __fdiv_rn(__fsub_rn(__fmul_rn(c2, scale), mean.z), stdv.z);
+                if (flip & 2) {  // PP rec (resize_norm_img): x / 255 is a DIVISION there, `scale` carries the divisor
+                    c0 = __fdiv_rn(c0, scale), c1 = __fdiv_rn(c1, scale), c2 = __fdiv_rn(c2, scale);
+                } else {
+                    c0 = __fmul_rn(c0, scale), c1 = __fmul_rn(c1, scale), c2 = __fmul_rn(c2, scale);
+                }
+                v[0] = __fdiv_rn(__fsub_rn(c0, mean.x), stdv.x);
+                v[1] = __fdiv_rn(__fsub_rn(c1, mean.y), stdv.y);
+                v[2] = __fdiv_rn(__fsub_rn(c2, mean.z), stdv.z);
             } else {
                 const long long plane = static_cast<long long>(H) * W;
                 const float* ip = f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(iy) * W + ix;
@@ -84,8 +101,8 @@ k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N
 
 // depthwise k x k, pad (k-1)/2, stride s; w fp32 [k*k][C] (BN scale folded), b fp32 [C]; one thread = (pixel, 8 channels)
 __global__ void __launch_bounds__(256)
-k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int k, int stride, int Ho, int Wo,
-         const float* __restrict__ w, const float* __restrict__ b, int act, __half* __restrict__ out, int ldo) {
+k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int k, int sh, int sw, int Ho, int Wo,
+         const float* __restrict__ w, const float* __restrict__ b, int act, float ps, float pb, __half* __restrict__ out, int ldo) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
@@ -101,10 +118,10 @@ k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int
     }
     const int pad = (k - 1) >> 1;
     for (int r = 0; r < k; ++r) {
-        const int iy = oy * stride - pad + r;
+        const int iy = oy * sh - pad + r;
         if (iy < 0 || iy >= H) continue;
         for (int s = 0; s < k; ++s) {
-            const int ix = ox * stride - pad + s;
+            const int ix = ox * sw - pad + s;
             if (ix < 0 || ix >= W) continue;
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * ldi + c8 * 8));
             const float4* wp = reinterpret_cast<const float4*>(w + static_cast<long long>(r * k + s) * C + c8 * 8);
@@ -124,8 +141,174 @@ k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int
     uint4 o;
     __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(act_f(acc[2 * i], act), act_f(acc[2 * i + 1], act));
+    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(fmaf(act_f(acc[2 * i], act), ps, pb), fmaf(act_f(acc[2 * i + 1], act), ps, pb));
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+}
+
+// kh x kw average pool with stride = kernel (floor output size), 8 channels per thread
+__global__ void __launch_bounds__(256)
+k_avgpool(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int kh, int kw, int Ho, int Wo, __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < kh; ++r)
+        for (int s = 0; s < kw; ++s) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + oy * kh + r) * W + ox * kw + s) * ldi + c8 * 8));
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 v = __half22float2(h[i]);
+                acc[2 * i] += v.x;
+                acc[2 * i + 1] += v.y;
+            }
+        }
+    const float inv = 1.f / static_cast<float>(kh * kw);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+}
+
+// [N, T, C] (row stride ldi) -> [N, T, 3C]: columns [x[t-1] | x[t] | x[t+1]], zeros outside the line
+__global__ void __launch_bounds__(256)
+k_unfold3(const __half* __restrict__ in, int N, int T, int C, int ldi, __half* __restrict__ out) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * T * 3 * cv) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long r = idx / cv;
+    const int tap = static_cast<int>(r % 3);
+    r /= 3;
+    const int t = static_cast<int>(r % T);
+    const long long n = r / T;
+    const int ts = t + tap - 1;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (ts >= 0 && ts < T) u = __ldg(reinterpret_cast<const uint4*>(in + (n * T + ts) * ldi + c8 * 8));
+    *reinterpret_cast<uint4*>(out + ((n * T + t) * 3 + tap) * C + c8 * 8) = u;
+}
+
+// LayerNorm over the C channels of each row (one warp per row, any C % 8 == 0 up to 1024), fp16 in / out
+__global__ void __launch_bounds__(256)
+k_ln_c(const __half* __restrict__ in, long long rows, int C, int ldi, const float* __restrict__ g, const float* __restrict__ b, float eps,
+       __half* __restrict__ out, int ldo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+    if (row >= rows) return;
+    const __half* ip = in + row * ldi;
+    float v[32];
+    float s = 0.f;
+    const int per = (C + 31) / 32;
+    for (int j = 0; j < per; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = c < C ? __half2float(ip[c]) : 0.f;
+        s += v[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / static_cast<float>(C);
+    float q = 0.f;
+    for (int j = 0; j < per; ++j) {
+        const int c = lane + 32 * j;
+        const float d = c < C ? v[j] - mean : 0.f;
+        v[j] = d;
+        q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+    __half* op = out + row * ldo;
+    for (int j = 0; j < per; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) op[c] = __float2half_rn(v[j] * rstd * __ldg(g + c) + __ldg(b + c));
+    }
+}
+
+// Global-mixer attention of the SVTR neck: qkv [N, T, 3D] (q | k | v, each head-major heads x hd; the 1/sqrt(hd) scale is
+// folded into the packed q weights) -> ctx [N, T, D].  One CTA per image; K and V of all heads staged in shared memory as
+// fp32, one thread per (head, query) with an online softmax (no score buffer, any T that fits shared memory).
+__global__ void __launch_bounds__(256)
+k_attn_small(const __half* __restrict__ qkv, int T, int D, int heads, __half* __restrict__ ctx) {
+    extern __shared__ float sm[];  // K [T][D] | V [T][D]
+    float* sK = sm;
+    float* sV = sm + static_cast<size_t>(T) * D;
+    const int n = blockIdx.x;
+    const int hd = D / heads;
+    const __half* base = qkv + static_cast<long long>(n) * T * 3 * D;
+    for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+        const int t = i / D, c = i - t * D;
+        sK[i] = __half2float(base[static_cast<long long>(t) * 3 * D + D + c]);
+        sV[i] = __half2float(base[static_cast<long long>(t) * 3 * D + 2 * D + c]);
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < heads * T; w += blockDim.x) {
+        const int h = w / T, qi = w - h * T;
+        float q[16], o[16];
+        for (int d = 0; d < hd; ++d) {
+            q[d] = __half2float(base[static_cast<long long>(qi) * 3 * D + h * hd + d]);
+            o[d] = 0.f;
+        }
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const float* kp = sK + j * D + h * hd;
+            float sc = 0.f;
+            for (int d = 0; d < hd; ++d) sc = fmaf(q[d], kp[d], sc);
+            const float mn = fmaxf(m, sc);
+            const float corr = __expf(m - mn), pj = __expf(sc - mn);
+            l = l * corr + pj;
+            const float* vp = sV + j * D + h * hd;
+            for (int d = 0; d < hd; ++d) o[d] = fmaf(o[d], corr, pj * vp[d]);
+            m = mn;
+        }
+        const float inv = 1.f / l;
+        __half* op = ctx + (static_cast<long long>(n) * T + qi) * D + h * hd;
+        for (int d = 0; d < hd; ++d) op[d] = __float2half_rn(o[d] * inv);
+    }
+}
+
+// fp32 logits [M, ld] -> softmax over the first C columns: probs [M, C] (optional), arg-max id and max probability per row
+__global__ void __launch_bounds__(256)
+k_softmax_rows(const float* __restrict__ logits, long long M, int ld, int C, float* __restrict__ probs, int32_t* __restrict__ ids,
+               float* __restrict__ maxp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+    if (row >= M) return;
+    const float* ip = logits + row * ld;
+    float mx = -INFINITY;
+    int arg = 0;
+    for (int c = lane; c < C; c += 32) {
+        const float v = ip[c];
+        if (v > mx) {
+            mx = v;
+            arg = c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > mx || (ov == mx && oa < arg)) {
+            mx = ov;
+            arg = oa;
+        }
+    }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(ip[c] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    if (probs != nullptr)
+        for (int c = lane; c < C; c += 32) probs[row * C + c] = expf(ip[c] - mx) * inv;
+    if (lane == 0) {
+        if (ids != nullptr) ids[row] = arg;
+        if (maxp != nullptr) maxp[row] = inv;  // exp(0) / sum
+    }
 }
 
 // SE squeeze: one CTA per image.  avg[c] -> hidden = relu(W1 avg + b1) -> scale[c] = hardsigmoid(W2 hidden + b2)
@@ -221,15 +404,21 @@ k_head_split(const float* __restrict__ raw, long long M, int ld, int C, int R, f
 
 struct GOp {
     int code, in_t, in_coff, in_c, out_t, out_coff, out_c, k, stride, act, w, aux;
-    ConvPlan plan;  // OP_PW / OP_HEAD
+    ConvPlan plan;  // OP_PW / OP_HEAD / OP_CTC
     const float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;
+    float ps = 1.f, pb = 0.f;  // post-activation affine (w{id}.pa), identity when absent
+    int has_pa = 0;
+    float eps = 1e-5f;         // OP_LN (w{id}.eps)
+    int sh() const { return stride < 256 ? stride : (stride & 255); }  // stride = sh | sw << 8 when the two differ
+    int sw() const { return stride < 256 ? stride : (stride >> 8); }
 };
 
 struct GraphNet : Model {
     Engine* e = nullptr;
     int N = 0, H = 0, W = 0;
+    int kind = 0;  // 0 = PicoDet (graph.meta[5]), 1 = PP-OCR recogniser
     int num_classes = 0, reg_bins = 32, head_ld = 40;
-    std::vector<int> tc, tdown;
+    std::vector<int> tc, tdh, tdw, tph, tpw;  // channels; size = floor(ceil(H / dh) / ph) x floor(ceil(W / dw) / pw)
     std::vector<GOp> ops;
     std::vector<Tensor> tens;
     std::vector<void*> mem;
@@ -270,8 +459,9 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
     for (size_t i = 1; i < nt; ++i) {  // tensor 0 is the input image
         Tensor& t = m->tens[i];
         t.N = N;
-        t.H = (H + m->tdown[i] - 1) / m->tdown[i];
-        t.W = (W + m->tdown[i] - 1) / m->tdown[i];
+        t.H = ((H + m->tdh[i] - 1) / m->tdh[i]) / m->tph[i];
+        t.W = ((W + m->tdw[i] - 1) / m->tdw[i]) / m->tpw[i];
+        if (t.H <= 0 || t.W <= 0) return set_err(e, DV_ERR_ARG, "graph: input %dx%d too small for tensor %zu", H, W, i);
         t.C = m->tc[i];
         void* p = nullptr;
         DV_TRY(m->alloc(&p, t.elems() * sizeof(__half)));
@@ -294,6 +484,25 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
                 op.f1 = wf32(e, op.w, "db", op.in_c, &rc);
                 m->flops += 2.0 * N * out.H * out.W * op.k * op.k * op.in_c;
                 break;
+            case OP_LN: {
+                op.f0 = wf32(e, op.w, "lnw", op.in_c, &rc);
+                op.f1 = wf32(e, op.w, "lnb", op.in_c, &rc);
+                const float* ep = wf32(e, op.w, "eps", 1, &rc);
+                if (!rc) DV_CUDA(e, cudaMemcpy(&op.eps, ep, 4, cudaMemcpyDeviceToHost));
+                if (op.in_c > 1024) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: LayerNorm over %d channels", op.in_c);
+                break;
+            }
+            case OP_ATTN:
+                if (op.k <= 0 || (op.out_c % op.k) || op.out_c / op.k > 16 || op.in_c != 3 * op.out_c || in.C != op.in_c || in.H != 1)
+                    rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: attention needs [N,1,T,3D] input, head dim <= 16");
+                m->flops += 4.0 * N * in.W * in.W * op.out_c;
+                break;
+            case OP_UNFOLD3:
+                if (in.H != 1 || out.C != 3 * op.in_c) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: unfold3 needs a [N,1,T,C] line and a dense [.,3C] output");
+                break;
+            case OP_CTC:
+                if (static_cast<size_t>(N) * in.H * in.W > max_head_rows) max_head_rows = static_cast<size_t>(N) * in.H * in.W;
+                break;
             case OP_SE:
                 op.f0 = wf32(e, op.w, "s1w", static_cast<size_t>(op.in_c) * op.in_c / 4, &rc);
                 op.f1 = wf32(e, op.w, "s1b", op.in_c / 4, &rc);
@@ -307,6 +516,16 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             default: break;
         }
         if (rc) return rc;
+        if (op.w >= 0 && (op.code == OP_DW || op.code == OP_PW)) {  // optional post-activation affine
+            const BlobTensor* pa = e->find("w" + std::to_string(op.w) + ".pa");
+            if (pa && pa->dtype == 0 && pa->nbytes >= 8) {
+                float h2[2];
+                DV_CUDA(e, cudaMemcpy(h2, pa->dptr, 8, cudaMemcpyDeviceToHost));
+                op.ps = h2[0];
+                op.pb = h2[1];
+                op.has_pa = 1;
+            }
+        }
     }
     if (max_se_c) {
         void* p = nullptr;
@@ -319,27 +538,30 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         m->head_raw = reinterpret_cast<float*>(p);
     }
     for (GOp& op : m->ops) {
-        if (op.code != OP_PW && op.code != OP_HEAD) continue;
+        if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
         const Tensor& in = m->tens[op.in_t];
         const Tensor& out = m->tens[op.out_t];
         const std::string wn = "w" + std::to_string(op.w);
         const BlobTensor* w = e->find(wn + ".w");
         const BlobTensor* b = e->find(wn + ".b");
-        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != op.out_c ||
-            static_cast<int>(w->dims[1]) != op.in_c)
+        // the packed K axis is padded to a multiple of 16 (weights.cin_pad_of); the A operand keeps its own width, the TMA unit
+        // zero-fills the columns beyond it
+        const int kpad = w ? static_cast<int>(w->dims[1]) : 0;
+        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != op.out_c || kpad < op.in_c ||
+            kpad - op.in_c >= 16 || (kpad % 16))
             return set_err(e, DV_ERR_WEIGHTS, "graph: bad 1x1 weights '%s' (want [%d,%d])", wn.c_str(), op.out_c, op.in_c);
         ConvSpec cs;
         cs.KH = cs.KW = 1;
         cs.Cin = op.in_c;
-        cs.Cin_pad = op.in_c;
+        cs.Cin_pad = kpad;
         cs.Cout = op.out_c;
-        cs.BK = (op.in_c % 64 == 0) ? 64 : (op.in_c % 32 == 0) ? 32 : 16;
+        cs.BK = (kpad % 64 == 0) ? 64 : (kpad % 32 == 0) ? 32 : 16;
         cs.w = reinterpret_cast<const __half*>(w->dptr);
         cs.bias = reinterpret_cast<const float*>(b->dptr);
         cs.flat = true;
         EpiSpec es;
         es.act = op.act;
-        if (op.code == OP_HEAD) {
+        if (op.code == OP_HEAD || op.code == OP_CTC) {
             es.out = m->head_raw;
             es.out_ld = m->head_ld;
             es.out_f32 = 1;
@@ -347,6 +569,16 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             es.out = out.p;
             es.out_ld = out.C;
             es.out_coff = op.out_coff;
+            es.post_affine = op.has_pa;
+            es.post_scale = op.ps;
+            es.post_bias = op.pb;
+            if (op.aux >= 0) {  // residual: a dense tensor of the output's shape
+                const Tensor& r = m->tens[op.aux];
+                if (r.C != op.out_c || r.H != out.H || r.W != out.W) return set_err(e, DV_ERR_WEIGHTS, "graph: residual shape mismatch at '%s'", wn.c_str());
+                es.res = r.p;
+                es.res_mode = RES_SAME;
+                es.res_ld = r.C;
+            }
         }
         const int M = N * in.H * in.W;
         DV_TRY(plan_linear(e, in.p + op.in_coff, M, op.in_c, cs, es, &op.plan, wn.c_str(), in.C));
@@ -367,7 +599,7 @@ int graph_create(Engine* e) {
     const BlobTensor* tt = e->find("graph.tensors");
     const BlobTensor* to = e->find("graph.ops");
     const BlobTensor* tm = e->find("graph.meta");
-    if (!tt || !to || !tm || tt->dtype != 2 || to->dtype != 2 || tm->dtype != 2 || to->dims[1] != 12 || tt->dims[1] != 2) {
+    if (!tt || !to || !tm || tt->dtype != 2 || to->dtype != 2 || tm->dtype != 2 || to->dims[1] != 12 || (tt->dims[1] != 2 && tt->dims[1] != 5)) {
         delete m;
         return set_err(e, DV_ERR_WEIGHTS, "graph model: missing graph.tensors / graph.ops / graph.meta");
     }
@@ -378,9 +610,19 @@ int graph_create(Engine* e) {
     m->num_classes = hm[0];
     m->reg_bins = hm[1];
     m->head_ld = hm[2];
+    m->kind = hm.size() > 5 ? hm[5] : 0;
+    const int tcols = static_cast<int>(tt->dims[1]);  // 2: (c, down); 5: (c, down_h, down_w, pool_h, pool_w)
     for (size_t i = 0; i < tt->dims[0]; ++i) {
-        m->tc.push_back(ht[2 * i]);
-        m->tdown.push_back(ht[2 * i + 1]);
+        const int32_t* r = &ht[tcols * i];
+        m->tc.push_back(r[0]);
+        m->tdh.push_back(r[1]);
+        m->tdw.push_back(tcols == 5 ? r[2] : r[1]);
+        m->tph.push_back(tcols == 5 ? r[3] : 1);
+        m->tpw.push_back(tcols == 5 ? r[4] : 1);
+        if (m->tdh.back() <= 0 || m->tdw.back() <= 0 || m->tph.back() <= 0 || m->tpw.back() <= 0) {
+            delete m;
+            return set_err(e, DV_ERR_WEIGHTS, "graph model: malformed tensor table");
+        }
     }
     for (size_t i = 0; i < to->dims[0]; ++i) {
         const int32_t* o = &ho[12 * i];
@@ -420,12 +662,21 @@ int graph_debug_tensor(Engine* e, int tensor_id, float* out_nchw, int* dims4) {
     return 0;
 }
 
-// scores_out[l] fp32 [N, HW_l, C], dfl_out[l] fp32 [N, HW_l, 32] (device), l = 0..3
-int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip,
-                    int N, int H, int W, float* const* scores_out, float* const* dfl_out) {
-    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
-    if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a picodet model");
-    if (N <= 0 || H <= 0 || W <= 0 || (!in_nchw && !in_u8) || !scores_out || !dfl_out) return set_err(e, DV_ERR_ARG, "picodet_forward: bad arguments");
+namespace {
+
+// Outputs of a graph program: PicoDet heads (scores / dfl per level) or the recogniser's CTC head (probs / ids / maxp).
+struct GraphOut {
+    float* const* scores = nullptr;
+    float* const* dfl = nullptr;
+    float* probs = nullptr;
+    int32_t* ids = nullptr;
+    float* maxp = nullptr;
+};
+
+int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, const float* mean3, const float* std3,
+              float scale, int flip, int N, int H, int W, const GraphOut& go) {
+    float* const* scores_out = go.scores;
+    float* const* dfl_out = go.dfl;
     if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
     cudaStream_t s = e->stream;
     for (GOp& op : m->ops) {
@@ -441,15 +692,15 @@ int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const
                 }
                 e->launch_begin("k_stem3x3s2", "conv1", 2.0 * total * 27 * 16, total * (12.0 * (in_u8 ? 1 : 4) + 32.0));
                 k_stem3x3s2<<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
-                                                                 out.p);
+                                                                 out.p, widths);
                 e->launch_end();
                 break;
             }
             case OP_DW: {
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
-                e->launch_begin("k_dwconv", "dw", 2.0 * total * 8 * op.k * op.k, total * 8 * 2.0 * (1.0 + 1.0 / (op.stride * op.stride)));
-                k_dwconv<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.k, op.stride, out.H, out.W, op.f0, op.f1,
-                                                              op.act, out.p + op.out_coff, out.C);
+                e->launch_begin("k_dwconv", "dw", 2.0 * total * 8 * op.k * op.k, total * 8 * 2.0 * (1.0 + 1.0 / (op.sh() * op.sw())));
+                k_dwconv<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.k, op.sh(), op.sw(), out.H, out.W, op.f0,
+                                                              op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
@@ -483,10 +734,56 @@ int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const
             case OP_HEAD: {
                 DV_TRY(launch_conv(e, op.plan));
                 const long long M = static_cast<long long>(N) * in.H * in.W;
-                if (op.aux < 0 || op.aux > 3 || !scores_out[op.aux] || !dfl_out[op.aux]) return set_err(e, DV_ERR_ARG, "picodet_forward: null output for level %d", op.aux);
+                if (!scores_out || !dfl_out || op.aux < 0 || op.aux > 3 || !scores_out[op.aux] || !dfl_out[op.aux])
+                    return set_err(e, DV_ERR_ARG, "picodet_forward: null output for level %d", op.aux);
                 e->launch_begin("k_head_split", "head", 0.0, M * (m->num_classes + m->reg_bins) * 8.0);
                 k_head_split<<<grid_for(M * (m->num_classes + m->reg_bins), 256), 256, 0, s>>>(m->head_raw, M, m->head_ld, m->num_classes, m->reg_bins,
                                                                                                scores_out[op.aux], dfl_out[op.aux]);
+                e->launch_end();
+                break;
+            }
+            case OP_AVGPOOL: {
+                const int kh = op.k & 255, kw = op.k >> 8;
+                const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
+                e->launch_begin("k_avgpool", "pool", 0.0, total * 16.0 * (kh * kw + 1));
+                k_avgpool<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, kh, kw, out.H, out.W, out.p + op.out_coff, out.C);
+                e->launch_end();
+                break;
+            }
+            case OP_UNFOLD3: {
+                const long long total = static_cast<long long>(N) * in.W * 3 * (op.in_c / 8);
+                e->launch_begin("k_unfold3", "unfold", 0.0, total * 32.0);
+                k_unfold3<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.W, op.in_c, in.C, out.p);
+                e->launch_end();
+                break;
+            }
+            case OP_LN: {
+                const long long rows = static_cast<long long>(N) * in.H * in.W;
+                e->launch_begin("k_ln_c", "ln", 0.0, rows * op.in_c * 4.0);
+                k_ln_c<<<grid_for(rows, 8), 256, 0, s>>>(in.p + op.in_coff, rows, op.in_c, in.C, op.f0, op.f1, op.eps, out.p + op.out_coff, out.C);
+                e->launch_end();
+                break;
+            }
+            case OP_ATTN: {
+                const int T = in.W, D = op.out_c;
+                const size_t smem = static_cast<size_t>(2) * T * D * sizeof(float);
+                if (smem > 200 * 1024) return set_err(e, DV_ERR_UNSUPPORTED, "graph: attention over %d positions exceeds shared memory", T);
+                static DeviceOnce attr_once;
+                if (attr_once.need(e->device)) {
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    attr_once.mark(e->device);
+                }
+                e->launch_begin("k_attn_small", "attn", 4.0 * N * T * T * D, static_cast<double>(N) * T * D * 8.0);
+                k_attn_small<<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
+                e->launch_end();
+                break;
+            }
+            case OP_CTC: {
+                DV_TRY(launch_conv(e, op.plan));
+                const long long M = static_cast<long long>(N) * in.H * in.W;
+                if (!go.ids && !go.probs && !go.maxp) return set_err(e, DV_ERR_ARG, "rec_forward: no output requested");
+                e->launch_begin("k_softmax_rows", "ctc", 0.0, M * m->num_classes * (go.probs ? 8.0 : 4.0));
+                k_softmax_rows<<<grid_for(M, 8), 256, 0, s>>>(m->head_raw, M, m->head_ld, m->num_classes, go.probs, go.ids, go.maxp);
                 e->launch_end();
                 break;
             }
@@ -495,6 +792,43 @@ int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const
     }
     DV_CUDA(e, cudaGetLastError());
     return 0;
+}
+
+}  // namespace
+
+// scores_out[l] fp32 [N, HW_l, C], dfl_out[l] fp32 [N, HW_l, 32] (device), l = 0..3
+int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip,
+                    int N, int H, int W, float* const* scores_out, float* const* dfl_out) {
+    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
+    if (!m || m->kind != 0) return set_err(e, DV_ERR_STATE, "handle was not created as a picodet model");
+    if (N <= 0 || H <= 0 || W <= 0 || (!in_nchw && !in_u8) || !scores_out || !dfl_out) return set_err(e, DV_ERR_ARG, "picodet_forward: bad arguments");
+    GraphOut go;
+    go.scores = scores_out;
+    go.dfl = dfl_out;
+    return run_graph(e, m, in_nchw, in_u8, nullptr, mean3, std3, scale, flip, N, H, W, go);
+}
+
+// PP-OCR recogniser: fp32 [N,3,H,W] (PPOcrRecPreProcessor's batch) or uint8 [N,H,W,3] crops resized to height H, left aligned
+// and valid up to widths[n] (normalisation (x/255 - 0.5)/0.5 and the zero padding fused into the stem) ->
+// probs fp32 [N,T,C] (optional), ids int32 [N,T], maxp fp32 [N,T]; T = rec_time_steps(W).
+int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, int N, int H, int W, float* probs, int32_t* ids,
+                float* maxp) {
+    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
+    if (!m || m->kind != 1) return set_err(e, DV_ERR_STATE, "handle was not created as a pp_rec model");
+    if (N <= 0 || H <= 0 || W <= 0 || (!in_nchw && !in_u8)) return set_err(e, DV_ERR_ARG, "rec_forward: bad arguments");
+    const float half3[3] = {0.5f, 0.5f, 0.5f};
+    GraphOut go;
+    go.probs = probs;
+    go.ids = ids;
+    go.maxp = maxp;
+    return run_graph(e, m, in_nchw, in_u8, widths, half3, half3, 255.0f, /*flip: divide by scale*/ 2, N, H, W, go);
+}
+
+int rec_time_steps(Engine* e, int H, int W) {
+    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
+    if (!m || m->kind != 1 || m->ops.empty()) return 0;
+    const int t = m->ops.back().in_t;
+    return ((H + m->tdh[t] - 1) / m->tdh[t]) / m->tph[t] * (((W + m->tdw[t] - 1) / m->tdw[t]) / m->tpw[t]);
 }
 
 }  // namespace dv

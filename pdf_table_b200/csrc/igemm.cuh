@@ -47,6 +47,7 @@ __device__ __forceinline__ float apply_act(float x) {
     }
     if constexpr (ACT == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
     if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    if constexpr (ACT == ACT_SWISH) return x / (1.f + __expf(-x));
     return x;
 }
 
@@ -468,6 +469,11 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         f[j] = apply_act<ACT>(f[j]);
                         f[j + 1] = apply_act<ACT>(f[j + 1]);
                     }
+                }
+                if (p.post_affine) {
+                    const float ps = p.post_scale, pb = p.post_bias;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], ps, pb);
                 }
                 if constexpr (ARGMAX) {
                     // torch.argmax semantics: first maximum wins (columns are visited in ascending order)

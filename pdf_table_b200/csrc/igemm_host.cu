@@ -140,6 +140,9 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.out_f32 = es.out_f32;
     p.m_dyn = es.m_dyn;
     p.split_off = es.split_off;
+    p.post_affine = es.post_affine;
+    p.post_scale = es.post_scale;
+    p.post_bias = es.post_bias;
     p.res_split_off = es.res_lo;
     if (es.res_lo && (es.res_f32 || es.res_mode == RES_NONE || (es.res_lo % 8)))
         return set_err(e, DV_ERR_ARG, "%s: split residual needs an fp16 residual and res_lo %% 8 == 0", name);
@@ -384,6 +387,8 @@ static IGemmKernel pick_kernel(int act, int out_f32, int res_f32, int argmax) {
         case ACT_SIGMOID * 2 + 1: return conv_igemm_tcgen05<ACT_SIGMOID, true, false, false>;
         case ACT_HSWISH * 2: return conv_igemm_tcgen05<ACT_HSWISH, false, false, false>;
         case ACT_HSWISH * 2 + 1: return conv_igemm_tcgen05<ACT_HSWISH, true, false, false>;
+        case ACT_SWISH * 2: return conv_igemm_tcgen05<ACT_SWISH, false, false, false>;
+        case ACT_SWISH * 2 + 1: return conv_igemm_tcgen05<ACT_SWISH, true, false, false>;
         default: return nullptr;
     }
 }
@@ -397,7 +402,7 @@ int launch_conv(Engine* e, const ConvPlan& plan) {
                 attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(k),
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
         };
-        for (int act = 0; act <= ACT_HSWISH; ++act)
+        for (int act = 0; act <= ACT_SWISH; ++act)
             for (int f = 0; f < 2; ++f) set(pick_kernel(act, f, 0, 0));
         set(pick_kernel(ACT_NONE, 1, 1, 0));
         set(pick_kernel(ACT_NONE, 1, 0, 1));

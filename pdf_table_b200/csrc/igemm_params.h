@@ -15,7 +15,7 @@ enum AMode : int {
                      // memory (TMA box {BK, 16, 18}) and the nine taps are shifted UMMA descriptors into it; only the
                      // per-tap weight tiles stream through the stage ring
 };
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_HSWISH = 4 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_HSWISH = 4, ACT_SWISH = 5 };
 enum ResMode : int { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };
 enum OutMode : int { OUT_NHWC = 0, OUT_REPL = 1, OUT_SHUF2 = 2 };
 
@@ -55,6 +55,10 @@ struct IGemmParams {
     int split_off;
     // fp16 residual stored as a split pair: > 0 = add the lo half found res_split_off columns after the hi half
     int res_split_off;
+    // post_affine != 0: y = act(x) * post_scale + post_bias (the LearnableAffineBlock that follows the activation in
+    // PPLCNetV3's rep layers; it cannot be folded into the next layer across a zero-padded depthwise conv or an SE gate)
+    int post_affine;
+    float post_scale, post_bias;
 };
 
 }  // namespace dv

@@ -536,6 +536,49 @@ class Engine:
               self._h, "dv_picodet_forward_u8")
         return scores, dfl
 
+    # ------------------------------------------------------------------ PP-OCR recogniser (model kind "pp_rec")
+    def rec_time_steps(self, height: int, width: int) -> int:
+        return int(self._lib.dv_rec_time_steps(self._h, int(height), int(width)))
+
+    @property
+    def rec_num_classes(self) -> int:
+        return int(self._lib.dv_rec_num_classes(self._h))
+
+    def _rec_outputs(self, n, h, w, dev, return_probs):
+        t, c = self.rec_time_steps(h, w), self.rec_num_classes
+        if t <= 0:
+            raise ValueError(f"rec_forward: a {h}x{w} input is too small for the network")
+        ids = torch.empty((n, t), dtype=torch.int32, device=dev)
+        maxp = torch.empty((n, t), dtype=torch.float32, device=dev)
+        probs = torch.empty((n, t, c), dtype=torch.float32, device=dev) if return_probs else None
+        return ids, maxp, probs
+
+    def rec_forward(self, x: torch.Tensor, return_probs: bool = False):
+        """fp32 NCHW [N,3,48,W] (cuda; PPOcrRecPreProcessor's batch) -> (ids int32 [N,T], maxp fp32 [N,T][, probs fp32 [N,T,C]])."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("rec_forward expects [N,3,H,W]")
+        ids, maxp, probs = self._rec_outputs(n, h, w, x.device, return_probs)
+        check(self._lib.dv_rec_forward(self._h, _ptr(x), n, h, w, _ptr(probs), _ptr(ids), _ptr(maxp)), self._h, "dv_rec_forward")
+        return (ids, maxp, probs) if return_probs else (ids, maxp)
+
+    def rec_forward_u8(self, crops: torch.Tensor, widths: Optional[torch.Tensor] = None, return_probs: bool = False):
+        """uint8 HWC [N,48,W,3] (cuda; resized crops, left aligned, valid up to widths[n]) -> as rec_forward; the normalisation
+        (x / 255 - 0.5) / 0.5 and the zero padding beyond each width are fused into the first kernel."""
+        crops = _require_cuda(crops, torch.uint8, "crops")
+        n, h, w, c = crops.shape
+        if c != 3:
+            raise ValueError("rec_forward_u8 expects [N,H,W,3]")
+        if widths is not None:
+            widths = _require_cuda(widths, torch.int32, "widths")
+            if widths.numel() != n:
+                raise ValueError("one width per crop")
+        ids, maxp, probs = self._rec_outputs(n, h, w, crops.device, return_probs)
+        check(self._lib.dv_rec_forward_u8(self._h, _ptr(crops), _ptr(widths), n, h, w, _ptr(probs), _ptr(ids), _ptr(maxp)), self._h,
+              "dv_rec_forward_u8")
+        return (ids, maxp, probs) if return_probs else (ids, maxp)
+
     def picodet_decode(self, scores, dfl, org_hw, scale_factor, in_hw=(800, 608), strides=(8, 16, 32, 64), score_threshold: float = 0.5,
                        nms_threshold: float = 0.5, nms_top_k: int = 1000, keep_top_k: int = 100):
         """scores[l] fp32 [N,HW_l,C], dfl[l] fp32 [N,HW_l,4*(reg_max+1)] (cuda, 4 levels); org_hw [N,2] (h, w), scale_factor [N,2]

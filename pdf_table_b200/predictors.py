@@ -237,8 +237,9 @@ class PPOcrRecPreProcessor:
     zero padding run in one kernel (``dv_pp_rec_normalise``), bit-exact."""
 
     def __init__(self, engine: Engine, rec_image_shape=(3, 48, 320), rec_batch_num: int = 6, limited_max_width: int = 1280,
-                 limited_min_width: int = 16):
+                 limited_min_width: int = 16, return_u8: bool = False):
         self.engine = engine
+        self.return_u8 = return_u8
         self.rec_image_shape = tuple(rec_image_shape)
         self.rec_batch_num = rec_batch_num
         self.limited_max_width, self.limited_min_width = limited_max_width, limited_min_width
@@ -264,6 +265,9 @@ class PPOcrRecPreProcessor:
             stage = np.zeros((len(widths), img_h, img_w, 3), np.uint8)
             for k, rw in enumerate(widths):
                 stage[k, :, :rw] = cv2.resize(imgs[indices[beg + k]], (rw, img_h))
+            if self.return_u8:  # the recogniser fuses the normalisation: keep the resized uint8 crops + their widths
+                out.append({"image_u8": stage, "widths": np.array(widths, np.int32), "indices": indices, "batch_beg_img_no": beg})
+                continue
             image = self.engine.pp_rec_normalise(torch.from_numpy(stage).to(dev),
                                                  torch.tensor(widths, dtype=torch.int32, device=dev))
             out.append({"image": image, "indices": indices, "batch_beg_img_no": beg})
@@ -537,18 +541,68 @@ class OcrRecognitionTask(BaseInferTask):
 
     def __init__(self, task: str = "ocr_recognition", model: str = "ConvNextViT", task_type: str = "general", state_dict=None,
                  vocab: Optional[Sequence[str]] = None, **kwargs):
-        if model != "ConvNextViT":
+        if model not in ("ConvNextViT", "PP-OCRv4"):
             raise RuntimeError(f"model {model} not support")
         if state_dict is None:
-            raise RuntimeError("OcrRecognitionTask(predictor_type='b200') needs state_dict= (a ConvNextViT state_dict or a path)")
+            raise RuntimeError("OcrRecognitionTask(predictor_type='b200') needs state_dict= (the recogniser's state_dict or a path)")
+        if model == "PP-OCRv4" and kwargs.get("precision", "fp16") != "fp16":
+            raise RuntimeError("the PP-OCRv4 recogniser runs in fp16 operand precision only")
         self._sd = _load_state_dict(state_dict)
-        self.label_mapping = {i + 2: ch for i, ch in enumerate(vocab)} if vocab is not None else None
+        if model == "PP-OCRv4":
+            # CTCLabelDecode (ocr_rec_pp/rec_postprocess.py:20-45, 163-165): character = ['blank'] + dict lines + [' '] (use_space_char)
+            self.character = ["blank"] + list(vocab) + [" "] if vocab is not None else None
+            self.label_mapping = None
+        else:
+            self.label_mapping = {i + 2: ch for i, ch in enumerate(vocab)} if vocab is not None else None
         super().__init__(task=task, model=model, **kwargs)
         self.post = Engine("post", device=self.device)
+        if model == "PP-OCRv4":
+            self._pp_pre = PPOcrRecPreProcessor(self.post, return_u8=True)
+            if self.character is not None and len(self.character) != self.predictor.rec_num_classes:
+                raise RuntimeError(f"PP-OCRv4: the dictionary gives {len(self.character)} classes, the network has {self.predictor.rec_num_classes}")
 
     def _construct_model(self, model):
-        self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd, precise=self.precision == "fp32x"), device=self.device)
+        if model == "PP-OCRv4":
+            from .pp_rec_graph import pack_pp_rec
+
+            self.predictor = Engine("pp_rec", pack_pp_rec(self._sd), device=self.device)
+        else:
+            self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
+
+    # ---- model="PP-OCRv4": PPOcrRecPreProcessor (a4) -> SVTR-LCNet (a5) -> CTC greedy decode (a6)
+    def _pp_call(self, inputs):
+        """OcrRecognitionTask.__call__ for the PaddleOCR models (ocr_recognition_task.py:62-136): aspect-sorted batches of six with
+        their own padded width (a4, host cv2.resize as the reference); batches of EQUAL width share one network launch (every op
+        of the network is per crop, so the result of a crop depends only on its own pixels and the padded width); per-step
+        arg-max / max probability come from the network's last kernel, dv_ctc_collapse decodes them on the device and the
+        characters are looked up on the host.  Returns the text of EVERY crop in input order (the reference's post-processor
+        keeps only one entry of a multi-crop list, processor_ocr_rec_pp.py:150-160 -- its orchestrator always passes one crop)."""
+        items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        batches = self._pp_pre(list(items))
+        dev = torch.device("cuda", self.device)
+        by_w: Dict[int, List[int]] = {}
+        for bi, bt in enumerate(batches):
+            by_w.setdefault(int(bt["image_u8"].shape[2]), []).append(bi)
+        pending = []
+        for w, bis in by_w.items():
+            crops = np.concatenate([batches[bi]["image_u8"] for bi in bis])
+            widths = np.concatenate([batches[bi]["widths"] for bi in bis])
+            order = np.concatenate([batches[bi]["indices"][batches[bi]["batch_beg_img_no"]: batches[bi]["batch_beg_img_no"] + len(batches[bi]["widths"])]
+                                    for bi in bis])
+            ids, maxp = self.predictor.rec_forward_u8(_h2d(torch.from_numpy(crops), dev), _h2d(torch.from_numpy(widths), dev))
+            out, ln, conf = self.post.ctc_collapse(ids, maxp)
+            pending.append((order, _d2h_async(out), _d2h_async(ln), _d2h_async(conf)))
+        torch.cuda.current_stream().synchronize()
+        texts: List[Optional[str]] = [None] * len(items)
+        self.last_confidences = [0.0] * len(items)
+        for order, out, ln, conf in pending:
+            out, ln, conf = out.numpy(), ln.numpy(), conf.numpy()
+            for k, i in enumerate(order):
+                seq = out[k, : ln[k]]
+                texts[int(i)] = " ".join(str(int(v)) for v in seq) if self.character is None else "".join(self.character[int(v)] for v in seq)
+                self.last_confidences[int(i)] = float(conf[k])
+        return texts
 
     def _preprocess(self, inputs) -> Dict[str, Any]:
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
@@ -572,6 +626,8 @@ class OcrRecognitionTask(BaseInferTask):
         """post(run(pre(x))) like the reference; a long list is walked in chunks of CALL_CHUNK crops so that the host
         pre-processing (cv2.resize, padding) of chunk k+1 overlaps the device work of chunk k (nothing waits for the GPU
         before the final _postprocess)."""
+        if self.model == "PP-OCRv4":
+            return self._pp_call(inputs)
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
         if len(items) <= self.CALL_CHUNK:
             return self._postprocess(self._run_model(self._preprocess(inputs), **kwargs), **kwargs)

@@ -653,3 +653,69 @@ def centernet_dla34_state_dict(seed: int = 0, perturb_up: bool = True) -> "Order
         sd[f"{head}.2.weight"] = _conv(rng, classes, 256, 1, 1, gain=1.0)
         sd[f"{head}.2.bias"] = _b(rng, classes) if head != "hm" else np.full(classes, -2.19, np.float32)
     return sd
+
+
+# --------------------------------------------------------------------------- PP-OCRv4 rec (PPLCNetV3-0.95 + SVTR neck + CTC)
+PP_REC_CONFIG = {  # PaddleOCR rec_lcnetv3.py NET_CONFIG_rec: k, in_c, out_c, stride, use_se
+    "blocks2": [[3, 16, 32, 1, False]],
+    "blocks3": [[3, 32, 64, 1, False], [3, 64, 64, 1, False]],
+    "blocks4": [[3, 64, 128, (2, 1), False], [3, 128, 128, 1, False]],
+    "blocks5": [[3, 128, 256, (1, 2), False], [5, 256, 256, 1, False], [5, 256, 256, 1, False], [5, 256, 256, 1, False],
+                [5, 256, 256, 1, False]],
+    "blocks6": [[5, 256, 512, (2, 1), True], [5, 512, 512, 1, True], [5, 512, 512, (2, 1), False], [5, 512, 512, 1, False]],
+}
+
+
+def pp_rec_ch(c: int, scale: float = 0.95) -> int:
+    """make_divisible(c * scale, 16) of rec_lcnetv3.py."""
+    v = c * scale
+    new_v = max(16, int(v + 8) // 16 * 16)
+    return new_v + 16 if new_v < 0.9 * v else new_v
+
+
+def pp_ocrv4_rec_state_dict(seed: int = 0, n_class: int = 97) -> "OrderedDict[str, np.ndarray]":
+    """Seeded weights of the deploy-form PP-OCRv4 recogniser (keys: oracle/pp_rec_ref.py).  The LearnableAffineBlock scalars are
+    drawn away from their (1, 0) initial values so that every affine is exercised."""
+    rng = np.random.Generator(np.random.PCG64(seed + 4040))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def lab(p):
+        sd[p + ".scale"] = rng.uniform(0.8, 1.25, 1).astype(np.float32)
+        sd[p + ".bias"] = (rng.standard_normal(1) * 0.05).astype(np.float32)
+
+    def rep(p, cin, cout, k, groups):
+        sd[p + ".reparam_conv.weight"] = _conv(rng, cout, cin // groups, k, k)
+        sd[p + ".reparam_conv.bias"] = _b(rng, cout)
+        lab(p + ".lab")
+        lab(p + ".act.lab")
+
+    sd["backbone.conv1.conv.weight"] = _conv(rng, 16, 3, 3, 3)
+    _bn(rng, sd, "backbone.conv1.bn", 16)
+    for name, cfg in PP_REC_CONFIG.items():
+        for i, (k, cin, cout, s, se) in enumerate(cfg):
+            ci, co = pp_rec_ch(cin), pp_rec_ch(cout)
+            p = f"backbone.{name}.{i}"
+            rep(p + ".dw_conv", ci, ci, k, ci)
+            if se:
+                sd[p + ".se.conv1.weight"] = _conv(rng, ci // 4, ci, 1, 1)
+                sd[p + ".se.conv1.bias"] = _b(rng, ci // 4)
+                sd[p + ".se.conv2.weight"] = _conv(rng, ci, ci // 4, 1, 1)
+                sd[p + ".se.conv2.bias"] = _b(rng, ci)
+            rep(p + ".pw_conv", ci, co, 1, 1)
+    cb, d = pp_rec_ch(512), 120
+    p = "head.ctc_encoder.encoder"
+    for name, cin, cout, kw in (("conv1", cb, cb // 8, 3), ("conv2", cb // 8, d, 1), ("conv3", d, cb, 1), ("conv4", 2 * cb, cb // 8, 3),
+                                ("conv1x1", cb // 8, d, 1)):
+        sd[f"{p}.{name}.conv.weight"] = _conv(rng, cout, cin, 1, kw)
+        _bn(rng, sd, f"{p}.{name}.norm", cout)
+    for i in range(2):
+        q = f"{p}.svtr_block.{i}"
+        _ln(rng, sd, q + ".norm1", d)
+        sd[q + ".mixer.qkv.weight"], sd[q + ".mixer.qkv.bias"] = _lin(rng, 3 * d, d), _b(rng, 3 * d)
+        sd[q + ".mixer.proj.weight"], sd[q + ".mixer.proj.bias"] = _lin(rng, d, d), _b(rng, d)
+        _ln(rng, sd, q + ".norm2", d)
+        sd[q + ".mlp.fc1.weight"], sd[q + ".mlp.fc1.bias"] = _lin(rng, 2 * d, d), _b(rng, 2 * d)
+        sd[q + ".mlp.fc2.weight"], sd[q + ".mlp.fc2.bias"] = _lin(rng, d, 2 * d), _b(rng, d)
+    _ln(rng, sd, p + ".norm", d)
+    sd["head.ctc_head.fc.weight"], sd["head.ctc_head.fc.bias"] = _lin(rng, n_class, d, gain=4.0), _b(rng, n_class)
+    return sd

@@ -23,6 +23,7 @@ def test_reference_arm_json_line():
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["config"]["workload"].startswith("BASELINE configs[4]") and "model" not in d["config"]  # the default line = the full cascade
     assert d["blocks"]["rec_sweep"]["unit"] == "crops/s" and d["blocks"]["rec_sweep"]["value"] > 0 and d["blocks"]["lore"]["unit"] == "images/s"
+    assert d["blocks"]["pp_rec"]["unit"] == "crops/s" and d["blocks"]["pp_rec"]["value"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

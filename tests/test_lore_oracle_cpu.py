@@ -235,3 +235,26 @@ def test_picodet_lowering_computes_the_reference_function():
             assert s.shape == ws[lvl].shape and d.shape == wd[lvl].shape
             assert float((s - ws[lvl]).abs().max()) < tol
             assert float((d - wd[lvl]).abs().max()) < tol * max(1.0, float(wd[lvl].abs().max()))
+
+
+def test_pp_rec_graph_program_reproduces_the_oracle_on_cpu():
+    """The lowering of the PP-OCRv4 recogniser (pp_rec_graph.py: rep-layer affines folded / kept as post-activation affines,
+    BatchNorm folding, (1,3) convs as unfold + GEMM, channel padding 60 -> 64, attention scale folded into q, concatenation
+    slices, CTC head padding) run op by op with the executor's semantics equals the oracle of the published architecture up to
+    the fp16 rounding of the packed weights (and of the activation buffers)."""
+    import torch
+
+    from oracle import graph_interp, pp_rec_ref
+    from pdf_table_b200 import pp_rec_graph, synth
+
+    sd = synth.pp_ocrv4_rec_state_dict(0, 97)
+    blob, meta = pp_rec_graph.build_pp_rec(sd)
+    assert meta["n_class"] == 97 and int(blob["graph.meta"][5]) == 1
+    for w in (320, 325, 96):
+        x = torch.from_numpy(np.random.default_rng(1).standard_normal((2, 3, 48, w)).astype(np.float32))
+        want, want_logits = pp_rec_ref.pp_rec_forward(sd, x, return_logits=True)
+        for fp16_act, tol in ((False, 4e-2), (True, 6e-2)):
+            _, heads = graph_interp.run_program(blob, x, fp16_activations=fp16_act)
+            assert tuple(heads["probs"].shape) == tuple(want.shape)
+            assert float((heads["logits"] - want_logits).abs().max()) < tol  # logit std ~4.7
+            assert float((heads["probs"] - want).abs().max()) < 1e-2
