@@ -378,7 +378,9 @@ def roofline_of(agg, peaks, peak_src, workload_key):
     common = {"kernel": top, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": tk["bytes"] / tk["n"],
               "algorithmic_flops_per_launch": tk["flops"] / tk["n"], "launches": tk["n"], "avg_launch_ms": tk["ms"] / tk["n"],
               "share_of_step": tk["ms"] / tot_ms, "hbm_achieved_gbs": tk["bytes"] / (tk["ms"] / 1e3) / 1e9}
-    if tk["flops"] > 0:
+    # a kernel whose arithmetic intensity is below the ridge (peak FLOP/s / peak B/s) is judged against the HBM roofline
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    if tk["flops"] > 0 and tk["flops"] / max(tk["bytes"], 1.0) >= ridge * 0.25:
         ach = tk["flops"] / (tk["ms"] / 1e3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"], "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)", **common}

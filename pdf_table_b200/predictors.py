@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Any, Dict, List, Mapping, Optional, Sequence, Union
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -302,6 +302,22 @@ def _to_device_u8(img, dev: torch.device) -> torch.Tensor:
     return _h2d(torch.from_numpy(np.ascontiguousarray(img)), dev)
 
 
+def _pack_u8(imgs: Sequence[np.ndarray]):
+    """uint8 HWC images -> (one flat uint8 array, byte offsets int64 [n]).  Images that are consecutive views of one contiguous
+    array (``list(batch)``) are used in place; anything else is concatenated once."""
+    n = len(imgs)
+    sizes = np.array([im.size for im in imgs], np.int64)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    first = imgs[0]
+    if n > 1 and first.base is not None and first.dtype == np.uint8 and all(
+            im.base is first.base and im.flags["C_CONTIGUOUS"] and im.dtype == np.uint8 and
+            im.__array_interface__["data"][0] == first.__array_interface__["data"][0] + int(offs[k]) for k, im in enumerate(imgs)):
+        total = int(sizes.sum())
+        flat = np.lib.stride_tricks.as_strided(first.reshape(-1), shape=(total,), strides=(1,), writeable=False)
+        return flat, offs
+    return np.concatenate([np.ascontiguousarray(im, dtype=np.uint8).reshape(-1) for im in imgs]), offs
+
+
 def order_points_batch(quads: np.ndarray) -> np.ndarray:
     """``order_point`` for n quads at once ([n,8] or [n,4,2] -> float32 [n,4,2]): the same numpy operations applied along a
     batch axis (sum / divide for the centroid, arctan2, the default argsort per quad, the rotation when the first corner is
@@ -570,27 +586,56 @@ class OcrRecognitionTask(BaseInferTask):
             self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
 
+    @staticmethod
+    def pp_read(items) -> List[np.ndarray]:
+        """Input decoding of PPOcrRecPreProcessor.__call__ (processor_ocr_rec_pp.py:69-98): path / PIL / ndarray, grey -> RGB."""
+        imgs = []
+        for it in items:
+            img = _read_image(it)
+            if img.ndim == 2:
+                import cv2
+
+                img = cv2.cvtColor(img, cv2.COLOR_GRAY2RGB)
+            imgs.append(img)
+        return imgs
+
+    def pp_batches_device(self, imgs: Sequence[np.ndarray]):
+        """a4 on the device: the batch plan (aspect sort, groups of six, padded width per group, resized width per crop) is the
+        reference's host rule (``pp_rec_batch_plan``); the cv2.resize of every crop is dv_resize_linear_u8 (bit-exact against
+        cv2) over ONE upload of the raw crops, written straight into the zero-padded uint8 batch the network's first kernel reads.
+        Groups of equal padded width are merged.  Returns [(original indices, uint8 [n,48,W,3] cuda, widths int32 [n] cuda)]."""
+        dev = torch.device("cuda", self.device)
+        indices, plan = pp_rec_batch_plan([im.shape[:2] for im in imgs])
+        flat, offs = _pack_u8(imgs)
+        import warnings
+
+        with warnings.catch_warnings():  # the in-place view of the caller's batch is read-only for torch: it is only uploaded
+            warnings.simplefilter("ignore", UserWarning)
+            src = _h2d(torch.from_numpy(flat), dev)
+        by_w: Dict[int, List[Tuple[int, int]]] = {}
+        for beg, img_w, widths in plan:
+            by_w.setdefault(int(img_w), []).extend((int(indices[beg + k]), int(rw)) for k, rw in enumerate(widths))
+        out = []
+        for w, members in by_w.items():
+            order = np.array([m[0] for m in members], np.int64)
+            widths = np.array([m[1] for m in members], np.int32)
+            sizes = np.array([[imgs[i].shape[1], imgs[i].shape[0]] for i in order], np.int32)
+            crops = self.post.resize_linear_u8((src, _h2d(torch.from_numpy(offs[order]), dev), _h2d(torch.from_numpy(sizes), dev)), widths, 48, w)
+            out.append((order, crops, _h2d(torch.from_numpy(widths), dev)))
+        return out
+
     # ---- model="PP-OCRv4": PPOcrRecPreProcessor (a4) -> SVTR-LCNet (a5) -> CTC greedy decode (a6)
     def _pp_call(self, inputs):
         """OcrRecognitionTask.__call__ for the PaddleOCR models (ocr_recognition_task.py:62-136): aspect-sorted batches of six with
-        their own padded width (a4, host cv2.resize as the reference); batches of EQUAL width share one network launch (every op
+        their own padded width (a4: ``pp_batches_device``); batches of EQUAL width share one network launch (every op
         of the network is per crop, so the result of a crop depends only on its own pixels and the padded width); per-step
         arg-max / max probability come from the network's last kernel, dv_ctc_collapse decodes them on the device and the
         characters are looked up on the host.  Returns the text of EVERY crop in input order (the reference's post-processor
         keeps only one entry of a multi-crop list, processor_ocr_rec_pp.py:150-160 -- its orchestrator always passes one crop)."""
         items = inputs if isinstance(inputs, (list, tuple)) else [inputs]
-        batches = self._pp_pre(list(items))
-        dev = torch.device("cuda", self.device)
-        by_w: Dict[int, List[int]] = {}
-        for bi, bt in enumerate(batches):
-            by_w.setdefault(int(bt["image_u8"].shape[2]), []).append(bi)
         pending = []
-        for w, bis in by_w.items():
-            crops = np.concatenate([batches[bi]["image_u8"] for bi in bis])
-            widths = np.concatenate([batches[bi]["widths"] for bi in bis])
-            order = np.concatenate([batches[bi]["indices"][batches[bi]["batch_beg_img_no"]: batches[bi]["batch_beg_img_no"] + len(batches[bi]["widths"])]
-                                    for bi in bis])
-            ids, maxp = self.predictor.rec_forward_u8(_h2d(torch.from_numpy(crops), dev), _h2d(torch.from_numpy(widths), dev))
+        for order, crops, widths_dev in self.pp_batches_device(self.pp_read(items)):
+            ids, maxp = self.predictor.rec_forward_u8(crops, widths_dev)
             out, ln, conf = self.post.ctc_collapse(ids, maxp)
             pending.append((order, _d2h_async(out), _d2h_async(ln), _d2h_async(conf)))
         torch.cuda.current_stream().synchronize()

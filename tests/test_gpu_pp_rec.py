@@ -87,6 +87,19 @@ def test_recognition_task_pp_ocrv4_chain():
     got = task(crops)
     assert isinstance(got, list) and len(got) == len(crops) and all(isinstance(t, str) for t in got)
     g = np.load(GOLDEN)
+    # a4 on the device (resize + fused normalisation) == the reference pre-processor's own batches, bit for bit
+    seen = 0
+    for order, crops_u8, widths in task.pp_batches_device(task.pp_read(crops)):
+        x = task.post.pp_rec_normalise(crops_u8, widths).cpu().numpy()
+        for k in range(int(g["n_batches"])):
+            beg, img = int(g[f"beg{k}"]), g[f"image{k}"]
+            if img.shape[3] != x.shape[3]:
+                continue
+            for j in range(img.shape[0]):
+                row = int(np.where(order == int(g["indices"][beg + j]))[0][0])
+                np.testing.assert_array_equal(x[row], img[j])
+                seen += 1
+    assert seen == len(crops)
     character = ["blank"] + vocab + [" "]
     want = [None] * len(crops)
     safe = True
