@@ -235,7 +235,7 @@ double dv_model_flops(dv_handle h) {
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
     if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_flops(h);
-    if (h->kind == "picodet") return graph_flops(h);
+    if (h->kind == "picodet" || h->kind == "pp_rec") return graph_flops(h);
     return 0.0;
 }
 

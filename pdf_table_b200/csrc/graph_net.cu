@@ -147,12 +147,24 @@ k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
 }
 
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // Depthwise k x k, stride 1 along W (any stride along H): one thread = 8 channels x P consecutive output pixels of a row.
 // The K + P - 1 input pixels a filter row touches are loaded ONCE into registers and slid across the P outputs, and every
 // filter tap's weights are loaded once per thread instead of once per output: 3.0x (k = 3) / 3.3x (k = 5) fewer load
 // instructions per output than k_dwconv, which was LSU-bound at 0.7 TB/s on the PP-OCRv4 backbone (profiles/r3h_bench.json).
 template <int K, int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_dwconv_row(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int sh, int Ho, int Wo,
              const float* __restrict__ w, const float* __restrict__ b, int act, float ps, float pb, __half* __restrict__ out, int ldo) {
     const int cv = C >> 3;
@@ -165,13 +177,14 @@ k_dwconv_row(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
     t /= wq;
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
     constexpr int PAD = (K - 1) / 2;
-    float acc[P][8];
+    // accumulators, pixels and weights live as packed fp32 pairs: Blackwell's fma.rn.f32x2 issues two IEEE FMAs per slot (same
+    // bits as two fmaf), and this kernel is issue-bound (ncu profiles/r3m_dwconv_ncu.txt: 62 % issue slots busy, L1 73 %, DRAM 16 %)
+    uint64_t acc[P][4];
     {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + c8 * 8 + 4));
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            acc[p][0] = b0.x, acc[p][1] = b0.y, acc[p][2] = b0.z, acc[p][3] = b0.w;
-            acc[p][4] = b1.x, acc[p][5] = b1.y, acc[p][6] = b1.z, acc[p][7] = b1.w;
+            acc[p][0] = pk2(b0.x, b0.y), acc[p][1] = pk2(b0.z, b0.w), acc[p][2] = pk2(b1.x, b1.y), acc[p][3] = pk2(b1.z, b1.w);
         }
     }
 #pragma unroll
@@ -179,29 +192,28 @@ k_dwconv_row(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
         const int iy = oy * sh - PAD + r;
         if (iy < 0 || iy >= H) continue;
         const __half* row = in + (static_cast<long long>(n) * H + iy) * W * ldi + c8 * 8;
-        uint4 px[K + P - 1];
+        // the K + P - 1 pixels of this filter row, converted to fp32 ONCE (each feeds up to K outputs)
+        uint64_t fx[K + P - 1][4];
 #pragma unroll
         for (int j = 0; j < K + P - 1; ++j) {
             const int ix = ox0 - PAD + j;
-            px[j] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * ldi)) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 u = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * ldi)) : make_uint4(0u, 0u, 0u, 0u);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 v = __half22float2(h[i]);
+                fx[j][i] = pk2(v.x, v.y);
+            }
         }
 #pragma unroll
         for (int s = 0; s < K; ++s) {
             const float4* wp = reinterpret_cast<const float4*>(w + static_cast<long long>(r * K + s) * C + c8 * 8);
             const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            const uint64_t wv[4] = {pk2(w0.x, w0.y), pk2(w0.z, w0.w), pk2(w1.x, w1.y), pk2(w1.z, w1.w)};
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const __half2* h = reinterpret_cast<const __half2*>(&px[p + s]);
-                const float2 v0 = __half22float2(h[0]), v1 = __half22float2(h[1]), v2 = __half22float2(h[2]), v3 = __half22float2(h[3]);
-                acc[p][0] = fmaf(v0.x, w0.x, acc[p][0]);
-                acc[p][1] = fmaf(v0.y, w0.y, acc[p][1]);
-                acc[p][2] = fmaf(v1.x, w0.z, acc[p][2]);
-                acc[p][3] = fmaf(v1.y, w0.w, acc[p][3]);
-                acc[p][4] = fmaf(v2.x, w1.x, acc[p][4]);
-                acc[p][5] = fmaf(v2.y, w1.y, acc[p][5]);
-                acc[p][6] = fmaf(v3.x, w1.z, acc[p][6]);
-                acc[p][7] = fmaf(v3.y, w1.w, acc[p][7]);
-            }
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[p][i] = fma2(fx[p + s][i], wv[i], acc[p][i]);
         }
     }
 #pragma unroll
@@ -210,8 +222,84 @@ k_dwconv_row(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
         uint4 o;
         __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(fmaf(act_f(acc[p][2 * i], act), ps, pb), fmaf(act_f(acc[p][2 * i + 1], act), ps, pb));
+        for (int i = 0; i < 4; ++i) {
+            float a0, a1;
+            upk2(acc[p][i], a0, a1);
+            ho[i] = __floats2half2_rn(fmaf(act_f(a0, act), ps, pb), fmaf(act_f(a1, act), ps, pb));
+        }
         *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox0 + p) * ldo + c8 * 8) = o;
+    }
+}
+
+// Depthwise k x k, stride 1 along W, stride SH along H: one thread = 2 channels x P consecutive output pixels x R output rows,
+// ALL k * k filter taps of its channel pair held in registers.  ncu on k_dwconv_row (profiles/r3m_dwconv_ncu.txt) showed the
+// L1 data path at 73 % with DRAM at 16 %: per output it re-loaded every tap's weights (32 B) and K input pixels per filter row.
+// Here a warp's 32 lanes read 32 consecutive channel pairs of one pixel (one 128-byte line per load instruction), weights cost
+// no loads inside the loop, an input row is loaded once for the R output rows it feeds and each pixel feeds up to K outputs:
+// ~0.3 B of L1 traffic per FMA instead of ~1.1.
+template <int K, int P, int R, int SH>
+__global__ void __launch_bounds__(128)
+k_dwconv_c2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int Ho, int Wo, const float* __restrict__ w,
+            const float* __restrict__ b, int act, float ps, float pb, __half* __restrict__ out, int ldo) {
+    const int cp = C >> 1;
+    const int wq = (Wo + P - 1) / P, hq = (Ho + R - 1) / R;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * hq * wq * cp) return;
+    const int c2 = static_cast<int>(idx % cp);
+    long long t = idx / cp;
+    const int ox0 = static_cast<int>(t % wq) * P;
+    t /= wq;
+    const int oy0 = static_cast<int>(t % hq) * R, n = static_cast<int>(t / hq);
+    constexpr int PAD = (K - 1) / 2;
+    uint64_t wv[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(w + static_cast<long long>(i) * C + c2 * 2));
+        wv[i] = pk2(v.x, v.y);
+    }
+    uint64_t acc[R][P];
+    {
+        const float2 bv = __ldg(reinterpret_cast<const float2*>(b + c2 * 2));
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < P; ++p) acc[r][p] = pk2(bv.x, bv.y);
+    }
+    constexpr int ROWS = (R - 1) * SH + K;  // input rows feeding the R output rows
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+        const int iy = oy0 * SH - PAD + j;
+        if (iy < 0 || iy >= H) continue;
+        const __half* row = in + (static_cast<long long>(n) * H + iy) * W * ldi + c2 * 2;
+        uint64_t fx[K + P - 1];
+#pragma unroll
+        for (int q = 0; q < K + P - 1; ++q) {
+            const int ix = ox0 - PAD + q;
+            float2 v = make_float2(0.f, 0.f);
+            if (ix >= 0 && ix < W) v = __half22float2(__ldg(reinterpret_cast<const __half2*>(row + static_cast<long long>(ix) * ldi)));
+            fx[q] = pk2(v.x, v.y);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int fr = j - r * SH;  // filter row of output row r that reads input row j (compile-time after unrolling)
+            if (fr < 0 || fr >= K) continue;
+#pragma unroll
+            for (int s2 = 0; s2 < K; ++s2)
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[r][p] = fma2(fx[p + s2], wv[fr * K + s2], acc[r][p]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (oy0 + r >= Ho) break;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if (ox0 + p >= Wo) break;
+            float a0, a1;
+            upk2(acc[r][p], a0, a1);
+            *reinterpret_cast<__half2*>(out + ((static_cast<long long>(n) * Ho + oy0 + r) * Wo + ox0 + p) * ldo + c2 * 2) =
+                __floats2half2_rn(fmaf(act_f(a0, act), ps, pb), fmaf(act_f(a1, act), ps, pb));
+        }
     }
 }
 
@@ -495,8 +583,49 @@ struct GraphNet : Model {
     float* se_scale = nullptr;
     float* head_raw = nullptr;
     double flops = 0;
+    // plans of other input shapes (the recogniser alternates between a full pass and a tail pass, and between padded widths):
+    // a shape change parks the current plan here instead of freeing it
+    struct Saved {
+        int N, H, W;
+        std::vector<Tensor> tens;
+        std::vector<void*> mem;
+        std::vector<GOp> ops;
+        float *se_scale, *head_raw;
+        double flops;
+    };
+    std::vector<Saved> cache;
+    double last_call_flops = 0;
+    int pass_n = 2048;  // images per pass of the recogniser: bounds the activation workspace (~10 MB per crop); smaller passes are
+                        // SLOWER on the B200 (profiles/r3j_pp_rec_pass_sweep.json: the kernels are issue-bound, not HBM-bound)
     ~GraphNet() override {
         for (void* p : mem) cudaFree(p);
+        for (Saved& sv : cache)
+            for (void* p : sv.mem) cudaFree(p);
+    }
+    void park() {
+        if (N == 0) return;
+        cache.push_back(Saved{N, H, W, std::move(tens), std::move(mem), ops, se_scale, head_raw, flops});
+        mem.clear();
+        tens.clear();
+        N = H = W = 0;
+        if (cache.size() > 6) {
+            for (void* p : cache.front().mem) cudaFree(p);
+            cache.erase(cache.begin());
+        }
+    }
+    bool restore(int n, int h, int w) {
+        for (size_t i = 0; i < cache.size(); ++i)
+            if (cache[i].N == n && cache[i].H == h && cache[i].W == w) {
+                Saved sv = std::move(cache[i]);
+                cache.erase(cache.begin() + i);
+                N = sv.N, H = sv.H, W = sv.W;
+                tens = std::move(sv.tens);
+                mem = std::move(sv.mem);
+                ops = std::move(sv.ops);
+                se_scale = sv.se_scale, head_raw = sv.head_raw, flops = sv.flops;
+                return true;
+            }
+        return false;
     }
     int alloc(void** p, size_t bytes) {
         cudaError_t st = cudaMalloc(p, bytes ? bytes : 16);
@@ -681,6 +810,9 @@ int graph_create(Engine* e) {
     m->reg_bins = hm[1];
     m->head_ld = hm[2];
     m->kind = hm.size() > 5 ? hm[5] : 0;
+    if (const char* ps = getenv("DV_REC_PASS")) {
+        if (atoi(ps) > 0) m->pass_n = atoi(ps);
+    }
     const int tcols = static_cast<int>(tt->dims[1]);  // 2: (c, down); 5: (c, down_h, down_w, pool_h, pool_w)
     for (size_t i = 0; i < tt->dims[0]; ++i) {
         const int32_t* r = &ht[tcols * i];
@@ -712,7 +844,7 @@ int graph_create(Engine* e) {
 
 double graph_flops(Engine* e) {
     GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
-    return m ? m->flops : 0.0;
+    return m ? (m->kind == 1 ? m->last_call_flops : m->flops) : 0.0;
 }
 
 int graph_num_classes(Engine* e) {
@@ -747,7 +879,10 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
               float scale, int flip, int N, int H, int W, const GraphOut& go) {
     float* const* scores_out = go.scores;
     float* const* dfl_out = go.dfl;
-    if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
+    if (m->N != N || m->H != H || m->W != W) {
+        m->park();
+        if (!m->restore(N, H, W)) DV_TRY(build(e, m, N, H, W));
+    }
     cudaStream_t s = e->stream;
     for (GOp& op : m->ops) {
         const Tensor& in = m->tens[op.in_t];
@@ -771,15 +906,29 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 // flops = 0: a depthwise conv is judged against the HBM roofline (k * k MACs per 4 bytes moved)
                 e->launch_begin("k_dwconv", "dw", 0.0, total * 8 * 2.0 * (1.0 + 1.0 * (op.sh() * op.sw())));
                 static const bool row_kernel = !(getenv("DV_DWROW") && atoi(getenv("DV_DWROW")) == 0);
-                if (row_kernel && op.sw() == 1 && (op.k == 3 || op.k == 5)) {
-                    constexpr int P = 4;
-                    const long long tot = static_cast<long long>(N) * out.H * ((out.W + P - 1) / P) * (op.in_c / 8);
-                    if (op.k == 3)
-                        k_dwconv_row<3, P><<<grid_for(tot, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.sh(), out.H, out.W, op.f0,
-                                                                             op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C);
-                    else
-                        k_dwconv_row<5, P><<<grid_for(tot, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.sh(), out.H, out.W, op.f0,
-                                                                             op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C);
+                static const int dw_mode = getenv("DV_DWMODE") ? atoi(getenv("DV_DWMODE")) : 1;  // 1: k_dwconv_row (default), 2: k_dwconv_c2 (2x slower on the B200: 4-byte loads), 0: k_dwconv
+                if (row_kernel && dw_mode == 2 && op.sw() == 1 && (op.k == 3 || op.k == 5) && (op.sh() == 1 || op.sh() == 2)) {
+#define DV_DWC2(KK, PP, RR, SS)                                                                                                                   \
+    k_dwconv_c2<KK, PP, RR, SS><<<grid_for(static_cast<long long>(N) * ((out.H + RR - 1) / RR) * ((out.W + PP - 1) / PP) * (op.in_c / 2), 128), 128, 0, s>>>( \
+        in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W, op.f0, op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C)
+                    if (op.k == 3 && op.sh() == 1) DV_DWC2(3, 8, 2, 1);
+                    else if (op.k == 3) DV_DWC2(3, 8, 2, 2);
+                    else if (op.sh() == 1) DV_DWC2(5, 8, 2, 1);
+                    else DV_DWC2(5, 8, 2, 2);
+#undef DV_DWC2
+                } else if (row_kernel && op.sw() == 1 && (op.k == 3 || op.k == 5)) {
+                    static const int dwp = getenv("DV_DWP") ? atoi(getenv("DV_DWP")) : 8;
+#define DV_DWROW(KK, PP)                                                                                                                        \
+    k_dwconv_row<KK, PP><<<grid_for(static_cast<long long>(N) * out.H * ((out.W + PP - 1) / PP) * (op.in_c / 8), 128), 128, 0, s>>>(              \
+        in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.sh(), out.H, out.W, op.f0, op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C)
+                    if (op.k == 3) {
+                        if (dwp == 8) DV_DWROW(3, 8);
+                        else DV_DWROW(3, 4);
+                    } else {
+                        if (dwp == 8) DV_DWROW(5, 8);
+                        else DV_DWROW(5, 4);
+                    }
+#undef DV_DWROW
                 } else {
                     k_dwconv<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.k, op.sh(), op.sw(), out.H, out.W, op.f0,
                                                                   op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C);
@@ -900,11 +1049,26 @@ int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int
     if (!m || m->kind != 1) return set_err(e, DV_ERR_STATE, "handle was not created as a pp_rec model");
     if (N <= 0 || H <= 0 || W <= 0 || (!in_nchw && !in_u8)) return set_err(e, DV_ERR_ARG, "rec_forward: bad arguments");
     const float half3[3] = {0.5f, 0.5f, 0.5f};
-    GraphOut go;
-    go.probs = probs;
-    go.ids = ids;
-    go.maxp = maxp;
-    return run_graph(e, m, in_nchw, in_u8, widths, half3, half3, 255.0f, /*flip: divide by scale*/ 2, N, H, W, go);
+    const int T = rec_time_steps(e, H, W);
+    if (T <= 0) return set_err(e, DV_ERR_ARG, "rec_forward: a %dx%d input is too small for the network", H, W);
+    // passes of at most pass_n crops (workspace bound); the crops are dealt evenly so that at most two plan shapes alternate
+    // (both stay cached)
+    const int passes = (N + m->pass_n - 1) / m->pass_n;
+    const int chunk = (N + passes - 1) / passes;
+    double flops = 0;
+    for (int done = 0; done < N; done += chunk) {
+        const int cur = N - done < chunk ? N - done : chunk;
+        GraphOut go;
+        go.probs = probs ? probs + static_cast<long long>(done) * T * m->num_classes : nullptr;
+        go.ids = ids ? ids + static_cast<long long>(done) * T : nullptr;
+        go.maxp = maxp ? maxp + static_cast<long long>(done) * T : nullptr;
+        DV_TRY(run_graph(e, m, in_nchw ? in_nchw + static_cast<long long>(done) * 3 * H * W : nullptr,
+                         in_u8 ? in_u8 + static_cast<long long>(done) * H * W * 3 : nullptr, widths ? widths + done : nullptr, half3, half3, 255.0f,
+                         /*flip: divide by scale*/ 2, cur, H, W, go));
+        flops += m->flops;
+    }
+    m->last_call_flops = flops;
+    return 0;
 }
 
 int rec_time_steps(Engine* e, int H, int W) {
