@@ -226,11 +226,9 @@ class Cascade:
         self.n_crops = PAGES_PER_GPU * CROPS_PER_PAGE
         self.n_tables = self.n_pages * TABLES_PER_PAGE if full else 0
         # ---- predictors (public API)
-        rec_sd = synth.convnext_vit_state_dict(0)
         det_task = predictors.OcrDetectionTask(model="db_pp", state_dict=synth.dbnet_r18_state_dict(0), device=device)
-        rec_task = predictors.OcrRecognitionTask(model="ConvNextViT", state_dict=rec_sd, device=device)
-        n_labels = int(rec_task.predictor._lib.dv_convnextvit_labels(rec_task.predictor._h))
-        rec_task.label_mapping = {i + 2: ch for i, ch in enumerate(synthetic_vocab(n_labels))}
+        rec_task = predictors.OcrRecognitionTask(model="PP-OCRv4", state_dict=synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES), device=device,
+                                                 vocab=[chr(33 + i) for i in range(PP_REC_CLASSES - 2)])
         lay_task = tsr_task = None
         if full:
             bb, nk, hd = synth.picodet_state_dicts(0, 5)
@@ -252,17 +250,11 @@ class Cascade:
         self.pages_np = self.pages_pinned.numpy()
         self.pages_dev = self.pages_pinned.to(dev)
         self.planted_maps = torch.from_numpy(make_prob_maps(rank, self.n_pages)).to(dev)
-        self.probs_host = torch.from_numpy(make_ctc_probs(rank, self.n_crops)).pin_memory()
-        self.probs_dev = self.probs_host.to(dev)
-        self.probs_stage = torch.empty_like(self.probs_dev)
         self.src_hw = [(PAGE_H, PAGE_W)] * self.n_pages
-        self.rec_crops = torch.empty((self.n_crops, 32, 804, 3), dtype=torch.uint8, device=dev)
+        self.rec_crops = torch.empty((self.n_crops, 48, 1280, 3), dtype=torch.uint8, device=dev)
         self.crop_ws = (torch.empty((self.n_crops,), dtype=torch.int32, device=dev), torch.empty((self.n_crops, 2), dtype=torch.int32, device=dev),
                         torch.empty((self.n_crops, 3, 3), dtype=torch.float64, device=dev))
-        self.tok_ids = torch.empty((self.n_crops, 201), dtype=torch.int32, device=dev)
         self.prob_map = torch.empty((self.n_pages, 1, PAGE_H, PAGE_W), dtype=torch.float32, device=dev)
-        self.ctc_host = (torch.empty((self.n_crops, CTC_T), dtype=torch.int32).pin_memory(), torch.empty((self.n_crops,), dtype=torch.int32).pin_memory(),
-                         torch.empty((self.n_crops,), dtype=torch.float32).pin_memory())
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # L2 flush buffer (> 126 MB)
         self.api_counts = {}
         if full:
@@ -282,8 +274,8 @@ class Cascade:
     @property
     def stages(self):
         s = ["det_preprocess_u8(fused)", "dbnet_r18_forward", "db_boxes(planted prob maps)",
-             "crop_quads_for_rec(homography + warp + keep-ratio resize)", "rec_preprocess_u8(fused)", "convnextvit_forward+argmax",
-             "ctc_collapse", "ctc_greedy_decode(planted PP-OCR probs)"]
+             "crop_quads_for_rec(homography + warp + PP resize_norm_img width rule)", "pp_rec_preprocess_u8(fused)",
+             "pp_ocrv4_rec_forward(PPLCNetV3 + SVTR + CTC head, per padded-width group)", "softmax+argmax+max", "ctc_greedy_decode"]
         if self.full:
             s = ["page_resize_u8(800x608)", "layout_preprocess_u8(fused)", "picodet_forward", "picodet_decode"] + s + [
                 "crop_tables_for_tsr(slice + warpAffine)", "lore_preprocess_u8(fused)", "lore_dla34_dcn_forward", "lore_decode(wiz_rev)",
@@ -304,10 +296,11 @@ class Cascade:
             self.lay = self.post.picodet_decode(scores, dfl, self.org_hw, self.layout_sf, (800, 608))
         self.det.dbnet_forward_u8(self.pages_dev, MEAN, STD, 1.0 / 255.0, True, out=self.prob_map)
         boxes, counts = self.post.db_boxes(self.planted_maps, self.src_hw)
-        self.post.crop_boxes_for_rec(self.pages_dev, boxes, counts, CROPS_PER_PAGE, out=self.rec_crops, ws=self.crop_ws)
-        self.rec.convnextvit_forward_u8(self.rec_crops, ids=self.tok_ids)
-        r_ids, r_len, _ = self.post.ctc_collapse(self.tok_ids)
-        self.ctc = self.post.ctc_greedy(self.probs_dev)
+        from pdf_table_b200 import predictors
+
+        crops, widths, sizes, _ = self.post.crop_boxes_for_rec(self.pages_dev, boxes, counts, CROPS_PER_PAGE, dst_h=48, dst_w_pad=1280,
+                                                                out=self.rec_crops, ws=self.crop_ws, width_rule=1)
+        r_ids, r_len, _ = predictors.pp_rec_launch_groups(self.rec, self.post, crops, widths, sizes)
         rec.update(boxes=boxes[:, :64].contiguous(), box_counts=counts, ids=r_ids, id_lens=r_len)
         if self.full:
             tables = self.post.crop_tables_for_tsr(self.pages_dev, self.table_rects, self.table_minv, 1024, 1024)
@@ -323,10 +316,6 @@ class Cascade:
 
     # ---- end-to-end leg (public API: numpy pages in, Python results out)
     def step_e2e(self):
-        self.probs_stage.copy_(self.probs_host, non_blocking=True)
-        ids, ln, conf = self.post.ctc_greedy(self.probs_stage)  # the PP-OCR head's decode on planted probabilities (a6)
-        for h, d in zip(self.ctc_host, (ids, ln, conf)):
-            h.copy_(d, non_blocking=True)
         planted = self.planted_maps
         out = self.system.predict_pages(self.pages_np, layout_tables=self.layout_tables if self.full else None,
                                         det_kwargs={"prob_override": lambda prob, idx: planted if len(idx) == planted.shape[0] else planted[idx]},
@@ -336,15 +325,12 @@ class Cascade:
         return self.system.device_record
 
     def e2e_bytes(self):
-        """(h2d, d2h) bytes of ONE e2e step, counted by the predictors' own transfer helpers (predictors.TRANSFER) plus the
-        planted CTC probabilities / decoded ids this class moves itself."""
+        """(h2d, d2h) bytes of ONE e2e step, counted by the predictors' own transfer helpers (predictors.TRANSFER)."""
         from pdf_table_b200 import predictors
 
         predictors.TRANSFER["h2d"] = predictors.TRANSFER["d2h"] = 0
         self.step_e2e()
-        h2d = predictors.TRANSFER["h2d"] + self.probs_host.numel() * 4
-        d2h = predictors.TRANSFER["d2h"] + sum(h.numel() * h.element_size() for h in self.ctc_host)
-        return int(h2d), int(d2h)
+        return int(predictors.TRANSFER["h2d"]), int(predictors.TRANSFER["d2h"])
 
     def flush_l2(self):
         self.flush.fill_(1)
@@ -433,13 +419,17 @@ def block_rec_sweep(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_s
     dev = torch.device("cuda", wl.device)
     counts = [len(range(r, SWEEP_CROPS, world)) for r in range(world)]
     n = counts[rank]
-    rec, post = wl.rec, wl.post
+    from pdf_table_b200 import predictors, synth
+
+    task = predictors.OcrRecognitionTask(model="ConvNextViT", state_dict=synth.convnext_vit_state_dict(0), device=wl.device)
+    n_labels = int(task.predictor._lib.dv_convnextvit_labels(task.predictor._h))
+    task.label_mapping = {i + 2: ch for i, ch in enumerate(synthetic_vocab(n_labels))}
+    rec, post = task.predictor, task.post
     crops_np = make_sweep_crops(n, rank, world)
     crops_list = list(crops_np)
     crops_dev = torch.from_numpy(crops_np).to(dev)
     ids = torch.empty((n, 201), dtype=torch.int32, device=dev)
     none = {"boxes": torch.zeros((0, 1, 8), dtype=torch.float32, device=dev), "box_counts": torch.zeros((0,), dtype=torch.int32, device=dev)}
-    task = wl.system.text_recognizer
 
     def gather(out, ln):
         if dist is not None:
@@ -614,11 +604,14 @@ def block_lore(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_src):
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, rec_sd, sample_maps):
-    """The reference's algorithm for the same stages on the host cores (oracle/ restatement of
-    PPOcrDetectionPreprocessor + DBModel + DBPostProcess, crop_image + OCRRecognitionPreprocessor + ConvNextViT + its
-    post-processor, and CTCLabelDecode)."""
-    from oracle import convnextvit_ref, crop_ref, ctc_ref, db_post_ref, dbnet_ref
+def cpu_reference_step(sample_pages: np.ndarray, sd, rec_sd, sample_maps):
+    """The reference's algorithm for the same stages on the host cores (oracle/ restatement of PPOcrDetectionPreprocessor +
+    DBModel + DBPostProcess, crop_image + PPOcrRecPreProcessor (one crop per call, as the orchestrator does) + the PP-OCRv4
+    recogniser + CTCLabelDecode)."""
+    import cv2
+    import math
+
+    from oracle import crop_ref, ctc_ref, db_post_ref, dbnet_ref, pp_rec_ref
 
     mean = np.array(MEAN, np.float32).reshape(1, 1, 3)
     std = np.array(STD, np.float32).reshape(1, 1, 3)
@@ -627,22 +620,19 @@ def cpu_reference_step(sample_pages: np.ndarray, sample_probs: np.ndarray, sd, r
         img = (img - mean) / std
         x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
         dbnet_ref.dbnet_r18_forward(sd, x)
-    cut = []
     for pg, m in zip(sample_pages, sample_maps):
         boxes = db_post_ref.db_postprocess(m[0], np.array([PAGE_H, PAGE_W, 1.0, 1.0]), (PAGE_H, PAGE_W, 3))
-        page_crops = []
-        for b in boxes[:CROPS_PER_PAGE]:  # OcrCommonUtils.crop_image per detected quad (ocr_system_task.py:300-313)
+        for b in boxes[:CROPS_PER_PAGE]:  # OcrCommonUtils.crop_image per detected quad, one recogniser call per crop (ocr_system_task.py:300-313)
             try:
-                page_crops.append(crop_ref.crop_image(pg, b.reshape(4, 2)))
+                crop = crop_ref.crop_image(pg, b.reshape(4, 2))
             except Exception:  # an empty crop: cv2 raises, the reference's orchestrator skips the box
-                pass
-        # the B200 arm runs CROPS_PER_PAGE recogniser slots per page (zero crops beyond the box count): same work here
-        page_crops += [np.zeros((32, 320, 3), np.uint8)] * (CROPS_PER_PAGE - len(page_crops))
-        cut += page_crops
-    for i in range(0, len(cut), 16):  # batches of 16 crops (48 chunks); the reference itself runs batch 1
-        chunks = convnextvit_ref.preprocess(list(cut[i:i + 16]))
-        convnextvit_ref.greedy_ids(convnextvit_ref.convnextvit_forward(rec_sd, chunks))
-    ctc_ref.ctc_greedy_ids(sample_probs)
+                continue
+            h, w = crop.shape[:2]
+            img_w = max(min(int(48 * max(w * 1.0 / h, 320 / 48)), 1280), 16)  # resize_norm_img for a batch of one
+            rw = min(img_w, max(math.ceil(48 * (w / float(h))), 16))
+            x = np.zeros((1, 3, 48, img_w), np.float32)
+            x[0, :, :, :rw] = (cv2.resize(crop, (rw, 48)).astype("float32").transpose(2, 0, 1) / 255 - 0.5) / 0.5
+            ctc_ref.ctc_greedy_ids(pp_rec_ref.pp_rec_forward(rec_sd, torch.from_numpy(x)).numpy())
     if FULL:
         cpu_full_extra(len(sample_pages))
 
@@ -716,17 +706,17 @@ class CpuArm:
 
         self.n_pages = n_pages
         self.sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
-        self.rec_sd = {k: torch.from_numpy(v) for k, v in synth.convnext_vit_state_dict(0).items()}
+        self.rec_sd = {k: torch.from_numpy(v) for k, v in synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES).items()}
         self.pages = make_pages(0, n_pages)
-        self.probs = make_ctc_probs(0, n_pages * CROPS_PER_PAGE)
         self.maps = make_prob_maps(0, n_pages)
 
     def step(self):
-        cpu_reference_step(self.pages, self.probs, self.sd, self.rec_sd, self.maps)
+        cpu_reference_step(self.pages, self.sd, self.rec_sd, self.maps)
 
     def sample(self):
         return (f"{self.n_pages} of {PAGES_PER_GPU} pages 960x960 per step, each with {CROPS_PER_PAGE} text-line crop slots cut from the page at the "
-                "detected quads (crop_image + keepratio_resize) through ConvNextViT (+ planted CTC decode)" +
+                "detected quads (crop_image + resize_norm_img, one crop per recogniser call as the reference's orchestrator) through the PP-OCRv4 "
+                "recogniser + CTC decode" +
                 (", PicoDet layout and Lore table structure on one table crop per page" if FULL else "") + ", oracle/ restatement in torch fp32 on the host cores")
 
 
@@ -795,10 +785,10 @@ def workload_config():
     cfg = {
         "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
         "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
-        "rec_model": f"ConvNextViT (in-tree recogniser standing in for the PP-OCRv4 rec ONNX, SURVEY.md a5/a8), {CROPS_PER_PAGE} crop slots per "
-                     "page cut on the device from the db_boxes quads of that page (crop_image + keepratio_resize, bit-exact vs cv2; the planted "
-                     "maps yield exactly that many boxes), seeded random weights",
-        "ctc_stage": f"CTC greedy decode of planted [{PAGES_PER_GPU * CROPS_PER_PAGE},{CTC_T},{CTC_C}] fp32 probabilities (PP-OCR rec head output)",
+        "rec_model": f"PP-OCRv4 rec = PPLCNetV3-0.95 + SVTR neck + CTC head (the published architecture the hub ONNX was exported from, SURVEY.md "
+                     f"a5; {PP_REC_CLASSES} classes), {CROPS_PER_PAGE} crops per page cut on the device from the db_boxes quads of that page "
+                     "(crop_image + resize_norm_img: 48 high, each crop padded to its own width as the reference's one-crop-per-call flow does; "
+                     "crops of equal padded width share a launch), CTC greedy decode of the network's own output, seeded random weights",
         "db_post_stage": "db_boxes on planted probability maps (40 analytic text-line blobs per page, every one a box; + specks): with random weights the "
                          "detector's own map is texture noise; the network still runs and its map is discarded",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],

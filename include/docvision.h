@@ -358,10 +358,14 @@ int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* s
  * out: device uint8 [n, dst_h, dst_w_pad, 3] = the input of dv_convnextvit_forward_u8 (dst_h 32, dst_w_pad 804);
  * dst_widths: device int32 [n], 0 where the reference's cv2 call would raise (empty crop / singular quad; the row block is
  * zero).  minv_ws (double [n, 9]) and sizes_ws (int32 [n, 2] = crop (w, h)) are caller-owned workspaces, readable afterwards.
+ * width_rule 0 = that keep-ratio rule (ConvNextViT: dst_h 32, dst_w_pad 804); width_rule 1 = the PP-OCR recogniser's
+ * resize_norm_img for a crop that is its own batch, as the reference's orchestrator calls it (ocr_rec_pp/processor_ocr_rec_pp.py:
+ * 43-59; dst_h 48, dst_w_pad 1280): dst_widths[i] = min(imgW, max(ceil(48 w / h), 16)), imgW = clamp(int(48 max(w / h, 320 / 48)),
+ * 16, 1280) being the padded width the host recomputes from sizes_ws to group the crops for dv_rec_forward_u8.
  */
 int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* quads,
                           const int32_t* page_idx, int n, int dst_h, int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws,
-                          int32_t* sizes_ws);
+                          int32_t* sizes_ws, int width_rule);
 /*
  * The same, reading dv_db_boxes' outputs directly: boxes device float32 [n_pages, box_stride, 8], box_counts device int32
  * [n_pages]; every page gets per_page crop slots (slot k = box k of that page, skipped with width 0 when k >= its count), so
@@ -369,7 +373,7 @@ int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
  */
 int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* boxes,
                           const int32_t* box_counts, int box_stride, int per_page, int dst_h, int dst_w_pad, uint8_t* out,
-                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws, int width_rule);
 /*
  * cv2.warpAffine(img, M, (out_w, out_h), flags=INTER_LINEAR) with a zero border on a uint8 HWC image, bit-exact against cv2
  * (OpenCV 4.13 fixed point): the warp of TableLorePreProcessor.process (lore/processer_lore.py:80-91) for an

@@ -502,7 +502,7 @@ int dv_resize_linear_u8(dv_handle h, const uint8_t* src_packed, const int64_t* s
 
 int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* quads,
                           const int32_t* page_idx, int n, int dst_h, int dst_w_pad, uint8_t* out, int32_t* dst_widths, double* minv_ws,
-                          int32_t* sizes_ws) {
+                          int32_t* sizes_ws, int width_rule) {
     if (!h) return DV_ERR_ARG;
     if (n == 0) return 0;
     if (!pages_hwc_u8 || !quads || !out || !dst_widths || !minv_ws || !sizes_ws || n < 0 || n_pages <= 0 || height <= 0 || width <= 0 ||
@@ -510,19 +510,19 @@ int dv_crop_quads_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages,
         return set_err(h, DV_ERR_ARG, "dv_crop_quads_for_rec: null pointer / bad size");
     DeviceGuard dev_guard(h->device);
     return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, quads, page_idx, nullptr, 0, 0, n, dst_h, dst_w_pad, out, dst_widths, minv_ws,
-                                 sizes_ws);
+                                 sizes_ws, width_rule);
 }
 
 int dv_crop_boxes_for_rec(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages, int height, int width, const float* boxes,
                           const int32_t* box_counts, int box_stride, int per_page, int dst_h, int dst_w_pad, uint8_t* out,
-                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws, int width_rule) {
     if (!h) return DV_ERR_ARG;
     if (!pages_hwc_u8 || !boxes || !box_counts || !out || !dst_widths || !minv_ws || !sizes_ws || n_pages <= 0 || height <= 0 || width <= 0 ||
         box_stride <= 0 || per_page <= 0 || per_page > box_stride || dst_h <= 0 || dst_w_pad <= 0)
         return set_err(h, DV_ERR_ARG, "dv_crop_boxes_for_rec: null pointer / bad size");
     DeviceGuard dev_guard(h->device);
     return op_crop_quads_for_rec(h, pages_hwc_u8, height, width, boxes, nullptr, box_counts, box_stride, per_page, n_pages * per_page, dst_h,
-                                 dst_w_pad, out, dst_widths, minv_ws, sizes_ws);
+                                 dst_w_pad, out, dst_widths, minv_ws, sizes_ws, width_rule);
 }
 
 int dv_warp_affine_u8(dv_handle h, const uint8_t* img_hwc_u8, int height, int width, const double* m_inv6_host, int out_w, int out_h,

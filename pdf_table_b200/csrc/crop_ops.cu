@@ -140,8 +140,13 @@ __device__ __forceinline__ double dfms(double a, double b, double c, double d) {
 
 // quads: [n][4][2], or -- with box_counts -- the dv_db_boxes output [pages][box_stride][8] read as per_page slots per page
 // (slot k of page p = box k if k < box_counts[p], else skipped)
+// width_rule 0: OCRRecognitionPreprocessor.keepratio_resize (ConvNextViT): cur_w = dst_w_max if ratio > dst_w_max / dst_h else
+//   int(dst_h * ratio).  width_rule 1: PPOcrRecPreProcessor.resize_norm_img for a crop that is its own batch, as the reference's
+//   orchestrator calls it (ocr_rec_pp/processor_ocr_rec_pp.py:43-59, one crop per call -- ocr_system_task.py:309-312):
+//   resized_w = min(imgW, max(ceil(dst_h * ratio), 16)) with imgW = clamp(int(dst_h * max(ratio, 320 / 48)), 16, 1280); the padded
+//   width imgW of each crop is the host's to recompute from `sizes` (predictors.pp_rec_padded_width).
 __global__ void k_quad_homography(const float* __restrict__ quads, const int32_t* __restrict__ box_counts, int box_stride, int per_page,
-                                  int n, int dst_h, int dst_w_max, double* __restrict__ minv /*[n][9]*/,
+                                  int n, int dst_h, int dst_w_max, int width_rule, double* __restrict__ minv /*[n][9]*/,
                                   int32_t* __restrict__ sizes /*[n][2]*/, int32_t* __restrict__ dst_widths /*[n]*/) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -193,9 +198,19 @@ __global__ void k_quad_homography(const float* __restrict__ quads, const int32_t
     dst_widths[q] = 0;
     if (w <= 0 || h <= 0) return;
     const double ratio = __ddiv_rn(static_cast<double>(w), static_cast<double>(h));
-    const int cur_w = ratio > __ddiv_rn(static_cast<double>(dst_w_max), static_cast<double>(dst_h))
-                          ? dst_w_max
-                          : static_cast<int>(__dmul_rn(static_cast<double>(dst_h), ratio));
+    int cur_w;
+    if (width_rule == 1) {
+        const double max_wh = fmax(ratio, __ddiv_rn(320.0, 48.0));
+        int img_w = static_cast<int>(__dmul_rn(static_cast<double>(dst_h), max_wh));
+        img_w = max(min(img_w, 1280), 16);
+        const int ratio_w = max(static_cast<int>(ceil(__dmul_rn(static_cast<double>(dst_h), ratio))), 16);
+        cur_w = ratio_w > img_w ? img_w : ratio_w;
+        if (cur_w > dst_w_max) cur_w = dst_w_max;  // never past the caller's buffer (dst_w_max >= 1280 keeps the rule exact)
+    } else {
+        cur_w = ratio > __ddiv_rn(static_cast<double>(dst_w_max), static_cast<double>(dst_h))
+                    ? dst_w_max
+                    : static_cast<int>(__dmul_rn(static_cast<double>(dst_h), ratio));
+    }
     if (cur_w <= 0) return;
     // float32 corner arrays: src = (x1,y1), (x2,y2), (x4,y4), (x3,y3);  dst = (0,0), (W-1,0), (0,H-1), (W-1,H-1)
     const float sx[4] = {static_cast<float>(x1), static_cast<float>(x2), static_cast<float>(x4), static_cast<float>(x3)};
@@ -462,12 +477,12 @@ int op_warp_affine_rects_u8(Engine* e, const uint8_t* pages, int n_pages, int H,
 
 int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
-                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws) {
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws, int width_rule) {
     if (n <= 0) return 0;
     if (n > 65535) return set_err(e, DV_ERR_UNSUPPORTED, "crop_quads_for_rec: more than 65535 quads per call");
     e->launch_begin("k_quad_homography", "crop", 0.0, n * 120.0);
-    k_quad_homography<<<(n + 63) / 64, 64, 0, e->stream>>>(quads, box_counts, box_stride, per_page, n, dst_h, dst_w_pad, minv_ws, sizes_ws,
-                                                           dst_widths);
+    k_quad_homography<<<(n + 63) / 64, 64, 0, e->stream>>>(quads, box_counts, box_stride, per_page, n, dst_h, dst_w_pad, width_rule, minv_ws,
+                                                           sizes_ws, dst_widths);
     e->launch_end();
     const int px = dst_h * dst_w_pad;
     e->launch_begin("k_crop_resize_fused", "crop", 0.0, static_cast<double>(n) * px * 3.0 * 2.0);

@@ -219,7 +219,7 @@ int op_resize_linear_u8(Engine* e, const uint8_t* src, const long long* src_off,
                         int n, int dst_h, int dst_w_pad, uint8_t* out);
 int op_crop_quads_for_rec(Engine* e, const uint8_t* pages, int H, int W, const float* quads, const int32_t* page_idx,
                           const int32_t* box_counts, int box_stride, int per_page, int n, int dst_h, int dst_w_pad, uint8_t* out,
-                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws);
+                          int32_t* dst_widths, double* minv_ws, int32_t* sizes_ws, int width_rule = 0);
 int op_warp_affine_u8(Engine* e, const uint8_t* img, int H, int W, const double* m_inv6, int w, int h, uint8_t* out);
 int op_warp_affine_rects_u8(Engine* e, const uint8_t* pages, int n_pages, int H, int W, const int32_t* rects, const double* minv,
                             int n, int w, int h, uint8_t* out);

@@ -239,7 +239,7 @@ class Engine:
         return self.resize_linear_u8((pages, offs, sizes), np.full((n,), dst_w, np.int32), dst_h, dst_w)
 
     def crop_quads_for_rec(self, pages: torch.Tensor, quads: torch.Tensor, page_idx: Optional[torch.Tensor] = None, dst_h: int = 32,
-                           dst_w_pad: int = 804):
+                           dst_w_pad: int = 804, width_rule: int = 0):
         """pages uint8 [P,H,W,3] (or [H,W,3]) + quads float32 [n,4,2] (+ page index int32 [n]), all cuda -> (crops uint8
         [n,dst_h,dst_w_pad,3], widths int32 [n] (0 = skipped), crop sizes int32 [n,2], inverse homographies float64 [n,3,3]),
         all on the device: crop_image + keepratio_resize of the reference for every quad, no host round trip."""
@@ -261,11 +261,11 @@ class Engine:
         minv = torch.empty((n, 3, 3), dtype=torch.float64, device=dev)
         sizes = torch.empty((n, 2), dtype=torch.int32, device=dev)
         check(self._lib.dv_crop_quads_for_rec(self._h, _ptr(pages), pp, hh, ww, _ptr(quads), _ptr(page_idx), n, dst_h, dst_w_pad,
-                                              _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_quads_for_rec")
+                                              _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes), int(width_rule)), self._h, "dv_crop_quads_for_rec")
         return out, widths, sizes, minv
 
     def crop_boxes_for_rec(self, pages: torch.Tensor, boxes: torch.Tensor, counts: torch.Tensor, per_page: int, dst_h: int = 32,
-                           dst_w_pad: int = 804, out: Optional[torch.Tensor] = None, ws=None):
+                           dst_w_pad: int = 804, out: Optional[torch.Tensor] = None, ws=None, width_rule: int = 0):
         """crop_quads_for_rec on db_boxes' own outputs: boxes float32 [P,S,8] + counts int32 [P] (cuda) -> per_page crop slots per
         page, (crops uint8 [P*per_page,dst_h,dst_w_pad,3], widths int32 [P*per_page], sizes, minv).  ``out`` / ``ws`` = (widths,
         sizes, minv) may be passed in to reuse buffers (no allocation on the hot path)."""
@@ -284,7 +284,7 @@ class Engine:
                   torch.empty((n, 3, 3), dtype=torch.float64, device=dev))
         widths, sizes, minv = ws
         check(self._lib.dv_crop_boxes_for_rec(self._h, _ptr(pages), pp, hh, ww, _ptr(boxes), _ptr(counts), boxes.shape[1], per_page, dst_h,
-                                              dst_w_pad, _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes)), self._h, "dv_crop_boxes_for_rec")
+                                              dst_w_pad, _ptr(out), _ptr(widths), _ptr(minv), _ptr(sizes), int(width_rule)), self._h, "dv_crop_boxes_for_rec")
         return out, widths, sizes, minv
 
     def warp_affine_u8(self, img: torch.Tensor, m_inv: np.ndarray, out_w: int, out_h: int) -> torch.Tensor:

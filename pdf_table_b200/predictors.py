@@ -24,7 +24,7 @@ from ._lib import DocVisionError
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
+           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "pp_rec_padded_width", "pp_rec_launch_groups", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -228,6 +228,51 @@ def pp_rec_batch_plan(shapes, rec_image_shape=(3, 48, 320), rec_batch_num: int =
             widths.append(img_w if ratio_w > img_w else int(ratio_w))
         plan.append((beg, img_w, widths))
     return indices, plan
+
+
+def pp_rec_padded_width(sizes, img_h: int = 48, img_w0: int = 320, limited_min_width: int = 16, limited_max_width: int = 1280) -> np.ndarray:
+    """The padded width PPOcrRecPreProcessor.resize_norm_img gives a crop that is its own batch (processor_ocr_rec_pp.py:43-49),
+    vectorised over crop sizes [n,2] = (w, h): imgW = clamp(int(48 * max(w / h, 320 / 48)), 16, 1280); 0 for an empty crop."""
+    sizes = np.asarray(sizes).reshape(-1, 2)
+    w, h = sizes[:, 0].astype(np.float64), sizes[:, 1].astype(np.float64)
+    ok = (w > 0) & (h > 0)
+    ratio = np.where(ok, w * 1.0 / np.where(ok, h, 1.0), 0.0)
+    img_w = (img_h * np.maximum(ratio, img_w0 / img_h)).astype(np.int64)
+    return np.where(ok, np.clip(img_w, limited_min_width, limited_max_width), 0).astype(np.int64)
+
+
+def pp_rec_launch_groups(rec: Engine, post: Engine, crops: torch.Tensor, widths: torch.Tensor, sizes: torch.Tensor, t_max: int = 160):
+    """PP-OCR recogniser over the output of dv_crop_quads_for_rec / dv_crop_boxes_for_rec with width_rule 1: crops uint8
+    [n,48,1280,3], widths int32 [n] (resized width, 0 = skipped quad), sizes int32 [n,2] (all cuda).  The reference recognises one
+    crop per call, i.e. every crop padded to ITS OWN width imgW (``pp_rec_padded_width``); the network is per-crop, so crops of
+    equal imgW share a launch.  The crop sizes come back to the host once (8 bytes per crop) to form the groups.  Returns
+    (ids int32 [n,t_max] left-packed / -1 padded, lens int32 [n], conf fp32 [n]) on the device."""
+    n = int(crops.shape[0])
+    dev = crops.device
+    TRANSFER["d2h"] += n * 12
+    img_w = pp_rec_padded_width(sizes.cpu().numpy())
+    img_w[widths.cpu().numpy() <= 0] = 0
+    ids_all = torch.full((n, t_max), -1, dtype=torch.int32, device=dev)
+    lens_all = torch.zeros((n,), dtype=torch.int32, device=dev)
+    conf_all = torch.zeros((n,), dtype=torch.float32, device=dev)
+    for w in np.unique(img_w[img_w > 0]):
+        idx = np.nonzero(img_w == w)[0]
+        if len(idx) == n:
+            g, gw = crops[:, :, : int(w)].contiguous(), widths
+            idx_dev = None
+        else:
+            idx_dev = _h2d(torch.from_numpy(idx), dev)
+            g, gw = crops[idx_dev, :, : int(w)], widths[idx_dev]
+        ids, maxp = rec.rec_forward_u8(g, gw)
+        out, ln, conf = post.ctc_collapse(ids, maxp)
+        t = int(out.shape[1])
+        if idx_dev is None:
+            ids_all[:, :t], lens_all, conf_all = out, ln, conf
+        else:
+            ids_all[idx_dev, :t] = out
+            lens_all[idx_dev] = ln
+            conf_all[idx_dev] = conf
+    return ids_all, lens_all, conf_all
 
 
 class PPOcrRecPreProcessor:
@@ -723,10 +768,15 @@ class OcrRecognitionTask(BaseInferTask):
         page_idx = np.repeat(np.arange(len(n_per), dtype=np.int32), n_per)
         q_dev = _h2d(torch.from_numpy(quads), dev)
         pi_dev = _h2d(torch.from_numpy(page_idx), dev)
-        # geometry, homography, warp and keep-ratio resize all on the device; width 0 = skipped quad
-        crops, widths, _, _ = self.post.crop_quads_for_rec(batch, q_dev, pi_dev)
-        ids = self.predictor.convnextvit_forward_u8(crops)
-        tok, ln, _ = self.post.ctc_collapse(ids)
+        # geometry, homography, warp and resize all on the device; width 0 = skipped quad
+        if self.model == "PP-OCRv4":  # crop_image + resize_norm_img (48 high, the crop's own padded width), then a5 + a6 per width group
+            crops, widths, sizes, _ = self.post.crop_quads_for_rec(batch, q_dev, pi_dev, dst_h=48, dst_w_pad=1280, width_rule=1)
+            tok, ln, conf = pp_rec_launch_groups(self.predictor, self.post, crops, widths, sizes)
+            rec["conf"] = _d2h_async(conf)
+        else:
+            crops, widths, _, _ = self.post.crop_quads_for_rec(batch, q_dev, pi_dev)
+            ids = self.predictor.convnextvit_forward_u8(crops)
+            tok, ln, _ = self.post.ctc_collapse(ids)
         rec.update(ids_dev=tok, len_dev=ln, widths_dev=widths, ids=_d2h_async(tok), len=_d2h_async(ln), widths=_d2h_async(widths))
         rec["event"] = torch.cuda.Event()
         rec["event"].record()
@@ -738,7 +788,13 @@ class OcrRecognitionTask(BaseInferTask):
         if rec["event"] is None:
             return [[] for _ in rec["n_per"]]
         rec["event"].synchronize()
-        texts = self._postprocess({"ids": rec["ids"].numpy(), "len": rec["len"].numpy()})
+        if self.model == "PP-OCRv4":
+            ids, lens = rec["ids"].numpy(), rec["len"].numpy()
+            texts = [(" ".join(str(int(v)) for v in row[:k]) if self.character is None else "".join(self.character[int(v)] for v in row[:k]))
+                     for row, k in zip(ids, lens)]
+            self.last_confidences = rec["conf"].numpy().tolist()
+        else:
+            texts = self._postprocess({"ids": rec["ids"].numpy(), "len": rec["len"].numpy()})
         widths = rec["widths"].numpy()
         o = 0
         for n in rec["n_per"]:

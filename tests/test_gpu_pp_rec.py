@@ -118,3 +118,37 @@ def test_recognition_task_pp_ocrv4_chain():
             assert abs(len(got[i]) - len(text)) <= 2
     print("pp-ocrv4 chain: strings identical" if safe else "pp-ocrv4 chain: some steps inside the margin band")
     assert task(crops[3]) == [got[3]]  # one crop per call, as the reference's orchestrator does
+
+
+def test_pp_ocrv4_recognize_page_equals_one_crop_per_call():
+    """det -> rec on the device for the PP-OCRv4 recogniser: recognize_page(page, quads) -- every quad cut, resized to 48 rows
+    with resize_norm_img's width rule and padded to its OWN width on the device, crops of equal padded width sharing a launch --
+    returns exactly what the reference's flow returns: OcrCommonUtils.crop_image on the host (cv2) and ONE recogniser call per
+    crop (ocr_pdf/ocr_system_task.py:300-313)."""
+    import math
+
+    import cv2
+
+    sd = synth.pp_ocrv4_rec_state_dict(0, N_CLASS)
+    vocab = [chr(33 + i) for i in range(N_CLASS - 2)]
+    task = predictors.OcrRecognitionTask(model="PP-OCRv4", state_dict=sd, vocab=vocab)
+    page = synth.synthetic_page(5, 480, 640)
+    rng = np.random.default_rng(3)
+    quads = []
+    for k in range(14):
+        cx, cy, bw, bh, ang = rng.uniform(100, 540), rng.uniform(60, 420), rng.uniform(30, 400), rng.uniform(12, 40), rng.uniform(-0.3, 0.3)
+        c, s = math.cos(ang), math.sin(ang)
+        quads.append((np.array([[-bw / 2, -bh / 2], [bw / 2, -bh / 2], [bw / 2, bh / 2], [-bw / 2, bh / 2]]) @ np.array([[c, s], [-s, c]])
+                      + [cx, cy]).astype(np.float32))
+    quads.append(np.array([[10, 10], [10.4, 10], [10.4, 30], [10, 30]], np.float32))  # zero-width crop: the reference's cv2 call raises
+    got = task.recognize_page(page, quads)
+    assert len(got) == len(quads) and got[-1] is None
+    conf = list(task.last_confidences)
+    widths = set()
+    for k, q in enumerate(quads[:-1]):
+        corners, trans, size = predictors.crop_geometry(q)
+        crop = cv2.warpPerspective(page, cv2.getPerspectiveTransform(corners, trans), size)
+        widths.add(int(predictors.pp_rec_padded_width([size])[0]))
+        assert task(crop) == [got[k]], k
+        assert task.last_confidences[0] == conf[k]
+    assert len(widths) > 3  # several padded-width groups were exercised
