@@ -41,7 +41,7 @@ if ROOT not in sys.path:
 os.environ.setdefault("NCCL_DEBUG", "INFO")
 if os.environ["NCCL_DEBUG"].upper() == "INFO":
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("TMPDIR", "/tmp"), "nccl.bench.%h.%p.log"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
