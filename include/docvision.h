@@ -283,6 +283,16 @@ int dv_rec_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int
 int dv_rec_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int n, int height, int width, float* probs_out,
                       int32_t* ids_out, float* maxp_out);
 int dv_rec_time_steps(dv_handle h, int height, int width);
+/*
+ * PULC image classifiers: PP-LCNet x1.0 (cls/cls_pp_lcnet.py:164-293) for model kind "pplcnet_cls" (weights
+ * packed by pdf_table_b200/pplcnet_graph.py; the stride list of the task -- (2,1) strides for textline_orientation /
+ * language_classification, cls/configuration_cls_pulc.py:20-42 -- is part of the packed program).  Replaces the torch forward of
+ * ClsImagePulcTask._run_model (ocr_pdf/cls_image_pulc_task.py:61-83).
+ *   in_nchw_f32 : device fp32 [n,3,height,width] = PPLCNetImageProcessor's pixel_values
+ *   logits_out  : device fp32 [n,C] = PPLCNet.forward's return value (what TableAttribute thresholds), or NULL
+ *   probs_out   : device fp32 [n,C] = softmax(logits) (what Topk sorts), or NULL;   C = dv_rec_num_classes(h)
+ */
+int dv_cls_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* logits_out, float* probs_out);
 int dv_rec_num_classes(dv_handle h);
 
 /*

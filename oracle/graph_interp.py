@@ -41,7 +41,7 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
     tens: List[torch.Tensor] = [x.float()]
     for row in tensors[1:]:
         c, dh, dw, ph, pw = (int(row[0]), int(row[1]), int(row[1]), 1, 1) if len(row) == 2 else (int(v) for v in row)
-        tens.append(torch.zeros((n, c, (-(-hh // dh)) // ph, (-(-ww // dw)) // pw), dtype=torch.float32))
+        tens.append(torch.zeros((n, c, 1 if ph == 0 else (-(-hh // dh)) // ph, 1 if pw == 0 else (-(-ww // dw)) // pw), dtype=torch.float32))
     heads: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
 
     def post_affine(t, wid):
@@ -87,7 +87,7 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
         elif code == OP_ADD:
             out = tens[in_t] + tens[aux]
         elif code == OP_AVGPOOL:
-            out = F.avg_pool2d(src, [k & 255, k >> 8])
+            out = F.adaptive_avg_pool2d(src, 1) if k == 0 else F.avg_pool2d(src, [k & 255, k >> 8])
         elif code == OP_UNFOLD3:  # [N,C,1,T] -> [N,3C,1,T], channel = tap * C + c
             pad = F.pad(src, (1, 1))
             out = torch.cat([pad[..., t:t + src.shape[-1]] for t in range(3)], 1)

@@ -145,7 +145,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = dbnet_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
-        } else if (e->kind == "picodet" || e->kind == "pp_rec") {
+        } else if (e->kind == "picodet" || e->kind == "pp_rec" || e->kind == "pplcnet_cls") {
             rc = graph_create(e);
         } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34") {
             rc = lore_create(e);
@@ -452,6 +452,12 @@ int dv_rec_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* w
     if (!h || !crops_hwc_u8) return DV_ERR_ARG;
     DeviceGuard dev_guard(h->device);
     return rec_forward(h, nullptr, crops_hwc_u8, widths, n, height, width, probs_out, ids_out, maxp_out);
+}
+
+int dv_cls_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* logits_out, float* probs_out) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return cls_forward(h, in_nchw_f32, n, height, width, logits_out, probs_out);
 }
 
 int dv_rec_time_steps(dv_handle h, int height, int width) { return h ? rec_time_steps(h, height, width) : 0; }

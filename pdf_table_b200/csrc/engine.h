@@ -288,6 +288,7 @@ int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const
 int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, int N, int H, int W, float* probs, int32_t* ids,
                 float* maxp);
 int rec_time_steps(Engine* e, int H, int W);
+int cls_forward(Engine* e, const float* in_nchw, int N, int H, int W, float* logits, float* probs);
 
 // picodet_decode.cu
 int picodet_decode(Engine* e, const float* const* scores, const float* const* dfl, int N, int C, int reg_max, const int* strides, int in_h,

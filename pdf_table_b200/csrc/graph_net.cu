@@ -433,7 +433,7 @@ k_attn_small(const __half* __restrict__ qkv, int T, int D, int heads, __half* __
 // fp32 logits [M, ld] -> softmax over the first C columns: probs [M, C] (optional), arg-max id and max probability per row
 __global__ void __launch_bounds__(256)
 k_softmax_rows(const float* __restrict__ logits, long long M, int ld, int C, float* __restrict__ probs, int32_t* __restrict__ ids,
-               float* __restrict__ maxp) {
+               float* __restrict__ maxp, float* __restrict__ raw) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
     if (row >= M) return;
@@ -463,6 +463,8 @@ k_softmax_rows(const float* __restrict__ logits, long long M, int ld, int C, flo
     const float inv = 1.f / s;
     if (probs != nullptr)
         for (int c = lane; c < C; c += 32) probs[row * C + c] = expf(ip[c] - mx) * inv;
+    if (raw != nullptr)
+        for (int c = lane; c < C; c += 32) raw[row * C + c] = ip[c];
     if (lane == 0) {
         if (ids != nullptr) ids[row] = arg;
         if (maxp != nullptr) maxp[row] = inv;  // exp(0) / sum
@@ -658,8 +660,9 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
     for (size_t i = 1; i < nt; ++i) {  // tensor 0 is the input image
         Tensor& t = m->tens[i];
         t.N = N;
-        t.H = ((H + m->tdh[i] - 1) / m->tdh[i]) / m->tph[i];
-        t.W = ((W + m->tdw[i] - 1) / m->tdw[i]) / m->tpw[i];
+        // pool factor 0 = globally pooled along that axis
+        t.H = m->tph[i] == 0 ? 1 : ((H + m->tdh[i] - 1) / m->tdh[i]) / m->tph[i];
+        t.W = m->tpw[i] == 0 ? 1 : ((W + m->tdw[i] - 1) / m->tdw[i]) / m->tpw[i];
         if (t.H <= 0 || t.W <= 0) return set_err(e, DV_ERR_ARG, "graph: input %dx%d too small for tensor %zu", H, W, i);
         t.C = m->tc[i];
         void* p = nullptr;
@@ -821,7 +824,7 @@ int graph_create(Engine* e) {
         m->tdw.push_back(tcols == 5 ? r[2] : r[1]);
         m->tph.push_back(tcols == 5 ? r[3] : 1);
         m->tpw.push_back(tcols == 5 ? r[4] : 1);
-        if (m->tdh.back() <= 0 || m->tdw.back() <= 0 || m->tph.back() <= 0 || m->tpw.back() <= 0) {
+        if (m->tdh.back() <= 0 || m->tdw.back() <= 0 || m->tph.back() < 0 || m->tpw.back() < 0) {
             delete m;
             return set_err(e, DV_ERR_WEIGHTS, "graph model: malformed tensor table");
         }
@@ -873,6 +876,7 @@ struct GraphOut {
     float* probs = nullptr;
     int32_t* ids = nullptr;
     float* maxp = nullptr;
+    float* logits = nullptr;
 };
 
 int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, const float* mean3, const float* std3,
@@ -975,7 +979,7 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 break;
             }
             case OP_AVGPOOL: {
-                const int kh = op.k & 255, kw = op.k >> 8;
+                const int kh = op.k == 0 ? in.H : (op.k & 255), kw = op.k == 0 ? in.W : (op.k >> 8);  // k = 0: global average pool
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
                 e->launch_begin("k_avgpool", "pool", 0.0, total * 16.0 * (kh * kw + 1));
                 k_avgpool<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, kh, kw, out.H, out.W, out.p + op.out_coff, out.C);
@@ -1013,9 +1017,9 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
             case OP_CTC: {
                 DV_TRY(launch_conv(e, op.plan));
                 const long long M = static_cast<long long>(N) * in.H * in.W;
-                if (!go.ids && !go.probs && !go.maxp) return set_err(e, DV_ERR_ARG, "rec_forward: no output requested");
+                if (!go.ids && !go.probs && !go.maxp && !go.logits) return set_err(e, DV_ERR_ARG, "graph head: no output requested");
                 e->launch_begin("k_softmax_rows", "ctc", 0.0, M * m->num_classes * (go.probs ? 8.0 : 4.0));
-                k_softmax_rows<<<grid_for(M, 8), 256, 0, s>>>(m->head_raw, M, m->head_ld, m->num_classes, go.probs, go.ids, go.maxp);
+                k_softmax_rows<<<grid_for(M, 8), 256, 0, s>>>(m->head_raw, M, m->head_ld, m->num_classes, go.probs, go.ids, go.maxp, go.logits);
                 e->launch_end();
                 break;
             }
@@ -1069,6 +1073,19 @@ int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int
     }
     m->last_call_flops = flops;
     return 0;
+}
+
+// PULC image classifiers (PP-LCNet, cls/cls_pp_lcnet.py:164-293), model kind "pplcnet_cls": fp32 [N,3,H,W] (the image processor's
+// pixel_values) -> logits fp32 [N,C] (PPLCNet.forward's return value) and / or softmax probabilities [N,C].
+int cls_forward(Engine* e, const float* in_nchw, int N, int H, int W, float* logits, float* probs) {
+    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
+    if (!m || m->kind != 2) return set_err(e, DV_ERR_STATE, "handle was not created as a pplcnet_cls model");
+    if (N <= 0 || H <= 0 || W <= 0 || !in_nchw || (!logits && !probs)) return set_err(e, DV_ERR_ARG, "cls_forward: bad arguments");
+    const float one3[3] = {1.f, 1.f, 1.f}, zero3[3] = {0.f, 0.f, 0.f};
+    GraphOut go;
+    go.logits = logits;
+    go.probs = probs;
+    return run_graph(e, m, in_nchw, nullptr, nullptr, zero3, one3, 1.f, 0, N, H, W, go);
 }
 
 int rec_time_steps(Engine* e, int H, int W) {

@@ -579,6 +579,18 @@ class Engine:
               "dv_rec_forward_u8")
         return (ids, maxp, probs) if return_probs else (ids, maxp)
 
+    def cls_forward(self, x: torch.Tensor, return_probs: bool = False):
+        """PULC classifier (model kind "pplcnet_cls"): fp32 NCHW [N,3,H,W] (cuda) -> logits fp32 [N,C] (+ softmax probabilities)."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, h, w = x.shape
+        if c != 3:
+            raise ValueError("cls_forward expects [N,3,H,W]")
+        nc = self.rec_num_classes
+        logits = torch.empty((n, nc), dtype=torch.float32, device=x.device)
+        probs = torch.empty((n, nc), dtype=torch.float32, device=x.device) if return_probs else None
+        check(self._lib.dv_cls_forward(self._h, _ptr(x), n, h, w, _ptr(logits), _ptr(probs)), self._h, "dv_cls_forward")
+        return (logits, probs) if return_probs else logits
+
     def picodet_decode(self, scores, dfl, org_hw, scale_factor, in_hw=(800, 608), strides=(8, 16, 32, 64), score_threshold: float = 0.5,
                        nms_threshold: float = 0.5, nms_top_k: int = 1000, keep_top_k: int = 100):
         """scores[l] fp32 [N,HW_l,C], dfl[l] fp32 [N,HW_l,4*(reg_max+1)] (cuda, 4 levels); org_hw [N,2] (h, w), scale_factor [N,2]

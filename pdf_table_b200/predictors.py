@@ -23,7 +23,7 @@ from . import weights
 from ._lib import DocVisionError
 from .engine import Engine
 
-__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "det_resize_for_test",
+__all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "ClsImagePulcTask", "det_resize_for_test",
            "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "pp_rec_padded_width", "pp_rec_launch_groups", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
 
 
@@ -1170,3 +1170,87 @@ class OcrLayoutTask(BaseInferTask):
         for rows, n in zip(inputs["boxes"].numpy(), inputs["counts"].numpy()):
             out.append([{"bbox": r[2:].copy(), "label": self.id2label[int(r[0])], "score": r[1], "category_id": int(r[0])} for r in rows[:n]])
         return out
+
+
+class ClsImagePulcTask(BaseInferTask):
+    """ClsImagePulcTask (ocr_pdf/cls_image_pulc_task.py:23-100): the PULC PP-LCNet classifiers the reference's
+    orchestrator runs before the cascade for image inputs (ocr_system_task.py:395-439) -- task_type "text_image_orientation",
+    "textline_orientation", "language_classification" (Topk post-process) or "table_attribute" (thresholds).  The host keeps the
+    reference's image processor steps (PIL bilinear resize through transformers.image_transforms, rescale 1/255, ImageNet
+    normalise, CHW: cls/image_processing_pplcnet.py:327-455) and its post-processors (:109-193); the network runs on the engine
+    (dv_cls_forward, graph program pplcnet_graph.py).  Returns what the reference returns: one result dict per input, the bare
+    dict for a single input (:94-96).  `state_dict` = the PPLCNet module's state_dict or a path."""
+
+    CLASS_ID_MAP = {  # cls/image_processing_pplcnet.py:41-72
+        "text_image_orientation": {0: "0", 1: "90", 2: "180", 3: "270"},
+        "textline_orientation": {0: "0_degree", 1: "180_degree"},
+        "language_classification": {0: "arabic", 1: "chinese_cht", 2: "cyrillic", 3: "devanagari", 4: "japan", 5: "ka", 6: "korean",
+                                    7: "ta", 8: "te", 9: "latin"},
+    }
+    IMAGE_SIZE = {"text_image_orientation": (224, 224), "textline_orientation": (80, 160), "language_classification": (80, 160)}
+    TOPK = {"text_image_orientation": 2, "textline_orientation": 1, "language_classification": 2}
+
+    def __init__(self, task: str = "cls_image", model: str = "PPLCNet", task_type: str = "text_image_orientation", state_dict=None, **kwargs):
+        from .pplcnet_graph import TASK_CLASSES
+
+        if model != "PPLCNet" or task_type not in TASK_CLASSES:
+            raise RuntimeError(f"model {model} / task_type {task_type} not support")
+        if state_dict is None:
+            raise RuntimeError("ClsImagePulcTask(predictor_type='b200') needs state_dict= (a PPLCNet state_dict or a path)")
+        self.task_type = task_type
+        self._sd = _load_state_dict(state_dict)
+        super().__init__(task=task, model=model, **kwargs)
+
+    def _construct_model(self, model):
+        from .pplcnet_graph import TASK_CLASSES, TASK_STRIDES, pack_pplcnet
+
+        if int(np.asarray(self._sd["fc.weight"]).shape[0]) != TASK_CLASSES[self.task_type]:
+            raise RuntimeError(f"task_type {self.task_type} expects {TASK_CLASSES[self.task_type]} classes")
+        self.predictor = Engine("pplcnet_cls", pack_pplcnet(self._sd, TASK_STRIDES[self.task_type]), device=self.device)
+        self._sd = None
+
+    def _preprocess(self, inputs, **kwargs):
+        from transformers.image_transforms import normalize, rescale, resize, to_channel_dimension_format
+        from transformers.image_utils import ChannelDimension, PILImageResampling, to_numpy_array
+        from transformers.utils import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+
+        items = inputs if isinstance(inputs, list) else [inputs]
+        size = self.IMAGE_SIZE.get(self.task_type, (224, 224))
+        batch = []
+        for it in items:
+            if isinstance(it, str):  # preprocess() reads paths with cv2 and flips to RGB (:389-397)
+                import cv2
+
+                img = cv2.imread(it)[:, :, ::-1]
+            else:
+                img = it
+            img = to_numpy_array(img)
+            img = resize(img, size=size, resample=PILImageResampling.BILINEAR)
+            img = normalize(rescale(img, 1 / 255), IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD)
+            batch.append(np.asarray(to_channel_dimension_format(img, ChannelDimension.FIRST), np.float32))
+        return {"pixel_values": np.stack(batch), "inputs": items}
+
+    def _run_model(self, inputs, **kwargs):
+        dev = torch.device("cuda", self.device)
+        logits = self.predictor.cls_forward(_h2d(torch.from_numpy(inputs["pixel_values"]), dev))
+        inputs["logits"] = _d2h(logits)
+        return inputs
+
+    def _postprocess(self, inputs, **kwargs):
+        logits = torch.from_numpy(inputs["logits"])
+        results = []
+        if self.task_type == "table_attribute":  # TableAttribute.__call__ (:125-153): thresholds 0.5 on the network's raw outputs
+            names = (("Scanned", "Photo"), ("Little", "Numerous"), ("Black-and-White", "Multicolor"), ("Clear", "Blurry"),
+                     ("Without-Obstacles", "With-Obstacles"), ("Horizontal", "Tilted"))
+            for res in logits.tolist():
+                results.append({"attributes": [a if v > 0.5 else b for v, (a, b) in zip(res, names)],
+                                "output": (np.array(res) > np.array([0.5] * 6)).astype(np.int8).tolist()})
+        else:  # Topk.__call__ (:162-192)
+            probs_all = torch.nn.functional.softmax(logits, dim=-1).numpy()
+            id_map = self.CLASS_ID_MAP[self.task_type]
+            for probs in probs_all:
+                index = probs.argsort(axis=0)[-self.TOPK[self.task_type]:][::-1].astype("int32")
+                results.append({"class_ids": [i.item() for i in index],
+                                "scores": np.around([probs[i].item() for i in index], decimals=5).tolist(),
+                                "label_names": [id_map[i.item()] for i in index]})
+        return results[0] if len(results) == 1 else results

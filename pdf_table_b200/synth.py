@@ -719,3 +719,27 @@ def pp_ocrv4_rec_state_dict(seed: int = 0, n_class: int = 97) -> "OrderedDict[st
     _ln(rng, sd, p + ".norm", d)
     sd["head.ctc_head.fc.weight"], sd["head.ctc_head.fc.bias"] = _lin(rng, n_class, d, gain=4.0), _b(rng, n_class)
     return sd
+
+
+# --------------------------------------------------------------------------- PULC classifiers (PP-LCNet x1.0, cls/cls_pp_lcnet.py)
+def pplcnet_cls_state_dict(seed: int = 0, class_num: int = 4) -> "OrderedDict[str, np.ndarray]":
+    """Seeded weights with the keys of the reference PPLCNet module (cls/cls_pp_lcnet.py:164-293, scale 1.0, class_expand 1280)."""
+    from .pplcnet_graph import NET_CONFIG
+
+    rng = np.random.Generator(np.random.PCG64(seed + 5050))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    sd["conv1.conv.weight"] = _conv(rng, 16, 3, 3, 3)
+    _bn(rng, sd, "conv1.bn", 16)
+    for name, cfg in NET_CONFIG.items():
+        for i, (k, ci, co, s, se) in enumerate(cfg):
+            p = f"{name}.{i}"
+            sd[p + ".dw_conv.conv.weight"] = _conv(rng, ci, 1, k, k)
+            _bn(rng, sd, p + ".dw_conv.bn", ci)
+            if se:
+                sd[p + ".se.conv1.weight"], sd[p + ".se.conv1.bias"] = _conv(rng, ci // 4, ci, 1, 1), _b(rng, ci // 4)
+                sd[p + ".se.conv2.weight"], sd[p + ".se.conv2.bias"] = _conv(rng, ci, ci // 4, 1, 1), _b(rng, ci)
+            sd[p + ".pw_conv.conv.weight"] = _conv(rng, co, ci, 1, 1)
+            _bn(rng, sd, p + ".pw_conv.bn", co)
+    sd["last_conv.weight"] = _conv(rng, 1280, 512, 1, 1)
+    sd["fc.weight"], sd["fc.bias"] = _lin(rng, class_num, 1280, gain=400.0), _b(rng, class_num)
+    return sd
