@@ -35,7 +35,7 @@ def _basic_block(x, sd, p, stride):
 @torch.no_grad()
 def dbnet_r18_forward(sd: Mapping[str, np.ndarray], x: torch.Tensor, return_features: bool = False):
     """x: fp32 [N,3,H,W] -> probability map fp32 [N,1,H,W]."""
-    x = x.float()
+    x = x.to(_t(sd, "backbone.conv1.weight").dtype)  # fp32 oracle; the dtype of the weights when a half copy is timed on the GPU
     x = F.relu(_bn(F.conv2d(x, _t(sd, "backbone.conv1.weight"), stride=2, padding=3), sd, "backbone.bn1"))
     x = F.max_pool2d(x, 3, 2, 1)
     feats = []

@@ -136,7 +136,7 @@ def _ida_up(layers, sd, p, startp, endp, up_f, tv):
 @torch.no_grad()
 def lore_dla34_features(sd: Mapping[str, np.ndarray], x: torch.Tensor, use_torchvision: bool = True) -> torch.Tensor:
     """x fp32 [N,3,H,W] (H, W multiples of 32) -> the 64-channel stride-4 feature map y[-1] the heads read."""
-    layers = dla34_base(sd, x.float())[2:]  # first_level = 2: strides 4, 8, 16, 32
+    layers = dla34_base(sd, x.to(_t(sd, "base.base_layer.0.weight").dtype))[2:]  # first_level = 2: strides 4, 8, 16, 32
     scales = np.array([1, 2, 4, 8], dtype=int)
     out = [layers[-1]]
     for i in range(len(layers) - 1):

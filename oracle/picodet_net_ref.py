@@ -77,7 +77,7 @@ def picohead_forward(sd, feats, num_classes):
 @torch.no_grad()
 def picodet_forward(backbone_sd, neck_sd, head_sd, x: torch.Tensor, num_classes: int = 5, return_features: bool = False):
     """x fp32 [N,3,H,W] (pre-processed) -> (scores[4] fp32 [N,HW_l,C], dfl[4] fp32 [N,HW_l,32])."""
-    c = lcnet_all(backbone_sd, x.float())
+    c = lcnet_all(backbone_sd, x.to(_t(backbone_sd, "conv1.conv.weight").dtype))
     neck = csppan_forward(neck_sd, c)
     s, d = picohead_forward(head_sd, neck, num_classes)
     if return_features:

@@ -79,3 +79,93 @@ def test_recogniser_full_batch_is_batch_independent():
     # identical arithmetic per token is expected (1.0); the bound only allows arg-max flips at exact near-ties
     assert same >= 0.999 and indep >= 0.999
     rec.close()
+
+
+# ---------------------------------------------------------------------------------------------- oracle parity AT the BASELINE sizes
+def test_dbnet_and_db_boxes_vs_oracle_on_a_full_960_page():
+    """One 960 x 960 page (BASELINE configs[0] / [1] page size) through the fp32 oracle (~1 s on the host): the fp16-operand engine
+    within PROB_TOL, the fp32x engine within the north-star's 1e-3, and the boxes of a planted full-size map identical to the
+    reference post-process restatement."""
+    from oracle import db_post_ref, dbnet_ref
+
+    sd = synth.dbnet_r18_state_dict(0)
+    page = synth.synthetic_page(401, PAGE, PAGE)
+    mean, std = np.array(MEAN, np.float32).reshape(1, 1, 3), np.array(STD, np.float32).reshape(1, 1, 3)
+    x = ((page[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)[None]
+    want = dbnet_ref.dbnet_r18_forward(sd, torch.from_numpy(np.ascontiguousarray(x))).numpy()
+    pages = torch.from_numpy(page[None]).cuda()
+    for precise, tol in ((False, PROB_TOL), (True, 1e-3)):
+        det = Engine("dbnet_r18", weights.pack_dbnet_r18(sd, precise=precise))
+        got = det.dbnet_forward_u8(pages, MEAN, STD, 1.0 / 255.0, True).cpu().numpy()
+        err = float(np.abs(got - want).max())
+        print(f"960x960 page, precise={precise}: max|dprob| = {err:.3e}")
+        assert err <= tol
+        det.close()
+    post = Engine("post")
+    prob = synth.synthetic_prob_map(500, PAGE, PAGE, CROPS_PER_PAGE)
+    boxes, counts = post.db_boxes(torch.from_numpy(prob)[None, None].cuda(), [(PAGE, PAGE)])
+    want_boxes = db_post_ref.db_postprocess(prob, np.array([PAGE, PAGE, 1.0, 1.0]), (PAGE, PAGE, 3))
+    got_boxes = boxes.cpu().numpy()[0, : int(counts[0])]
+    assert got_boxes.shape == want_boxes.shape and len(want_boxes) > 10
+    np.testing.assert_array_equal(got_boxes, want_boxes.astype(np.float32))
+    post.close()
+
+
+def test_recogniser_vs_oracle_on_a_96_crop_pass():
+    """96 text-line crops 32 x 320 (one recogniser pass of the round-1 bench) through the fp32 oracle: fp16-operand logits within
+    2e-2 with the arg-max equal outside the margin band; fp32x logits within 1e-3 and EVERY token id equal."""
+    from oracle import convnextvit_ref as ref
+
+    sd = synth.convnext_vit_state_dict(0)
+    crops = np.stack([synth.synthetic_text_crop(600 + i, 32, 320) for i in range(96)])
+    want = ref.convnextvit_forward(sd, ref.preprocess(list(crops)))
+    cu = torch.from_numpy(crops).cuda()
+    for precise, tol in ((False, 2e-2), (True, 1e-3)):
+        rec = Engine("convnext_vit", weights.pack_convnext_vit(sd, precise=precise))
+        ids, logits = rec.convnextvit_forward_u8(cu, return_logits=True)
+        err = float((logits.cpu() - want).abs().max())
+        print(f"96 crops, precise={precise}: max|dlogit| = {err:.3e}")
+        assert err <= tol
+        bad = ids.cpu().numpy() != want.argmax(-1).numpy()
+        if precise:
+            assert not bad.any()
+        else:
+            top2 = torch.topk(want, 2, dim=-1).values
+            assert ((top2[..., 0] - top2[..., 1]).numpy()[bad] <= 2 * tol).all()
+        rec.close()
+
+
+def test_lore_vs_oracle_on_a_full_1024_image():
+    """One 1024 x 1024 table image (BASELINE configs[2] crop size) through the fp32 oracle of the Lore detector (~10 s on the
+    host): the four decoded head maps within the relative tolerance of the small-size parity tests, and the decode of the engine's
+    own maps identical to the oracle decode."""
+    from oracle import lore_decode_ref, lore_net_ref
+    from pdf_table_b200 import predictors
+
+    sd = synth.lore_dla34_state_dict(0)
+    sd["hm.2.bias"] = np.array([-0.3, -3.5], np.float32)
+    warped, meta = predictors.lore_preprocess(synth.synthetic_page(40, 1024, 1024))
+    lmean = np.array(Engine.LORE_MEAN, np.float32).reshape(1, 1, 3)
+    lstd = np.array(Engine.LORE_STD, np.float32).reshape(1, 1, 3)
+    x = ((warped / 255. - lmean) / lstd).astype(np.float32).transpose(2, 0, 1)[None]
+    want = lore_net_ref.lore_dla34_forward(sd, torch.from_numpy(np.ascontiguousarray(x)), heads=("hm", "reg", "wh", "st"))
+    eng, post = Engine("lore_dla34", weights.pack_lore_dla34(sd)), Engine("post")
+    maps = eng.lore_detect_forward_u8(torch.from_numpy(warped[None]).cuda())
+    m = maps.cpu().numpy()[0]
+    for name, sl in (("hm", slice(0, 2)), ("reg", slice(2, 4)), ("wh", slice(4, 12)), ("st", slice(12, 20))):
+        w = want[name][0].numpy()
+        if name == "hm":
+            w = 1.0 / (1.0 + np.exp(-w))
+        rel = float(np.abs(m[:, :, sl].transpose(2, 0, 1) - w).max() / max(np.abs(w).max(), 1e-6))
+        print(f"1024x1024 lore {name}: rel max|err| = {rel:.3e}")
+        assert rel <= 4e-3
+    inv = predictors.lore_affine([np.float32(meta[0]), np.float32(meta[1])], np.float32(meta[2]), 256, 256, True)[None]
+    dec = post.lore_decode(maps, None, None, None, inv)
+    n = int(dec["counts"][0])
+    z = np.zeros((1, 256, 256), np.float32)
+    ref = lore_decode_ref.lore_decode(m[:, :, 0:2].transpose(2, 0, 1), m[:, :, 2:4].transpose(2, 0, 1), m[:, :, 4:12].transpose(2, 0, 1),
+                                      m[:, :, 12:20].transpose(2, 0, 1), z, z, meta)
+    assert n == len(ref["polygons"]) and n > 5
+    np.testing.assert_array_equal(dec["polygons"][0, :n].cpu().numpy(), ref["polygons"])
+    eng.close()
+    post.close()
