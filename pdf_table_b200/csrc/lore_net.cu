@@ -23,7 +23,7 @@
 namespace dv {
 
 int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
-                    int flip, __half* out);
+                    int flip, __half* out, long long lo);
 int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out);
 int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer);
 int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer);
@@ -50,8 +50,14 @@ struct Step {
     std::string name;
 };
 
+// fp32x mode (blob entry "precision", weights.pack_lore_dla34(precise=True)): as in dbnet.cu every activation is a split-fp16
+// pair and every conv weight a [W_hi | W_lo | W_hi] triple per filter tap; root concatenations are [hi(all) | lo(all)] buffers
+// whose channel slices keep the buffer-wide lo offset; the deformable sampling blends hi + lo in fp32 with fp32 weights and
+// writes split column rows; the two full-resolution layers run on conv_igemm_tcgen05 (the window-conv kernel keeps fp16
+// weights in shared memory).  Head maps land within 1e-3 of the fp32 oracle's range (tests/test_gpu_lore.py).
 struct LoreNet : Model {
     Engine* e = nullptr;
+    bool precise = false;
     bool plain_up = false;  // CenterNet: DLAUp of plain IDAUp blocks (no DCN), heads hm / v2c / c2v / reg
     int N = 0, H = 0, W = 0;
     std::vector<void*> mem;
@@ -87,10 +93,27 @@ struct LoreNet : Model {
         t->W = w;
         t->C = c;
         t->ld = 0;
+        t->lo = 0;
         void* p = nullptr;
-        DV_TRY(alloc(mem, &p, t->elems() * sizeof(__half), zero));
+        DV_TRY(alloc(mem, &p, t->elems() * sizeof(__half) * (precise ? 2 : 1), zero));
         t->p = reinterpret_cast<__half*>(p);
+        if (precise) {  // [hi(C) | lo(C)] per pixel
+            t->ld = 2 * c;
+            t->lo = c;
+        }
         return 0;
+    }
+    // the zero-bordered stem image: never a pixel pair -- the lo copy is a second image batch behind the first
+    int stem_tensor(Tensor* t, int n, int h, int w, int c) {
+        const bool pr = precise;
+        precise = false;
+        const int rc = tensor(t, pr ? 2 * n : n, h, w, c, /*zero=*/true);
+        precise = pr;
+        if (rc == 0 && pr) {
+            t->N = n;
+            t->lo = static_cast<long long>(n) * h * w * c;
+        }
+        return rc;
     }
     // plan_* allocate their delta tables through the engine: move them into this model's pool
     void adopt(std::vector<void*>& pool) {
@@ -106,10 +129,11 @@ int get_conv(Engine* e, const std::string& name, ConvSpec* cs) {
     if (w->dtype != 1 || b->dtype != 0 || w->ndim != 2) return set_err(e, DV_ERR_WEIGHTS, "bad dtype/rank for '%s'", name.c_str());
     cs->w = reinterpret_cast<const __half*>(w->dptr);
     cs->bias = reinterpret_cast<const float*>(b->dptr);
-    const int taps = cs->KH * cs->KW;
+    const int parts = cs->split ? 3 : 1;  // fp32x: [W_hi | W_lo | W_hi] per filter tap
+    const int taps = cs->KH * cs->KW * parts;
     if (cs->stem) {
-        if (static_cast<int>(w->dims[0]) != cs->Cout || w->dims[1] != 448)
-            return set_err(e, DV_ERR_WEIGHTS, "'%s': stride-1 stem weight must be [%d,448]", name.c_str(), cs->Cout);
+        if (static_cast<int>(w->dims[0]) != cs->Cout || static_cast<int>(w->dims[1]) != 448 * parts)
+            return set_err(e, DV_ERR_WEIGHTS, "'%s': stride-1 stem weight must be [%d,%d]", name.c_str(), cs->Cout, 448 * parts);
         cs->Cin_pad = 64;
         cs->BK = 64;
     } else {
@@ -117,6 +141,7 @@ int get_conv(Engine* e, const std::string& name, ConvSpec* cs) {
             return set_err(e, DV_ERR_WEIGHTS, "'%s': weight shape [%u,%u] does not match Cout=%d taps=%d", name.c_str(), w->dims[0],
                            w->dims[1], cs->Cout, taps);
         cs->Cin_pad = static_cast<int>(w->dims[1]) / taps;
+        if (cs->split && cs->KH == 1 && cs->stride == 1) cs->Cin_pad *= 3;  // flat GEMM: plan_linear counts all three parts
         cs->BK = (cs->Cin_pad % 64 == 0) ? 64 : (cs->Cin_pad % 32 == 0) ? 32 : 16;
     }
     if (b->dims[0] < static_cast<uint32_t>((cs->Cout + 255) / 256 * 256))
@@ -128,11 +153,13 @@ EpiSpec epi(const Tensor& out, int act, const Tensor* res = nullptr) {
     EpiSpec es;
     es.out = out.p;
     es.out_ld = out.ldc();
+    es.split_off = static_cast<int>(out.lo);
     es.act = act;
     if (res) {
         es.res = res->p;
         es.res_mode = RES_SAME;
         es.res_ld = res->ldc();
+        es.res_lo = static_cast<int>(res->lo);
     }
     return es;
 }
@@ -145,6 +172,7 @@ int add_conv(LoreNet* m, const std::string& name, const Tensor& in, int cout, in
     cs.Cin = stem ? 3 : in.C;
     cs.Cout = cout;
     cs.stem = stem;
+    cs.split = m->precise;
     DV_TRY(get_conv(m->e, name, &cs));
     const int Ho = stem ? in.H - 6 : in.H / stride, Wo = stem ? in.W - 8 : in.W / stride;
     Step st;
@@ -225,7 +253,8 @@ int add_level(LoreNet* m, int lvl, const Tensor& x, Tensor* out) {
 int add_dcn(LoreNet* m, const std::string& p, const Tensor& x, int cout, Tensor* dst) {
     DV_TRY(m->tensor(dst, x.N, x.H, x.W, cout));
     const size_t rows = static_cast<size_t>(x.N) * x.H * x.W;
-    if (rows > m->om_rows || rows * 9 * x.C > m->col_elems) return set_err(m->e, DV_ERR_STATE, "lore: DCN scratch too small for %s", p.c_str());
+    if (rows > m->om_rows || rows * 9 * x.C * (m->precise ? 2 : 1) > m->col_elems)
+        return set_err(m->e, DV_ERR_STATE, "lore: DCN scratch too small for %s", p.c_str());
     {
         EpiSpec es;
         es.out = m->om;
@@ -245,8 +274,9 @@ int add_dcn(LoreNet* m, const std::string& p, const Tensor& x, int cout, Tensor*
         ConvSpec cs;
         cs.KH = cs.KW = 1;
         cs.Cout = cout;
+        cs.split = m->precise;
         DV_TRY(get_conv(m->e, p + ".dcn", &cs));
-        if (cs.Cin_pad != 9 * x.C) return set_err(m->e, DV_ERR_WEIGHTS, "'%s.dcn': K %d != 9*%d", p.c_str(), cs.Cin_pad, x.C);
+        if (cs.Cin_pad != 9 * x.C * (m->precise ? 3 : 1)) return set_err(m->e, DV_ERR_WEIGHTS, "'%s.dcn': K %d != 9*%d", p.c_str(), cs.Cin_pad, x.C);
         cs.Cin = 9 * x.C;
         cs.BK = 64;
         cs.flat = true;
@@ -354,10 +384,10 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
     m->N = N;
     m->H = H;
     m->W = W;
-    DV_TRY(m->tensor(&m->stem_in, N, H + 6, W + 8, 8, /*zero=*/true));
+    DV_TRY(m->stem_tensor(&m->stem_in, N, H + 6, W + 8, 8));
     // DCN scratch: the largest sampling matrix is 9*64 channels at stride 4 (or 9*128 at stride 8: same size)
     m->om_rows = static_cast<size_t>(N) * (H / 4) * (W / 4);
-    m->col_elems = m->plain_up ? 0 : m->om_rows * 9 * 64;
+    m->col_elems = m->plain_up ? 0 : m->om_rows * 9 * 64 * (m->precise ? 2 : 1);
     {
         void* p = nullptr;
         if (!m->plain_up) {
@@ -372,7 +402,8 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
     Tensor b0, l0, l1;
     DV_TRY(m->tensor(&l0, N, H, W, 16));
     DV_TRY(m->tensor(&l1, N, H / 2, W / 2, 32));
-    static const bool use_win = !(getenv("DV_WINCONV") && atoi(getenv("DV_WINCONV")) == 0);
+    static const bool win_env = !(getenv("DV_WINCONV") && atoi(getenv("DV_WINCONV")) == 0);
+    const bool use_win = win_env && !m->precise;
     if (use_win) {
         // the two full-resolution 16-channel layers run on conv_win_tcgen05 (load/store producer, resident filter):
         // base writes into a zero-bordered buffer (interior at +1,+1) so that level0 reads 4-pixel x 16-channel windows
@@ -462,7 +493,7 @@ int get_flat(Engine* e, const std::string& name, int K, int N, ConvSpec* cs) {
     cs->KH = cs->KW = 1;
     cs->Cout = N;
     DV_TRY(get_conv(e, name, cs));
-    if (cs->Cin_pad != K) return set_err(e, DV_ERR_WEIGHTS, "'%s': K %d != %d", name.c_str(), cs->Cin_pad, K);
+    if (cs->Cin_pad != K * (cs->split ? 3 : 1)) return set_err(e, DV_ERR_WEIGHTS, "'%s': K %d != %d", name.c_str(), cs->Cin_pad, K);
     cs->Cin = K;
     cs->flat = true;
     return 0;
@@ -480,13 +511,14 @@ int build_feat(Engine* e, LoreNet* m, int K, int cap) {
     m->offsets = reinterpret_cast<int32_t*>(p);
     m->totals = m->offsets + m->N + 1;
     m->overflow = m->totals + 2;
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 9 * C * 2, true));
+    const size_t sp = m->precise ? 2 : 1;  // fp32x: patch rows and hidden rows are [hi | lo] pairs
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 9 * C * 2 * sp, true));
     m->col_ax = reinterpret_cast<__half*>(p);
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * 9 * C * 2, true));
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * 9 * C * 2 * sp, true));
     m->col_cr = reinterpret_cast<__half*>(p);
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 2, true));
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 2 * sp, true));
     m->hid_ax = reinterpret_cast<__half*>(p);
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * D * 2, true));
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * D * 2 * sp, true));
     m->hid_cr = reinterpret_cast<__half*>(p);
     DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 4, true));
     m->out_ax = reinterpret_cast<float*>(p);
@@ -497,11 +529,13 @@ int build_feat(Engine* e, LoreNet* m, int K, int cap) {
         const int rows = h == 0 ? cap : 4 * cap;
         const int* m_dyn = m->totals + h;
         ConvSpec c1, c2;
+        c1.split = c2.split = m->precise;
         DV_TRY(get_flat(e, std::string(heads[h]) + ".conv", 9 * C, D, &c1));
         DV_TRY(get_flat(e, std::string(heads[h]) + ".out", D, D, &c2));
         EpiSpec e1, e2;
         e1.out = h == 0 ? m->hid_ax : m->hid_cr;
-        e1.out_ld = D;
+        e1.out_ld = D * static_cast<int>(sp);
+        e1.split_off = m->precise ? D : 0;
         e1.act = ACT_RELU;
         e1.m_dyn = m_dyn;
         e2.out = h == 0 ? m->out_ax : m->out_cr;
@@ -525,6 +559,7 @@ int lore_create(Engine* e) {
     LoreNet* m = new LoreNet();
     m->e = e;
     m->plain_up = e->kind == "centernet_dla34";
+    m->precise = e->find("precision") != nullptr;
     e->model.reset(m);
     return 0;
 }
@@ -540,14 +575,14 @@ int lore_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4) 
     auto it = m->named.find(name);
     if (it == m->named.end()) return set_err(e, DV_ERR_ARG, "no tensor named '%s'", name);
     const Tensor& t = it->second;
-    if (t.ld != 0) return set_err(e, DV_ERR_UNSUPPORTED, "tensor '%s' is a slice", name);
+    if (t.ld != 0 && t.lo == 0) return set_err(e, DV_ERR_UNSUPPORTED, "tensor '%s' is a slice", name);
     if (dims4) {
         dims4[0] = t.N;
         dims4[1] = t.C;
         dims4[2] = t.H;
         dims4[3] = t.W;
     }
-    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw);
+    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw, t.ldc(), static_cast<int>(t.lo));
     return 0;
 }
 
@@ -558,7 +593,7 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
     if (N <= 0 || H <= 0 || W <= 0) return set_err(e, DV_ERR_ARG, "lore_detect_forward: bad arguments");
     if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
     if (!in_nchw && !in_u8) return set_err(e, DV_ERR_ARG, "lore_detect_forward: no input");
-    DV_TRY(op_img_to_stem8(e, in_u8, in_nchw, N, H, W, mean3, std3, flip, m->stem_in.p));
+    DV_TRY(op_img_to_stem8(e, in_u8, in_nchw, N, H, W, mean3, std3, flip, m->stem_in.p, m->stem_in.lo));
     float* maps = maps_out ? maps_out : m->maps;
     for (Step& st : m->steps) {
         switch (st.kind) {

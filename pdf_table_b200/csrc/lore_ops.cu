@@ -16,12 +16,37 @@ namespace dv {
 
 static inline int grid_for(long long n, int block) { return static_cast<int>((n + block - 1) / block); }
 
+// fp32x (split-fp16) helpers: a value = hi + lo, both fp16, `lo` elements apart (engine.h Tensor::lo)
+__device__ __forceinline__ void load8_split(const __half* p, long long lo, float* v) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + lo));
+    const __half2 *ha = reinterpret_cast<const __half2*>(&a), *hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 x = __half22float2(ha[i]), y = __half22float2(hb[i]);
+        v[2 * i] = x.x + y.x;
+        v[2 * i + 1] = x.y + y.y;
+    }
+}
+__device__ __forceinline__ void store8_split(__half* p, long long lo, const float* v) {
+    uint4 a, b;
+    __half2 *ha = reinterpret_cast<__half2*>(&a), *hb = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ha[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(ha[i]);
+        hb[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(p) = a;
+    *reinterpret_cast<uint4*>(p + lo) = b;
+}
+
 // ---------------------------------------------------------------------------------------------- stem input
 // in: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W] (already normalised) -> fp16 [N, H+6, W+8, 8], interior at (+3,+3).
 // The u8 path mirrors numpy: (x / 255. - mean) / std evaluated in float64, then .astype(float32).
 __global__ void __launch_bounds__(256)
 k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, double3 mean, double3 stdv,
-               int flip, __half* __restrict__ out) {
+               int flip, __half* __restrict__ out, long long lo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * H * W;
     if (idx >= total) return;
@@ -55,11 +80,20 @@ k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, in
     u.z = 0u;
     u.w = 0u;
     const int Hp = H + 6, Wp = W + 8;
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 8) = u;
+    __half* op = out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 8;
+    *reinterpret_cast<uint4*>(op) = u;
+    if (lo > 0) {  // fp32x: the residual halves go to a second image batch `lo` elements further
+        const float2 fa = __half22float2(a);
+        const __half2 la = __floats2half2_rn(v0 - fa.x, v1 - fa.y);
+        const __half2 lb = __floats2half2_rn(v2 - __low2float(b), 0.f);
+        u.x = *reinterpret_cast<const uint32_t*>(&la);
+        u.y = *reinterpret_cast<const uint32_t*>(&lb);
+        *reinterpret_cast<uint4*>(op + lo) = u;
+    }
 }
 
 int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
-                    int flip, __half* out) {
+                    int flip, __half* out, long long lo) {
     const long long total = static_cast<long long>(N) * H * W;
     double3 m = make_double3(0, 0, 0), s = make_double3(1, 1, 1);
     if (u8) {
@@ -68,7 +102,7 @@ int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H
         s = make_double3(std3[0], std3[1], std3[2]);
     }
     e->launch_begin("k_img_to_stem8", "pre", 0.0, total * ((u8 ? 3.0 : 12.0) + 16.0));
-    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out);
+    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out, lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -101,10 +135,43 @@ k_maxpool2x2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
 }
 
+__global__ void __launch_bounds__(256)
+k_maxpool2x2_split(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, long long loi, __half* __restrict__ out, int ldo, long long loo) {
+    const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const __half* ip = in + ((static_cast<long long>(n) * H + 2 * oy) * W + 2 * ox) * ldi + c8 * 8;
+    float a[8], b[8];
+    load8_split(ip, loi, a);
+    load8_split(ip + ldi, loi, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], b[i]);
+    load8_split(ip + static_cast<long long>(W) * ldi, loi, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], b[i]);
+    load8_split(ip + static_cast<long long>(W) * ldi + ldi, loi, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], b[i]);
+    store8_split(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8, loo, a);
+}
+
 int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out) {
-    if ((in.C % 8) || (in.H & 1) || (in.W & 1) || out.C != in.C || out.H != in.H / 2 || out.W != in.W / 2)
+    if ((in.C % 8) || (in.H & 1) || (in.W & 1) || out.C != in.C || out.H != in.H / 2 || out.W != in.W / 2 || (in.lo > 0) != (out.lo > 0))
         return set_err(e, DV_ERR_UNSUPPORTED, "maxpool2x2: bad shapes");
     const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    if (in.lo > 0) {
+        e->launch_begin("k_maxpool2x2", "maxpool", 0.0, 4.0 * (double)in.elems() * 1.25);
+        k_maxpool2x2_split<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), in.lo, out.p, out.ldc(), out.lo);
+        e->launch_end();
+        DV_CUDA(e, cudaGetLastError());
+        return 0;
+    }
     e->launch_begin("k_maxpool2x2", "maxpool", 0.0, 2.0 * (double)in.elems() * 1.25);
     k_maxpool2x2<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), out.p, out.ldc());
     e->launch_end();
@@ -226,7 +293,59 @@ k_dcn_im2col(const __half* __restrict__ in, int H, int W, int lcv, int ldi, cons
     }
 }
 
+// fp32x variant: one thread = (pixel, 8 channels), nine taps in a loop; samples are hi + lo in fp32, blend weights stay fp32
+// (torchvision's bilinear_interpolate arithmetic), the column row is written as [hi(9C) | lo(9C)].
+__global__ void __launch_bounds__(256)
+k_dcn_im2col_split(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, long long lo, const float* __restrict__ om,
+                   __half* __restrict__ col) {
+    const int cv = C >> 3;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * H * W * cv) return;
+    const int c8 = static_cast<int>(idx % cv);
+    const long long pix = idx / cv;
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const long long n = pix / (static_cast<long long>(W) * H);
+    const float* o = om + pix * 32;
+    const __half* base = in + n * H * W * ldi + c8 * 8;
+    __half* dst = col + pix * 18 * C + c8 * 8;
+    for (int tap = 0; tap < 9; ++tap) {
+        const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1);
+        const float mask = 1.f / (1.f + expf(-__ldg(o + 18 + tap)));
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const float py = static_cast<float>(y + ky - 1) + dy, px = static_cast<float>(x + kx - 1) + dx;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (py > -1.f && py < static_cast<float>(H) && px > -1.f && px < static_cast<float>(W)) {
+            const float fy = floorf(py), fx = floorf(px);
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+            const float wts[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+                if (yy < 0 || yy > H - 1 || xx < 0 || xx > W - 1) continue;
+                float v[8];
+                load8_split(base + (static_cast<long long>(yy) * W + xx) * ldi, lo, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(wts[k], v[i], acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] *= mask;
+        }
+        store8_split(dst + tap * C, 9LL * C, acc);
+    }
+}
+
 int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer) {
+    if (in.lo > 0) {
+        if (in.C % 8) return set_err(e, DV_ERR_UNSUPPORTED, "dcn_im2col: C %% 8 != 0");
+        const long long total = static_cast<long long>(in.N) * in.H * in.W * (in.C / 8);
+        const double px = static_cast<double>(in.N) * in.H * in.W;
+        e->launch_begin("k_dcn_im2col", layer, px * 9 * in.C * 9.0, px * (in.C * 4.0 + 128.0 + 36.0 * in.C));
+        k_dcn_im2col_split<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), in.lo, om, col);
+        e->launch_end();
+        DV_CUDA(e, cudaGetLastError());
+        return 0;
+    }
     const int cv = in.C >> 3;
     int lcv = 0;
     while ((1 << lcv) < cv) ++lcv;
@@ -300,12 +419,52 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
 }
 
+__global__ void __launch_bounds__(256)
+k_up_dw_add_split(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, long long loi, const float* __restrict__ wt, int f,
+                  const __half* __restrict__ skip, int lds, long long los, __half* __restrict__ out, int ldo, long long loo) {
+    const int cv = C >> 3, Ho = h * f, Wo = w * f, k2 = 2 * f, pad = f >> 1;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
+    const int c8 = static_cast<int>(idx % cv);
+    long long t = idx / cv;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (skip != nullptr) load8_split(skip + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * lds + c8 * 8, los, acc);
+    const int iy1 = (oy + pad) / f, ix1 = (ox + pad) / f;
+    for (int a = 0; a < 2; ++a) {
+        const int iy = iy1 - a, ky = oy + pad - iy * f;
+        if (iy < 0 || iy >= h || ky >= k2) continue;
+        for (int b = 0; b < 2; ++b) {
+            const int ix = ix1 - b, kx = ox + pad - ix * f;
+            if (ix < 0 || ix >= w || kx >= k2) continue;
+            float v[8];
+            load8_split(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8, loi, v);
+            const float* wp = wt + (static_cast<long long>(ky) * k2 + kx) * C + c8 * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], __ldg(wp + i), acc[i]);
+        }
+    }
+    store8_split(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8, loo, acc);
+}
+
 // skip.p == nullptr: plain up-sampling (CenterNet's IDAUp concatenates instead of adding)
 int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer) {
     if ((in.C % 8) || out.C != in.C || out.H != in.H * f || out.W != in.W * f || (f != 2 && f != 4 && f != 8) ||
         (skip.p != nullptr && (skip.C != in.C || skip.H != out.H || skip.W != out.W)))
         return set_err(e, DV_ERR_UNSUPPORTED, "up_dw_add: bad shapes");
     const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+    if (in.lo > 0) {
+        if (out.lo <= 0 || (skip.p != nullptr && skip.lo <= 0)) return set_err(e, DV_ERR_UNSUPPORTED, "up_dw_add: mixed split / plain tensors");
+        e->launch_begin("k_up_dw_add", layer, 8.0 * (double)out.elems(), 4.0 * ((double)in.elems() + 2.0 * (double)out.elems()));
+        k_up_dw_add_split<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), in.lo, wt, f, skip.p,
+                                                                     skip.p ? skip.ldc() : 0, skip.lo, out.p, out.ldc(), out.lo);
+        e->launch_end();
+        DV_CUDA(e, cudaGetLastError());
+        return 0;
+    }
     e->launch_begin("k_up_dw_add", layer, 8.0 * (double)out.elems(), 2.0 * ((double)in.elems() + 2.0 * (double)out.elems()));
     k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.p ? skip.ldc() : 0, out.p,
                                                            out.ldc());
@@ -328,8 +487,10 @@ k_copy_slice(const __half* __restrict__ in, long long pixels, int C, int ldi, __
 int op_copy_slice(Engine* e, const Tensor& in, const Tensor& out) {
     if ((in.C % 8) || out.C != in.C || out.H != in.H || out.W != in.W || out.N != in.N) return set_err(e, DV_ERR_UNSUPPORTED, "copy_slice: bad shapes");
     const long long pixels = static_cast<long long>(in.N) * in.H * in.W;
+    if ((in.lo > 0) != (out.lo > 0)) return set_err(e, DV_ERR_UNSUPPORTED, "copy_slice: mixed split / plain tensors");
     e->launch_begin("k_copy_slice", "concat", 0.0, pixels * in.C * 4.0);
     k_copy_slice<<<grid_for(pixels * (in.C / 8), 256), 256, 0, e->stream>>>(in.p, pixels, in.C, in.ldc(), out.p, out.ldc());
+    if (in.lo > 0) k_copy_slice<<<grid_for(pixels * (in.C / 8), 256), 256, 0, e->stream>>>(in.p + in.lo, pixels, in.C, in.ldc(), out.p + out.lo, out.ldc());
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -375,7 +536,7 @@ __global__ void k_cell_offsets(const int32_t* __restrict__ counts, int N, int ca
 __global__ void __launch_bounds__(128)
 k_gather_patch3x3(const __half* __restrict__ feat, int H, int W, int C, int K, int cap, const int32_t* __restrict__ counts,
                   const int32_t* __restrict__ offsets, const int32_t* __restrict__ ax_idx, const int32_t* __restrict__ cr_idx,
-                  __half* __restrict__ col_ax, __half* __restrict__ col_cr) {
+                  __half* __restrict__ col_ax, __half* __restrict__ col_cr, int ldf, long long lof) {
     const int j = blockIdx.x, n = blockIdx.y;
     if (j >= counts[n]) return;
     const int row = offsets[n] + j;
@@ -388,11 +549,18 @@ k_gather_patch3x3(const __half* __restrict__ feat, int H, int W, int C, int K, i
         const int pt = t / (9 * cv);
         const int pix = pt == 0 ? ax_idx[o] : cr_idx[o * 4 + pt - 1];
         const int y = pix / W + tap / 3 - 1, x = pix % W + tap % 3 - 1;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < H && x >= 0 && x < W)
-            u = __ldg(reinterpret_cast<const uint4*>(feat + ((static_cast<long long>(n) * H + y) * W + x) * C + c8 * 8));
-        __half* dst = pt == 0 ? col_ax + static_cast<long long>(row) * 9 * C : col_cr + (4LL * row + pt - 1) * 9 * C;
+        uint4 u = make_uint4(0, 0, 0, 0), ul = make_uint4(0, 0, 0, 0);
+        const bool in_img = y >= 0 && y < H && x >= 0 && x < W;
+        const __half* src = feat + ((static_cast<long long>(n) * H + y) * W + x) * ldf + c8 * 8;
+        if (in_img) u = __ldg(reinterpret_cast<const uint4*>(src));
+        // fp32x: the feature map is a split pair and the patch rows are [hi(9C) | lo(9C)]
+        const int rw = lof > 0 ? 18 * C : 9 * C;
+        __half* dst = pt == 0 ? col_ax + static_cast<long long>(row) * rw : col_cr + (4LL * row + pt - 1) * rw;
         *reinterpret_cast<uint4*>(dst + tap * C + c8 * 8) = u;
+        if (lof > 0) {
+            if (in_img) ul = __ldg(reinterpret_cast<const uint4*>(src + lof));
+            *reinterpret_cast<uint4*>(dst + 9 * C + tap * C + c8 * 8) = ul;
+        }
     }
 }
 
@@ -421,10 +589,10 @@ int op_cell_offsets(Engine* e, const int32_t* counts, int N, int cap, int32_t* o
 
 int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int32_t* counts, const int32_t* offsets,
                        const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr) {
-    if ((feat.C % 8) || feat.ld != 0) return set_err(e, DV_ERR_UNSUPPORTED, "gather_patch3x3: dense C %% 8 == 0 input");
-    e->launch_begin("k_gather_patch3x3", "lore_feat", 0.0, (double)cap * 5 * 9 * feat.C * 4.0);
+    if ((feat.C % 8) || (feat.ld != 0 && feat.lo == 0)) return set_err(e, DV_ERR_UNSUPPORTED, "gather_patch3x3: dense C %% 8 == 0 input");
+    e->launch_begin("k_gather_patch3x3", "lore_feat", 0.0, (double)cap * 5 * 9 * feat.C * (feat.lo ? 8.0 : 4.0));
     k_gather_patch3x3<<<dim3(K, feat.N), 128, 0, e->stream>>>(feat.p, feat.H, feat.W, feat.C, K, cap, counts, offsets, ax_idx, cr_idx,
-                                                              col_ax, col_cr);
+                                                              col_ax, col_cr, feat.ldc(), feat.lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -916,6 +916,7 @@ class OcrTableStructureTask(BaseInferTask):
     (the reference's model_best.pth / processor_best.pth, lore/modeling_lore.py:88-101)."""
 
     K, MK = 3000, 5000  # process_detect_output (lore/lineless_table_process.py:593)
+    SUPPORTS_FP32X = True  # Lore detector: split-fp16 operand pairs (csrc/lore_net.cu); the processor always runs split
 
     def __init__(self, task: str = "ocr_table_structure", model: str = "Lore", task_type: str = "wtw", state_dict=None,
                  table_structure_merge: bool = False, max_cells_per_image: int = 3000, **kwargs):
@@ -927,6 +928,8 @@ class OcrTableStructureTask(BaseInferTask):
             raise RuntimeError("OcrTableStructureTask(model='Lore', predictor_type='b200') needs state_dict=(detector, processor)")
         if model == "CenterNet" and state_dict is None:
             raise RuntimeError("OcrTableStructureTask(model='CenterNet', predictor_type='b200') needs state_dict= (a DLASeg state_dict or a path)")
+        if model == "CenterNet" and kwargs.get("precision", "fp16") != "fp16":
+            raise RuntimeError("the CenterNet detector runs in fp16 operand precision only")
         self.task_type, self.table_structure_merge = task_type, table_structure_merge
         self.resolution, self.vis_thresh, self.wiz_rev = (1024, 1024), 0.2, True  # LoreConfig wtw (configuration_lore.py:86-100)
         # capacity of the cell-feature / processor buffers per image; the decode keeps at most K = 3000 cells per image
@@ -940,7 +943,7 @@ class OcrTableStructureTask(BaseInferTask):
         if model == "CenterNet":
             self.predictor = Engine("centernet_dla34", weights.pack_centernet_dla34(self._sd), device=self.device)
         else:
-            self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0]), device=self.device)
+            self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0], precise=self.precision == "fp32x"), device=self.device)
             self.processor = Engine("lore_processor", weights.pack_lore_processor(self._sd[1]), device=self.device)
         self._sd = None
 

@@ -268,7 +268,7 @@ def pack_convnext_vit(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> 
 
 
 # --------------------------------------------------------------------------- Lore (DLA-34 + DCNv2 detector)
-def pack_stem7x7_s1(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+def pack_stem7x7_s1(weight, bn=None, split: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """7x7 stride-1 stem on a 3-channel image: K index = r*64 + s*8 + c (s padded 7->8, c padded 3->8), matching the
     overlapping-window TMA view of the zero-bordered 8-channel input (csrc/igemm_host.cu, A_STEM stride 1)."""
     w = _np(weight).astype(np.float32)
@@ -276,9 +276,10 @@ def pack_stem7x7_s1(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
     assert (cin, kh, kw) == (3, 7, 7), w.shape
     scale, shift = bn_affine(bn, cout)
     w = w * scale[:, None, None, None]
-    packed = np.zeros((cout, 7, 8, 8), np.float16)
-    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1).astype(np.float16)
-    return packed.reshape(cout, 7 * 64), pad_bias(shift)
+    packed = np.zeros((cout, 7, 8, 8), np.float32)
+    packed[:, :, :7, :3] = w.transpose(0, 2, 3, 1)
+    packed = packed.reshape(cout, 7 * 64)
+    return (split_packed(packed, 7) if split else packed.astype(np.float16)), pad_bias(shift)
 
 
 def pack_win3x3_c16(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
@@ -332,8 +333,10 @@ def _pad_rows(w: np.ndarray, b: np.ndarray, rows: int) -> Tuple[np.ndarray, np.n
 LORE_SMALL_HEADS = (("hm", 2), ("reg", 2), ("wh", 8), ("st", 8))  # channel order of the packed 24-wide map
 
 
-def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
-    """state_dict of the reference `get_dla_dcn(34, heads)` (lore/lore_dla_34.py:193-206) -> engine blob.
+def pack_lore_dla34(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> bytes:
+    """state_dict of the reference `get_dla_dcn(34, heads)` (lore/lore_dla_34.py:193-206) -> engine blob.  precise=True packs
+    every conv weight as a split-fp16 triple (per filter tap; over the whole K for the convs that run as flat GEMMs over gathered
+    columns: DCN main conv, ax / cr 3x3) and marks the blob with a "precision" entry (fp32x mode, csrc/lore_net.cu).
 
     BatchNorm is folded everywhere (incl. the BN after each DCN).  conv_offset_mask keeps its 27 outputs padded to 32
     (fp32 epilogue).  The four small heads share one 3x3 conv (64 -> 4*256) and one block-diagonal 1x1 (1024 -> 24);
@@ -344,10 +347,15 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
     def put(name, wb):
         t[name + ".w"], t[name + ".b"] = wb
 
-    put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1")))
+    pack_conv = pack_conv_split if precise else globals()["pack_conv"]
+    flat = (lambda w, b=None, bn=None: pack_conv_split(w, b, bn, flat=True)) if precise else globals()["pack_conv"]
+    if precise:
+        t["precision"] = np.array([1], np.int32)
+    put("base", pack_stem7x7_s1(sd["base.base_layer.0.weight"], _bn(sd, "base.base_layer.1"), split=precise))
     put("level0", pack_conv(sd["base.level0.0.weight"], None, _bn(sd, "base.level0.1")))
-    put("level0.win", pack_win3x3_c16(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
-    put("level0.winp", pack_win3x3_c16_planar(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
+    if not precise:  # the window-conv kernel keeps fp16 weights in shared memory: fp32x runs these two layers on conv_igemm_tcgen05
+        put("level0.win", pack_win3x3_c16(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
+        put("level0.winp", pack_win3x3_c16_planar(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
     put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
     for k in sd:
         if not k.startswith("base.level") or k.startswith(("base.level0", "base.level1")):
@@ -364,7 +372,7 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
     for k in sd:
         if k.endswith(".conv.conv_offset_mask.weight"):
             p = k[: -len(".conv.conv_offset_mask.weight")]  # e.g. dla_up.ida_0.proj_1
-            put(p + ".dcn", pack_conv(sd[p + ".conv.weight"], sd[p + ".conv.bias"], _bn(sd, p + ".actf.0")))
+            put(p + ".dcn", flat(sd[p + ".conv.weight"], sd[p + ".conv.bias"], _bn(sd, p + ".actf.0")))
             w, b = pack_conv(sd[k], sd[p + ".conv.conv_offset_mask.bias"])
             put(p + ".om", _pad_rows(w, b, 32))
         elif ".up_" in k and k.endswith(".weight"):
@@ -383,7 +391,7 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
         row += c
     put("heads.out", pack_conv(w1, b1))
     for h in ("ax", "cr"):
-        put(f"{h}.conv", pack_conv(f(f"{h}.0.weight"), f(f"{h}.0.bias")))
+        put(f"{h}.conv", flat(f(f"{h}.0.weight"), f(f"{h}.0.bias")))
         put(f"{h}.out", pack_conv(f(f"{h}.2.weight"), f(f"{h}.2.bias")))
     return write_blob(t)
 

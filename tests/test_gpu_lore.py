@@ -77,6 +77,57 @@ def test_lore_detector_levels_vs_oracle(lore_engine):
     assert err < REL_TOL * max(float(np.abs(want).max()), 1.0)
 
 
+def test_lore_detector_fp32x_meets_the_north_star_bound(post_engine):
+    """precision="fp32x" (split-fp16 operand pairs through every conv, fp32 deformable sampling): head maps, DLA levels and the
+    sparse ax / cr cell features within 1e-3 of the fp32 oracle (relative to each tensor's range, absolute for ranges < 1)."""
+    TOL = 1e-3
+    sd = synth.lore_dla34_state_dict(0)
+    eng = Engine("lore_dla34", weights.pack_lore_dla34(sd, precise=True))
+    g = np.load(os.path.join(GOLDEN, "lore_dla34_seed0.npz"))
+    got = _unpack(eng.lore_detect_forward(torch.from_numpy(g["x"]).cuda()))
+    for k in ("hm", "reg", "wh", "st"):
+        want = g[k].transpose(0, 2, 3, 1)
+        if k == "hm":
+            want = 1.0 / (1.0 + np.exp(-want))
+        err = float(np.abs(got[k] - want).max()) / max(1.0, float(np.abs(want).max()))
+        print(f"fp32x {k}: rel max|err| {err:.3e}")
+        assert err < TOL, k
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.standard_normal((2, 3, 96, 160)).astype(np.float32))
+    maps = eng.lore_detect_forward(x.cuda())
+    base = lore_net_ref.dla34_base(sd, x)
+    for lvl in range(0, 6):
+        want = base[lvl].numpy()
+        err = float(np.abs(eng.debug_tensor(f"level{lvl}").cpu().numpy() - want).max())
+        print(f"fp32x level{lvl}: max|err| {err:.3e} (max|x| {float(np.abs(want).max()):.2f})")
+        assert err < TOL * max(float(np.abs(want).max()), 1.0), f"level{lvl}"
+    want = lore_net_ref.lore_dla34_features(sd, x).numpy()
+    err = float(np.abs(eng.debug_tensor("feat").cpu().numpy() - want).max())
+    print(f"fp32x feat: max|err| {err:.3e} (max|x| {float(np.abs(want).max()):.2f})")
+    assert err < TOL * max(float(np.abs(want).max()), 1.0)
+    # sparse ax / cr heads on planted cells
+    planted = maps.clone()
+    prng = np.random.default_rng(5)
+    for i in range(2):
+        for _ in range(20):
+            planted[i, int(prng.integers(2, 22)), int(prng.integers(2, 38)), 0] = float(prng.uniform(0.5, 0.95))
+    eye = np.tile(np.array([[1.0, 0, 0], [0, 1.0, 0]]), (2, 1, 1))
+    dec = post_engine.lore_decode(planted, None, None, None, eye, wiz_rev=False, vis_thresh=0.3)
+    feat, offsets = eng.lore_cell_features(dec, max_rows=128, check_overflow=True)
+    out = lore_net_ref.lore_dla34_forward(sd, x, heads=("ax", "cr"))
+    counts, offs = dec["counts"].cpu().numpy(), offsets.cpu().numpy()
+    worst, scale = 0.0, 1.0
+    for i in range(2):
+        ax, cr = out["ax"][i].numpy().reshape(256, -1), out["cr"][i].numpy().reshape(256, -1)
+        a_idx, c_idx = dec["ax_idx"].cpu().numpy()[i, : counts[i]], dec["cr_idx"].cpu().numpy()[i, : counts[i]]
+        want = ax[:, a_idx].T + sum(cr[:, c_idx[:, k]].T for k in range(4))
+        worst = max(worst, float(np.abs(feat.cpu().numpy()[offs[i]: offs[i + 1]] - want).max()))
+        scale = max(scale, float(np.abs(want).max()))
+    print(f"fp32x cell features: {counts.sum()} cells, max|err| {worst:.3e} (max|x| {scale:.2f})")
+    assert counts.sum() >= 20 and worst < TOL * scale
+    eng.close()
+
+
 def test_lore_cell_features_vs_dense_heads(lore_engine, post_engine):
     """The sparse ax / cr evaluation equals gathering the oracle's dense head maps at the same points."""
     sd = synth.lore_dla34_state_dict(0)

