@@ -14,6 +14,7 @@
 #include "igemm_params.h"
 #include "win_conv_params.h"
 #include "mlp_params.h"
+#include "dcn_params.h"
 
 namespace dv {
 
@@ -210,6 +211,19 @@ bool mlp_fused_supported(int C);  // C in {96, 192, 256}; DV_MLP_FUSED=0 disable
 int plan_mlp(Engine* e, const __half* h, int M, int C, const __half* w1, const float* b1, const __half* w2, const float* b2,
              float* x, MlpPlan* plan, const char* name);
 int launch_mlp(Engine* e, const MlpPlan& plan);
+
+// dcn_fused_tcgen05 (dcn_fused.cuh): deformable sampling + 3x3 GEMM + bias + ReLU, no column buffer in global memory
+struct DcnPlan {
+    DcnParams prm;
+    int grid = 0;
+    size_t smem = 0;
+    double flops = 0, bytes = 0;
+    std::string name;
+};
+bool dcn_fused_enabled();  // DV_DCN_FUSED=0 selects k_dcn_im2col + the flat GEMM
+int plan_dcn(Engine* e, const Tensor& in, const float* om, const __half* w, const float* bias, int cout, int act, const Tensor& out,
+             DcnPlan* plan, const char* name);
+int launch_dcn(Engine* e, const DcnPlan& plan);
 
 // ops.cu (simple HBM-bound kernels)
 int op_nchw_f32_to_stem(Engine* e, const float* in, int N, int H, int W, __half* out, long long lo = 0);

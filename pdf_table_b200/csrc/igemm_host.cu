@@ -11,6 +11,7 @@
 #include "igemm.cuh"
 #include "win_conv.cuh"
 #include "mlp_fused.cuh"
+#include "dcn_fused.cuh"
 
 namespace dv {
 
@@ -585,6 +586,71 @@ int launch_mlp(Engine* e, const MlpPlan& plan) {
         case 256: return launch_mlp_c<256>(e, plan);
     }
     return set_err(e, DV_ERR_UNSUPPORTED, "launch %s: fused MLP C = %d", plan.name.c_str(), plan.C);
+}
+
+// ------------------------------------------------------------------------------------------------ dcn_fused_tcgen05
+bool dcn_fused_enabled() {
+    const char* s = getenv("DV_DCN_FUSED");  // read at plan time: the A/B test builds one engine each way
+    return !(s && atoi(s) == 0);
+}
+
+int plan_dcn(Engine* e, const Tensor& in, const float* om, const __half* w, const float* bias, int cout, int act, const Tensor& out,
+             DcnPlan* plan, const char* name) {
+    if ((in.C % 64) || in.lo > 0 || out.lo > 0 || !(cout == 64 || cout == 128 || cout == 256) || out.C != cout || out.N != in.N ||
+        out.H != in.H || out.W != in.W || (in.ldc() % 8) || (out.ldc() % 8))
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: fused DCN needs C %% 64 == 0, cout in {64, 128, 256}, fp16 operands", name);
+    if (static_cast<long long>(in.H) * in.W * in.ldc() * 2 >= (1LL << 31))  // 32-bit byte offsets inside an image
+        return set_err(e, DV_ERR_UNSUPPORTED, "%s: fused DCN image too large", name);
+    DcnParams& p = plan->prm;
+    memset(&p, 0, sizeof(p));
+    const uint64_t K = 9ull * in.C;
+    {
+        uint64_t dims[2] = {K, static_cast<uint64_t>(cout)}, str[1] = {K * 2};
+        uint32_t box[2] = {64, static_cast<uint32_t>(cout)};
+        DV_TRY(encode_map(e, &p.tmB, w, 2, dims, str, box, 128, name));
+    }
+    p.in = in.p;
+    p.om = om;
+    p.bias = bias;
+    p.out = out.p;
+    p.N = in.N;
+    p.H = in.H;
+    p.W = in.W;
+    p.C = in.C;
+    p.ldi = in.ldc();
+    p.ldo = out.ldc();
+    p.cout = cout;
+    p.tiles_x = (in.W + kDcnTW - 1) / kDcnTW;
+    p.tiles_y = (in.H + kDcnTH - 1) / kDcnTH;
+    p.n_tiles = p.tiles_x * p.tiles_y * in.N;
+    p.stages = cout == 64 ? 4 : cout == 128 ? 4 : 3;
+    if (getenv("DV_DCN_STAGES")) p.stages = std::min(kDcnMaxStages, std::max(2, atoi(getenv("DV_DCN_STAGES"))));
+    p.act = act;
+    p.dbg = getenv("DV_DCN_DEBUG") ? atoi(getenv("DV_DCN_DEBUG")) : 0;
+    plan->grid = p.n_tiles < e->num_sms ? p.n_tiles : e->num_sms;
+    plan->smem = dcn_smem_bytes(p.stages, cout);
+    if (plan->smem > 220 * 1024) return set_err(e, DV_ERR_UNSUPPORTED, "%s: fused DCN shared memory %zu", name, plan->smem);
+    const double px = static_cast<double>(in.N) * in.H * in.W;
+    plan->flops = 2.0 * px * static_cast<double>(K) * cout;
+    plan->bytes = px * (2.0 * in.C + 128.0 + 2.0 * cout) + 2.0 * static_cast<double>(K) * cout;  // input, offsets / masks, output, weights: once
+    plan->name = name;
+    return 0;
+}
+
+int launch_dcn(Engine* e, const DcnPlan& plan) {
+    static DeviceOnce attr_once;
+    if (attr_once.need(e->device)) {
+        cudaError_t attr_rc = cudaFuncSetAttribute(reinterpret_cast<const void*>(dcn_fused_tcgen05), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   220 * 1024);
+        if (attr_rc != cudaSuccess) return set_err(e, DV_ERR_CUDA, "cudaFuncSetAttribute(dcn_fused_tcgen05): %s", cudaGetErrorString(attr_rc));
+        attr_once.mark(e->device);
+    }
+    e->launch_begin("dcn_fused_tcgen05", plan.name, plan.flops, plan.bytes);
+    dcn_fused_tcgen05<<<plan.grid, kDcnThreads, plan.smem, e->stream>>>(plan.prm);
+    e->launch_end();
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess) return set_err(e, DV_ERR_CUDA, "launch %s failed: %s", plan.name.c_str(), cudaGetErrorString(st));
+    return 0;
 }
 
 }  // namespace dv

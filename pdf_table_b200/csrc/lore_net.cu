@@ -40,8 +40,9 @@ constexpr int kCh[6] = {16, 32, 64, 128, 256, 512};
 constexpr int kLevels[6] = {1, 1, 1, 2, 2, 1};
 
 struct Step {
-    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY, WINCONV } kind;
+    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY, WINCONV, DCN } kind;
     ConvPlan plan;
+    DcnPlan dcn;
     WinConvPlan win;
     double win_flops = 0;
     Tensor a, b, c;
@@ -261,6 +262,21 @@ int add_dcn(LoreNet* m, const std::string& p, const Tensor& x, int cout, Tensor*
         es.out_ld = 32;
         es.out_f32 = 1;
         DV_TRY(add_conv(m, p + ".om", x, 32, 3, 1, es));
+    }
+    if (!m->precise && dcn_fused_enabled() && x.C % 64 == 0 && (cout == 64 || cout == 128 || cout == 256)) {
+        // one kernel: sampling producers -> swizzled shared-memory A tiles -> tcgen05 GEMM -> bias + ReLU (dcn_fused.cuh)
+        ConvSpec cs;
+        cs.KH = cs.KW = 1;
+        cs.Cout = cout;
+        DV_TRY(get_conv(m->e, p + ".dcn", &cs));
+        if (cs.Cin_pad != 9 * x.C) return set_err(m->e, DV_ERR_WEIGHTS, "'%s.dcn': K %d != 9*%d", p.c_str(), cs.Cin_pad, x.C);
+        Step st;
+        st.kind = Step::DCN;
+        st.name = p + ".dcn";
+        DV_TRY(plan_dcn(m->e, x, m->om, cs.w, cs.bias, cout, ACT_RELU, *dst, &st.dcn, st.name.c_str()));
+        m->flops += st.dcn.flops;
+        m->steps.push_back(st);
+        return 0;
     }
     {
         Step st;
@@ -607,6 +623,7 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
             case Step::SIGMOID: DV_TRY(op_sigmoid_cols(e, maps, static_cast<long long>(N) * (H / 4) * (W / 4), 24, 2)); break;
             case Step::COPY: DV_TRY(op_copy_slice(e, st.a, st.b)); break;
             case Step::WINCONV: DV_TRY(launch_win_conv(e, st.win, st.win_flops)); break;
+            case Step::DCN: DV_TRY(launch_dcn(e, st.dcn)); break;
         }
     }
     return 0;

@@ -77,6 +77,35 @@ def test_lore_detector_levels_vs_oracle(lore_engine):
     assert err < REL_TOL * max(float(np.abs(want).max()), 1.0)
 
 
+def test_fused_dcn_equals_the_three_launch_path(lore_engine, monkeypatch):
+    """dcn_fused_tcgen05 (sampling producers -> shared-memory A tiles -> tcgen05 GEMM, no column buffer) against k_dcn_im2col +
+    the flat GEMM it replaces (DV_DCN_FUSED=0): same fp16 blend weights, same K order -> bit-identical head maps and feature
+    map, on a ragged map size (24 x 40: partial 8 x 16 tiles on the right edge) and on a batch whose maps are tile multiples."""
+    ref_eng = Engine("lore_dla34", weights.pack_lore_dla34(synth.lore_dla34_state_dict(0)))
+    rng = np.random.default_rng(77)
+    for shape in ((2, 3, 96, 160), (1, 3, 256, 320), (3, 3, 64, 64)):
+        x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).cuda()
+        monkeypatch.setenv("DV_DCN_FUSED", "0")  # read when the network is planned for a new input shape
+        want = ref_eng.lore_detect_forward(x).clone()
+        monkeypatch.delenv("DV_DCN_FUSED")
+        want_feat = ref_eng.debug_tensor("feat").clone()
+        got = lore_engine.lore_detect_forward(x)
+        got_feat = lore_engine.debug_tensor("feat")
+        d = float((got - want).abs().max())
+        print(f"fused DCN vs im2col + GEMM {shape}: max |d maps| = {d:.3e}, max |d feat| = {float((got_feat - want_feat).abs().max()):.3e}")
+        assert torch.equal(got_feat, want_feat) and torch.equal(got, want)
+    names = [r["kernel"] for r in _profile(lore_engine, x)]
+    assert "dcn_fused_tcgen05" in names and "k_dcn_im2col" not in names
+    assert "k_dcn_im2col" in [r["kernel"] for r in _profile(ref_eng, x)]
+    ref_eng.close()
+
+
+def _profile(eng, x):
+    eng.profile_begin()
+    eng.lore_detect_forward(x)
+    return eng.profile_report()
+
+
 def test_lore_detector_fp32x_meets_the_north_star_bound(post_engine):
     """precision="fp32x" (split-fp16 operand pairs through every conv, fp32 deformable sampling): head maps, DLA levels and the
     sparse ax / cr cell features within 1e-3 of the fp32 oracle (relative to each tensor's range, absolute for ranges < 1)."""
