@@ -82,7 +82,9 @@ int dv_profile_begin(dv_handle h);
 long long dv_profile_report(dv_handle h, char* buf_host, size_t cap);
 
 /*
- * DBNet forward: fp32 NCHW pages -> fp32 probability map [N,1,H,W].
+ * DB text-detector forward: fp32 NCHW pages -> fp32 probability map [N,1,H,W].  The handle's model kind selects the
+ * network: "dbnet_r18" (the in-tree DBModel, db_net/dbnet.py:715) or "pp_det" (the PP-OCRv4 mobile detector, PPLCNetV3-0.75 +
+ * RSE-FPN + DBHead, the graph the reference downloads as ONNX: ocr_table_model_config.py:134-147).
  * Replaces OcrDetectionTask._run_model (ocr_detection_task.py:89-124): predictor(image) -> pred[0].
  * H and W must be multiples of 32 (DetResizeForTest guarantees it, db_pp/image_operators.py:304-305).
  */

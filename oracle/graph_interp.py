@@ -17,13 +17,15 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_STEM, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC = range(12)
-ACT_NONE, ACT_HSWISH, ACT_SWISH = 0, 4, 5
+OP_STEM, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC, OP_CONV, OP_DECONV2, OP_DBHEAD = range(15)
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SWISH = 0, 1, 4, 5
 
 
 def _act(x: torch.Tensor, act: int) -> torch.Tensor:
     if act == ACT_NONE:
         return x
+    if act == ACT_RELU:
+        return F.relu(x)
     if act == ACT_HSWISH:
         return F.hardswish(x)
     if act == ACT_SWISH:
@@ -78,12 +80,14 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
             avg = src.mean((2, 3))
             hid = F.relu(avg @ wt(w, "s1w").t() + wt(w, "s1b"))
             scale = torch.clamp((hid @ wt(w, "s2w").t() + wt(w, "s2b")) / 6.0 + 0.5, 0.0, 1.0)
-            out = src * scale[:, :, None, None]
+            out = src * (scale + (1.0 if k == 2 else 0.0))[:, :, None, None]  # k = 2: RSELayer shortcut x + x * s
         elif code == OP_UP2:  # nearest, to the destination tensor's own size
             dst = tens[out_t]
             iy = torch.clamp(torch.arange(dst.shape[2]) * src.shape[2] // dst.shape[2], max=src.shape[2] - 1)
             ix = torch.clamp(torch.arange(dst.shape[3]) * src.shape[3] // dst.shape[3], max=src.shape[3] - 1)
             out = src[:, :, iy][:, :, :, ix]
+            if aux >= 0:  # top-down FPN sum
+                out = out + tens[aux]
         elif code == OP_ADD:
             out = tens[in_t] + tens[aux]
         elif code == OP_AVGPOOL:
@@ -98,6 +102,16 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
             qkv = src[:, :, 0].transpose(1, 2).reshape(n, t_len, 3, k, d // k).permute(2, 0, 3, 1, 4)
             attn = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2), -1)
             out = (attn @ qkv[2]).permute(0, 2, 1, 3).reshape(n, t_len, d).transpose(1, 2)[:, :, None]
+        elif code == OP_CONV:  # dense k x k conv, stride 1: w fp16 [Cout][k*k*Cin_pad] (tap-major), b fp32 padded
+            wk = wt(w, "w").reshape(out_c, k * k, -1)[:, :, :in_c].reshape(out_c, k, k, in_c).permute(0, 3, 1, 2).contiguous()
+            out = _act(F.conv2d(src, wk, wt(w, "b")[:out_c], padding=k // 2), act)
+        elif code == OP_DECONV2:  # ConvTranspose 2x2 s2 as a GEMM + pixel shuffle: w [(dy*2+dx)*Cout + co][Cin_pad]
+            wk = wt(w, "w")[:, :in_c].reshape(2, 2, out_c, in_c).permute(3, 2, 0, 1).contiguous()  # -> [Cin, Cout, 2, 2]
+            out = _act(F.conv_transpose2d(src, wk, wt(w, "b")[:out_c], stride=2), act)
+        elif code == OP_DBHEAD:  # ConvTranspose 2x2 s2 C -> 1 + sigmoid -> fp32 probability map
+            wk = wt(w, "hw").reshape(in_c, 1, 2, 2)
+            heads["prob"] = torch.sigmoid(F.conv_transpose2d(src, wk, wt(w, "hb"), stride=2))
+            continue
         else:
             raise ValueError(f"unknown opcode {code}")
         dst = tens[out_t]

@@ -145,7 +145,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = dbnet_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
-        } else if (e->kind == "picodet" || e->kind == "pp_rec" || e->kind == "pplcnet_cls") {
+        } else if (e->kind == "picodet" || e->kind == "pp_rec" || e->kind == "pplcnet_cls" || e->kind == "pp_det") {
             rc = graph_create(e);
         } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34") {
             rc = lore_create(e);
@@ -235,7 +235,7 @@ double dv_model_flops(dv_handle h) {
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
     if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_flops(h);
-    if (h->kind == "picodet" || h->kind == "pp_rec") return graph_flops(h);
+    if (h->kind == "picodet" || h->kind == "pp_rec" || h->kind == "pp_det") return graph_flops(h);
     return 0.0;
 }
 
@@ -243,6 +243,7 @@ int dv_dbnet_forward(dv_handle h, const float* in_nchw_f32, int n, int height, i
     if (!h) return DV_ERR_ARG;
     if (!in_nchw_f32) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward: null input");
     DeviceGuard dev_guard(h->device);
+    if (h->kind == "pp_det") return ppdet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0.f, 0, n, height, width, prob_out);
     return dbnet_forward(h, in_nchw_f32, nullptr, nullptr, nullptr, 0.f, 0, n, height, width, prob_out);
 }
 
@@ -251,6 +252,7 @@ int dv_dbnet_forward_u8(dv_handle h, const uint8_t* pages_hwc_u8, int n, int hei
     if (!h) return DV_ERR_ARG;
     if (!pages_hwc_u8 || !mean3_host || !std3_host) return set_err(h, DV_ERR_ARG, "dv_dbnet_forward_u8: null input");
     DeviceGuard dev_guard(h->device);
+    if (h->kind == "pp_det") return ppdet_forward(h, nullptr, pages_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, prob_out);
     return dbnet_forward(h, nullptr, pages_hwc_u8, mean3_host, std3_host, scale, flip, n, height, width, prob_out);
 }
 
@@ -259,7 +261,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
     DeviceGuard dev_guard(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
-    if (h->kind == "picodet" && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
+    if ((h->kind == "picodet" || h->kind == "pp_det" || h->kind == "pp_rec") && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
     return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
 }
 

@@ -302,6 +302,8 @@ int picodet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const
 int rec_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, int N, int H, int W, float* probs, int32_t* ids,
                 float* maxp);
 int rec_time_steps(Engine* e, int H, int W);
+int ppdet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip, int N,
+                  int H, int W, float* prob_out);
 int cls_forward(Engine* e, const float* in_nchw, int N, int H, int W, float* logits, float* probs);
 
 // picodet_decode.cu

@@ -19,6 +19,13 @@
 //   OP_LN       LayerNorm over the channels of each position
 //   OP_ATTN     softmax(q k^T) v per (image, head) over the T positions of a text line (global mixer, 8 heads x 15)
 //   OP_CTC      Linear -> fp32 logits -> softmax: probabilities [N,T,C] (optional) + per-step arg-max / max probability
+// and, for the PP-OCRv4 mobile detector (pdf_table_b200/pp_det_graph.py: PPLCNetV3-0.75 + RSE-FPN + DBHead; CPU
+// mirror oracle/pp_det_ref.py):
+//   OP_SE with k = 2     the RSELayer shortcut x + x * s (db_fpn.py RSELayer), output may be a concatenation slice
+//   OP_UP2 with aux      nearest up-sampling + addend: the top-down sums out_k = in_k + up2(out_k+1)
+//   OP_CONV     dense k x k conv, stride 1, + bias + activation                       conv_igemm_tcgen05 (A_PATCH)
+//   OP_DECONV2  ConvTranspose 2x2 stride 2 + folded BN + activation                   conv_igemm_tcgen05, pixel-shuffle store
+//   OP_DBHEAD   ConvTranspose 2x2 stride 2 C -> 1 + sigmoid -> fp32 probability map [N,1,H,W]
 // Every tensor is NHWC fp16; an operand may be a channel slice (coff, c) of a wider buffer, which is how the CSP
 // concatenations exist without copies.  The plan (buffers, TMA descriptors) is built once per input shape.
 #include <stdlib.h>
@@ -29,7 +36,7 @@ namespace dv {
 
 namespace {
 
-enum { OP_STEM = 0, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC };
+enum { OP_STEM = 0, OP_DW, OP_PW, OP_SE, OP_UP2, OP_ADD, OP_HEAD, OP_AVGPOOL, OP_UNFOLD3, OP_LN, OP_ATTN, OP_CTC, OP_CONV, OP_DECONV2, OP_DBHEAD };
 
 __device__ __forceinline__ float act_f(float x, int act) {
     if (act == ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
@@ -500,12 +507,14 @@ k_se_scale(const __half* __restrict__ in, int HW, int C, const float* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-k_se_apply(const __half* __restrict__ in, long long total8, int HW, int C, const float* __restrict__ scale, __half* __restrict__ out) {
+k_se_apply(const __half* __restrict__ in, long long total8, int HW, int C, const float* __restrict__ scale, float shortcut,
+           __half* __restrict__ out, int ldo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= total8) return;
     const int cv = C >> 3;
     const int c8 = static_cast<int>(idx % cv);
-    const int n = static_cast<int>(idx / (static_cast<long long>(cv) * HW));
+    const long long pix = idx / cv;
+    const int n = static_cast<int>(pix / HW);
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(in) + idx);
     const float* sp = scale + n * C + c8 * 8;
     const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -514,13 +523,14 @@ k_se_apply(const __half* __restrict__ in, long long total8, int HW, int C, const
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float2 v = __half22float2(h[i]);
-        ho[i] = __floats2half2_rn(v.x * sp[2 * i], v.y * sp[2 * i + 1]);
+        ho[i] = __floats2half2_rn(v.x * (sp[2 * i] + shortcut), v.y * (sp[2 * i + 1] + shortcut));  // shortcut = 1: x + x * s
     }
-    reinterpret_cast<uint4*>(out)[idx] = o;
+    *reinterpret_cast<uint4*>(out + pix * ldo + c8 * 8) = o;
 }
 
 __global__ void __launch_bounds__(256)
-k_up2(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho, int Wo, __half* __restrict__ out, int ldo) {
+k_up2(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho, int Wo, const __half* __restrict__ add, __half* __restrict__ out,
+      int ldo) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
@@ -531,8 +541,56 @@ k_up2(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
     // F.interpolate(mode="nearest") to an explicit size: src = floor(dst * in / out)
     const int iy = min(static_cast<int>(static_cast<long long>(oy) * h / Ho), h - 1), ix = min(static_cast<int>(static_cast<long long>(ox) * w / Wo), w - 1);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8));
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8));
+    if (add != nullptr) {  // dense addend of the output's shape (the top-down sum of an FPN)
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(add + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + c8 * 8));
+        const __half2* ha = reinterpret_cast<const __half2*>(&a);
+        __half2* hu = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 x = __half22float2(hu[i]), y = __half22float2(ha[i]);
+            hu[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+        }
+    }
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = u;
+}
+
+// ConvTranspose2d(C -> 1, k 2, s 2) + sigmoid: fp16 [N,H,W,C] -> fp32 probability map [N,1,2H,2W]; w fp32 [C][dy*2+dx].
+// One thread per input pixel (DBHead.binarize conv3, det_db_head.py).
+__global__ void __launch_bounds__(128)
+k_dbhead(const __half* __restrict__ in, long long npix, int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
+         float* __restrict__ out) {
+    __shared__ float sw[64 * 4];
+    for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= npix) return;
+    const int x = static_cast<int>(idx % W), y = static_cast<int>((idx / W) % H);
+    const long long n = idx / (static_cast<long long>(W) * H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const uint4* ip = reinterpret_cast<const uint4*>(in + idx * C);
+    for (int j = 0; j < (C >> 3); ++j) {
+        const uint4 u = __ldg(ip + j);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 f = __half22float2(h[e2]);
+            const int c = j * 8 + e2 * 2;
+            a0 = fmaf(f.x, sw[c * 4 + 0], a0);
+            a1 = fmaf(f.x, sw[c * 4 + 1], a1);
+            a2 = fmaf(f.x, sw[c * 4 + 2], a2);
+            a3 = fmaf(f.x, sw[c * 4 + 3], a3);
+            a0 = fmaf(f.y, sw[c * 4 + 4], a0);
+            a1 = fmaf(f.y, sw[c * 4 + 5], a1);
+            a2 = fmaf(f.y, sw[c * 4 + 6], a2);
+            a3 = fmaf(f.y, sw[c * 4 + 7], a3);
+        }
+    }
+    const float b = __ldg(bias);
+    const int W2 = 2 * W;
+    float* op = out + (n * 2 * H + 2 * y) * W2 + 2 * x;
+    *reinterpret_cast<float2*>(op) = make_float2(1.f / (1.f + expf(-(a0 + b))), 1.f / (1.f + expf(-(a1 + b))));
+    *reinterpret_cast<float2*>(op + W2) = make_float2(1.f / (1.f + expf(-(a2 + b))), 1.f / (1.f + expf(-(a3 + b))));
 }
 
 __global__ void __launch_bounds__(256) k_add(const __half* __restrict__ a, const __half* __restrict__ b, long long total8, __half* __restrict__ out) {
@@ -564,7 +622,7 @@ k_head_split(const float* __restrict__ raw, long long M, int ld, int C, int R, f
 
 struct GOp {
     int code, in_t, in_coff, in_c, out_t, out_coff, out_c, k, stride, act, w, aux;
-    ConvPlan plan;  // OP_PW / OP_HEAD / OP_CTC
+    ConvPlan plan;  // OP_PW / OP_HEAD / OP_CTC / OP_CONV / OP_DECONV2
     const float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;
     float ps = 1.f, pb = 0.f;  // post-activation affine (w{id}.pa), identity when absent
     int has_pa = 0;
@@ -576,7 +634,7 @@ struct GOp {
 struct GraphNet : Model {
     Engine* e = nullptr;
     int N = 0, H = 0, W = 0;
-    int kind = 0;  // 0 = PicoDet (graph.meta[5]), 1 = PP-OCR recogniser
+    int kind = 0;  // graph.meta[5]: 0 = PicoDet, 1 = PP-OCR recogniser, 2 = PULC classifier, 3 = PP-OCR detector
     int num_classes = 0, reg_bins = 32, head_ld = 40;
     std::vector<int> tc, tdh, tdw, tph, tpw;  // channels; size = floor(ceil(H / dh) / ph) x floor(ceil(W / dw) / pw)
     std::vector<GOp> ops;
@@ -715,6 +773,12 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             case OP_HEAD:
                 if (static_cast<size_t>(N) * in.H * in.W > max_head_rows) max_head_rows = static_cast<size_t>(N) * in.H * in.W;
                 break;
+            case OP_DBHEAD:
+                if (op.in_c > 64 || in.C != op.in_c) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: DB head over %d channels", op.in_c);
+                op.f0 = wf32(e, op.w, "hw", static_cast<size_t>(op.in_c) * 4, &rc);
+                op.f1 = wf32(e, op.w, "hb", 1, &rc);
+                m->flops += 2.0 * N * in.H * in.W * op.in_c * 4;
+                break;
             default: break;
         }
         if (rc) return rc;
@@ -738,6 +802,49 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         void* p = nullptr;
         DV_TRY(m->alloc(&p, max_head_rows * m->head_ld * 4 + 16));
         m->head_raw = reinterpret_cast<float*>(p);
+    }
+    for (GOp& op : m->ops) {
+        if (op.code != OP_CONV && op.code != OP_DECONV2) continue;
+        const Tensor& in = m->tens[op.in_t];
+        const Tensor& out = m->tens[op.out_t];
+        const std::string wn = "w" + std::to_string(op.w);
+        const BlobTensor* w = e->find(wn + ".w");
+        const BlobTensor* b = e->find(wn + ".b");
+        const bool dec = op.code == OP_DECONV2;
+        const int taps = dec ? 1 : op.k * op.k, rows = dec ? 4 * op.out_c : op.out_c;
+        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != rows || (w->dims[1] % taps) ||
+            static_cast<int>(w->dims[1]) / taps < op.in_c || ((w->dims[1] / taps) % 16))
+            return set_err(e, DV_ERR_WEIGHTS, "graph: bad conv weights '%s' (want [%d, %d x >= %d])", wn.c_str(), rows, taps, op.in_c);
+        ConvSpec cs;
+        cs.KH = cs.KW = dec ? 1 : op.k;
+        cs.pad = dec ? 0 : op.k / 2;
+        cs.stride = 1;
+        cs.Cin = op.in_c;
+        cs.Cin_pad = static_cast<int>(w->dims[1]) / taps;
+        cs.Cout = rows;
+        cs.BK = (cs.Cin_pad % 64 == 0) ? 64 : (cs.Cin_pad % 32 == 0) ? 32 : 16;
+        cs.w = reinterpret_cast<const __half*>(w->dptr);
+        cs.bias = reinterpret_cast<const float*>(b->dptr);
+        EpiSpec es;
+        es.act = op.act;
+        es.out = out.p;
+        es.out_ld = out.C;
+        es.out_coff = op.out_coff;
+        if (dec) {
+            es.out_mode = OUT_SHUF2;
+            if (out.H != 2 * in.H || out.W != 2 * in.W || op.out_coff != 0 || out.C != op.out_c)
+                return set_err(e, DV_ERR_WEIGHTS, "graph: transposed conv '%s' needs a dense output at twice the input size", wn.c_str());
+        } else if (out.H != in.H || out.W != in.W) {
+            return set_err(e, DV_ERR_WEIGHTS, "graph: conv '%s' changes the map size", wn.c_str());
+        }
+        Tensor a = in;  // the op's channel slice of the input buffer
+        a.p = in.p + op.in_coff;
+        a.ld = in.C;
+        a.C = op.in_c;
+        DV_TRY(plan_conv(e, a, cs, es, in.H, in.W, &op.plan, wn.c_str()));
+        m->mem.push_back(e->owned.back());
+        e->owned.pop_back();
+        m->flops += op.plan.flops;
     }
     for (GOp& op : m->ops) {
         if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
@@ -877,6 +984,7 @@ struct GraphOut {
     int32_t* ids = nullptr;
     float* maxp = nullptr;
     float* logits = nullptr;
+    float* prob = nullptr;  // OP_DBHEAD: fp32 probability map [N,1,H,W]
 };
 
 int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8, const int32_t* widths, const float* mean3, const float* std3,
@@ -940,7 +1048,17 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 e->launch_end();
                 break;
             }
-            case OP_PW: DV_TRY(launch_conv(e, op.plan)); break;
+            case OP_PW:
+            case OP_CONV:
+            case OP_DECONV2: DV_TRY(launch_conv(e, op.plan)); break;
+            case OP_DBHEAD: {
+                if (!go.prob) return set_err(e, DV_ERR_ARG, "graph: no probability-map output");
+                const long long npix = static_cast<long long>(N) * in.H * in.W;
+                e->launch_begin("k_dbhead", "head", 2.0 * npix * op.in_c * 4, npix * (2.0 * op.in_c + 16.0));
+                k_dbhead<<<grid_for(npix, 128), 128, 0, s>>>(in.p, npix, in.H, in.W, op.in_c, op.f0, op.f1, go.prob);
+                e->launch_end();
+                break;
+            }
             case OP_SE: {
                 const int HW = in.H * in.W;
                 e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
@@ -948,14 +1066,15 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 e->launch_end();
                 const long long total8 = static_cast<long long>(N) * HW * (op.in_c / 8);
                 e->launch_begin("k_se_apply", "se", 0.0, total8 * 32.0);
-                k_se_apply<<<grid_for(total8, 256), 256, 0, s>>>(in.p, total8, HW, op.in_c, m->se_scale, out.p);
+                k_se_apply<<<grid_for(total8, 256), 256, 0, s>>>(in.p, total8, HW, op.in_c, m->se_scale, op.k == 2 ? 1.f : 0.f, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
             case OP_UP2: {
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
                 e->launch_begin("k_up2", "up", 0.0, total * 16.0 * 1.25);
-                k_up2<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W, out.p + op.out_coff, out.C);
+                k_up2<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W,
+                                                           op.aux >= 0 ? m->tens[op.aux].p : nullptr, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
@@ -1086,6 +1205,20 @@ int cls_forward(Engine* e, const float* in_nchw, int N, int H, int W, float* log
     go.logits = logits;
     go.probs = probs;
     return run_graph(e, m, in_nchw, nullptr, nullptr, zero3, one3, 1.f, 0, N, H, W, go);
+}
+
+// PP-OCRv4 detector: fp32 [N,3,H,W] (pre-processed) or uint8 [N,H,W,3] pages (flip / scale / mean / std fused into the stem as
+// dbnet_forward does) -> probability map fp32 [N,1,H,W]; H and W multiples of 32 (DetResizeForTest).
+int ppdet_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, const float* mean3, const float* std3, float scale, int flip, int N,
+                  int H, int W, float* prob_out) {
+    GraphNet* m = dynamic_cast<GraphNet*>(e->model.get());
+    if (!m || m->kind != 3) return set_err(e, DV_ERR_STATE, "handle was not created as a pp_det model");
+    if (N <= 0 || H <= 0 || W <= 0 || (H % 32) || (W % 32) || (!in_nchw && !in_u8) || !prob_out)
+        return set_err(e, DV_ERR_ARG, "ppdet_forward: bad arguments (H and W must be multiples of 32)");
+    const float one3[3] = {1.f, 1.f, 1.f}, zero3[3] = {0.f, 0.f, 0.f};
+    GraphOut go;
+    go.prob = prob_out;
+    return run_graph(e, m, in_nchw, in_u8, nullptr, in_u8 ? mean3 : zero3, in_u8 ? std3 : one3, in_u8 ? scale : 1.f, in_u8 ? flip : 0, N, H, W, go);
 }
 
 int rec_time_steps(Engine* e, int H, int W) {

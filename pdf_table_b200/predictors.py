@@ -470,6 +470,13 @@ class OcrDetectionTask(BaseInferTask):
             raise RuntimeError(f"model {model} not support")  # ocr_detection_task.py:58
         if state_dict is None:
             raise RuntimeError("OcrDetectionTask(predictor_type='b200') needs state_dict= (a DBModel state_dict or a path)")
+        # backbone="resnet18": the in-tree DBModel (db_net/dbnet.py:715); backbone="PPLCNetV3" (model="db_pp" only): the PP-OCRv4
+        # mobile detector the reference's db_pp back-end downloads as ONNX (PPLCNetV3-0.75 + RSE-FPN + DBHead, pp_det_graph.py)
+        if backbone not in ("resnet18", "PPLCNetV3") or (backbone == "PPLCNetV3" and model != "db_pp"):
+            raise RuntimeError(f"backbone {backbone} not support for model {model}")
+        if backbone == "PPLCNetV3" and kwargs.get("precision", "fp16") != "fp16":
+            raise RuntimeError("the PP-OCRv4 detector runs in fp16 operand precision only")
+        self.backbone = backbone
         self.thresh, self.unclip_ratio, self.max_candidates = thresh, unclip_ratio, max_candidates
         self.box_thresh = box_thresh if box_thresh is not None else (0.3 if model == "db" else 0.6)
         self.limit_side_len, self.limit_type, self.image_short_side = limit_side_len, limit_type, image_short_side
@@ -477,7 +484,12 @@ class OcrDetectionTask(BaseInferTask):
         super().__init__(task=task, model=model, **kwargs)
 
     def _construct_model(self, model):
-        self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd, precise=self.precision == "fp32x"), device=self.device)
+        if self.backbone == "PPLCNetV3":
+            from . import pp_det_graph
+
+            self.predictor = Engine("pp_det", pp_det_graph.pack_pp_det(self._sd), device=self.device)
+        else:
+            self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
 
     def _norm(self):

@@ -721,6 +721,76 @@ def pp_ocrv4_rec_state_dict(seed: int = 0, n_class: int = 97) -> "OrderedDict[st
     return sd
 
 
+# --------------------------------------------------------------------------- PP-OCRv4 mobile detector (PPLCNetV3-0.75 + RSE-FPN + DBHead)
+PP_DET_CONFIG = {  # PaddleOCR rec_lcnetv3.py NET_CONFIG_det: k, in_c, out_c, stride, use_se
+    "blocks2": [[3, 16, 32, 1, False]],
+    "blocks3": [[3, 32, 64, 2, False], [3, 64, 64, 1, False]],
+    "blocks4": [[3, 64, 128, 2, False], [3, 128, 128, 1, False]],
+    "blocks5": [[3, 128, 256, 2, False], [5, 256, 256, 1, False], [5, 256, 256, 1, False], [5, 256, 256, 1, False],
+                [5, 256, 256, 1, False]],
+    "blocks6": [[5, 256, 512, 2, True], [5, 512, 512, 1, True], [5, 512, 512, 1, False], [5, 512, 512, 1, False]],
+}
+PP_DET_SCALE, PP_DET_MV_C, PP_DET_FPN = 0.75, (16, 24, 56, 480), 96
+
+
+def pp_ocrv4_det_state_dict(seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Seeded weights of the deploy-form PP-OCRv4 mobile detector (keys: oracle/pp_det_ref.py)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 4141))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    ch = lambda c: pp_rec_ch(c, PP_DET_SCALE)  # noqa: E731
+
+    def lab(p):
+        sd[p + ".scale"] = rng.uniform(0.8, 1.25, 1).astype(np.float32)
+        sd[p + ".bias"] = (rng.standard_normal(1) * 0.05).astype(np.float32)
+
+    def rep(p, cin, cout, k, groups, stride):
+        sd[p + ".reparam_conv.weight"] = _conv(rng, cout, cin // groups, k, k)
+        sd[p + ".reparam_conv.bias"] = _b(rng, cout)
+        lab(p + ".lab")
+        if stride != 2:
+            lab(p + ".act.lab")
+
+    def se(p, c):
+        sd[p + ".conv1.weight"] = _conv(rng, c // 4, c, 1, 1)
+        sd[p + ".conv1.bias"] = _b(rng, c // 4)
+        sd[p + ".conv2.weight"] = _conv(rng, c, c // 4, 1, 1)
+        sd[p + ".conv2.bias"] = _b(rng, c)
+
+    sd["backbone.conv1.conv.weight"] = _conv(rng, 16, 3, 3, 3)
+    _bn(rng, sd, "backbone.conv1.bn", 16)
+    tap_in = []
+    for name, cfg in PP_DET_CONFIG.items():
+        for i, (k, cin, cout, s, use_se) in enumerate(cfg):
+            ci, co = ch(cin), ch(cout)
+            p = f"backbone.{name}.{i}"
+            rep(p + ".dw_conv", ci, ci, k, ci, s)
+            if use_se:
+                se(p + ".se", ci)
+            rep(p + ".pw_conv", ci, co, 1, 1, 1)
+        if name != "blocks2":
+            tap_in.append(co)
+    taps = [int(c * PP_DET_SCALE) for c in PP_DET_MV_C]
+    for i, (ci, co) in enumerate(zip(tap_in, taps)):
+        sd[f"backbone.layer_list.{i}.weight"] = _conv(rng, co, ci, 1, 1)
+        sd[f"backbone.layer_list.{i}.bias"] = _b(rng, co)
+    f = PP_DET_FPN
+    for i, c in enumerate(taps):
+        # linear stages (no activation follows): unit gain keeps the synthetic logits in a few units instead of saturating the sigmoid
+        sd[f"neck.ins_conv.{i}.in_conv.weight"] = _conv(rng, f, c, 1, 1, gain=0.5)
+        se(f"neck.ins_conv.{i}.se_block", f)
+        sd[f"neck.inp_conv.{i}.in_conv.weight"] = _conv(rng, f // 4, f, 3, 3, gain=0.25)
+        se(f"neck.inp_conv.{i}.se_block", f // 4)
+    p = "head.binarize"
+    sd[p + ".conv1.weight"] = _conv(rng, f // 4, f, 3, 3, gain=1.0)
+    _bn(rng, sd, p + ".conv_bn1", f // 4)
+    sd[p + ".conv2.weight"] = (rng.standard_normal((f // 4, f // 4, 2, 2)) * np.sqrt(1.0 / (f // 4))).astype(np.float32)
+    sd[p + ".conv2.bias"] = _b(rng, f // 4)
+    _bn(rng, sd, p + ".conv_bn2", f // 4)
+    sd[p + ".conv3.weight"] = (rng.standard_normal((f // 4, 1, 2, 2)) * np.sqrt(1.0 / (f // 4))).astype(np.float32)
+    sd[p + ".conv3.bias"] = _b(rng, 1)
+    return sd
+
+
 # --------------------------------------------------------------------------- PULC classifiers (PP-LCNet x1.0, cls/cls_pp_lcnet.py)
 def pplcnet_cls_state_dict(seed: int = 0, class_num: int = 4) -> "OrderedDict[str, np.ndarray]":
     """Seeded weights with the keys of the reference PPLCNet module (cls/cls_pp_lcnet.py:164-293, scale 1.0, class_expand 1280)."""

@@ -258,3 +258,26 @@ def test_pp_rec_graph_program_reproduces_the_oracle_on_cpu():
             assert tuple(heads["probs"].shape) == tuple(want.shape)
             assert float((heads["logits"] - want_logits).abs().max()) < tol  # logit std ~4.7
             assert float((heads["probs"] - want).abs().max()) < 1e-2
+
+
+def test_pp_det_graph_program_reproduces_the_oracle_on_cpu():
+    """The lowering of the PP-OCRv4 detector (pp_det_graph.py: stride-2 rep layers without activation, tap conv folded into the
+    neck's ins_conv, RSE shortcut SE with the slope-0.2 hardsigmoid folded into conv2, top-down sums, up-sampling into the
+    concatenation slices, padded head channels, transposed convs as GEMM + pixel shuffle) run op by op with the executor's
+    semantics equals the oracle of the published architecture up to the fp16 rounding of the packed weights / buffers."""
+    import torch
+
+    from oracle import graph_interp, pp_det_ref
+    from pdf_table_b200 import pp_det_graph, synth
+
+    sd = synth.pp_ocrv4_det_state_dict(0)
+    blob, meta = pp_det_graph.build_pp_det(sd)
+    assert int(blob["graph.meta"][5]) == 3
+    for h, w in ((96, 160), (64, 64)):
+        x = torch.from_numpy(np.random.default_rng(2).standard_normal((2, 3, h, w)).astype(np.float32))
+        want, fuse = pp_det_ref.pp_det_forward(sd, x, return_fuse=True)
+        for fp16_act, tol in ((False, 5e-3), (True, 8e-3)):
+            tens, heads = graph_interp.run_program(blob, x, fp16_activations=fp16_act)
+            assert tuple(heads["prob"].shape) == tuple(want.shape) == (2, 1, h, w)
+            assert float((tens[meta["fuse"]] - fuse).abs().max()) < 1e-2 * float(fuse.abs().max())
+            assert float((heads["prob"] - want).abs().max()) < tol
