@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the driver's measurement contract for the pdf_table hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cascade full|ocr]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cascade full|ocr] [--det ppocrv4|dbnet_r18]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 ONE JSON line on rank 0.  The headline (`metric`/`value`/`e2e`) is BASELINE.json's second quantity, pages/s through the
@@ -60,6 +60,7 @@ SWEEP_CROPS, SWEEP_H, SWEEP_W = 4096, 32, 320   # BASELINE configs[3]
 LORE_BATCH = 16                                 # BASELINE configs[2]
 PP_REC_CLASSES = 97                             # en dictionary of the PP-OCRv4 recogniser
 FULL = True
+DET = "ppocrv4"  # --det: ppocrv4 = PPLCNetV3-0.75 + RSE-FPN + DBHead (the PP-OCRv4 det graph); dbnet_r18 = the in-tree DBModel
 
 
 def measured_traffic(kernel: str, workload: str):
@@ -226,7 +227,10 @@ class Cascade:
         self.n_crops = PAGES_PER_GPU * CROPS_PER_PAGE
         self.n_tables = self.n_pages * TABLES_PER_PAGE if full else 0
         # ---- predictors (public API)
-        det_task = predictors.OcrDetectionTask(model="db_pp", state_dict=synth.dbnet_r18_state_dict(0), device=device)
+        if DET == "ppocrv4":
+            det_task = predictors.OcrDetectionTask(model="db_pp", backbone="PPLCNetV3", state_dict=synth.pp_ocrv4_det_state_dict(0), device=device)
+        else:
+            det_task = predictors.OcrDetectionTask(model="db_pp", state_dict=synth.dbnet_r18_state_dict(0), device=device)
         rec_task = predictors.OcrRecognitionTask(model="PP-OCRv4", state_dict=synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES), device=device,
                                                  vocab=[chr(33 + i) for i in range(PP_REC_CLASSES - 2)])
         lay_task = tsr_task = None
@@ -273,7 +277,8 @@ class Cascade:
 
     @property
     def stages(self):
-        s = ["det_preprocess_u8(fused)", "dbnet_r18_forward", "db_boxes(planted prob maps)",
+        s = ["det_preprocess_u8(fused)", "pp_ocrv4_det_forward(PPLCNetV3 + RSE-FPN + DBHead)" if DET == "ppocrv4" else "dbnet_r18_forward",
+             "db_boxes(planted prob maps)",
              "crop_quads_for_rec(homography + warp + PP resize_norm_img width rule)", "pp_rec_preprocess_u8(fused)",
              "pp_ocrv4_rec_forward(PPLCNetV3 + SVTR + CTC head, per padded-width group)", "softmax+argmax+max", "ctc_greedy_decode"]
         if self.full:
@@ -611,7 +616,7 @@ def cpu_reference_step(sample_pages: np.ndarray, sd, rec_sd, sample_maps):
     import cv2
     import math
 
-    from oracle import crop_ref, ctc_ref, db_post_ref, dbnet_ref, pp_rec_ref
+    from oracle import crop_ref, ctc_ref, db_post_ref, dbnet_ref, pp_det_ref, pp_rec_ref
 
     mean = np.array(MEAN, np.float32).reshape(1, 1, 3)
     std = np.array(STD, np.float32).reshape(1, 1, 3)
@@ -619,7 +624,10 @@ def cpu_reference_step(sample_pages: np.ndarray, sd, rec_sd, sample_maps):
         img = pg[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0)
         img = (img - mean) / std
         x = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))[None])
-        dbnet_ref.dbnet_r18_forward(sd, x)
+        if DET == "ppocrv4":
+            pp_det_ref.pp_det_forward(sd, x)
+        else:
+            dbnet_ref.dbnet_r18_forward(sd, x)
     for pg, m in zip(sample_pages, sample_maps):
         boxes = db_post_ref.db_postprocess(m[0], np.array([PAGE_H, PAGE_W, 1.0, 1.0]), (PAGE_H, PAGE_W, 3))
         for b in boxes[:CROPS_PER_PAGE]:  # OcrCommonUtils.crop_image per detected quad, one recogniser call per crop (ocr_system_task.py:300-313)
@@ -705,7 +713,7 @@ class CpuArm:
         from pdf_table_b200 import synth
 
         self.n_pages = n_pages
-        self.sd = {k: torch.from_numpy(v) for k, v in synth.dbnet_r18_state_dict(0).items()}
+        self.sd = {k: torch.from_numpy(v) for k, v in (synth.pp_ocrv4_det_state_dict(0) if DET == "ppocrv4" else synth.dbnet_r18_state_dict(0)).items()}
         self.rec_sd = {k: torch.from_numpy(v) for k, v in synth.pp_ocrv4_rec_state_dict(0, PP_REC_CLASSES).items()}
         self.pages = make_pages(0, n_pages)
         self.maps = make_prob_maps(0, n_pages)
@@ -784,7 +792,9 @@ def run_reference(args, rank: int):
 def workload_config():
     cfg = {
         "workload": "BASELINE configs[1]: DB detect + text-line recognise, batch=32 synthetic pages 960x960 per GPU",
-        "det_model": "DBNet-R18 (in-tree stand-in for the PP-OCRv4 det ONNX, SURVEY.md a2), seeded random weights",
+        "det_model": ("PP-OCRv4 det = PPLCNetV3-0.75 + RSE-FPN + DBHead (the published architecture the hub ONNX was exported from, SURVEY.md a2), "
+                      "seeded random weights" if DET == "ppocrv4" else
+                      "DBNet-R18 (the reference's in-tree model='db' network, --det dbnet_r18), seeded random weights"),
         "rec_model": f"PP-OCRv4 rec = PPLCNetV3-0.95 + SVTR neck + CTC head (the published architecture the hub ONNX was exported from, SURVEY.md "
                      f"a5; {PP_REC_CLASSES} classes), {CROPS_PER_PAGE} crops per page cut on the device from the db_boxes quads of that page "
                      "(crop_image + resize_norm_img: 48 high, each crop padded to its own width as the reference's one-crop-per-call flow does; "
@@ -816,9 +826,12 @@ def main():
     ap.add_argument("--no-blocks", action="store_true", help="skip the configs[3] / configs[2] blocks (profiling runs)")
     ap.add_argument("--cascade", default="full", choices=["ocr", "full"],
                     help="full = BASELINE configs[4] per GPU (the default line); ocr = configs[1] (DB detect + recognise only)")
+    ap.add_argument("--det", default="ppocrv4", choices=["ppocrv4", "dbnet_r18"],
+                    help="detector network of the cascade: the PP-OCRv4 det graph (default, BASELINE configs[1] / [4]) or the in-tree DBNet-R18")
     args = ap.parse_args()
-    global FULL
+    global FULL, DET
     FULL = args.cascade == "full"
+    DET = args.det
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -506,6 +506,68 @@ k_se_scale(const __half* __restrict__ in, int HW, int C, const float* __restrict
     }
 }
 
+// SE squeeze over a LARGE map (the detector's RSE layers pool 240 x 240 x 96 per page): partial channel sums of kSePoolRows
+// pixels per CTA, grid (chunks, N), summed in a fixed order by k_se_scale_p -- deterministic, and 300x the single-CTA loop's
+// 45 GB/s (profiles/r4g_layers_ppdet.txt: 13.7 of 20.1 ms per 32 pages before).
+constexpr int kSePoolRows = 512;
+constexpr int kSePoolMin = 2048;  // maps with fewer pixels keep the one-kernel squeeze
+__global__ void __launch_bounds__(256)
+k_se_pool(const __half* __restrict__ in, int HW, int C, float* __restrict__ partial) {
+    extern __shared__ float sm[];  // [slots][C]
+    const int cv = C >> 3, slots = 256 / cv;
+    const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    const int c8 = threadIdx.x % cv, slot = threadIdx.x / cv;
+    const int p0 = chunk * kSePoolRows, p1 = min(p0 + kSePoolRows, HW);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (slot < slots) {
+        const __half* base = in + (static_cast<long long>(n) * HW) * C + c8 * 8;
+        for (int p = p0 + slot; p < p1; p += slots) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * C));
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 v = __half22float2(h[i]);
+                acc[2 * i] += v.x;
+                acc[2 * i + 1] += v.y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm[slot * C + c8 * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < slots; ++k) s += sm[k * C + c];
+        partial[(static_cast<long long>(n) * nchunks + chunk) * C + c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_se_scale_p(const float* __restrict__ partial, int nchunks, int HW, int C, const float* __restrict__ w1, const float* __restrict__ b1,
+             const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ scale) {
+    extern __shared__ float sm[];  // avg[C] | hidden[C/4]
+    float* avg = sm;
+    float* hid = sm + C;
+    const int n = blockIdx.x, R = C >> 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nchunks; ++k) s += partial[(static_cast<long long>(n) * nchunks + k) * C + c];
+        avg[c] = s / static_cast<float>(HW);
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float s = b1[r];
+        for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], avg[c], s);
+        hid[r] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = b2[c];
+        for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
+        scale[n * C + c] = fminf(fmaxf(s * (1.f / 6.f) + 0.5f, 0.f), 1.f);  // F.hardsigmoid
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_se_apply(const __half* __restrict__ in, long long total8, int HW, int C, const float* __restrict__ scale, float shortcut,
            __half* __restrict__ out, int ldo) {
@@ -641,6 +703,7 @@ struct GraphNet : Model {
     std::vector<Tensor> tens;
     std::vector<void*> mem;
     float* se_scale = nullptr;
+    float* se_partial = nullptr;  // k_se_pool partial sums [N][chunks][C] (large maps only)
     float* head_raw = nullptr;
     double flops = 0;
     // plans of other input shapes (the recogniser alternates between a full pass and a tail pass, and between padded widths):
@@ -650,7 +713,7 @@ struct GraphNet : Model {
         std::vector<Tensor> tens;
         std::vector<void*> mem;
         std::vector<GOp> ops;
-        float *se_scale, *head_raw;
+        float *se_scale, *head_raw, *se_partial;
         double flops;
     };
     std::vector<Saved> cache;
@@ -664,7 +727,7 @@ struct GraphNet : Model {
     }
     void park() {
         if (N == 0) return;
-        cache.push_back(Saved{N, H, W, std::move(tens), std::move(mem), ops, se_scale, head_raw, flops});
+        cache.push_back(Saved{N, H, W, std::move(tens), std::move(mem), ops, se_scale, head_raw, se_partial, flops});
         mem.clear();
         tens.clear();
         N = H = W = 0;
@@ -682,7 +745,7 @@ struct GraphNet : Model {
                 tens = std::move(sv.tens);
                 mem = std::move(sv.mem);
                 ops = std::move(sv.ops);
-                se_scale = sv.se_scale, head_raw = sv.head_raw, flops = sv.flops;
+                se_scale = sv.se_scale, head_raw = sv.head_raw, se_partial = sv.se_partial, flops = sv.flops;
                 return true;
             }
         return false;
@@ -727,7 +790,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         DV_TRY(m->alloc(&p, t.elems() * sizeof(__half)));
         t.p = reinterpret_cast<__half*>(p);
     }
-    size_t max_head_rows = 0;
+    size_t max_head_rows = 0, max_se_partial = 0;
     int max_se_c = 0;
     for (GOp& op : m->ops) {
         int rc = 0;
@@ -769,6 +832,12 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
                 op.f2 = wf32(e, op.w, "s2w", static_cast<size_t>(op.in_c) * op.in_c / 4, &rc);
                 op.f3 = wf32(e, op.w, "s2b", op.in_c, &rc);
                 if (op.in_c > max_se_c) max_se_c = op.in_c;
+                if (in.C != op.in_c || op.in_coff != 0) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: SE needs a dense input");
+                if (in.H * in.W >= kSePoolMin) {
+                    const size_t need = static_cast<size_t>(N) * ((in.H * in.W + kSePoolRows - 1) / kSePoolRows) * op.in_c;
+                    if (need > max_se_partial) max_se_partial = need;
+                    if (op.in_c > 2048) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: SE over %d channels", op.in_c);
+                }
                 break;
             case OP_HEAD:
                 if (static_cast<size_t>(N) * in.H * in.W > max_head_rows) max_head_rows = static_cast<size_t>(N) * in.H * in.W;
@@ -797,6 +866,11 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         void* p = nullptr;
         DV_TRY(m->alloc(&p, static_cast<size_t>(N) * max_se_c * 4));
         m->se_scale = reinterpret_cast<float*>(p);
+    }
+    if (max_se_partial) {
+        void* p = nullptr;
+        DV_TRY(m->alloc(&p, max_se_partial * 4));
+        m->se_partial = reinterpret_cast<float*>(p);
     }
     {
         void* p = nullptr;
@@ -1061,9 +1135,20 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
             }
             case OP_SE: {
                 const int HW = in.H * in.W;
-                e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
-                k_se_scale<<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(in.p, HW, op.in_c, op.f0, op.f1, op.f2, op.f3, m->se_scale);
-                e->launch_end();
+                if (HW >= kSePoolMin) {
+                    const int nchunks = (HW + kSePoolRows - 1) / kSePoolRows, cv = op.in_c / 8;
+                    e->launch_begin("k_se_pool", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
+                    k_se_pool<<<dim3(nchunks, N), 256, static_cast<size_t>(256 / cv) * op.in_c * sizeof(float), s>>>(in.p, HW, op.in_c, m->se_partial);
+                    e->launch_end();
+                    e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * nchunks * op.in_c * 4.0);
+                    k_se_scale_p<<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(m->se_partial, nchunks, HW, op.in_c, op.f0, op.f1, op.f2, op.f3,
+                                                                                        m->se_scale);
+                    e->launch_end();
+                } else {
+                    e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
+                    k_se_scale<<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(in.p, HW, op.in_c, op.f0, op.f1, op.f2, op.f3, m->se_scale);
+                    e->launch_end();
+                }
                 const long long total8 = static_cast<long long>(N) * HW * (op.in_c / 8);
                 e->launch_begin("k_se_apply", "se", 0.0, total8 * 32.0);
                 k_se_apply<<<grid_for(total8, 256), 256, 0, s>>>(in.p, total8, HW, op.in_c, m->se_scale, op.k == 2 ? 1.f : 0.f, out.p + op.out_coff, out.C);

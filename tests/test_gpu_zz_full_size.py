@@ -137,6 +137,24 @@ def test_recogniser_vs_oracle_on_a_96_crop_pass():
         rec.close()
 
 
+def test_pp_ocrv4_det_vs_oracle_on_a_full_960_page():
+    """One 960 x 960 page (BASELINE configs[1] page size) through the fp32 oracle of the PP-OCRv4 detector."""
+    from oracle import pp_det_ref
+    from pdf_table_b200 import pp_det_graph
+
+    sd = synth.pp_ocrv4_det_state_dict(0)
+    page = synth.synthetic_page(41, 960, 960)
+    mean, std = np.array(MEAN, np.float32).reshape(1, 1, 3), np.array(STD, np.float32).reshape(1, 1, 3)
+    x = ((page[:, :, ::-1].astype("float32") * np.float32(1.0 / 255.0) - mean) / std).transpose(2, 0, 1)[None]
+    want = pp_det_ref.pp_det_forward(sd, torch.from_numpy(np.ascontiguousarray(x))).numpy()
+    det = Engine("pp_det", pp_det_graph.pack_pp_det(sd))
+    got = det.dbnet_forward_u8(torch.from_numpy(page[None]).cuda(), MEAN, STD, 1.0 / 255.0, True).cpu().numpy()
+    err = float(np.abs(got - want).max())
+    print(f"960x960 page, PP-OCRv4 det: max|dprob| = {err:.3e}")
+    assert err <= 2e-2  # fp16 operands; maximum over 921 600 outputs
+    det.close()
+
+
 def test_lore_vs_oracle_on_a_full_1024_image():
     """One 1024 x 1024 table image (BASELINE configs[2] crop size) through the fp32 oracle of the Lore detector (~10 s on the
     host): the four decoded head maps within the relative tolerance of the small-size parity tests, and the decode of the engine's

@@ -1,5 +1,5 @@
 """Per-layer device times (CUDA events around every launch, dv_profile_*) of one forward of a model.
-usage: python tools/layer_profile.py {dbnet|rec|lore} [batch]   -- tuning aid, not the bench."""
+usage: python tools/layer_profile.py {dbnet|rec|ppdet|lore} [batch]   -- tuning aid, not the bench."""
 import collections
 import sys
 
@@ -22,6 +22,14 @@ elif model == "rec":
     eng = Engine("convnext_vit", weights.pack_convnext_vit(synth.convnext_vit_state_dict(0)))
     x = torch.rand(3 * n, 3, 32, 300, device="cuda")
     run = lambda: eng.convnextvit_forward(x)
+elif model == "ppdet":
+    from pdf_table_b200 import pp_det_graph
+
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    eng = Engine("pp_det", pp_det_graph.pack_pp_det(synth.pp_ocrv4_det_state_dict(0)))
+    x = torch.randint(0, 255, (n, 960, 960, 3), dtype=torch.uint8, device="cuda")
+    out = torch.empty(n, 1, 960, 960, device="cuda")
+    run = lambda: eng.dbnet_forward_u8(x, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), 1.0 / 255.0, True, out=out)
 else:
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     eng = Engine("lore_dla34", weights.pack_lore_dla34(synth.lore_dla34_state_dict(0)))
