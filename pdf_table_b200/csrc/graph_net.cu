@@ -510,7 +510,7 @@ k_se_scale(const __half* __restrict__ in, int HW, int C, const float* __restrict
 // pixels per CTA, grid (chunks, N), summed in a fixed order by k_se_scale_p -- deterministic, and 300x the single-CTA loop's
 // 45 GB/s (profiles/r4g_layers_ppdet.txt: 13.7 of 20.1 ms per 32 pages before).
 constexpr int kSePoolRows = 512;
-constexpr int kSePoolMin = 1024;  // maps with fewer pixels keep the one-kernel squeeze
+constexpr int kSePoolMin = 256;  // maps with fewer pixels keep the one-kernel squeeze
 __global__ void __launch_bounds__(256)
 k_se_pool(const __half* __restrict__ in, int HW, int C, float* __restrict__ partial) {
     extern __shared__ float sm[];  // [slots][C]

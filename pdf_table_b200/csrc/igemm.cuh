@@ -335,6 +335,11 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         int m_tile, n_tile;
         float best_v = -INFINITY;
         int best_i = 0;
+        // TMA-store epilogue (fp16 NHWC output): this warp's two 2 KB staging tiles, used alternately
+        const bool tma_st = !OUT_F32 && !ARGMAX && p.tma_store != 0;
+        const uint32_t stg_base = smem_base + static_cast<uint32_t>(p.stg_off) + static_cast<uint32_t>(warp - 2) * 4096u;
+        uint32_t n_st = 0;
+        if (tma_st && lane == 0) ptx::prefetch_tmap(&p.tmD);
         while (it.next(p, m_tile, n_tile)) {
             // ---- which output pixel does this thread own?
             int img, y, x;
@@ -362,6 +367,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             if (res_mode == RES_UP2)
                 res_pix = (static_cast<long long>(img) * (Ho >> 1) + (y >> 1)) * (Wo >> 1) + (x >> 1);
             if (p.res_mod > 0) res_pix = pix % p.res_mod;  // broadcast rows (position embeddings)
+            if (tma_st && !valid) res_pix = 0;  // rows outside the output still run the (warp-collective) store path; TMA clips them
             if constexpr (ARGMAX) {
                 if (n_tile == 0) {
                     best_v = -INFINITY;
@@ -391,7 +397,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                 c += kStep;
                 have = c < BLOCK_N && n_tile * BLOCK_N + c < Cout;
                 if (have) ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c), v);
-                if (!valid) continue;
+                if (!valid && !tma_st) continue;
                 const int ncol = min(32, Cout - col0);
                 if (bias_smem) {
                     const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
@@ -532,6 +538,35 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
                     }
+                    if (tma_st) {
+                        // 32 rows x 32 columns of this warp -> shared memory (64-byte rows, 16-byte piece j of row l at
+                        // j ^ ((l >> 1) & 3) = SWIZZLE_64B: conflict-free) -> one cp.async.bulk.tensor store; rows / columns
+                        // outside the tensor are clipped by the TMA unit
+                        const uint32_t sbuf = stg_base + (n_st & 1u) * 2048u;
+                        if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last read this buffer (two stores ago) is done with it
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t addr = sbuf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(j) ^ ((static_cast<uint32_t>(lane) >> 1) & 3u)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[j].x), "r"(o[j].y), "r"(o[j].z), "r"(o[j].w)
+                                         : "memory");
+                        }
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (mode == A_FLAT) {
+                                ptx::tma_store_2d(&p.tmD, sbuf, col0, m_tile * 128 + q * 32);
+                            } else {
+                                const int r0 = q * 32, ly0 = r0 / TW;
+                                const int t = m_tile - img * tiles_per_img;
+                                const int ty = t / tiles_x, tx = t - ty * tiles_x;
+                                ptx::tma_store_4d(&p.tmD, sbuf, col0, tx * TW + (r0 - ly0 * TW), ty * TH + ly0, img);
+                            }
+                            ptx::bulk_commit();
+                        }
+                        ++n_st;
+                        continue;
+                    }
                     const int split_off = p.split_off;
                     if (split_off > 0) {  // residual halves of the split-fp16 representation (any store pattern)
 #pragma unroll
@@ -590,6 +625,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
         }
     }
 
+    if (warp >= 2 && lane == 0 && p.tma_store != 0) ptx::bulk_wait_read<0>();  // shared memory must outlive the last tile stores
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -98,27 +98,54 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     p.BLOCK_N = block_n;
     p.n_tiles = (cs.Cout + block_n - 1) / block_n;
     const int row_bytes = 2 * cs.BK;
+    // TMA-store epilogue: plain fp16 NHWC outputs (any A mode).  Not for fp32 / replicated / pixel-shuffled / split stores, the
+    // arg-max epilogue or device-side row counts (the store would also write the rows past the count).
+    static const bool tma_store_env = !(getenv("DV_TMA_STORE") && atoi(getenv("DV_TMA_STORE")) == 0);
+    const bool tma_store = tma_store_env && !es.out_f32 && es.out_mode == OUT_NHWC && es.split_off == 0 && es.arg_out == nullptr &&
+                           es.m_dyn == nullptr && cs.Cout >= 32 && es.out != nullptr;
+    const size_t stg_bytes = tma_store ? 8 * 2 * 2048 : 0;
+    const size_t ring_budget = 206 * 1024 - stg_bytes;
+    size_t ring_bytes = 0;
     if (p.mode == A_HALO) {
         // shared memory: halo-patch ring (18 x 16 pixels x BK channels each) + a ring of per-tap weight tiles
         const size_t halo_bytes = static_cast<size_t>(18) * 16 * row_bytes, b_bytes = static_cast<size_t>(block_n) * row_bytes;
         int hs = p.ncb > 1 ? 3 : 2;
-        int stages = static_cast<int>((206 * 1024 - hs * halo_bytes) / b_bytes);
+        int stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
         if (stages < 3 && hs > 2) {
             hs = 2;
-            stages = static_cast<int>((206 * 1024 - hs * halo_bytes) / b_bytes);
+            stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
         }
         if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
         p.halo_stages = hs;
         p.num_stages = stages;
-        plan->smem = hs * halo_bytes + stages * b_bytes + 1024;
+        ring_bytes = hs * halo_bytes + stages * b_bytes;
     } else {
         const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
-        int stages = static_cast<int>((206 * 1024) / stage_bytes);
+        int stages = static_cast<int>(ring_budget / stage_bytes);
         if (stages > kMaxStages) stages = kMaxStages;
         if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: stage too large", name);
         p.num_stages = stages;
-        plan->smem = stages * stage_bytes + 1024;
+        ring_bytes = stages * stage_bytes;
+    }
+    p.tma_store = tma_store ? 1 : 0;
+    p.stg_off = static_cast<int>((ring_bytes + 1023) / 1024 * 1024);
+    plan->smem = p.stg_off + stg_bytes + 1024;
+    if (tma_store) {
+        const uint64_t ld_bytes = static_cast<uint64_t>(es.out_ld) * 2;
+        const __half* obase = reinterpret_cast<const __half*>(es.out) + es.out_coff;
+        if (p.mode == A_FLAT) {
+            uint64_t dims[2] = {static_cast<uint64_t>(cs.Cout), static_cast<uint64_t>(p.M)}, str[1] = {ld_bytes};
+            uint32_t box[2] = {32, 32};
+            DV_TRY(encode_map(e, &p.tmD, obase, 2, dims, str, box, 64, name));
+        } else {
+            p.st_bw = p.TW >= 32 ? 32 : p.TW;
+            if (32 % p.st_bw) return set_err(e, DV_ERR_UNSUPPORTED, "%s: tile width %d does not divide a warp's 32 rows", name, p.TW);
+            uint64_t dims[4] = {static_cast<uint64_t>(cs.Cout), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho), static_cast<uint64_t>(p.Nimg)};
+            uint64_t str[3] = {ld_bytes, ld_bytes * p.Wo, ld_bytes * p.Wo * p.Ho};
+            uint32_t box[4] = {32, static_cast<uint32_t>(p.st_bw), static_cast<uint32_t>(32 / p.st_bw), 1};
+            DV_TRY(encode_map(e, &p.tmD, obase, 4, dims, str, box, 64, name));
+        }
     }
     p.bias = cs.bias;
     p.res = es.res;

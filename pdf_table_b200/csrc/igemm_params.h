@@ -22,6 +22,12 @@ enum OutMode : int { OUT_NHWC = 0, OUT_REPL = 1, OUT_SHUF2 = 2 };
 struct IGemmParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmD;       // tma_store: the fp16 NHWC output (slice) as {Cout, M} (A_FLAT) or {Cout, Wo, Ho, N}, box = one epilogue
+                           // warp's 32 rows x 32 columns, SWIZZLE_64B
+    int tma_store;         // 1: the epilogue stages its 32 x 32 fp16 tiles in shared memory and stores them with
+                           // cp.async.bulk.tensor (full-line writes; per-thread row stores cost 32 L1 wavefronts per instruction)
+    int stg_off;           // byte offset of the staging buffers (8 warps x 2 x 2 KB) from the aligned shared-memory base
+    int st_bw;             // PATCH modes: the store box covers st_bw columns x 32 / st_bw rows of the tile's pixel patch
     const int4* kb_delta;  // [num_kb] per-k-block coordinate deltas (see producer)
     int mode;
     int num_kb;
