@@ -60,6 +60,7 @@ SWEEP_CROPS, SWEEP_H, SWEEP_W = 4096, 32, 320   # BASELINE configs[3]
 LORE_BATCH = 16                                 # BASELINE configs[2]
 PP_REC_CLASSES = 97                             # en dictionary of the PP-OCRv4 recogniser
 FULL = True
+TWO_STREAMS = os.environ.get("DV_BENCH_STREAMS", "2") == "2"  # the table-structure branch on its own stream, as OcrSystemTask.predict_pages runs it (1: one stream)
 DET = "ppocrv4"  # --det: ppocrv4 = PPLCNetV3-0.75 + RSE-FPN + DBHead (the PP-OCRv4 det graph); dbnet_r18 = the in-tree DBModel
 
 
@@ -248,6 +249,7 @@ class Cascade:
         self.layout = lay_task.predictor if full else None
         self.lore = tsr_task.predictor if full else None
         self.lore_proc = tsr_task.processor if full else None
+        self.tsr_post = tsr_task.post if full else None
         self._tasks = [t for t in (det_task, rec_task, lay_task, tsr_task) if t is not None]
         # ---- inputs: host pages live in pinned memory and reach the API as a numpy array
         self.pages_pinned = torch.from_numpy(make_pages(rank, self.n_pages)).pin_memory()
@@ -260,6 +262,8 @@ class Cascade:
                         torch.empty((self.n_crops, 3, 3), dtype=torch.float64, device=dev))
         self.prob_map = torch.empty((self.n_pages, 1, PAGE_H, PAGE_W), dtype=torch.float32, device=dev)
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # L2 flush buffer (> 126 MB)
+        self._side = torch.cuda.Stream(device=dev)
+        self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
         self.api_counts = {}
         if full:
             from pdf_table_b200 import predictors as P
@@ -295,6 +299,16 @@ class Cascade:
     # ---- device-resident leg (C-ABI level, inputs in HBM)
     def step_device(self):
         rec = {}
+        if self.full and TWO_STREAMS:
+            # the table-structure branch depends on the resident pages only: it runs on a second stream beside layout -> detect
+            # -> recognise, so that the latency-bound kernels of one branch (contour tracing, crop warps, small attention) share the
+            # SMs with the other's
+            main = torch.cuda.current_stream()
+            self._fork.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._fork)
+                self._tables_branch(rec)
+                self._join.record(self._side)
         if self.full:
             lay_in = self.post.resize_pages_u8(self.pages_dev, 608, 800)
             scores, dfl = self.layout.picodet_forward_u8(lay_in, flip=True)
@@ -307,17 +321,22 @@ class Cascade:
                                                                 out=self.rec_crops, ws=self.crop_ws, width_rule=1)
         r_ids, r_len, _ = predictors.pp_rec_launch_groups(self.rec, self.post, crops, widths, sizes)
         rec.update(boxes=boxes[:, :64].contiguous(), box_counts=counts, ids=r_ids, id_lens=r_len)
-        if self.full:
-            tables = self.post.crop_tables_for_tsr(self.pages_dev, self.table_rects, self.table_minv, 1024, 1024)
-            self.lore.lore_detect_forward_u8(tables, out=self.lore_maps)
-            dec = self.post.lore_decode(self.lore_maps, None, None, None, self.lore_inv)
-            feat, offsets = self.lore.lore_cell_features(dec, max_rows=self.n_tables * 1024)
-            logi = self.lore_proc.lore_process_forward(feat, offsets)[1]
-            idx = offsets[:-1].long()[:, None] + torch.arange(256, device=logi.device)[None, :]
-            rec.update(cells=dec["polygons"][:, :256].contiguous(), cell_counts=dec["counts"],
-                       cell_logi=logi[idx.clamp_(max=int(logi.shape[0]) - 1)])
+        if self.full and TWO_STREAMS:
+            torch.cuda.current_stream().wait_event(self._join)
+        elif self.full:
+            self._tables_branch(rec)
         self.record = rec
         return rec
+
+    def _tables_branch(self, rec):
+        tables = self.tsr_post.crop_tables_for_tsr(self.pages_dev, self.table_rects, self.table_minv, 1024, 1024)
+        self.lore.lore_detect_forward_u8(tables, out=self.lore_maps)
+        dec = self.tsr_post.lore_decode(self.lore_maps, None, None, None, self.lore_inv)
+        feat, offsets = self.lore.lore_cell_features(dec, max_rows=self.n_tables * 1024)
+        logi = self.lore_proc.lore_process_forward(feat, offsets)[1]
+        idx = offsets[:-1].long()[:, None] + torch.arange(256, device=logi.device)[None, :]
+        rec.update(cells=dec["polygons"][:, :256].contiguous(), cell_counts=dec["counts"],
+                   cell_logi=logi[idx.clamp_(max=int(logi.shape[0]) - 1)])
 
     # ---- end-to-end leg (public API: numpy pages in, Python results out)
     def step_e2e(self):
@@ -803,6 +822,8 @@ def workload_config():
                          "detector's own map is texture noise; the network still runs and its map is discarded",
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
+        "streams": "2: the table-structure branch (crop + Lore + decode + processor) runs on its own CUDA stream beside layout -> detect -> recognise, "
+                   "in the device leg and in OcrSystemTask.predict_pages alike" if TWO_STREAMS else "1",
         "parallelism": "page-sharded replicas, one process per GPU; one all-gather of the packed decoded results per batch inside the timed step",
     }
     if FULL:
