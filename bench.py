@@ -823,7 +823,7 @@ def workload_config():
         "pages_per_gpu": PAGES_PER_GPU, "page": [PAGE_H, PAGE_W, 3],
         "l2": "flushed between timed steps (256 MiB write); activations per step exceed L2",
         "streams": "2: the table-structure branch (crop + Lore + decode + processor) runs on its own CUDA stream beside layout -> detect -> recognise, "
-                   "in the device leg and in OcrSystemTask.predict_pages alike" if TWO_STREAMS else "1",
+                   "in the device leg and in OcrSystemTask.predict_pages alike; the per-kernel table / roofline come from a one-stream pass of the same step" if TWO_STREAMS else "1",
         "parallelism": "page-sharded replicas, one process per GPU; one all-gather of the packed decoded results per batch inside the timed step",
     }
     if FULL:
@@ -850,7 +850,7 @@ def main():
     ap.add_argument("--det", default="ppocrv4", choices=["ppocrv4", "dbnet_r18"],
                     help="detector network of the cascade: the PP-OCRv4 det graph (default, BASELINE configs[1] / [4]) or the in-tree DBNet-R18")
     args = ap.parse_args()
-    global FULL, DET
+    global FULL, DET, TWO_STREAMS
     FULL = args.cascade == "full"
     DET = args.det
     rank = int(os.environ.get("RANK", "0"))
@@ -909,7 +909,9 @@ def main():
     h2d, d2h = wl.e2e_bytes()
     api_boxes = sum(len(p["det"]) for p in wl.api_out)
     api_cells = sum(len(t[1]["polygons"]) for p in wl.api_out for t in p["tables"])
-    # ---- per-kernel device times (CUDA events on the launching stream, same steps, separate pass)
+    # ---- per-kernel device times (CUDA events on the launching stream, same steps, separate pass).  The pass runs the step on ONE
+    # stream: with the table branch on its own stream the events around a launch would also span the other branch's kernels
+    two_streams, TWO_STREAMS = TWO_STREAMS, False
     for e in wl.engines:
         e.profile_begin()
     for _ in range(args.steps):
@@ -918,6 +920,7 @@ def main():
     recs = []
     for e in wl.engines:
         recs += e.profile_report()
+    TWO_STREAMS = two_streams
     dev_ms, e2e_ms = max_over_ranks(dist, [dev_ms, e2e_ms], dev)
 
     peaks, peak_src = load_peaks()
