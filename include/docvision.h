@@ -338,6 +338,21 @@ int dv_convnextvit_forward(dv_handle h, const float* chunks_nchw_f32, int n_crop
 int dv_convnextvit_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, int n_crops, int crop_w, float* logits_out,
                               int32_t* ids_out, float* max_out);
 int dv_convnextvit_labels(dv_handle h);
+
+/*
+ * CRNN text-line recogniser forward (model kind "crnn").
+ * Replaces OcrRecognitionTask._run_model for model="CRNN" (ocr_recognition_task.py:81-116) = OCRRecognition.forward
+ * (ocr_recognition/modeling_ocr_recognition.py:137-149) -> CRNN.forward (crnn/modeling_crnn.py:90-113: RGB -> gray, seven
+ * convs + BatchNorm + ReLU with max-pools, the (2,1) row-folding conv, two bidirectional LSTMs + Linear, 512 -> L classifier),
+ * fused with the arg-max of OCRRecognitionPostProcessor (ocr_recognition/processor_ocr_recognition.py:147-151).
+ *   in_nchw_f32 : [n, 3, 32, width] fp32 in [0,1] (the output of OCRRecognitionPreprocessor, :73-115; width % 4 == 0)
+ *   logits_out  : [n, width / 4, L] fp32 or NULL (parity dump; L = dv_crnn_labels)
+ *   ids_out     : [n, width / 4] int32 per-step arg-max (torch.argmax: first maximum); collapse with dv_ctc_collapse(blank 0)
+ *   max_out     : [n, width / 4] fp32 maximum logit or NULL
+ */
+int dv_crnn_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* logits_out, int32_t* ids_out,
+                    float* max_out);
+int dv_crnn_labels(dv_handle h);
 /* crops per internal pass (default 96): sizes the activation workspace so the widest tensor stays near L2 */
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops);
 /*

@@ -143,6 +143,8 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
         if (e->kind == "post") {
         } else if (e->kind == "dbnet_r18") {
             rc = dbnet_create(e);
+        } else if (e->kind == "crnn") {
+            rc = crnn_create(e);
         } else if (e->kind == "convnext_vit") {
             rc = cnv_create(e);
         } else if (e->kind == "picodet" || e->kind == "pp_rec" || e->kind == "pplcnet_cls" || e->kind == "pp_det") {
@@ -234,6 +236,7 @@ double dv_model_flops(dv_handle h) {
     if (!h) return 0.0;
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
+    if (h->kind == "crnn") return crnn_flops(h);
     if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_flops(h);
     if (h->kind == "picodet" || h->kind == "pp_rec" || h->kind == "pp_det") return graph_flops(h);
     return 0.0;
@@ -482,6 +485,16 @@ int dv_convnextvit_forward_u8(dv_handle h, const uint8_t* crops_hwc_u8, int n_cr
 }
 
 int dv_convnextvit_labels(dv_handle h) { return h ? cnv_labels(h) : 0; }
+
+int dv_crnn_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* logits_out, int32_t* ids_out,
+                    float* max_out) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    if (n > 0 && (!in_nchw_f32 || !ids_out)) return set_err(h, DV_ERR_ARG, "dv_crnn_forward: null input / output");
+    return crnn_forward(h, in_nchw_f32, n, height, width, logits_out, ids_out, max_out);
+}
+
+int dv_crnn_labels(dv_handle h) { return h ? crnn_labels(h) : 0; }
 
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops) {
     if (!h) return DV_ERR_ARG;

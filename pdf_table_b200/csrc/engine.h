@@ -260,6 +260,12 @@ int cnv_set_pass_crops(Engine* e, int crops);
 int cnv_labels(Engine* e);
 double cnv_flops(Engine* e);
 
+// crnn.cu
+int crnn_create(Engine* e);
+int crnn_forward(Engine* e, const float* in, int N, int H, int W, float* logits, int32_t* ids, float* maxv);
+int crnn_labels(Engine* e);
+double crnn_flops(Engine* e);
+
 // db_post.cu
 int db_boxes(Engine* e, const float* prob, int N, int H, int W, const double* src_hw_host, float thresh, double box_thresh,
              double unclip_ratio, int max_candidates, float* boxes_out, int32_t* counts_out, int32_t* overflow_host, int variant = 0);

@@ -180,6 +180,26 @@ class Engine:
               "dv_convnextvit_forward_u8")
         return (ids, logits) if return_logits else ids
 
+    def crnn_forward(self, x: torch.Tensor, return_logits: bool = False, return_max: bool = False):
+        """CRNN (model kind "crnn"): fp32 [n,3,32,W] (cuda, in [0,1], W % 4 == 0) -> per-step arg-max ids int32 [n, W/4]
+        (+ logits fp32 [n, W/4, L], + max logit [n, W/4])."""
+        x = _require_cuda(x, torch.float32, "x")
+        n, c, hh, ww = x.shape
+        if c != 3 or hh != 32 or ww % 4:
+            raise ValueError("x must be [n,3,32,W] with W % 4 == 0")
+        t = ww // 4
+        labels = int(self._lib.dv_crnn_labels(self._h))
+        ids = torch.empty((n, t), dtype=torch.int32, device=x.device)
+        logits = torch.empty((n, t, labels), dtype=torch.float32, device=x.device) if return_logits else None
+        mx = torch.empty((n, t), dtype=torch.float32, device=x.device) if return_max else None
+        check(self._lib.dv_crnn_forward(self._h, _ptr(x), n, hh, ww, _ptr(logits), _ptr(ids), _ptr(mx)), self._h, "dv_crnn_forward")
+        out = (ids,)
+        if return_logits:
+            out += (logits,)
+        if return_max:
+            out += (mx,)
+        return out if len(out) > 1 else ids
+
     def set_pass_crops(self, crops: int):
         check(self._lib.dv_convnextvit_set_pass_crops(self._h, int(crops)), self._h, "dv_convnextvit_set_pass_crops")
 

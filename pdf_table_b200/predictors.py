@@ -606,16 +606,25 @@ def _batch_of(members) -> torch.Tensor:
 
 
 class OcrRecognitionTask(BaseInferTask):
-    """OcrRecognitionTask (ocr_pdf/ocr_recognition_task.py:28-136) for model="ConvNextViT".
+    """OcrRecognitionTask (ocr_pdf/ocr_recognition_task.py:28-136) for model="ConvNextViT", "PP-OCRv4" and "CRNN".
     Returns list[str] like the reference (:118-136).  `vocab` is the character list of the checkpoint's vocab file
-    (label ids start at 2 because do_chunking is set, ocr_recognition/processor_ocr_recognition.py:137-145)."""
+    (label ids start at 2 because do_chunking is set, ocr_recognition/processor_ocr_recognition.py:137-145).
+
+    model="CRNN" (crnn/modeling_crnn.py) follows the reference's configuration as written: OCRRecognitionConfig is built with
+    its defaults for every model_scope recogniser (ocr_recognition_task.py:33-35), i.e. do_chunking=True and width 804, so the
+    pre-processor hands the network three 32 x 300 chunks per crop and the task returns the FIRST chunk's string
+    (`predict['preds'][0]`, :124-128).  do_chunking=False (constructor kwarg) is the full-width mode the model was published
+    with: one 32 x 804 image per crop, label ids from 1."""
 
     SUPPORTS_FP32X = True
 
     def __init__(self, task: str = "ocr_recognition", model: str = "ConvNextViT", task_type: str = "general", state_dict=None,
-                 vocab: Optional[Sequence[str]] = None, **kwargs):
-        if model not in ("ConvNextViT", "PP-OCRv4"):
+                 vocab: Optional[Sequence[str]] = None, do_chunking: bool = True, **kwargs):
+        if model not in ("ConvNextViT", "PP-OCRv4", "CRNN"):
             raise RuntimeError(f"model {model} not support")
+        if model != "ConvNextViT" and kwargs.get("precision", "fp16") != "fp16" and model == "CRNN":
+            raise RuntimeError("the CRNN recogniser runs in fp16 operand precision only")
+        self.do_chunking = do_chunking if model == "CRNN" else True
         if state_dict is None:
             raise RuntimeError("OcrRecognitionTask(predictor_type='b200') needs state_dict= (the recogniser's state_dict or a path)")
         if model == "PP-OCRv4" and kwargs.get("precision", "fp16") != "fp16":
@@ -626,7 +635,8 @@ class OcrRecognitionTask(BaseInferTask):
             self.character = ["blank"] + list(vocab) + [" "] if vocab is not None else None
             self.label_mapping = None
         else:
-            self.label_mapping = {i + 2: ch for i, ch in enumerate(vocab)} if vocab is not None else None
+            first = 2 if self.do_chunking else 1  # load_vocab (processor_ocr_recognition.py:137-145)
+            self.label_mapping = {i + first: ch for i, ch in enumerate(vocab)} if vocab is not None else None
         super().__init__(task=task, model=model, **kwargs)
         self.post = Engine("post", device=self.device)
         if model == "PP-OCRv4":
@@ -639,6 +649,8 @@ class OcrRecognitionTask(BaseInferTask):
             from .pp_rec_graph import pack_pp_rec
 
             self.predictor = Engine("pp_rec", pack_pp_rec(self._sd), device=self.device)
+        elif model == "CRNN":
+            self.predictor = Engine("crnn", weights.pack_crnn(self._sd), device=self.device)
         else:
             self.predictor = Engine("convnext_vit", weights.pack_convnext_vit(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None
@@ -739,9 +751,31 @@ class OcrRecognitionTask(BaseInferTask):
             out += self._postprocess(r, **kwargs)
         return out
 
+    def _crnn_batch(self, crops: np.ndarray) -> np.ndarray:
+        """The rest of OCRRecognitionPreprocessor.__call__ (processor_ocr_recognition.py:57-61, 103-113) for the padded uint8
+        crops [n,32,w,3]: pad to 804, float / 255, three chunks at x0 = 0, 252, 504 (or the whole line), NCHW."""
+        n, _, w, _ = crops.shape
+        full = np.zeros((n, 32, 804, 3), np.uint8)
+        full[:, :, :w] = crops
+        x = full.astype(np.float32) / np.float32(255.0)
+        if self.do_chunking:
+            x = np.stack([x[:, :, (300 - 48) * i:(300 - 48) * i + 300] for i in range(3)], 1).reshape(n * 3, 32, 300, 3)
+        return np.ascontiguousarray(x.transpose(0, 3, 1, 2))
+
     def _run_model(self, inputs, **kwargs):
         dev = torch.device("cuda", self.device)
         crops = inputs["crops"]
+        if self.model == "CRNN":
+            x = self._crnn_batch(crops.numpy() if isinstance(crops, torch.Tensor) else crops)
+            ids = self.predictor.crnn_forward(_h2d(torch.from_numpy(x), dev))
+            if self.do_chunking:
+                ids = ids.view(-1, 3, ids.shape[1])[:, 0].contiguous()  # predict['preds'][0]: the first chunk of every crop
+            out, ln, _ = self.post.ctc_collapse(ids)
+            inputs["ids_dev"], inputs["len_dev"] = out, ln
+            inputs["ids"], inputs["len"] = _d2h_async(out), _d2h_async(ln)
+            inputs["event"] = torch.cuda.Event()
+            inputs["event"].record()
+            return inputs
         ids = self.predictor.convnextvit_forward_u8(_h2d(crops if isinstance(crops, torch.Tensor) else torch.from_numpy(crops), dev))
         out, ln, _ = self.post.ctc_collapse(ids)
         inputs["ids_dev"], inputs["len_dev"] = out, ln

@@ -791,6 +791,46 @@ def pp_ocrv4_det_state_dict(seed: int = 0) -> "OrderedDict[str, np.ndarray]":
     return sd
 
 
+# --------------------------------------------------------------------------- CRNN (crnn/modeling_crnn.py)
+CRNN_LABELS = 7644
+
+
+def crnn_state_dict(seed: int = 0, num_labels: int = CRNN_LABELS) -> "OrderedDict[str, np.ndarray]":
+    """Seeded weights with the keys / shapes of the reference CRNN module (crnn/modeling_crnn.py:36-88)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 6060))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+
+    def conv(p, cout, cin, kh, kw):
+        sd[p + ".weight"] = _conv(rng, cout, cin, kh, kw)
+        sd[p + ".bias"] = _b(rng, cout)
+
+    conv("conv0.0", 64, 1, 3, 3)
+    _bn(rng, sd, "conv0.1", 64)
+    conv("conv1.0", 128, 64, 3, 3)
+    _bn(rng, sd, "conv1.1", 128)
+    conv("conv2.0", 256, 128, 3, 3)
+    _bn(rng, sd, "conv2.1", 256)
+    conv("conv2.3", 256, 256, 3, 3)
+    _bn(rng, sd, "conv2.4", 256)
+    conv("conv3.0", 512, 256, 3, 3)
+    _bn(rng, sd, "conv3.1", 512)
+    conv("conv3.3", 512, 512, 3, 3)
+    _bn(rng, sd, "conv3.4", 512)
+    conv("conv4.0", 512, 512, 2, 1)
+    _bn(rng, sd, "conv4.1", 512)
+    for layer, (nin, nout) in enumerate(((512, 256), (256, 512))):
+        k = 1.0 / np.sqrt(256.0)  # nn.LSTM's own init range
+        for suffix in ("", "_reverse"):
+            sd[f"rnn.{layer}.rnn.weight_ih_l0{suffix}"] = rng.uniform(-k, k, (1024, nin)).astype(np.float32) * np.float32(np.sqrt(256.0 / nin) * 1.5)
+            sd[f"rnn.{layer}.rnn.weight_hh_l0{suffix}"] = rng.uniform(-k, k, (1024, 256)).astype(np.float32) * np.float32(1.5)
+            sd[f"rnn.{layer}.rnn.bias_ih_l0{suffix}"] = rng.uniform(-k, k, 1024).astype(np.float32)
+            sd[f"rnn.{layer}.rnn.bias_hh_l0{suffix}"] = rng.uniform(-k, k, 1024).astype(np.float32)
+        sd[f"rnn.{layer}.embedding.weight"] = _lin(rng, nout, 512, gain=2.0)
+        sd[f"rnn.{layer}.embedding.bias"] = _b(rng, nout)
+    sd["cls.weight"] = _lin(rng, num_labels, 512, gain=8.0)
+    return sd
+
+
 # --------------------------------------------------------------------------- PULC classifiers (PP-LCNet x1.0, cls/cls_pp_lcnet.py)
 def pplcnet_cls_state_dict(seed: int = 0, class_num: int = 4) -> "OrderedDict[str, np.ndarray]":
     """Seeded weights with the keys of the reference PPLCNet module (cls/cls_pp_lcnet.py:164-293, scale 1.0, class_expand 1280)."""

@@ -475,3 +475,34 @@ def pack_centernet_dla34(sd: Mapping[str, "np.ndarray"]) -> bytes:
         row += c
     put("heads.out", pack_conv(w1, b1))
     return write_blob(t)
+
+
+# --------------------------------------------------------------------------- CRNN (crnn/modeling_crnn.py)
+def pack_crnn(sd: Mapping[str, "np.ndarray"]) -> bytes:
+    """state_dict of the reference CRNN module (crnn/modeling_crnn.py:36-88) -> engine blob (model kind "crnn", csrc/crnn.cu).
+    BatchNorm folded into every conv; conv0's single gray input channel becomes channel 0 of an 8-channel pixel; conv4's (2,1)
+    kernel is packed tap-major (row 0, row 1); per LSTM layer the input projections of both directions are ONE matrix
+    [W_ih ; W_ih_reverse] with bias b_ih + b_hh, the recurrent matrices stay per direction (no bias); cls has no bias."""
+    t: Dict[str, np.ndarray] = {}
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    w0 = _np(sd["conv0.0.weight"]).astype(np.float32)
+    w0p = np.zeros((w0.shape[0], 8, 3, 3), np.float32)
+    w0p[:, :1] = w0
+    put("conv0", pack_conv(w0p, sd["conv0.0.bias"], _bn(sd, "conv0.1")))
+    for name, c, b in (("conv1", "conv1.0", "conv1.1"), ("conv2a", "conv2.0", "conv2.1"), ("conv2b", "conv2.3", "conv2.4"),
+                       ("conv3a", "conv3.0", "conv3.1"), ("conv3b", "conv3.3", "conv3.4"), ("conv4", "conv4.0", "conv4.1")):
+        put(name, pack_conv(sd[c + ".weight"], sd[c + ".bias"], _bn(sd, b)))
+    for layer in (0, 1):
+        p = f"rnn.{layer}.rnn."
+        wih = np.concatenate([_np(sd[p + "weight_ih_l0"]), _np(sd[p + "weight_ih_l0_reverse"])], 0).astype(np.float32)
+        bias = np.concatenate([_np(sd[p + "bias_ih_l0"]) + _np(sd[p + "bias_hh_l0"]),
+                               _np(sd[p + "bias_ih_l0_reverse"]) + _np(sd[p + "bias_hh_l0_reverse"])]).astype(np.float32)
+        put(f"rnn.{layer}.ih", pack_linear(wih, bias))
+        t[f"rnn.{layer}.hh.w"] = pack_linear(sd[p + "weight_hh_l0"])[0]
+        t[f"rnn.{layer}.hh_reverse.w"] = pack_linear(sd[p + "weight_hh_l0_reverse"])[0]
+        put(f"rnn.{layer}.emb", pack_linear(sd[f"rnn.{layer}.embedding.weight"], sd[f"rnn.{layer}.embedding.bias"]))
+    t["cls.w"] = pack_linear(sd["cls.weight"])[0]
+    return write_blob(t)

@@ -211,3 +211,22 @@ def test_packed_convnextvit_blob_computes_the_reference_function():
     k = "vitstr.vit.encoder.layer.0.attention.attention.query.weight"
     bad[k] = sd2[k] / np.float32(8.0)
     assert float((ref.convnextvit_forward(bad, chunks) - want).abs().max()) > 5 * err
+
+
+def test_crnn_oracle_matches_the_reference_module():
+    """oracle/crnn_ref.py (conv stack, hand-rolled bidirectional LSTMs, embeddings, classifier) against the logits the reference
+    CRNN module produced in the build container on the same seeded weights (oracle/gen_golden_crnn.py)."""
+    import torch
+
+    from oracle import crnn_ref
+    from oracle.gen_golden_crnn import LABELS, case_input
+    from pdf_table_b200 import synth, weights
+
+    sd = synth.crnn_state_dict(0, LABELS)
+    g = np.load(os.path.join(GOLDEN, "crnn_seed0.npz"))
+    for n, w in ((2, 300), (1, 640), (3, 64)):
+        got = crnn_ref.crnn_forward(sd, torch.from_numpy(case_input(n, w))).numpy()
+        want = g[f"logits_{n}x{w}"]
+        assert got.shape == want.shape == (n, w // 4, LABELS)
+        assert float(np.abs(got - want).max()) < 1e-5
+    assert len(weights.pack_crnn(sd)) > 0
