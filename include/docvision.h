@@ -431,6 +431,16 @@ int dv_crop_tables_for_tsr(dv_handle h, const uint8_t* pages_hwc_u8, int n_pages
 int dv_pp_rec_normalise(dv_handle h, const uint8_t* crops_hwc_u8, const int32_t* widths, int b, int height, int width,
                         float* out_nchw_f32);
 /*
+ * Cell / text matching of the table export: for every recognised text box the table cell it belongs to.
+ * Replaces the loop of OcrTableToHtmlTask.match_table_cell_and_text_cell over find_top1_mach_box
+ * (ocr_pdf/ocr_table_to_html_task.py:48-77, 196-207): the first cell (list order) that contains the text box
+ * (box_in_other_box with diff 2, pdf_table/table_common.py:138-160), else the cell with the smallest
+ * (1 - compute_iou_v2, distance) key, first occurrence on ties (table_common.py:435-441, 473-516).
+ *   text_boxes : device float64 [n_text, 4] = x1, y1, x2, y2 (OcrCell.to_bbox);  cell_boxes : device float64 [n_cells, 4] (Cell.to_bbox)
+ *   top1_out   : device int32 [n_text] cell index per text box.  float64 arithmetic in the reference's operation order: identical indices.
+ */
+int dv_match_cells(dv_handle h, const double* text_boxes, int n_text, const double* cell_boxes, int n_cells, int32_t* top1_out);
+/*
  * Collapse per-step arg-max ids: keep[t] = ids[t] != blank && (t == 0 || ids[t] != ids[t-1]).
  * Replaces the loop of OCRRecognitionPostProcessor.__call__ (processor_ocr_recognition.py:152-162) and, given
  * scores, the confidence of BaseRecLabelDecode.decode (ocr_rec_pp/rec_postprocess.py:126-161).

@@ -69,6 +69,7 @@ SIGNATURES = {
     "dv_convnextvit_labels": (C.c_int, [C.c_void_p]),
     "dv_crnn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dv_crnn_labels": (C.c_int, [C.c_void_p]),
+    "dv_match_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dv_convnextvit_set_pass_crops": (C.c_int, [C.c_void_p, C.c_int]),
     "dv_warp_perspective_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.c_void_p]),

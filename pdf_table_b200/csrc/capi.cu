@@ -496,6 +496,12 @@ int dv_crnn_forward(dv_handle h, const float* in_nchw_f32, int n, int height, in
 
 int dv_crnn_labels(dv_handle h) { return h ? crnn_labels(h) : 0; }
 
+int dv_match_cells(dv_handle h, const double* text_boxes, int n_text, const double* cell_boxes, int n_cells, int32_t* top1_out) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return match_cells(h, text_boxes, n_text, cell_boxes, n_cells, top1_out);
+}
+
 int dv_convnextvit_set_pass_crops(dv_handle h, int crops) {
     if (!h) return DV_ERR_ARG;
     return cnv_set_pass_crops(h, crops);

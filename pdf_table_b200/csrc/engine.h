@@ -317,6 +317,9 @@ int picodet_decode(Engine* e, const float* const* scores, const float* const* df
                    int in_w, const float* org_hw_host, const float* scale_host, float score_thr, double iou_thr, int nms_top_k,
                    int keep_top_k, int out_cap, double* out, int32_t* counts);
 
+// match.cu
+int match_cells(Engine* e, const double* text_boxes, int n_text, const double* cell_boxes, int n_cells, int32_t* top1_out);
+
 // ctc.cu
 int ctc_collapse(Engine* e, const int32_t* ids, const float* scores, int B, int T, int blank, int32_t* out_ids,
                  int32_t* out_len, float* out_conf);

@@ -365,6 +365,18 @@ class Engine:
               self._h, "dv_ctc_collapse")
         return out, ln, conf
 
+    def match_cells(self, text_boxes: torch.Tensor, cell_boxes: torch.Tensor) -> torch.Tensor:
+        """float64 [T,4] text boxes and [C,4] table cells (cuda; x1, y1, x2, y2) -> int32 [T]: the cell of every text box
+        (find_top1_mach_box of the reference's table export)."""
+        text_boxes = _require_cuda(text_boxes, torch.float64, "text_boxes")
+        cell_boxes = _require_cuda(cell_boxes, torch.float64, "cell_boxes")
+        if text_boxes.dim() != 2 or text_boxes.shape[1] != 4 or cell_boxes.dim() != 2 or cell_boxes.shape[1] != 4 or cell_boxes.shape[0] == 0:
+            raise ValueError("text_boxes [T,4], cell_boxes [C>0,4]")
+        out = torch.empty((text_boxes.shape[0],), dtype=torch.int32, device=text_boxes.device)
+        check(self._lib.dv_match_cells(self._h, _ptr(text_boxes), int(text_boxes.shape[0]), _ptr(cell_boxes), int(cell_boxes.shape[0]), _ptr(out)),
+              self._h, "dv_match_cells")
+        return out
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         """Named intermediate activation of the last forward as fp32 NCHW (parity debugging)."""
         dims = (C.c_int * 4)()

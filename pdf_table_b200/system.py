@@ -18,7 +18,7 @@ import torch
 
 from .predictors import _h2d, order_point, order_points_batch, sort_det_boxes
 
-__all__ = ["OcrSystemTask", "get_layout_by_type"]
+__all__ = ["OcrSystemTask", "get_layout_by_type", "match_table_cell_and_text_cell"]
 
 
 def get_layout_by_type(layout_result: List[Dict[str, Any]], label: str = "figure", score_threshold: float = 0.8) -> List[Dict[str, Any]]:
@@ -27,6 +27,25 @@ def get_layout_by_type(layout_result: List[Dict[str, Any]], label: str = "figure
     results = [item for item in layout_result if item["label"].lower() == label.lower() and item["score"] >= score_threshold]
     results.sort(key=lambda x: x["bbox"][1])
     return results
+
+
+def match_table_cell_and_text_cell(engine, table_cells, text_bboxs) -> Dict[int, List[int]]:
+    """The matching half of OcrTableToHtmlTask.match_table_cell_and_text_cell (ocr_pdf/ocr_table_to_html_task.py:178-207): every
+    text box goes to the table cell find_top1_mach_box picks (:48-77) -- on the device (dv_match_cells: one warp per text box,
+    float64 arithmetic in the reference's operation order, identical indices).  table_cells / text_bboxs: sequences of
+    [x1, y1, x2, y2] (Cell.to_bbox / OcrCell.to_bbox).  Returns the reference's ``matched`` dict {cell index: [text indices in
+    input order]} (insertion-ordered by first match, like the reference's loop); text merging and the HTML export stay the
+    reference's."""
+    matched: Dict[int, List[int]] = {}
+    if len(text_bboxs) == 0:
+        return matched
+    dev = torch.device("cuda", engine.device)
+    t = torch.as_tensor(np.asarray(text_bboxs, dtype=np.float64).reshape(-1, 4)).to(dev)
+    c = torch.as_tensor(np.asarray(table_cells, dtype=np.float64).reshape(-1, 4)).to(dev)
+    top1 = engine.match_cells(t, c).cpu().numpy()
+    for index, cell in enumerate(top1.tolist()):
+        matched.setdefault(int(cell), []).append(index)
+    return matched
 
 
 class OcrSystemTask:

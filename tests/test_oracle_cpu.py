@@ -230,3 +230,22 @@ def test_crnn_oracle_matches_the_reference_module():
         assert got.shape == want.shape == (n, w // 4, LABELS)
         assert float(np.abs(got - want).max()) < 1e-5
     assert len(weights.pack_crnn(sd)) > 0
+
+
+def test_cell_text_matching_oracle_equals_the_reference_functions():
+    """oracle/match_ref.py against the indices the reference's own find_top1_mach_box / box_in_other_box / distance /
+    compute_iou_v2 produced in the build container (their source executed as is: oracle/gen_golden_match.py)."""
+    from oracle import match_ref
+
+    g = np.load(os.path.join(GOLDEN, "match_seed0.npz"))
+    n = 0
+    for i in range(6):
+        got = match_ref.match(g[f"texts{i}"], g[f"cells{i}"])
+        assert got == g[f"top1_{i}"].tolist()
+        n += len(got)
+    assert n > 200
+    # known answers: containment beats IoU, the FIRST containing cell wins, ties go to the first cell
+    cells = [[0, 0, 100, 50], [0, 0, 100, 50], [100, 0, 200, 50]]
+    assert match_ref.match([[10, 10, 40, 30]], cells) == [0]
+    assert match_ref.match([[90, 10, 160, 30]], cells) == [2]
+    assert match_ref.match([[300, 300, 320, 310]], cells) == [2]
