@@ -221,6 +221,16 @@ int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t
  */
 int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
                             float* logic_out, float* stacked_out);
+/*
+ * The 2-D position embeddings of the wiz_2dpe configurations ("ptn", "wireless": lore/configuration_lore.py:72-116), added to the
+ * cell features before dv_lore_process_forward: feat += x_pe[d0] + y_pe[d1] + x_pe[d2] + y_pe[d5] with d = the integer position
+ * features of the decode (LoreProcessModel.forward, lore/lore_processor.py:486-490; called with dets=slct_dets_feat from
+ * LoreModel.forward, lore/modeling_lore.py:155-159).  In place on a "lore_processor" handle (its blob holds the two tables).
+ *   feat [max_rows][256] fp32 (device); dets_feat [n_images][K][8] int32, counts [n_images], offsets [n_images+1] (device):
+ *   outputs of dv_lore_decode / dv_lore_cell_features.
+ */
+int dv_lore_add_position_embeddings(dv_handle h, float* feat, int max_rows, const int32_t* dets_feat, const int32_t* counts,
+                                    const int32_t* offsets, int n_images, int K);
 
 /*
  * CenterNet table-structure detector (model kind "centernet_dla34"): DLA-34 + plain IDA-up + heads hm / v2c / c2v / reg.

@@ -409,6 +409,13 @@ int dv_lore_cell_features(dv_handle h, int n, int K, int max_rows, const int32_t
     return lore_cell_features(h, n, K, max_rows, counts, ax_idx, cr_idx, logi_feat, offsets_out, overflow_host);
 }
 
+int dv_lore_add_position_embeddings(dv_handle h, float* feat, int max_rows, const int32_t* dets_feat, const int32_t* counts,
+                                    const int32_t* offsets, int n_images, int K) {
+    if (!h) return DV_ERR_ARG;
+    DeviceGuard dev_guard(h->device);
+    return lore_add_position_embeddings(h, feat, max_rows, dets_feat, counts, offsets, n_images, K);
+}
+
 int dv_lore_process_forward(dv_handle h, const float* feat, int max_rows, const int32_t* n_rows_dev, const int32_t* offsets, int n_images,
                             float* logic_out, float* stacked_out) {
     if (!h) return DV_ERR_ARG;

@@ -294,6 +294,8 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
 int lore_cell_features(Engine* e, int N, int K, int cap, const int32_t* counts, const int32_t* ax_idx, const int32_t* cr_idx,
                        float* logi_feat, int32_t* offsets_out, int32_t* overflow_host);
 int lore_proc_create(Engine* e);
+int lore_add_position_embeddings(Engine* e, float* feat, int cap_rows, const int32_t* dets_feat, const int32_t* counts, const int32_t* offsets,
+                                 int n_img, int K);
 int lore_process_forward(Engine* e, const float* feat, int cap_rows, const int32_t* rows_dev, const int32_t* offsets, int n_img,
                          float* logic_out, float* stacked_out);
 

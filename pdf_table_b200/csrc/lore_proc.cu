@@ -349,6 +349,47 @@ int lore_proc_create(Engine* e) {
     return 0;
 }
 
+// 2-D position embeddings of the wiz_2dpe configurations (ptn, wireless; LoreProcessModel.forward, lore_processor.py:486-490):
+// feat[row] = feat[row] + x_pe[d0] + y_pe[d1] + x_pe[d2] + y_pe[d5] (fp32, the reference's left-to-right order), row =
+// offsets[n] + j for cell j of image n, d = dets_feat[n][j][0..7] (the integer position features of the decode), clamped to the
+// table of 256 positions.  In place; one thread per (row, 4 channels).
+__global__ void __launch_bounds__(256)
+k_add_pos_emb(float* __restrict__ feat, const int32_t* __restrict__ dets, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets,
+              int K, int cap, const float* __restrict__ xpe, const float* __restrict__ ype) {
+    const int n = blockIdx.y, j = blockIdx.x * 4 + (threadIdx.x >> 6), c4 = threadIdx.x & 63;
+    if (j >= counts[n]) return;
+    const int row = offsets[n] + j;
+    if (row >= cap) return;
+    const int32_t* d = dets + (static_cast<long long>(n) * K + j) * 8;
+    auto pos = [](int v) { return min(max(v, 0), 255); };
+    const float4 a = *reinterpret_cast<const float4*>(xpe + pos(d[0]) * kD + c4 * 4), b = *reinterpret_cast<const float4*>(ype + pos(d[1]) * kD + c4 * 4);
+    const float4 c = *reinterpret_cast<const float4*>(xpe + pos(d[2]) * kD + c4 * 4), e = *reinterpret_cast<const float4*>(ype + pos(d[5]) * kD + c4 * 4);
+    float4* fp = reinterpret_cast<float4*>(feat + static_cast<long long>(row) * kD + c4 * 4);
+    float4 f = *fp;
+    f.x = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(f.x, a.x), b.x), c.x), e.x);
+    f.y = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(f.y, a.y), b.y), c.y), e.y);
+    f.z = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(f.z, a.z), b.z), c.z), e.z);
+    f.w = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(f.w, a.w), b.w), c.w), e.w);
+    *fp = f;
+}
+
+int lore_add_position_embeddings(Engine* e, float* feat, int cap_rows, const int32_t* dets_feat, const int32_t* counts, const int32_t* offsets,
+                                 int n_img, int K) {
+    if (!dynamic_cast<LoreProc*>(e->model.get())) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_processor model");
+    if (!feat || !dets_feat || !counts || !offsets || cap_rows <= 0 || n_img <= 0 || K <= 0)
+        return set_err(e, DV_ERR_ARG, "lore_add_position_embeddings: bad arguments");
+    const BlobTensor* xp = e->find("x_pos");
+    const BlobTensor* yp = e->find("y_pos");
+    if (!xp || !yp || xp->dtype != 0 || yp->dtype != 0 || xp->nbytes < 256 * kD * 4 || yp->nbytes < 256 * kD * 4)
+        return set_err(e, DV_ERR_WEIGHTS, "lore_processor: missing x_pos / y_pos embedding tables [256,256]");
+    e->launch_begin("k_add_pos_emb", "pos_emb", 0.0, static_cast<double>(cap_rows) * kD * 4.0 * 6.0);
+    k_add_pos_emb<<<dim3((K + 3) / 4, n_img), 256, 0, e->stream>>>(feat, dets_feat, counts, offsets, K, cap_rows, reinterpret_cast<const float*>(xp->dptr),
+                                                                  reinterpret_cast<const float*>(yp->dptr));
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 // feat fp32 [cap_rows, 256] (device), rows_dev: device int = number of valid rows, offsets: device int32 [n_img + 1]
 // (per-image segments of the rows), logic_out / stacked_out fp32 [cap_rows, 4] (device).
 int lore_process_forward(Engine* e, const float* feat, int cap_rows, const int32_t* rows_dev, const int32_t* offsets, int n_img,

@@ -452,6 +452,18 @@ class Engine:
             raise DocVisionError(f"lore_cell_features: {ovf.value} cells exceed max_rows={max_rows}")
         return feat, offsets
 
+    def lore_add_position_embeddings(self, feat: torch.Tensor, dec: dict, offsets: torch.Tensor) -> torch.Tensor:
+        """wiz_2dpe configurations (ptn / wireless): adds x / y position embeddings of the decode's integer position features to
+        the packed cell features, in place (on the "lore_processor" handle)."""
+        feat = _require_cuda(feat, torch.float32, "feat")
+        offsets = _require_cuda(offsets, torch.int32, "offsets")
+        dets = _require_cuda(dec["dets_feat"], torch.int32, "dets_feat")
+        counts = _require_cuda(dec["counts"], torch.int32, "counts")
+        n, k = int(dets.shape[0]), int(dets.shape[1])
+        check(self._lib.dv_lore_add_position_embeddings(self._h, _ptr(feat), int(feat.shape[0]), _ptr(dets), _ptr(counts), _ptr(offsets), n, k),
+              self._h, "dv_lore_add_position_embeddings")
+        return feat
+
     def lore_process_forward(self, feat: torch.Tensor, offsets: torch.Tensor):
         """feat fp32 [max_rows,256], offsets int32 [N+1] (device) -> (logic [max_rows,4], stacked [max_rows,4]) fp32."""
         feat = _require_cuda(feat, torch.float32, "feat")

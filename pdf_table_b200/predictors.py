@@ -972,7 +972,8 @@ def table_crop_rect(bbox, height: int, width: int):
 
 class OcrTableStructureTask(BaseInferTask):
     """OcrTableStructureTask (ocr_pdf/ocr_table_structure_task.py:50-271) for model="Lore", task_type="wtw"
-    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers) and model="CenterNet"
+    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers) or task_type="ptn" (the same
+    detector at 512 x 512, no corner snapping, 3-layer transformers fed with 2-D position embeddings) and model="CenterNet"
     (DLA-34 + plain IDA-up, vertex grouping; returns list[dict{polygons [n,8]}] like OCRTableCenterNetPostProcessor).
     Returns list[dict{polygons [n,8] float32 source pixels, logi [n,4] integer-valued, inputs}] like the reference's
     TableLorePostProcessor (lore/processer_lore.py:163-188).  `state_dict` = (detector, processor) state_dicts or paths
@@ -985,8 +986,9 @@ class OcrTableStructureTask(BaseInferTask):
                  table_structure_merge: bool = False, max_cells_per_image: int = 3000, **kwargs):
         if model not in ("Lore", "CenterNet"):
             raise RuntimeError(f"model {model} not support")
-        if model == "Lore" and task_type != "wtw":
-            raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements the DLA-34 'wtw' configuration)")
+        if model == "Lore" and task_type not in ("wtw", "ptn"):
+            raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements the DLA-34 configurations 'wtw' and 'ptn'; "
+                               "'wireless' needs the ResNet-18 detector, lore/lore_detector.py)")
         if model == "Lore" and (state_dict is None or len(state_dict) != 2):
             raise RuntimeError("OcrTableStructureTask(model='Lore', predictor_type='b200') needs state_dict=(detector, processor)")
         if model == "CenterNet" and state_dict is None:
@@ -994,7 +996,10 @@ class OcrTableStructureTask(BaseInferTask):
         if model == "CenterNet" and kwargs.get("precision", "fp16") != "fp16":
             raise RuntimeError("the CenterNet detector runs in fp16 operand precision only")
         self.task_type, self.table_structure_merge = task_type, table_structure_merge
-        self.resolution, self.vis_thresh, self.wiz_rev = (1024, 1024), 0.2, True  # LoreConfig wtw (configuration_lore.py:86-100)
+        if task_type == "ptn":  # LoreConfig ptn (configuration_lore.py:101-116): 512 x 512, 3 + 3 layers, 2-D position embeddings
+            self.resolution, self.vis_thresh, self.wiz_rev, self.wiz_2dpe = (512, 512), 0.35, False, True
+        else:  # LoreConfig wtw (configuration_lore.py:86-100)
+            self.resolution, self.vis_thresh, self.wiz_rev, self.wiz_2dpe = (1024, 1024), 0.2, True, False
         # capacity of the cell-feature / processor buffers per image; the decode keeps at most K = 3000 cells per image
         # (process_detect_output), so the default can never overflow.  A smaller cap saves workspace; exceeding it raises.
         self.max_cells_per_image = max_cells_per_image
@@ -1110,6 +1115,8 @@ class OcrTableStructureTask(BaseInferTask):
         dec = self.post.lore_decode(maps, None, None, None, inv, K=self.K, MK=self.MK, wiz_rev=self.wiz_rev, vis_thresh=self.vis_thresh)
         cap = n * min(self.max_cells_per_image, self.K)
         feat, offsets = self.predictor.lore_cell_features(dec, max_rows=cap)
+        if self.wiz_2dpe:  # LoreModel.forward passes dets=slct_dets_feat (modeling_lore.py:155-159)
+            self.processor.lore_add_position_embeddings(feat, dec, offsets)
         _, stacked = self.processor.lore_process_forward(feat, offsets)
         inputs["dev"] = {"polygons": dec["polygons"], "counts": dec["counts"], "offsets": offsets, "logi": stacked}
         inputs["cap"] = cap

@@ -232,3 +232,44 @@ def test_lore_processor_segments(proc_engine):
         wl, ws = lore_processor_ref.lore_processor_forward(sd, torch.from_numpy(feat[a:b]))
         assert float(np.abs(logic.cpu().numpy()[a:b] - wl.numpy()).max()) < PROC_TOL
         assert float(np.abs(stacked.cpu().numpy()[a:b] - ws.numpy()).max()) < PROC_TOL
+
+
+def test_lore_ptn_configuration(post_engine):
+    """task_type="ptn" (configuration_lore.py:101-116): 512 x 512 input, 3-layer transformers, the decode's integer position
+    features looked up in the x / y embedding tables and added to the cell features (dv_lore_add_position_embeddings) -- against
+    the processor oracle called with dets=, and end to end through OcrTableStructureTask."""
+    from pdf_table_b200 import predictors
+
+    psd = synth.lore_processor_state_dict(0, layers=3, stacking_layers=3)
+    proc = Engine("lore_processor", weights.pack_lore_processor(psd))
+    rng = np.random.default_rng(12)
+    n_img, k, counts = 2, 40, np.array([23, 31], np.int32)
+    feat = (rng.standard_normal((64, 256)) * 0.5).astype(np.float32)
+    dets = rng.integers(0, 128, (n_img, k, 8)).astype(np.int32)
+    offs = np.array([0, 23, 54], np.int32)
+    dec = {"dets_feat": torch.from_numpy(dets).cuda(), "counts": torch.from_numpy(counts).cuda()}
+    f_dev = torch.from_numpy(feat).cuda()
+    proc.lore_add_position_embeddings(f_dev, dec, torch.from_numpy(offs).cuda())
+    xe, ye = psd["x_position_embeddings.weight"], psd["y_position_embeddings.weight"]
+    want = feat.copy()
+    for i in range(n_img):
+        d = dets[i, : counts[i]]
+        want[offs[i]: offs[i + 1]] = (((feat[offs[i]: offs[i + 1]] + xe[d[:, 0]]) + ye[d[:, 1]]) + xe[d[:, 2]]) + ye[d[:, 5]]
+    np.testing.assert_array_equal(f_dev.cpu().numpy(), want)  # fp32 adds in the reference's order: exact
+    _, stacked = proc.lore_process_forward(f_dev, torch.from_numpy(offs).cuda())
+    for i in range(n_img):
+        _, ws = lore_processor_ref.lore_processor_forward(psd, torch.from_numpy(feat[offs[i]: offs[i + 1]]), layers=3, stacking_layers=3,
+                                                          dets=torch.from_numpy(dets[i, : counts[i]].astype(np.int64)))
+        err = float((stacked[offs[i]: offs[i + 1]].cpu() - ws).abs().max())
+        print(f"ptn processor image {i}: max|err| {err:.2e}")
+        assert err < PROC_TOL
+    proc.close()
+    # end to end
+    sd = synth.lore_dla34_state_dict(0)
+    sd["hm.2.bias"] = np.array([-0.3, -3.5], np.float32)
+    task = predictors.OcrTableStructureTask(model="Lore", task_type="ptn", state_dict=(sd, psd))
+    assert task.resolution == (512, 512) and task.vis_thresh == 0.35 and not task.wiz_rev
+    res = task([synth.synthetic_page(7, 400, 600)])
+    assert len(res) == 1 and res[0]["polygons"].shape[1] == 8 and res[0]["logi"].shape == (len(res[0]["polygons"]), 4)
+    with pytest.raises(RuntimeError):
+        predictors.OcrTableStructureTask(model="Lore", task_type="wireless", state_dict=(sd, psd))
