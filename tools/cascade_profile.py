@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--top", type=int, default=60)
     args = ap.parse_args()
     bench.DET = args.det
+    bench.TWO_STREAMS = False  # per-launch events are only meaningful when the branches do not overlap
     peaks, _ = bench.load_peaks() if hasattr(bench, "load_peaks") else ({"hbm_gbs": 6536.0, "bf16_tflops_sustained": 1353.7}, "")
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1353.7)) * 1e12
     bw_peak = float(peaks.get("hbm_gbs", 6536.0)) * 1e9
