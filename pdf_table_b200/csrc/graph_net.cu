@@ -45,11 +45,43 @@ __device__ __forceinline__ float act_f(float x, int act) {
     return x;
 }
 
+// Element access for the two activation storages of a graph program: fp16 (default) and fp32 (the fp32x mode: "precision" blob
+// entry, see GraphNet::precise).  8 consecutive channels per vector access.
+__device__ __forceinline__ void ld8(const __half* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x, v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void st8(__half* p, const float (&v)[8]) {
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+
 // image -> 16 channels at half resolution.  One thread per output pixel; weights [27][16] (tap-major: r, s, c) in smem.
+template <typename T>
 __global__ void __launch_bounds__(128)
 k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, int Ho, int Wo, float3 mean,
             float3 stdv, float scale, int flip, const float* __restrict__ w, const float* __restrict__ bias, int act,
-            __half* __restrict__ out, const int32_t* __restrict__ widths) {
+            T* __restrict__ out, const int32_t* __restrict__ widths) {
     __shared__ float sw[27 * 16];
     __shared__ float sb[16];
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
@@ -99,19 +131,18 @@ k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N
             }
         }
     }
-    uint4 o[2];
-    __half2* h = reinterpret_cast<__half2*>(o);
+    float lo8[8], hi8[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) h[c] = __floats2half2_rn(act_f(acc[2 * c], act), act_f(acc[2 * c + 1], act));
-    uint4* op = reinterpret_cast<uint4*>(out + idx * 16);
-    op[0] = o[0];
-    op[1] = o[1];
+    for (int c = 0; c < 8; ++c) lo8[c] = act_f(acc[c], act), hi8[c] = act_f(acc[8 + c], act);
+    st8(out + idx * 16, lo8);
+    st8(out + idx * 16 + 8, hi8);
 }
 
 // depthwise k x k, pad (k-1)/2, stride s; w fp32 [k*k][C] (BN scale folded), b fp32 [C]; one thread = (pixel, 8 channels)
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int k, int sh, int sw, int Ho, int Wo,
-         const float* __restrict__ w, const float* __restrict__ b, int act, float ps, float pb, __half* __restrict__ out, int ldo) {
+k_dwconv(const T* __restrict__ in, int N, int H, int W, int C, int ldi, int k, int sh, int sw, int Ho, int Wo,
+         const float* __restrict__ w, const float* __restrict__ b, int act, float ps, float pb, T* __restrict__ out, int ldo) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
@@ -132,26 +163,23 @@ k_dwconv(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int
         for (int s = 0; s < k; ++s) {
             const int ix = ox * sw - pad + s;
             if (ix < 0 || ix >= W) continue;
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + iy) * W + ix) * ldi + c8 * 8));
+            float v[8];
+            ld8(in + ((static_cast<long long>(n) * H + iy) * W + ix) * ldi + c8 * 8, v);
             const float4* wp = reinterpret_cast<const float4*>(w + static_cast<long long>(r * k + s) * C + c8 * 8);
             const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
-            const float2 v0 = __half22float2(h[0]), v1 = __half22float2(h[1]), v2 = __half22float2(h[2]), v3 = __half22float2(h[3]);
-            acc[0] = fmaf(v0.x, w0.x, acc[0]);
-            acc[1] = fmaf(v0.y, w0.y, acc[1]);
-            acc[2] = fmaf(v1.x, w0.z, acc[2]);
-            acc[3] = fmaf(v1.y, w0.w, acc[3]);
-            acc[4] = fmaf(v2.x, w1.x, acc[4]);
-            acc[5] = fmaf(v2.y, w1.y, acc[5]);
-            acc[6] = fmaf(v3.x, w1.z, acc[6]);
-            acc[7] = fmaf(v3.y, w1.w, acc[7]);
+            acc[0] = fmaf(v[0], w0.x, acc[0]);
+            acc[1] = fmaf(v[1], w0.y, acc[1]);
+            acc[2] = fmaf(v[2], w0.z, acc[2]);
+            acc[3] = fmaf(v[3], w0.w, acc[3]);
+            acc[4] = fmaf(v[4], w1.x, acc[4]);
+            acc[5] = fmaf(v[5], w1.y, acc[5]);
+            acc[6] = fmaf(v[6], w1.z, acc[6]);
+            acc[7] = fmaf(v[7], w1.w, acc[7]);
         }
     }
-    uint4 o;
-    __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(fmaf(act_f(acc[2 * i], act), ps, pb), fmaf(act_f(acc[2 * i + 1], act), ps, pb));
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(act_f(acc[i], act), ps, pb);
+    st8(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8, acc);
 }
 
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
@@ -311,8 +339,9 @@ k_dwconv_c2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, 
 }
 
 // kh x kw average pool with stride = kernel (floor output size), 8 channels per thread
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_avgpool(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, int kh, int kw, int Ho, int Wo, __half* __restrict__ out, int ldo) {
+k_avgpool(const T* __restrict__ in, int N, int H, int W, int C, int ldi, int kh, int kw, int Ho, int Wo, T* __restrict__ out, int ldo) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
@@ -324,26 +353,21 @@ k_avgpool(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, in
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int r = 0; r < kh; ++r)
         for (int s = 0; s < kw; ++s) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * H + oy * kh + r) * W + ox * kw + s) * ldi + c8 * 8));
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+            float v[8];
+            ld8(in + ((static_cast<long long>(n) * H + oy * kh + r) * W + ox * kw + s) * ldi + c8 * 8, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 v = __half22float2(h[i]);
-                acc[2 * i] += v.x;
-                acc[2 * i + 1] += v.y;
-            }
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
         }
     const float inv = 1.f / static_cast<float>(kh * kw);
-    uint4 o;
-    __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    st8(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8, acc);
 }
 
 // [N, T, C] (row stride ldi) -> [N, T, 3C]: columns [x[t-1] | x[t] | x[t+1]], zeros outside the line
+template <typename T_>
 __global__ void __launch_bounds__(256)
-k_unfold3(const __half* __restrict__ in, int N, int T, int C, int ldi, __half* __restrict__ out) {
+k_unfold3(const T_* __restrict__ in, int N, int T, int C, int ldi, T_* __restrict__ out) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * T * 3 * cv) return;
@@ -354,25 +378,26 @@ k_unfold3(const __half* __restrict__ in, int N, int T, int C, int ldi, __half* _
     const int t = static_cast<int>(r % T);
     const long long n = r / T;
     const int ts = t + tap - 1;
-    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (ts >= 0 && ts < T) u = __ldg(reinterpret_cast<const uint4*>(in + (n * T + ts) * ldi + c8 * 8));
-    *reinterpret_cast<uint4*>(out + ((n * T + t) * 3 + tap) * C + c8 * 8) = u;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ts >= 0 && ts < T) ld8(in + (n * T + ts) * ldi + c8 * 8, v);
+    st8(out + ((n * T + t) * 3 + tap) * C + c8 * 8, v);  // fp16 -> fp32 -> fp16 is exact: a plain copy either way
 }
 
 // LayerNorm over the C channels of each row (one warp per row, any C % 8 == 0 up to 1024), fp16 in / out
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_ln_c(const __half* __restrict__ in, long long rows, int C, int ldi, const float* __restrict__ g, const float* __restrict__ b, float eps,
-       __half* __restrict__ out, int ldo) {
+k_ln_c(const T* __restrict__ in, long long rows, int C, int ldi, const float* __restrict__ g, const float* __restrict__ b, float eps,
+       T* __restrict__ out, int ldo) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
     if (row >= rows) return;
-    const __half* ip = in + row * ldi;
+    const T* ip = in + row * ldi;
     float v[32];
     float s = 0.f;
     const int per = (C + 31) / 32;
     for (int j = 0; j < per; ++j) {
         const int c = lane + 32 * j;
-        v[j] = c < C ? __half2float(ip[c]) : 0.f;
+        v[j] = c < C ? ld1(ip + c) : 0.f;
         s += v[j];
     }
 #pragma unroll
@@ -388,35 +413,36 @@ k_ln_c(const __half* __restrict__ in, long long rows, int C, int ldi, const floa
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
-    __half* op = out + row * ldo;
+    T* op = out + row * ldo;
     for (int j = 0; j < per; ++j) {
         const int c = lane + 32 * j;
-        if (c < C) op[c] = __float2half_rn(v[j] * rstd * __ldg(g + c) + __ldg(b + c));
+        if (c < C) st1(op + c, v[j] * rstd * __ldg(g + c) + __ldg(b + c));
     }
 }
 
 // Global-mixer attention of the SVTR neck: qkv [N, T, 3D] (q | k | v, each head-major heads x hd; the 1/sqrt(hd) scale is
 // folded into the packed q weights) -> ctx [N, T, D].  One CTA per image; K and V of all heads staged in shared memory as
 // fp32, one thread per (head, query) with an online softmax (no score buffer, any T that fits shared memory).
+template <typename T_>
 __global__ void __launch_bounds__(256)
-k_attn_small(const __half* __restrict__ qkv, int T, int D, int heads, __half* __restrict__ ctx) {
+k_attn_small(const T_* __restrict__ qkv, int T, int D, int heads, T_* __restrict__ ctx) {
     extern __shared__ float sm[];  // K [T][D] | V [T][D]
     float* sK = sm;
     float* sV = sm + static_cast<size_t>(T) * D;
     const int n = blockIdx.x;
     const int hd = D / heads;
-    const __half* base = qkv + static_cast<long long>(n) * T * 3 * D;
+    const T_* base = qkv + static_cast<long long>(n) * T * 3 * D;
     for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
         const int t = i / D, c = i - t * D;
-        sK[i] = __half2float(base[static_cast<long long>(t) * 3 * D + D + c]);
-        sV[i] = __half2float(base[static_cast<long long>(t) * 3 * D + 2 * D + c]);
+        sK[i] = ld1(base + static_cast<long long>(t) * 3 * D + D + c);
+        sV[i] = ld1(base + static_cast<long long>(t) * 3 * D + 2 * D + c);
     }
     __syncthreads();
     for (int w = threadIdx.x; w < heads * T; w += blockDim.x) {
         const int h = w / T, qi = w - h * T;
         float q[16], o[16];
         for (int d = 0; d < hd; ++d) {
-            q[d] = __half2float(base[static_cast<long long>(qi) * 3 * D + h * hd + d]);
+            q[d] = ld1(base + static_cast<long long>(qi) * 3 * D + h * hd + d);
             o[d] = 0.f;
         }
         float m = -INFINITY, l = 0.f;
@@ -432,8 +458,8 @@ k_attn_small(const __half* __restrict__ qkv, int T, int D, int heads, __half* __
             m = mn;
         }
         const float inv = 1.f / l;
-        __half* op = ctx + (static_cast<long long>(n) * T + qi) * D + h * hd;
-        for (int d = 0; d < hd; ++d) op[d] = __float2half_rn(o[d] * inv);
+        T_* op = ctx + (static_cast<long long>(n) * T + qi) * D + h * hd;
+        for (int d = 0; d < hd; ++d) st1(op + d, o[d] * inv);
     }
 }
 
@@ -479,17 +505,18 @@ k_softmax_rows(const float* __restrict__ logits, long long M, int ld, int C, flo
 }
 
 // SE squeeze: one CTA per image.  avg[c] -> hidden = relu(W1 avg + b1) -> scale[c] = hardsigmoid(W2 hidden + b2)
+template <typename T>
 __global__ void __launch_bounds__(512)
-k_se_scale(const __half* __restrict__ in, int HW, int C, const float* __restrict__ w1, const float* __restrict__ b1,
+k_se_scale(const T* __restrict__ in, int HW, int C, const float* __restrict__ w1, const float* __restrict__ b1,
            const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ scale) {
     extern __shared__ float sm[];  // avg[C] | hidden[C/4]
     float* avg = sm;
     float* hid = sm + C;
     const int n = blockIdx.x, R = C >> 2;
-    const __half* base = in + static_cast<long long>(n) * HW * C;
+    const T* base = in + static_cast<long long>(n) * HW * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
-        for (int p = 0; p < HW; ++p) s += __half2float(base[static_cast<long long>(p) * C + c]);
+        for (int p = 0; p < HW; ++p) s += ld1(base + static_cast<long long>(p) * C + c);
         avg[c] = s / static_cast<float>(HW);
     }
     __syncthreads();
@@ -511,8 +538,9 @@ k_se_scale(const __half* __restrict__ in, int HW, int C, const float* __restrict
 // 45 GB/s (profiles/r4g_layers_ppdet.txt: 13.7 of 20.1 ms per 32 pages before).
 constexpr int kSePoolRows = 512;
 constexpr int kSePoolMin = 256;  // maps with fewer pixels keep the one-kernel squeeze
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_se_pool(const __half* __restrict__ in, int HW, int C, float* __restrict__ partial) {
+k_se_pool(const T* __restrict__ in, int HW, int C, float* __restrict__ partial) {
     extern __shared__ float sm[];  // [slots][C]
     const int cv = C >> 3, slots = 256 / cv;
     const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -520,16 +548,12 @@ k_se_pool(const __half* __restrict__ in, int HW, int C, float* __restrict__ part
     const int p0 = chunk * kSePoolRows, p1 = min(p0 + kSePoolRows, HW);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (slot < slots) {
-        const __half* base = in + (static_cast<long long>(n) * HW) * C + c8 * 8;
+        const T* base = in + (static_cast<long long>(n) * HW) * C + c8 * 8;
         for (int p = p0 + slot; p < p1; p += slots) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * C));
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+            float v[8];
+            ld8(base + static_cast<long long>(p) * C, v);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 v = __half22float2(h[i]);
-                acc[2 * i] += v.x;
-                acc[2 * i + 1] += v.y;
-            }
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) sm[slot * C + c8 * 8 + i] = acc[i];
@@ -568,26 +592,22 @@ k_se_scale_p(const float* __restrict__ partial, int nchunks, int HW, int C, cons
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_se_apply(const __half* __restrict__ in, long long total8, int HW, int C, const float* __restrict__ scale, float shortcut,
-           __half* __restrict__ out, int ldo) {
+k_se_apply(const T* __restrict__ in, long long total8, int HW, int C, const float* __restrict__ scale, float shortcut,
+           T* __restrict__ out, int ldo) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= total8) return;
     const int cv = C >> 3;
     const int c8 = static_cast<int>(idx % cv);
     const long long pix = idx / cv;
     const int n = static_cast<int>(pix / HW);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in) + idx);
+    float v[8];
+    ld8(in + idx * 8, v);
     const float* sp = scale + n * C + c8 * 8;
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-    uint4 o;
-    __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 v = __half22float2(h[i]);
-        ho[i] = __floats2half2_rn(v.x * (sp[2 * i] + shortcut), v.y * (sp[2 * i + 1] + shortcut));  // shortcut = 1: x + x * s
-    }
-    *reinterpret_cast<uint4*>(out + pix * ldo + c8 * 8) = o;
+    for (int i = 0; i < 8; ++i) v[i] *= sp[i] + shortcut;  // shortcut = 1: x + x * s
+    st8(out + pix * ldo + c8 * 8, v);
 }
 
 __global__ void __launch_bounds__(256)
@@ -682,6 +702,30 @@ k_head_split(const float* __restrict__ raw, long long M, int ld, int C, int R, f
     else dfl[m * R + (j - C)] = v;
 }
 
+// fp32x mode: fp32 rows [M, ld] (columns [0, K)) -> the split-fp16 A operand [M, 2 * Kp]: hi = fp16(x) at [0, Kp) (zero beyond K),
+// lo = fp16(x - hi) at [Kp, 2 * Kp); with weights packed [W_hi | W_lo | W_hi] conv_igemm_tcgen05 accumulates the three partial
+// products in fp32 (plan_linear, ConvSpec::split)
+__global__ void __launch_bounds__(256)
+k_split_f32(const float* __restrict__ in, long long M, int K, int Kp, int ld, __half* __restrict__ out) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const int kv = Kp >> 3;
+    if (idx >= M * kv) return;
+    const long long r = idx / kv;
+    const int c = static_cast<int>(idx - r * kv) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < K) ld8(in + r * ld + c, v);  // K % 8 == 0
+    uint4 hi, lo;
+    __half2 *hh = reinterpret_cast<__half2*>(&hi), *hl = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(hh[i]);
+        hl[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * 2 * Kp + c) = hi;
+    *reinterpret_cast<uint4*>(out + r * 2 * Kp + Kp + c) = lo;
+}
+
 struct GOp {
     int code, in_t, in_coff, in_c, out_t, out_coff, out_c, k, stride, act, w, aux;
     ConvPlan plan;  // OP_PW / OP_HEAD / OP_CTC / OP_CONV / OP_DECONV2
@@ -689,6 +733,7 @@ struct GOp {
     float ps = 1.f, pb = 0.f;  // post-activation affine (w{id}.pa), identity when absent
     int has_pa = 0;
     float eps = 1e-5f;         // OP_LN (w{id}.eps)
+    int kp = 0;                // fp32x: padded K of the split A operand
     int sh() const { return stride < 256 ? stride : (stride & 255); }  // stride = sh | sw << 8 when the two differ
     int sw() const { return stride < 256 ? stride : (stride >> 8); }
 };
@@ -697,6 +742,12 @@ struct GraphNet : Model {
     Engine* e = nullptr;
     int N = 0, H = 0, W = 0;
     int kind = 0;  // graph.meta[5]: 0 = PicoDet, 1 = PP-OCR recogniser, 2 = PULC classifier, 3 = PP-OCR detector
+    // fp32x mode (blob entry "precision", pp_rec_graph.pack_pp_rec(precise=True)): every activation buffer is fp32, the CUDA-core
+    // kernels read / write fp32, and every GEMM takes its A operand through k_split_f32 as a split-fp16 pair against weights
+    // packed [W_hi | W_lo | W_hi] (three MMAs per product, fp32 accumulation, fp32 output).  Probabilities of the PP-OCRv4
+    // recogniser land within 1e-4 of the fp32 oracle (tests/test_gpu_pp_rec.py).
+    bool precise = false;
+    __half* split_buf = nullptr;
     int num_classes = 0, reg_bins = 32, head_ld = 40;
     std::vector<int> tc, tdh, tdw, tph, tpw;  // channels; size = floor(ceil(H / dh) / ph) x floor(ceil(W / dw) / pw)
     std::vector<GOp> ops;
@@ -714,6 +765,7 @@ struct GraphNet : Model {
         std::vector<void*> mem;
         std::vector<GOp> ops;
         float *se_scale, *head_raw, *se_partial;
+        __half* split_buf;
         double flops;
     };
     std::vector<Saved> cache;
@@ -727,7 +779,7 @@ struct GraphNet : Model {
     }
     void park() {
         if (N == 0) return;
-        cache.push_back(Saved{N, H, W, std::move(tens), std::move(mem), ops, se_scale, head_raw, se_partial, flops});
+        cache.push_back(Saved{N, H, W, std::move(tens), std::move(mem), ops, se_scale, head_raw, se_partial, split_buf, flops});
         mem.clear();
         tens.clear();
         N = H = W = 0;
@@ -745,7 +797,7 @@ struct GraphNet : Model {
                 tens = std::move(sv.tens);
                 mem = std::move(sv.mem);
                 ops = std::move(sv.ops);
-                se_scale = sv.se_scale, head_raw = sv.head_raw, se_partial = sv.se_partial, flops = sv.flops;
+                se_scale = sv.se_scale, head_raw = sv.head_raw, se_partial = sv.se_partial, split_buf = sv.split_buf, flops = sv.flops;
                 return true;
             }
         return false;
@@ -787,8 +839,8 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         if (t.H <= 0 || t.W <= 0) return set_err(e, DV_ERR_ARG, "graph: input %dx%d too small for tensor %zu", H, W, i);
         t.C = m->tc[i];
         void* p = nullptr;
-        DV_TRY(m->alloc(&p, t.elems() * sizeof(__half)));
-        t.p = reinterpret_cast<__half*>(p);
+        DV_TRY(m->alloc(&p, t.elems() * (m->precise ? sizeof(float) : sizeof(__half))));
+        t.p = reinterpret_cast<__half*>(p);  // fp32x: the buffer holds floats (see F32 below)
     }
     size_t max_head_rows = 0, max_se_partial = 0;
     int max_se_c = 0;
@@ -843,6 +895,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
                 if (static_cast<size_t>(N) * in.H * in.W > max_head_rows) max_head_rows = static_cast<size_t>(N) * in.H * in.W;
                 break;
             case OP_DBHEAD:
+                if (m->precise) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
                 if (op.in_c > 64 || in.C != op.in_c) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: DB head over %d channels", op.in_c);
                 op.f0 = wf32(e, op.w, "hw", static_cast<size_t>(op.in_c) * 4, &rc);
                 op.f1 = wf32(e, op.w, "hb", 1, &rc);
@@ -879,6 +932,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
     }
     for (GOp& op : m->ops) {
         if (op.code != OP_CONV && op.code != OP_DECONV2) continue;
+        if (m->precise) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
         const Tensor& in = m->tens[op.in_t];
         const Tensor& out = m->tens[op.out_t];
         const std::string wn = "w" + std::to_string(op.w);
@@ -920,6 +974,19 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         e->owned.pop_back();
         m->flops += op.plan.flops;
     }
+    if (m->precise) {  // one split-operand scratch for all GEMMs of the program (they run one after the other)
+        size_t need = 0;
+        for (const GOp& op : m->ops) {
+            if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
+            if (op.code == OP_HEAD) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
+            const BlobTensor* w = e->find("w" + std::to_string(op.w) + ".w");
+            const Tensor& in = m->tens[op.in_t];
+            if (w && w->ndim == 2) need = std::max(need, static_cast<size_t>(N) * in.H * in.W * 2 * (w->dims[1] / 3));
+        }
+        void* p = nullptr;
+        DV_TRY(m->alloc(&p, need * sizeof(__half)));
+        m->split_buf = reinterpret_cast<__half*>(p);
+    }
     for (GOp& op : m->ops) {
         if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
         const Tensor& in = m->tens[op.in_t];
@@ -929,19 +996,22 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         const BlobTensor* b = e->find(wn + ".b");
         // the packed K axis is padded to a multiple of 16 (weights.cin_pad_of); the A operand keeps its own width, the TMA unit
         // zero-fills the columns beyond it
-        const int kpad = w ? static_cast<int>(w->dims[1]) : 0;
+        const int kw_total = w ? static_cast<int>(w->dims[1]) : 0;
+        const int kpad = m->precise ? kw_total / 3 : kw_total;  // fp32x: [W_hi | W_lo | W_hi], each Kp wide
         if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != op.out_c || kpad < op.in_c ||
-            kpad - op.in_c >= 16 || (kpad % 16))
+            (m->precise ? (kw_total != 3 * kpad || kpad - op.in_c >= 64) : (kpad - op.in_c >= 16)) || (kpad % 16))
             return set_err(e, DV_ERR_WEIGHTS, "graph: bad 1x1 weights '%s' (want [%d,%d])", wn.c_str(), op.out_c, op.in_c);
         ConvSpec cs;
         cs.KH = cs.KW = 1;
         cs.Cin = op.in_c;
-        cs.Cin_pad = kpad;
+        cs.Cin_pad = kw_total;
         cs.Cout = op.out_c;
         cs.BK = (kpad % 64 == 0) ? 64 : (kpad % 32 == 0) ? 32 : 16;
         cs.w = reinterpret_cast<const __half*>(w->dptr);
         cs.bias = reinterpret_cast<const float*>(b->dptr);
         cs.flat = true;
+        cs.split = m->precise;
+        op.kp = kpad;
         EpiSpec es;
         es.act = op.act;
         if (op.code == OP_HEAD || op.code == OP_CTC) {
@@ -952,6 +1022,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             es.out = out.p;
             es.out_ld = out.C;
             es.out_coff = op.out_coff;
+            es.out_f32 = m->precise ? 1 : 0;
             es.post_affine = op.has_pa;
             es.post_scale = op.ps;
             es.post_bias = op.pb;
@@ -961,7 +1032,17 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
                 es.res = r.p;
                 es.res_mode = RES_SAME;
                 es.res_ld = r.C;
+                es.res_f32 = m->precise ? 1 : 0;
+                if (m->precise && op.act != ACT_NONE) return set_err(e, DV_ERR_UNSUPPORTED, "graph: fp32x residual with an activation at '%s'", wn.c_str());
             }
+        }
+        if (m->precise) {
+            const int M = N * in.H * in.W;
+            DV_TRY(plan_linear(e, m->split_buf, M, kpad, cs, es, &op.plan, wn.c_str(), 2 * kpad, kpad));
+            m->mem.push_back(e->owned.back());
+            e->owned.pop_back();
+            m->flops += op.plan.flops;
+            continue;
         }
         const int M = N * in.H * in.W;
         DV_TRY(plan_linear(e, in.p + op.in_coff, M, op.in_c, cs, es, &op.plan, wn.c_str(), in.C));
@@ -994,6 +1075,8 @@ int graph_create(Engine* e) {
     m->reg_bins = hm[1];
     m->head_ld = hm[2];
     m->kind = hm.size() > 5 ? hm[5] : 0;
+    m->precise = e->find("precision") != nullptr;
+    if (m->precise) m->pass_n = 512;  // fp32 buffers + the split scratch: ~4x the workspace per crop
     if (const char* ps = getenv("DV_REC_PASS")) {
         if (atoi(ps) > 0) m->pass_n = atoi(ps);
     }
@@ -1041,6 +1124,7 @@ int graph_debug_tensor(Engine* e, int tensor_id, float* out_nchw, int* dims4) {
     if (!m) return set_err(e, DV_ERR_STATE, "not a graph-model handle");
     if (tensor_id <= 0 || tensor_id >= static_cast<int>(m->tens.size()) || !m->tens[tensor_id].p) return set_err(e, DV_ERR_ARG, "no tensor %d", tensor_id);
     const Tensor& t = m->tens[tensor_id];
+    if (m->precise) return set_err(e, DV_ERR_UNSUPPORTED, "graph: tensor dumps are not available in the fp32x mode");
     if (dims4) {
         dims4[0] = t.N, dims4[1] = t.C, dims4[2] = t.H, dims4[3] = t.W;
     }
@@ -1070,9 +1154,13 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
         if (!m->restore(N, H, W)) DV_TRY(build(e, m, N, H, W));
     }
     cudaStream_t s = e->stream;
+    const bool pr = m->precise;
+    auto F32 = [](const Tensor& t, int coff) { return reinterpret_cast<float*>(t.p) + coff; };  // fp32x: the buffers hold floats
     for (GOp& op : m->ops) {
         const Tensor& in = m->tens[op.in_t];
         const Tensor& out = m->tens[op.out_t];
+        if (pr && (op.code == OP_UP2 || op.code == OP_ADD || op.code == OP_HEAD || op.code == OP_CONV || op.code == OP_DECONV2 || op.code == OP_DBHEAD))
+            return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
         switch (op.code) {
             case OP_STEM: {
                 const long long total = static_cast<long long>(N) * out.H * out.W;
@@ -1082,8 +1170,10 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                     stdv = make_float3(std3[0], std3[1], std3[2]);
                 }
                 e->launch_begin("k_stem3x3s2", "conv1", 2.0 * total * 27 * 16, total * (12.0 * (in_u8 ? 1 : 4) + 32.0));
-                k_stem3x3s2<<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
-                                                                 out.p, widths);
+                if (pr) k_stem3x3s2<float><<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
+                                                                                F32(out, 0), widths);
+                else k_stem3x3s2<__half><<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
+                                                                              out.p, widths);
                 e->launch_end();
                 break;
             }
@@ -1093,7 +1183,10 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 e->launch_begin("k_dwconv", "dw", 0.0, total * 8 * 2.0 * (1.0 + 1.0 * (op.sh() * op.sw())));
                 static const bool row_kernel = !(getenv("DV_DWROW") && atoi(getenv("DV_DWROW")) == 0);
                 static const int dw_mode = getenv("DV_DWMODE") ? atoi(getenv("DV_DWMODE")) : 1;  // 1: k_dwconv_row (default), 2: k_dwconv_c2 (2x slower on the B200: 4-byte loads), 0: k_dwconv
-                if (row_kernel && dw_mode == 2 && op.sw() == 1 && (op.k == 3 || op.k == 5) && (op.sh() == 1 || op.sh() == 2)) {
+                if (pr) {
+                    k_dwconv<float><<<grid_for(total, 256), 256, 0, s>>>(F32(in, op.in_coff), N, in.H, in.W, op.in_c, in.C, op.k, op.sh(), op.sw(), out.H, out.W,
+                                                                         op.f0, op.f1, op.act, op.ps, op.pb, F32(out, op.out_coff), out.C);
+                } else if (row_kernel && dw_mode == 2 && op.sw() == 1 && (op.k == 3 || op.k == 5) && (op.sh() == 1 || op.sh() == 2)) {
 #define DV_DWC2(KK, PP, RR, SS)                                                                                                                   \
     k_dwconv_c2<KK, PP, RR, SS><<<grid_for(static_cast<long long>(N) * ((out.H + RR - 1) / RR) * ((out.W + PP - 1) / PP) * (op.in_c / 2), 128), 128, 0, s>>>( \
         in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W, op.f0, op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C)
@@ -1116,13 +1209,21 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                     }
 #undef DV_DWROW
                 } else {
-                    k_dwconv<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.k, op.sh(), op.sw(), out.H, out.W, op.f0,
+                    k_dwconv<__half><<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, op.k, op.sh(), op.sw(), out.H, out.W, op.f0,
                                                                   op.f1, op.act, op.ps, op.pb, out.p + op.out_coff, out.C);
                 }
                 e->launch_end();
                 break;
             }
             case OP_PW:
+                if (pr) {
+                    const long long M = static_cast<long long>(N) * in.H * in.W;
+                    e->launch_begin("k_split_f32", "split", 0.0, M * (4.0 * op.in_c + 4.0 * op.kp));
+                    k_split_f32<<<grid_for(M * (op.kp / 8), 256), 256, 0, s>>>(F32(in, op.in_coff), M, op.in_c, op.kp, in.C, m->split_buf);
+                    e->launch_end();
+                }
+                DV_TRY(launch_conv(e, op.plan));
+                break;
             case OP_CONV:
             case OP_DECONV2: DV_TRY(launch_conv(e, op.plan)); break;
             case OP_DBHEAD: {
@@ -1138,7 +1239,8 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 if (HW >= kSePoolMin) {
                     const int nchunks = (HW + kSePoolRows - 1) / kSePoolRows, cv = op.in_c / 8;
                     e->launch_begin("k_se_pool", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
-                    k_se_pool<<<dim3(nchunks, N), 256, static_cast<size_t>(256 / cv) * op.in_c * sizeof(float), s>>>(in.p, HW, op.in_c, m->se_partial);
+                    if (pr) k_se_pool<float><<<dim3(nchunks, N), 256, static_cast<size_t>(256 / cv) * op.in_c * sizeof(float), s>>>(F32(in, 0), HW, op.in_c, m->se_partial);
+                    else k_se_pool<__half><<<dim3(nchunks, N), 256, static_cast<size_t>(256 / cv) * op.in_c * sizeof(float), s>>>(in.p, HW, op.in_c, m->se_partial);
                     e->launch_end();
                     e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * nchunks * op.in_c * 4.0);
                     k_se_scale_p<<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(m->se_partial, nchunks, HW, op.in_c, op.f0, op.f1, op.f2, op.f3,
@@ -1146,12 +1248,14 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                     e->launch_end();
                 } else {
                     e->launch_begin("k_se_scale", "se", 0.0, static_cast<double>(N) * HW * op.in_c * 2.0);
-                    k_se_scale<<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(in.p, HW, op.in_c, op.f0, op.f1, op.f2, op.f3, m->se_scale);
+                    if (pr) k_se_scale<float><<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(F32(in, 0), HW, op.in_c, op.f0, op.f1, op.f2, op.f3, m->se_scale);
+                    else k_se_scale<__half><<<N, 512, (op.in_c + op.in_c / 4) * sizeof(float), s>>>(in.p, HW, op.in_c, op.f0, op.f1, op.f2, op.f3, m->se_scale);
                     e->launch_end();
                 }
                 const long long total8 = static_cast<long long>(N) * HW * (op.in_c / 8);
                 e->launch_begin("k_se_apply", "se", 0.0, total8 * 32.0);
-                k_se_apply<<<grid_for(total8, 256), 256, 0, s>>>(in.p, total8, HW, op.in_c, m->se_scale, op.k == 2 ? 1.f : 0.f, out.p + op.out_coff, out.C);
+                if (pr) k_se_apply<float><<<grid_for(total8, 256), 256, 0, s>>>(F32(in, 0), total8, HW, op.in_c, m->se_scale, op.k == 2 ? 1.f : 0.f, F32(out, op.out_coff), out.C);
+                else k_se_apply<__half><<<grid_for(total8, 256), 256, 0, s>>>(in.p, total8, HW, op.in_c, m->se_scale, op.k == 2 ? 1.f : 0.f, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
@@ -1186,21 +1290,24 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 const int kh = op.k == 0 ? in.H : (op.k & 255), kw = op.k == 0 ? in.W : (op.k >> 8);  // k = 0: global average pool
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
                 e->launch_begin("k_avgpool", "pool", 0.0, total * 16.0 * (kh * kw + 1));
-                k_avgpool<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, kh, kw, out.H, out.W, out.p + op.out_coff, out.C);
+                if (pr) k_avgpool<float><<<grid_for(total, 256), 256, 0, s>>>(F32(in, op.in_coff), N, in.H, in.W, op.in_c, in.C, kh, kw, out.H, out.W, F32(out, op.out_coff), out.C);
+                else k_avgpool<__half><<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, kh, kw, out.H, out.W, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
             case OP_UNFOLD3: {
                 const long long total = static_cast<long long>(N) * in.W * 3 * (op.in_c / 8);
                 e->launch_begin("k_unfold3", "unfold", 0.0, total * 32.0);
-                k_unfold3<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.W, op.in_c, in.C, out.p);
+                if (pr) k_unfold3<float><<<grid_for(total, 256), 256, 0, s>>>(F32(in, op.in_coff), N, in.W, op.in_c, in.C, F32(out, 0));
+                else k_unfold3<__half><<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.W, op.in_c, in.C, out.p);
                 e->launch_end();
                 break;
             }
             case OP_LN: {
                 const long long rows = static_cast<long long>(N) * in.H * in.W;
                 e->launch_begin("k_ln_c", "ln", 0.0, rows * op.in_c * 4.0);
-                k_ln_c<<<grid_for(rows, 8), 256, 0, s>>>(in.p + op.in_coff, rows, op.in_c, in.C, op.f0, op.f1, op.eps, out.p + op.out_coff, out.C);
+                if (pr) k_ln_c<float><<<grid_for(rows, 8), 256, 0, s>>>(F32(in, op.in_coff), rows, op.in_c, in.C, op.f0, op.f1, op.eps, F32(out, op.out_coff), out.C);
+                else k_ln_c<__half><<<grid_for(rows, 8), 256, 0, s>>>(in.p + op.in_coff, rows, op.in_c, in.C, op.f0, op.f1, op.eps, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }
@@ -1210,15 +1317,23 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 if (smem > 200 * 1024) return set_err(e, DV_ERR_UNSUPPORTED, "graph: attention over %d positions exceeds shared memory", T);
                 static DeviceOnce attr_once;
                 if (attr_once.need(e->device)) {
-                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_once.mark(e->device);
                 }
                 e->launch_begin("k_attn_small", "attn", 4.0 * N * T * T * D, static_cast<double>(N) * T * D * 8.0);
-                k_attn_small<<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
+                if (pr) k_attn_small<float><<<N, 256, smem, s>>>(F32(in, 0), T, D, op.k, F32(out, 0));
+                else k_attn_small<__half><<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
                 e->launch_end();
                 break;
             }
             case OP_CTC: {
+                if (pr) {
+                    const long long Mr = static_cast<long long>(N) * in.H * in.W;
+                    e->launch_begin("k_split_f32", "split", 0.0, Mr * (4.0 * op.in_c + 4.0 * op.kp));
+                    k_split_f32<<<grid_for(Mr * (op.kp / 8), 256), 256, 0, s>>>(F32(in, op.in_coff), Mr, op.in_c, op.kp, in.C, m->split_buf);
+                    e->launch_end();
+                }
                 DV_TRY(launch_conv(e, op.plan));
                 const long long M = static_cast<long long>(N) * in.H * in.W;
                 if (!go.ids && !go.probs && !go.maxp && !go.logits) return set_err(e, DV_ERR_ARG, "graph head: no output requested");

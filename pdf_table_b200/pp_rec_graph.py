@@ -67,18 +67,20 @@ def _pad_to(a: np.ndarray, axis: int, n: int) -> np.ndarray:
 
 
 def _gemm_weight(b: _Builder, w2d: np.ndarray, bias: np.ndarray, pa=None) -> int:
-    """[Cout, K] fp32 (+bias) -> packed 1x1 weight of the executor."""
-    wp, bp = W.pack_conv(w2d[:, :, None, None], bias)
+    """[Cout, K] fp32 (+bias) -> packed 1x1 weight of the executor (fp32x builders: the split-fp16 triple [W_hi | W_lo | W_hi])."""
+    wp, bp = W.pack_split_linear(w2d, bias) if getattr(b, "precise", False) else W.pack_conv(w2d[:, :, None, None], bias)
     arrays = {"w": wp, "b": bp}
     if pa is not None:
         arrays["pa"] = np.array(pa, np.float32)
     return b.weight(**arrays)
 
 
-def build_pp_rec(sd: Mapping, n_class: int = None):
+def build_pp_rec(sd: Mapping, n_class: int = None, precise: bool = False):
     """-> (blob tensor dict for weights.write_blob, meta).  Program format: picodet_graph.py's, with the 5-column tensor table
-    (channels, down_h, down_w, pool_h, pool_w) and the extra opcodes of csrc/graph_net.cu."""
+    (channels, down_h, down_w, pool_h, pool_w) and the extra opcodes of csrc/graph_net.cu.  precise=True: the fp32x mode -- every
+    GEMM weight as a split-fp16 triple and a "precision" entry that makes the executor keep its activations in fp32."""
     b = _Builder()
+    b.precise = precise
     n_class = int(_f(sd, "head.ctc_head.fc.weight").shape[0]) if n_class is None else n_class
     img = b.tensor(3, 1, 1)
     # ---- conv1: 3x3 stride 2 + BatchNorm, no activation
@@ -191,12 +193,14 @@ def build_pp_rec(sd: Mapping, n_class: int = None):
     fw, fb = _f(sd, "head.ctc_head.fc.weight"), _f(sd, "head.ctc_head.fc.bias")
     b.op(OP_CTC, seq, seq, out_c=pad_out, w=_gemm_weight(b, _pad_to(fw, 0, pad_out), _pad_to(fb, 0, pad_out)))
     blob = dict(b.blob)
+    if precise:
+        blob["precision"] = np.array([1], np.int32)
     blob["graph.tensors"] = np.array(b.tensors, np.int32)
     blob["graph.ops"] = np.array(b.ops, np.int32)
     blob["graph.meta"] = np.array([n_class, 0, pad_out, len(b.tensors), len(b.ops), 1, 0, 0], np.int32)
     return blob, {"features": feats, "pooled": cat, "seq": seq, "n_class": n_class}
 
 
-def pack_pp_rec(sd: Mapping, n_class: int = None) -> bytes:
-    blob, _ = build_pp_rec(sd, n_class)
+def pack_pp_rec(sd: Mapping, n_class: int = None, precise: bool = False) -> bytes:
+    blob, _ = build_pp_rec(sd, n_class, precise)
     return W.write_blob(blob)

@@ -627,8 +627,6 @@ class OcrRecognitionTask(BaseInferTask):
         self.do_chunking = do_chunking if model == "CRNN" else True
         if state_dict is None:
             raise RuntimeError("OcrRecognitionTask(predictor_type='b200') needs state_dict= (the recogniser's state_dict or a path)")
-        if model == "PP-OCRv4" and kwargs.get("precision", "fp16") != "fp16":
-            raise RuntimeError("the PP-OCRv4 recogniser runs in fp16 operand precision only")
         self._sd = _load_state_dict(state_dict)
         if model == "PP-OCRv4":
             # CTCLabelDecode (ocr_rec_pp/rec_postprocess.py:20-45, 163-165): character = ['blank'] + dict lines + [' '] (use_space_char)
@@ -648,7 +646,7 @@ class OcrRecognitionTask(BaseInferTask):
         if model == "PP-OCRv4":
             from .pp_rec_graph import pack_pp_rec
 
-            self.predictor = Engine("pp_rec", pack_pp_rec(self._sd), device=self.device)
+            self.predictor = Engine("pp_rec", pack_pp_rec(self._sd, precise=self.precision == "fp32x"), device=self.device)
         elif model == "CRNN":
             self.predictor = Engine("crnn", weights.pack_crnn(self._sd), device=self.device)
         else:
