@@ -610,9 +610,9 @@ k_se_apply(const T* __restrict__ in, long long total8, int HW, int C, const floa
     st8(out + pix * ldo + c8 * 8, v);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_up2(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho, int Wo, const __half* __restrict__ add, __half* __restrict__ out,
-      int ldo) {
+k_up2(const T* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho, int Wo, const T* __restrict__ add, T* __restrict__ out, int ldo) {
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
@@ -623,24 +623,22 @@ k_up2(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
     // F.interpolate(mode="nearest") to an explicit size: src = floor(dst * in / out)
     const int iy = min(static_cast<int>(static_cast<long long>(oy) * h / Ho), h - 1), ix = min(static_cast<int>(static_cast<long long>(ox) * w / Wo), w - 1);
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8));
+    float v[8];
+    ld8(in + ((static_cast<long long>(n) * h + iy) * w + ix) * ldi + c8 * 8, v);
     if (add != nullptr) {  // dense addend of the output's shape (the top-down sum of an FPN)
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(add + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + c8 * 8));
-        const __half2* ha = reinterpret_cast<const __half2*>(&a);
-        __half2* hu = reinterpret_cast<__half2*>(&u);
+        float a[8];
+        ld8(add + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * C + c8 * 8, a);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 x = __half22float2(hu[i]), y = __half22float2(ha[i]);
-            hu[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
-        }
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = u;
+    st8(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8, v);
 }
 
 // ConvTranspose2d(C -> 1, k 2, s 2) + sigmoid: fp16 [N,H,W,C] -> fp32 probability map [N,1,2H,2W]; w fp32 [C][dy*2+dx].
 // One thread per input pixel (DBHead.binarize conv3, det_db_head.py).
+template <typename T>
 __global__ void __launch_bounds__(128)
-k_dbhead(const __half* __restrict__ in, long long npix, int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
+k_dbhead(const T* __restrict__ in, long long npix, int H, int W, int C, const float* __restrict__ w, const float* __restrict__ bias,
          float* __restrict__ out) {
     __shared__ float sw[64 * 4];
     for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sw[i] = w[i];
@@ -650,22 +648,16 @@ k_dbhead(const __half* __restrict__ in, long long npix, int H, int W, int C, con
     const int x = static_cast<int>(idx % W), y = static_cast<int>((idx / W) % H);
     const long long n = idx / (static_cast<long long>(W) * H);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const uint4* ip = reinterpret_cast<const uint4*>(in + idx * C);
     for (int j = 0; j < (C >> 3); ++j) {
-        const uint4 u = __ldg(ip + j);
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        float f[8];
+        ld8(in + idx * C + j * 8, f);
 #pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 f = __half22float2(h[e2]);
-            const int c = j * 8 + e2 * 2;
-            a0 = fmaf(f.x, sw[c * 4 + 0], a0);
-            a1 = fmaf(f.x, sw[c * 4 + 1], a1);
-            a2 = fmaf(f.x, sw[c * 4 + 2], a2);
-            a3 = fmaf(f.x, sw[c * 4 + 3], a3);
-            a0 = fmaf(f.y, sw[c * 4 + 4], a0);
-            a1 = fmaf(f.y, sw[c * 4 + 5], a1);
-            a2 = fmaf(f.y, sw[c * 4 + 6], a2);
-            a3 = fmaf(f.y, sw[c * 4 + 7], a3);
+        for (int e2 = 0; e2 < 8; ++e2) {
+            const int c = j * 8 + e2;
+            a0 = fmaf(f[e2], sw[c * 4 + 0], a0);
+            a1 = fmaf(f[e2], sw[c * 4 + 1], a1);
+            a2 = fmaf(f[e2], sw[c * 4 + 2], a2);
+            a3 = fmaf(f[e2], sw[c * 4 + 3], a3);
         }
     }
     const float b = __ldg(bias);
@@ -895,7 +887,6 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
                 if (static_cast<size_t>(N) * in.H * in.W > max_head_rows) max_head_rows = static_cast<size_t>(N) * in.H * in.W;
                 break;
             case OP_DBHEAD:
-                if (m->precise) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
                 if (op.in_c > 64 || in.C != op.in_c) rc = set_err(e, DV_ERR_UNSUPPORTED, "graph: DB head over %d channels", op.in_c);
                 op.f0 = wf32(e, op.w, "hw", static_cast<size_t>(op.in_c) * 4, &rc);
                 op.f1 = wf32(e, op.w, "hb", 1, &rc);
@@ -930,25 +921,42 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         DV_TRY(m->alloc(&p, max_head_rows * m->head_ld * 4 + 16));
         m->head_raw = reinterpret_cast<float*>(p);
     }
+    if (m->precise) {  // one split-operand scratch for all GEMMs of the program (they run one after the other)
+        size_t need = 0;
+        for (const GOp& op : m->ops) {
+            if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC && op.code != OP_CONV && op.code != OP_DECONV2) continue;
+            if (op.code == OP_HEAD) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode does not cover the PicoDet head");
+            const BlobTensor* w = e->find("w" + std::to_string(op.w) + ".w");
+            const Tensor& in = m->tens[op.in_t];
+            const int taps = op.code == OP_CONV ? op.k * op.k : 1;
+            if (w && w->ndim == 2) need = std::max(need, static_cast<size_t>(N) * in.H * in.W * 2 * (w->dims[1] / 3 / taps));
+        }
+        void* p = nullptr;
+        DV_TRY(m->alloc(&p, need * sizeof(__half)));
+        m->split_buf = reinterpret_cast<__half*>(p);
+    }
     for (GOp& op : m->ops) {
         if (op.code != OP_CONV && op.code != OP_DECONV2) continue;
-        if (m->precise) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
         const Tensor& in = m->tens[op.in_t];
         const Tensor& out = m->tens[op.out_t];
         const std::string wn = "w" + std::to_string(op.w);
         const BlobTensor* w = e->find(wn + ".w");
         const BlobTensor* b = e->find(wn + ".b");
         const bool dec = op.code == OP_DECONV2;
+        const int parts = m->precise ? 3 : 1;  // fp32x: [W_hi | W_lo | W_hi] per filter tap
         const int taps = dec ? 1 : op.k * op.k, rows = dec ? 4 * op.out_c : op.out_c;
-        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != rows || (w->dims[1] % taps) ||
-            static_cast<int>(w->dims[1]) / taps < op.in_c || ((w->dims[1] / taps) % 16))
+        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != rows || (w->dims[1] % (taps * parts)) ||
+            static_cast<int>(w->dims[1]) / (taps * parts) < op.in_c || ((w->dims[1] / (taps * parts)) % 16))
             return set_err(e, DV_ERR_WEIGHTS, "graph: bad conv weights '%s' (want [%d, %d x >= %d])", wn.c_str(), rows, taps, op.in_c);
+        const int kpad = static_cast<int>(w->dims[1]) / (taps * parts);
+        op.kp = kpad;
         ConvSpec cs;
         cs.KH = cs.KW = dec ? 1 : op.k;
         cs.pad = dec ? 0 : op.k / 2;
         cs.stride = 1;
-        cs.Cin = op.in_c;
-        cs.Cin_pad = static_cast<int>(w->dims[1]) / taps;
+        cs.Cin = m->precise ? kpad : op.in_c;
+        cs.Cin_pad = (m->precise && dec) ? 3 * kpad : kpad;  // the flat (1x1) path counts all three parts, the patch path one
+        cs.split = m->precise;
         cs.Cout = rows;
         cs.BK = (cs.Cin_pad % 64 == 0) ? 64 : (cs.Cin_pad % 32 == 0) ? 32 : 16;
         cs.w = reinterpret_cast<const __half*>(w->dptr);
@@ -958,6 +966,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         es.out = out.p;
         es.out_ld = out.C;
         es.out_coff = op.out_coff;
+        es.out_f32 = m->precise ? 1 : 0;
         if (dec) {
             es.out_mode = OUT_SHUF2;
             if (out.H != 2 * in.H || out.W != 2 * in.W || op.out_coff != 0 || out.C != op.out_c)
@@ -969,23 +978,16 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         a.p = in.p + op.in_coff;
         a.ld = in.C;
         a.C = op.in_c;
+        if (m->precise) {  // the split scratch as an NHWC tensor of [hi(Kp) | lo(Kp)] pixels (k_split_f32 fills it before the launch)
+            a.p = m->split_buf;
+            a.C = kpad;
+            a.ld = 2 * kpad;
+            a.lo = kpad;
+        }
         DV_TRY(plan_conv(e, a, cs, es, in.H, in.W, &op.plan, wn.c_str()));
         m->mem.push_back(e->owned.back());
         e->owned.pop_back();
         m->flops += op.plan.flops;
-    }
-    if (m->precise) {  // one split-operand scratch for all GEMMs of the program (they run one after the other)
-        size_t need = 0;
-        for (const GOp& op : m->ops) {
-            if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
-            if (op.code == OP_HEAD) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
-            const BlobTensor* w = e->find("w" + std::to_string(op.w) + ".w");
-            const Tensor& in = m->tens[op.in_t];
-            if (w && w->ndim == 2) need = std::max(need, static_cast<size_t>(N) * in.H * in.W * 2 * (w->dims[1] / 3));
-        }
-        void* p = nullptr;
-        DV_TRY(m->alloc(&p, need * sizeof(__half)));
-        m->split_buf = reinterpret_cast<__half*>(p);
     }
     for (GOp& op : m->ops) {
         if (op.code != OP_PW && op.code != OP_HEAD && op.code != OP_CTC) continue;
@@ -1159,8 +1161,7 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
     for (GOp& op : m->ops) {
         const Tensor& in = m->tens[op.in_t];
         const Tensor& out = m->tens[op.out_t];
-        if (pr && (op.code == OP_UP2 || op.code == OP_ADD || op.code == OP_HEAD || op.code == OP_CONV || op.code == OP_DECONV2 || op.code == OP_DBHEAD))
-            return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode covers the recogniser's ops only");
+        if (pr && (op.code == OP_ADD || op.code == OP_HEAD)) return set_err(e, DV_ERR_UNSUPPORTED, "graph: the fp32x mode does not cover PicoDet's ops");
         switch (op.code) {
             case OP_STEM: {
                 const long long total = static_cast<long long>(N) * out.H * out.W;
@@ -1225,12 +1226,21 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 DV_TRY(launch_conv(e, op.plan));
                 break;
             case OP_CONV:
-            case OP_DECONV2: DV_TRY(launch_conv(e, op.plan)); break;
+            case OP_DECONV2:
+                if (pr) {
+                    const long long M = static_cast<long long>(N) * in.H * in.W;
+                    e->launch_begin("k_split_f32", "split", 0.0, M * (4.0 * op.in_c + 4.0 * op.kp));
+                    k_split_f32<<<grid_for(M * (op.kp / 8), 256), 256, 0, s>>>(F32(in, op.in_coff), M, op.in_c, op.kp, in.C, m->split_buf);
+                    e->launch_end();
+                }
+                DV_TRY(launch_conv(e, op.plan));
+                break;
             case OP_DBHEAD: {
                 if (!go.prob) return set_err(e, DV_ERR_ARG, "graph: no probability-map output");
                 const long long npix = static_cast<long long>(N) * in.H * in.W;
                 e->launch_begin("k_dbhead", "head", 2.0 * npix * op.in_c * 4, npix * (2.0 * op.in_c + 16.0));
-                k_dbhead<<<grid_for(npix, 128), 128, 0, s>>>(in.p, npix, in.H, in.W, op.in_c, op.f0, op.f1, go.prob);
+                if (pr) k_dbhead<float><<<grid_for(npix, 128), 128, 0, s>>>(F32(in, 0), npix, in.H, in.W, op.in_c, op.f0, op.f1, go.prob);
+                else k_dbhead<__half><<<grid_for(npix, 128), 128, 0, s>>>(in.p, npix, in.H, in.W, op.in_c, op.f0, op.f1, go.prob);
                 e->launch_end();
                 break;
             }
@@ -1262,8 +1272,10 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
             case OP_UP2: {
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
                 e->launch_begin("k_up2", "up", 0.0, total * 16.0 * 1.25);
-                k_up2<<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W,
-                                                           op.aux >= 0 ? m->tens[op.aux].p : nullptr, out.p + op.out_coff, out.C);
+                if (pr) k_up2<float><<<grid_for(total, 256), 256, 0, s>>>(F32(in, op.in_coff), N, in.H, in.W, op.in_c, in.C, out.H, out.W,
+                                                                          op.aux >= 0 ? F32(m->tens[op.aux], 0) : nullptr, F32(out, op.out_coff), out.C);
+                else k_up2<__half><<<grid_for(total, 256), 256, 0, s>>>(in.p + op.in_coff, N, in.H, in.W, op.in_c, in.C, out.H, out.W,
+                                                                        op.aux >= 0 ? m->tens[op.aux].p : nullptr, out.p + op.out_coff, out.C);
                 e->launch_end();
                 break;
             }

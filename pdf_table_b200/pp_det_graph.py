@@ -37,9 +37,12 @@ ACT_RELU = 1
 HEAD_PAD = 32  # the 24-channel head tensors are padded to 32
 
 
-def build_pp_det(sd: Mapping):
-    """-> (blob tensor dict for weights.write_blob, meta).  Program format: pp_rec_graph.py's."""
+def build_pp_det(sd: Mapping, precise: bool = False):
+    """-> (blob tensor dict for weights.write_blob, meta).  Program format: pp_rec_graph.py's.  precise=True: the fp32x mode (fp32
+    activation buffers, every GEMM / conv weight as a split-fp16 triple, see csrc/graph_net.cu GraphNet::precise)."""
     b = _Builder()
+    b.precise = precise
+    pack3x3 = W.pack_conv_split if precise else W.pack_conv
     ch = lambda c: pp_rec_ch(c, PP_DET_SCALE)  # noqa: E731
     img = b.tensor(3, 1, 1)
     w = _f(sd, "backbone.conv1.conv.weight")
@@ -111,7 +114,7 @@ def build_pp_det(sd: Mapping):
         src, dd = outs[i]
         wc = _f(sd, f"neck.inp_conv.{i}.in_conv.weight")  # [24, 96, 3, 3]
         u = b.tensor(q, dd, dd)
-        wp, bp = W.pack_conv(wc, np.zeros(q, np.float32))
+        wp, bp = pack3x3(wc, np.zeros(q, np.float32))
         b.op(OP_CONV, src, u, k=3, stride=1, act=ACT_NONE, w=b.weight(w=wp, b=bp))
         coff = (3 - i) * q
         if i == 0:
@@ -123,7 +126,7 @@ def build_pp_det(sd: Mapping):
     # ---- DBHead.binarize
     p = "head.binarize"
     bn1 = {k: _f(sd, f"{p}.conv_bn1.{k}") for k in ("weight", "bias", "running_mean", "running_var")}
-    wp, bp = W.pack_conv(_pad_to(_f(sd, p + ".conv1.weight"), 0, HEAD_PAD), None,
+    wp, bp = pack3x3(_pad_to(_f(sd, p + ".conv1.weight"), 0, HEAD_PAD), None,
                          {k: np.concatenate([v, np.ones(HEAD_PAD - q, np.float32) if k in ("weight", "running_var") else np.zeros(HEAD_PAD - q, np.float32)])
                           for k, v in bn1.items()})
     bp[q:HEAD_PAD] = 0.0
@@ -136,19 +139,21 @@ def build_pp_det(sd: Mapping):
     b2[:q] = _f(sd, p + ".conv2.bias")
     bn2p = {k: np.concatenate([v, np.ones(HEAD_PAD - q, np.float32) if k in ("weight", "running_var") else np.zeros(HEAD_PAD - q, np.float32)])
             for k, v in bn2.items()}
-    wp, bp = W.pack_deconv2x2(w2, b2, bn2p)
+    wp, bp = W.pack_deconv2x2(w2, b2, bn2p, split=precise)
     h2 = b.tensor(HEAD_PAD, d4 // 2, d4 // 2)
     b.op(OP_DECONV2, h1, h2, act=ACT_RELU, w=b.weight(w=wp, b=bp))
     w3 = np.zeros((HEAD_PAD, 4), np.float32)
     w3[:q] = _f(sd, p + ".conv3.weight").reshape(q, 4)  # [c][dy * 2 + dx]
     b.op(OP_DBHEAD, h2, h2, w=b.weight(hw=w3, hb=_f(sd, p + ".conv3.bias").reshape(1)))
     blob = dict(b.blob)
+    if precise:
+        blob["precision"] = np.array([1], np.int32)
     blob["graph.tensors"] = np.array(b.tensors, np.int32)
     blob["graph.ops"] = np.array(b.ops, np.int32)
     blob["graph.meta"] = np.array([1, 0, 8, len(b.tensors), len(b.ops), 3, 0, 0], np.int32)
     return blob, {"fuse": fuse, "ins": [t for t, _ in ins], "outs": [t for t, _ in outs], "h1": h1, "h2": h2}
 
 
-def pack_pp_det(sd: Mapping) -> bytes:
-    blob, _ = build_pp_det(sd)
+def pack_pp_det(sd: Mapping, precise: bool = False) -> bytes:
+    blob, _ = build_pp_det(sd, precise)
     return W.write_blob(blob)

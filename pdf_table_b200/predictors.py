@@ -474,8 +474,6 @@ class OcrDetectionTask(BaseInferTask):
         # mobile detector the reference's db_pp back-end downloads as ONNX (PPLCNetV3-0.75 + RSE-FPN + DBHead, pp_det_graph.py)
         if backbone not in ("resnet18", "PPLCNetV3") or (backbone == "PPLCNetV3" and model != "db_pp"):
             raise RuntimeError(f"backbone {backbone} not support for model {model}")
-        if backbone == "PPLCNetV3" and kwargs.get("precision", "fp16") != "fp16":
-            raise RuntimeError("the PP-OCRv4 detector runs in fp16 operand precision only")
         self.backbone = backbone
         self.thresh, self.unclip_ratio, self.max_candidates = thresh, unclip_ratio, max_candidates
         self.box_thresh = box_thresh if box_thresh is not None else (0.3 if model == "db" else 0.6)
@@ -487,7 +485,7 @@ class OcrDetectionTask(BaseInferTask):
         if self.backbone == "PPLCNetV3":
             from . import pp_det_graph
 
-            self.predictor = Engine("pp_det", pp_det_graph.pack_pp_det(self._sd), device=self.device)
+            self.predictor = Engine("pp_det", pp_det_graph.pack_pp_det(self._sd, precise=self.precision == "fp32x"), device=self.device)
         else:
             self.predictor = Engine("dbnet_r18", weights.pack_dbnet_r18(self._sd, precise=self.precision == "fp32x"), device=self.device)
         self._sd = None

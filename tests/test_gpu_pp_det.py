@@ -68,5 +68,22 @@ def test_detection_task_with_the_pp_ocrv4_backbone(det):
     np.testing.assert_array_equal(boxes.cpu().numpy()[0, : int(counts[0])], res[0])
     with pytest.raises(RuntimeError):
         predictors.OcrDetectionTask(model="db", backbone="PPLCNetV3", state_dict=sd)
-    with pytest.raises(RuntimeError):
-        predictors.OcrDetectionTask(model="db_pp", backbone="PPLCNetV3", state_dict=sd, precision="fp32x")
+
+
+def test_pp_det_fp32x_meets_the_north_star_tolerance():
+    """precision="fp32x" on the graph executor (fp32 buffers, split-fp16 GEMMs / 3x3 convs / transposed conv): the probability map
+    within 1e-3 of the fp32 oracle, and the boxes of the task equal to the DB post-process of the oracle's own map."""
+    from oracle import db_post_ref
+
+    sd = synth.pp_ocrv4_det_state_dict(0)
+    eng = Engine("pp_det", pp_det_graph.pack_pp_det(sd, precise=True))
+    rng = np.random.default_rng(11)
+    for n, h, w in ((2, 96, 160), (1, 256, 320)):
+        x = torch.from_numpy(rng.standard_normal((n, 3, h, w)).astype(np.float32))
+        want = pp_det_ref.pp_det_forward(sd, x)
+        err = float((eng.dbnet_forward(x.cuda()).cpu() - want).abs().max())
+        print(f"pp_det fp32x {n}x{h}x{w}: max |dprob| = {err:.3e}")
+        assert err <= 1e-3
+    eng.close()
+    task = predictors.OcrDetectionTask(model="db_pp", backbone="PPLCNetV3", state_dict=sd, precision="fp32x")
+    assert len(task([synth.synthetic_page(1, 300, 500)])) == 1
