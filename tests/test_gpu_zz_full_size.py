@@ -137,6 +137,32 @@ def test_recogniser_vs_oracle_on_a_96_crop_pass():
         rec.close()
 
 
+def test_pp_ocrv4_recogniser_vs_oracle_on_96_crops():
+    """96 text-line crops 48 x 320 (BASELINE's PP-OCRv4 rec shape: T = 40, C = 97) through the fp32 oracle of the published
+    architecture: fp16-operand probabilities within 1e-2, fp32x within 1e-3 with EVERY per-step arg-max equal."""
+    from oracle import pp_rec_ref
+    from pdf_table_b200 import pp_rec_graph
+
+    sd = synth.pp_ocrv4_rec_state_dict(0, 97)
+    crops = np.stack([synth.synthetic_text_crop(700 + i, 48, 320) for i in range(96)])
+    x = ((crops.astype(np.float32).transpose(0, 3, 1, 2) / 255 - 0.5) / 0.5).astype(np.float32)
+    want = pp_rec_ref.pp_rec_forward(sd, torch.from_numpy(x))
+    widths = torch.full((96,), 320, dtype=torch.int32).cuda()
+    for precise, tol in ((False, 1e-2), (True, 1e-3)):
+        eng = Engine("pp_rec", pp_rec_graph.pack_pp_rec(sd, precise=precise))
+        ids, maxp, probs = eng.rec_forward_u8(torch.from_numpy(crops).cuda(), widths, return_probs=True)
+        err = float((probs.cpu() - want).abs().max())
+        print(f"96 crops 48x320, PP-OCRv4 rec, precise={precise}: max|dprob| = {err:.3e}")
+        assert tuple(probs.shape) == (96, 40, 97) and err <= tol
+        bad = ids.cpu().numpy() != want.argmax(-1).numpy()
+        if precise:
+            assert not bad.any()
+        else:
+            top2 = torch.topk(want, 2, dim=-1).values
+            assert ((top2[..., 0] - top2[..., 1]).numpy()[bad] <= 2 * tol).all()
+        eng.close()
+
+
 def test_pp_ocrv4_det_vs_oracle_on_a_full_960_page():
     """One 960 x 960 page (BASELINE configs[1] page size) through the fp32 oracle of the PP-OCRv4 detector."""
     from oracle import pp_det_ref

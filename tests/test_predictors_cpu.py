@@ -72,7 +72,9 @@ def test_error_behaviour_without_gpu():
     with pytest.raises(RuntimeError):
         predictors.OcrDetectionTask(model="east", state_dict={})
     with pytest.raises(RuntimeError):
-        predictors.OcrRecognitionTask(model="CRNN", state_dict={})
+        predictors.OcrRecognitionTask(model="LightweightEdge", state_dict={})
+    with pytest.raises(RuntimeError):  # CRNN has no fp32x mode
+        predictors.OcrRecognitionTask(model="CRNN", precision="fp32x", state_dict={})
     with pytest.raises(RuntimeError):
         predictors.OcrTableStructureTask(model="CenterNet", state_dict=({}, {}))
     with pytest.raises(RuntimeError):
