@@ -149,7 +149,7 @@ int dv_create(const char* model_kind, const void* weight_blob_host, size_t nbyte
             rc = cnv_create(e);
         } else if (e->kind == "picodet" || e->kind == "pp_rec" || e->kind == "pplcnet_cls" || e->kind == "pp_det") {
             rc = graph_create(e);
-        } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34") {
+        } else if (e->kind == "lore_dla34" || e->kind == "centernet_dla34" || e->kind == "lore_resnet18") {
             rc = lore_create(e);
         } else if (e->kind == "lore_processor") {
             rc = lore_proc_create(e);
@@ -237,7 +237,7 @@ double dv_model_flops(dv_handle h) {
     if (h->kind == "dbnet_r18") return dbnet_flops(h);
     if (h->kind == "convnext_vit") return cnv_flops(h);
     if (h->kind == "crnn") return crnn_flops(h);
-    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_flops(h);
+    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34" || h->kind == "lore_resnet18") return lore_flops(h);
     if (h->kind == "picodet" || h->kind == "pp_rec" || h->kind == "pp_det") return graph_flops(h);
     return 0.0;
 }
@@ -263,7 +263,7 @@ int dv_debug_get_tensor(dv_handle h, const char* name, float* out_nchw_f32, int*
     if (!h || !name) return DV_ERR_ARG;
     DeviceGuard dev_guard(h->device);
     if (h->kind == "dbnet_r18") return dbnet_debug_tensor(h, name, out_nchw_f32, dims4_host);
-    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
+    if (h->kind == "lore_dla34" || h->kind == "centernet_dla34" || h->kind == "lore_resnet18") return lore_debug_tensor(h, name, out_nchw_f32, dims4_host);
     if ((h->kind == "picodet" || h->kind == "pp_det" || h->kind == "pp_rec") && name[0] == 't') return graph_debug_tensor(h, atoi(name + 1), out_nchw_f32, dims4_host);
     return set_err(h, DV_ERR_UNSUPPORTED, "dv_debug_get_tensor: not supported for '%s'", h->kind.c_str());
 }

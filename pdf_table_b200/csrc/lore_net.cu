@@ -23,7 +23,7 @@
 namespace dv {
 
 int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
-                    int flip, __half* out, long long lo);
+                    int flip, __half* out, long long lo, int cpp);
 int op_maxpool2x2(Engine* e, const Tensor& in, const Tensor& out);
 int op_dcn_im2col(Engine* e, const Tensor& in, const float* om, __half* col, const char* layer);
 int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tensor& skip, const Tensor& out, const char* layer);
@@ -33,6 +33,8 @@ int op_cell_offsets(Engine* e, const int32_t* counts, int N, int cap, int32_t* o
 int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int32_t* counts, const int32_t* offsets,
                        const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr);
 int op_logi_combine(Engine* e, const float* ax, const float* cr, int C, int cap, const int32_t* totals, float* out);
+int op_gather_pix(Engine* e, const Tensor& fa, const Tensor& fc, int K, int cap, const int32_t* counts, const int32_t* offsets,
+                  const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr);
 
 namespace {
 
@@ -40,7 +42,7 @@ constexpr int kCh[6] = {16, 32, 64, 128, 256, 512};
 constexpr int kLevels[6] = {1, 1, 1, 2, 2, 1};
 
 struct Step {
-    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY, WINCONV, DCN } kind;
+    enum Kind { CONV, MAXPOOL, IM2COL, UPADD, SIGMOID, COPY, WINCONV, DCN, MAXPOOL3 } kind;
     ConvPlan plan;
     DcnPlan dcn;
     WinConvPlan win;
@@ -60,6 +62,8 @@ struct LoreNet : Model {
     Engine* e = nullptr;
     bool precise = false;
     bool plain_up = false;  // CenterNet: DLAUp of plain IDAUp blocks (no DCN), heads hm / v2c / c2v / reg
+    bool resnet = false;    // Lore wireless: ResNet-18 key-point detector (build_r18); ax / cr end in a 1x1 over their own hidden maps
+    Tensor feat_ax, feat_cr;
     int N = 0, H = 0, W = 0;
     std::vector<void*> mem;
     std::vector<Step> steps;
@@ -505,6 +509,153 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ Lore wireless (ResNet-18)
+// LoreDetectModel (lore/lore_detector.py:148-389).  The 7x7 stride-2 stem reads the zero-bordered 4-channel image through the
+// overlapping-window view (A_STEM, as DBNet's); every stage is entered with stride 2 (:180-187); each ConvTranspose 4x4 s2 + BN +
+// ReLU is a 3x3 conv to 4 x 256 channels with the pixel-shuffle store (weights.deconv4x4_as_conv3x3) and the 1x1 `adaption`
+// lateral takes it as its epilogue residual; the six heads' first convs are one 3x3 conv to 6 x 64 channels, their 64 -> 64 convs
+// ping-pong between two 384-wide buffers on channel slices, the small heads end in one block-diagonal 1x1 to the packed 24-wide
+// fp32 map, and `ax` / `cr` leave their 64-channel hidden maps for the sparse 1x1 at the decoded points (build_feat).
+int add_stem_s2(LoreNet* m, const Tensor& in, const Tensor& out) {
+    Engine* e = m->e;
+    const BlobTensor* w = e->find("stem.w");
+    const BlobTensor* b = e->find("stem.b");
+    const int parts = m->precise ? 3 : 1;
+    if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || w->dims[0] != 64 || static_cast<int>(w->dims[1]) != 224 * parts)
+        return set_err(e, DV_ERR_WEIGHTS, "lore_resnet18: stem weight must be [64,%d]", 224 * parts);
+    ConvSpec cs;
+    cs.KH = cs.KW = 7;
+    cs.stride = 2;
+    cs.pad = 3;
+    cs.Cin = 3;
+    cs.Cout = 64;
+    cs.stem = true;
+    cs.split = m->precise;
+    cs.BK = 32;
+    cs.Cin_pad = 32;
+    cs.w = reinterpret_cast<const __half*>(w->dptr);
+    cs.bias = reinterpret_cast<const float*>(b->dptr);
+    Step st;
+    st.kind = Step::CONV;
+    st.name = "stem";
+    DV_TRY(plan_conv(e, in, cs, epi(out, ACT_RELU), out.H, out.W, &st.plan, "stem"));
+    m->adopt(m->mem);
+    m->flops += st.plan.flops;
+    m->steps.push_back(st);
+    return 0;
+}
+
+int build_r18(Engine* e, LoreNet* m, int N, int H, int W) {
+    if ((H % 64) || (W % 64)) return set_err(e, DV_ERR_ARG, "lore_resnet18: H and W must be multiples of 64 (got %dx%d)", H, W);
+    for (void* p : m->mem) cudaFree(p);
+    m->mem.clear();
+    m->steps.clear();
+    m->named.clear();
+    m->flops = 0;
+    m->e = e;
+    m->N = N;
+    m->H = H;
+    m->W = W;
+    DV_TRY(m->stem_tensor(&m->stem_in, N, H + 6, W + 8, 4));
+    m->om_rows = static_cast<size_t>(N) * (H / 4) * (W / 4);
+    {
+        void* p = nullptr;
+        DV_TRY(m->alloc(m->mem, &p, m->om_rows * 24 * sizeof(float)));
+        m->maps = reinterpret_cast<float*>(p);
+    }
+    Tensor c1, x[5];
+    DV_TRY(m->tensor(&c1, N, H / 2, W / 2, 64));
+    DV_TRY(m->tensor(&x[0], N, H / 4, W / 4, 64));
+    DV_TRY(add_stem_s2(m, m->stem_in, c1));
+    {
+        Step st;
+        st.kind = Step::MAXPOOL3;
+        st.a = c1;
+        st.b = x[0];
+        m->steps.push_back(st);
+    }
+    m->named["c1"] = c1;
+    m->named["x0"] = x[0];
+    const int planes[4] = {64, 128, 256, 256};
+    Tensor y = x[0];
+    for (int L = 0; L < 4; ++L) {
+        for (int B = 0; B < 2; ++B) {
+            const int stride = B == 0 ? 2 : 1;
+            const std::string pre = "layer" + std::to_string(L + 1) + "." + std::to_string(B);
+            Tensor t, o, ds;
+            DV_TRY(m->tensor(&t, N, y.H / stride, y.W / stride, planes[L]));
+            DV_TRY(m->tensor(&o, N, y.H / stride, y.W / stride, planes[L]));
+            DV_TRY(add_conv(m, pre + ".conv1", y, planes[L], 3, stride, epi(t, ACT_RELU)));
+            const Tensor* res = &y;
+            if (B == 0) {
+                DV_TRY(m->tensor(&ds, N, y.H / stride, y.W / stride, planes[L]));
+                DV_TRY(add_conv(m, pre + ".down", y, planes[L], 1, stride, epi(ds, ACT_NONE)));
+                res = &ds;
+            }
+            DV_TRY(add_conv(m, pre + ".conv2", t, planes[L], 3, 1, epi(o, ACT_RELU, res)));
+            y = o;
+        }
+        x[L + 1] = y;
+        m->named["x" + std::to_string(L + 1)] = y;
+    }
+    // top-down: up = ConvTranspose 4x4 s2 + BN + ReLU (3x3 conv + pixel shuffle), lateral = adaption 1x1 + up as residual
+    Tensor top = x[4];
+    const char* lateral[4] = {"adaption3", "adaption2", "adaption1", "adaption0"};
+    for (int i = 0; i < 4; ++i) {
+        const Tensor& skip = x[3 - i];
+        Tensor up, sum;
+        DV_TRY(m->tensor(&up, N, skip.H, skip.W, 256));
+        DV_TRY(m->tensor(&sum, N, skip.H, skip.W, 256));
+        EpiSpec es = epi(up, ACT_RELU);
+        es.out_mode = OUT_SHUF2;
+        DV_TRY(add_conv(m, "up" + std::to_string(i + 1), top, 1024, 3, 1, es));
+        DV_TRY(add_conv(m, lateral[i], skip, 256, 1, 1, epi(sum, ACT_NONE, &up)));
+        m->named["x" + std::to_string(3 - i) + "_"] = sum;
+        top = sum;
+    }
+    DV_TRY(m->tensor(&m->feat, N, H / 4, W / 4, 256));
+    DV_TRY(add_conv(m, "adaptionU1", top, 256, 1, 1, epi(m->feat, ACT_NONE)));
+    m->named["feat"] = m->feat;
+    // heads: channel slices [hm | reg | wh | st | ax | cr] of two 384-wide buffers
+    Tensor A, B;
+    DV_TRY(m->tensor(&A, N, H / 4, W / 4, 384));
+    DV_TRY(m->tensor(&B, N, H / 4, W / 4, 384));
+    DV_TRY(add_conv(m, "heads.conv1", m->feat, 384, 3, 1, epi(A, ACT_RELU)));
+    const char* hn[6] = {"hm", "reg", "wh", "st", "ax", "cr"};
+    for (int h = 0; h < 6; ++h) {
+        if (h == 1) continue;  // reg: conv3x3 + 1x1 only
+        const Tensor a = A.slice(64 * h, 64), b = B.slice(64 * h, 64);
+        const std::string pre = std::string("heads.") + hn[h];
+        DV_TRY(add_conv(m, pre + ".2", a, 64, 3, 1, epi(b, ACT_RELU)));
+        DV_TRY(add_conv(m, pre + ".4", b, 64, 3, 1, epi(a, ACT_RELU)));
+        DV_TRY(add_conv(m, pre + ".6", a, 64, 3, 1, epi(b, ACT_RELU)));
+    }
+    {
+        Step st;
+        st.kind = Step::COPY;
+        st.name = "reg.hidden";
+        st.a = A.slice(64, 64);
+        st.b = B.slice(64, 64);
+        m->steps.push_back(st);
+    }
+    {
+        EpiSpec es;
+        es.out = m->maps;  // re-pointed per call when the caller supplies its own buffer
+        es.out_ld = 24;
+        es.out_f32 = 1;
+        DV_TRY(add_conv(m, "heads.out", B.slice(0, 256), 24, 1, 1, es));
+    }
+    {
+        Step st;
+        st.kind = Step::SIGMOID;
+        st.name = "hm.sigmoid";
+        m->steps.push_back(st);
+    }
+    m->feat_ax = B.slice(256, 64);
+    m->feat_cr = B.slice(320, 64);
+    return 0;
+}
+
 int get_flat(Engine* e, const std::string& name, int K, int N, ConvSpec* cs) {
     cs->KH = cs->KW = 1;
     cs->Cout = N;
@@ -528,9 +679,10 @@ int build_feat(Engine* e, LoreNet* m, int K, int cap) {
     m->totals = m->offsets + m->N + 1;
     m->overflow = m->totals + 2;
     const size_t sp = m->precise ? 2 : 1;  // fp32x: patch rows and hidden rows are [hi | lo] pairs
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 9 * C * 2 * sp, true));
+    const int taps = m->resnet ? 1 : 9;   // ResNet-18 detector: the heads end in a 1x1 over their own hidden pixel
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * taps * C * 2 * sp, true));
     m->col_ax = reinterpret_cast<__half*>(p);
-    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * 9 * C * 2 * sp, true));
+    DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * 4 * taps * C * 2 * sp, true));
     m->col_cr = reinterpret_cast<__half*>(p);
     DV_TRY(m->alloc(m->feat_mem, &p, static_cast<size_t>(cap) * D * 2 * sp, true));
     m->hid_ax = reinterpret_cast<__half*>(p);
@@ -544,6 +696,21 @@ int build_feat(Engine* e, LoreNet* m, int K, int cap) {
     for (int h = 0; h < 2; ++h) {
         const int rows = h == 0 ? cap : 4 * cap;
         const int* m_dyn = m->totals + h;
+        if (m->resnet) {
+            ConvSpec c;
+            c.split = m->precise;
+            DV_TRY(get_flat(e, std::string(heads[h]) + ".out", C, D, &c));
+            EpiSpec es;
+            es.out = h == 0 ? m->out_ax : m->out_cr;
+            es.out_ld = D;
+            es.out_f32 = 1;
+            es.m_dyn = m_dyn;
+            ConvPlan pl;
+            DV_TRY(plan_linear(e, h == 0 ? m->col_ax : m->col_cr, rows, C, c, es, &pl, (std::string(heads[h]) + ".out").c_str()));
+            m->adopt(m->feat_mem);
+            m->feat_plans.push_back(pl);
+            continue;
+        }
         ConvSpec c1, c2;
         c1.split = c2.split = m->precise;
         DV_TRY(get_flat(e, std::string(heads[h]) + ".conv", 9 * C, D, &c1));
@@ -575,6 +742,7 @@ int lore_create(Engine* e) {
     LoreNet* m = new LoreNet();
     m->e = e;
     m->plain_up = e->kind == "centernet_dla34";
+    m->resnet = e->kind == "lore_resnet18";
     m->precise = e->find("precision") != nullptr;
     e->model.reset(m);
     return 0;
@@ -607,9 +775,9 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
     LoreNet* m = dynamic_cast<LoreNet*>(e->model.get());
     if (!m) return set_err(e, DV_ERR_STATE, "handle was not created as a lore_dla34 / centernet_dla34 model");
     if (N <= 0 || H <= 0 || W <= 0) return set_err(e, DV_ERR_ARG, "lore_detect_forward: bad arguments");
-    if (m->N != N || m->H != H || m->W != W) DV_TRY(build(e, m, N, H, W));
+    if (m->N != N || m->H != H || m->W != W) DV_TRY(m->resnet ? build_r18(e, m, N, H, W) : build(e, m, N, H, W));
     if (!in_nchw && !in_u8) return set_err(e, DV_ERR_ARG, "lore_detect_forward: no input");
-    DV_TRY(op_img_to_stem8(e, in_u8, in_nchw, N, H, W, mean3, std3, flip, m->stem_in.p, m->stem_in.lo));
+    DV_TRY(op_img_to_stem8(e, in_u8, in_nchw, N, H, W, mean3, std3, flip, m->stem_in.p, m->stem_in.lo, m->resnet ? 4 : 8));
     float* maps = maps_out ? maps_out : m->maps;
     for (Step& st : m->steps) {
         switch (st.kind) {
@@ -618,6 +786,7 @@ int lore_detect_forward(Engine* e, const float* in_nchw, const uint8_t* in_u8, c
                 DV_TRY(launch_conv(e, st.plan));
                 break;
             case Step::MAXPOOL: DV_TRY(op_maxpool2x2(e, st.a, st.b)); break;
+            case Step::MAXPOOL3: DV_TRY(op_maxpool3x3s2(e, st.a, st.b)); break;
             case Step::IM2COL: DV_TRY(op_dcn_im2col(e, st.a, m->om, m->col, st.name.c_str())); break;
             case Step::UPADD: DV_TRY(op_up_dw_add(e, st.a, st.wt, st.f, st.b, st.c, st.name.c_str())); break;
             case Step::SIGMOID: DV_TRY(op_sigmoid_cols(e, maps, static_cast<long long>(N) * (H / 4) * (W / 4), 24, 2)); break;
@@ -639,7 +808,8 @@ int lore_cell_features(Engine* e, int N, int K, int cap, const int32_t* counts, 
     if (m->K != K || m->cap != cap || m->feat_plans.empty()) DV_TRY(build_feat(e, m, K, cap));
     DV_CUDA(e, cudaMemsetAsync(m->overflow, 0, 4, e->stream));
     DV_TRY(op_cell_offsets(e, counts, N, cap, m->offsets, m->totals, m->overflow));
-    DV_TRY(op_gather_patch3x3(e, m->feat, K, cap, counts, m->offsets, ax_idx, cr_idx, m->col_ax, m->col_cr));
+    if (m->resnet) DV_TRY(op_gather_pix(e, m->feat_ax, m->feat_cr, K, cap, counts, m->offsets, ax_idx, cr_idx, m->col_ax, m->col_cr));
+    else DV_TRY(op_gather_patch3x3(e, m->feat, K, cap, counts, m->offsets, ax_idx, cr_idx, m->col_ax, m->col_cr));
     for (const ConvPlan& p : m->feat_plans) DV_TRY(launch_conv(e, p));
     DV_TRY(op_logi_combine(e, m->out_ax, m->out_cr, 256, cap, m->totals, logi_feat));
     if (offsets_out)

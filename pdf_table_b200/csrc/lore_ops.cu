@@ -46,7 +46,7 @@ __device__ __forceinline__ void store8_split(__half* p, long long lo, const floa
 // The u8 path mirrors numpy: (x / 255. - mean) / std evaluated in float64, then .astype(float32).
 __global__ void __launch_bounds__(256)
 k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, double3 mean, double3 stdv,
-               int flip, __half* __restrict__ out, long long lo) {
+               int flip, __half* __restrict__ out, long long lo, int cpp) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * H * W;
     if (idx >= total) return;
@@ -80,20 +80,23 @@ k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, in
     u.z = 0u;
     u.w = 0u;
     const int Hp = H + 6, Wp = W + 8;
-    __half* op = out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * 8;
-    *reinterpret_cast<uint4*>(op) = u;
+    __half* op = out + ((static_cast<long long>(n) * Hp + y + 3) * Wp + x + 3) * cpp;
+    // cpp = 8: the stride-1 stem of DLA-34 (8-channel pixels); cpp = 4: the stride-2 stem of the ResNet-18 detector (A_STEM view)
+    if (cpp == 8) *reinterpret_cast<uint4*>(op) = u;
+    else *reinterpret_cast<uint2*>(op) = make_uint2(u.x, u.y);
     if (lo > 0) {  // fp32x: the residual halves go to a second image batch `lo` elements further
         const float2 fa = __half22float2(a);
         const __half2 la = __floats2half2_rn(v0 - fa.x, v1 - fa.y);
         const __half2 lb = __floats2half2_rn(v2 - __low2float(b), 0.f);
         u.x = *reinterpret_cast<const uint32_t*>(&la);
         u.y = *reinterpret_cast<const uint32_t*>(&lb);
-        *reinterpret_cast<uint4*>(op + lo) = u;
+        if (cpp == 8) *reinterpret_cast<uint4*>(op + lo) = u;
+        else *reinterpret_cast<uint2*>(op + lo) = make_uint2(u.x, u.y);
     }
 }
 
 int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
-                    int flip, __half* out, long long lo) {
+                    int flip, __half* out, long long lo, int cpp) {
     const long long total = static_cast<long long>(N) * H * W;
     double3 m = make_double3(0, 0, 0), s = make_double3(1, 1, 1);
     if (u8) {
@@ -101,8 +104,8 @@ int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H
         m = make_double3(mean3[0], mean3[1], mean3[2]);
         s = make_double3(std3[0], std3[1], std3[2]);
     }
-    e->launch_begin("k_img_to_stem8", "pre", 0.0, total * ((u8 ? 3.0 : 12.0) + 16.0));
-    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out, lo);
+    e->launch_begin("k_img_to_stem8", "pre", 0.0, total * ((u8 ? 3.0 : 12.0) + 2.0 * cpp));
+    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out, lo, cpp);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -564,6 +567,29 @@ k_gather_patch3x3(const __half* __restrict__ feat, int H, int W, int C, int K, i
     }
 }
 
+// The ResNet-18 detector's `ax` / `cr` heads end in a 1x1 conv over their own 64-channel hidden maps: one CTA per (cell j,
+// image n) copies the hidden pixel of the centre (from fa) and of the four corners (from fc) into the GEMM rows.
+__global__ void __launch_bounds__(64)
+k_gather_pix(const __half* __restrict__ fa, const __half* __restrict__ fc, int H, int W, int C, int K, int cap,
+             const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, const int32_t* __restrict__ ax_idx,
+             const int32_t* __restrict__ cr_idx, __half* __restrict__ col_ax, __half* __restrict__ col_cr, int ldf, long long lof) {
+    const int j = blockIdx.x, n = blockIdx.y;
+    if (j >= counts[n]) return;
+    const int row = offsets[n] + j;
+    if (row >= cap) return;
+    const int cv = C >> 3;
+    const size_t o = static_cast<size_t>(n) * K + j;
+    const int rw = lof > 0 ? 2 * C : C;  // fp32x rows are [hi(C) | lo(C)]
+    for (int t = threadIdx.x; t < 5 * cv; t += blockDim.x) {
+        const int c8 = t % cv, pt = t / cv;
+        const int pix = pt == 0 ? ax_idx[o] : cr_idx[o * 4 + pt - 1];
+        const __half* src = (pt == 0 ? fa : fc) + (static_cast<long long>(n) * H * W + pix) * ldf + c8 * 8;
+        __half* dst = pt == 0 ? col_ax + static_cast<long long>(row) * rw : col_cr + (4LL * row + pt - 1) * rw;
+        *reinterpret_cast<uint4*>(dst + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(src));
+        if (lof > 0) *reinterpret_cast<uint4*>(dst + C + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(src + lof));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_logi_combine(const float* __restrict__ ax, const float* __restrict__ cr, int C, const int32_t* __restrict__ totals,
                float* __restrict__ out) {
@@ -593,6 +619,18 @@ int op_gather_patch3x3(Engine* e, const Tensor& feat, int K, int cap, const int3
     e->launch_begin("k_gather_patch3x3", "lore_feat", 0.0, (double)cap * 5 * 9 * feat.C * (feat.lo ? 8.0 : 4.0));
     k_gather_patch3x3<<<dim3(K, feat.N), 128, 0, e->stream>>>(feat.p, feat.H, feat.W, feat.C, K, cap, counts, offsets, ax_idx, cr_idx,
                                                               col_ax, col_cr, feat.ldc(), feat.lo);
+    e->launch_end();
+    DV_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+int op_gather_pix(Engine* e, const Tensor& fa, const Tensor& fc, int K, int cap, const int32_t* counts, const int32_t* offsets,
+                  const int32_t* ax_idx, const int32_t* cr_idx, __half* col_ax, __half* col_cr) {
+    if ((fa.C % 8) || fa.C != fc.C || fa.ldc() != fc.ldc() || fa.lo != fc.lo || fa.H != fc.H || fa.W != fc.W)
+        return set_err(e, DV_ERR_UNSUPPORTED, "gather_pix: the two hidden maps must share one layout, C %% 8 == 0");
+    e->launch_begin("k_gather_pix", "lore_feat", 0.0, (double)cap * 5 * fa.C * (fa.lo ? 8.0 : 4.0));
+    k_gather_pix<<<dim3(K, fa.N), 64, 0, e->stream>>>(fa.p, fc.p, fa.H, fa.W, fa.C, K, cap, counts, offsets, ax_idx, cr_idx, col_ax,
+                                                      col_cr, fa.ldc(), fa.lo);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -24,7 +24,7 @@ from ._lib import DocVisionError
 from .engine import Engine
 
 __all__ = ["BaseInferTask", "OcrDetectionTask", "OcrRecognitionTask", "OcrTableStructureTask", "OcrLayoutTask", "ClsImagePulcTask", "det_resize_for_test",
-           "keepratio_resize", "lore_affine", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "pp_rec_padded_width", "pp_rec_launch_groups", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
+           "keepratio_resize", "lore_affine", "lore_affine_upper_left", "lore_preprocess", "pp_rec_batch_plan", "PPOcrRecPreProcessor", "crop_geometry", "crop_images", "crops_for_recognition", "invert_affine", "lore_preprocess_device", "pp_rec_padded_width", "pp_rec_launch_groups", "table_crop_rect", "sort_det_boxes", "order_point", "order_points_batch", "det_resize_shape", "det_resize_for_test_device", "dbnet_resize_shape"]
 
 
 def _read_image(inputs) -> np.ndarray:
@@ -907,17 +907,51 @@ def lore_affine(center, scale, out_w: int, out_h: int, inv: bool = False) -> np.
     return cv2.getAffineTransform(dst, src) if inv else cv2.getAffineTransform(src, dst)
 
 
-def lore_preprocess(img: np.ndarray, resolution=(1024, 1024)):
+def lore_affine_upper_left(center, scale, out_w: int, out_h: int, inv: bool = False) -> np.ndarray:
+    """get_affine_transform_upper_left(center, scale, rot=0, output_size=(out_w, out_h), inv) of the reference
+    (lore/lineless_table_process.py:441-468), the `wireless` configuration's frame: `center` maps to the output's origin and
+    the point one `scale` along an axis maps one out_w along it (the axis is chosen by center[0] < center[1]; the
+    pre-processor passes center = (0, 0), :74-79, so it is the y axis and the map is the scaling out_w / scale about the
+    upper-left corner)."""
+    import cv2
+
+    c = np.asarray(center, np.float32)
+    sc = np.float32(scale)
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0] = c
+    if c[0] < c[1]:
+        src[1] = [sc, c[1]]
+        dst[1] = [out_w, 0]
+    else:
+        src[1] = [c[0], sc]
+        dst[1] = [0, out_w]
+    d = src[0] - src[1]
+    src[2] = src[1] + np.array([-d[1], d[0]], np.float32)
+    d = dst[0] - dst[1]
+    dst[2] = dst[1] + np.array([-d[1], d[0]], np.float32)
+    return cv2.getAffineTransform(dst, src) if inv else cv2.getAffineTransform(src, dst)
+
+
+def _lore_frame(height: int, width: int, upper_left: bool):
+    """(centre, scale, affine function) of TableLorePreProcessor.process (lore/processer_lore.py:73-83)."""
+    s = max(height, width) * 1.0
+    if upper_left:
+        return np.array([0, 0], dtype=np.float32), s, lore_affine_upper_left
+    return np.array([width / 2.0, height / 2.0], dtype=np.float32), s, lore_affine
+
+
+def lore_preprocess(img: np.ndarray, resolution=(1024, 1024), upper_left: bool = False):
     """TableLorePreProcessor.process (lore/processer_lore.py:66-109) up to the uint8 warp: centre-anchored similarity
-    warp (scale = resolution / max(h, w)) with cv2.warpAffine (bilinear, zero border).  The normalisation and the CHW
+    warp (scale = resolution / max(h, w); anchored at the upper-left corner for the `wireless` configuration) with
+    cv2.warpAffine (bilinear, zero border).  The normalisation and the CHW
     layout run fused on the GPU.  Returns (uint8 [H,W,3], meta int64 [7] = update_meta :112-130)."""
     import cv2
 
     height, width = img.shape[:2]
     inp_h, inp_w = resolution
-    c = np.array([width / 2.0, height / 2.0], dtype=np.float32)
-    s = max(height, width) * 1.0
-    trans = lore_affine(c, s, inp_w, inp_h)
+    c, s, affine = _lore_frame(height, width, upper_left)
+    trans = affine(c, s, inp_w, inp_h)
     warped = cv2.warpAffine(np.ascontiguousarray(img), trans, (inp_w, inp_h), flags=cv2.INTER_LINEAR)
     meta = np.array([c[0], c[1], s, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64)  # .long(): cx, cy truncated
     return warped, meta
@@ -940,16 +974,15 @@ def invert_affine(m) -> np.ndarray:
     return m.reshape(2, 3)
 
 
-def lore_preprocess_device(engine: Engine, img, resolution=(1024, 1024)):
+def lore_preprocess_device(engine: Engine, img, resolution=(1024, 1024), upper_left: bool = False):
     """lore_preprocess with the warp on the device (``dv_warp_affine_u8``, bit-exact against cv2.warpAffine): img is a uint8 HWC
     ndarray or cuda tensor; only the raw image goes up.  Returns (uint8 [H,W,3] cuda tensor, meta int64 [7])."""
     dev = torch.device("cuda", engine.device)
     t = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img)).to(dev)
     height, width = int(t.shape[0]), int(t.shape[1])
     inp_h, inp_w = resolution
-    c = np.array([width / 2.0, height / 2.0], dtype=np.float32)
-    s = max(height, width) * 1.0
-    warped = engine.warp_affine_u8(t, invert_affine(lore_affine(c, s, inp_w, inp_h)), inp_w, inp_h)
+    c, s, affine = _lore_frame(height, width, upper_left)
+    warped = engine.warp_affine_u8(t, invert_affine(affine(c, s, inp_w, inp_h)), inp_w, inp_h)
     meta = np.array([c[0], c[1], s, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64)
     return warped, meta
 
@@ -968,8 +1001,10 @@ def table_crop_rect(bbox, height: int, width: int):
 
 class OcrTableStructureTask(BaseInferTask):
     """OcrTableStructureTask (ocr_pdf/ocr_table_structure_task.py:50-271) for model="Lore", task_type="wtw"
-    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers) or task_type="ptn" (the same
-    detector at 512 x 512, no corner snapping, 3-layer transformers fed with 2-D position embeddings) and model="CenterNet"
+    (DLA-34 + DCNv2 detector, wiz_rev corner snapping, two 4-layer logical-location transformers), task_type="ptn" (the same
+    detector at 512 x 512, no corner snapping, 3-layer transformers fed with 2-D position embeddings) or task_type="wireless"
+    (the ResNet-18 key-point detector of lore/lore_detector.py at 768 x 768 in the upper-left-anchored frame, 4-layer
+    transformers with 2-D position embeddings) and model="CenterNet"
     (DLA-34 + plain IDA-up, vertex grouping; returns list[dict{polygons [n,8]}] like OCRTableCenterNetPostProcessor).
     Returns list[dict{polygons [n,8] float32 source pixels, logi [n,4] integer-valued, inputs}] like the reference's
     TableLorePostProcessor (lore/processer_lore.py:163-188).  `state_dict` = (detector, processor) state_dicts or paths
@@ -982,9 +1017,8 @@ class OcrTableStructureTask(BaseInferTask):
                  table_structure_merge: bool = False, max_cells_per_image: int = 3000, **kwargs):
         if model not in ("Lore", "CenterNet"):
             raise RuntimeError(f"model {model} not support")
-        if model == "Lore" and task_type not in ("wtw", "ptn"):
-            raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements the DLA-34 configurations 'wtw' and 'ptn'; "
-                               "'wireless' needs the ResNet-18 detector, lore/lore_detector.py)")
+        if model == "Lore" and task_type not in ("wtw", "ptn", "wireless"):
+            raise RuntimeError(f"task_type {task_type} not support (the b200 predictor implements 'wtw', 'ptn' and 'wireless')")
         if model == "Lore" and (state_dict is None or len(state_dict) != 2):
             raise RuntimeError("OcrTableStructureTask(model='Lore', predictor_type='b200') needs state_dict=(detector, processor)")
         if model == "CenterNet" and state_dict is None:
@@ -992,8 +1026,11 @@ class OcrTableStructureTask(BaseInferTask):
         if model == "CenterNet" and kwargs.get("precision", "fp16") != "fp16":
             raise RuntimeError("the CenterNet detector runs in fp16 operand precision only")
         self.task_type, self.table_structure_merge = task_type, table_structure_merge
+        self.upper_left = False
         if task_type == "ptn":  # LoreConfig ptn (configuration_lore.py:101-116): 512 x 512, 3 + 3 layers, 2-D position embeddings
             self.resolution, self.vis_thresh, self.wiz_rev, self.wiz_2dpe = (512, 512), 0.35, False, True
+        elif task_type == "wireless" and model == "Lore":  # configuration_lore.py:73-85: ResNet-18, 768 x 768, upper-left frame
+            self.resolution, self.vis_thresh, self.wiz_rev, self.wiz_2dpe, self.upper_left = (768, 768), 0.2, False, True, True
         else:  # LoreConfig wtw (configuration_lore.py:86-100)
             self.resolution, self.vis_thresh, self.wiz_rev, self.wiz_2dpe = (1024, 1024), 0.2, True, False
         # capacity of the cell-feature / processor buffers per image; the decode keeps at most K = 3000 cells per image
@@ -1007,7 +1044,10 @@ class OcrTableStructureTask(BaseInferTask):
         if model == "CenterNet":
             self.predictor = Engine("centernet_dla34", weights.pack_centernet_dla34(self._sd), device=self.device)
         else:
-            self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0], precise=self.precision == "fp32x"), device=self.device)
+            if self.upper_left:  # LoreModel.__init__ picks the detector by the backbone name (lore/modeling_lore.py:79-89)
+                self.predictor = Engine("lore_resnet18", weights.pack_lore_resnet18(self._sd[0], precise=self.precision == "fp32x"), device=self.device)
+            else:
+                self.predictor = Engine("lore_dla34", weights.pack_lore_dla34(self._sd[0], precise=self.precision == "fp32x"), device=self.device)
             self.processor = Engine("lore_processor", weights.pack_lore_processor(self._sd[1]), device=self.device)
         self._sd = None
 
@@ -1026,10 +1066,10 @@ class OcrTableStructureTask(BaseInferTask):
             if not isinstance(it, np.ndarray):
                 img = img[:, :, ::-1]  # path / PIL inputs reach the network as BGR, ndarrays unchanged (processer_lore.py:51-60, 146)
             if self.kwargs.get("host_warp", False):
-                warped, meta = lore_preprocess(img, self.resolution)
+                warped, meta = lore_preprocess(img, self.resolution, self.upper_left)
                 warped = _to_device_u8(warped, dev)
             else:
-                warped, meta = lore_preprocess_device(self.post, _to_device_u8(img, dev), self.resolution)
+                warped, meta = lore_preprocess_device(self.post, _to_device_u8(img, dev), self.resolution, self.upper_left)
             images.append(warped)
             metas.append(meta)
             h, w = img.shape[:2]
@@ -1071,10 +1111,9 @@ class OcrTableStructureTask(BaseInferTask):
             if not 0 <= pg < n_pages:
                 raise ValueError(f"table page {pg} outside the batch of {n_pages} pages")
             x0, y0, cw, ch = table_crop_rect(tb["bbox"], height, width)
-            c = np.array([cw / 2.0, ch / 2.0], dtype=np.float32)
-            sc = max(ch, cw) * 1.0
+            c, sc, affine = _lore_frame(ch, cw, self.upper_left)
             rects.append([pg, x0, y0, cw, ch])
-            minv.append(invert_affine(lore_affine(c, sc, inp_w, inp_h)))
+            minv.append(invert_affine(affine(c, sc, inp_w, inp_h)))
             metas.append(np.array([c[0], c[1], sc, inp_h, inp_w, inp_h // 4, inp_w // 4]).astype(np.int64))
             cs.append((c, sc))
         warped = self.post.crop_tables_for_tsr(t, np.array(rects, np.int32), np.stack(minv), inp_w, inp_h)
@@ -1106,7 +1145,9 @@ class OcrTableStructureTask(BaseInferTask):
             return self._run_centernet(inputs)
         n = len(inputs["images"])
         metas = inputs["meta"]
-        inv = np.stack([lore_affine([np.float32(m[0]), np.float32(m[1])], np.float32(m[2]), int(m[6]), int(m[5]), inv=True) for m in metas])
+        # ctdet_4ps_post_process / _upper_left (lineless_table_process.py:493-530) on the integer meta (update_meta's .long())
+        affine = lore_affine_upper_left if self.upper_left else lore_affine
+        inv = np.stack([affine([np.float32(m[0]), np.float32(m[1])], np.float32(m[2]), int(m[6]), int(m[5]), inv=True) for m in metas])
         maps = self.predictor.lore_detect_forward_u8(self._images_on_device(inputs["images"]))
         dec = self.post.lore_decode(maps, None, None, None, inv, K=self.K, MK=self.MK, wiz_rev=self.wiz_rev, vis_thresh=self.vis_thresh)
         cap = n * min(self.max_cells_per_image, self.K)

@@ -853,3 +853,50 @@ def pplcnet_cls_state_dict(seed: int = 0, class_num: int = 4) -> "OrderedDict[st
     sd["last_conv.weight"] = _conv(rng, 1280, 512, 1, 1)
     sd["fc.weight"], sd["fc.bias"] = _lin(rng, class_num, 1280, gain=400.0), _b(rng, class_num)
     return sd
+
+
+# --------------------------------------------------------------------------- Lore wireless (ResNet-18 key-point detector)
+LORE_R18_PLANES = (64, 128, 256, 256)  # layer1..4, every one entered with stride 2 (lore/lore_detector.py:180-187)
+LORE_R18_HEAD_CONV = 64
+
+
+def lore_resnet18_state_dict(seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Keys / shapes of `LoreDetectModel` (reference model/lore/lore_detector.py:148-389): 7x7 stem, four 2-block stages
+    (BasicBlock convs WITH bias, :75-79), four ConvTranspose 4x4 s2 up-steps with 1x1 `adaption` laterals, six heads of
+    head_conv = 64 (`reg`: conv3x3 + 1x1; the others: four conv3x3 + 1x1)."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    sd["conv1.weight"] = _conv(rng, 64, 3, 7, 7)
+    _bn(rng, sd, "bn1", 64)
+    inpl = 64
+    for L, planes in enumerate(LORE_R18_PLANES, start=1):
+        for B in range(2):
+            p = f"layer{L}.{B}"
+            sd[p + ".conv1.weight"] = _conv(rng, planes, inpl, 3, 3)
+            sd[p + ".conv1.bias"] = _b(rng, planes)
+            _bn(rng, sd, p + ".bn1", planes)
+            sd[p + ".conv2.weight"] = _conv(rng, planes, planes, 3, 3, gain=1.0)
+            sd[p + ".conv2.bias"] = _b(rng, planes)
+            _bn(rng, sd, p + ".bn2", planes)
+            if B == 0:
+                sd[p + ".downsample.0.weight"] = _conv(rng, planes, inpl, 1, 1, gain=1.0)
+                _bn(rng, sd, p + ".downsample.1", planes)
+            inpl = planes
+    for name, cin in (("adaption3", 256), ("adaption2", 128), ("adaption1", 64), ("adaption0", 64), ("adaptionU1", 256)):
+        sd[name + ".weight"] = _conv(rng, 256, cin, 1, 1, gain=1.0)
+    for i in range(1, 5):  # ConvTranspose2d weight [Cin, Cout, 4, 4]; every output pixel sums 2 x 2 taps x 256 channels
+        sd[f"deconv_layers{i}.0.weight"] = (rng.standard_normal((256, 256, 4, 4)) * np.sqrt(2.0 / (256 * 4))).astype(np.float32)
+        _bn(rng, sd, f"deconv_layers{i}.1", 256)
+    hc = LORE_R18_HEAD_CONV
+    for head, classes in sorted(LORE_HEADS):
+        sd[f"{head}.0.weight"] = _conv(rng, hc, 256, 3, 3)
+        sd[f"{head}.0.bias"] = _b(rng, hc)
+        last = 2
+        if head != "reg":
+            for j in (2, 4, 6):
+                sd[f"{head}.{j}.weight"] = _conv(rng, hc, hc, 3, 3, gain=1.4)
+                sd[f"{head}.{j}.bias"] = _b(rng, hc)
+            last = 8
+        sd[f"{head}.{last}.weight"] = _conv(rng, classes, hc, 1, 1, gain=0.25)
+        sd[f"{head}.{last}.bias"] = _b(rng, classes) if head != "hm" else np.full(classes, -2.19, np.float32)
+    return sd

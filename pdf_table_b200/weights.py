@@ -396,6 +396,85 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> by
     return write_blob(t)
 
 
+def deconv4x4_as_conv3x3(weight, bn=None) -> Tuple[np.ndarray, np.ndarray]:
+    """ConvTranspose2d(k=4, s=2, p=1, no bias) weight [Cin, Cout, 4, 4] (+BN) -> the equivalent 3x3 stride-1 pad-1 conv weight
+    [4*Cout, Cin, 3, 3] whose output is pixel-shuffled (OUT_SHUF2, row (py*2 + px)*Cout + co) plus its bias [4*Cout].
+    Output pixel (2y + py, 2x + px) receives input (y + dy, x + dx) through kernel tap ky = py + 1 - 2 dy (same in x): two of the
+    three conv rows per parity, the third stays zero."""
+    w = _np(weight).astype(np.float32)
+    cin, cout, kh, kw = w.shape
+    assert (kh, kw) == (4, 4), w.shape
+    scale, shift = bn_affine(bn, cout)
+    ws = w * scale[None, :, None, None]
+    out = np.zeros((2, 2, cout, cin, 3, 3), np.float32)
+    for py in range(2):
+        for r in range(3):
+            ky = py + 3 - 2 * r
+            if not 0 <= ky < 4:
+                continue
+            for px in range(2):
+                for c in range(3):
+                    kx = px + 3 - 2 * c
+                    if 0 <= kx < 4:
+                        out[py, px, :, :, r, c] = ws[:, :, ky, kx].T
+    return out.reshape(4 * cout, cin, 3, 3), np.tile(shift, 4).astype(np.float32)
+
+
+LORE_R18_HEAD_ORDER = ("hm", "reg", "wh", "st", "ax", "cr")  # channel-slice order of the 384-wide head buffers
+
+
+def pack_lore_resnet18(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> bytes:
+    """state_dict of the reference `LoreDetectModel` (lore/lore_detector.py:148-389, the `wireless` configuration) -> engine blob
+    (model kind "lore_resnet18", csrc/lore_net.cu build_r18).  BatchNorm folded everywhere; each ConvTranspose 4x4 s2 becomes a
+    3x3 conv to 4 x 256 pixel-shuffled channels (deconv4x4_as_conv3x3); the first conv of the six heads is ONE 3x3 conv
+    256 -> 6 x 64 (order LORE_R18_HEAD_ORDER), the 64 -> 64 convs stay per head, the last 1x1 of hm / reg / wh / st is one
+    block-diagonal 256 -> 24 conv (LORE_SMALL_HEADS columns), `ax` / `cr` keep their 64 -> 256 matrices for the sparse
+    evaluation at decoded points."""
+    t: Dict[str, np.ndarray] = {}
+    f = lambda k: _np(sd[k]).astype(np.float32)
+
+    def put(name, wb):
+        t[name + ".w"], t[name + ".b"] = wb
+
+    pack = pack_conv_split if precise else pack_conv
+    if precise:
+        t["precision"] = np.array([1], np.int32)
+    put("stem", pack_stem7x7(sd["conv1.weight"], _bn(sd, "bn1"), split=precise))
+    for L in range(1, 5):
+        for B in range(2):
+            p = f"layer{L}.{B}"
+            put(p + ".conv1", pack(sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], _bn(sd, p + ".bn1")))
+            put(p + ".conv2", pack(sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], _bn(sd, p + ".bn2")))
+            if (p + ".downsample.0.weight") in sd:
+                put(p + ".down", pack(sd[p + ".downsample.0.weight"], None, _bn(sd, p + ".downsample.1")))
+    for name in ("adaption3", "adaption2", "adaption1", "adaption0", "adaptionU1"):
+        put(name, pack(sd[name + ".weight"]))
+    for i in range(1, 5):
+        w3, b3 = deconv4x4_as_conv3x3(sd[f"deconv_layers{i}.0.weight"], _bn(sd, f"deconv_layers{i}.1"))
+        put(f"up{i}", pack(w3, b3))
+    hc = 64
+    put("heads.conv1", pack(np.concatenate([f(f"{h}.0.weight") for h in LORE_R18_HEAD_ORDER], 0),
+                            np.concatenate([f(f"{h}.0.bias") for h in LORE_R18_HEAD_ORDER], 0)))
+    for h in LORE_R18_HEAD_ORDER:
+        if h == "reg":
+            continue
+        for j in (2, 4, 6):
+            put(f"heads.{h}.{j}", pack(f(f"{h}.{j}.weight"), f(f"{h}.{j}.bias")))
+    w1 = np.zeros((24, 4 * hc, 1, 1), np.float32)
+    b1 = np.zeros(24, np.float32)
+    row = 0
+    for i, (h, c) in enumerate(LORE_SMALL_HEADS):
+        assert LORE_R18_HEAD_ORDER[i] == h
+        last = 2 if h == "reg" else 8
+        w1[row: row + c, hc * i: hc * (i + 1)] = f(f"{h}.{last}.weight")
+        b1[row: row + c] = f(f"{h}.{last}.bias")
+        row += c
+    put("heads.out", pack(w1, b1))
+    for h in ("ax", "cr"):
+        put(f"{h}.out", pack(f(f"{h}.8.weight"), f(f"{h}.8.bias")))
+    return write_blob(t)
+
+
 def pack_lore_processor(sd: Mapping[str, "np.ndarray"]) -> bytes:
     """state_dict of the reference LoreProcessModel (lore/lore_processor.py:399-514) -> engine blob.  Every Linear is
     packed for the split-fp16 GEMM (the cell counts are tiny, the outputs are ROUNDED to integers downstream, so this

@@ -272,4 +272,4 @@ def test_lore_ptn_configuration(post_engine):
     res = task([synth.synthetic_page(7, 400, 600)])
     assert len(res) == 1 and res[0]["polygons"].shape[1] == 8 and res[0]["logi"].shape == (len(res[0]["polygons"]), 4)
     with pytest.raises(RuntimeError):
-        predictors.OcrTableStructureTask(model="Lore", task_type="wireless", state_dict=(sd, psd))
+        predictors.OcrTableStructureTask(model="Lore", task_type="fin", state_dict=(sd, psd))

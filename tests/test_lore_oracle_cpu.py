@@ -281,3 +281,27 @@ def test_pp_det_graph_program_reproduces_the_oracle_on_cpu():
             assert tuple(heads["prob"].shape) == tuple(want.shape) == (2, 1, h, w)
             assert float((tens[meta["fuse"]] - fuse).abs().max()) < 1e-2 * float(fuse.abs().max())
             assert float((heads["prob"] - want).abs().max()) < tol
+
+
+def test_lore_wireless_network_oracle_matches_reference_golden():
+    """oracle/lore_wireless_ref.py vs LoreDetectModel (lore/lore_detector.py) run by oracle/gen_golden_lore_wireless.py."""
+    from oracle import lore_wireless_ref
+
+    g = np.load(os.path.join(GOLDEN, "lore_resnet18_seed0.npz"))
+    out = lore_wireless_ref.lore_resnet18_forward(synth.lore_resnet18_state_dict(0), torch.from_numpy(g["x"]))
+    for k in ("hm", "st", "wh", "ax", "cr", "reg"):
+        np.testing.assert_allclose(out[k].numpy(), g[k], atol=2e-5, rtol=0, err_msg=k)
+
+
+def test_lore_wireless_decode_oracle_matches_reference_golden():
+    """process_detect_output(upper_left=True, wiz_rev=False): the decode in the wireless configuration's frame."""
+    g = np.load(os.path.join(GOLDEN, "lore_resnet18_seed0.npz"))
+    m = synth.lore_planted_maps(4, 192, 192)
+    out = lore_decode_ref.lore_decode(m["hm"], m["reg"], m["wh"], m["st"], m["ax"], m["cr"], g["dec_meta"], upper_left=True, wiz_rev=False)
+    res = g["dec_results"]
+    n = len(g["dec_logi_feat"])
+    assert n > 0 and len(out["polygons"]) == n
+    np.testing.assert_array_equal(out["polygons"], res[:n, :8])
+    np.testing.assert_array_equal(out["scores"], res[:n, 8])
+    np.testing.assert_array_equal(out["dets_feat"], g["dec_dets_feat"])
+    np.testing.assert_allclose(out["logi_feat"], g["dec_logi_feat"], atol=1e-6, rtol=0)

@@ -51,6 +51,25 @@ def test_lore_preprocess_matches_reference():
         np.testing.assert_allclose([x.astype(np.float64).sum(), np.abs(x.astype(np.float64)).sum()], g[f"sum{i}"], rtol=1e-12)
 
 
+def test_lore_wireless_preprocess_matches_reference():
+    """upper_left=True (LoreConfig wireless, processer_lore.py:74-79): the warp anchored at the upper-left corner, 768 x 768."""
+    from oracle import lore_decode_ref
+
+    g = np.load(os.path.join(GOLDEN, "lore_resnet18_seed0.npz"))
+    mean = np.array([0.408, 0.447, 0.470], dtype=np.float32).reshape(1, 1, 3)
+    std = np.array([0.289, 0.274, 0.278], dtype=np.float32).reshape(1, 1, 3)
+    for i, (h, w) in enumerate(g["pre_sizes"]):
+        warped, meta = predictors.lore_preprocess(synth.synthetic_page(3, int(h), int(w)), (768, 768), upper_left=True)
+        np.testing.assert_array_equal(meta, g[f"pre_meta{i}"])
+        x = ((warped / 255. - mean) / std).astype(np.float32).transpose(2, 0, 1)
+        np.testing.assert_array_equal(x[:, 100:164, 200:264], g[f"pre_patch{i}"])
+        np.testing.assert_allclose([x.astype(np.float64).sum(), np.abs(x.astype(np.float64)).sum()], g[f"pre_sum{i}"], rtol=1e-12)
+    for c, sc in (((0, 0), 900.0), ((3, 7), 500.0), ((9, 2), 640.0)):
+        for inv in (False, True):
+            np.testing.assert_array_equal(predictors.lore_affine_upper_left(c, sc, 192, 192, inv),
+                                          lore_decode_ref.upper_left_matrix(np.float32(c), np.float32(sc), 192, 192, inv))
+
+
 def test_picodet_preprocess_matches_reference():
     """cv2.resize on the un-flipped page, then flip + (x * scale - mean) / std in fp32 == OCRPicodetPreProcessor's image."""
     import cv2
