@@ -630,6 +630,73 @@ def block_lore(wl: Cascade, rank, world, dist, args, barrier, peaks, peak_src):
             "roofline": roofline_of(agg, peaks, peak_src, "lore"), "gpu_launches": int(launches * args.steps), "kernels": kernel_table(agg, args.steps)}
 
 
+def block_lore_wireless(wl: Cascade, rank, local_rank, world, dist, args, barrier, peaks, peak_src):
+    """Lore `wireless` (ResNet-18 key-point detector, 768 x 768 upper-left frame, 2-D position embeddings), 16 synthetic table
+    crops per GPU: detect + decode + cell features + position embeddings + processor; e2e through OcrTableStructureTask.__call__."""
+    from pdf_table_b200 import predictors, synth
+
+    dev = torch.device("cuda", local_rank)
+    crops_list = [synth.synthetic_page(rank * 1000 + 700 + i % 4, 900, 768) for i in range(LORE_BATCH)]
+    pre = [predictors.lore_preprocess(c, (768, 768), upper_left=True) for c in crops_list[:4]]
+    imgs_dev = torch.from_numpy(np.stack([pre[i % 4][0] for i in range(LORE_BATCH)])).to(dev)
+    sd = synth.lore_resnet18_state_dict(0)
+    # seeded random weights: calibrate the heat map's bias so that ~150 cells per table pass the 0.2 gate (a trained detector's
+    # count; unshifted, the random heat map saturates the decode's 3000-cell cap and the step would time the processor only)
+    probe = predictors.OcrTableStructureTask(model="Lore", task_type="wireless", device=local_rank, state_dict=(sd, synth.lore_processor_state_dict(0)))
+    hm = probe.predictor.lore_detect_forward_u8(imgs_dev[:4])[..., 0].clamp(1e-6, 1 - 1e-6)
+    peaks_at = torch.nn.functional.max_pool2d(hm[:, None], 3, 1, 1)[:, 0] == hm
+    logit = torch.log(hm / (1 - hm))[peaks_at]
+    kth = float(torch.topk(logit, min(150 * 4, logit.numel())).values[-1])
+    for e in (probe.predictor, probe.processor, probe.post):
+        e.close()
+    sd["hm.8.bias"] = sd["hm.8.bias"] + np.float32(np.log(0.2 / 0.8) - kth)
+    task = predictors.OcrTableStructureTask(model="Lore", task_type="wireless", device=local_rank, host_warp=True,
+                                            state_dict=(sd, synth.lore_processor_state_dict(0)))
+    inv = np.stack([predictors.lore_affine_upper_left([np.float32(0), np.float32(0)], np.float32(pre[i % 4][1][2]), 192, 192, True) for i in range(LORE_BATCH)])
+    maps = torch.empty((LORE_BATCH, 192, 192, 24), dtype=torch.float32, device=dev)
+    det, proc, post = task.predictor, task.processor, task.post
+    engines = (det, proc, post)
+
+    def step_device():
+        det.lore_detect_forward_u8(imgs_dev, out=maps)
+        dec = post.lore_decode(maps, None, None, None, inv, wiz_rev=False, vis_thresh=0.2)
+        feat, offsets = det.lore_cell_features(dec, max_rows=LORE_BATCH * 1024)
+        proc.lore_add_position_embeddings(feat, dec, offsets)
+        return dec, proc.lore_process_forward(feat, offsets)
+
+    l0 = sum(e.launch_count for e in engines)
+    dec, _ = step_device()
+    launches = sum(e.launch_count for e in engines) - l0
+    for _ in range(max(args.warmup, 3) - 1):
+        step_device()
+    cells = int(dec["counts"].sum())
+    dev_ms = timed_steps(step_device, wl.flush_l2, args.steps, barrier)
+    task(crops_list)
+    e2e_ms = timed_loop(lambda: task(crops_list), args.steps, barrier)
+    for e in engines:
+        e.profile_begin()
+    for _ in range(args.steps):
+        wl.flush_l2()
+        step_device()
+    recs = []
+    for e in engines:
+        recs += e.profile_report()
+    agg = aggregate(recs)
+    dev_ms, e2e_ms = max_over_ranks(dist, [dev_ms, e2e_ms], dev)
+    total = LORE_BATCH * world * args.steps
+    out = {"metric": "table_images_per_sec", "value": total / (dev_ms / 1e3), "unit": "images/s", "ms_per_step": dev_ms / args.steps,
+           "scaling": "weak", "higher_is_better": True, "dtype": "f16",
+           "config": {"workload": f"Lore ResNet-18 (wireless) table structure, {LORE_BATCH} synthetic table crops per GPU warped to 768x768",
+                      "cells_per_step": cells, "model_gflop_per_image": det.model_flops / LORE_BATCH / 1e9},
+           "e2e": {"value": total / (e2e_ms / 1e3), "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
+                   "h2d_bytes_per_step": int(LORE_BATCH * 768 * 768 * 3), "d2h_bytes_per_step": int(LORE_BATCH * 8 + 4 + cells * (8 + 4) * 4),
+                   "api": "OcrTableStructureTask(task_type='wireless').__call__ on a list of numpy crops (cv2.warpAffine on the host, dicts out)"},
+           "roofline": roofline_of(agg, peaks, peak_src, "lore_wireless"), "gpu_launches": int(launches * args.steps), "kernels": kernel_table(agg, args.steps)}
+    for e in engines:
+        e.close()
+    return out
+
+
 def block_fp32x(rank, local_rank, world, dist, args, barrier):
     """The same cascade step with precision="fp32x" in the three networks the north star's 1e-3 bound addresses (detector,
     recogniser, Lore detector): the price of the precise mode, device-resident leg only."""
@@ -955,6 +1022,7 @@ def main():
         blocks["rec_sweep"] = block_rec_sweep(wl, rank, world, dist, args, barrier, peaks, peak_src)
         if FULL:
             blocks["lore"] = block_lore(wl, rank, world, dist, args, barrier, peaks, peak_src)
+            blocks["lore_wireless"] = block_lore_wireless(wl, rank, local_rank, world, dist, args, barrier, peaks, peak_src)
             blocks["cascade_fp32x"] = block_fp32x(rank, local_rank, world, dist, args, barrier)
 
     if rank == 0:

@@ -54,6 +54,8 @@ const char* dv_last_error(dv_handle h);
  *                "convnext_vit"  ConvNextViT text-line recogniser (reference model/convnext_vit/
  *                                modeling_convnext_vit.py:20-45)
  *                "lore_dla34"    Lore table-structure detector, DLA-34 + DCNv2 (reference model/lore/lore_dla_34.py:193)
+ *                "lore_resnet18" Lore `wireless` key-point detector, ResNet-18 + transposed-conv up path
+ *                                (reference model/lore/lore_detector.py:148-389)
  *                "centernet_dla34" CenterNet table-structure detector (reference model/center_net/modeling_centernet.py:601)
  *                "picodet"       PicoDet layout detector as a graph program (reference model/picodet/{lcnet,csp_pan,pico_head}.py)
  *                "lore_processor" Lore logical-location transformers (reference model/lore/lore_processor.py:399)
@@ -190,6 +192,10 @@ int dv_lore_gather_logi(dv_handle h, const float* ax, const float* cr, int n, in
  *                 wh0-7, st0-7, 4 pad -- the `layout 1` input of dv_lore_decode.
  * The 256-channel `ax` / `cr` heads are NOT evaluated densely (the reference only gathers them at the selected
  * cells): the 64-channel feature map stays resident in the handle for dv_lore_cell_features.
+ * Model kind "lore_resnet18" (the `wireless` configuration, LoreDetectModel.forward lore/lore_detector.py:353-389) takes the
+ * same calls and returns the same packed map; height, width multiples of 64 (768 x 768 for the configuration); its `ax` /
+ * `cr` heads are evaluated densely up to their last 64-channel hidden maps, which stay resident for dv_lore_cell_features
+ * (the final 1x1 convs run only at the selected cells).
  */
 int dv_lore_detect_forward(dv_handle h, const float* in_nchw_f32, int n, int height, int width, float* maps_out);
 int dv_lore_detect_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, int height, int width, const float* mean3_host,
