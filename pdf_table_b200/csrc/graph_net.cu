@@ -504,6 +504,28 @@ k_softmax_rows(const float* __restrict__ logits, long long M, int ld, int C, flo
     }
 }
 
+// The two SE matrices, one warp per output row: the lanes stride over the row of the weight matrix (coalesced; a thread per
+// row would read w1 / w2 with a stride of a whole row) and the partial sums meet in a shuffle tree.
+__device__ __forceinline__ void se_fc(const float* avg, float* hid, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
+                                      const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ scale_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < R; r += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + r * C + c), avg[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[r] = fmaxf(s + b1[r], 0.f);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += nwarps) {
+        float s = 0.f;
+        for (int r = lane; r < R; r += 32) s = fmaf(__ldg(w2 + c * R + r), hid[r], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) scale_out[c] = fminf(fmaxf((s + b2[c]) * (1.f / 6.f) + 0.5f, 0.f), 1.f);  // F.hardsigmoid
+    }
+}
+
 // SE squeeze: one CTA per image.  avg[c] -> hidden = relu(W1 avg + b1) -> scale[c] = hardsigmoid(W2 hidden + b2)
 template <typename T>
 __global__ void __launch_bounds__(512)
@@ -520,17 +542,7 @@ k_se_scale(const T* __restrict__ in, int HW, int C, const float* __restrict__ w1
         avg[c] = s / static_cast<float>(HW);
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        float s = b1[r];
-        for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], avg[c], s);
-        hid[r] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = b2[c];
-        for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
-        scale[n * C + c] = fminf(fmaxf(s * (1.f / 6.f) + 0.5f, 0.f), 1.f);  // F.hardsigmoid
-    }
+    se_fc(avg, hid, C, R, w1, b1, w2, b2, scale + n * C);
 }
 
 // SE squeeze over a LARGE map (the detector's RSE layers pool 240 x 240 x 96 per page): partial channel sums of kSePoolRows
@@ -579,17 +591,7 @@ k_se_scale_p(const float* __restrict__ partial, int nchunks, int HW, int C, cons
         avg[c] = s / static_cast<float>(HW);
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        float s = b1[r];
-        for (int c = 0; c < C; ++c) s = fmaf(w1[r * C + c], avg[c], s);
-        hid[r] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = b2[c];
-        for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
-        scale[n * C + c] = fminf(fmaxf(s * (1.f / 6.f) + 0.5f, 0.f), 1.f);  // F.hardsigmoid
-    }
+    se_fc(avg, hid, C, R, w1, b1, w2, b2, scale + n * C);
 }
 
 template <typename T>

@@ -23,6 +23,7 @@ namespace dv {
 
 static constexpr int kIGemmThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
 static constexpr int kMaxKB = 224;  // k-blocks per tile whose coordinate deltas are staged in smem (3x3 x 512 channels x 3 split parts = 216)
+static constexpr int kMaxHaloStages = 8;
 static constexpr int kMaxStages = 32;  // TMA -> MMA ring depth.  Small-K layers (BK 16 / 32: 5-16 KB stages) are latency-bound on
                                        // bytes in flight: with the former cap of 8 a Cin=16 conv kept 40 KB per SM in flight
 static constexpr int kBiasSmem = 2048;  // bias values staged in smem (layers with more padded columns read global)
@@ -137,8 +138,9 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
-    __shared__ __align__(8) uint64_t hfull_bar[4];
-    __shared__ __align__(8) uint64_t hempty_bar[4];
+    __shared__ __align__(8) uint64_t hfull_bar[kMaxHaloStages];
+    __shared__ __align__(8) uint64_t hempty_bar[kMaxHaloStages];
+    __shared__ __align__(8) uint64_t bres_bar;  // A_HALO with a resident filter: all weight tiles have landed
     __shared__ uint32_t tmem_base_smem;
     __shared__ int4 s_delta[kMaxKB];
     __shared__ __align__(16) float s_bias[kBiasSmem];  // the layer's bias, staged once (see the epilogue)
@@ -176,10 +178,11 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 8);
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kMaxHaloStages; ++i) {
             ptx::mbar_init(ptx::smem_u32(&hfull_bar[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&hempty_bar[i]), 1);
         }
+        ptx::mbar_init(ptx::smem_u32(&bres_bar), 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA);
         ptx::prefetch_tmap(&p.tmB);
@@ -203,6 +206,13 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             const int tiles_per_img = p.tiles_x * p.tiles_y;
             const int mode = p.mode;
             const int BK = p.BK, BLOCK_N = p.BLOCK_N;
+            if (halo && p.b_resident) {
+                // the whole filter (9 taps x ncb channel blocks, one n-tile) is loaded once and stays: the per-tap weight stream
+                // and its barrier round trips disappear, the ring budget goes to a deeper halo-patch ring
+                const uint32_t bb = ptx::smem_u32(&bres_bar);
+                ptx::mbar_expect_tx(bb, 9u * static_cast<uint32_t>(p.ncb) * b_bytes);
+                for (int t = 0; t < 9 * p.ncb; ++t) ptx::tma_load_2d(ring_base + t * b_bytes, &p.tmB, bb, t * BK, 0);
+            }
             TileIter it(m_tiles_rt);
             int m_tile, n_tile;
             while (it.next(p, m_tile, n_tile)) {
@@ -221,6 +231,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         ptx::mbar_expect_tx(hb, halo_bytes);
                         ptx::tma_load_5d(smem_base + hstage * halo_bytes, &p.tmA, hb, cb * BK, x0 - 1, y0 - 1, img, 0);
                         if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
+                        if (p.b_resident) continue;
                         for (int tap = 0; tap < 9; ++tap) {
                             ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
                             const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
@@ -262,12 +273,48 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             uint32_t acc_phase = 0;
             const uint32_t idesc = ptx::make_idesc_f16_m128(static_cast<uint32_t>(p.BLOCK_N));
             const int k_steps = p.BK >> 4;
+            const bool b_res = halo && p.b_resident;
+            const uint64_t b_res_desc = ptx::make_kmajor_desc(ring_base, row_bytes);
+            if (b_res) {
+                ptx::mbar_wait(ptx::smem_u32(&bres_bar), 0u);
+                ptx::tc_fence_after();
+            }
             TileIter it(m_tiles_rt);
             int m_tile, n_tile;
             while (it.next(p, m_tile, n_tile)) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+                if (b_res) {
+                    // Resident filter: no weight barriers, and every descriptor is the stage's base descriptor plus a constant --
+                    // the issuing thread's own instruction stream is what bounds the small-N layers (ncu, profiles/r4y: 130
+                    // scalar instructions per tap with run-time tap / 3, % 3 and descriptor packing made the thread, not the
+                    // tensor pipe, TMA or the epilogue, the limit), so the tap loop is unrolled with compile-time patch offsets
+                    // (shared-memory addresses are < 256 KB: the 14-bit start-address field never carries).
+                    const uint32_t rb16 = row_bytes >> 4, bt16 = b_bytes >> 4;
+                    uint32_t accum = 0u;
+                    for (int cb = 0; cb < p.ncb; ++cb) {
+                        ptx::mbar_wait(ptx::smem_u32(&hfull_bar[hstage]), hphase);
+                        ptx::tc_fence_after();
+                        const uint64_t a_base = ptx::make_kmajor_desc_sbo(smem_base + hstage * halo_bytes, row_bytes, 16u * row_bytes, 0);
+                        uint64_t b_tap = b_res_desc + static_cast<uint64_t>(static_cast<uint32_t>(cb) * bt16);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t a_tap = a_base + static_cast<uint64_t>(static_cast<uint32_t>((tap / 3) * 16 + tap % 3) * rb16);
+                            for (int k = 0; k < k_steps; ++k) {
+                                ptx::umma_f16_ss(d_tmem, a_tap + 2ull * k, b_tap + 2ull * k, idesc, accum);
+                                accum = 1u;
+                            }
+                            b_tap += static_cast<uint64_t>(static_cast<uint32_t>(p.ncb) * bt16);
+                        }
+                        ptx::umma_commit(ptx::smem_u32(&hempty_bar[hstage]));  // patch free once its 9 x k_steps MMAs retire
+                        if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 if (halo) {
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         ptx::mbar_wait(ptx::smem_u32(&hfull_bar[hstage]), hphase);

@@ -101,25 +101,44 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     // TMA-store epilogue: plain fp16 NHWC outputs (any A mode).  Not for fp32 / replicated / pixel-shuffled / split stores, the
     // arg-max epilogue or device-side row counts (the store would also write the rows past the count).
     static const bool tma_store_env = !(getenv("DV_TMA_STORE") && atoi(getenv("DV_TMA_STORE")) == 0);
-    const bool tma_store = tma_store_env && !es.out_f32 && es.out_mode == OUT_NHWC && es.split_off == 0 && es.arg_out == nullptr &&
-                           es.m_dyn == nullptr && cs.Cout >= 32 && es.out != nullptr;
-    const size_t stg_bytes = tma_store ? 8 * 2 * 2048 : 0;
-    const size_t ring_budget = 206 * 1024 - stg_bytes;
+    bool tma_store = tma_store_env && !es.out_f32 && es.out_mode == OUT_NHWC && es.split_off == 0 && es.arg_out == nullptr &&
+                     es.m_dyn == nullptr && cs.Cout >= 32 && es.out != nullptr;
+    size_t stg_bytes = tma_store ? 8 * 2 * 2048 : 0;
+    size_t ring_budget = 206 * 1024 - stg_bytes;
     size_t ring_bytes = 0;
     if (p.mode == A_HALO) {
         // shared memory: halo-patch ring (18 x 16 pixels x BK channels each) + a ring of per-tap weight tiles
         const size_t halo_bytes = static_cast<size_t>(18) * 16 * row_bytes, b_bytes = static_cast<size_t>(block_n) * row_bytes;
-        int hs = p.ncb > 1 ? 3 : 2;
-        int stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
-        if (stages < 3 && hs > 2) {
-            hs = 2;
-            stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
+        const size_t filter_bytes = 9 * static_cast<size_t>(p.ncb) * b_bytes;
+        if (tma_store && p.n_tiles == 1 && filter_bytes <= 96 * 1024 && (ring_budget - filter_bytes) / halo_bytes < 3 &&
+            (206 * 1024 - filter_bytes) / halo_bytes >= 3) {
+            // a resident filter with a three-deep patch ring beats the store staging (measured on the 64 -> 64 layers)
+            tma_store = false;
+            stg_bytes = 0;
+            ring_budget = 206 * 1024;
         }
-        if (stages > kMaxStages) stages = kMaxStages;
-        if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
-        p.halo_stages = hs;
-        p.num_stages = stages;
-        ring_bytes = hs * halo_bytes + stages * b_bytes;
+        // small filters (one n-tile, <= 96 KB) stay resident for the whole kernel and the ring budget buys a deeper patch ring
+        static const int min_hs = getenv("DV_HALO_MINHS") ? atoi(getenv("DV_HALO_MINHS")) : 3;
+        if (p.n_tiles == 1 && filter_bytes <= 96 * 1024 && static_cast<int>((ring_budget - filter_bytes) / halo_bytes) >= min_hs) {
+            int hs = static_cast<int>((ring_budget - filter_bytes) / halo_bytes);
+            if (hs > kMaxHaloStages) hs = kMaxHaloStages;
+            p.b_resident = 1;
+            p.halo_stages = hs;
+            p.num_stages = 1;
+            ring_bytes = hs * halo_bytes + filter_bytes;
+        } else {
+            int hs = p.ncb > 1 ? 3 : 2;
+            int stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
+            if (stages < 3 && hs > 2) {
+                hs = 2;
+                stages = static_cast<int>((ring_budget - hs * halo_bytes) / b_bytes);
+            }
+            if (stages > kMaxStages) stages = kMaxStages;
+            if (stages < 2) return set_err(e, DV_ERR_UNSUPPORTED, "%s: halo stage too large", name);
+            p.halo_stages = hs;
+            p.num_stages = stages;
+            ring_bytes = hs * halo_bytes + stages * b_bytes;
+        }
     } else {
         const size_t stage_bytes = static_cast<size_t>(128 + block_n) * row_bytes;
         int stages = static_cast<int>(ring_budget / stage_bytes);
@@ -337,9 +356,12 @@ int plan_conv(Engine* e, const Tensor& in, const ConvSpec& cs, const EpiSpec& es
         const uint64_t cb = static_cast<uint64_t>(in.ldc()) * 2;  // bytes between consecutive pixels
         if ((in.ldc() % 8) || (reinterpret_cast<uintptr_t>(in.p) & 15))
             return set_err(e, DV_ERR_UNSUPPORTED, "%s: input slice must be 16-byte aligned (ld %% 8, offset %% 8)", name);
-        static const int halo_env = getenv("DV_HALO") ? atoi(getenv("DV_HALO")) : 0;  // opt-in until its pipeline depth is tuned (profiles/r1f)
+        static const int halo_env = getenv("DV_HALO") ? atoi(getenv("DV_HALO")) : 2;  // streaming-filter halo mode (1) is slower than the patch mode (profiles/r1f, r4x)
         static const int halo_baseoff = getenv("DV_HALO_BASEOFF") ? atoi(getenv("DV_HALO_BASEOFF")) : 0;  // measured on B200: the swizzle is a function of the absolute shared-memory address, shifted starts need NO base offset
-        if (cs.stride == 1 && cs.KH == 3 && cs.KW == 3 && cs.pad == 1 && halo_env && !cs.split) {
+        // DV_HALO: 0 = never, 1 = every 3x3 stride-1 conv, 2 = only where the whole filter fits resident (<= 96 KB, one n-tile)
+        const size_t filter_bytes = 9ull * cin_blocks * ((cs.Cout + 31) / 32 * 32) * 2 * cs.BK;
+        const bool filter_fits = cs.Cout <= 256 && filter_bytes <= 96 * 1024 && (206 * 1024 - filter_bytes) / (288ull * 2 * cs.BK) >= 3;
+        if (cs.stride == 1 && cs.KH == 3 && cs.KW == 3 && cs.pad == 1 && (halo_env == 1 || (halo_env == 2 && filter_fits)) && !cs.split) {
             // halo-patch mode: 16 x 8 output pixels per tile, one {BK, 16, 18} box per channel block
             p.mode = A_HALO;
             p.TH = 16;

@@ -21,6 +21,8 @@ CASES = [
     ("3x3_cout40", 1, 12, 20, 32, 40, 3, 1, 1, False, 0),
     ("3x3_many_tiles", 4, 120, 120, 64, 64, 3, 1, 1, True, 1),
     ("3x3_c16", 1, 24, 40, 16, 32, 3, 1, 1, False, 1),
+    ("3x3_c96_cout32", 2, 40, 56, 96, 32, 3, 1, 1, False, 1),     # PP-OCRv4 det head / neck shape (BK 32, three channel blocks)
+    ("3x3_c64_cout32_odd", 3, 37, 29, 64, 32, 3, 1, 1, False, 0),  # the offset / mask conv of a deformable layer, ragged tiles
 ]
 
 
