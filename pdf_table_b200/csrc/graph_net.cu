@@ -78,14 +78,25 @@ __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 
 // image -> 16 channels at half resolution.  One thread per output pixel; weights [27][16] (tap-major: r, s, c) in smem.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, int Ho, int Wo, float3 mean,
             float3 stdv, float scale, int flip, const float* __restrict__ w, const float* __restrict__ bias, int act,
             T* __restrict__ out, const int32_t* __restrict__ widths) {
     __shared__ float sw[27 * 16];
     __shared__ float sb[16];
+    __shared__ float lut[3][256];  // u8 input: the normalised value of every (channel, byte), evaluated ONCE per CTA with the
+                                   // reference's own operation sequence (a tap otherwise costs two IEEE divisions per channel)
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
+    if (u8) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int ci = i >> 8;
+            float c = static_cast<float>(i & 255);
+            // PP rec (resize_norm_img): x / 255 is a DIVISION there, `scale` carries the divisor; no FMA contraction anywhere
+            c = (flip & 2) ? __fdiv_rn(c, scale) : __fmul_rn(c, scale);
+            lut[ci][i & 255] = __fdiv_rn(__fsub_rn(c, ci == 0 ? mean.x : ci == 1 ? mean.y : mean.z), ci == 0 ? stdv.x : ci == 1 ? stdv.y : stdv.z);
+        }
+    }
     __syncthreads();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo) return;
@@ -104,20 +115,10 @@ k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N
                 v[0] = v[1] = v[2] = 0.f;  // PP rec: zero padding AFTER the normalisation (resize_norm_img)
             } else if (u8) {
                 const uint8_t* ip = u8 + ((static_cast<long long>(n) * H + iy) * W + ix) * 3;
-                float c0 = ip[0], c1 = ip[1], c2 = ip[2];
-                if (flip & 1) {
-                    const float t = c0;
-                    c0 = c2;
-                    c2 = t;
-                }
-                if (flip & 2) {  // PP rec (resize_norm_img): x / 255 is a DIVISION there, `scale` carries the divisor
-                    c0 = __fdiv_rn(c0, scale), c1 = __fdiv_rn(c1, scale), c2 = __fdiv_rn(c2, scale);
-                } else {
-                    c0 = __fmul_rn(c0, scale), c1 = __fmul_rn(c1, scale), c2 = __fmul_rn(c2, scale);
-                }
-                v[0] = __fdiv_rn(__fsub_rn(c0, mean.x), stdv.x);
-                v[1] = __fdiv_rn(__fsub_rn(c1, mean.y), stdv.y);
-                v[2] = __fdiv_rn(__fsub_rn(c2, mean.z), stdv.z);
+                const int b0 = ip[0], b1 = ip[1], b2 = ip[2];
+                v[0] = lut[0][(flip & 1) ? b2 : b0];  // flip & 1: the channel-flipped image (processor_ocr_db_pp.py:124)
+                v[1] = lut[1][b1];
+                v[2] = lut[2][(flip & 1) ? b0 : b2];
             } else {
                 const long long plane = static_cast<long long>(H) * W;
                 const float* ip = f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(iy) * W + ix;
@@ -1173,9 +1174,9 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                     stdv = make_float3(std3[0], std3[1], std3[2]);
                 }
                 e->launch_begin("k_stem3x3s2", "conv1", 2.0 * total * 27 * 16, total * (12.0 * (in_u8 ? 1 : 4) + 32.0));
-                if (pr) k_stem3x3s2<float><<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
+                if (pr) k_stem3x3s2<float><<<grid_for(total, 256), 256, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
                                                                                 F32(out, 0), widths);
-                else k_stem3x3s2<__half><<<grid_for(total, 128), 128, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
+                else k_stem3x3s2<__half><<<grid_for(total, 256), 256, 0, s>>>(in_u8, in_nchw, N, H, W, out.H, out.W, mean, stdv, scale, flip, op.f0, op.f1, op.act,
                                                                               out.p, widths);
                 e->launch_end();
                 break;

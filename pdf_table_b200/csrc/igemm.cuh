@@ -292,6 +292,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                     // tensor pipe, TMA or the epilogue, the limit), so the tap loop is unrolled with compile-time patch offsets
                     // (shared-memory addresses are < 256 KB: the 14-bit start-address field never carries).
                     const uint32_t rb16 = row_bytes >> 4, bt16 = b_bytes >> 4;
+                    // (two alternating accumulators were tried here: no change -- a chain of dependent N = 32 MMAs is not the limit)
                     uint32_t accum = 0u;
                     for (int cb = 0; cb < p.ncb; ++cb) {
                         ptx::mbar_wait(ptx::smem_u32(&hfull_bar[hstage]), hphase);

@@ -44,11 +44,26 @@ __device__ __forceinline__ void store8_split(__half* p, long long lo, const floa
 // ---------------------------------------------------------------------------------------------- stem input
 // in: uint8 HWC [N,H,W,3] or fp32 NCHW [N,3,H,W] (already normalised) -> fp16 [N, H+6, W+8, 8], interior at (+3,+3).
 // The u8 path mirrors numpy: (x / 255. - mean) / std evaluated in float64, then .astype(float32).
+constexpr int kStemPix = 8;  // pixels per thread: the per-CTA table of 768 float64 normalisations is amortised over 2048 pixels
 __global__ void __launch_bounds__(256)
 k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N, int H, int W, double3 mean, double3 stdv,
                int flip, __half* __restrict__ out, long long lo, int cpp) {
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    // u8 input: (x / 255. - mean) / std in float64 -> float32 for every (channel, byte) once per CTA (three double divisions
+    // per pixel otherwise: the kernel ran at a quarter of its HBM bound)
+    __shared__ float lut[3][256];
+    if (u8) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int ci = i >> 8;
+            const double m = ci == 0 ? mean.x : ci == 1 ? mean.y : mean.z, sd = ci == 0 ? stdv.x : ci == 1 ? stdv.y : stdv.z;
+            lut[ci][i & 255] = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(static_cast<double>(i & 255), 255.0), m), sd));
+        }
+        __syncthreads();
+    }
     const long long total = static_cast<long long>(N) * H * W;
+    const long long base = static_cast<long long>(blockIdx.x) * (256 * kStemPix) + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < kStemPix; ++it) {
+    const long long idx = base + static_cast<long long>(it) * 256;
     if (idx >= total) return;
     const int x = static_cast<int>(idx % W);
     const int y = static_cast<int>((idx / W) % H);
@@ -56,15 +71,10 @@ k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, in
     float v0, v1, v2;
     if (u8) {
         const uint8_t* ip = u8 + idx * 3;
-        double c0 = ip[0], c1 = ip[1], c2 = ip[2];
-        if (flip) {
-            const double t = c0;
-            c0 = c2;
-            c2 = t;
-        }
-        v0 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c0, 255.0), mean.x), stdv.x));
-        v1 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c1, 255.0), mean.y), stdv.y));
-        v2 = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(c2, 255.0), mean.z), stdv.z));
+        const int b0 = ip[0], b1 = ip[1], b2 = ip[2];
+        v0 = lut[0][flip ? b2 : b0];
+        v1 = lut[1][b1];
+        v2 = lut[2][flip ? b0 : b2];
     } else {
         const long long plane = static_cast<long long>(H) * W;
         const float* ip = f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(y) * W + x;
@@ -93,6 +103,7 @@ k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, in
         if (cpp == 8) *reinterpret_cast<uint4*>(op + lo) = u;
         else *reinterpret_cast<uint2*>(op + lo) = make_uint2(u.x, u.y);
     }
+    }
 }
 
 int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H, int W, const float* mean3, const float* std3,
@@ -105,7 +116,7 @@ int op_img_to_stem8(Engine* e, const uint8_t* u8, const float* f32, int N, int H
         s = make_double3(std3[0], std3[1], std3[2]);
     }
     e->launch_begin("k_img_to_stem8", "pre", 0.0, total * ((u8 ? 3.0 : 12.0) + 2.0 * cpp));
-    k_img_to_stem8<<<grid_for(total, 256), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out, lo, cpp);
+    k_img_to_stem8<<<grid_for(total, 256 * kStemPix), 256, 0, e->stream>>>(u8, f32, N, H, W, m, s, flip, out, lo, cpp);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
