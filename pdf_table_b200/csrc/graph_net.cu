@@ -100,7 +100,10 @@ k_stem3x3s2(const uint8_t* __restrict__ u8, const float* __restrict__ f32, int N
     __syncthreads();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo) return;
-    const int ox = static_cast<int>(idx % Wo), oy = static_cast<int>((idx / Wo) % Ho), n = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho));
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (a launch covers < 2^32 pixels)
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = sb[c];
@@ -147,8 +150,9 @@ k_dwconv(const T* __restrict__ in, int N, int H, int W, int C, int ldi, int k, i
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
@@ -207,7 +211,7 @@ k_dwconv_row(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
     const int wq = (Wo + P - 1) / P;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * wq * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
+    const int c8 = static_cast<int>(idx % cv);  // 64-bit decode kept here: the 32-bit form made ptxas schedule this kernel 15 % slower (profiles/r5i)
     long long t = idx / cv;
     const int ox0 = static_cast<int>(t % wq) * P;
     t /= wq;
@@ -281,8 +285,9 @@ k_dwconv_c2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi, 
     const int wq = (Wo + P - 1) / P, hq = (Ho + R - 1) / R;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * hq * wq * cp) return;
-    const int c2 = static_cast<int>(idx % cp);
-    long long t = idx / cp;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c2 = static_cast<int>(t % cp);
+    t /= cp;
     const int ox0 = static_cast<int>(t % wq) * P;
     t /= wq;
     const int oy0 = static_cast<int>(t % hq) * R, n = static_cast<int>(t / hq);
@@ -346,8 +351,9 @@ k_avgpool(const T* __restrict__ in, int N, int H, int W, int C, int ldi, int kh,
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
@@ -372,8 +378,9 @@ k_unfold3(const T_* __restrict__ in, int N, int T, int C, int ldi, T_* __restric
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * T * 3 * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long r = idx / cv;
+    unsigned r = static_cast<unsigned>(idx);  // 32-bit index decode
+    const int c8 = static_cast<int>(r % cv);
+    r /= cv;
     const int tap = static_cast<int>(r % 3);
     r /= 3;
     const int t = static_cast<int>(r % T);
@@ -602,9 +609,10 @@ k_se_apply(const T* __restrict__ in, long long total8, int HW, int C, const floa
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= total8) return;
     const int cv = C >> 3;
-    const int c8 = static_cast<int>(idx % cv);
-    const long long pix = idx / cv;
-    const int n = static_cast<int>(pix / HW);
+    const unsigned i32 = static_cast<unsigned>(idx);  // 32-bit index decode (a launch covers < 2^32 work items)
+    const int c8 = static_cast<int>(i32 % cv);
+    const long long pix = i32 / cv;
+    const int n = static_cast<int>((i32 / cv) / HW);
     float v[8];
     ld8(in + idx * 8, v);
     const float* sp = scale + n * C + c8 * 8;
@@ -619,8 +627,9 @@ k_up2(const T* __restrict__ in, int N, int h, int w, int C, int ldi, int Ho, int
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho), n = static_cast<int>(t / Ho);
@@ -999,12 +1008,13 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         const std::string wn = "w" + std::to_string(op.w);
         const BlobTensor* w = e->find(wn + ".w");
         const BlobTensor* b = e->find(wn + ".b");
-        // the packed K axis is padded to a multiple of 16 (weights.cin_pad_of); the A operand keeps its own width, the TMA unit
-        // zero-fills the columns beyond it
+        // the packed K axis is padded to a multiple of 16 (weights.cin_pad_of) or, for the wide layers, of 64 (pp_rec_graph.
+        // _gemm_weight: 64-wide k-blocks = 128-byte TMA rows and half the barrier round trips); the A operand keeps its own
+        // width, the TMA unit zero-fills the columns beyond it
         const int kw_total = w ? static_cast<int>(w->dims[1]) : 0;
         const int kpad = m->precise ? kw_total / 3 : kw_total;  // fp32x: [W_hi | W_lo | W_hi], each Kp wide
         if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != op.out_c || kpad < op.in_c ||
-            (m->precise ? (kw_total != 3 * kpad || kpad - op.in_c >= 64) : (kpad - op.in_c >= 16)) || (kpad % 16))
+            (m->precise ? kw_total != 3 * kpad : false) || kpad - op.in_c >= 64 || (kpad % 16))
             return set_err(e, DV_ERR_WEIGHTS, "graph: bad 1x1 weights '%s' (want [%d,%d])", wn.c_str(), op.out_c, op.in_c);
         ConvSpec cs;
         cs.KH = cs.KW = 1;

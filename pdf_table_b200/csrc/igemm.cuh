@@ -24,6 +24,7 @@ namespace dv {
 static constexpr int kIGemmThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quadrant)
 static constexpr int kMaxKB = 224;  // k-blocks per tile whose coordinate deltas are staged in smem (3x3 x 512 channels x 3 split parts = 216)
 static constexpr int kMaxHaloStages = 8;
+static constexpr int kMaxAccStages = 8;  // TMEM accumulator ring: 512 columns / the n-tile's (power-of-two) width, 2..8 deep
 static constexpr int kMaxStages = 32;  // TMA -> MMA ring depth.  Small-K layers (BK 16 / 32: 5-16 KB stages) are latency-bound on
                                        // bytes in flight: with the former cap of 8 a Cin=16 conv kept 40 KB per SM in flight
 static constexpr int kBiasSmem = 2048;  // bias values staged in smem (layers with more padded columns read global)
@@ -136,8 +137,8 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tfull_bar[2];
-    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ __align__(8) uint64_t tfull_bar[kMaxAccStages];
+    __shared__ __align__(8) uint64_t tempty_bar[kMaxAccStages];
     __shared__ __align__(8) uint64_t hfull_bar[kMaxHaloStages];
     __shared__ __align__(8) uint64_t hempty_bar[kMaxHaloStages];
     __shared__ __align__(8) uint64_t bres_bar;  // A_HALO with a resident filter: all weight tiles have landed
@@ -159,6 +160,10 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
     const uint32_t ring_base = smem_base + (halo ? static_cast<uint32_t>(p.halo_stages) * halo_bytes : 0u);
     const int num_stages = p.num_stages;
     const int num_kb = p.num_kb;
+    // accumulator ring: the epilogue of a tile (TMEM load, activation, staging, TMA store) is a ~2 us latency chain; with two
+    // accumulators a small-K tile (one or two MMAs) waited for it -- narrow n-tiles get up to eight
+    const int acc_stages = p.acc_stages;
+    const uint32_t acc_stride = 512u / static_cast<uint32_t>(acc_stages);
     // data-dependent row count (A_FLAT): every role derives the same tile range from it
     const int M_rows = p.m_dyn != nullptr ? min(__ldg(p.m_dyn), p.M) : p.M;
     const int m_tiles_rt = p.m_dyn != nullptr ? (M_rows + 127) >> 7 : p.m_tiles;
@@ -174,7 +179,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::mbar_init(ptx::smem_u32(&full_bar[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&empty_bar[i]), 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxAccStages; ++i) {
             ptx::mbar_init(ptx::smem_u32(&tfull_bar[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&tempty_bar[i]), 8);
         }
@@ -284,7 +289,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             while (it.next(p, m_tile, n_tile)) {
                 ptx::mbar_wait(ptx::smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_stride;
                 if (b_res) {
                     // Resident filter: no weight barriers, and every descriptor is the stage's base descriptor plus a constant --
                     // the issuing thread's own instruction stream is what bounds the small-N layers (ncu, profiles/r4y: 130
@@ -312,8 +317,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
                     }
                     ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
+                    if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
                     continue;
                 }
                 if (halo) {
@@ -339,8 +343,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                         if (++hstage == p.halo_stages) { hstage = 0; hphase ^= 1u; }
                     }
                     ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
+                    if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
                     continue;
                 }
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -358,8 +361,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
                     if (++stage == num_stages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(ptx::smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -426,7 +428,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::mbar_wait(ptx::smem_u32(&tfull_bar[acc]), acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                   static_cast<uint32_t>(acc) * 256u;
+                                   static_cast<uint32_t>(acc) * acc_stride;
             // arg-max epilogue: each of the two warps of a quadrant keeps the first maximum of ITS 32-column chunks (visited
             // in ascending order); the pair is merged after the last n-tile (ties -> lower index = torch.argmax)
             // Software-pipelined over 32-column chunks: the tcgen05.ld of the next chunk is in flight while the current
@@ -668,8 +670,7 @@ conv_igemm_tcgen05(const __grid_constant__ IGemmParams p) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[acc]));
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     }
 

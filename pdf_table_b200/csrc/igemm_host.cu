@@ -93,10 +93,16 @@ static int finish_plan(Engine* e, ConvPlan* plan, const ConvSpec& cs, const EpiS
     if (cs.Cout <= 256) {
         block_n = (cs.Cout + 31) / 32 * 32;
     } else {
-        block_n = (cs.Cout % 256 == 0 || cs.Cout > 1024) ? 256 : 128;
+        // 256-wide n-tiles unless 128-wide ones waste fewer padded columns (360 -> 3 x 128; 480 -> 2 x 256: the A tile is re-read
+        // per n-tile and a 128-wide MMA leaves the issuing thread as little time per k-block as it needs itself)
+        const int waste256 = (cs.Cout + 255) / 256 * 256 - cs.Cout, waste128 = (cs.Cout + 127) / 128 * 128 - cs.Cout;
+        block_n = (waste256 <= waste128 || cs.Cout > 1024) ? 256 : 128;
     }
     p.BLOCK_N = block_n;
     p.n_tiles = (cs.Cout + block_n - 1) / block_n;
+    static const int acc_env = getenv("DV_ACC_STAGES") ? atoi(getenv("DV_ACC_STAGES")) : 0;
+    p.acc_stages = block_n <= 64 ? 8 : block_n <= 128 ? 4 : 2;
+    if (acc_env == 2 || acc_env == 4 || acc_env == 8) p.acc_stages = std::min(p.acc_stages, acc_env);
     const int row_bytes = 2 * cs.BK;
     // TMA-store epilogue: plain fp16 NHWC outputs (any A mode).  Not for fp32 / replicated / pixel-shuffled / split stores, the
     // arg-max epilogue or device-side row counts (the store would also write the rows past the count).

@@ -34,6 +34,7 @@ struct IGemmParams {
     int BK;         // 64 / 32 / 16 fp16 per k-block (row_bytes = 2*BK = swizzle span)
     int num_stages;
     int halo_stages;  // A_HALO: depth of the halo-patch ring (each 18*16*2*BK bytes)
+    int acc_stages;   // TMEM accumulator ring depth: 2 (n-tile > 128 columns), 4 (> 64) or 8
     int b_resident;   // A_HALO: all 9 * ncb weight tiles stay in shared memory for the whole kernel (one n-tile, small filter)
     int ncb;          // A_HALO: channel blocks (Cin_pad / BK); k-block index of (tap, cb) = tap * ncb + cb
     int desc_base_off;  // A_HALO: set the UMMA descriptor base-offset field from the start address

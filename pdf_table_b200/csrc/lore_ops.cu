@@ -65,9 +65,10 @@ k_img_to_stem8(const uint8_t* __restrict__ u8, const float* __restrict__ f32, in
     for (int it = 0; it < kStemPix; ++it) {
     const long long idx = base + static_cast<long long>(it) * 256;
     if (idx >= total) return;
-    const int x = static_cast<int>(idx % W);
-    const int y = static_cast<int>((idx / W) % H);
-    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (a launch covers < 2^32 pixels)
+    const int x = static_cast<int>(t % W);
+    t /= W;
+    const int y = static_cast<int>(t % H), n = static_cast<int>(t / H);
     float v0, v1, v2;
     if (u8) {
         const uint8_t* ip = u8 + idx * 3;
@@ -129,8 +130,9 @@ k_maxpool2x2(const __half* __restrict__ in, int N, int H, int W, int C, int ldi,
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -154,8 +156,9 @@ k_maxpool2x2_split(const __half* __restrict__ in, int N, int H, int W, int C, in
     const int cv = C >> 3, Ho = H >> 1, Wo = W >> 1;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -384,8 +387,9 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -433,14 +437,94 @@ k_up_dw_add(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, 
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * ldo + c8 * 8) = o;
 }
 
+// Same operation, one (output-phase class, channel group) per thread: an output pixel (m f + py, x f + px) always uses the same 2 x 2
+// filter taps of its class, so the class's 4 x 8 weights stay in registers while the thread walks kUpPix input-grid positions.
+// The per-pixel kernel above spent 8 of its 14 memory instructions re-fetching those weights (2.0 TB/s of 6.5).
+constexpr int kUpPix = 4;
+__global__ void __launch_bounds__(256)
+k_up_dw_add_cls(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, const float* __restrict__ wt, int f,
+                const __half* __restrict__ skip, int lds, __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3, lanes = 256 / cv, k2 = 2 * f, pad = f >> 1, Wo = w * f, Ho = h * f;
+    const int c8 = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const int py = blockIdx.y / f, px = blockIdx.y - py * f;
+    const int dy = py >= pad ? 1 : 0, dx = px >= pad ? 1 : 0;
+    const int ky0 = (py + pad) - dy * f, kx0 = (px + pad) - dx * f;  // taps (ky0 + a f, kx0 + b f) meet inputs (m + dy - a, x + dx - b)
+    float wr[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const float4* wp = reinterpret_cast<const float4*>(wt + (static_cast<long long>(ky0 + a * f) * k2 + kx0 + b * f) * C + c8 * 8);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            wr[a][b][0] = w0.x, wr[a][b][1] = w0.y, wr[a][b][2] = w0.z, wr[a][b][3] = w0.w;
+            wr[a][b][4] = w1.x, wr[a][b][5] = w1.y, wr[a][b][6] = w1.z, wr[a][b][7] = w1.w;
+        }
+    const long long total = static_cast<long long>(N) * h * w;
+    if (lane >= lanes) return;
+#pragma unroll 2
+    for (int it = 0; it < kUpPix; ++it) {
+        const long long p = (static_cast<long long>(blockIdx.x) * kUpPix + it) * lanes + lane;
+        if (p >= total) return;
+        unsigned t = static_cast<unsigned>(p);  // 32-bit index decode
+        const int x = static_cast<int>(t % w);
+        t /= w;
+        const int m = static_cast<int>(t % h), n = static_cast<int>(t / h);
+        const long long opix = (static_cast<long long>(n) * Ho + m * f + py) * Wo + x * f + px;
+        // all five loads are issued before the first use (ncu: with the bounds checks as branches every load was waited for on
+        // its own); a tap outside the image reads a clamped address and gets a zero weight (fma(v, 0, acc) == acc)
+        uint4 us = make_uint4(0u, 0u, 0u, 0u), ui[2][2];
+        float ok[2][2];
+        if (skip != nullptr) us = __ldg(reinterpret_cast<const uint4*>(skip + opix * lds + c8 * 8));
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int iy = m + dy - a, ix = x + dx - b;
+                ok[a][b] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? 1.f : 0.f;
+                const int cy = min(max(iy, 0), h - 1), cx = min(max(ix, 0), w - 1);
+                ui[a][b] = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(n) * h + cy) * w + cx) * ldi + c8 * 8));
+            }
+        float acc[8];
+        {
+            const __half2* hh = reinterpret_cast<const __half2*>(&us);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 v = __half22float2(hh[i]);
+                acc[2 * i] = v.x;
+                acc[2 * i + 1] = v.y;
+            }
+        }
+        // same accumulation order as k_up_dw_add: a = 0, 1 over b = 0, 1
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const __half2* hh = reinterpret_cast<const __half2*>(&ui[a][b]);
+                const float g = ok[a][b];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 v = __half22float2(hh[i]);
+                    acc[2 * i] = fmaf(v.x, wr[a][b][2 * i] * g, acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(v.y, wr[a][b][2 * i + 1] * g, acc[2 * i + 1]);
+                }
+            }
+        uint4 o;
+        __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ho[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        *reinterpret_cast<uint4*>(out + opix * ldo + c8 * 8) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_up_dw_add_split(const __half* __restrict__ in, int N, int h, int w, int C, int ldi, long long loi, const float* __restrict__ wt, int f,
                   const __half* __restrict__ skip, int lds, long long los, __half* __restrict__ out, int ldo, long long loo) {
     const int cv = C >> 3, Ho = h * f, Wo = w * f, k2 = 2 * f, pad = f >> 1;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * cv) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -480,8 +564,17 @@ int op_up_dw_add(Engine* e, const Tensor& in, const float* wt, int f, const Tens
         return 0;
     }
     e->launch_begin("k_up_dw_add", layer, 8.0 * (double)out.elems(), 2.0 * ((double)in.elems() + 2.0 * (double)out.elems()));
-    k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.p ? skip.ldc() : 0, out.p,
-                                                           out.ldc());
+    static const bool cls_env = !(getenv("DV_UPCLS") && atoi(getenv("DV_UPCLS")) == 0);
+    const int cv = in.C / 8;
+    if (cls_env && cv <= 256 && (256 % cv) == 0) {
+        const long long per_cta = static_cast<long long>(256 / cv) * kUpPix;
+        const long long ctas = (static_cast<long long>(in.N) * in.H * in.W + per_cta - 1) / per_cta;
+        k_up_dw_add_cls<<<dim3(static_cast<unsigned>(ctas), f * f), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p,
+                                                                                      skip.p ? skip.ldc() : 0, out.p, out.ldc());
+    } else {
+        k_up_dw_add<<<grid_for(total, 256), 256, 0, e->stream>>>(in.p, in.N, in.H, in.W, in.C, in.ldc(), wt, f, skip.p, skip.p ? skip.ldc() : 0, out.p,
+                                                               out.ldc());
+    }
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;
@@ -493,8 +586,9 @@ k_copy_slice(const __half* __restrict__ in, long long pixels, int C, int ldi, __
     const int cv = C >> 3;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= pixels * cv) return;
-    const long long px = idx / cv;
-    const int c8 = static_cast<int>(idx % cv);
+    const unsigned i32 = static_cast<unsigned>(idx);  // 32-bit index decode
+    const long long px = i32 / cv;
+    const int c8 = static_cast<int>(i32 % cv);
     *reinterpret_cast<uint4*>(out + px * ldo + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(in + px * ldi + c8 * 8));
 }
 

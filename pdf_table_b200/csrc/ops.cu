@@ -125,8 +125,9 @@ __global__ void k_maxpool3x3s2(const __half* __restrict__ in, int N, int H, int 
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -162,8 +163,9 @@ __global__ void k_maxpool3x3s2_split(const __half* __restrict__ in, int N, int H
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * Ho * Wo * cv;
     if (idx >= total) return;
-    const int c8 = static_cast<int>(idx % cv);
-    long long t = idx / cv;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c8 = static_cast<int>(t % cv);
+    t /= cv;
     const int ox = static_cast<int>(t % Wo);
     t /= Wo;
     const int oy = static_cast<int>(t % Ho);
@@ -294,8 +296,9 @@ __global__ void k_nchw_f32_to_nhwc_f16(const float* __restrict__ in, int N, int 
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * C * H * W;
     if (idx >= total) return;
-    const int c = static_cast<int>(idx % C);
-    long long t = idx / C;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int c = static_cast<int>(t % C);
+    t /= C;
     const int x = static_cast<int>(t % W);
     t /= W;
     const int y = static_cast<int>(t % H);
@@ -307,8 +310,9 @@ __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * C * H * W;
     if (idx >= total) return;
-    const int x = static_cast<int>(idx % W);
-    long long t = idx / W;
+    unsigned t = static_cast<unsigned>(idx);  // 32-bit index decode (every launch covers < 2^32 work items): a 64-bit division is ~100 SASS instructions
+    const int x = static_cast<int>(t % W);
+    t /= W;
     const int y = static_cast<int>(t % H);
     t /= H;
     const int c = static_cast<int>(t % C);

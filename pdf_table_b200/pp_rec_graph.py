@@ -68,6 +68,9 @@ def _pad_to(a: np.ndarray, axis: int, n: int) -> np.ndarray:
 
 def _gemm_weight(b: _Builder, w2d: np.ndarray, bias: np.ndarray, pa=None) -> int:
     """[Cout, K] fp32 (+bias) -> packed 1x1 weight of the executor (fp32x builders: the split-fp16 triple [W_hi | W_lo | W_hi])."""
+    if not getattr(b, "precise", False) and w2d.shape[1] >= 128 and w2d.shape[1] % 64:
+        # wide layers: K padded to whole 64-channel k-blocks (240 -> 256, 480 -> 512); the executor's TMA zero-fills the A columns
+        w2d = _pad_to(w2d, 1, (w2d.shape[1] + 63) // 64 * 64)
     wp, bp = W.pack_split_linear(w2d, bias) if getattr(b, "precise", False) else W.pack_conv(w2d[:, :, None, None], bias)
     arrays = {"w": wp, "b": bp}
     if pa is not None:
