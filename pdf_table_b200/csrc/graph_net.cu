@@ -1192,9 +1192,13 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 break;
             }
             case OP_DW: {
+                static const bool profile_layers = getenv("DV_PROFILE_LAYERS") != nullptr;  // per-shape labels for tools/cascade_profile.py
                 const long long total = static_cast<long long>(N) * out.H * out.W * (op.in_c / 8);
                 // flops = 0: a depthwise conv is judged against the HBM roofline (k * k MACs per 4 bytes moved)
-                e->launch_begin("k_dwconv", "dw", 0.0, total * 8 * 2.0 * (1.0 + 1.0 * (op.sh() * op.sw())));
+                e->launch_begin("k_dwconv", profile_layers ? "dw c" + std::to_string(op.in_c) + " k" + std::to_string(op.k) + " s" + std::to_string(op.sh()) + "x" +
+                                                                  std::to_string(op.sw()) + " @" + std::to_string(out.H) + "x" + std::to_string(out.W)
+                                                            : std::string("dw"),
+                                0.0, total * 8 * 2.0 * (1.0 + 1.0 * (op.sh() * op.sw())));
                 static const bool row_kernel = !(getenv("DV_DWROW") && atoi(getenv("DV_DWROW")) == 0);
                 static const int dw_mode = getenv("DV_DWMODE") ? atoi(getenv("DV_DWMODE")) : 1;  // 1: k_dwconv_row (default), 2: k_dwconv_c2 (2x slower on the B200: 4-byte loads), 0: k_dwconv
                 if (pr) {
