@@ -63,7 +63,15 @@ def run_program(blob: Dict[str, np.ndarray], x: torch.Tensor, fp16_activations: 
             st = stride if stride < 256 else (stride & 255, stride >> 8)
             out = post_affine(_act(F.conv2d(src, wk, wt(w, "db"), stride=st, padding=k // 2, groups=in_c), act), w)
         elif code in (OP_PW, OP_HEAD, OP_CTC):  # w fp16 [Cout][Cin_pad], b fp32 padded
-            wk = wt(w, "w")[:, :in_c].reshape(-1, in_c, 1, 1)
+            wk = wt(w, "w")
+            if code == OP_PW and k > 1:  # k pixels per GEMM row against diag(w, ..., w): every diagonal block is the layer's matrix
+                full = wk[: k * out_c, : k * in_c]
+                for j in range(k):
+                    assert torch.equal(full[j * out_c:(j + 1) * out_c, j * in_c:(j + 1) * in_c], full[:out_c, :in_c]), "packed 1x1: unequal blocks"
+                assert float(full.abs().sum()) == k * float(full[:out_c, :in_c].abs().sum()), "packed 1x1: off-diagonal weights"
+                assert (n * src.shape[2] * src.shape[3]) % k == 0 and in_coff == 0 and out_coff == 0
+                wk = full[:out_c]
+            wk = wk[:, :in_c].reshape(-1, in_c, 1, 1)
             out = F.conv2d(src, wk, wt(w, "b")[:wk.shape[0]])
             if code == OP_PW and aux >= 0:
                 out = out + tens[aux]

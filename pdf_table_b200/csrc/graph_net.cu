@@ -1013,14 +1013,21 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
         // width, the TMA unit zero-fills the columns beyond it
         const int kw_total = w ? static_cast<int>(w->dims[1]) : 0;
         const int kpad = m->precise ? kw_total / 3 : kw_total;  // fp32x: [W_hi | W_lo | W_hi], each Kp wide
-        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != op.out_c || kpad < op.in_c ||
-            (m->precise ? kw_total != 3 * kpad : false) || kpad - op.in_c >= 64 || (kpad % 16))
-            return set_err(e, DV_ERR_WEIGHTS, "graph: bad 1x1 weights '%s' (want [%d,%d])", wn.c_str(), op.out_c, op.in_c);
+        // OP_PW with k > 1: k consecutive pixels per GEMM row against diag(w, ..., w) (pp_rec_graph.pw_pack_factor) -- a pure
+        // re-interpretation of the dense NHWC buffers as [M / k, k * C]
+        const int pack = (op.code == OP_PW && op.k > 1) ? op.k : 1;
+        if (pack > 1 && (m->precise || op.in_coff || op.out_coff || in.C != op.in_c || out.C != op.out_c || op.aux >= 0 ||
+                         (static_cast<long long>(N) * in.H * in.W) % pack))
+            return set_err(e, DV_ERR_UNSUPPORTED, "graph: packed 1x1 '%s' needs dense whole tensors, no residual and a pixel count divisible by %d", wn.c_str(), pack);
+        const int kin = op.in_c * pack, nout = op.out_c * pack;
+        if (!w || !b || w->dtype != 1 || b->dtype != 0 || w->ndim != 2 || static_cast<int>(w->dims[0]) != nout || kpad < kin ||
+            (m->precise ? kw_total != 3 * kpad : false) || kpad - kin >= 64 || (kpad % 16))
+            return set_err(e, DV_ERR_WEIGHTS, "graph: bad 1x1 weights '%s' (want [%d,%d])", wn.c_str(), nout, kin);
         ConvSpec cs;
         cs.KH = cs.KW = 1;
-        cs.Cin = op.in_c;
+        cs.Cin = kin;
         cs.Cin_pad = kw_total;
-        cs.Cout = op.out_c;
+        cs.Cout = nout;
         cs.BK = (kpad % 64 == 0) ? 64 : (kpad % 32 == 0) ? 32 : 16;
         cs.w = reinterpret_cast<const __half*>(w->dptr);
         cs.bias = reinterpret_cast<const float*>(b->dptr);
@@ -1035,7 +1042,7 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             es.out_f32 = 1;
         } else {
             es.out = out.p;
-            es.out_ld = out.C;
+            es.out_ld = out.C * pack;
             es.out_coff = op.out_coff;
             es.out_f32 = m->precise ? 1 : 0;
             es.post_affine = op.has_pa;
@@ -1059,10 +1066,11 @@ int build(Engine* e, GraphNet* m, int N, int H, int W) {
             m->flops += op.plan.flops;
             continue;
         }
-        const int M = N * in.H * in.W;
-        DV_TRY(plan_linear(e, in.p + op.in_coff, M, op.in_c, cs, es, &op.plan, wn.c_str(), in.C));
+        const int M = N * in.H * in.W / pack;
+        DV_TRY(plan_linear(e, in.p + op.in_coff, M, kin, cs, es, &op.plan, wn.c_str(), in.C * pack));
         m->mem.push_back(e->owned.back());
         e->owned.pop_back();
+        op.plan.flops /= pack;  // the off-diagonal zero blocks are not algorithmic work
         m->flops += op.plan.flops;
     }
     return 0;

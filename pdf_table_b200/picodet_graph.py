@@ -58,9 +58,23 @@ def _bn(sd, p):
     return {k: W._np(sd[f"{p}.{k}"]) for k in ("weight", "bias", "running_mean", "running_var")}
 
 
-def _pw(b: _Builder, sd, conv_key, bn_prefix, bias_key=None):
-    w, bias = W.pack_conv(_f(sd, conv_key), None if bias_key is None else _f(sd, bias_key), None if bn_prefix is None else _bn(sd, bn_prefix))
-    return b.weight(w=w, b=bias)
+def _pw(b: _Builder, sd, conv_key, bn_prefix, bias_key=None, pack: int = 1):
+    """1x1 conv + folded BN.  pack > 1: the block-diagonal weight of `pack` consecutive pixels per GEMM row (OP_PW with k = pack;
+    see pp_rec_graph.pw_pack_factor for why the 16- / 32-channel layers run that way)."""
+    bias_in, bn = None if bias_key is None else _f(sd, bias_key), None if bn_prefix is None else _bn(sd, bn_prefix)
+    if pack == 1:
+        w, bias = W.pack_conv(_f(sd, conv_key), bias_in, bn)
+        return b.weight(w=w, b=bias)
+    cout, cin = (int(v) for v in _f(sd, conv_key).shape[:2])
+    w32, b32, _ = W.conv_matrix_f32(_f(sd, conv_key), bias_in, bn)
+    wd = np.zeros((pack * cout, pack * cin), np.float32)
+    for j in range(pack):
+        wd[j * cout:(j + 1) * cout, j * cin:(j + 1) * cin] = w32[:, :cin]
+    return b.weight(w=wd.astype(np.float16), b=W.pad_bias(np.tile(b32[:cout], pack)))
+
+
+def pw_pack(cin: int, cout: int) -> int:
+    return 64 // cin if (cin <= 32 and cin % 16 == 0 and cout * (64 // cin) <= 256) else 1
 
 
 def _dw(b: _Builder, sd, conv_key, bn_prefix):
@@ -96,7 +110,8 @@ def build_picodet(backbone: Mapping, neck: Mapping, head: Mapping, num_classes: 
                                              s2w=_f(backbone, p + ".se.conv2.weight").reshape(cin, cin // 4), s2b=_f(backbone, p + ".se.conv2.bias")))
                 t = t2
             x = b.tensor(cout, down)
-            b.op(OP_PW, t, x, act=ACT_HSWISH, w=_pw(b, backbone, p + ".pw_conv.conv.weight", p + ".pw_conv.bn"))
+            pk = pw_pack(cin, cout)
+            b.op(OP_PW, t, x, k=pk, act=ACT_HSWISH, w=_pw(b, backbone, p + ".pw_conv.conv.weight", p + ".pw_conv.bn", pack=pk))
         feats[name] = x
     c3, c4, c5 = feats["blocks4"], feats["blocks5"], feats["blocks6"]
     # ---- CSP-PAN (csp_pan.py:310-347).  Concatenation buffers: cat_a = [up(t2) | t1], cat_b = [up(inner1) | t0],

@@ -29,7 +29,7 @@ import numpy as np
 
 from . import weights as W
 from .picodet_graph import OP_DW, OP_PW, OP_SE, OP_STEM, OP_UP2
-from .pp_rec_graph import ACT_HSWISH, ACT_NONE, _Builder, _f, _gemm_weight, _pad_to
+from .pp_rec_graph import ACT_HSWISH, ACT_NONE, _Builder, _f, _gemm_weight, _pad_to, pw_pack_factor
 from .synth import PP_DET_CONFIG, PP_DET_FPN, PP_DET_SCALE, pp_rec_ch
 
 OP_CONV, OP_DECONV2, OP_DBHEAD = 12, 13, 14
@@ -78,7 +78,8 @@ def build_pp_det(sd: Mapping, precise: bool = False):
             wp = _f(sd, p + ".pw_conv.reparam_conv.weight").reshape(co, ci) * s1
             bp = _f(sd, p + ".pw_conv.reparam_conv.bias") * s1 + c1
             x = b.tensor(co, d, d)
-            b.op(OP_PW, t, x, act=ACT_HSWISH, w=_gemm_weight(b, wp, bp, pa=lab(p + ".pw_conv.act.lab")))
+            pk = pw_pack_factor(b, ci, co)
+            b.op(OP_PW, t, x, k=pk, act=ACT_HSWISH, w=_gemm_weight(b, wp, bp, pa=lab(p + ".pw_conv.act.lab"), pack=pk))
         if name != "blocks2":
             taps.append((x, co, d))
 

@@ -66,8 +66,30 @@ def _pad_to(a: np.ndarray, axis: int, n: int) -> np.ndarray:
     return np.pad(a, pad)
 
 
-def _gemm_weight(b: _Builder, w2d: np.ndarray, bias: np.ndarray, pa=None) -> int:
+def pw_pack_factor(b: _Builder, cin: int, cout: int) -> int:
+    """Pixels per GEMM row for a narrow 1x1 layer (the executor's OP_PW with k = factor): a 16- or 32-channel layer is run on
+    4 (2) consecutive pixels at once against a block-diagonal weight -- K = 64 (128-byte TMA rows instead of 32 / 64-byte ones),
+    N = factor * cout -- because at K = 16 a 128-pixel tile is one MMA and the kernel is bound by per-tile TMA rows and barrier
+    round trips, not by bytes.  fp32x programs keep one pixel per row."""
+    if getattr(b, "precise", False) or cin > 32 or cin % 16 or cout * (64 // cin) > 256:
+        return 1
+    return 64 // cin
+
+
+def block_diagonal(w2d: np.ndarray, bias: np.ndarray, pack: int):
+    """w [Cout, K] -> diag(w, ..., w) [pack * Cout, pack * K] and the bias tiled: output row j * Cout + o of a packed row is
+    channel o of its j-th pixel."""
+    cout, k = w2d.shape
+    out = np.zeros((pack * cout, pack * k), np.float32)
+    for j in range(pack):
+        out[j * cout:(j + 1) * cout, j * k:(j + 1) * k] = w2d
+    return out, np.tile(bias, pack)
+
+
+def _gemm_weight(b: _Builder, w2d: np.ndarray, bias: np.ndarray, pa=None, pack: int = 1) -> int:
     """[Cout, K] fp32 (+bias) -> packed 1x1 weight of the executor (fp32x builders: the split-fp16 triple [W_hi | W_lo | W_hi])."""
+    if pack > 1:
+        w2d, bias = block_diagonal(w2d, bias, pack)
     if not getattr(b, "precise", False) and w2d.shape[1] >= 128 and w2d.shape[1] % 64:
         # wide layers: K padded to whole 64-channel k-blocks (240 -> 256, 480 -> 512); the executor's TMA zero-fills the A columns
         w2d = _pad_to(w2d, 1, (w2d.shape[1] + 63) // 64 * 64)
@@ -122,7 +144,8 @@ def build_pp_rec(sd: Mapping, n_class: int = None, precise: bool = False):
             wp = _f(sd, p + ".pw_conv.reparam_conv.weight").reshape(co, ci) * s1
             bp = _f(sd, p + ".pw_conv.reparam_conv.bias") * s1 + c1
             x = b.tensor(co, dh, dw)
-            b.op(OP_PW, t, x, act=ACT_HSWISH, w=_gemm_weight(b, wp, bp, pa=lab(p + ".pw_conv.act.lab")))
+            pk = pw_pack_factor(b, ci, co)
+            b.op(OP_PW, t, x, k=pk, act=ACT_HSWISH, w=_gemm_weight(b, wp, bp, pa=lab(p + ".pw_conv.act.lab"), pack=pk))
         feats[name] = x
     cb = pp_rec_ch(512)
     d = int(_f(sd, "head.ctc_encoder.encoder.norm.weight").shape[0])

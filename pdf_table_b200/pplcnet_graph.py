@@ -15,7 +15,7 @@ import numpy as np
 
 from . import weights as W
 from .picodet_graph import OP_DW, OP_PW, OP_SE, OP_STEM
-from .pp_rec_graph import ACT_HSWISH, ACT_NONE, OP_AVGPOOL, OP_CTC, _Builder, _f, _gemm_weight, _pad_to
+from .pp_rec_graph import ACT_HSWISH, ACT_NONE, OP_AVGPOOL, OP_CTC, _Builder, _f, _gemm_weight, _pad_to, pw_pack_factor
 
 NET_CONFIG = {  # cls/cls_pp_lcnet.py:52-63: k, in_c, out_c, stride, use_se (the first stride of blocks3..6 comes from stride_list)
     "blocks2": [[3, 16, 32, 1, False]],
@@ -70,7 +70,8 @@ def build_pplcnet(sd: Mapping, stride_list: Sequence = (2, 2, 2, 2, 2)):
                 t = t2
             scale, shift = bn(p + ".pw_conv.bn", co)
             x = b.tensor(co, dh, dw)
-            b.op(OP_PW, t, x, act=ACT_HSWISH, w=_gemm_weight(b, _f(sd, p + ".pw_conv.conv.weight").reshape(co, ci) * scale[:, None], shift))
+            pk = pw_pack_factor(b, ci, co)
+            b.op(OP_PW, t, x, k=pk, act=ACT_HSWISH, w=_gemm_weight(b, _f(sd, p + ".pw_conv.conv.weight").reshape(co, ci) * scale[:, None], shift, pack=pk))
     pooled = b.tensor(512, dh, dw, 0, 0)
     b.op(OP_AVGPOOL, x, pooled, k=0)
     expand = int(_f(sd, "last_conv.weight").shape[0])
