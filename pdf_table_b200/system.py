@@ -10,6 +10,7 @@ these methods return exactly what its next steps consume.
 """
 from __future__ import annotations
 
+import contextlib
 import time
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -58,6 +59,7 @@ class OcrSystemTask:
         # branches share only the resident pages); False keeps everything on the caller's stream
         self.table_stream = table_stream
         self._side: Optional[torch.cuda.Stream] = None
+        self._chain: Optional[torch.cuda.Stream] = None
         self.text_detector = text_detector
         self.text_recognizer = text_recognizer
         self.table_structure_recognizer = table_structure_recognizer
@@ -128,26 +130,37 @@ class OcrSystemTask:
             batch.record_stream(self._side)
             return run
 
-        # ---- stage 1 (GPU): layout + detection enqueued back to back
-        lay_run = None
-        if self.layout_detector is not None:
-            lay_run = self.layout_detector._run_model(self.layout_detector._preprocess(page_list))
-        det_run = det._run_model(det._preprocess(page_list), **(det_kwargs or {}))
-        # with the table boxes given, the table branch does not wait for the layout results: its host preparation (crop rects,
-        # affine matrices) runs while the device already works on stage 1
-        if tsr is not None and layout_tables is not None:
-            tsr_run = launch_tables(None)
-        # ---- host: layout records -> table boxes; stage 2 (GPU): table structure
-        layouts = self.layout_detector._postprocess(lay_run) if lay_run is not None else [[] for _ in range(n_pages)]
-        if tsr is not None and layout_tables is None:
-            tsr_run = launch_tables(layouts)
-        # ---- host (while the tables run): reading order + corner order of the detected boxes; stage 3 (GPU): recognition
-        dets = [sort_det_boxes(d) if len(d) else np.zeros((0, 8)) for d in det._postprocess(det_run)]
-        pts = [order_points_batch(d) for d in dets]
-        rec_run = rec.launch_pages(batch, pts)
-        # ---- collect
+        # The layout -> detection -> recognition chain runs on a HIGH-priority stream when the tables have their own: the chain
+        # then finishes first and the host's share of the text results (dictionary lookups, string building: ~5 ms per 32 pages)
+        # overlaps the rest of the table branch instead of following the whole device step.
+        chain = contextlib.nullcontext()
+        if self.table_stream and tsr is not None:
+            if self._chain is None or self._chain.device != dev:
+                self._chain = torch.cuda.Stream(device=dev, priority=-1)
+            self._chain.wait_event(uploaded)
+            batch.record_stream(self._chain)
+            chain = torch.cuda.stream(self._chain)
+        with chain:
+            # ---- stage 1 (GPU): layout + detection enqueued back to back
+            lay_run = None
+            if self.layout_detector is not None:
+                lay_run = self.layout_detector._run_model(self.layout_detector._preprocess(page_list))
+            det_run = det._run_model(det._preprocess(page_list), **(det_kwargs or {}))
+            # with the table boxes given, the table branch does not wait for the layout results: its host preparation (crop
+            # rects, affine matrices) runs while the device already works on stage 1
+            if tsr is not None and layout_tables is not None:
+                tsr_run = launch_tables(None)
+            # ---- host: layout records -> table boxes; stage 2 (GPU): table structure
+            layouts = self.layout_detector._postprocess(lay_run) if lay_run is not None else [[] for _ in range(n_pages)]
+            if tsr is not None and layout_tables is None:
+                tsr_run = launch_tables(layouts)
+            # ---- host (while the tables run): reading order + corner order of the detected boxes; stage 3 (GPU): recognition
+            dets = [sort_det_boxes(d) if len(d) else np.zeros((0, 8)) for d in det._postprocess(det_run)]
+            pts = [order_points_batch(d) for d in dets]
+            rec_run = rec.launch_pages(batch, pts)
+            # ---- collect: the texts first (their chain ends first), the tables last
+            texts = rec.collect_pages(rec_run)
         tables = self.table_structure_recognizer.collect_tables(tsr_run) if tsr_run is not None else []
-        texts = rec.collect_pages(rec_run)
         out = []
         for p in range(n_pages):
             ocr = [{"index": i + 1, "text": "" if t is None else t, "bbox": q} for i, (t, q) in enumerate(zip(texts[p], pts[p]))]
