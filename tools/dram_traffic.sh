@@ -23,7 +23,7 @@ for r in rows[1:]:
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
     base = re.sub(r"^void ", "", r[ki]).replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
     base = re.sub(r"[<(].*$", "", base).split("::")[-1].strip()
-    base = {"k_dwconv_row": "k_dwconv", "k_dwconv_c2": "k_dwconv"}.get(base, base)  # bench.py's launch names
+    base = {"k_dwconv_row": "k_dwconv", "k_dwconv_c2": "k_dwconv", "k_up_dw_add_cls": "k_up_dw_add"}.get(base, base)  # bench.py's launch names
     per.setdefault((r[ii], base), {})[r[mi]] = v
 agg = collections.OrderedDict()
 for (_, k), d in per.items():
