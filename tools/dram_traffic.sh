@@ -1,7 +1,7 @@
 #!/bin/bash
 # roofline.traffic source: dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel, from an ncu pass over the
 # default bench workload (one-stream step) and over the three blocks.  usage: gpurun -- bash tools/dram_traffic.sh TAG
-#   -> gpurun_out/TAG_dram_traffic_{full,pp_rec,rec_sweep,lore}.json (copy to profiles/)
+#   -> gpurun_out/TAG_dram_traffic_{full,pp_rec,rec_sweep,lore}.json (copy to profiles/ as TAG_{workload}_dram_traffic.json: bench.py globs *_dram_traffic.json)
 TAG=${1:-r4}
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
 run() {  # name, command...
