@@ -60,6 +60,29 @@ def test_predict_pages_equals_the_per_page_calls(cascade):
             np.testing.assert_array_equal(res["logi"], want[tuple(bbox)]["logi"])
 
 
+def test_predict_stream_equals_predict_pages(cascade):
+    """predict_stream (batch i + 1 uploaded by a copy stream while batch i computes) yields exactly predict_pages' results, batch
+    by batch, from views of one pinned buffer."""
+    host = torch.empty((3, 2, 480, 640, 3), dtype=torch.uint8).pin_memory()
+    for b in range(3):
+        for i in range(2):
+            host[b, i] = torch.from_numpy(synth.synthetic_page(40 + 2 * b + i, 480, 640))
+    batches = [host[b].numpy() for b in range(3)]
+    tables = [[TABLE], [[100.0, 200.0, 500.0, 470.0]]]
+    want = [cascade.predict_pages(bt, layout_tables=tables) for bt in batches]
+    got = list(cascade.predict_stream(iter(batches), layout_tables=tables))
+    assert len(got) == 3
+    for w, g in zip(want, got):
+        for pw, pg in zip(w, g):
+            np.testing.assert_array_equal(pw["det"], pg["det"])
+            assert [o["text"] for o in pw["ocr"]] == [o["text"] for o in pg["ocr"]]
+            assert len(pw["layout"]) == len(pg["layout"]) and len(pw["tables"]) == len(pg["tables"])
+            for (_, a), (_, b) in zip(pw["tables"], pg["tables"]):
+                np.testing.assert_array_equal(a["polygons"], b["polygons"])
+                np.testing.assert_array_equal(a["logi"], b["logi"])
+    assert list(cascade.predict_stream(iter([]))) == []
+
+
 def test_detection_task_dbnet_backend():
     """OcrDetectionTask(model="db"): the fused pre-process equals OCRDetectionPreprocessor's tensor (golden from the reference
     class) within the fp16 rounding of the stem input, the network sees exactly that input, and the boxes of a planted map
