@@ -852,13 +852,19 @@ class OcrRecognitionTask(BaseInferTask):
             return [" ".join(str(int(v)) for v in row[:k]) for row, k in zip(ids, lens)]
         tab = getattr(self, "_char_tab", None)
         if tab is None:
-            single = all(isinstance(c, str) and len(c) == 1 for c in self.character)
-            tab = self._char_tab = np.array(self.character, dtype="<U1") if single else False
+            # entry 0 is CTCLabelDecode's 'blank' token (a word, never emitted: the collapse removes it, and it pads the rows): it
+            # gets a one-character stand-in that no dictionary entry uses, and a row that shows it inside its length falls back
+            single = all(isinstance(c, str) and len(c) == 1 for c in self.character[1:])
+            self._blank_mark = next(c for c in map(chr, range(0xE000, 0xF8FF)) if c not in set(self.character))
+            first = self.character[0] if len(self.character[0]) == 1 else self._blank_mark
+            tab = self._char_tab = np.array([first] + list(self.character[1:]), dtype="<U1") if single else False
         t = ids.shape[1] if ids.ndim == 2 else 0
         if tab is not False and t > 0 and ids.size and int(ids.min()) >= 0 and int(ids.max()) < len(tab):
             rows = np.ascontiguousarray(tab[ids]).view(f"<U{t}").reshape(-1)
+            mark = self._blank_mark if len(self.character[0]) != 1 else None
             # a row made of NUL-free characters keeps its full width; lengths cut the padding off
-            return [str(r)[:k] if len(r) >= k else "".join(self.character[int(v)] for v in row[:k]) for r, k, row in zip(rows, lens.tolist(), ids)]
+            return [str(r)[:k] if len(r) >= k and (mark is None or mark not in str(r)[:k]) else "".join(self.character[int(v)] for v in row[:k])
+                    for r, k, row in zip(rows, lens.tolist(), ids)]
         return ["".join(self.character[int(v)] for v in row[:k]) for row, k in zip(ids, lens)]
 
     def recognize_pages(self, pages, positions_per_page) -> List[List[Optional[str]]]:

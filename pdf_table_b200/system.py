@@ -91,7 +91,9 @@ class OcrSystemTask:
         """The throughput form of ``predict_pages``: a generator over an iterable of page batches that yields what
         ``predict_pages(batch, **kwargs)`` returns for each, with batch i + 1 uploaded by a copy stream while batch i computes
         (give it views of pinned memory: the copy engine then works beside the SMs and the step no longer starts with an idle
-        device waiting for its 2.8 MB per page).  Two batches are resident at a time."""
+        device waiting for its 2.8 MB per page) and the results of batch i - 1 collected (read-back, string building, result dicts)
+        after batch i has been enqueued, so the host's share of a batch overlaps the device's share of the next.  Two batches are
+        in flight at a time; the results are those of ``predict_pages``, one batch late."""
         det = self._need(self.text_detector, "text_detector")
         dev = torch.device("cuda", det.device)
         if self._copy is None or self._copy.device != dev:
@@ -104,16 +106,27 @@ class OcrSystemTask:
                 ev.record()
             return batch, ev
 
+        keep = bool(kwargs.pop("keep_device_record", False))
         it = iter(batches)
         nxt = next(it, None)
         up = start(nxt) if nxt is not None else None
+        pending = None
         while up is not None:
             cur, nxt = up, next(it, None)
             up = start(nxt) if nxt is not None else None
-            yield self.predict_pages(None, _uploaded=cur, **kwargs)
+            # everything of batch i is enqueued (its recognition pass follows the host's look at its detected boxes) BEFORE the
+            # results of batch i - 1 are collected: the host's result building and the read-back of batch i - 1 then run while
+            # the device works on batch i.  Every run owns its result tensors and the engines' internal buffers are reused in
+            # stream order, so the two batches in flight do not meet.
+            state = self.predict_pages(None, _uploaded=cur, _defer=True, **kwargs)
+            if pending is not None:
+                yield self._finish_batch(pending, keep)
+            pending = state
+        if pending is not None:
+            yield self._finish_batch(pending, keep)
 
     def predict_pages(self, pages, layout_tables=None, det_kwargs: Optional[Dict[str, Any]] = None,
-                      keep_device_record: bool = False, _uploaded=None) -> List[Dict[str, Any]]:
+                      keep_device_record: bool = False, _uploaded=None, _defer: bool = False) -> List[Dict[str, Any]]:
         """The reference's per-page sequence (cli/main.py:116-144 -> ocr_system_task.py:549-734: layout_analysis,
         text_detection, text_recognition, table_structure_detection) for a BATCH of equally sized pages, with the host steps
         of one stage overlapped with the device work of another:
@@ -192,17 +205,24 @@ class OcrSystemTask:
             dets = [sort_det_boxes(d) if len(d) else np.zeros((0, 8)) for d in det._postprocess(det_run)]
             pts = [order_points_batch(d) for d in dets]
             rec_run = rec.launch_pages(batch, pts)
-            # ---- collect: the texts first (their chain ends first), the tables last
-            texts = rec.collect_pages(rec_run)
-        tables = self.table_structure_recognizer.collect_tables(tsr_run) if tsr_run is not None else []
+        state = {"batch": batch, "n_pages": n_pages, "layouts": layouts, "dets": dets, "pts": pts, "det_run": det_run, "rec_run": rec_run,
+                 "tsr_run": tsr_run, "tables_flat": tables_flat}
+        return state if _defer else self._finish_batch(state, keep_device_record)
+
+    def _finish_batch(self, st: Dict[str, Any], keep_device_record: bool) -> List[Dict[str, Any]]:
+        """Second half of ``predict_pages``: waits for the copies and builds the per-page results -- the texts first (their chain
+        ends first), the tables last."""
+        n_pages, pts = st["n_pages"], st["pts"]
+        texts = self.text_recognizer.collect_pages(st["rec_run"])
+        tables = self.table_structure_recognizer.collect_tables(st["tsr_run"]) if st["tsr_run"] is not None else []
         out = []
         for p in range(n_pages):
             ocr = [{"index": i + 1, "text": "" if t is None else t, "bbox": q} for i, (t, q) in enumerate(zip(texts[p], pts[p]))]
-            out.append({"layout": layouts[p], "det": dets[p], "ocr": ocr, "tables": []})
-        for tb, res in zip(tables_flat, tables):
+            out.append({"layout": st["layouts"][p], "det": st["dets"][p], "ocr": ocr, "tables": []})
+        for tb, res in zip(st["tables_flat"], tables):
             out[tb["page"]]["tables"].append(res)
         if keep_device_record:
-            self.device_record = self._device_record(det_run, rec_run, tsr_run, n_pages)
+            self.device_record = self._device_record(st["det_run"], st["rec_run"], st["tsr_run"], n_pages)
         return out
 
     @staticmethod
