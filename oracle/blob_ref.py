@@ -141,3 +141,48 @@ def convnext_vit_state_dict_from_blob(t: Dict[str, np.ndarray]) -> Dict[str, np.
     sd[v + ".layernorm.weight"], sd[v + ".layernorm.bias"] = t["vit.ln.w"].copy(), t["vit.ln.b"].copy()
     sd["vitstr.classifier.weight"], sd["vitstr.classifier.bias"] = _unpack_linear(t, "cls", 192)
     return sd
+
+
+@torch.no_grad()
+def lore_resnet18_from_blob(t: Dict[str, np.ndarray], x: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """t = read_blob(pack_lore_resnet18(sd)); x fp32 [N,3,H,W] (H, W multiples of 64) -> {'maps': the packed 24-wide head map
+    [N,24,H/4,W/4] (hm NOT sigmoid-ed here), 'ax' / 'cr': dense [N,256,H/4,W/4]} computed FROM THE PACKED TENSORS in the order
+    csrc/lore_net.cu build_r18 plans them: the transposed convs as 3x3 convs to 4 x 256 pixel-shuffled channels, the six first
+    head convs as one conv, the 64 -> 64 convs on channel slices [hm | reg | wh | st | ax | cr], the small heads' last 1x1 as one
+    block-diagonal conv over the first 256 hidden channels (reg's slice is its first conv's output)."""
+    def conv(name, inp, cin, k, stride=1, relu=False):
+        w, b = _unpack_conv(t, name, cin, k)
+        y = F.conv2d(inp, w, b, stride=stride, padding=k // 2)
+        return F.relu(y) if relu else y
+
+    ws = torch.from_numpy(t["stem.w"].astype(np.float32)).reshape(64, 7, 8, 4)[:, :, :7, :3].permute(0, 3, 1, 2).contiguous()
+    y = F.relu(F.conv2d(x.float(), ws, torch.from_numpy(t["stem.b"][:64].copy()), stride=2, padding=3))
+    xs = [F.max_pool2d(y, 3, 2, 1)]
+    y, cin = xs[0], 64
+    for L, cout in zip(range(1, 5), (64, 128, 256, 256)):
+        for B in range(2):
+            stride = 2 if B == 0 else 1
+            p = f"layer{L}.{B}"
+            o = conv(p + ".conv1", y, cin, 3, stride, relu=True)
+            o = conv(p + ".conv2", o, cout, 3)
+            if (p + ".down.w") in t:
+                y = conv(p + ".down", y, cin, 1, stride)
+            y = F.relu(o + y)
+            cin = cout
+        xs.append(y)
+    top = xs[4]
+    for i, (name, skip) in enumerate((("adaption3", xs[3]), ("adaption2", xs[2]), ("adaption1", xs[1]), ("adaption0", xs[0]))):
+        up = conv(f"up{i + 1}", top, 256, 3, relu=True)  # [N, 4*256, h, w], row (py*2 + px)*256 + co
+        n, _, h, w = up.shape
+        up = up.reshape(n, 2, 2, 256, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, 256, 2 * h, 2 * w)
+        top = conv(name, skip, skip.shape[1], 1) + up
+    feat = conv("adaptionU1", top, 256, 1)
+    a = conv("heads.conv1", feat, 256, 3, relu=True)  # 6 x 64
+    hid = []
+    for h, head in enumerate(("hm", "reg", "wh", "st", "ax", "cr")):
+        v = a[:, 64 * h: 64 * (h + 1)]
+        if head != "reg":
+            for j in (2, 4, 6):
+                v = conv(f"heads.{head}.{j}", v, 64, 3, relu=True)
+        hid.append(v)
+    return {"maps": conv("heads.out", torch.cat(hid[:4], 1), 256, 1), "ax": conv("ax.out", hid[4], 64, 1), "cr": conv("cr.out", hid[5], 64, 1)}

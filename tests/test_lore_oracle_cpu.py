@@ -305,3 +305,29 @@ def test_lore_wireless_decode_oracle_matches_reference_golden():
     np.testing.assert_array_equal(out["scores"], res[:n, 8])
     np.testing.assert_array_equal(out["dets_feat"], g["dec_dets_feat"])
     np.testing.assert_allclose(out["logi_feat"], g["dec_logi_feat"], atol=1e-6, rtol=0)
+
+
+def test_packed_lore_resnet18_blob_computes_the_reference_function():
+    """pack_lore_resnet18 on CPU: BatchNorm folding, the ConvTranspose 4x4 s2 -> 3x3 conv + pixel shuffle identity, the fused first
+    head conv, the block-diagonal last 1x1 -- the network run from the packed tensors equals the oracle up to fp16 weight rounding."""
+    from oracle import blob_ref, lore_wireless_ref
+    from pdf_table_b200 import weights
+
+    sd = synth.lore_resnet18_state_dict(0)
+    w3, _ = weights.deconv4x4_as_conv3x3(sd["deconv_layers1.0.weight"])
+    xin = torch.from_numpy(np.random.default_rng(2).standard_normal((1, 256, 5, 7)).astype(np.float32))
+    y = torch.nn.functional.conv2d(xin, torch.from_numpy(w3), padding=1).reshape(1, 2, 2, 256, 5, 7).permute(0, 3, 4, 1, 5, 2).reshape(1, 256, 10, 14)
+    ref = torch.nn.functional.conv_transpose2d(xin, torch.from_numpy(sd["deconv_layers1.0.weight"]), stride=2, padding=1)
+    assert float((y - ref).abs().max()) < 1e-4  # exact up to the summation order
+    t = blob_ref.read_blob(weights.pack_lore_resnet18(sd))
+    assert t["up1.w"].shape == (1024, 9 * 256) and t["heads.conv1.w"].shape == (384, 9 * 256) and t["heads.out.w"].shape == (24, 256)
+    g = np.load(os.path.join(GOLDEN, "lore_resnet18_seed0.npz"))
+    x = torch.from_numpy(g["x"])
+    got = blob_ref.lore_resnet18_from_blob(t, x)
+    worst = 0.0
+    for k, sl in (("hm", slice(0, 2)), ("reg", slice(2, 4)), ("wh", slice(4, 12)), ("st", slice(12, 20))):
+        worst = max(worst, float(np.abs(got["maps"][:, sl].numpy() - g[k]).max()) / max(1.0, float(np.abs(g[k]).max())))
+    for k in ("ax", "cr"):
+        worst = max(worst, float(np.abs(got[k].numpy() - g[k]).max()) / max(1.0, float(np.abs(g[k]).max())))
+    assert worst < 3e-3, worst  # fp16 rounding of the packed weights
+    assert float(got["maps"][:, 20:].abs().max()) == 0.0  # the four pad columns
