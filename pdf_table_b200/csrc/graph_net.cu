@@ -431,14 +431,17 @@ k_ln_c(const T* __restrict__ in, long long rows, int C, int ldi, const float* __
 // Global-mixer attention of the SVTR neck: qkv [N, T, 3D] (q | k | v, each head-major heads x hd; the 1/sqrt(hd) scale is
 // folded into the packed q weights) -> ctx [N, T, D].  One CTA per image; K and V of all heads staged in shared memory as
 // fp32, one thread per (head, query) with an online softmax (no score buffer, any T that fits shared memory).
-template <typename T_>
+// HD > 0: the head width is a compile-time constant (15 for the PP-OCRv4 neck), so q / o live in registers and the inner loops
+// unroll; with the run-time width (HD = 0) the two arrays were indexed dynamically and went to local memory (0.33 ms per launch
+// against 0.05).
+template <typename T_, int HD>
 __global__ void __launch_bounds__(256)
 k_attn_small(const T_* __restrict__ qkv, int T, int D, int heads, T_* __restrict__ ctx) {
     extern __shared__ float sm[];  // K [T][D] | V [T][D]
     float* sK = sm;
     float* sV = sm + static_cast<size_t>(T) * D;
     const int n = blockIdx.x;
-    const int hd = D / heads;
+    const int hd = HD > 0 ? HD : D / heads;
     const T_* base = qkv + static_cast<long long>(n) * T * 3 * D;
     for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
         const int t = i / D, c = i - t * D;
@@ -446,28 +449,36 @@ k_attn_small(const T_* __restrict__ qkv, int T, int D, int heads, T_* __restrict
         sV[i] = ld1(base + static_cast<long long>(t) * 3 * D + 2 * D + c);
     }
     __syncthreads();
+    constexpr int kMaxHd = HD > 0 ? HD : 16;
     for (int w = threadIdx.x; w < heads * T; w += blockDim.x) {
         const int h = w / T, qi = w - h * T;
-        float q[16], o[16];
-        for (int d = 0; d < hd; ++d) {
-            q[d] = ld1(base + static_cast<long long>(qi) * 3 * D + h * hd + d);
+        float q[kMaxHd], o[kMaxHd];
+#pragma unroll
+        for (int d = 0; d < kMaxHd; ++d) {
+            q[d] = d < hd ? ld1(base + static_cast<long long>(qi) * 3 * D + h * hd + d) : 0.f;
             o[d] = 0.f;
         }
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < T; ++j) {
             const float* kp = sK + j * D + h * hd;
             float sc = 0.f;
-            for (int d = 0; d < hd; ++d) sc = fmaf(q[d], kp[d], sc);
+#pragma unroll
+            for (int d = 0; d < kMaxHd; ++d)
+                if (d < hd) sc = fmaf(q[d], kp[d], sc);
             const float mn = fmaxf(m, sc);
             const float corr = __expf(m - mn), pj = __expf(sc - mn);
             l = l * corr + pj;
             const float* vp = sV + j * D + h * hd;
-            for (int d = 0; d < hd; ++d) o[d] = fmaf(o[d], corr, pj * vp[d]);
+#pragma unroll
+            for (int d = 0; d < kMaxHd; ++d)
+                if (d < hd) o[d] = fmaf(o[d], corr, pj * vp[d]);
             m = mn;
         }
         const float inv = 1.f / l;
         T_* op = ctx + (static_cast<long long>(n) * T + qi) * D + h * hd;
-        for (int d = 0; d < hd; ++d) st1(op + d, o[d] * inv);
+#pragma unroll
+        for (int d = 0; d < kMaxHd; ++d)
+            if (d < hd) st1(op + d, o[d] * inv);
     }
 }
 
@@ -1354,13 +1365,21 @@ int run_graph(Engine* e, GraphNet* m, const float* in_nchw, const uint8_t* in_u8
                 if (smem > 200 * 1024) return set_err(e, DV_ERR_UNSUPPORTED, "graph: attention over %d positions exceeds shared memory", T);
                 static DeviceOnce attr_once;
                 if (attr_once.need(e->device)) {
-                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<__half, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<__half, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    DV_CUDA(e, cudaFuncSetAttribute(k_attn_small<float, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_once.mark(e->device);
                 }
+                if (op.k <= 0 || D % op.k || D / op.k > 16) return set_err(e, DV_ERR_UNSUPPORTED, "graph: attention head width %d > 16", op.k > 0 ? D / op.k : 0);
                 e->launch_begin("k_attn_small", "attn", 4.0 * N * T * T * D, static_cast<double>(N) * T * D * 8.0);
-                if (pr) k_attn_small<float><<<N, 256, smem, s>>>(F32(in, 0), T, D, op.k, F32(out, 0));
-                else k_attn_small<__half><<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
+                if (D / op.k == 15) {
+                    if (pr) k_attn_small<float, 15><<<N, 256, smem, s>>>(F32(in, 0), T, D, op.k, F32(out, 0));
+                    else k_attn_small<__half, 15><<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
+                } else {
+                    if (pr) k_attn_small<float, 0><<<N, 256, smem, s>>>(F32(in, 0), T, D, op.k, F32(out, 0));
+                    else k_attn_small<__half, 0><<<N, 256, smem, s>>>(in.p, T, D, op.k, out.p);
+                }
                 e->launch_end();
                 break;
             }
