@@ -243,7 +243,8 @@ int op_u8_to_stem(Engine* e, const uint8_t* in, int N, int H, int W, const float
 int op_maxpool3x3s2(Engine* e, const Tensor& in, Tensor& out);
 int op_deconv2x2_c1_sigmoid(Engine* e, const Tensor& in, const __half* w, const float* w32, float bias, float* out);
 int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out);
-int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld = 0, int lo = 0);
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld = 0, int lo = 0, int Hp = 0, int Wp = 0,
+                            int py = 0, int px = 0);
 
 // dbnet.cu
 int dbnet_create(Engine* e);

@@ -62,6 +62,7 @@ struct LoreNet : Model {
     Engine* e = nullptr;
     bool precise = false;
     bool plain_up = false;  // CenterNet: DLAUp of plain IDAUp blocks (no DCN), heads hm / v2c / c2v / reg
+    int level0_pad = 0;     // 1: the level0 tensor is zero-bordered [N, H + 2, W + 8, 16] with its interior at (+1, +1)
     bool resnet = false;    // Lore wireless: ResNet-18 key-point detector (build_r18); ax / cr end in a 1x1 over their own hidden maps
     Tensor feat_ax, feat_cr;
     int N = 0, H = 0, W = 0;
@@ -420,10 +421,16 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         m->maps = reinterpret_cast<float*>(p);
     }
     Tensor b0, l0, l1;
-    DV_TRY(m->tensor(&l0, N, H, W, 16));
     DV_TRY(m->tensor(&l1, N, H / 2, W / 2, 32));
     static const bool win_env = !(getenv("DV_WINCONV") && atoi(getenv("DV_WINCONV")) == 0);
+    static const bool win_l1_env = !(getenv("DV_WINCONV_L1") && atoi(getenv("DV_WINCONV_L1")) == 0);
     const bool use_win = win_env && !m->precise;
+    // level1 (3x3 stride 2, 16 -> 32) also runs on conv_win_tcgen05 when its window-packed filter is in the blob: level0 then writes
+    // into a zero-bordered buffer (interior at +1,+1) -- through the TMA patch mode its 32-byte rows made it TMA-row-rate bound
+    const bool win_l1 = use_win && win_l1_env && e->find("level1.win.w") != nullptr;
+    m->level0_pad = win_l1 ? 1 : 0;
+    if (win_l1) DV_TRY(m->tensor(&l0, N, H + 2, W + 8, 16, /*zero=*/true));
+    else DV_TRY(m->tensor(&l0, N, H, W, 16));
     if (use_win) {
         // the two full-resolution 16-channel layers run on conv_win_tcgen05 (load/store producer, resident filter):
         // base writes into a zero-bordered buffer (interior at +1,+1) so that level0 reads 4-pixel x 16-channel windows
@@ -439,7 +446,7 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
             st.kind = Step::WINCONV;
             st.name = i == 0 ? "base" : "level0";
             DV_TRY(plan_win_conv(e, i == 0 ? m->stem_in : b0, 1, i == 0 ? 7 : 3, H, W, reinterpret_cast<const __half*>(w->dptr),
-                                 reinterpret_cast<const float*>(b->dptr), 16, ACT_RELU, i == 0 ? b0 : l0, i == 0 ? 1 : 0, &st.win, st.name.c_str()));
+                                 reinterpret_cast<const float*>(b->dptr), 16, ACT_RELU, i == 0 ? b0 : l0, (i == 0 || win_l1) ? 1 : 0, &st.win, st.name.c_str()));
             st.win_flops = 2.0 * N * H * W * (i == 0 ? 147.0 : 144.0) * 16;
             m->flops += st.win_flops;
             m->steps.push_back(st);
@@ -449,7 +456,21 @@ int build(Engine* e, LoreNet* m, int N, int H, int W) {
         DV_TRY(add_conv(m, "base", m->stem_in, 16, 7, 1, epi(b0, ACT_RELU), /*stem=*/true));
         DV_TRY(add_conv(m, "level0", b0, 16, 3, 1, epi(l0, ACT_RELU)));
     }
-    DV_TRY(add_conv(m, "level1", l0, 32, 3, 2, epi(l1, ACT_RELU)));
+    if (win_l1) {
+        const BlobTensor* w = e->find("level1.win.w");
+        const BlobTensor* b = e->find("level1.win.b");
+        if (!b || w->dtype != 1 || b->dtype != 0 || w->dims[0] != 32 || w->dims[1] != 192) return set_err(e, DV_ERR_WEIGHTS, "bad 'level1.win'");
+        Step st;
+        st.kind = Step::WINCONV;
+        st.name = "level1";
+        DV_TRY(plan_win_conv(e, l0, 2, 3, H / 2, W / 2, reinterpret_cast<const __half*>(w->dptr), reinterpret_cast<const float*>(b->dptr), 32, ACT_RELU,
+                             l1, 0, &st.win, st.name.c_str()));
+        st.win_flops = 2.0 * N * (H / 2) * (W / 2) * 144.0 * 32;
+        m->flops += st.win_flops;
+        m->steps.push_back(st);
+    } else {
+        DV_TRY(add_conv(m, "level1", l0, 32, 3, 2, epi(l1, ACT_RELU)));
+    }
     m->named["level0"] = l0;
     m->named["level1"] = l1;
     std::vector<Tensor> layers(4);
@@ -765,13 +786,17 @@ int lore_debug_tensor(Engine* e, const char* name, float* out_nchw, int* dims4) 
     if (it == m->named.end()) return set_err(e, DV_ERR_ARG, "no tensor named '%s'", name);
     const Tensor& t = it->second;
     if (t.ld != 0 && t.lo == 0) return set_err(e, DV_ERR_UNSUPPORTED, "tensor '%s' is a slice", name);
+    const bool pad = m->level0_pad && std::string(name) == "level0";
     if (dims4) {
         dims4[0] = t.N;
         dims4[1] = t.C;
-        dims4[2] = t.H;
-        dims4[3] = t.W;
+        dims4[2] = pad ? t.H - 2 : t.H;
+        dims4[3] = pad ? t.W - 8 : t.W;
     }
-    if (out_nchw) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw, t.ldc(), static_cast<int>(t.lo));
+    if (out_nchw) {
+        if (pad) return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H - 2, t.W - 8, out_nchw, t.ldc(), static_cast<int>(t.lo), t.H, t.W, 1, 1);
+        return op_nhwc_f16_to_nchw_f32(e, t.p, t.N, t.C, t.H, t.W, out_nchw, t.ldc(), static_cast<int>(t.lo));
+    }
     return 0;
 }
 

@@ -306,7 +306,7 @@ __global__ void k_nchw_f32_to_nhwc_f16(const float* __restrict__ in, int N, int 
     out[idx] = __float2half_rn(in[((static_cast<long long>(n) * C + c) * H + y) * W + x]);
 }
 __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int C, int H, int W,
-                                       float* __restrict__ out, int ld, int lo) {
+                                       float* __restrict__ out, int ld, int lo, int Hp, int Wp, int py, int px) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(N) * C * H * W;
     if (idx >= total) return;
@@ -317,7 +317,8 @@ __global__ void k_nhwc_f16_to_nchw_f32(const __half* __restrict__ in, int N, int
     t /= H;
     const int c = static_cast<int>(t % C);
     const int n = static_cast<int>(t / C);
-    const __half* ip = in + ((static_cast<long long>(n) * H + y) * W + x) * ld + c;
+    // Hp x Wp = the rows / pixels per row of the buffer in memory (a zero-bordered tensor: interior at (py, px))
+    const __half* ip = in + ((static_cast<long long>(n) * Hp + y + py) * Wp + x + px) * ld + c;
     out[idx] = __half2float(ip[0]) + (lo ? __half2float(ip[lo]) : 0.f);
 }
 int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int W, __half* out) {
@@ -328,10 +329,10 @@ int op_nchw_f32_to_nhwc_f16(Engine* e, const float* in, int N, int C, int H, int
     DV_CUDA(e, cudaGetLastError());
     return 0;
 }
-int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld, int lo) {
+int op_nhwc_f16_to_nchw_f32(Engine* e, const __half* in, int N, int C, int H, int W, float* out, int ld, int lo, int Hp, int Wp, int py, int px) {
     const long long total = static_cast<long long>(N) * C * H * W;
     e->launch_begin("k_nhwc_f16_to_nchw_f32", "layout", 0.0, total * 6.0);
-    k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out, ld ? ld : C, lo);
+    k_nhwc_f16_to_nchw_f32<<<grid_for(total, 256), 256, 0, e->stream>>>(in, N, C, H, W, out, ld ? ld : C, lo, Hp ? Hp : H, Wp ? Wp : W, py, px);
     e->launch_end();
     DV_CUDA(e, cudaGetLastError());
     return 0;

@@ -357,6 +357,8 @@ def pack_lore_dla34(sd: Mapping[str, "np.ndarray"], precise: bool = False) -> by
         put("level0.win", pack_win3x3_c16(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
         put("level0.winp", pack_win3x3_c16_planar(sd["base.level0.0.weight"], _bn(sd, "base.level0.1")))
     put("level1", pack_conv(sd["base.level1.0.weight"], None, _bn(sd, "base.level1.1")))
+    if not precise:  # stride-2 window form for conv_win_tcgen05 (the same 4-pixel x 16-channel window as level0.win)
+        put("level1.win", pack_win3x3_c16(sd["base.level1.0.weight"], _bn(sd, "base.level1.1")))
     for k in sd:
         if not k.startswith("base.level") or k.startswith(("base.level0", "base.level1")):
             continue
