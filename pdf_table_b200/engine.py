@@ -49,6 +49,13 @@ class _StreamBoundLib:
         return fn
 
 
+def _params_to(a: np.ndarray, dev) -> torch.Tensor:
+    """A small host parameter array -> device WITHOUT a stream synchronisation: `tensor.to(dev)` of pageable memory waits for the
+    whole current stream after the copy, which parked the host behind the previous batch's device work once two batches were in
+    flight (12.8 ms per step in OcrSystemTask.predict_stream); the non-blocking form returns once CUDA has staged the bytes."""
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+
 class Engine:
     """One handle per (model kind, device).  Not thread-safe; distinct handles are independent."""
 
@@ -222,9 +229,9 @@ class Engine:
         offsets = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64)
         dev = page.device
         out = torch.empty((int(nbytes.sum()),), dtype=torch.uint8, device=dev)
-        d_m = torch.from_numpy(minv).to(dev)
-        d_s = torch.from_numpy(sizes).to(dev)
-        d_o = torch.from_numpy(offsets).to(dev)
+        d_m = _params_to(minv, dev)
+        d_s = _params_to(sizes, dev)
+        d_o = _params_to(offsets, dev)
         check(self._lib.dv_warp_perspective_u8(self._h, _ptr(page), hh, ww, _ptr(d_m), _ptr(d_s), _ptr(d_o), n,
                                                int((nbytes // 3).max()), _ptr(out)), self._h, "dv_warp_perspective_u8")
         views = [out[int(o):int(o + b)].view(int(s[1]), int(s[0]), 3) for o, b, s in zip(offsets, nbytes, sizes)]
@@ -239,7 +246,7 @@ class Engine:
         if dst_widths.shape[0] != n or (dst_widths <= 0).any() or (dst_widths > dst_w_pad).any():
             raise ValueError("one positive width <= dst_w_pad per crop")
         out = torch.empty((n, dst_h, dst_w_pad, 3), dtype=torch.uint8, device=buf.device)
-        d_w = torch.from_numpy(dst_widths).to(buf.device)
+        d_w = _params_to(dst_widths, buf.device)
         check(self._lib.dv_resize_linear_u8(self._h, _ptr(buf), _ptr(d_o), _ptr(d_s), _ptr(d_w), n, dst_h, dst_w_pad, _ptr(out)),
               self._h, "dv_resize_linear_u8")
         return out
@@ -254,8 +261,8 @@ class Engine:
         if n == 0 or dst_w <= 0 or dst_h <= 0:
             raise ValueError("resize_pages_u8: empty batch / bad size")
         dev = pages.device
-        offs = (torch.arange(n, dtype=torch.int64) * (hh * ww * 3)).to(dev)
-        sizes = torch.tensor([[ww, hh]] * n, dtype=torch.int32).to(dev)
+        offs = _params_to((np.arange(n, dtype=np.int64) * (hh * ww * 3)), dev)
+        sizes = _params_to(np.array([[ww, hh]] * n, dtype=np.int32), dev)
         return self.resize_linear_u8((pages, offs, sizes), np.full((n,), dst_w, np.int32), dst_h, dst_w)
 
     def crop_quads_for_rec(self, pages: torch.Tensor, quads: torch.Tensor, page_idx: Optional[torch.Tensor] = None, dst_h: int = 32,
@@ -333,8 +340,8 @@ class Engine:
         out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=pages.device)
         if n == 0:
             return out
-        rects_d = torch.from_numpy(rects).to(pages.device)
-        m_d = torch.from_numpy(m).to(pages.device)
+        rects_d = _params_to(rects, pages.device)
+        m_d = _params_to(m, pages.device)
         check(self._lib.dv_crop_tables_for_tsr(self._h, _ptr(pages), pages.shape[0], pages.shape[1], pages.shape[2], _ptr(rects_d), _ptr(m_d), n,
                                                out_w, out_h, _ptr(out)), self._h, "dv_crop_tables_for_tsr")
         return out

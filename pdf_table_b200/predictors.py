@@ -859,8 +859,9 @@ class OcrRecognitionTask(BaseInferTask):
             first = self.character[0] if len(self.character[0]) == 1 else self._blank_mark
             tab = self._char_tab = np.array([first] + list(self.character[1:]), dtype="<U1") if single else False
         t = ids.shape[1] if ids.ndim == 2 else 0
-        if tab is not False and t > 0 and ids.size and int(ids.min()) >= 0 and int(ids.max()) < len(tab):
-            rows = np.ascontiguousarray(tab[ids]).view(f"<U{t}").reshape(-1)
+        if tab is not False and t > 0 and ids.size and int(ids.min()) >= -1 and int(ids.max()) < len(tab):
+            # -1 pads the rows beyond their length (pp_rec_launch_groups): looked up as the blank stand-in, cut off below
+            rows = np.ascontiguousarray(tab[np.maximum(ids, 0)]).view(f"<U{t}").reshape(-1)
             mark = self._blank_mark if len(self.character[0]) != 1 else None
             # a row made of NUL-free characters keeps its full width; lengths cut the padding off
             return [str(r)[:k] if len(r) >= k and (mark is None or mark not in str(r)[:k]) else "".join(self.character[int(v)] for v in row[:k])
