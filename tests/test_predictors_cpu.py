@@ -125,3 +125,49 @@ def test_dbnet_backend_preprocess_matches_reference():
     mean = np.array(predictors.OcrDetectionTask.DB_MEAN, np.float32)
     x = (res[:, :, ::-1].astype(np.float32) * np.float32(1.0) - mean) / np.float32(255.0)
     np.testing.assert_array_equal(x.transpose(2, 0, 1), g["page_chw"])
+
+
+def test_ids_to_texts_table_lookup_equals_the_per_token_join():
+    """OcrRecognitionTask._ids_to_texts: the one-look-up path (single-character dictionary, 'blank' word at id 0, rows padded with
+    -1 beyond their length) returns exactly what CTCLabelDecode's per-token join returns -- also for a row that shows id 0 inside
+    its length (never produced by the collapse, but the mapping must not depend on that) and for a multi-character dictionary."""
+    class _T:
+        pass
+
+    f = predictors.OcrRecognitionTask._ids_to_texts
+    rng = np.random.default_rng(0)
+    for chars in ([chr(0x4E00 + i) for i in range(60)], ["ab", "c"] + [chr(0x4E00 + i) for i in range(58)]):
+        t = _T()
+        t.character = ["blank"] + chars + [" "]
+        ids = rng.integers(1, len(t.character), (200, 25)).astype(np.int32)
+        lens = rng.integers(0, 26, 200).astype(np.int32)
+        for i in range(200):
+            ids[i, lens[i]:] = -1
+        ids[7, 0] = 0
+        lens[7] = max(int(lens[7]), 3)
+        ids[7, :3] = [0, 5, 0]
+        want = ["".join(t.character[int(v)] for v in row[:k]) for row, k in zip(ids, lens)]
+        assert f(t, ids, lens) == want
+    t = _T()
+    t.character = None
+    assert f(t, np.array([[3, 4, -1]], np.int32), np.array([2], np.int32)) == ["3 4"]
+
+
+def test_packed_narrow_pointwise_weights():
+    """pp_rec_graph.pw_pack_factor / block_diagonal: a 16- (32-) channel 1x1 layer is packed 4 (2) pixels per GEMM row; the packed
+    product over a [M / p, p * K] view equals the layer applied per pixel."""
+    from pdf_table_b200 import pp_rec_graph as G
+
+    class _B:
+        precise = False
+
+    assert G.pw_pack_factor(_B(), 16, 32) == 4 and G.pw_pack_factor(_B(), 32, 64) == 2 and G.pw_pack_factor(_B(), 64, 64) == 1
+    assert G.pw_pack_factor(_B(), 16, 128) == 1  # 4 x 128 output columns would not fit one n-tile
+    pb = _B()
+    pb.precise = True
+    assert G.pw_pack_factor(pb, 16, 32) == 1
+    rng = np.random.default_rng(1)
+    w, b = rng.standard_normal((32, 16)).astype(np.float32), rng.standard_normal(32).astype(np.float32)
+    wd, bd = G.block_diagonal(w, b, 4)
+    x = rng.standard_normal((40, 16)).astype(np.float32)
+    np.testing.assert_allclose((x.reshape(10, 64) @ wd.T + bd).reshape(40, 32), x @ w.T + b, rtol=1e-5, atol=1e-5)
