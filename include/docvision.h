@@ -206,7 +206,9 @@ int dv_lore_detect_forward_u8(dv_handle h, const uint8_t* images_hwc_u8, int n, 
  * on this handle: the `ax` head (3x3 conv + ReLU + 1x1) at each cell centre plus the `cr` head at its four cc_match
  * corners.  Same values as gathering the reference's dense maps (dv_lore_gather_logi), at 5 x cells rows instead of
  * height/4 x width/4 pixels.  Replaces the `ax` / `cr` heads of DLASeg.forward together with
- * _tranpose_and_gather_feat / _get_4ps_feat (lore/lineless_table_process.py:31-63).
+ * _tranpose_and_gather_feat / _get_4ps_feat (lore/lineless_table_process.py:31-63).  On a "lore_resnet18" handle the two heads'
+ * four 3x3 convs were evaluated densely by dv_lore_detect_forward (their 64-channel hidden maps are resident) and this call runs
+ * the last 1x1 conv (64 -> 256) on the gathered pixels only.
  *   counts [n], ax_idx [n][K], cr_idx [n][K][4] : outputs of dv_lore_decode (device)
  *   max_rows     : capacity of the packed row list (sum of counts over the batch must fit)
  *   logi_feat    : [max_rows][256] fp32 (device); image i's cells occupy rows offsets[i] .. offsets[i+1]
